@@ -1,0 +1,286 @@
+/*
+ * ref_shim.cpp -- C handle onto the REFERENCE's own C primitives (test infrastructure).
+ *
+ * Compiled ONLY where /root/reference exists (this container), together with the
+ * reference's pixel.cpp / dct.cpp / lowpassdct.cpp / ipfilter.cpp / intrapred.cpp /
+ * loopfilter.cpp / constants.cpp / primitives.cpp, straight from where they lie
+ * (oracle/Makefile, target `ref`), into oracle/_ref/libx265ref_<depth>.so.
+ * Nothing from the reference is copied into this repository; this file only
+ * includes the reference's headers at build time and calls through the table that
+ * setupCPrimitives() + setupAliasPrimitives() fill (primitives.h:471-474), exactly
+ * as source/test/testbench.cpp:224-227 does.
+ *
+ * Uses: (1) pin oracle/x265_oracle.c (tests/test_oracle_vs_ref.py),
+ *       (2) generate tests/golden/*.npz (tests/golden/make_golden.py),
+ *       (3) CPU baseline "kind": "reference" in bench.py.
+ * The product never loads this library.
+ */
+#include "common.h"
+#include "primitives.h"
+#include "constants.h"
+#include "contexts.h"
+#include "temporalfilter.h"
+
+#include <thread>
+#include <vector>
+#include <cstring>
+
+/* ---- link stubs for subsystems that are off the hot path and not compiled in ----
+ * (encoder/sao.cpp, encoder/framefilter.cpp, encoder/entropy.cpp, common/cpu.cpp,
+ * common/common.cpp, common/temporalfilter.cpp pull in the whole encoder).  None of
+ * these is reachable from a hot-path slot. */
+namespace X265_NS {
+void setupSaoPrimitives_c(EncoderPrimitives&) {}
+void setupSeaIntegralPrimitives_c(EncoderPrimitives&) {}
+void setupMCSTFPrimitives_scalar(MCSTFPrimitives&) {}
+MCSTFPrimitives mcstfPrim;
+const uint32_t g_entropyBits[128] = { 0 };
+const uint8_t g_nextState[128][2] = { { 0 } };
+const cpu_name_t cpu_names[] = { { "", 0 } };
+uint32_t cpu_detect(bool) { return 0; }
+void general_log(const x265_param*, const char*, int, const char*, ...) {}
+void* x265_malloc(size_t size) { void* p = NULL; return posix_memalign(&p, 64, size) ? NULL : p; }
+void x265_free(void* p) { free(p); }
+}
+extern "C" const uint32_t PFX(entropyStateBits)[128] = { 0 };
+
+using namespace X265_NS;
+
+namespace X265_NS { extern const uint8_t lumaPartitionMapTable[]; }
+
+namespace {
+template<typename F>
+void parfor(int n, int nthreads, F f)
+{
+    if (nthreads <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    int chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++)
+    {
+        int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) break;
+        th.emplace_back([=] { f(lo, hi); });
+    }
+    for (auto& t : th) t.join();
+}
+
+EncoderPrimitives g_c;     // plain C table + aliases
+EncoderPrimitives g_lp;    // copy with enableLowpassDCTPrimitives applied (standard_dct bound)
+bool g_ready = false;
+
+void ensure()
+{
+    if (g_ready) return;
+    memset(&g_c, 0, sizeof(g_c));
+    setupCPrimitives(g_c);
+    setupAliasPrimitives(g_c);
+    /* HBD alias trampolines dispatch through the global table (primitives.cpp:98-168) */
+    memcpy(&primitives, &g_c, sizeof(g_c));
+    g_ready = true;
+}
+
+int lumaPart(int w, int h)
+{
+    if ((w & 3) || (h & 3) || w < 4 || h < 4 || w > 64 || h > 64) return -1;
+    int p = lumaPartitionMapTable[(((w >> 2) - 1) << 4) + ((h >> 2) - 1)];
+    return p == 255 ? -1 : p;
+}
+
+/* find a (csp, lumaPart) whose chroma PU is w x h: 4:4:4 (w,h), 4:2:0 (2w,2h), 4:2:2 (2w,h) */
+bool chromaSlot(int w, int h, int& csp, int& part, bool needSatd)
+{
+    int p;
+    if ((p = lumaPart(w, h)) >= 0) { csp = X265_CSP_I444; part = p; return true; }
+    if ((p = lumaPart(2 * w, 2 * h)) >= 0 && (!needSatd || g_c.chroma[X265_CSP_I420].pu[p].satd))
+    { csp = X265_CSP_I420; part = p; return true; }
+    if ((p = lumaPart(2 * w, h)) >= 0 && (!needSatd || g_c.chroma[X265_CSP_I422].pu[p].satd))
+    { csp = X265_CSP_I422; part = p; return true; }
+    return false;
+}
+}
+
+extern "C" {
+
+int ref_depth() { return X265_DEPTH; }
+int ref_table_bytes() { return (int)sizeof(EncoderPrimitives); }
+
+void ref_get_dct_matrix(int N, int16_t* out)
+{
+    const int16_t* t = N == 4 ? &g_t4[0][0] : N == 8 ? &g_t8[0][0] : N == 16 ? &g_t16[0][0] : &g_t32[0][0];
+    memcpy(out, t, (size_t)N * N * sizeof(int16_t));
+}
+void ref_get_luma_taps(int16_t* out) { memcpy(out, g_lumaFilter, sizeof(int16_t) * 4 * 8); }
+void ref_get_chroma_taps(int16_t* out) { memcpy(out, g_chromaFilter, sizeof(int16_t) * 8 * 4); }
+
+/* ---- pixel metrics ---- */
+int ref_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{ ensure(); int p = lumaPart(w, h); return p < 0 ? -1 : g_c.pu[p].sad(a, sa, b, sb); }
+
+void ref_sad_x3(int w, int h, const pixel* f, const pixel* r0, const pixel* r1, const pixel* r2, intptr_t rs, int32_t* res)
+{ ensure(); g_c.pu[lumaPart(w, h)].sad_x3(f, r0, r1, r2, rs, res); }
+
+void ref_sad_x4(int w, int h, const pixel* f, const pixel* r0, const pixel* r1, const pixel* r2, const pixel* r3, intptr_t rs, int32_t* res)
+{ ensure(); g_c.pu[lumaPart(w, h)].sad_x4(f, r0, r1, r2, r3, rs, res); }
+
+int ref_ads(int w, int h, int* encDC, uint32_t* sums, int delta, uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{ ensure(); return g_c.pu[lumaPart(w, h)].ads(encDC, sums, delta, costMvX, mvs, width, thresh); }
+
+int ref_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    ensure();
+    int p = lumaPart(w, h);
+    if (p >= 0) return g_c.pu[p].satd(a, sa, b, sb);
+    int csp, part;
+    if (!chromaSlot(w, h, csp, part, true)) return -1;
+    return g_c.chroma[csp].pu[part].satd(a, sa, b, sb);
+}
+
+/* sa8d slots: luma cu[] (square w == h), 4:2:0 chroma cu (w == h, cu = 2w), 4:2:2 chroma cu (h == 2w).
+ * `chroma` = 0 luma table, 1 = 4:2:0 table, 2 = 4:2:2 table. */
+int ref_sa8d(int chroma, int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    ensure();
+    if (chroma == 0) return g_c.cu[w == 4 ? 0 : w == 8 ? 1 : w == 16 ? 2 : w == 32 ? 3 : 4].sa8d(a, sa, b, sb);
+    int cuw = 2 * w;
+    int idx = cuw == 8 ? 1 : cuw == 16 ? 2 : cuw == 32 ? 3 : 4;
+    return g_c.chroma[chroma == 1 ? X265_CSP_I420 : X265_CSP_I422].cu[idx].sa8d(a, sa, b, sb);
+}
+
+uint64_t ref_sse_pp(int chroma, int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    ensure();
+    (void)h;
+    if (chroma == 0) return g_c.cu[w == 4 ? 0 : w == 8 ? 1 : w == 16 ? 2 : w == 32 ? 3 : 4].sse_pp(a, sa, b, sb);
+    int cuw = 2 * w;
+    int idx = cuw == 4 ? 0 : cuw == 8 ? 1 : cuw == 16 ? 2 : cuw == 32 ? 3 : 4;
+    return g_c.chroma[chroma == 1 ? X265_CSP_I420 : X265_CSP_I422].cu[idx].sse_pp(a, sa, b, sb);
+}
+uint64_t ref_sse_ss(int w, const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb)
+{ ensure(); return g_c.cu[w == 4 ? 0 : w == 8 ? 1 : w == 16 ? 2 : w == 32 ? 3 : 4].sse_ss(a, sa, b, sb); }
+uint64_t ref_ssd_s(int w, const int16_t* a, intptr_t sa)
+{ ensure(); return g_c.cu[w == 4 ? 0 : w == 8 ? 1 : w == 16 ? 2 : w == 32 ? 3 : 4].ssd_s[NONALIGNED](a, sa); }
+
+/* ---- transforms ---- */
+static int trIdx(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : 3; }
+void ref_dct(int n, const int16_t* src, int16_t* dst, intptr_t stride) { ensure(); g_c.cu[trIdx(n)].dct(src, dst, stride); }
+void ref_idct(int n, const int16_t* src, int16_t* dst, intptr_t stride) { ensure(); g_c.cu[trIdx(n)].idct(src, dst, stride); }
+void ref_dst4(const int16_t* src, int16_t* dst, intptr_t stride) { ensure(); g_c.dst4x4(src, dst, stride); }
+void ref_idst4(const int16_t* src, int16_t* dst, intptr_t stride) { ensure(); g_c.idst4x4(src, dst, stride); }
+void ref_lowpass_dct(int n, const int16_t* src, int16_t* dst, intptr_t stride)
+{
+    ensure();
+    /* lowpassdct.cpp keeps file-static pointers to the standard_dct slots of the table
+     * setupLowPassPrimitives_c last saw (g_c); fill them the way
+     * enableLowpassDCTPrimitives does (primitives.cpp:77-88), on g_c itself. */
+    for (int i = 0; i < 4; i++)
+        if (!g_c.cu[i].standard_dct) g_c.cu[i].standard_dct = g_c.cu[i].dct;
+    g_c.cu[trIdx(n)].lowpass_dct(src, dst, stride);
+}
+uint32_t ref_quant(const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int n)
+{ ensure(); return g_c.quant(coef, qc, deltaU, qCoef, qBits, add, n); }
+uint32_t ref_nquant(const int16_t* coef, const int32_t* qc, int16_t* qCoef, int qBits, int add, int n)
+{ ensure(); return g_c.nquant(coef, qc, qCoef, qBits, add, n); }
+void ref_dequant_normal(const int16_t* q, int16_t* coef, int num, int scale, int shift)
+{ ensure(); g_c.dequant_normal(q, coef, num, scale, shift); }
+void ref_dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* coef, int num, int per, int shift)
+{ ensure(); g_c.dequant_scaling(q, dq, coef, num, per, shift); }
+
+/* ---- interpolation: N = 8 luma pu[] slots, N = 4 chroma[csp].pu[] slots ---- */
+#define PICK(lumaSlot, chromaSlotName)                                                        \
+    ensure();                                                                                 \
+    int part = lumaPart(w, h), csp = 0;                                                       \
+    if (N == 8) { if (part < 0) return -1; }                                                  \
+    else if (!chromaSlot(w, h, csp, part, false)) return -1;
+
+int ref_interp_hpp(int N, int w, int h, const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idx)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_hpp : g_c.chroma[csp].pu[part].filter_hpp)(s, ss, d, ds, idx); return 0; }
+int ref_interp_vpp(int N, int w, int h, const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idx)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_vpp : g_c.chroma[csp].pu[part].filter_vpp)(s, ss, d, ds, idx); return 0; }
+int ref_interp_hps(int N, int w, int h, const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int idx, int ext)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_hps : g_c.chroma[csp].pu[part].filter_hps)(s, ss, d, ds, idx, ext); return 0; }
+int ref_interp_vps(int N, int w, int h, const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int idx)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_vps : g_c.chroma[csp].pu[part].filter_vps)(s, ss, d, ds, idx); return 0; }
+int ref_interp_vsp(int N, int w, int h, const int16_t* s, intptr_t ss, pixel* d, intptr_t ds, int idx)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_vsp : g_c.chroma[csp].pu[part].filter_vsp)(s, ss, d, ds, idx); return 0; }
+int ref_interp_vss(int N, int w, int h, const int16_t* s, intptr_t ss, int16_t* d, intptr_t ds, int idx)
+{ PICK(0, 0); (N == 8 ? g_c.pu[part].luma_vss : g_c.chroma[csp].pu[part].filter_vss)(s, ss, d, ds, idx); return 0; }
+int ref_interp_hvpp(int N, int w, int h, const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int ix, int iy)
+{
+    ensure();
+    int part = lumaPart(w, h);
+    if (N != 8 || part < 0) return -1;       /* only the luma table has an hv slot */
+    g_c.pu[part].luma_hvpp(s, ss, d, ds, ix, iy);
+    return 0;
+}
+int ref_p2s(int w, int h, const pixel* s, intptr_t ss, int16_t* d, intptr_t ds)
+{
+    ensure();
+    int part = lumaPart(w, h), csp = 0;
+    if (part >= 0) { g_c.pu[part].convert_p2s[NONALIGNED](s, ss, d, ds); return 0; }
+    if (!chromaSlot(w, h, csp, part, false)) return -1;
+    g_c.chroma[csp].pu[part].p2s[NONALIGNED](s, ss, d, ds);
+    return 0;
+}
+
+/* ---- slot census for the coverage contract (SURVEY.md section 8a checklist) ---- */
+int ref_count_nonnull_slots()
+{
+    ensure();
+    const void* const* slots = (const void* const*)&g_c;
+    int n = 0;
+    for (size_t i = 0; i < sizeof(g_c) / sizeof(void*); i++) n += slots[i] != NULL;
+    return n;
+}
+
+/* ---- batched, multi-threaded drivers over descriptor arrays (CPU baseline) ---- */
+enum { OP_SAD = 0, OP_SATD = 1, OP_SA8D = 2, OP_SSE_PP = 3 };
+
+int ref_pixelcmp_batch(int op, int w, int h, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb,
+                       const int32_t* offA, const int32_t* offB, int n, void* out, int nthreads)
+{
+    ensure();
+    int part = lumaPart(w, h);
+    if (part < 0) return -1;
+    int cu = w == 4 ? 0 : w == 8 ? 1 : w == 16 ? 2 : w == 32 ? 3 : 4;
+    pixelcmp_t f = op == OP_SAD ? g_c.pu[part].sad : op == OP_SATD ? g_c.pu[part].satd : g_c.cu[cu].sa8d;
+    pixel_sse_t fs = g_c.cu[cu].sse_pp;
+    if ((op == OP_SA8D || op == OP_SSE_PP) && w != h) return -1;
+    parfor(n, nthreads, [=](int lo, int hi) {
+        for (int i = lo; i < hi; i++)
+        {
+            if (op == OP_SSE_PP) ((uint64_t*)out)[i] = fs(A + offA[i], sa, B + offB[i], sb);
+            else ((int32_t*)out)[i] = f(A + offA[i], sa, B + offB[i], sb);
+        }
+    });
+    return 0;
+}
+
+/* residual via the reference's own sub_ps slot (pixel.cpp), then dct slot, per block */
+int ref_residual_dct_batch(int N, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb,
+                           const int32_t* offA, const int32_t* offB, int n, int16_t* out, int nthreads)
+{
+    ensure();
+    int cu = trIdx(N);
+    parfor(n, nthreads, [=](int lo, int hi) {
+        ALIGN_VAR_32(int16_t, resi[32 * 32]);
+        for (int i = lo; i < hi; i++)
+        {
+            g_c.cu[cu].sub_ps(resi, N, A + offA[i], B + offB[i], sa, sb);
+            g_c.cu[cu].dct(resi, out + (size_t)i * N * N, N);
+        }
+    });
+    return 0;
+}
+
+int ref_dct_batch(int N, const int16_t* src, intptr_t srcStride, const int32_t* off, int n, int16_t* out, int nthreads)
+{
+    ensure();
+    int cu = trIdx(N);
+    parfor(n, nthreads, [=](int lo, int hi) {
+        for (int i = lo; i < hi; i++)
+            g_c.cu[cu].dct(src + off[i], out + (size_t)i * N * N, srcStride);
+    });
+    return 0;
+}
+
+} // extern "C"

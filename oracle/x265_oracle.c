@@ -1,0 +1,646 @@
+/*
+ * x265_oracle.c -- CPU restatement of the x265 analysis-primitive hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * leg may load it.  The product (x265-mod-by-patman_b200/) never links or calls it.
+ *
+ * Parity status: PINNED.  Every function below is checked bit-for-bit against
+ *   (1) the reference's own C primitives compiled from /root/reference into
+ *       oracle/_ref/libx265ref_<depth>.so (tests/test_oracle_vs_ref.py, runs wherever
+ *       oracle/_ref exists), and
+ *   (2) golden vectors generated from that library and committed under
+ *       tests/golden/ (tests/test_oracle_golden.py, runs everywhere).
+ * The reference ships no golden vectors of its own.
+ *
+ * Written from the algorithm descriptions, in a deliberately different code shape
+ * from the reference (plain int32 Hadamard instead of SWAR lane packing, full-matrix
+ * two-stage transforms instead of partial butterflies, generated coefficient
+ * tables).  Each function cites the reference file:line whose behaviour it restates
+ * (paths relative to /root/reference/source/common).
+ *
+ * Build: one shared object per bit depth, -DX265_DEPTH={8,10,12}  (oracle/Makefile).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef X265_DEPTH
+#error "compile with -DX265_DEPTH=8|10|12"
+#endif
+
+#if X265_DEPTH == 8
+typedef uint8_t pixel;          /* common.h:127-143 */
+typedef uint32_t sse_t;         /* common.h:145-149 */
+#else
+typedef uint16_t pixel;
+typedef uint64_t sse_t;
+#endif
+
+#define PIXEL_MAX ((1 << X265_DEPTH) - 1)
+#define FENC_STRIDE 64          /* common.h:71 */
+#define IF_INTERNAL_PREC 14     /* constants.h:66-70 */
+#define IF_FILTER_PREC 6
+#define IF_INTERNAL_OFFS (1 << (IF_INTERNAL_PREC - 1))
+
+#define EXPORT __attribute__((visibility("default")))
+
+static inline int iabs(int v) { return v < 0 ? -v : v; }
+static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+/* two's-complement wrapping helpers: the reference relies on what gcc does for int
+ * overflow / shifts of negatives; state it explicitly here. */
+static inline int32_t wrap_mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static inline int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static inline int32_t wrap_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+static inline int32_t wrap_shl(int32_t a, int s) { return (int32_t)((uint32_t)a << s); }
+
+EXPORT int orc_depth(void) { return X265_DEPTH; }
+EXPORT int orc_pixel_bytes(void) { return (int)sizeof(pixel); }
+EXPORT int orc_sse_bytes(void) { return (int)sizeof(sse_t); }
+
+/* ------------------------------------------------------------------ constants */
+
+/* HEVC core transform: T32[k][n] = C[(k*(2n+1)) mod 128] where C is the integer
+ * "cosine" with the 32 unique magnitudes below and the symmetries of cos(m*pi/64).
+ * TN[k][n] = T32[k*(32/N)][n].  Equals g_t4/g_t8/g_t16/g_t32, constants.cpp:270-344
+ * (checked element-wise against the reference in tests/test_oracle_vs_ref.py). */
+static const int16_t k_cosmag[32] = {
+    64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
+    64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4 };
+
+static int16_t g_T32[32][32];
+static int g_tables_ready;
+
+static int cos128(int m)
+{
+    m &= 127;
+    if (m > 64) m = 128 - m;        /* cos(2pi - x) = cos x */
+    if (m == 32) return 0;
+    if (m > 32) return -(int)k_cosmag[64 - m]; /* cos(pi - x) = -cos x; m == 64 -> -64 */
+    return k_cosmag[m];
+}
+
+static void init_tables(void)
+{
+    if (g_tables_ready) return;
+    for (int k = 0; k < 32; k++)
+        for (int n = 0; n < 32; n++)
+            g_T32[k][n] = (int16_t)cos128(k * (2 * n + 1));
+    g_tables_ready = 1;
+}
+
+static inline int tcoef(int N, int k, int n) { return g_T32[k * (32 / N)][n]; }
+
+/* 4x4 DST-VII matrix; equivalent to fastForwardDst / inversedst, dct.cpp:43-81 */
+static const int16_t k_dst4[4][4] = {
+    { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+
+/* constants.cpp:250-268 (HEVC spec tables 8-11 / 8-12) */
+static const int16_t k_luma_taps[4][8] = {
+    { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 },
+    { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+static const int16_t k_chroma_taps[8][4] = {
+    { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+    { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+EXPORT void orc_get_dct_matrix(int N, int16_t* out /* N*N */)
+{
+    init_tables();
+    for (int k = 0; k < N; k++)
+        for (int n = 0; n < N; n++)
+            out[k * N + n] = (int16_t)tcoef(N, k, n);
+}
+EXPORT void orc_get_dst_matrix(int16_t* out) { memcpy(out, k_dst4, sizeof(k_dst4)); }
+EXPORT void orc_get_luma_taps(int16_t* out) { memcpy(out, k_luma_taps, sizeof(k_luma_taps)); }
+EXPORT void orc_get_chroma_taps(int16_t* out) { memcpy(out, k_chroma_taps, sizeof(k_chroma_taps)); }
+
+/* ------------------------------------------------------------------ pixel metrics */
+
+/* pixel.cpp:40-55  sad<lx,ly> */
+EXPORT int orc_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int sum = 0;
+    for (int y = 0; y < h; y++, a += sa, b += sb)
+        for (int x = 0; x < w; x++)
+            sum += iabs((int)a[x] - (int)b[x]);
+    return sum;
+}
+
+/* pixel.cpp:74-119  sad_x3 / sad_x4: fenc stride is the constant FENC_STRIDE */
+EXPORT void orc_sad_xn(int w, int h, int n, const pixel* fenc, const pixel* const* refs,
+                       intptr_t frefstride, int32_t* res)
+{
+    for (int i = 0; i < n; i++)
+        res[i] = orc_sad(w, h, fenc, FENC_STRIDE, refs[i], frefstride);
+}
+EXPORT void orc_sad_x3(int w, int h, const pixel* fenc, const pixel* r0, const pixel* r1,
+                       const pixel* r2, intptr_t frefstride, int32_t* res)
+{
+    const pixel* r[3] = { r0, r1, r2 };
+    orc_sad_xn(w, h, 3, fenc, r, frefstride, res);
+}
+EXPORT void orc_sad_x4(int w, int h, const pixel* fenc, const pixel* r0, const pixel* r1,
+                       const pixel* r2, const pixel* r3, intptr_t frefstride, int32_t* res)
+{
+    const pixel* r[4] = { r0, r1, r2, r3 };
+    orc_sad_xn(w, h, 4, fenc, r, frefstride, res);
+}
+
+/* pixel.cpp:121-165 ads_x4/x2/x1 and the per-shape choice, pixel.cpp:1122-1146.
+ * Returns which form (4, 2 or 1 DC terms) the reference binds to a w x h PU. */
+EXPORT int orc_ads_terms(int w, int h)
+{
+    static const struct { int w, h, k; } tab[] = {
+        {4,4,1},{8,8,1},{8,4,2},{4,8,2},{16,16,4},{16,8,2},{8,16,2},{16,12,1},{12,16,1},
+        {16,4,1},{4,16,1},{32,32,4},{32,16,2},{16,32,2},{32,24,4},{24,32,4},{32,8,4},{8,32,4},
+        {64,64,4},{64,32,2},{32,64,2},{64,48,4},{48,64,4},{64,16,4},{16,64,4} };
+    for (unsigned i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
+        if (tab[i].w == w && tab[i].h == h) return tab[i].k;
+    return 0;
+}
+
+EXPORT int orc_ads(int w, int h, const int* encDC, const uint32_t* sums, int delta,
+                   const uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    int k = orc_ads_terms(w, h);
+    int nmv = 0;
+    int half = w >> 1;
+    /* the reference loop index is an int16_t (pixel.cpp:125); width <= 32767 in any caller */
+    for (int i = 0; i < width; i++)
+    {
+        const uint32_t* s = sums + i;
+        long ads;
+        if (k == 4)
+            ads = labs((long)encDC[0] - (long)s[0]) + labs((long)encDC[1] - (long)s[half])
+                + labs((long)encDC[2] - (long)s[delta]) + labs((long)encDC[3] - (long)s[delta + half]);
+        else if (k == 2)
+            ads = labs((long)encDC[0] - (long)s[0]) + labs((long)encDC[1] - (long)s[delta]);
+        else
+            ads = labs((long)encDC[0] - (long)s[0]);
+        /* reference: int ads = <long sum> + costMvX[i]; -> truncation to int */
+        int adsi = (int)(ads + costMvX[i]);
+        if (adsi < thresh)
+            mvs[nmv++] = (int16_t)i;
+    }
+    return nmv;
+}
+
+/* pixel.cpp:167-186  sse<lx,ly,T1,T2>: squares in int, accumulates in sse_t */
+EXPORT sse_t orc_sse_pp(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    sse_t sum = 0;
+    for (int y = 0; y < h; y++, a += sa, b += sb)
+        for (int x = 0; x < w; x++)
+        {
+            int t = (int)a[x] - (int)b[x];
+            sum += (sse_t)(t * t);
+        }
+    return sum;
+}
+EXPORT sse_t orc_sse_ss(int w, int h, const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb)
+{
+    sse_t sum = 0;
+    for (int y = 0; y < h; y++, a += sa, b += sb)
+        for (int x = 0; x < w; x++)
+        {
+            int t = (int)a[x] - (int)b[x];
+            /* (tmp * tmp) is an int product in the reference: wraps beyond |t| > 46340,
+             * then converts (sign-extending) to sse_t */
+            sum += (sse_t)wrap_mul(t, t);
+        }
+    return sum;
+}
+/* pixel.cpp:371-383 pixel_ssd_s_c<size> */
+EXPORT sse_t orc_ssd_s(int size, const int16_t* a, intptr_t stride)
+{
+    sse_t sum = 0;
+    for (int y = 0; y < size; y++, a += stride)
+        for (int x = 0; x < size; x++)
+            sum += (sse_t)((int)a[x] * (int)a[x]);
+    return sum;
+}
+
+/* 4x4 Hadamard SATD tile, raw (un-halved) sum.  pixel.cpp:210-261: satd_4x4 returns
+ * raw>>1 and satd_8x4 returns (raw_left + raw_right)>>1; every raw tile sum is even,
+ * so a per-tile >>1 is identical. */
+static int hadamard4x4_abs(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int d[4][4], t[4][4];
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++)
+            d[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    for (int y = 0; y < 4; y++)
+    {
+        int s0 = d[y][0] + d[y][1], s1 = d[y][0] - d[y][1];
+        int s2 = d[y][2] + d[y][3], s3 = d[y][2] - d[y][3];
+        t[y][0] = s0 + s2; t[y][1] = s1 + s3; t[y][2] = s0 - s2; t[y][3] = s1 - s3;
+    }
+    int sum = 0;
+    for (int x = 0; x < 4; x++)
+    {
+        int s0 = t[0][x] + t[1][x], s1 = t[0][x] - t[1][x];
+        int s2 = t[2][x] + t[3][x], s3 = t[2][x] - t[3][x];
+        sum += iabs(s0 + s2) + iabs(s1 + s3) + iabs(s0 - s2) + iabs(s1 - s3);
+    }
+    return sum;
+}
+
+/* pixel.cpp:263-289 satd4<w,h> / satd8<w,h>; slot binding pixel.cpp:1148-1172 */
+EXPORT int orc_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int satd = 0;
+    for (int y = 0; y < h; y += 4)
+        for (int x = 0; x < w; x += 4)
+            satd += hadamard4x4_abs(a + y * sa + x, sa, b + y * sb + x, sb) >> 1;
+    return satd;
+}
+
+/* pixel.cpp:291-334 _sa8d_8x8: raw sum of |H8 * D * H8^T| */
+static int hadamard8x8_abs(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int m[8][8];
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            m[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    /* rows then columns, radix-2 */
+    for (int y = 0; y < 8; y++)
+        for (int step = 1; step < 8; step <<= 1)
+            for (int i = 0; i < 8; i += step << 1)
+                for (int j = i; j < i + step; j++)
+                {
+                    int u = m[y][j], v = m[y][j + step];
+                    m[y][j] = u + v; m[y][j + step] = u - v;
+                }
+    for (int x = 0; x < 8; x++)
+        for (int step = 1; step < 8; step <<= 1)
+            for (int i = 0; i < 8; i += step << 1)
+                for (int j = i; j < i + step; j++)
+                {
+                    int u = m[j][x], v = m[j + step][x];
+                    m[j][x] = u + v; m[j + step][x] = u - v;
+                }
+    int sum = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            sum += iabs(m[y][x]);
+    return sum;
+}
+
+/* pixel.cpp:336-369: sa8d8<w,h> = sum of (raw8x8+2)>>2; sa8d16<w,h> = sum over 16x16 of
+ * (four raw 8x8 + 2)>>2.  Slot binding: pixel.cpp:1180-1184,1260-1263,1339-1342:
+ * both dims multiple of 16 -> sa8d16 form; both multiple of 8 -> sa8d8 form; else satd. */
+EXPORT int orc_sa8d(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int cost = 0;
+    if (w % 16 == 0 && h % 16 == 0)
+    {
+        for (int y = 0; y < h; y += 16)
+            for (int x = 0; x < w; x += 16)
+            {
+                int raw = 0;
+                for (int q = 0; q < 4; q++)
+                {
+                    int ox = x + (q & 1) * 8, oy = y + (q >> 1) * 8;
+                    raw += hadamard8x8_abs(a + oy * sa + ox, sa, b + oy * sb + ox, sb);
+                }
+                cost += (raw + 2) >> 2;
+            }
+    }
+    else if (w % 8 == 0 && h % 8 == 0)
+    {
+        for (int y = 0; y < h; y += 8)
+            for (int x = 0; x < w; x += 8)
+                cost += (hadamard8x8_abs(a + y * sa + x, sa, b + y * sb + x, sb) + 2) >> 2;
+    }
+    else
+        cost = orc_satd(w, h, a, sa, b, sb);
+    return cost;
+}
+
+/* ------------------------------------------------------------------ transforms */
+
+/* Forward stage in matrix form (restates partialButterflyN,
+ * dct.cpp:83-240,418-440): dst[k*n + j] = (int16)((sum_i M[k][i]*src[j*n + i] + add) >> shift) */
+static void fwd_stage(int n, int dst4, const int16_t* src, int16_t* dst, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int j = 0; j < n; j++)
+        for (int k = 0; k < n; k++)
+        {
+            int acc = 0;
+            for (int i = 0; i < n; i++)
+                acc += (dst4 ? k_dst4[k][i] : tcoef(n, k, i)) * (int)src[j * n + i];
+            dst[k * n + j] = (int16_t)((acc + add) >> shift);  /* truncation, dct.cpp:113 */
+        }
+}
+
+/* Inverse stage (restates partialButterflyInverseN, dct.cpp:242-416):
+ * dst[j*n + i] = clip16((sum_k M[k][i]*src[k*n + j] + add) >> shift) */
+static void inv_stage(int n, int dst4, const int16_t* src, int16_t* dst, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++)
+        {
+            int acc = 0;
+            for (int k = 0; k < n; k++)
+                acc += (dst4 ? k_dst4[k][i] : tcoef(n, k, i)) * (int)src[k * n + j];
+            dst[j * n + i] = (int16_t)clip3(-32768, 32767, (acc + add) >> shift); /* dct.cpp:257 */
+        }
+}
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+/* dct.cpp:443-526 dst4_c / dct4_c .. dct32_c */
+static void fwd_transform(int n, int dst4, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    int16_t block[32 * 32], coef[32 * 32];
+    init_tables();
+    int l2 = ilog2(n);
+    for (int y = 0; y < n; y++)
+        memcpy(block + y * n, src + y * srcStride, (size_t)n * sizeof(int16_t));
+    fwd_stage(n, dst4, block, coef, l2 - 1 + (X265_DEPTH - 8));
+    fwd_stage(n, dst4, coef, dst, l2 + 6);
+}
+/* dct.cpp:528-611 idst4_c / idct4_c .. idct32_c */
+static void inv_transform(int n, int dst4, const int16_t* src, int16_t* dst, intptr_t dstStride)
+{
+    int16_t block[32 * 32], coef[32 * 32];
+    init_tables();
+    inv_stage(n, dst4, src, coef, 7);
+    inv_stage(n, dst4, coef, block, 12 - (X265_DEPTH - 8));
+    for (int y = 0; y < n; y++)
+        memcpy(dst + y * dstStride, block + y * n, (size_t)n * sizeof(int16_t));
+}
+
+EXPORT void orc_dct(int n, const int16_t* src, int16_t* dst, intptr_t srcStride) { fwd_transform(n, 0, src, dst, srcStride); }
+EXPORT void orc_idct(int n, const int16_t* src, int16_t* dst, intptr_t dstStride) { inv_transform(n, 0, src, dst, dstStride); }
+EXPORT void orc_dst4(const int16_t* src, int16_t* dst, intptr_t srcStride) { fwd_transform(4, 1, src, dst, srcStride); }
+EXPORT void orc_idst4(const int16_t* src, int16_t* dst, intptr_t dstStride) { inv_transform(4, 1, src, dst, dstStride); }
+
+/* lowpassdct.cpp:34-116: 2x2-average the block, run the (n/2)-point DCT, place it in
+ * the top-left quadrant, zero the rest, overwrite DC with the scaled block sum.
+ * Note the int16 truncation of every 2x2 sum, and of the running total for n == 8. */
+EXPORT void orc_lowpass_dct(int n, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    int hn = n / 2;
+    int16_t avg[16 * 16], coef[16 * 16];
+    int32_t total32 = 0;
+    int16_t total16 = 0;
+    for (int i = 0; i < hn; i++)
+        for (int j = 0; j < hn; j++)
+        {
+            int16_t sum = (int16_t)(src[2 * i * srcStride + 2 * j] + src[2 * i * srcStride + 2 * j + 1]
+                                  + src[(2 * i + 1) * srcStride + 2 * j] + src[(2 * i + 1) * srcStride + 2 * j + 1]);
+            avg[i * hn + j] = (int16_t)(sum >> 2);
+            total32 += sum;
+            total16 = (int16_t)(total16 + sum);
+        }
+    orc_dct(hn, avg, coef, hn);
+    memset(dst, 0, (size_t)n * n * sizeof(int16_t));
+    for (int i = 0; i < hn; i++)
+        memcpy(dst + i * n, coef + i * hn, (size_t)hn * sizeof(int16_t));
+    if (n == 8)
+    {
+#if X265_DEPTH == 8
+        dst[0] = (int16_t)wrap_shl(total16, 1);
+#else
+        dst[0] = (int16_t)(total16 >> (X265_DEPTH - 9));
+#endif
+    }
+    else if (n == 16)
+        dst[0] = (int16_t)(total32 >> (1 + (X265_DEPTH - 8)));
+    else
+        dst[0] = (int16_t)(total32 >> (3 + (X265_DEPTH - 8)));
+}
+
+/* dct.cpp:666-688 quant_c.  int32 products wrap (TestBench feeds negative quantCoeff). */
+EXPORT uint32_t orc_quant(const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU,
+                          int16_t* qCoef, int qBits, int add, int numCoeff)
+{
+    int qBits8 = qBits - 8;
+    uint32_t numSig = 0;
+    for (int i = 0; i < numCoeff; i++)
+    {
+        int level = coef[i];
+        int sign = level < 0 ? -1 : 1;
+        int32_t tmplevel = wrap_mul(iabs(level), quantCoeff[i]);
+        level = wrap_add(tmplevel, add) >> qBits;
+        deltaU[i] = wrap_sub(tmplevel, wrap_shl(level, qBits)) >> qBits8;
+        if (level) ++numSig;
+        level = wrap_mul(level, sign);
+        qCoef[i] = (int16_t)clip3(-32768, 32767, level);
+    }
+    return numSig;
+}
+
+/* dct.cpp:690-715 nquant_c: stores abs(clip16(level)); -32768 stays -32768 after the cast */
+EXPORT uint32_t orc_nquant(const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef,
+                           int qBits, int add, int numCoeff)
+{
+    uint32_t numSig = 0;
+    for (int i = 0; i < numCoeff; i++)
+    {
+        int level = coef[i];
+        int sign = level < 0 ? -1 : 1;
+        int32_t tmplevel = wrap_mul(iabs(level), quantCoeff[i]);
+        level = wrap_add(tmplevel, add) >> qBits;
+        if (level) ++numSig;
+        level = wrap_mul(level, sign);
+        qCoef[i] = (int16_t)iabs(clip3(-32768, 32767, level));
+    }
+    return numSig;
+}
+
+/* dct.cpp:614-636 dequant_normal_c */
+EXPORT void orc_dequant_normal(const int16_t* quantCoef, int16_t* coef, int num, int scale, int shift)
+{
+    int add = 1 << (shift - 1);
+    for (int n = 0; n < num; n++)
+    {
+        int q = wrap_add(wrap_mul(quantCoef[n], scale), add) >> shift;
+        coef[n] = (int16_t)clip3(-32768, 32767, q);
+    }
+}
+
+/* dct.cpp:638-664 dequant_scaling_c: two regimes on (shift + 4) > per */
+EXPORT void orc_dequant_scaling(const int16_t* quantCoef, const int32_t* deQuantCoef, int16_t* coef,
+                                int num, int per, int shift)
+{
+    shift += 4;
+    if (shift > per)
+    {
+        int add = 1 << (shift - per - 1);
+        for (int n = 0; n < num; n++)
+        {
+            int q = wrap_add(wrap_mul(quantCoef[n], deQuantCoef[n]), add) >> (shift - per);
+            coef[n] = (int16_t)clip3(-32768, 32767, q);
+        }
+    }
+    else
+    {
+        for (int n = 0; n < num; n++)
+        {
+            int q = clip3(-32768, 32767, wrap_mul(quantCoef[n], deQuantCoef[n]));
+            coef[n] = (int16_t)clip3(-32768, 32767, wrap_mul(q, 1 << (per - shift)));
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ interpolation */
+
+static inline const int16_t* taps(int N, int idx) { return N == 8 ? k_luma_taps[idx] : k_chroma_taps[idx]; }
+
+/* ipfilter.cpp:40-57 filterPixelToShort_c */
+EXPORT void orc_p2s(int w, int h, const pixel* src, intptr_t srcStride, int16_t* dst, intptr_t dstStride)
+{
+    int shift = IF_INTERNAL_PREC - X265_DEPTH;
+    for (int y = 0; y < h; y++, src += srcStride, dst += dstStride)
+        for (int x = 0; x < w; x++)
+        {
+            int16_t val = (int16_t)((int)src[x] << shift);
+            dst[x] = (int16_t)(val - (int16_t)IF_INTERNAL_OFFS);
+        }
+}
+
+/* ipfilter.cpp:79-118 interp_horiz_pp_c / :164-203 interp_vert_pp_c.
+ * step = 1 for horizontal, srcStride for vertical. */
+static void filt_pp(int N, int w, int h, const pixel* src, intptr_t srcStride, intptr_t step,
+                    pixel* dst, intptr_t dstStride, int idx)
+{
+    const int16_t* c = taps(N, idx);
+    src -= (N / 2 - 1) * step;
+    for (int y = 0; y < h; y++, src += srcStride, dst += dstStride)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < N; t++) sum += (int)src[x + t * step] * c[t];
+            int16_t val = (int16_t)((sum + 32) >> IF_FILTER_PREC);   /* cast before clip */
+            if (val < 0) val = 0;
+            if (val > PIXEL_MAX) val = PIXEL_MAX;
+            dst[x] = (pixel)val;
+        }
+}
+EXPORT void orc_interp_hpp(int N, int w, int h, const pixel* src, intptr_t ss, pixel* dst, intptr_t ds, int idx)
+{ filt_pp(N, w, h, src, ss, 1, dst, ds, idx); }
+EXPORT void orc_interp_vpp(int N, int w, int h, const pixel* src, intptr_t ss, pixel* dst, intptr_t ds, int idx)
+{ filt_pp(N, w, h, src, ss, ss, dst, ds, idx); }
+
+/* ipfilter.cpp:120-162 interp_horiz_ps_c (isRowExt adds N/2-1 rows above, N/2 below)
+ * ipfilter.cpp:205-238 interp_vert_ps_c */
+EXPORT void orc_interp_hps(int N, int w, int h, const pixel* src, intptr_t ss, int16_t* dst, intptr_t ds,
+                           int idx, int isRowExt)
+{
+    const int16_t* c = taps(N, idx);
+    int shift = IF_FILTER_PREC - (IF_INTERNAL_PREC - X265_DEPTH);
+    int offset = (int)((unsigned)-IF_INTERNAL_OFFS << shift);
+    int rows = h;
+    src -= N / 2 - 1;
+    if (isRowExt) { src -= (N / 2 - 1) * ss; rows += N - 1; }
+    for (int y = 0; y < rows; y++, src += ss, dst += ds)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < N; t++) sum += (int)src[x + t] * c[t];
+            dst[x] = (int16_t)((sum + offset) >> shift);
+        }
+}
+EXPORT void orc_interp_vps(int N, int w, int h, const pixel* src, intptr_t ss, int16_t* dst, intptr_t ds, int idx)
+{
+    const int16_t* c = taps(N, idx);
+    int shift = IF_FILTER_PREC - (IF_INTERNAL_PREC - X265_DEPTH);
+    int offset = (int)((unsigned)-IF_INTERNAL_OFFS << shift);
+    src -= (N / 2 - 1) * ss;
+    for (int y = 0; y < h; y++, src += ss, dst += ds)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < N; t++) sum += (int)src[x + t * ss] * c[t];
+            dst[x] = (int16_t)((sum + offset) >> shift);
+        }
+}
+/* ipfilter.cpp:240-283 interp_vert_sp_c */
+EXPORT void orc_interp_vsp(int N, int w, int h, const int16_t* src, intptr_t ss, pixel* dst, intptr_t ds, int idx)
+{
+    const int16_t* c = taps(N, idx);
+    int shift = IF_FILTER_PREC + (IF_INTERNAL_PREC - X265_DEPTH);
+    int offset = (1 << (shift - 1)) + (IF_INTERNAL_OFFS << IF_FILTER_PREC);
+    src -= (N / 2 - 1) * ss;
+    for (int y = 0; y < h; y++, src += ss, dst += ds)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < N; t++) sum += (int)src[x + t * ss] * c[t];
+            int16_t val = (int16_t)((sum + offset) >> shift);
+            if (val < 0) val = 0;
+            if (val > PIXEL_MAX) val = PIXEL_MAX;
+            dst[x] = (pixel)val;
+        }
+}
+/* ipfilter.cpp:285-317 interp_vert_ss_c: >>6, no rounding, int16 wrap */
+EXPORT void orc_interp_vss(int N, int w, int h, const int16_t* src, intptr_t ss, int16_t* dst, intptr_t ds, int idx)
+{
+    const int16_t* c = taps(N, idx);
+    src -= (N / 2 - 1) * ss;
+    for (int y = 0; y < h; y++, src += ss, dst += ds)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int t = 0; t < N; t++) sum += (int)src[x + t * ss] * c[t];
+            dst[x] = (int16_t)(sum >> IF_FILTER_PREC);
+        }
+}
+/* ipfilter.cpp:362-369 interp_hv_pp_c: hps(isRowExt=1) into a w-stride scratch, then vertical sp */
+EXPORT void orc_interp_hvpp(int N, int w, int h, const pixel* src, intptr_t ss, pixel* dst, intptr_t ds,
+                            int idxX, int idxY)
+{
+    int16_t* immed = (int16_t*)malloc((size_t)w * (h + N - 1) * sizeof(int16_t));
+    orc_interp_hps(N, w, h, src, ss, immed, w, idxX, 1);
+    orc_interp_vsp(N, w, h, immed + (N / 2 - 1) * w, w, dst, ds, idxY);
+    free(immed);
+}
+
+/* ------------------------------------------------------------------ batched drivers
+ * Descriptor-array loops used to diff whole-frame GPU output element-wise and as the
+ * "port" CPU baseline.  Offsets are element offsets from the plane base pointers. */
+
+enum { ORC_SAD = 0, ORC_SATD = 1, ORC_SA8D = 2, ORC_SSE_PP = 3 };
+
+EXPORT void orc_pixelcmp_batch(int op, int w, int h, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb,
+                               const int32_t* offA, const int32_t* offB, int n, void* out)
+{
+    for (int i = 0; i < n; i++)
+    {
+        const pixel* a = A + offA[i];
+        const pixel* b = B + offB[i];
+        switch (op)
+        {
+        case ORC_SAD:  ((int32_t*)out)[i] = orc_sad(w, h, a, sa, b, sb); break;
+        case ORC_SATD: ((int32_t*)out)[i] = orc_satd(w, h, a, sa, b, sb); break;
+        case ORC_SA8D: ((int32_t*)out)[i] = orc_sa8d(w, h, a, sa, b, sb); break;
+        default:       ((uint64_t*)out)[i] = (uint64_t)orc_sse_pp(w, h, a, sa, b, sb); break;
+        }
+    }
+}
+
+/* residual = fenc - pred (pixel.cpp: sub_ps, adjacent slot) for building DCT inputs */
+EXPORT void orc_residual_batch(int w, int h, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb,
+                               const int32_t* offA, const int32_t* offB, int n, int16_t* out /* n*w*h */)
+{
+    for (int i = 0; i < n; i++)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                out[(size_t)i * w * h + y * w + x] = (int16_t)((int)A[offA[i] + y * sa + x] - (int)B[offB[i] + y * sb + x]);
+}
+
+/* dct over n strided blocks of one int16 plane; output contiguous n x (N*N) */
+EXPORT void orc_dct_batch(int N, int dst4, const int16_t* src, intptr_t srcStride, const int32_t* off, int n, int16_t* out)
+{
+    for (int i = 0; i < n; i++)
+        fwd_transform(N, dst4, src + off[i], out + (size_t)i * N * N, srcStride);
+}
+EXPORT void orc_idct_batch(int N, int dst4, const int16_t* src, int n, int16_t* dst, intptr_t dstStride, const int32_t* off)
+{
+    for (int i = 0; i < n; i++)
+        inv_transform(N, dst4, src + (size_t)i * N * N, dst + off[i], dstStride);
+}

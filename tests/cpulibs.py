@@ -1,0 +1,258 @@
+"""ctypes handles for the two CPU checkers (test infrastructure only).
+
+Oracle     -> oracle/lib/liboracle_<depth>.so   (our C restatement; built on demand with gcc)
+Reference  -> oracle/_ref/libx265ref_<depth>.so (the reference's own C primitives; prebuilt in
+              the authoring container, shipped to the GPU box, never rebuilt there)
+
+Both expose the same Python methods so a test can run one against the other.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP = 0, 1, 2, 3
+
+
+def pixel_dtype(depth):
+    return np.uint8 if depth == 8 else np.uint16
+
+
+def _ptr(arr, off=0):
+    """address of element `off` (in elements) of a numpy array"""
+    return C.c_void_p(arr.ctypes.data + int(off) * arr.itemsize)
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+
+
+def have_reference(depth=10):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libx265ref_%d.so" % depth))
+
+
+class _Base:
+    prefix = ""
+
+    def __init__(self, depth):
+        self.depth = depth
+        self.pix = pixel_dtype(depth)
+        self.pmax = (1 << depth) - 1
+
+    def _f(self, name, restype=C.c_int):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = restype
+        return f
+
+    # ---- metrics -------------------------------------------------------------------
+    def sad(self, w, h, a, oa, sa, b, ob, sb):
+        return self._f("sad")(w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))
+
+    def satd(self, w, h, a, oa, sa, b, ob, sb):
+        return self._f("satd")(w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))
+
+    def sad_x3(self, w, h, fenc, of, ref, offs, rs):
+        res = np.zeros(3, np.int32)
+        self._f("sad_x3", None)(w, h, _ptr(fenc, of), _ptr(ref, offs[0]), _ptr(ref, offs[1]),
+                                _ptr(ref, offs[2]), C.c_ssize_t(rs), _ptr(res))
+        return res
+
+    def sad_x4(self, w, h, fenc, of, ref, offs, rs):
+        res = np.zeros(4, np.int32)
+        self._f("sad_x4", None)(w, h, _ptr(fenc, of), _ptr(ref, offs[0]), _ptr(ref, offs[1]),
+                                _ptr(ref, offs[2]), _ptr(ref, offs[3]), C.c_ssize_t(rs), _ptr(res))
+        return res
+
+    def ads(self, w, h, encDC, sums, osum, delta, cost, width, thresh):
+        enc = np.ascontiguousarray(encDC, np.int32)
+        mvs = np.full(width + 8, -1, np.int16)
+        n = self._f("ads")(w, h, _ptr(enc), _ptr(sums, osum), int(delta), _ptr(cost), _ptr(mvs),
+                           int(width), int(thresh))
+        return n, mvs[:n].copy()
+
+    def ssd_s(self, size, a, oa, sa):
+        return int(self._f("ssd_s", C.c_uint64)(size, _ptr(a, oa), C.c_ssize_t(sa)))
+
+    # ---- transforms ------------------------------------------------------------------
+    def dct(self, n, src, osrc, stride):
+        dst = np.zeros(n * n, np.int16)
+        self._f("dct", None)(n, _ptr(src, osrc), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def idct(self, n, src, stride, dst=None, odst=0):
+        if dst is None:
+            dst = np.zeros(n * stride, np.int16)
+        self._f("idct", None)(n, _ptr(src), _ptr(dst, odst), C.c_ssize_t(stride))
+        return dst
+
+    def dst4(self, src, osrc, stride):
+        dst = np.zeros(16, np.int16)
+        self._f("dst4", None)(_ptr(src, osrc), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def idst4(self, src, stride):
+        dst = np.zeros(4 * stride, np.int16)
+        self._f("idst4", None)(_ptr(src), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def lowpass_dct(self, n, src, osrc, stride):
+        dst = np.full(n * n, 0x5a5a, np.int16)
+        self._f("lowpass_dct", None)(n, _ptr(src, osrc), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def quant(self, coef, qc, qbits, add, n):
+        deltaU = np.zeros(n, np.int32)
+        q = np.zeros(n, np.int16)
+        r = self._f("quant", C.c_uint32)(_ptr(coef), _ptr(qc), _ptr(deltaU), _ptr(q), qbits, add, n)
+        return int(r), q, deltaU
+
+    def nquant(self, coef, qc, qbits, add, n):
+        q = np.zeros(n, np.int16)
+        r = self._f("nquant", C.c_uint32)(_ptr(coef), _ptr(qc), _ptr(q), qbits, add, n)
+        return int(r), q
+
+    def dequant_normal(self, q, n, scale, shift):
+        out = np.zeros(n, np.int16)
+        self._f("dequant_normal", None)(_ptr(q), _ptr(out), n, scale, shift)
+        return out
+
+    def dequant_scaling(self, q, dq, n, per, shift):
+        out = np.zeros(n, np.int16)
+        self._f("dequant_scaling", None)(_ptr(q), _ptr(dq), _ptr(out), n, per, shift)
+        return out
+
+    # ---- interpolation: every call writes into a caller buffer `dst` at `od` ------------
+    def interp(self, kind, N, w, h, src, os_, ss, dst, od, ds, idx, idy_or_ext=0):
+        a = (N, w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds), idx)
+        if kind in ("hps", "hvpp"):
+            a = a + (idy_or_ext,)
+        return self._f("interp_" + kind)(*a)
+
+    def p2s(self, w, h, src, os_, ss, dst, od, ds):
+        return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
+
+    # ---- tables -----------------------------------------------------------------------
+    def dct_matrix(self, n):
+        out = np.zeros(n * n, np.int16)
+        self._f("get_dct_matrix", None)(n, _ptr(out))
+        return out.reshape(n, n)
+
+    def luma_taps(self):
+        out = np.zeros(32, np.int16)
+        self._f("get_luma_taps", None)(_ptr(out))
+        return out.reshape(4, 8)
+
+    def chroma_taps(self):
+        out = np.zeros(32, np.int16)
+        self._f("get_chroma_taps", None)(_ptr(out))
+        return out.reshape(8, 4)
+
+
+class Oracle(_Base):
+    prefix = "orc_"
+
+    def __init__(self, depth):
+        super().__init__(depth)
+        path = os.path.join(ORACLE_DIR, "lib", "liboracle_%d.so" % depth)
+        src = os.path.join(ORACLE_DIR, "x265_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build_oracle()
+        self.lib = C.CDLL(path)
+        assert self.lib.orc_depth() == depth
+
+    def sa8d(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
+        return self._f("sa8d")(w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))
+
+    def sse_pp(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
+        rt = C.c_uint32 if self.depth == 8 else C.c_uint64
+        return int(self._f("sse_pp", rt)(w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb)))
+
+    def sse_ss(self, w, a, oa, sa, b, ob, sb):
+        rt = C.c_uint32 if self.depth == 8 else C.c_uint64
+        return int(self._f("sse_ss", rt)(w, w, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb)))
+
+    def ssd_s(self, size, a, oa, sa):
+        rt = C.c_uint32 if self.depth == 8 else C.c_uint64
+        return int(self._f("ssd_s", rt)(size, _ptr(a, oa), C.c_ssize_t(sa)))
+
+    def pixelcmp_batch(self, op, w, h, A, sa, B, sb, offA, offB, nthreads=1):
+        n = len(offA)
+        out = np.zeros(n, np.uint64 if op == OP_SSE_PP else np.int32)
+        self._f("pixelcmp_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
+                                        _ptr(offA), _ptr(offB), n, _ptr(out))
+        return out
+
+    def residual_batch(self, w, h, A, sa, B, sb, offA, offB):
+        n = len(offA)
+        out = np.zeros(n * w * h, np.int16)
+        self._f("residual_batch", None)(w, h, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
+                                        _ptr(offA), _ptr(offB), n, _ptr(out))
+        return out
+
+    def dct_batch(self, N, src, stride, off, dst4=0):
+        n = len(off)
+        out = np.zeros(n * N * N, np.int16)
+        self._f("dct_batch", None)(N, dst4, _ptr(src), C.c_ssize_t(stride), _ptr(off), n, _ptr(out))
+        return out
+
+    def idct_batch(self, N, src, dst, stride, off, dst4=0):
+        n = len(off)
+        self._f("idct_batch", None)(N, dst4, _ptr(src), n, _ptr(dst), C.c_ssize_t(stride), _ptr(off))
+        return dst
+
+
+class Reference(_Base):
+    prefix = "ref_"
+
+    def __init__(self, depth):
+        super().__init__(depth)
+        path = os.path.join(ORACLE_DIR, "_ref", "libx265ref_%d.so" % depth)
+        self.lib = C.CDLL(path)
+        assert self.lib.ref_depth() == depth
+
+    def sa8d(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
+        return self._f("sa8d")(chroma, w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))
+
+    def sse_pp(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
+        return int(self._f("sse_pp", C.c_uint64)(chroma, w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb)))
+
+    def sse_ss(self, w, a, oa, sa, b, ob, sb):
+        return int(self._f("sse_ss", C.c_uint64)(w, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb)))
+
+    def pixelcmp_batch(self, op, w, h, A, sa, B, sb, offA, offB, nthreads=1):
+        n = len(offA)
+        out = np.zeros(n, np.uint64 if op == OP_SSE_PP else np.int32)
+        r = self._f("pixelcmp_batch")(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
+                                      _ptr(offA), _ptr(offB), n, _ptr(out), nthreads)
+        assert r == 0
+        return out
+
+    def dct_batch(self, N, src, stride, off, nthreads=1):
+        n = len(off)
+        out = np.zeros(n * N * N, np.int16)
+        self._f("dct_batch")(N, _ptr(src), C.c_ssize_t(stride), _ptr(off), n, _ptr(out), nthreads)
+        return out
+
+    def residual_dct_batch(self, N, A, sa, B, sb, offA, offB, nthreads=1):
+        n = len(offA)
+        out = np.zeros(n * N * N, np.int16)
+        self._f("residual_dct_batch")(N, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
+                                      _ptr(offA), _ptr(offB), n, _ptr(out), nthreads)
+        return out
+
+    def count_nonnull_slots(self):
+        return self.lib.ref_count_nonnull_slots()
+
+
+LUMA_PU = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 8), (16, 8), (8, 16), (32, 16),
+           (16, 32), (64, 32), (32, 64), (16, 12), (12, 16), (16, 4), (4, 16), (32, 24), (24, 32),
+           (32, 8), (8, 32), (64, 48), (48, 64), (64, 16), (16, 64)]          # primitives.h:41-55
+# chroma-only PU sizes (4:2:0 = luma/2 both ways, 4:2:2 = luma/2 horizontally)
+CHROMA_ONLY_420 = [(4, 2), (2, 4), (8, 6), (6, 8), (8, 2), (2, 8)]
+CHROMA_ONLY_422 = [(2, 4), (2, 8), (4, 32), (8, 64), (8, 12), (6, 16), (2, 16), (16, 24), (12, 32),
+                   (32, 48), (24, 64)]
+SATD_CHROMA_422 = [(4, 32), (8, 64), (8, 12), (16, 24), (12, 32), (32, 48), (24, 64)]

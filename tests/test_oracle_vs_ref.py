@@ -1,0 +1,270 @@
+"""Pins oracle/x265_oracle.c against the reference's own C primitives (oracle/_ref).
+
+Runs wherever oracle/_ref/libx265ref_<depth>.so exists (the authoring container, and the GPU box
+because the prebuilt .so travels); skipped otherwise.  Covers the TestBench input classes
+(random / all-min / all-max) plus the cases TestBench never feeds:
+full-range int16 into IDCT / ss / ps filters, real quant tables, ADS.
+"""
+import numpy as np
+import pytest
+
+from cpulibs import (CHROMA_ONLY_420, CHROMA_ONLY_422, LUMA_PU, SATD_CHROMA_422, Oracle, Reference,
+                     have_reference)
+
+pytestmark = pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+
+DEPTHS = [8, 10, 12]
+
+
+@pytest.fixture(scope="module", params=DEPTHS)
+def libs(request):
+    d = request.param
+    return Oracle(d), Reference(d)
+
+
+def pixel_bufs(rng, depth, n):
+    dt = np.uint8 if depth == 8 else np.uint16
+    pmax = (1 << depth) - 1
+    yield rng.integers(0, pmax + 1, n).astype(dt), rng.integers(0, pmax + 1, n).astype(dt)
+    yield np.zeros(n, dt), np.full(n, pmax, dt)
+    yield np.full(n, pmax, dt), np.zeros(n, dt)
+    chk = ((np.arange(n) + np.arange(n) // 64) & 1).astype(dt) * pmax      # max-contrast checkerboard
+    yield chk, (pmax - chk).astype(dt)
+
+
+def test_tables(libs):
+    o, r = libs
+    for n in (4, 8, 16, 32):
+        assert np.array_equal(o.dct_matrix(n), r.dct_matrix(n))
+    assert np.array_equal(o.luma_taps(), r.luma_taps())
+    assert np.array_equal(o.chroma_taps(), r.chroma_taps())
+
+
+def test_sad_satd_all_pu(libs):
+    o, r = libs
+    rng = np.random.default_rng(1)
+    for a, b in pixel_bufs(rng, o.depth, 64 * 80 + 200 * 80):
+        for (w, h) in LUMA_PU:
+            for oa, ob, sa, sb in ((0, 0, 64, 64), (5, 37, 64, 171), (64, 3, 70, 64)):
+                assert o.sad(w, h, a, oa, sa, b, ob, sb) == r.sad(w, h, a, oa, sa, b, ob, sb)
+                assert o.satd(w, h, a, oa, sa, b, ob, sb) == r.satd(w, h, a, oa, sa, b, ob, sb)
+
+
+def test_satd_chroma_shapes(libs):
+    o, r = libs
+    rng = np.random.default_rng(2)
+    for a, b in pixel_bufs(rng, o.depth, 100 * 100):
+        for (w, h) in SATD_CHROMA_422 + [(8, 4), (4, 4), (16, 12)]:
+            assert o.satd(w, h, a, 3, 100, b, 7, 97) == r.satd(w, h, a, 3, 100, b, 7, 97), (w, h)
+
+
+def test_sa8d(libs):
+    o, r = libs
+    rng = np.random.default_rng(3)
+    for a, b in pixel_bufs(rng, o.depth, 64 * 80 + 200 * 80):
+        for w in (4, 8, 16, 32, 64):
+            assert o.sa8d(w, w, a, 1, 64, b, 9, 150) == r.sa8d(w, w, a, 1, 64, b, 9, 150)
+        for w in (4, 8, 16, 32):                       # 4:2:0 chroma cu slots (cu = 2w)
+            assert o.sa8d(w, w, a, 1, 64, b, 9, 150) == r.sa8d(w, w, a, 1, 64, b, 9, 150, chroma=1)
+        for w in (4, 8, 16, 32):                       # 4:2:2 chroma cu slots: w x 2w
+            assert o.sa8d(w, 2 * w, a, 1, 64, b, 9, 150) == r.sa8d(w, 2 * w, a, 1, 64, b, 9, 150, chroma=2)
+
+
+def test_sad_x3_x4(libs):
+    o, r = libs
+    rng = np.random.default_rng(4)
+    for a, b in pixel_bufs(rng, o.depth, 64 * 80 + 200 * 80):
+        for (w, h) in LUMA_PU:
+            offs = [0, 1, 2, 3]
+            assert np.array_equal(o.sad_x3(w, h, a, 0, b, offs, 59), r.sad_x3(w, h, a, 0, b, offs, 59))
+            offs = [200, 7, 64 * 3 + 1, 1000]
+            assert np.array_equal(o.sad_x4(w, h, a, 64, b, offs, 131), r.sad_x4(w, h, a, 64, b, offs, 131))
+
+
+def test_sse(libs):
+    o, r = libs
+    rng = np.random.default_rng(5)
+    pmax = o.pmax
+    for a, b in pixel_bufs(rng, o.depth, 64 * 80 + 200 * 80):
+        for w in (4, 8, 16, 32, 64):
+            assert o.sse_pp(w, w, a, 2, 64, b, 5, 99) == r.sse_pp(w, w, a, 2, 64, b, 5, 99)
+        for w in (4, 8, 16, 32):                       # chroma cu slots: 4:2:0 w x w, 4:2:2 w x 2w
+            if True:
+                assert o.sse_pp(w, w, a, 2, 64, b, 5, 99) == r.sse_pp(w, w, a, 2, 64, b, 5, 99, chroma=1)
+                assert o.sse_pp(w, 2 * w, a, 2, 64, b, 5, 99) == r.sse_pp(w, 2 * w, a, 2, 64, b, 5, 99, chroma=2)
+    for lo, hi in ((-pmax, pmax + 1), (-4096, 4097), (-23000, 23000)):
+        sa_ = rng.integers(lo, hi, 64 * 80).astype(np.int16)
+        sb_ = rng.integers(lo, hi, 64 * 80).astype(np.int16)
+        for w in (4, 8, 16, 32, 64):
+            assert o.sse_ss(w, sa_, 3, 64, sb_, 1, 70) == r.sse_ss(w, sa_, 3, 64, sb_, 1, 70)
+            assert o.ssd_s(w, sa_, 5, 66) == r.ssd_s(w, sa_, 5, 66)
+    full = rng.integers(-32768, 32768, 64 * 80).astype(np.int16)
+    for w in (4, 8, 16, 32, 64):
+        assert o.ssd_s(w, full, 5, 66) == r.ssd_s(w, full, 5, 66)
+
+
+def test_ads(libs):
+    o, r = libs
+    rng = np.random.default_rng(6)
+    stride = 300
+    for trial in range(6):
+        scale = [1 << 10, 1 << 16, 1 << 22, 0xFFFFFFFF][trial % 4]
+        sums = rng.integers(0, scale, stride * 80, dtype=np.uint64).astype(np.uint32)
+        cost = rng.integers(0, 4000, 256).astype(np.uint16)
+        for (w, h) in LUMA_PU:
+            enc = rng.integers(0, min(scale, 1 << 30), 4).astype(np.int32)
+            delta = (h >> 1) * stride if trial % 2 else rng.integers(1, 4000)
+            width = int(rng.integers(1, 29)) * 4
+            for thresh in (0, int(scale // 2 % (1 << 31)), (1 << 31) - 1):
+                n0, m0 = o.ads(w, h, enc, sums, 17, delta, cost, width, thresh)
+                n1, m1 = r.ads(w, h, enc, sums, 17, delta, cost, width, thresh)
+                assert n0 == n1 and np.array_equal(m0, m1), (w, h, trial, thresh)
+
+
+def residual_inputs(rng, pmax, n):
+    yield rng.integers(-pmax, pmax + 1, n).astype(np.int16)
+    yield np.full(n, -pmax, np.int16)
+    yield np.full(n, pmax, np.int16)
+    yield rng.integers(-32768, 32768, n).astype(np.int16)
+    yield np.full(n, 32767, np.int16)
+    yield np.full(n, -32768, np.int16)
+    alt = np.where(np.arange(n) & 1, 32767, -32768).astype(np.int16)
+    yield alt
+
+
+def test_dct_idct_dst(libs):
+    o, r = libs
+    rng = np.random.default_rng(7)
+    for src in residual_inputs(rng, o.pmax, 64 * 40 + 64):
+        for n in (4, 8, 16, 32):
+            for off, stride in ((0, n), (16, 64), (3, 37 if n <= 32 else 64)):
+                if stride < n:
+                    continue
+                assert np.array_equal(o.dct(n, src, off, stride), r.dct(n, src, off, stride)), n
+            for stride in (n, 64):
+                assert np.array_equal(o.idct(n, src, stride), r.idct(n, src, stride)), n
+        assert np.array_equal(o.dst4(src, 5, 4), r.dst4(src, 5, 4))
+        assert np.array_equal(o.dst4(src, 5, 64), r.dst4(src, 5, 64))
+        assert np.array_equal(o.idst4(src, 4), r.idst4(src, 4))
+        assert np.array_equal(o.idst4(src, 9), r.idst4(src, 9))
+
+
+def test_lowpass_dct(libs):
+    o, r = libs
+    rng = np.random.default_rng(8)
+    for src in residual_inputs(rng, o.pmax, 64 * 40 + 64):
+        for n in (8, 16, 32):
+            for off, stride in ((0, n), (7, 64)):
+                assert np.array_equal(o.lowpass_dct(n, src, off, stride), r.lowpass_dct(n, src, off, stride)), n
+
+
+def test_quant_family(libs):
+    o, r = libs
+    rng = np.random.default_rng(9)
+    pmax = o.pmax
+    flat = np.array([26214, 23302, 20560, 18396, 16384, 14564], np.int32)     # scalinglist.cpp:129
+    for trial in range(40):
+        n = [16, 64, 256, 1024][trial % 4]
+        kind = trial % 5
+        if kind == 0:
+            coef = rng.integers(-pmax, pmax + 1, n).astype(np.int16)
+            qc = rng.integers(-pmax, pmax + 1, n).astype(np.int32)
+        elif kind == 1:
+            coef = np.full(n, -pmax, np.int16); qc = np.full(n, -pmax, np.int32)
+        elif kind == 2:
+            coef = rng.integers(-32768, 32768, n).astype(np.int16)
+            qc = np.full(n, flat[trial % 6], np.int32)
+        elif kind == 3:
+            coef = rng.integers(-32768, 32768, n).astype(np.int16)
+            qc = rng.integers(1, 1 << 17, n).astype(np.int32)               # scaling-list magnitude
+        else:
+            coef = np.full(n, -32768, np.int16); qc = np.full(n, 26214 << 2, np.int32)
+        for qbits in (8, 9, 14, 17, 21, 25):
+            for add in ((171 << (qbits - 9)) if qbits >= 9 else 85, 1 << (qbits - 1)):
+                a0 = o.quant(coef, qc, qbits, add, n); a1 = r.quant(coef, qc, qbits, add, n)
+                assert a0[0] == a1[0] and np.array_equal(a0[1], a1[1]) and np.array_equal(a0[2], a1[2])
+                b0 = o.nquant(coef, qc, qbits, add, n); b1 = r.nquant(coef, qc, qbits, add, n)
+                assert b0[0] == b1[0] and np.array_equal(b0[1], b1[1])
+        for shift in (1, 2, 3, 5, 8, 10):
+            for scale in (40, 72 << 4, 64 << 8, 32767):
+                assert np.array_equal(o.dequant_normal(coef, n, scale, shift), r.dequant_normal(coef, n, scale, shift))
+        dq = rng.integers(1, 1 << 12, n).astype(np.int32)
+        for per in (0, 3, 8, 12):
+            for shift in (0, 1, 4, 6):
+                assert np.array_equal(o.dequant_scaling(coef, dq, n, per, shift), r.dequant_scaling(coef, dq, n, per, shift))
+
+
+def interp_case(o, r, kind, N, w, h, src, ss, ds, idx, extra, src_off):
+    dt = o.pix if kind in ("hpp", "vpp", "vsp", "hvpp") else np.int16
+    d0 = np.full(200 * 200, 123, dt); d1 = d0.copy()
+    r0 = o.interp(kind, N, w, h, src, src_off, ss, d0, 5, ds, idx, extra)
+    r1 = r.interp(kind, N, w, h, src, src_off, ss, d1, 5, ds, idx, extra)
+    assert r1 == 0, (kind, N, w, h)
+    assert np.array_equal(d0, d1), (kind, N, w, h, idx, extra)
+
+
+def test_interp_luma(libs):
+    o, r = libs
+    rng = np.random.default_rng(10)
+    pmax = o.pmax
+    psrcs = [rng.integers(0, pmax + 1, 200 * 200).astype(o.pix), np.zeros(200 * 200, o.pix), np.full(200 * 200, pmax, o.pix)]
+    ssrcs = [rng.integers(-4096, 4096, 200 * 200).astype(np.int16), rng.integers(-32768, 32768, 200 * 200).astype(np.int16)]
+    for (w, h) in LUMA_PU:
+        for idx in (1, 2, 3):
+            ss = int(rng.integers(w + 8, 130)); ds = int(rng.integers(64, 160))
+            off = 4 * ss + 8
+            for ps in psrcs:
+                interp_case(o, r, "hpp", 8, w, h, ps, ss, ds, idx, 0, off)
+                interp_case(o, r, "vpp", 8, w, h, ps, ss, ds, idx, 0, off)
+                interp_case(o, r, "hps", 8, w, h, ps, ss, ds, idx, 0, off)
+                interp_case(o, r, "hps", 8, w, h, ps, ss, ds, idx, 1, off)
+                interp_case(o, r, "vps", 8, w, h, ps, ss, ds, idx, 0, off)
+                interp_case(o, r, "hvpp", 8, w, h, ps, ss, ds, idx, 1 + (idx % 3), off)
+            for s16 in ssrcs:
+                interp_case(o, r, "vsp", 8, w, h, s16, ss, ds, idx, 0, off)
+                interp_case(o, r, "vss", 8, w, h, s16, ss, ds, idx, 0, off)
+        dp0 = np.full(200 * 200, 77, np.int16); dp1 = dp0.copy()
+        o.p2s(w, h, psrcs[0], 3, 99, dp0, 1, 80); assert r.p2s(w, h, psrcs[0], 3, 99, dp1, 1, 80) == 0
+        assert np.array_equal(dp0, dp1)
+
+
+def test_interp_chroma(libs):
+    o, r = libs
+    rng = np.random.default_rng(11)
+    pmax = o.pmax
+    ps = rng.integers(0, pmax + 1, 200 * 200).astype(o.pix)
+    s16 = rng.integers(-32768, 32768, 200 * 200).astype(np.int16)
+    shapes = LUMA_PU + CHROMA_ONLY_420 + CHROMA_ONLY_422
+    for (w, h) in shapes:
+        for idx in range(8):
+            ss = int(rng.integers(w + 4, 120)); ds = int(rng.integers(64, 160))
+            off = 2 * ss + 4
+            interp_case(o, r, "hpp", 4, w, h, ps, ss, ds, idx, 0, off)
+            interp_case(o, r, "vpp", 4, w, h, ps, ss, ds, idx, 0, off)
+            interp_case(o, r, "hps", 4, w, h, ps, ss, ds, idx, idx & 1, off)
+            interp_case(o, r, "vps", 4, w, h, ps, ss, ds, idx, 0, off)
+            interp_case(o, r, "vsp", 4, w, h, s16, ss, ds, idx, 0, off)
+            interp_case(o, r, "vss", 4, w, h, s16, ss, ds, idx, 0, off)
+        dp0 = np.full(200 * 200, 77, np.int16); dp1 = dp0.copy()
+        o.p2s(w, h, ps, 3, 99, dp0, 1, 80); assert r.p2s(w, h, ps, 3, 99, dp1, 1, 80) == 0
+        assert np.array_equal(dp0, dp1)
+
+
+def test_batched_drivers(libs):
+    o, r = libs
+    rng = np.random.default_rng(12)
+    stride, rows = 256, 160
+    A = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+    B = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+    for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (24, 32)):
+        n = 50
+        offA = (rng.integers(0, rows - h, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+        offB = (rng.integers(0, rows - h, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+        ops = [0, 1] + ([2, 3] if w == h else [])
+        for op in ops:
+            assert np.array_equal(o.pixelcmp_batch(op, w, h, A, stride, B, stride, offA, offB),
+                                  r.pixelcmp_batch(op, w, h, A, stride, B, stride, offA, offB, nthreads=3))
+        if w == h and w <= 32:
+            res = o.residual_batch(w, h, A, stride, B, stride, offA, offB)
+            off = (np.arange(n) * w * w).astype(np.int32)
+            assert np.array_equal(o.dct_batch(w, res, w, off), r.residual_dct_batch(w, A, stride, B, stride, offA, offB, 2))
