@@ -1,0 +1,183 @@
+/*
+ * x265b200.h -- C ABI of the B200 (sm_100a) analysis-primitive path for x265.
+ *
+ * Drop-in boundary: x265's EncoderPrimitives function-pointer table
+ * (reference source/common/primitives.h:239-432).  Two families of entry points:
+ *
+ *  A. per-call HOST entries (section "host") -- one per primitive typedef of
+ *     primitives.h:133-182, same argument order and meaning, with (ctx, width, height)
+ *     prepended because the reference bakes the block size into the slot (pu[part] / cu[size])
+ *     and the pixel type into the build (X265_DEPTH).  `pixel` is uint8_t when the context was
+ *     opened at 8 bit and uint16_t at 10/12 bit (common.h:127-143); it is passed as void*.
+ *     setupB200Primitives() (csrc/setup_b200_primitives.cpp) binds every hot-path slot to a thunk
+ *     that calls these.  They stage the block through pinned memory, run the same CUDA kernels as
+ *     family B with n = 1, and copy the result back.  There is NO CPU fallback: if the device is
+ *     unusable the call records a sticky error (x265b200_status) and returns 0 / leaves outputs
+ *     untouched, because a slot has no way to report errors (SURVEY.md 8b "Errors").
+ *
+ *  B. batched DEVICE entries (section "device") -- arrays of block descriptors over planes that are
+ *     already resident in HBM, one launch per primitive class and block shape.  All pointers are
+ *     device pointers, offsets are element offsets from the plane base, `stream` is a cudaStream_t.
+ *     These have no counterpart in the reference (it calls one block at a time); they are what a
+ *     batching caller (ThreadedME, lookahead, the benchmark) uses.
+ *
+ * All functions return X265B200_OK (0) or a negative error code unless stated otherwise.
+ */
+#ifndef X265B200_H
+#define X265B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct x265b200_ctx x265b200_ctx;
+typedef void* x265b200_stream;          /* cudaStream_t; NULL = the legacy default stream */
+
+enum {
+    X265B200_OK = 0,
+    X265B200_ERR_ARG = -1,              /* bad size / pointer / depth */
+    X265B200_ERR_CUDA = -2,             /* a CUDA runtime call failed (see x265b200_last_error) */
+    X265B200_ERR_NO_DEVICE = -3
+};
+
+/* block-compare operations for x265b200_pixelcmp_batch */
+enum {
+    X265B200_SAD = 0,                   /* pixelcmp_t  pu[].sad        pixel.cpp:40-55   */
+    X265B200_SATD = 1,                  /* pixelcmp_t  pu[].satd       pixel.cpp:190-289 */
+    X265B200_SA8D = 2,                  /* pixelcmp_t  cu[].sa8d       pixel.cpp:291-369 */
+    X265B200_SSE_PP = 3                 /* pixel_sse_t cu[].sse_pp     pixel.cpp:167-186 */
+};
+
+/* transform kinds for x265b200_dct_batch / x265b200_idct_batch */
+enum {
+    X265B200_TR_DCT = 0,                /* cu[].dct / cu[].idct        dct.cpp:443-611 */
+    X265B200_TR_DST = 1,                /* dst4x4 / idst4x4 (N = 4)    dct.cpp:43-81   */
+    X265B200_TR_LOWPASS = 2             /* cu[].lowpass_dct (forward only, N = 8,16,32) lowpassdct.cpp:34-116 */
+};
+
+/* interpolation kinds for x265b200_interp_batch */
+enum {
+    X265B200_IP_HPP = 0,                /* filter_pp_t    luma_hpp / filter_hpp   ipfilter.cpp:79-118  */
+    X265B200_IP_HPS = 1,                /* filter_hps_t   luma_hps / filter_hps   ipfilter.cpp:120-162 */
+    X265B200_IP_VPP = 2,                /* filter_pp_t    luma_vpp / filter_vpp   ipfilter.cpp:164-203 */
+    X265B200_IP_VPS = 3,                /* filter_ps_t    luma_vps / filter_vps   ipfilter.cpp:205-238 */
+    X265B200_IP_VSP = 4,                /* filter_sp_t    luma_vsp / filter_vsp   ipfilter.cpp:240-283 */
+    X265B200_IP_VSS = 5,                /* filter_ss_t    luma_vss / filter_vss   ipfilter.cpp:285-317 */
+    X265B200_IP_HVPP = 6,               /* filter_hv_pp_t luma_hvpp               ipfilter.cpp:362-369 */
+    X265B200_IP_P2S = 7                 /* filter_p2s_t   convert_p2s / p2s       ipfilter.cpp:40-57   */
+};
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* bit_depth in {8, 10, 12}: fixes sizeof(pixel) and every depth-dependent shift, exactly as
+ * X265_DEPTH does at compile time in the reference (source/CMakeLists.txt:787-798). */
+int x265b200_open(int device, int bit_depth, x265b200_ctx** ctx);
+void x265b200_close(x265b200_ctx* ctx);
+int x265b200_bit_depth(const x265b200_ctx* ctx);
+int x265b200_sm_count(const x265b200_ctx* ctx);
+/* sticky status: first error recorded by any entry (host entries cannot return one) */
+int x265b200_status(const x265b200_ctx* ctx);
+const char* x265b200_last_error(const x265b200_ctx* ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+uint64_t x265b200_launch_count(const x265b200_ctx* ctx);
+
+/* ------------------------------------------------------------------ device (batched) */
+
+/* out[i] = op(planeA + offA[i], strideA, planeB + offB[i], strideB) for i < n.
+ * out is int32[n] for SAD/SATD/SA8D and uint64[n] for SSE_PP.  Any w,h multiple of 4
+ * (SA8D: both multiples of 16 -> per-16x16 rounding, both multiples of 8 -> per-8x8, else SATD,
+ * which reproduces every luma/chroma sa8d slot binding, pixel.cpp:1180-1184,1260-1263,1339-1342). */
+int x265b200_pixelcmp_batch(x265b200_ctx* ctx, int op, int w, int h,
+                            const void* planeA, intptr_t strideA, const void* planeB, intptr_t strideB,
+                            const int32_t* offA, const int32_t* offB, int n, void* out, x265b200_stream stream);
+
+/* K candidates per block sharing one fenc block (sad_x3 / sad_x4 generalised, pixel.cpp:74-119):
+ * out[i*K + k] = sad(fenc + offF[i], strideF, ref + offR[i*K + k], strideR). */
+int x265b200_sad_multi_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t strideF,
+                             const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR,
+                             int K, int n, int32_t* out, x265b200_stream stream);
+
+/* pixel_sse_ss_t (pixel.cpp:167-186 with int16 inputs) and pixel_ssd_s_t (pixel.cpp:371-383);
+ * out is uint64[n] (truncate to 32 bit for an 8-bit build's sse_t). */
+int x265b200_sse_ss_batch(x265b200_ctx* ctx, int w, int h, const int16_t* A, intptr_t strideA,
+                          const int16_t* B, intptr_t strideB, const int32_t* offA, const int32_t* offB,
+                          int n, uint64_t* out, x265b200_stream stream);
+int x265b200_ssd_s_batch(x265b200_ctx* ctx, int size, const int16_t* A, intptr_t strideA,
+                         const int32_t* offA, int n, uint64_t* out, x265b200_stream stream);
+
+/* SEA candidate filter (pixelcmp_ads_t, pixel.cpp:121-165).  Job i scans `width[i]` positions of the
+ * integral-sum row starting at sums + sumOff[i]; `terms` in {1,2,4} DC terms (half = w>>1 as in
+ * ads_x4); survivors are written in ascending order to mvs + i*mvsPitch, their count to count[i]. */
+int x265b200_ads_batch(x265b200_ctx* ctx, int terms, int half, const int32_t* encDC /* n*4 */,
+                       const uint32_t* sums, const int32_t* sumOff, const int32_t* delta,
+                       const uint16_t* costMvX, const int32_t* costOff, const int32_t* width,
+                       const int32_t* thresh, int n, int16_t* mvs, int mvsPitch, int32_t* count,
+                       x265b200_stream stream);
+
+/* forward transform of n blocks: src block i at src + off[i] with srcStride (elements);
+ * dst block i contiguous at dst + i*N*N.  (dct_t, primitives.h:153) */
+int x265b200_dct_batch(x265b200_ctx* ctx, int kind, int N, const int16_t* src, intptr_t srcStride,
+                       const int32_t* off, int n, int16_t* dst, x265b200_stream stream);
+/* inverse: src block i contiguous at src + i*N*N, dst block i at dst + off[i] with dstStride. (idct_t) */
+int x265b200_idct_batch(x265b200_ctx* ctx, int kind, int N, const int16_t* src, int n,
+                        int16_t* dst, intptr_t dstStride, const int32_t* off, x265b200_stream stream);
+
+/* quant_t / nquant_t over n blocks of numCoeff coefficients each (contiguous); quantCoeff is one
+ * table of numCoeff entries shared by all blocks; numSig[i] receives the return value of block i.
+ * deltaU == NULL selects nquant (dct.cpp:690-715), else quant (dct.cpp:666-688). */
+int x265b200_quant_batch(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU,
+                         int16_t* qCoef, int qBits, int add, int numCoeff, int n, uint32_t* numSig,
+                         x265b200_stream stream);
+/* dequant_normal_t (dct.cpp:614-636) over `num` coefficients (any multiple of 8) */
+int x265b200_dequant_normal_batch(x265b200_ctx* ctx, const int16_t* quantCoef, int16_t* coef, int num,
+                                  int scale, int shift, x265b200_stream stream);
+/* dequant_scaling_t (dct.cpp:638-664): n blocks of `num` coefficients sharing one table of `num` entries */
+int x265b200_dequant_scaling_batch(x265b200_ctx* ctx, const int16_t* quantCoef, const int32_t* deQuantCoef,
+                                   int16_t* coef, int num, int n, int per, int shift, x265b200_stream stream);
+
+/* interpolation of n blocks.  taps = 8 (luma) or 4 (chroma).  src/dst element types follow the kind
+ * (pixel or int16).  coeffIdx[i] packs idxX | idxY << 4 | isRowExt << 8 (idxY only for HVPP,
+ * isRowExt only for HPS).  For HPS with isRowExt the block writes h + taps - 1 rows starting at
+ * dst + offDst[i], exactly like the reference. */
+int x265b200_interp_batch(x265b200_ctx* ctx, int kind, int taps, int w, int h,
+                          const void* src, intptr_t srcStride, const int32_t* offSrc,
+                          void* dst, intptr_t dstStride, const int32_t* offDst,
+                          const int32_t* coeffIdx, int n, x265b200_stream stream);
+
+/* residual = fenc - pred for n blocks (pixel_sub_ps_t, adjacent slot; used to build DCT inputs on device):
+ * dst block i contiguous at dst + i*w*h. */
+int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const void* A, intptr_t strideA,
+                            const void* B, intptr_t strideB, const int32_t* offA, const int32_t* offB,
+                            int n, int16_t* dst, x265b200_stream stream);
+
+/* ------------------------------------------------------------------ host (per-call, drop-in slots) */
+
+int x265b200_sad(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
+int x265b200_satd(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
+int x265b200_sa8d(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
+uint64_t x265b200_sse_pp(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
+uint64_t x265b200_sse_ss(x265b200_ctx*, int w, int h, const int16_t* fenc, intptr_t fencstride, const int16_t* fref, intptr_t frefstride);
+uint64_t x265b200_ssd_s(x265b200_ctx*, int size, const int16_t* a, intptr_t stride);
+/* fenc stride is FENC_STRIDE = 64 (common.h:71) as in the reference */
+void x265b200_sad_x3(x265b200_ctx*, int w, int h, const void* fenc, const void* fref0, const void* fref1, const void* fref2, intptr_t frefstride, int32_t* res);
+void x265b200_sad_x4(x265b200_ctx*, int w, int h, const void* fenc, const void* fref0, const void* fref1, const void* fref2, const void* fref3, intptr_t frefstride, int32_t* res);
+int x265b200_ads(x265b200_ctx*, int w, int h, const int* encDC, const uint32_t* sums, int delta, const uint16_t* costMvX, int16_t* mvs, int width, int thresh);
+
+void x265b200_dct(x265b200_ctx*, int kind, int N, const int16_t* src, int16_t* dst, intptr_t srcStride);
+void x265b200_idct(x265b200_ctx*, int kind, int N, const int16_t* src, int16_t* dst, intptr_t dstStride);
+uint32_t x265b200_quant(x265b200_ctx*, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef, int qBits, int add, int numCoeff);
+uint32_t x265b200_nquant(x265b200_ctx*, const int16_t* coef, const int32_t* quantCoeff, int16_t* qCoef, int qBits, int add, int numCoeff);
+void x265b200_dequant_normal(x265b200_ctx*, const int16_t* quantCoef, int16_t* coef, int num, int scale, int shift);
+void x265b200_dequant_scaling(x265b200_ctx*, const int16_t* src, const int32_t* dequantCoef, int16_t* dst, int num, int mcqp_miper, int shift);
+
+/* kind = X265B200_IP_*; extra = isRowExt for HPS, idxY for HVPP (coeffIdx is then idxX), else ignored */
+void x265b200_interp(x265b200_ctx*, int kind, int taps, int w, int h, const void* src, intptr_t srcStride,
+                     void* dst, intptr_t dstStride, int coeffIdx, int extra);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X265B200_H */

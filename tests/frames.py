@@ -1,0 +1,62 @@
+"""Deterministic synthetic planes and block-descriptor arrays with x265's plane geometry
+(reference geometry: source/common/picyuv.cpp:86-118)."""
+import numpy as np
+
+
+def splitmix64(idx, seed):
+    z = (idx.astype(np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+class Geometry:
+    """luma plane geometry of a w x h picture with CTU size `ctu` (picyuv.cpp:86-92)"""
+
+    def __init__(self, width, height, ctu=64):
+        self.width, self.height, self.ctu = width, height, ctu
+        self.cu_w = (width + ctu - 1) // ctu
+        self.cu_h = (height + ctu - 1) // ctu
+        self.margin_x = ctu + 32
+        self.margin_y = ctu + 16
+        self.stride = self.cu_w * ctu + 2 * self.margin_x
+        self.rows = self.cu_h * ctu + 2 * self.margin_y
+        self.origin = self.margin_y * self.stride + self.margin_x     # element offset of pixel (0,0)
+        self.plane_elems = self.stride * self.rows
+
+    def coded(self):
+        return self.cu_w * self.ctu, self.cu_h * self.ctu
+
+
+def make_plane(geo, depth, seed, kind="uniform"):
+    dt = np.uint8 if depth == 8 else np.uint16
+    pmax = (1 << depth) - 1
+    idx = np.arange(geo.plane_elems, dtype=np.uint64)
+    if kind == "uniform":
+        return (splitmix64(idx, seed) & np.uint64(pmax)).astype(dt)
+    y = (idx // np.uint64(geo.stride)).astype(np.float64)
+    x = (idx % np.uint64(geo.stride)).astype(np.float64)
+    mid, amp = 1 << (depth - 1), 1 << (depth - 3)
+    noise = ((splitmix64(idx, seed) & np.uint64(31)).astype(np.int64) - 16) * (1 << (depth - 8))
+    v = mid + amp * (np.sin(x / 97.0) + np.cos(y / 61.0)) + noise
+    return np.clip(np.rint(v), 0, pmax).astype(dt)
+
+
+def tile_blocks(geo, w, h, seed, merange=57):
+    """every w x h block of a full tiling of the coded area, with one MV per block drawn uniformly in
+    +-merange (clamped so the reference block stays inside the padded plane).
+    returns (offA, offB) int32 element offsets from the plane base."""
+    cw, ch = geo.coded()
+    xs = np.arange(0, cw, w, dtype=np.int64)
+    ys = np.arange(0, ch, h, dtype=np.int64)
+    X, Y = np.meshgrid(xs, ys)
+    X = X.ravel(); Y = Y.ravel()
+    n = X.size
+    r = splitmix64(np.arange(n, dtype=np.uint64), seed * 7919 + w * 131 + h)
+    mvx = (r % np.uint64(2 * merange + 1)).astype(np.int64) - merange
+    mvy = ((r >> np.uint64(20)) % np.uint64(2 * merange + 1)).astype(np.int64) - merange
+    RX = np.clip(X + mvx, -geo.margin_x + 8, cw + geo.margin_x - w - 8)
+    RY = np.clip(Y + mvy, -geo.margin_y + 8, ch + geo.margin_y - h - 8)
+    offA = (geo.origin + Y * geo.stride + X).astype(np.int32)
+    offB = (geo.origin + RY * geo.stride + RX).astype(np.int32)
+    return offA, offB

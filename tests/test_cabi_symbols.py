@@ -1,0 +1,39 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU and exports every symbol the header
+declares.  No compute call is made here."""
+import ctypes
+import os
+
+import pytest
+
+from gpulib import pkg
+
+
+def test_library_built_and_exports_all_declared_symbols():
+    if not os.path.exists(pkg.LIB_PATH):
+        pkg.build_library(glue=False)
+    lib = pkg.load_library()
+    syms = pkg.declared_symbols()
+    assert len(syms) >= 35
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        pkg.Context(10)
+
+
+def test_product_does_not_reference_oracle():
+    """the product tree must never import / link the oracle (parity claims depend on it)"""
+    root = os.path.dirname(pkg.LIB_PATH)
+    pkgdir = os.path.dirname(root)
+    for dp, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "x265_oracle" not in text and "liboracle" not in text and "cpulibs" not in text, os.path.join(dp, f)
+    out = os.popen("ldd %s" % pkg.LIB_PATH).read()
+    assert "oracle" not in out and "x265ref" not in out

@@ -1,0 +1,143 @@
+"""Batched DEVICE entries of the C ABI against the oracle on seeded full-plane inputs.
+
+Element-wise diffs at sizes the oracle finishes in seconds (BASELINE config #2 geometry, 1080p),
+size-independent properties at BASELINE's full 2160p10 size."""
+import numpy as np
+import pytest
+
+from cpulibs import OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP, LUMA_PU, Oracle
+from frames import Geometry, make_plane, tile_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a).cuda()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_pixelcmp_frame_all_shapes(depth, torch_mod):
+    torch = torch_mod
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(640, 384)
+    A = make_plane(geo, depth, 0x265, "natural"); B = make_plane(geo, depth, 0x266, "uniform")
+    dA, dB = dev(A.view(np.int16 if depth > 8 else np.uint8)), dev(B.view(np.int16 if depth > 8 else np.uint8))
+    for (w, h) in LUMA_PU:
+        offA, offB = tile_blocks(geo, w, h, seed=3)
+        dOA, dOB = dev(offA), dev(offB)
+        ops = [OP_SAD, OP_SATD] + ([OP_SA8D, OP_SSE_PP] if w == h else [])
+        for op in ops:
+            out = torch.zeros(len(offA), dtype=torch.int64 if op == OP_SSE_PP else torch.int32, device="cuda")
+            ctx.pixelcmp_batch(op, w, h, dA, geo.stride, dB, geo.stride, dOA, dOB, out)
+            ref = orc.pixelcmp_batch(op, w, h, A, geo.stride, B, geo.stride, offA, offB)
+            assert np.array_equal(out.cpu().numpy().astype(np.int64), ref.astype(np.int64)), (w, h, op)
+    ctx.check()
+
+
+def test_sad_multi_and_ragged(torch_mod):
+    torch = torch_mod
+    from gpulib import context
+    depth = 10
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(256, 128)
+    A = make_plane(geo, depth, 1); B = make_plane(geo, depth, 2)
+    dA, dB = dev(A.view(np.int16)), dev(B.view(np.int16))
+    for (w, h), K in (((16, 16), 4), ((8, 8), 3), ((64, 32), 9), ((12, 16), 5)):
+        offA, offB0 = tile_blocks(geo, w, h, seed=5)
+        n = len(offA)
+        offR = np.stack([offB0 + k * 3 - (k % 2) * geo.stride for k in range(K)], axis=1).astype(np.int32).ravel()
+        out = torch.zeros(n * K, dtype=torch.int32, device="cuda")
+        ctx.sad_multi_batch(w, h, dA, geo.stride, dB, geo.stride, dev(offA), dev(offR), K, out)
+        ref = orc.pixelcmp_batch(OP_SAD, w, h, A, geo.stride, B, geo.stride, np.repeat(offA, K).astype(np.int32), offR)
+        assert np.array_equal(out.cpu().numpy(), ref)
+    # empty batch is a no-op
+    e = torch.zeros(0, dtype=torch.int32, device="cuda")
+    ctx.pixelcmp_batch(OP_SATD, 8, 8, dA, geo.stride, dB, geo.stride, e, e, e)
+    # n = 1 and n not a multiple of the lane-group packing
+    for n in (1, 3, 33):
+        offA, offB = tile_blocks(geo, 8, 8, seed=9)
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.pixelcmp_batch(OP_SATD, 8, 8, dA, geo.stride, dB, geo.stride, dev(offA[:n].copy()), dev(offB[:n].copy()), out)
+        assert np.array_equal(out.cpu().numpy(), orc.pixelcmp_batch(OP_SATD, 8, 8, A, geo.stride, B, geo.stride, offA[:n].copy(), offB[:n].copy()))
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_residual_dct_idct_frame(depth, torch_mod):
+    torch = torch_mod
+    from gpulib import context, pkg
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(320, 192)
+    A = make_plane(geo, depth, 11, "natural"); B = make_plane(geo, depth, 12, "uniform")
+    vt = np.int16 if depth > 8 else np.uint8
+    dA, dB = dev(A.view(vt)), dev(B.view(vt))
+    for N in (4, 8, 16, 32):
+        offA, offB = tile_blocks(geo, N, N, seed=7)
+        n = len(offA)
+        res = torch.zeros(n * N * N, dtype=torch.int16, device="cuda")
+        ctx.residual_batch(N, N, dA, geo.stride, dB, geo.stride, dev(offA), dev(offB), res)
+        ref_res = orc.residual_batch(N, N, A, geo.stride, B, geo.stride, offA, offB)
+        assert np.array_equal(res.cpu().numpy(), ref_res)
+        off = (np.arange(n) * N * N).astype(np.int32)
+        coef = torch.zeros(n * N * N, dtype=torch.int16, device="cuda")
+        ctx.dct_batch(pkg.TR_DCT, N, res, N, dev(off), coef)
+        ref_coef = orc.dct_batch(N, ref_res, N, off)
+        assert np.array_equal(coef.cpu().numpy(), ref_coef), N
+        # inverse into a strided plane (dstStride > N)
+        stride = 40 * N
+        rows = (n + 39) // 40
+        plane = torch.zeros(rows * N * stride, dtype=torch.int16, device="cuda")
+        offD = ((np.arange(n) // 40) * N * stride + (np.arange(n) % 40) * N).astype(np.int32)
+        ctx.idct_batch(pkg.TR_DCT, N, coef, plane, stride, dev(offD))
+        ref_plane = orc.idct_batch(N, ref_coef, np.zeros(rows * N * stride, np.int16), stride, offD)
+        assert np.array_equal(plane.cpu().numpy(), ref_plane), N
+        if N == 4:
+            ctx.dct_batch(pkg.TR_DST, 4, res, 4, dev(off), coef)
+            assert np.array_equal(coef.cpu().numpy(), orc.dct_batch(4, ref_res, 4, off, dst4=1))
+    ctx.check()
+
+
+def test_full_size_properties_2160p10(torch_mod):
+    """BASELINE config #3 size: properties that do not need the oracle at full size."""
+    torch = torch_mod
+    from gpulib import context
+    depth = 10
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(3840, 2160)
+    A = make_plane(geo, depth, 21); B = make_plane(geo, depth, 22)
+    dA, dB = dev(A.view(np.int16)), dev(B.view(np.int16))
+    tot = {}
+    for (w, h) in ((64, 64), (32, 32), (16, 16), (8, 8), (4, 4)):
+        offA, _ = tile_blocks(geo, w, h, seed=1)
+        offB = offA.copy()                                  # zero motion: every tiling covers the same samples
+        dO = dev(offA)
+        sad = torch.zeros(len(offA), dtype=torch.int32, device="cuda")
+        sse = torch.zeros(len(offA), dtype=torch.int64, device="cuda")
+        ctx.pixelcmp_batch(OP_SAD, w, h, dA, geo.stride, dB, geo.stride, dO, dO, sad)
+        ctx.pixelcmp_batch(OP_SSE_PP, w, h, dA, geo.stride, dB, geo.stride, dO, dO, sse)
+        tot[w] = (int(sad.sum(dtype=torch.int64)), int(sse.sum()))
+        # identical blocks: every metric is exactly zero
+        z = torch.ones(len(offA), dtype=torch.int32, device="cuda")
+        ctx.pixelcmp_batch(OP_SATD, w, h, dA, geo.stride, dA, geo.stride, dO, dO, z)
+        assert int(z.abs().max()) == 0
+        # sampled element-wise check against the oracle
+        sel = np.linspace(0, len(offA) - 1, 64).astype(np.int64)
+        satd = torch.zeros(len(offA), dtype=torch.int32, device="cuda")
+        ctx.pixelcmp_batch(OP_SATD, w, h, dA, geo.stride, dB, geo.stride, dO, dO, satd)
+        ref = orc.pixelcmp_batch(OP_SATD, w, h, A, geo.stride, B, geo.stride, offA[sel].copy(), offB[sel].copy())
+        assert np.array_equal(satd.cpu().numpy()[sel], ref)
+    # SAD and SSE are additive over any tiling: totals agree across block sizes and with numpy
+    assert len(set(tot.values())) == 1
+    cw, ch = geo.coded()
+    a2 = A.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + ch, geo.margin_x:geo.margin_x + cw].astype(np.int64)
+    b2 = B.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + ch, geo.margin_x:geo.margin_x + cw].astype(np.int64)
+    assert tot[64] == (int(np.abs(a2 - b2).sum()), int(((a2 - b2) ** 2).sum()))
+    ctx.check()

@@ -1,0 +1,259 @@
+"""ctypes binding of include/x265b200.h (plumbing for tests and the benchmark)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libx265b200.so")
+HEADER = os.path.join(ROOT, "include", "x265b200.h")
+
+OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP = 0, 1, 2, 3
+TR_DCT, TR_DST, TR_LOWPASS = 0, 1, 2
+IP_KINDS = {"hpp": 0, "hps": 1, "vpp": 2, "vps": 3, "vsp": 4, "vss": 5, "hvpp": 6, "p2s": 7}
+
+_lib = None
+
+
+def build_library(glue=True):
+    """compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)"""
+    subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "lib"], check=True)
+    if glue and os.path.isdir("/root/reference/source") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "cfg", "x265_config.h")):
+        subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "glue"], check=True)
+
+
+def declared_symbols():
+    """every function name include/x265b200.h declares"""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(x265b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA library %s is missing: run __graft_entry__.build() (there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.x265b200_last_error.restype = C.c_char_p
+        _lib.x265b200_launch_count.restype = C.c_uint64
+        for name in ("x265b200_sse_pp", "x265b200_sse_ss", "x265b200_ssd_s"):
+            getattr(_lib, name).restype = C.c_uint64
+        for name in ("x265b200_quant", "x265b200_nquant"):
+            getattr(_lib, name).restype = C.c_uint32
+        for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
+                     "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp"):
+            getattr(_lib, name).restype = None
+    return _lib
+
+
+def _p(arr, off=0):
+    return C.c_void_p(arr.ctypes.data + int(off) * arr.itemsize)
+
+
+def _dp(t, off=0):
+    """device pointer of a torch CUDA tensor (or None)"""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr() + int(off) * t.element_size())
+
+
+def _ss(v):
+    return C.c_ssize_t(int(v))
+
+
+class Context:
+    """One x265b200 context = one device + one bit depth (mirrors a per-depth x265 build)."""
+
+    def __init__(self, depth, device=0):
+        self.lib = load_library()
+        self.depth = depth
+        self.pix = np.uint8 if depth == 8 else np.uint16
+        self.pmax = (1 << depth) - 1
+        h = C.c_void_p()
+        r = self.lib.x265b200_open(int(device), int(depth), C.byref(h))
+        if r != 0:
+            raise RuntimeError("x265b200_open(device=%d, depth=%d) failed with %d: no usable sm_100 GPU "
+                               "(the CUDA path has no CPU fallback)" % (device, depth, r))
+        self.h = h
+        self.host = HostAPI(self)
+
+    def close(self):
+        if self.h:
+            self.lib.x265b200_close(self.h)
+            self.h = None
+
+    def check(self):
+        st = self.lib.x265b200_status(self.h)
+        if st != 0:
+            raise RuntimeError("x265b200 error %d: %s" % (st, self.lib.x265b200_last_error(self.h).decode()))
+
+    def launch_count(self):
+        return int(self.lib.x265b200_launch_count(self.h))
+
+    def sm_count(self):
+        return int(self.lib.x265b200_sm_count(self.h))
+
+    def _call(self, name, *args):
+        r = getattr(self.lib, name)(self.h, *args)
+        if r != 0:
+            raise RuntimeError("%s failed (%d): %s" % (name, r, self.lib.x265b200_last_error(self.h).decode()))
+
+    # ---------------- batched device entries: torch CUDA tensors in, results written into `out`
+    def pixelcmp_batch(self, op, w, h, A, sa, B, sb, offA, offB, out, stream=0):
+        self._call("x265b200_pixelcmp_batch", op, w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
+                   int(offA.numel()), _dp(out), C.c_void_p(stream))
+
+    def sad_multi_batch(self, w, h, F, sf, R, sr, offF, offR, K, out, stream=0):
+        self._call("x265b200_sad_multi_batch", w, h, _dp(F), _ss(sf), _dp(R), _ss(sr), _dp(offF), _dp(offR), K,
+                   int(offF.numel()), _dp(out), C.c_void_p(stream))
+
+    def sse_ss_batch(self, w, h, A, sa, B, sb, offA, offB, out, stream=0):
+        self._call("x265b200_sse_ss_batch", w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
+                   int(offA.numel()), _dp(out), C.c_void_p(stream))
+
+    def ssd_s_batch(self, size, A, sa, offA, out, stream=0):
+        self._call("x265b200_ssd_s_batch", size, _dp(A), _ss(sa), _dp(offA), int(offA.numel()), _dp(out), C.c_void_p(stream))
+
+    def ads_batch(self, terms, half, encDC, sums, sumOff, delta, cost, costOff, width, thresh, mvs, pitch, count, stream=0):
+        self._call("x265b200_ads_batch", terms, half, _dp(encDC), _dp(sums), _dp(sumOff), _dp(delta), _dp(cost),
+                   _dp(costOff), _dp(width), _dp(thresh), int(sumOff.numel()), _dp(mvs), pitch, _dp(count), C.c_void_p(stream))
+
+    def dct_batch(self, kind, N, src, stride, off, dst, stream=0):
+        self._call("x265b200_dct_batch", kind, N, _dp(src), _ss(stride), _dp(off), int(off.numel()), _dp(dst), C.c_void_p(stream))
+
+    def idct_batch(self, kind, N, src, dst, stride, off, stream=0):
+        self._call("x265b200_idct_batch", kind, N, _dp(src), int(off.numel()), _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))
+
+    def quant_batch(self, coef, qc, deltaU, qCoef, qBits, add, numCoeff, n, numSig, stream=0):
+        self._call("x265b200_quant_batch", _dp(coef), _dp(qc), _dp(deltaU), _dp(qCoef), qBits, add, numCoeff, n,
+                   _dp(numSig), C.c_void_p(stream))
+
+    def dequant_normal_batch(self, q, coef, num, scale, shift, stream=0):
+        self._call("x265b200_dequant_normal_batch", _dp(q), _dp(coef), num, scale, shift, C.c_void_p(stream))
+
+    def dequant_scaling_batch(self, q, dq, coef, num, n, per, shift, stream=0):
+        self._call("x265b200_dequant_scaling_batch", _dp(q), _dp(dq), _dp(coef), num, n, per, shift, C.c_void_p(stream))
+
+    def interp_batch(self, kind, taps, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, stream=0):
+        self._call("x265b200_interp_batch", IP_KINDS[kind], taps, w, h, _dp(src), _ss(ss), _dp(offSrc), _dp(dst), _ss(ds),
+                   _dp(offDst), _dp(coeffIdx), int(offSrc.numel()), C.c_void_p(stream))
+
+    def residual_batch(self, w, h, A, sa, B, sb, offA, offB, dst, stream=0):
+        self._call("x265b200_residual_batch", w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
+                   int(offA.numel()), _dp(dst), C.c_void_p(stream))
+
+
+class HostAPI:
+    """Per-call host entries with numpy buffers; same method names as the CPU checkers in tests/ so the
+    reference-style parity cases can run against it unchanged."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.h = ctx.h
+        self.depth = ctx.depth
+        self.pix = ctx.pix
+        self.pmax = ctx.pmax
+
+    def _cmp(self, name, w, h, a, oa, sa, b, ob, sb):
+        r = getattr(self.lib, name)(self.h, w, h, _p(a, oa), _ss(sa), _p(b, ob), _ss(sb))
+        self.ctx.check()
+        return int(r)
+
+    def sad(self, w, h, a, oa, sa, b, ob, sb): return self._cmp("x265b200_sad", w, h, a, oa, sa, b, ob, sb)
+    def satd(self, w, h, a, oa, sa, b, ob, sb): return self._cmp("x265b200_satd", w, h, a, oa, sa, b, ob, sb)
+    def sa8d(self, w, h, a, oa, sa, b, ob, sb, chroma=0): return self._cmp("x265b200_sa8d", w, h, a, oa, sa, b, ob, sb)
+
+    def sse_pp(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
+        r = self._cmp("x265b200_sse_pp", w, h, a, oa, sa, b, ob, sb)
+        return r & 0xFFFFFFFF if self.depth == 8 else r         # sse_t is uint32 at 8 bit (common.h:145-149)
+
+    def sse_ss(self, w, a, oa, sa, b, ob, sb):
+        r = self._cmp("x265b200_sse_ss", w, w, a, oa, sa, b, ob, sb)
+        return r & 0xFFFFFFFF if self.depth == 8 else r
+
+    def ssd_s(self, size, a, oa, sa):
+        r = int(self.lib.x265b200_ssd_s(self.h, size, _p(a, oa), _ss(sa)))
+        self.ctx.check()
+        return r & 0xFFFFFFFF if self.depth == 8 else r
+
+    def sad_x3(self, w, h, fenc, of, ref, offs, rs):
+        res = np.zeros(3, np.int32)
+        self.lib.x265b200_sad_x3(self.h, w, h, _p(fenc, of), _p(ref, offs[0]), _p(ref, offs[1]), _p(ref, offs[2]), _ss(rs), _p(res))
+        self.ctx.check()
+        return res
+
+    def sad_x4(self, w, h, fenc, of, ref, offs, rs):
+        res = np.zeros(4, np.int32)
+        self.lib.x265b200_sad_x4(self.h, w, h, _p(fenc, of), _p(ref, offs[0]), _p(ref, offs[1]), _p(ref, offs[2]),
+                                 _p(ref, offs[3]), _ss(rs), _p(res))
+        self.ctx.check()
+        return res
+
+    def ads(self, w, h, encDC, sums, osum, delta, cost, width, thresh):
+        enc = np.ascontiguousarray(encDC, np.int32)
+        mvs = np.full(width + 8, -1, np.int16)
+        n = self.lib.x265b200_ads(self.h, w, h, _p(enc), _p(sums, osum), int(delta), _p(cost), _p(mvs), int(width), int(thresh))
+        self.ctx.check()
+        return n, mvs[:n].copy()
+
+    def dct(self, n, src, osrc, stride, kind=TR_DCT):
+        dst = np.zeros(n * n, np.int16)
+        self.lib.x265b200_dct(self.h, kind, n, _p(src, osrc), _p(dst), _ss(stride))
+        self.ctx.check()
+        return dst
+
+    def idct(self, n, src, stride, dst=None, odst=0, kind=TR_DCT):
+        if dst is None:
+            dst = np.zeros(n * stride, np.int16)
+        self.lib.x265b200_idct(self.h, kind, n, _p(src), _p(dst, odst), _ss(stride))
+        self.ctx.check()
+        return dst
+
+    def dst4(self, src, osrc, stride): return self.dct(4, src, osrc, stride, TR_DST)
+    def idst4(self, src, stride): return self.idct(4, src, stride, kind=TR_DST)
+
+    def lowpass_dct(self, n, src, osrc, stride):
+        dst = np.full(n * n, 0x5a5a, np.int16)
+        self.lib.x265b200_dct(self.h, TR_LOWPASS, n, _p(src, osrc), _p(dst), _ss(stride))
+        self.ctx.check()
+        return dst
+
+    def quant(self, coef, qc, qbits, add, n):
+        deltaU = np.zeros(n, np.int32)
+        q = np.zeros(n, np.int16)
+        r = self.lib.x265b200_quant(self.h, _p(coef), _p(qc), _p(deltaU), _p(q), qbits, add, n)
+        self.ctx.check()
+        return int(r), q, deltaU
+
+    def nquant(self, coef, qc, qbits, add, n):
+        q = np.zeros(n, np.int16)
+        r = self.lib.x265b200_nquant(self.h, _p(coef), _p(qc), _p(q), qbits, add, n)
+        self.ctx.check()
+        return int(r), q
+
+    def dequant_normal(self, q, n, scale, shift):
+        out = np.zeros(n, np.int16)
+        self.lib.x265b200_dequant_normal(self.h, _p(q), _p(out), n, scale, shift)
+        self.ctx.check()
+        return out
+
+    def dequant_scaling(self, q, dq, n, per, shift):
+        out = np.zeros(n, np.int16)
+        self.lib.x265b200_dequant_scaling(self.h, _p(q), _p(dq), _p(out), n, per, shift)
+        self.ctx.check()
+        return out
+
+    def interp(self, kind, N, w, h, src, os_, ss, dst, od, ds, idx, idy_or_ext=0):
+        self.lib.x265b200_interp(self.h, IP_KINDS[kind], N, w, h, _p(src, os_), _ss(ss), _p(dst, od), _ss(ds), idx, idy_or_ext)
+        self.ctx.check()
+        return 0
+
+    def p2s(self, w, h, src, os_, ss, dst, od, ds):
+        self.lib.x265b200_interp(self.h, IP_KINDS["p2s"], 8, w, h, _p(src, os_), _ss(ss), _p(dst, od), _ss(ds), 0, 0)
+        self.ctx.check()
+        return 0

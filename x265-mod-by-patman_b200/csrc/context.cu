@@ -1,0 +1,413 @@
+// context.cu -- context lifecycle and the per-call HOST entries (drop-in slot bodies).
+//
+// A host entry receives the raw host pointers/strides an EncoderPrimitives slot receives
+// (reference primitives.h:133-182), packs exactly the footprint the reference function would read
+// into pinned staging, copies it to the device, runs the SAME batched kernel the device entries
+// use with n = 1, copies the result back and writes exactly the cells the reference would write.
+// No CPU arithmetic on sample data happens here: a missing/failed device makes the call a no-op
+// that records a sticky error (x265b200_status), never a CPU fallback.
+#include "internal.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace b200 {
+
+int upload_transform_tables(x265b200_ctx* ctx);   // transform.cu
+int upload_filter_tables(x265b200_ctx* ctx);      // ipfilter.cu
+
+int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e)
+{
+    if (!ctx) return code;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    int expected = 0;
+    if (ctx->status.compare_exchange_strong(expected, code))
+    {
+        ctx->err = what;
+        if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+static Lane* lane_acquire(x265b200_ctx* ctx)
+{
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { fail(ctx, X265B200_ERR_CUDA, "cudaSetDevice"); return nullptr; }
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (!ctx->free_lanes.empty())
+        {
+            Lane* l = ctx->free_lanes.back();
+            ctx->free_lanes.pop_back();
+            return l;
+        }
+    }
+    Lane* l = new Lane();
+    cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h, LANE_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&l->d, LANE_BYTES);
+    if (e != cudaSuccess)
+    {
+        fail(ctx, X265B200_ERR_CUDA, "lane allocation", e);
+        if (l->h) cudaFreeHost(l->h);
+        if (l->stream) cudaStreamDestroy(l->stream);
+        delete l;
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->all_lanes.push_back(l);
+    return l;
+}
+
+static void lane_release(x265b200_ctx* ctx, Lane* l)
+{
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->free_lanes.push_back(l);
+}
+
+// One host call: bump-allocates matching host/device staging, then upload -> kernels -> download.
+struct Call
+{
+    x265b200_ctx* ctx;
+    Lane* lane;
+    size_t used = 0;
+    explicit Call(x265b200_ctx* c) : ctx(c), lane(c ? lane_acquire(c) : nullptr) {}
+    ~Call() { if (lane) lane_release(ctx, lane); }
+    bool ok() const { return lane != nullptr; }
+    size_t alloc(size_t bytes)
+    {
+        size_t off = (used + 63) & ~(size_t)63;
+        used = off + bytes;
+        if (used > LANE_BYTES) { fail(ctx, X265B200_ERR_ARG, "host call exceeds staging size"); lane_release(ctx, lane); lane = nullptr; return 0; }
+        return off;
+    }
+    template<typename T> T* h(size_t off) { return (T*)(lane->h + off); }
+    template<typename T> T* d(size_t off) { return (T*)(lane->d + off); }
+    cudaStream_t st() const { return lane->stream; }
+    bool upload(size_t off, size_t bytes)
+    {
+        cudaError_t e = cudaMemcpyAsync(lane->d + off, lane->h + off, bytes, cudaMemcpyHostToDevice, lane->stream);
+        if (e != cudaSuccess) { fail(ctx, X265B200_ERR_CUDA, "H2D", e); return false; }
+        return true;
+    }
+    bool download(size_t off, size_t bytes)
+    {
+        cudaError_t e = cudaMemcpyAsync(lane->h + off, lane->d + off, bytes, cudaMemcpyDeviceToHost, lane->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lane->stream);
+        if (e != cudaSuccess) { fail(ctx, X265B200_ERR_CUDA, "D2H", e); return false; }
+        return true;
+    }
+};
+
+// copy `rows` rows of `rowBytes` from a strided host block into packed staging
+static void pack(void* dst, const void* src, int rows, size_t rowBytes, intptr_t strideBytes)
+{
+    uint8_t* d = (uint8_t*)dst;
+    const uint8_t* s = (const uint8_t*)src;
+    for (int r = 0; r < rows; r++) memcpy(d + r * rowBytes, s + r * strideBytes, rowBytes);
+}
+static void unpack(void* dst, const void* src, int rows, size_t rowBytes, intptr_t strideBytes)
+{
+    uint8_t* d = (uint8_t*)dst;
+    const uint8_t* s = (const uint8_t*)src;
+    for (int r = 0; r < rows; r++) memcpy(d + r * strideBytes, s + r * rowBytes, rowBytes);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+// ------------------------------------------------------------------ lifecycle
+
+extern "C" int x265b200_open(int device, int bit_depth, x265b200_ctx** out)
+{
+    if (!out || (bit_depth != 8 && bit_depth != 10 && bit_depth != 12)) return X265B200_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return X265B200_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return X265B200_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return X265B200_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return X265B200_ERR_CUDA;
+    if (prop.major != 10)
+    {
+        fprintf(stderr, "x265b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+        return X265B200_ERR_NO_DEVICE;
+    }
+    x265b200_ctx* ctx = new x265b200_ctx();
+    ctx->device = device;
+    ctx->depth = bit_depth;
+    ctx->pixbytes = bit_depth == 8 ? 1 : 2;
+    ctx->sm_count = prop.multiProcessorCount;
+    int r = upload_transform_tables(ctx);
+    if (r == X265B200_OK) r = upload_filter_tables(ctx);
+    if (r != X265B200_OK) { fprintf(stderr, "x265b200: %s\n", ctx->err.c_str()); delete ctx; return r; }
+    *out = ctx;
+    return X265B200_OK;
+}
+
+extern "C" void x265b200_close(x265b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (Lane* l : ctx->all_lanes)
+    {
+        cudaStreamSynchronize(l->stream);
+        cudaFree(l->d);
+        cudaFreeHost(l->h);
+        cudaStreamDestroy(l->stream);
+        delete l;
+    }
+    delete ctx;
+}
+
+extern "C" int x265b200_bit_depth(const x265b200_ctx* ctx) { return ctx ? ctx->depth : 0; }
+extern "C" int x265b200_sm_count(const x265b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int x265b200_status(const x265b200_ctx* ctx) { return ctx ? ctx->status.load() : X265B200_ERR_ARG; }
+extern "C" const char* x265b200_last_error(const x265b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t x265b200_launch_count(const x265b200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+// ------------------------------------------------------------------ host entries: metrics
+
+// shared body of sad / satd / sa8d / sse_pp
+static uint64_t host_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    size_t pb = ctx->pixbytes, blk = (size_t)w * h * pb;
+    size_t oA = c.alloc(blk), oB = c.alloc(blk), oOff = c.alloc(8), oOut = c.alloc(8);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oA), a, h, w * pb, sa * pb);
+    pack(c.h<void>(oB), b, h, w * pb, sb * pb);
+    c.h<int32_t>(oOff)[0] = 0; c.h<int32_t>(oOff)[1] = 0;
+    if (!c.upload(0, oOff + 8)) return 0;
+    if (x265b200_pixelcmp_batch(ctx, op, w, h, c.d<void>(oA), w, c.d<void>(oB), w, c.d<int32_t>(oOff), c.d<int32_t>(oOff) + 1,
+                                1, c.d<void>(oOut), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oOut, 8)) return 0;
+    return op == X265B200_SSE_PP ? *c.h<uint64_t>(oOut) : (uint64_t)(int64_t)*c.h<int32_t>(oOut);
+}
+
+extern "C" int x265b200_sad(x265b200_ctx* ctx, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{ return (int)host_pixelcmp(ctx, X265B200_SAD, w, h, a, sa, b, sb); }
+extern "C" int x265b200_satd(x265b200_ctx* ctx, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{ return (int)host_pixelcmp(ctx, X265B200_SATD, w, h, a, sa, b, sb); }
+extern "C" int x265b200_sa8d(x265b200_ctx* ctx, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{ return (int)host_pixelcmp(ctx, X265B200_SA8D, w, h, a, sa, b, sb); }
+extern "C" uint64_t x265b200_sse_pp(x265b200_ctx* ctx, int w, int h, const void* a, intptr_t sa, const void* b, intptr_t sb)
+{ return host_pixelcmp(ctx, X265B200_SSE_PP, w, h, a, sa, b, sb); }
+
+extern "C" uint64_t x265b200_sse_ss(x265b200_ctx* ctx, int w, int h, const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    size_t blk = (size_t)w * h * 2;
+    size_t oA = c.alloc(blk), oB = c.alloc(blk), oOff = c.alloc(8), oOut = c.alloc(8);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oA), a, h, w * 2, sa * 2);
+    pack(c.h<void>(oB), b, h, w * 2, sb * 2);
+    c.h<int32_t>(oOff)[0] = 0; c.h<int32_t>(oOff)[1] = 0;
+    if (!c.upload(0, oOff + 8)) return 0;
+    if (x265b200_sse_ss_batch(ctx, w, h, c.d<int16_t>(oA), w, c.d<int16_t>(oB), w, c.d<int32_t>(oOff), c.d<int32_t>(oOff) + 1,
+                              1, c.d<uint64_t>(oOut), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oOut, 8)) return 0;
+    return *c.h<uint64_t>(oOut);
+}
+
+extern "C" uint64_t x265b200_ssd_s(x265b200_ctx* ctx, int size, const int16_t* a, intptr_t sa)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    size_t oA = c.alloc((size_t)size * size * 2), oOff = c.alloc(8), oOut = c.alloc(8);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oA), a, size, size * 2, sa * 2);
+    c.h<int32_t>(oOff)[0] = 0;
+    if (!c.upload(0, oOff + 8)) return 0;
+    if (x265b200_ssd_s_batch(ctx, size, c.d<int16_t>(oA), size, c.d<int32_t>(oOff), 1, c.d<uint64_t>(oOut), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oOut, 8)) return 0;
+    return *c.h<uint64_t>(oOut);
+}
+
+static void host_sad_xn(x265b200_ctx* ctx, int w, int h, int K, const void* fenc, const void* const* refs, intptr_t rs, int32_t* res)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t pb = ctx->pixbytes, blk = (size_t)w * h * pb;
+    size_t oF = c.alloc(blk), oR = c.alloc(blk * K), oOff = c.alloc(4 * (1 + K)), oOut = c.alloc(4 * K);
+    if (!c.ok()) return;
+    pack(c.h<void>(oF), fenc, h, w * pb, FENC_STRIDE * pb);                     // pixel.cpp:86 / :110
+    for (int k = 0; k < K; k++) pack(c.h<uint8_t>(oR) + k * blk, refs[k], h, w * pb, rs * pb);
+    int32_t* off = c.h<int32_t>(oOff);
+    off[0] = 0;
+    for (int k = 0; k < K; k++) off[1 + k] = k * w * h;
+    if (!c.upload(0, oOff + 4 * (1 + K))) return;
+    if (x265b200_sad_multi_batch(ctx, w, h, c.d<void>(oF), w, c.d<void>(oR), w, c.d<int32_t>(oOff), c.d<int32_t>(oOff) + 1,
+                                 K, 1, c.d<int32_t>(oOut), c.st()) != X265B200_OK) return;
+    if (!c.download(oOut, 4 * K)) return;
+    memcpy(res, c.h<int32_t>(oOut), 4 * K);
+}
+
+extern "C" void x265b200_sad_x3(x265b200_ctx* ctx, int w, int h, const void* fenc, const void* r0, const void* r1, const void* r2,
+                                intptr_t rs, int32_t* res)
+{ const void* r[3] = { r0, r1, r2 }; host_sad_xn(ctx, w, h, 3, fenc, r, rs, res); }
+extern "C" void x265b200_sad_x4(x265b200_ctx* ctx, int w, int h, const void* fenc, const void* r0, const void* r1, const void* r2,
+                                const void* r3, intptr_t rs, int32_t* res)
+{ const void* r[4] = { r0, r1, r2, r3 }; host_sad_xn(ctx, w, h, 4, fenc, r, rs, res); }
+
+// number of DC terms the reference binds to a w x h PU (pixel.cpp:1122-1146)
+static int ads_terms(int w, int h)
+{
+    static const struct { int w, h, k; } tab[] = {
+        {4,4,1},{8,8,1},{8,4,2},{4,8,2},{16,16,4},{16,8,2},{8,16,2},{16,12,1},{12,16,1},
+        {16,4,1},{4,16,1},{32,32,4},{32,16,2},{16,32,2},{32,24,4},{24,32,4},{32,8,4},{8,32,4},
+        {64,64,4},{64,32,2},{32,64,2},{64,48,4},{48,64,4},{64,16,4},{16,64,4} };
+    for (const auto& t : tab) if (t.w == w && t.h == h) return t.k;
+    return 0;
+}
+
+extern "C" int x265b200_ads(x265b200_ctx* ctx, int w, int h, const int* encDC, const uint32_t* sums, int delta,
+                            const uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{
+    int terms = ads_terms(w, h);
+    if (!terms || width <= 0) { if (!terms) fail(ctx, X265B200_ERR_ARG, "ads: not a PU size"); return 0; }
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    int half = terms == 4 ? w >> 1 : 0;
+    int seg = width + half;                                   // samples read from each of the two sum rows
+    size_t oEnc = c.alloc(16), oSum = c.alloc((size_t)seg * 8), oCost = c.alloc((size_t)width * 2), oJob = c.alloc(5 * 4);
+    size_t oMvs = c.alloc((size_t)width * 2), oCnt = c.alloc(4);
+    if (!c.ok()) return 0;
+    int32_t* e = c.h<int32_t>(oEnc);
+    for (int i = 0; i < 4; i++) e[i] = i < terms ? encDC[i] : 0;
+    memcpy(c.h<uint32_t>(oSum), sums, (size_t)seg * 4);
+    if (terms > 1) memcpy(c.h<uint32_t>(oSum) + seg, sums + delta, (size_t)seg * 4);
+    memcpy(c.h<void>(oCost), costMvX, (size_t)width * 2);
+    int32_t* job = c.h<int32_t>(oJob);
+    job[0] = 0; job[1] = seg; job[2] = 0; job[3] = width; job[4] = thresh;     // sumOff, delta, costOff, width, thresh
+    if (!c.upload(0, oJob + 20)) return 0;
+    int32_t* dj = c.d<int32_t>(oJob);
+    if (x265b200_ads_batch(ctx, terms, half, c.d<int32_t>(oEnc), c.d<uint32_t>(oSum), dj, dj + 1, c.d<uint16_t>(oCost), dj + 2,
+                           dj + 3, dj + 4, 1, c.d<int16_t>(oMvs), width, c.d<int32_t>(oCnt), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oMvs, oCnt + 4 - oMvs)) return 0;
+    int n = *c.h<int32_t>(oCnt);
+    memcpy(mvs, c.h<int16_t>(oMvs), (size_t)n * 2);
+    return n;
+}
+
+// ------------------------------------------------------------------ host entries: transforms
+
+extern "C" void x265b200_dct(x265b200_ctx* ctx, int kind, int N, const int16_t* src, int16_t* dst, intptr_t srcStride)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t blk = (size_t)N * N * 2;
+    size_t oS = c.alloc(blk), oOff = c.alloc(4), oD = c.alloc(blk);
+    if (!c.ok()) return;
+    pack(c.h<void>(oS), src, N, N * 2, srcStride * 2);
+    *c.h<int32_t>(oOff) = 0;
+    if (!c.upload(0, oOff + 4)) return;
+    if (x265b200_dct_batch(ctx, kind, N, c.d<int16_t>(oS), N, c.d<int32_t>(oOff), 1, c.d<int16_t>(oD), c.st()) != X265B200_OK) return;
+    if (!c.download(oD, blk)) return;
+    memcpy(dst, c.h<void>(oD), blk);
+}
+
+extern "C" void x265b200_idct(x265b200_ctx* ctx, int kind, int N, const int16_t* src, int16_t* dst, intptr_t dstStride)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t blk = (size_t)N * N * 2;
+    size_t oS = c.alloc(blk), oOff = c.alloc(4), oD = c.alloc(blk);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oS), src, blk);
+    *c.h<int32_t>(oOff) = 0;
+    if (!c.upload(0, oOff + 4)) return;
+    if (x265b200_idct_batch(ctx, kind, N, c.d<int16_t>(oS), 1, c.d<int16_t>(oD), N, c.d<int32_t>(oOff), c.st()) != X265B200_OK) return;
+    if (!c.download(oD, blk)) return;
+    unpack(dst, c.h<void>(oD), N, N * 2, dstStride * 2);
+}
+
+static uint32_t host_quant(x265b200_ctx* ctx, const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef,
+                           int qBits, int add, int numCoeff)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    size_t n = (size_t)numCoeff;
+    size_t oC = c.alloc(n * 2), oQ = c.alloc(n * 4), oIn = c.used;
+    size_t oOut = c.alloc(n * 2), oDu = c.alloc(n * 4), oSig = c.alloc(4);
+    if (!c.ok()) return 0;
+    memcpy(c.h<void>(oC), coef, n * 2);
+    memcpy(c.h<void>(oQ), qc, n * 4);
+    if (!c.upload(0, oIn)) return 0;
+    if (x265b200_quant_batch(ctx, c.d<int16_t>(oC), c.d<int32_t>(oQ), deltaU ? c.d<int32_t>(oDu) : nullptr, c.d<int16_t>(oOut),
+                             qBits, add, numCoeff, 1, c.d<uint32_t>(oSig), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oOut, oSig + 4 - oOut)) return 0;
+    memcpy(qCoef, c.h<void>(oOut), n * 2);
+    if (deltaU) memcpy(deltaU, c.h<void>(oDu), n * 4);
+    return *c.h<uint32_t>(oSig);
+}
+
+extern "C" uint32_t x265b200_quant(x265b200_ctx* ctx, const int16_t* coef, const int32_t* qc, int32_t* deltaU, int16_t* qCoef,
+                                   int qBits, int add, int numCoeff)
+{
+    if (!deltaU) { fail(ctx, X265B200_ERR_ARG, "quant: deltaU is NULL"); return 0; }
+    return host_quant(ctx, coef, qc, deltaU, qCoef, qBits, add, numCoeff);
+}
+extern "C" uint32_t x265b200_nquant(x265b200_ctx* ctx, const int16_t* coef, const int32_t* qc, int16_t* qCoef, int qBits, int add, int numCoeff)
+{ return host_quant(ctx, coef, qc, nullptr, qCoef, qBits, add, numCoeff); }
+
+extern "C" void x265b200_dequant_normal(x265b200_ctx* ctx, const int16_t* q, int16_t* coef, int num, int scale, int shift)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t oS = c.alloc((size_t)num * 2), oD = c.alloc((size_t)num * 2);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oS), q, (size_t)num * 2);
+    if (!c.upload(0, (size_t)num * 2)) return;
+    if (x265b200_dequant_normal_batch(ctx, c.d<int16_t>(oS), c.d<int16_t>(oD), num, scale, shift, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)num * 2)) return;
+    memcpy(coef, c.h<void>(oD), (size_t)num * 2);
+}
+
+extern "C" void x265b200_dequant_scaling(x265b200_ctx* ctx, const int16_t* q, const int32_t* dq, int16_t* coef, int num, int per, int shift)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t oS = c.alloc((size_t)num * 2), oT = c.alloc((size_t)num * 4), oIn = c.used, oD = c.alloc((size_t)num * 2);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oS), q, (size_t)num * 2);
+    memcpy(c.h<void>(oT), dq, (size_t)num * 4);
+    if (!c.upload(0, oIn)) return;
+    if (x265b200_dequant_scaling_batch(ctx, c.d<int16_t>(oS), c.d<int32_t>(oT), c.d<int16_t>(oD), num, 1, per, shift, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)num * 2)) return;
+    memcpy(coef, c.h<void>(oD), (size_t)num * 2);
+}
+
+// ------------------------------------------------------------------ host entries: interpolation
+
+extern "C" void x265b200_interp(x265b200_ctx* ctx, int kind, int taps, int w, int h, const void* src, intptr_t srcStride,
+                                void* dst, intptr_t dstStride, int coeffIdx, int extra)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const bool srcShort = kind == X265B200_IP_VSP || kind == X265B200_IP_VSS;
+    const bool dstShort = kind == X265B200_IP_HPS || kind == X265B200_IP_VPS || kind == X265B200_IP_VSS || kind == X265B200_IP_P2S;
+    const size_t sb = srcShort ? 2 : ctx->pixbytes, db = dstShort ? 2 : ctx->pixbytes;
+    const bool horiz = kind == X265B200_IP_HPP || kind == X265B200_IP_HPS || kind == X265B200_IP_HVPP;
+    const bool rowExt = kind == X265B200_IP_HVPP || (kind == X265B200_IP_HPS && extra);
+    const bool vert = kind == X265B200_IP_VPP || kind == X265B200_IP_VPS || kind == X265B200_IP_VSP || kind == X265B200_IP_VSS;
+    // footprint the reference reads: taps/2-1 before and taps/2 after along each filtered direction
+    int left = horiz ? taps / 2 - 1 : 0, right = horiz ? taps / 2 : 0;
+    int top = (vert || rowExt) ? taps / 2 - 1 : 0, bottom = (vert || rowExt) ? taps / 2 : 0;
+    int pw = w + left + right, ph = h + top + bottom;
+    int outRows = (kind == X265B200_IP_HPS && extra) ? h + taps - 1 : h;
+    size_t oS = c.alloc((size_t)pw * ph * sb), oJob = c.alloc(12), oD = c.alloc((size_t)w * outRows * db);
+    if (!c.ok()) return;
+    pack(c.h<void>(oS), (const uint8_t*)src - ((intptr_t)top * srcStride + left) * (intptr_t)sb, ph, pw * sb, srcStride * sb);
+    int32_t* job = c.h<int32_t>(oJob);
+    job[0] = top * pw + left;                                   // offSrc: the block origin inside the packed tile
+    job[1] = 0;                                                 // offDst
+    job[2] = kind == X265B200_IP_HVPP ? (coeffIdx | extra << 4) : (coeffIdx | (extra ? 1 << 8 : 0));
+    if (!c.upload(0, oJob + 12)) return;
+    int32_t* dj = c.d<int32_t>(oJob);
+    if (x265b200_interp_batch(ctx, kind, taps, w, h, c.d<void>(oS), pw, dj, c.d<void>(oD), w, dj + 1, dj + 2, 1, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)w * outRows * db)) return;
+    unpack(dst, c.h<void>(oD), outRows, w * db, dstStride * db);
+}

@@ -1,0 +1,63 @@
+// internal.h -- shared declarations of the B200 primitive library (not part of the C ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/x265b200.h"
+
+namespace b200 {
+
+constexpr int FENC_STRIDE = 64;             // common.h:71
+constexpr size_t LANE_BYTES = 1u << 20;     // staging per host-call lane (pinned + device)
+
+// One host-call lane: a stream plus pinned/device staging.  A thread that enters a host (per-call)
+// entry borrows a lane for the duration of the call, so slots are re-entrant from any number of
+// encoder worker threads without a global lock on the fast path (SURVEY.md 8b "Threading").
+struct Lane
+{
+    cudaStream_t stream = nullptr;
+    uint8_t* h = nullptr;       // pinned host staging
+    uint8_t* d = nullptr;       // device staging
+};
+
+} // namespace b200
+
+struct x265b200_ctx
+{
+    int device = 0;
+    int depth = 8;
+    int pixbytes = 1;
+    int sm_count = 0;
+    std::atomic<int> status{0};
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;
+    std::string err;
+    std::vector<b200::Lane*> free_lanes;
+    std::vector<b200::Lane*> all_lanes;
+};
+
+namespace b200 {
+
+int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess);
+
+#define B200_CUDA(ctx, call)                                                         \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) return b200::fail((ctx), X265B200_ERR_CUDA, #call, e__); \
+    } while (0)
+
+// checks the launch itself (configuration errors); asynchronous faults surface at the next sync
+#define B200_LAUNCH_CHECK(ctx)                                                       \
+    do {                                                                             \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                     \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) return b200::fail((ctx), X265B200_ERR_CUDA, "kernel launch", e__); \
+    } while (0)
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+} // namespace b200
