@@ -1,0 +1,150 @@
+// setup_b200_primitives.cpp -- binds x265's EncoderPrimitives slots to the B200 C ABI.
+//
+// This is the file a maintainer would add to the reference tree (e.g. source/common/b200/) next to
+// the AArch64 intrinsics filler it is modelled on (reference common/aarch64/asm-primitives.cpp:697-720):
+// it includes the reference's own primitives.h, so it is compiled once per bit depth / namespace
+// exactly like libx265 itself, and is called between setupAssemblyPrimitives() and
+// setupAliasPrimitives() (reference primitives.cpp:355-367).  See INTEGRATION.md.
+//
+// Every hot-path slot gets a thunk with the exact typedef'd signature
+// (primitives.h:133-182) that forwards to the per-call host entry of include/x265b200.h with the
+// block size baked in as a template argument -- the same way the reference bakes it into
+// sad<W, H> etc.  Slots outside the hot path are left untouched.
+#include "common.h"
+#include "primitives.h"
+#include "x265b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace X265_NS {
+
+static x265b200_ctx* g_b200;    // one context per process and depth, like the global `primitives` table
+
+namespace {
+
+// ---- metrics ----
+template<int W, int H> int t_sad(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return x265b200_sad(g_b200, W, H, a, sa, b, sb); }
+template<int W, int H> int t_satd(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return x265b200_satd(g_b200, W, H, a, sa, b, sb); }
+template<int W, int H> int t_sa8d(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return x265b200_sa8d(g_b200, W, H, a, sa, b, sb); }
+template<int W, int H> sse_t t_sse_pp(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return (sse_t)x265b200_sse_pp(g_b200, W, H, a, sa, b, sb); }
+template<int W, int H> sse_t t_sse_ss(const int16_t* a, intptr_t sa, const int16_t* b, intptr_t sb) { return (sse_t)x265b200_sse_ss(g_b200, W, H, a, sa, b, sb); }
+template<int W> sse_t t_ssd_s(const int16_t* a, intptr_t sa) { return (sse_t)x265b200_ssd_s(g_b200, W, a, sa); }
+template<int W, int H> void t_sad_x3(const pixel* f, const pixel* r0, const pixel* r1, const pixel* r2, intptr_t rs, int32_t* res)
+{ x265b200_sad_x3(g_b200, W, H, f, r0, r1, r2, rs, res); }
+template<int W, int H> void t_sad_x4(const pixel* f, const pixel* r0, const pixel* r1, const pixel* r2, const pixel* r3, intptr_t rs, int32_t* res)
+{ x265b200_sad_x4(g_b200, W, H, f, r0, r1, r2, r3, rs, res); }
+template<int W, int H> int t_ads(int encDC[], uint32_t* sums, int delta, uint16_t* costMvX, int16_t* mvs, int width, int thresh)
+{ return x265b200_ads(g_b200, W, H, encDC, sums, delta, costMvX, mvs, width, thresh); }
+
+// ---- transforms ----
+template<int N> void t_dct(const int16_t* s, int16_t* d, intptr_t st) { x265b200_dct(g_b200, X265B200_TR_DCT, N, s, d, st); }
+template<int N> void t_idct(const int16_t* s, int16_t* d, intptr_t st) { x265b200_idct(g_b200, X265B200_TR_DCT, N, s, d, st); }
+template<int N> void t_lowpass(const int16_t* s, int16_t* d, intptr_t st) { x265b200_dct(g_b200, X265B200_TR_LOWPASS, N, s, d, st); }
+void t_dst4(const int16_t* s, int16_t* d, intptr_t st) { x265b200_dct(g_b200, X265B200_TR_DST, 4, s, d, st); }
+void t_idst4(const int16_t* s, int16_t* d, intptr_t st) { x265b200_idct(g_b200, X265B200_TR_DST, 4, s, d, st); }
+uint32_t t_quant(const int16_t* c, const int32_t* q, int32_t* du, int16_t* qc, int qBits, int add, int n) { return x265b200_quant(g_b200, c, q, du, qc, qBits, add, n); }
+uint32_t t_nquant(const int16_t* c, const int32_t* q, int16_t* qc, int qBits, int add, int n) { return x265b200_nquant(g_b200, c, q, qc, qBits, add, n); }
+void t_dequant_normal(const int16_t* q, int16_t* c, int num, int scale, int shift) { x265b200_dequant_normal(g_b200, q, c, num, scale, shift); }
+void t_dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* c, int num, int per, int shift) { x265b200_dequant_scaling(g_b200, q, dq, c, num, per, shift); }
+
+// ---- interpolation ----
+template<int T, int W, int H> void t_hpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_HPP, T, W, H, s, ss, d, ds, idx, 0); }
+template<int T, int W, int H> void t_hps(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int idx, int ext) { x265b200_interp(g_b200, X265B200_IP_HPS, T, W, H, s, ss, d, ds, idx, ext); }
+template<int T, int W, int H> void t_vpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_VPP, T, W, H, s, ss, d, ds, idx, 0); }
+template<int T, int W, int H> void t_vps(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_VPS, T, W, H, s, ss, d, ds, idx, 0); }
+template<int T, int W, int H> void t_vsp(const int16_t* s, intptr_t ss, pixel* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_VSP, T, W, H, s, ss, d, ds, idx, 0); }
+template<int T, int W, int H> void t_vss(const int16_t* s, intptr_t ss, int16_t* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_VSS, T, W, H, s, ss, d, ds, idx, 0); }
+template<int W, int H> void t_hvpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int ix, int iy) { x265b200_interp(g_b200, X265B200_IP_HVPP, 8, W, H, s, ss, d, ds, ix, iy); }
+template<int W, int H> void t_p2s(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds) { x265b200_interp(g_b200, X265B200_IP_P2S, 8, W, H, s, ss, d, ds, 0, 0); }
+
+template<int W, int H> void lumaPU(EncoderPrimitives::PU& pu)
+{
+    pu.sad = t_sad<W, H>; pu.sad_x3 = t_sad_x3<W, H>; pu.sad_x4 = t_sad_x4<W, H>; pu.ads = t_ads<W, H>; pu.satd = t_satd<W, H>;
+    pu.luma_hpp = t_hpp<8, W, H>; pu.luma_hps = t_hps<8, W, H>; pu.luma_vpp = t_vpp<8, W, H>; pu.luma_vps = t_vps<8, W, H>;
+    pu.luma_vsp = t_vsp<8, W, H>; pu.luma_vss = t_vss<8, W, H>; pu.luma_hvpp = t_hvpp<W, H>;
+    pu.convert_p2s[NONALIGNED] = t_p2s<W, H>; pu.convert_p2s[ALIGNED] = t_p2s<W, H>;
+}
+
+// chroma PU of size W x H (already subsampled); satd only where the reference has one (dims % 4 == 0)
+template<int W, int H> void chromaPU(EncoderPrimitives::Chroma::PUChroma& pu)
+{
+    pu.filter_hpp = t_hpp<4, W, H>; pu.filter_hps = t_hps<4, W, H>; pu.filter_vpp = t_vpp<4, W, H>; pu.filter_vps = t_vps<4, W, H>;
+    pu.filter_vsp = t_vsp<4, W, H>; pu.filter_vss = t_vss<4, W, H>;
+    pu.p2s[NONALIGNED] = t_p2s<W, H>; pu.p2s[ALIGNED] = t_p2s<W, H>;
+    pu.satd = (W % 4 == 0 && H % 4 == 0) ? (pixelcmp_t)t_satd<(W % 4 ? 4 : W), (H % 4 ? 4 : H)> : NULL;
+}
+
+template<int W> void lumaCU(EncoderPrimitives::CU& cu)
+{
+    cu.sse_pp = t_sse_pp<W, W>; cu.sse_ss = t_sse_ss<W, W>; cu.sa8d = t_sa8d<W, W>;
+    cu.ssd_s[NONALIGNED] = t_ssd_s<W>; cu.ssd_s[ALIGNED] = t_ssd_s<W>;
+}
+template<int W, int H> void chromaCU(EncoderPrimitives::Chroma::CUChroma& cu)
+{
+    cu.sa8d = t_sa8d<W, H>; cu.sse_pp = t_sse_pp<W, H>;
+}
+
+} // anonymous namespace
+
+#define FOR_ALL_LUMA_PU(X) \
+    X(4, 4) X(8, 8) X(16, 16) X(32, 32) X(64, 64) X(8, 4) X(4, 8) X(16, 8) X(8, 16) X(32, 16) X(16, 32) X(64, 32) X(32, 64) \
+    X(16, 12) X(12, 16) X(16, 4) X(4, 16) X(32, 24) X(24, 32) X(32, 8) X(8, 32) X(64, 48) X(48, 64) X(64, 16) X(16, 64)
+
+void setupB200Primitives(EncoderPrimitives& p)
+{
+#define L(W, H) lumaPU<W, H>(p.pu[LUMA_ ## W ## x ## H]);
+    FOR_ALL_LUMA_PU(L)
+#undef L
+    // 4:4:4 chroma filters use luma block sizes with the 4-tap kernel (ipfilter.cpp:391-399); the rest
+    // of the 4:4:4 table is aliased from luma by setupAliasPrimitives (primitives.cpp:185-206)
+#define C444(W, H) { pixelcmp_t keep = p.chroma[X265_CSP_I444].pu[LUMA_ ## W ## x ## H].satd; \
+                     chromaPU<W, H>(p.chroma[X265_CSP_I444].pu[LUMA_ ## W ## x ## H]); (void)keep; }
+    FOR_ALL_LUMA_PU(C444)
+#undef C444
+    // 4:2:0: chroma PU = (W/2) x (H/2); the reference has no entry for luma 4x4 (ipfilter.cpp:414-462)
+#define C420(W, H) if (W > 4 || H > 4) chromaPU<(W) / 2, (H) / 2>(p.chroma[X265_CSP_I420].pu[LUMA_ ## W ## x ## H]);
+    FOR_ALL_LUMA_PU(C420)
+#undef C420
+    // 4:2:2: chroma PU = (W/2) x H
+#define C422(W, H) chromaPU<(W) / 2, H>(p.chroma[X265_CSP_I422].pu[LUMA_ ## W ## x ## H]);
+    FOR_ALL_LUMA_PU(C422)
+#undef C422
+
+    lumaCU<4>(p.cu[BLOCK_4x4]); lumaCU<8>(p.cu[BLOCK_8x8]); lumaCU<16>(p.cu[BLOCK_16x16]);
+    lumaCU<32>(p.cu[BLOCK_32x32]); lumaCU<64>(p.cu[BLOCK_64x64]);
+
+    // chroma CU slots the alias pass does not derive from luma (pixel.cpp:1260-1263,1325,1339-1342)
+    chromaCU<4, 4>(p.chroma[X265_CSP_I420].cu[BLOCK_8x8]);   chromaCU<8, 8>(p.chroma[X265_CSP_I420].cu[BLOCK_16x16]);
+    chromaCU<16, 16>(p.chroma[X265_CSP_I420].cu[BLOCK_32x32]); chromaCU<32, 32>(p.chroma[X265_CSP_I420].cu[BLOCK_64x64]);
+    chromaCU<4, 8>(p.chroma[X265_CSP_I422].cu[BLOCK_8x8]);   chromaCU<8, 16>(p.chroma[X265_CSP_I422].cu[BLOCK_16x16]);
+    chromaCU<16, 32>(p.chroma[X265_CSP_I422].cu[BLOCK_32x32]); chromaCU<32, 64>(p.chroma[X265_CSP_I422].cu[BLOCK_64x64]);
+
+    p.cu[BLOCK_4x4].dct = t_dct<4>;     p.cu[BLOCK_4x4].idct = t_idct<4>;
+    p.cu[BLOCK_8x8].dct = t_dct<8>;     p.cu[BLOCK_8x8].idct = t_idct<8>;
+    p.cu[BLOCK_16x16].dct = t_dct<16>;  p.cu[BLOCK_16x16].idct = t_idct<16>;
+    p.cu[BLOCK_32x32].dct = t_dct<32>;  p.cu[BLOCK_32x32].idct = t_idct<32>;
+    p.cu[BLOCK_8x8].lowpass_dct = t_lowpass<8>;
+    p.cu[BLOCK_16x16].lowpass_dct = t_lowpass<16>;
+    p.cu[BLOCK_32x32].lowpass_dct = t_lowpass<32>;
+    p.dst4x4 = t_dst4;  p.idst4x4 = t_idst4;
+    p.quant = t_quant;  p.nquant = t_nquant;
+    p.dequant_normal = t_dequant_normal;  p.dequant_scaling = t_dequant_scaling;
+}
+
+} // namespace X265_NS
+
+// C handle for drivers that cannot name the C++ symbol: opens the context (once) and fills `table`,
+// which must point at an EncoderPrimitives of this build's bit depth.  Returns 0 or an X265B200_ERR_*.
+extern "C" int x265b200_setup_primitives(void* table, int device)
+{
+    if (!X265_NS::g_b200)
+    {
+        int r = x265b200_open(device, X265_DEPTH, &X265_NS::g_b200);
+        if (r != X265B200_OK) return r;
+    }
+    X265_NS::setupB200Primitives(*(X265_NS::EncoderPrimitives*)table);
+    return X265B200_OK;
+}
+extern "C" x265b200_ctx* x265b200_glue_context(void) { return X265_NS::g_b200; }
+extern "C" int x265b200_glue_depth(void) { return X265_DEPTH; }
