@@ -62,6 +62,79 @@ __device__ __forceinline__ void load4(const int16_t* p, int (&v)[4])
     }
 }
 
+// ---- fast tile loads (throughput kernels) -------------------------------------------------------
+// Four rows of four horizontally adjacent samples, returned as packed 16-bit pairs
+// (lo[r] = samples 0,1 ; hi[r] = samples 2,3 of row r).  The row stride must be a multiple of four
+// samples (every x265 plane and every staging tile is), so the misalignment of the tile against
+// the 8-byte (16-bit samples) / 4-byte (8-bit samples) grid is the same for all rows: the kernel
+// issues ALL aligned chunk loads of the tile back to back (no data-dependent code in between, so
+// they overlap in flight) and then realigns with funnel shifts.  Only chunks that contain at least
+// one requested sample are touched.
+__device__ __forceinline__ void load_tile4x4(const uint16_t* p, intptr_t stride, uint32_t (&lo)[4], uint32_t (&hi)[4])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)(a >> 1) & 3;                              // misalignment in samples
+    const uint2* base = (const uint2*)(a & ~(uintptr_t)7);
+    intptr_t cs = stride >> 2;                              // row stride in 8-byte chunks
+    uint2 q0[4], q1[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) q0[r] = __ldg(base + r * cs);
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) q1[r] = __ldg(base + r * cs + 1);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) q1[r] = make_uint2(0, 0);
+    }
+    int sh = (s & 1) << 4;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        uint32_t w0 = q0[r].x, w1 = q0[r].y, w2 = q1[r].x, w3 = q1[r].y;
+        if (s & 2) { w0 = w1; w1 = w2; w2 = w3; }
+        lo[r] = __funnelshift_r(w0, w1, sh);
+        hi[r] = __funnelshift_r(w1, w2, sh);
+    }
+}
+
+__device__ __forceinline__ void load_tile4x4(const uint8_t* p, intptr_t stride, uint32_t (&lo)[4], uint32_t (&hi)[4])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)a & 3;
+    const uint32_t* base = (const uint32_t*)(a & ~(uintptr_t)3);
+    intptr_t cs = stride >> 2;
+    uint32_t c0[4], c1[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) c0[r] = __ldg(base + r * cs);
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) c1[r] = __ldg(base + r * cs + 1);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) c1[r] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        uint32_t w = __funnelshift_r(c0[r], c1[r], s << 3);
+        lo[r] = __byte_perm(w, 0, 0x4140);                 // bytes 0,1 -> 16-bit lanes
+        hi[r] = __byte_perm(w, 0, 0x4342);                 // bytes 2,3
+    }
+}
+
+// packed signed pair x + (y << 16) (as produced by subtracting two packed unsigned pairs) -> x, y
+__device__ __forceinline__ void unpack_s16x2(uint32_t w, int& x, int& y)
+{
+    x = (int)(int16_t)(w & 0xffff);
+    y = (int)(w + 0x8000u) >> 16;                          // +0x8000 undoes the borrow a negative x took
+}
+
 // butterfly sum over the low `lanes` (power of two <= 32) lanes of each aligned lane group
 template<typename T>
 __device__ __forceinline__ T group_sum(T v, int lanes)
