@@ -1,0 +1,103 @@
+// satd_lab.cu -- tuning lab for the SATD throughput kernel: instantiates variants of
+// csrc/tile_kernels.cuh side by side on 2160p10-shaped planes, checks that they agree, prints ms.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I x265-mod-by-patman_b200/csrc tools/satd_lab.cu -o tools/satd_lab
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "tile_kernels.cuh"
+
+using namespace b200;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+static uint64_t splitmix(uint64_t z) { z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+
+__global__ void fill(uint16_t* p, size_t n, uint64_t seed)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t z = i + seed; z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    p[i] = (uint16_t)(z & 1023);
+}
+
+typedef void (*kern_t)(const uint16_t*, intptr_t, const uint16_t*, intptr_t, const int32_t*, const int32_t*, int, int, int, int, int, int32_t*);
+
+struct Variant { const char* name; kern_t k; int threads; };
+
+int main(int argc, char** argv)
+{
+    const int F = 8, W = 3840, H = 2176, stride = 4032, rows = 2336, mx = 96, my = 80;
+    const size_t pe = (size_t)stride * rows;
+    uint16_t *A, *B;
+    CK(cudaMalloc(&A, F * pe * 2)); CK(cudaMalloc(&B, F * pe * 2));
+    fill<<<(F * pe + 255) / 256, 256>>>(A, F * pe, 1); fill<<<(F * pe + 255) / 256, 256>>>(B, F * pe, 77);
+    CK(cudaDeviceSynchronize());
+    Variant vars[] = {
+        { "u1 natural regs, 256 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 256 },
+        { "u1 natural regs, 128 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128 },
+        { "u1 minblk 6 (<=40 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 6>, 256 },
+        { "u1 minblk 8 (<=32 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 8>, 256 },
+        { "u2 natural regs", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 256 },
+        { "u2 minblk 4 (<=64 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 4>, 256 },
+        { "u2 minblk 5 (<=48 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 5>, 256 },
+        { "u2 minblk 6 (<=40 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 6>, 256 },
+    };
+    const int NV = sizeof(vars) / sizeof(vars[0]);
+    for (int v = 0; v < NV; v++)
+    {
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void*)vars[v].k));
+        printf("variant %d: %-28s regs %d\n", v, vars[v].name, fa.numRegs);
+    }
+    int shapes[][2] = { {64, 64}, {64, 32}, {32, 32}, {16, 16}, {8, 8}, {4, 8} };
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (auto& sh : shapes)
+    {
+        int w = sh[0], h = sh[1];
+        std::vector<int32_t> oa, ob;
+        for (int f = 0; f < F; f++)
+            for (int y = 0; y < H; y += h)
+                for (int x = 0; x < W; x += w)
+                {
+                    uint64_t r = splitmix(oa.size() * 31 + w * 7 + h);
+                    int mvx = (int)(r % 115) - 57, mvy = (int)((r >> 20) % 115) - 57;
+                    int rx = x + mvx, ry = y + mvy;
+                    if (rx < -mx + 8) rx = -mx + 8; if (rx > W + mx - w - 8) rx = W + mx - w - 8;
+                    if (ry < -my + 8) ry = -my + 8; if (ry > H + my - h - 8) ry = H + my - h - 8;
+                    oa.push_back((int32_t)(f * pe + (size_t)(my + y) * stride + mx + x));
+                    ob.push_back((int32_t)(f * pe + (size_t)(my + ry) * stride + mx + rx));
+                }
+        int n = (int)oa.size();
+        int32_t *dOA, *dOB, *out0, *out;
+        CK(cudaMalloc(&dOA, n * 4)); CK(cudaMalloc(&dOB, n * 4)); CK(cudaMalloc(&out0, n * 4)); CK(cudaMalloc(&out, n * 4));
+        CK(cudaMemcpy(dOA, oa.data(), n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dOB, ob.data(), n * 4, cudaMemcpyHostToDevice));
+        int T4 = (w / 4) * (h / 4), G = 1; while (G < T4 && G < 32) G <<= 1;
+        double bytes = (double)n * w * h * 4 + n * 4.0;
+        printf("shape %dx%d  n=%d  G=%d  (roofline 6534.8 GB/s -> %.4f ms)\n", w, h, n, G, bytes / 6534.8e9 * 1e3);
+        std::vector<int32_t> h0(n), h1(n);
+        for (int v = 0; v < NV; v++)
+        {
+            int32_t* o = v == 0 ? out0 : out;
+            long long threads = (long long)n * G;
+            int grid = (int)((threads + vars[v].threads - 1) / vars[v].threads);
+            float best = 1e9f;
+            for (int rep = 0; rep < 6; rep++)
+            {
+                CK(cudaEventRecord(e0));
+                vars[v].k<<<grid, vars[v].threads>>>(A, stride, B, stride, dOA, dOB, 1, n, w, h, G, o);
+                CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep >= 2 && ms < best) best = ms;
+            }
+            CK(cudaGetLastError());
+            bool same = true;
+            if (v > 0)
+            {
+                CK(cudaMemcpy(h0.data(), out0, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h1.data(), out, n * 4, cudaMemcpyDeviceToHost));
+                for (int i = 0; i < n; i++) if (h0[i] != h1[i]) { same = false; break; }
+            }
+            printf("   v%d %-28s %.4f ms  %.0f GB/s  %.2f of roofline %s\n", v, vars[v].name, best, bytes / best / 1e6, bytes / best / 1e6 / 6534.8, same ? "" : "MISMATCH");
+        }
+        cudaFree(dOA); cudaFree(dOB); cudaFree(out0); cudaFree(out);
+    }
+    return 0;
+}

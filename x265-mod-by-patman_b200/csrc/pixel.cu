@@ -10,10 +10,10 @@
 // load covers whole 128-byte lines of the plane.
 #include "internal.h"
 #include "device_util.cuh"
+#include "tile_kernels.cuh"
 
 namespace b200 {
 
-enum { OP_SAD = 0, OP_SATD = 1, OP_SA8D = 2, OP_SSE = 3, OP_SSD = 4 };
 
 __device__ __forceinline__ int hadamard4x4_abs(int (&d)[4][4])
 {
@@ -136,81 +136,6 @@ tile4_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intp
             for (int y = 0; y < 4; y++)
 #pragma unroll
                 for (int x = 0; x < 4; x++) acc += (ACC)(long long)(int)((unsigned)d[y][x] * (unsigned)d[y][x]);
-        }
-    }
-    acc = group_sum(acc, G);
-    if (live && l == 0) out[blk] = (OUT)acc;
-}
-
-// Throughput version of SAD / SATD / SSE for pixel planes whose strides are multiples of 4 samples.
-// Differences are formed on packed 16-bit pairs (one IADD per two samples, no unpacking of the
-// inputs); for SATD the vertical 4-point Hadamard also runs packed (|value| <= 4 * 4095 fits a
-// 16-bit lane at every depth), then the eight words are unpacked once for the horizontal pass.
-template<typename T, int OP, typename ACC, typename OUT>
-__global__ void __launch_bounds__(256)
-tile4_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
-                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB, int kdiv,
-                  int n, int w, int h, int G, OUT* __restrict__ out)
-{
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int lg = __ffs(G) - 1;                                  // G is a power of two
-    int blk = (int)(gid >> lg);
-    int l = (int)gid & (G - 1);
-    bool live = blk < n;
-    int tw = w >> 2;
-    int T4 = tw * (h >> 2);
-    // tile coordinates advance incrementally (no division in the loop)
-    int tx = l % tw, ty = l / tw;
-    int dx = G % tw, dy = G / tw;
-    const T* a = A;
-    const T* b = B;
-    if (live)
-    {
-        a += offA[kdiv > 1 ? blk / kdiv : blk];
-        b += offB[blk];
-    }
-    ACC acc = 0;
-    for (int t = l; t < T4; t += G)
-    {
-        if (!live) break;
-        uint32_t alo[4], ahi[4], blo[4], bhi[4];
-        load_tile4x4(a + (intptr_t)(ty << 2) * sa + (tx << 2), sa, alo, ahi);
-        load_tile4x4(b + (intptr_t)(ty << 2) * sb + (tx << 2), sb, blo, bhi);
-        tx += dx; ty += dy;
-        if (tx >= tw) { tx -= tw; ty++; }
-        uint32_t dl[4], dh[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) { dl[r] = alo[r] - blo[r]; dh[r] = ahi[r] - bhi[r]; }
-        if (OP == OP_SATD)
-        {
-            // vertical Hadamard on packed columns (0,1) and (2,3)
-            uint32_t s0 = dl[0] + dl[1], s1 = dl[0] - dl[1], s2 = dl[2] + dl[3], s3 = dl[2] - dl[3];
-            dl[0] = s0 + s2; dl[1] = s1 + s3; dl[2] = s0 - s2; dl[3] = s1 - s3;
-            s0 = dh[0] + dh[1]; s1 = dh[0] - dh[1]; s2 = dh[2] + dh[3]; s3 = dh[2] - dh[3];
-            dh[0] = s0 + s2; dh[1] = s1 + s3; dh[2] = s0 - s2; dh[3] = s1 - s3;
-            int sum = 0;
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                int x0, x1, x2, x3;
-                unpack_s16x2(dl[r], x0, x1);
-                unpack_s16x2(dh[r], x2, x3);
-                int u0 = x0 + x1, u1 = x0 - x1, u2 = x2 + x3, u3 = x2 - x3;
-                sum += abs(u0 + u2) + abs(u1 + u3) + abs(u0 - u2) + abs(u1 - u3);
-            }
-            acc += sum >> 1;
-        }
-        else
-        {
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                int x0, x1, x2, x3;
-                unpack_s16x2(dl[r], x0, x1);
-                unpack_s16x2(dh[r], x2, x3);
-                if (OP == OP_SAD) acc += abs(x0) + abs(x1) + abs(x2) + abs(x3);
-                else acc += (ACC)(x0 * x0 + x1 * x1) + (ACC)(x2 * x2 + x3 * x3);   // |x| <= 4095: no int overflow
-            }
         }
     }
     acc = group_sum(acc, G);
@@ -372,14 +297,14 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
         switch (op)
         {
         case X265B200_SAD:
-            tile4_fast_kernel<T, OP_SAD, int, int32_t><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
+            tile4_fast_kernel<T, OP_SAD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
             break;
         case X265B200_SATD:
         case X265B200_SA8D:
-            tile4_fast_kernel<T, OP_SATD, int, int32_t><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
+            tile4_fast_kernel<T, OP_SATD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
             break;
         case X265B200_SSE_PP:
-            tile4_fast_kernel<T, OP_SSE, unsigned long long, unsigned long long><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (unsigned long long*)out);
+            tile4_fast_kernel<T, OP_SSE, unsigned long long, unsigned long long, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (unsigned long long*)out);
             break;
         default:
             return fail(ctx, X265B200_ERR_ARG, "pixelcmp: unknown op");

@@ -1,0 +1,116 @@
+// tile_kernels.cuh -- throughput kernels for SAD / SATD / SSE over pixel planes (shared by pixel.cu
+// and the tuning lab tools/satd_lab.cu, which instantiates the variants side by side).
+#pragma once
+#include "device_util.cuh"
+
+namespace b200 {
+
+enum { OP_SAD = 0, OP_SATD = 1, OP_SA8D = 2, OP_SSE = 3, OP_SSD = 4 };
+
+// configuration used by the library (chosen with tools/satd_lab.cu on B200, see profiles/)
+constexpr int FAST_UNROLL = 1;
+constexpr int FAST_MINBLK = 1;
+
+template<int OP, typename ACC>
+__device__ __forceinline__ void tile4_accumulate(const uint32_t (&alo)[4], const uint32_t (&ahi)[4],
+                                                 const uint32_t (&blo)[4], const uint32_t (&bhi)[4], ACC& acc)
+{
+    uint32_t dl[4], dh[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { dl[r] = alo[r] - blo[r]; dh[r] = ahi[r] - bhi[r]; }
+    if (OP == OP_SATD)
+    {
+        // vertical Hadamard on packed columns (0,1) and (2,3)
+        uint32_t s0 = dl[0] + dl[1], s1 = dl[0] - dl[1], s2 = dl[2] + dl[3], s3 = dl[2] - dl[3];
+        dl[0] = s0 + s2; dl[1] = s1 + s3; dl[2] = s0 - s2; dl[3] = s1 - s3;
+        s0 = dh[0] + dh[1]; s1 = dh[0] - dh[1]; s2 = dh[2] + dh[3]; s3 = dh[2] - dh[3];
+        dh[0] = s0 + s2; dh[1] = s1 + s3; dh[2] = s0 - s2; dh[3] = s1 - s3;
+        int sum = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            int x0, x1, x2, x3;
+            unpack_s16x2(dl[r], x0, x1);
+            unpack_s16x2(dh[r], x2, x3);
+            int u0 = x0 + x1, u1 = x0 - x1, u2 = x2 + x3, u3 = x2 - x3;
+            sum += abs(u0 + u2) + abs(u1 + u3) + abs(u0 - u2) + abs(u1 - u3);
+        }
+        acc += sum >> 1;       // per-tile halving == the reference's 8x4 pairing (raw tile sums are even)
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            int x0, x1, x2, x3;
+            unpack_s16x2(dl[r], x0, x1);
+            unpack_s16x2(dh[r], x2, x3);
+            if (OP == OP_SAD) acc += abs(x0) + abs(x1) + abs(x2) + abs(x3);
+            else acc += (ACC)(x0 * x0 + x1 * x1) + (ACC)(x2 * x2 + x3 * x3);   // |x| <= 4095: no int overflow
+        }
+    }
+}
+
+// Differences are formed on packed 16-bit pairs (one IADD per two samples, no unpacking of the
+// inputs); for SATD the vertical 4-point Hadamard also runs packed (|value| <= 4 * 4095 fits a
+// 16-bit lane at every depth), then the eight words are unpacked once for the horizontal pass.
+// Plane strides must be multiples of 4 samples.  UNROLL tiles are loaded before any is consumed.
+template<typename T, int OP, typename ACC, typename OUT, int UNROLL, int MINBLK>
+__global__ void __launch_bounds__(256, MINBLK)
+tile4_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
+                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB, int kdiv,
+                  int n, int w, int h, int G, OUT* __restrict__ out)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lg = __ffs(G) - 1;                                  // G is a power of two
+    int blk = (int)(gid >> lg);
+    int l = (int)gid & (G - 1);
+    bool live = blk < n;
+    int tw = w >> 2;
+    int T4 = tw * (h >> 2);
+    const T* a = A;
+    const T* b = B;
+    if (live)
+    {
+        a += offA[kdiv > 1 ? blk / kdiv : blk];
+        b += offB[blk];
+    }
+    // tile coordinates advance incrementally (no division in the loop)
+    int tx = l % tw, ty = l / tw;
+    int dx = G % tw, dy = G / tw;
+    ACC acc = 0;
+    if (live)
+    {
+        int t = l;
+        if (UNROLL == 2)
+        {
+            for (; t + G < T4; t += 2 * G)
+            {
+                uint32_t alo[2][4], ahi[2][4], blo[2][4], bhi[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    load_tile4x4(a + (intptr_t)(ty << 2) * sa + (tx << 2), sa, alo[u], ahi[u]);
+                    load_tile4x4(b + (intptr_t)(ty << 2) * sb + (tx << 2), sb, blo[u], bhi[u]);
+                    tx += dx; ty += dy;
+                    if (tx >= tw) { tx -= tw; ty++; }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) tile4_accumulate<OP, ACC>(alo[u], ahi[u], blo[u], bhi[u], acc);
+            }
+        }
+        for (; t < T4; t += G)
+        {
+            uint32_t alo[4], ahi[4], blo[4], bhi[4];
+            load_tile4x4(a + (intptr_t)(ty << 2) * sa + (tx << 2), sa, alo, ahi);
+            load_tile4x4(b + (intptr_t)(ty << 2) * sb + (tx << 2), sb, blo, bhi);
+            tx += dx; ty += dy;
+            if (tx >= tw) { tx -= tw; ty++; }
+            tile4_accumulate<OP, ACC>(alo, ahi, blo, bhi, acc);
+        }
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) out[blk] = (OUT)acc;
+}
+
+} // namespace b200
