@@ -81,6 +81,9 @@ int x265b200_sm_count(const x265b200_ctx* ctx);
 /* sticky status: first error recorded by any entry (host entries cannot return one) */
 int x265b200_status(const x265b200_ctx* ctx);
 const char* x265b200_last_error(const x265b200_ctx* ctx);
+/* Forward DCT 16/32 implementation: 0 (default) = tensor cores (IMMA, csrc/transform_mma.cu),
+ * 1 = the CUDA-core partial-butterfly kernels (csrc/transform.cu), kept as the validation twin. */
+int x265b200_set_dct_path(x265b200_ctx* ctx, int path);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t x265b200_launch_count(const x265b200_ctx* ctx);
 

@@ -141,3 +141,35 @@ def test_full_size_properties_2160p10(torch_mod):
     b2 = B.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + ch, geo.margin_x:geo.margin_x + cw].astype(np.int64)
     assert tot[64] == (int(np.abs(a2 - b2).sum()), int(((a2 - b2) ** 2).sum()))
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_dct_tensor_core_and_butterfly_paths_full_range(depth, torch_mod):
+    """forward DCT 16/32 on the IMMA path and on the CUDA-core twin, residual-range and full-range int16
+    inputs (TestBench never feeds the latter), contiguous and strided / misaligned sources."""
+    torch = torch_mod
+    from gpulib import context, pkg
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(99 + depth)
+    pmax = (1 << depth) - 1
+    n = 150
+    try:
+        for N in (16, 32, 8, 4):
+            inputs = [rng.integers(-pmax, pmax + 1, n * N * N + 64).astype(np.int16),
+                      rng.integers(-32768, 32768, n * N * N + 64).astype(np.int16),
+                      np.full(n * N * N + 64, -32768, np.int16), np.full(n * N * N + 64, 32767, np.int16)]
+            for src in inputs:
+                d_src = dev(src)
+                layouts = [(N, (np.arange(n) * N * N).astype(np.int32)),                 # contiguous TUs
+                           (2 * N, (np.arange(n // 2) * 2 * N * N + 2).astype(np.int32)),  # strided, 4-byte aligned only
+                           (2 * N + 4, (np.arange(n // 3) * 2 * N * N + 1).astype(np.int32))]  # odd offsets: 2-byte aligned
+                for stride, off in layouts:
+                    ref = orc.dct_batch(N, src, stride, off)
+                    for path in (0, 1):
+                        ctx.set_dct_path(path)
+                        out = torch.zeros(len(off) * N * N, dtype=torch.int16, device="cuda")
+                        ctx.dct_batch(pkg.TR_DCT, N, d_src, stride, dev(off), out)
+                        assert np.array_equal(out.cpu().numpy(), ref), (N, stride, path)
+    finally:
+        ctx.set_dct_path(0)
+    ctx.check()

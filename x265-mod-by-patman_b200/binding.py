@@ -91,6 +91,12 @@ class Context:
         if st != 0:
             raise RuntimeError("x265b200 error %d: %s" % (st, self.lib.x265b200_last_error(self.h).decode()))
 
+    def set_dct_path(self, path):
+        """0 = tensor-core IMMA for N >= 16 (default), 1 = CUDA-core butterfly kernels"""
+        r = self.lib.x265b200_set_dct_path(self.h, int(path))
+        if r != 0:
+            raise RuntimeError("x265b200_set_dct_path failed")
+
     def launch_count(self):
         return int(self.lib.x265b200_launch_count(self.h))
 

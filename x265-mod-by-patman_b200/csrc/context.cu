@@ -15,6 +15,7 @@ namespace b200 {
 
 int upload_transform_tables(x265b200_ctx* ctx);   // transform.cu
 int upload_filter_tables(x265b200_ctx* ctx);      // ipfilter.cu
+int upload_mma_tables(x265b200_ctx* ctx);         // transform_mma.cu
 
 int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e)
 {
@@ -140,6 +141,7 @@ extern "C" int x265b200_open(int device, int bit_depth, x265b200_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     int r = upload_transform_tables(ctx);
     if (r == X265B200_OK) r = upload_filter_tables(ctx);
+    if (r == X265B200_OK) r = upload_mma_tables(ctx);
     if (r != X265B200_OK) { fprintf(stderr, "x265b200: %s\n", ctx->err.c_str()); delete ctx; return r; }
     *out = ctx;
     return X265B200_OK;
@@ -158,6 +160,13 @@ extern "C" void x265b200_close(x265b200_ctx* ctx)
         delete l;
     }
     delete ctx;
+}
+
+extern "C" int x265b200_set_dct_path(x265b200_ctx* ctx, int path)
+{
+    if (!ctx || path < 0 || path > 1) return X265B200_ERR_ARG;
+    ctx->dct_path = path;
+    return X265B200_OK;
 }
 
 extern "C" int x265b200_bit_depth(const x265b200_ctx* ctx) { return ctx ? ctx->depth : 0; }

@@ -32,6 +32,7 @@ struct x265b200_ctx
     int depth = 8;
     int pixbytes = 1;
     int sm_count = 0;
+    int dct_path = 0;           // 0 = tensor-core IMMA for N >= 16 (default), 1 = CUDA-core butterfly everywhere
     std::atomic<int> status{0};
     std::atomic<uint64_t> launches{0};
     std::mutex mu;

@@ -406,6 +406,9 @@ dequant_scaling_kernel(const int16_t* __restrict__ q, const int32_t* __restrict_
 
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 
+bool launch_dct_imma(x265b200_ctx* ctx, int N, const int16_t* src, intptr_t srcStride, const int32_t* off, int n,
+                     int16_t* dst, int shift1, int shift2, cudaStream_t st, int dst4);    // transform_mma.cu
+
 } // namespace b200
 
 using namespace b200;
@@ -420,7 +423,12 @@ extern "C" int x265b200_dct_batch(x265b200_ctx* ctx, int kind, int N, const int1
     int d8 = ctx->depth - 8;
 #define FWD(NN, MODE, TN) fwd_kernel<NN, MODE><<<ceil_div(n, Tile<NN>::PER_CTA), TR_THREADS, 0, st>>>( \
         src, srcStride, off, n, dst, ilog2(TN) - 1 + d8, ilog2(TN) + 6, ctx->depth)
-    if (kind == X265B200_TR_DCT)
+    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path == 0 &&
+        launch_dct_imma(ctx, N, src, srcStride, off, n, dst, ilog2(N) - 1 + d8, ilog2(N) + 6, st, kind == X265B200_TR_DST))
+    {
+        // tensor-core path (transform_mma.cu)
+    }
+    else if (kind == X265B200_TR_DCT)
     {
         if (N == 4) FWD(4, MODE_DCT, 4); else if (N == 8) FWD(8, MODE_DCT, 8);
         else if (N == 16) FWD(16, MODE_DCT, 16); else if (N == 32) FWD(32, MODE_DCT, 32);
