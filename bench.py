@@ -242,7 +242,7 @@ def run_b200_arm(args):
             if world > 1:
                 comm_stream.wait_stream(stream)
                 with torch.cuda.stream(comm_stream):
-                    dist.all_gather_into_tensor(recon_all, recon_send)
+                    dist.all_gather_into_tensor(recon_all.view(torch.uint8), recon_send.view(torch.uint8))
             for s in SATD_SHAPES:
                 a, b, _ = dev_desc[s]
                 if marks is not None:
@@ -253,7 +253,7 @@ def run_b200_arm(args):
             for n in DCT_SIZES:
                 if marks is not None:
                     e0 = ev(); e0.record(stream)
-                ctx.dct_batch(pkg.TR_DCT, n, resid, n, tu_off[n], coef, sh)
+                ctx.dct_batch(pkg.TR_DCT, n, resid, n, None, coef, sh, count=samples // (n * n))
                 if marks is not None:
                     e1 = ev(); e1.record(stream); marks.append(("dct", n, e0, e1))
             if world > 1:
@@ -369,7 +369,7 @@ def run_e2e(torch, pkg, ctx, geo, hF, hR, desc, F, args, world, dist):
             a, b = dd[(32, 32)]
             ctx.residual_batch(32, 32, sl["F"], geo.stride, sl["R"], geo.stride, a, b, sl["res"], sh)
             for i, n in enumerate(DCT_SIZES):
-                ctx.dct_batch(pkg.TR_DCT, n, sl["res"], n, tu_off[n], sl["coef"][i * samples:(i + 1) * samples], sh)
+                ctx.dct_batch(pkg.TR_DCT, n, sl["res"], n, None, sl["coef"][i * samples:(i + 1) * samples], sh, count=samples // (n * n))
             sl["hcoef"].copy_(sl["coef"], non_blocking=True)
             sl["hcost"].copy_(sl["cost"], non_blocking=True)
 

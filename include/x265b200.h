@@ -121,7 +121,8 @@ int x265b200_ads_batch(x265b200_ctx* ctx, int terms, int half, const int32_t* en
                        x265b200_stream stream);
 
 /* forward transform of n blocks: src block i at src + off[i] with srcStride (elements);
- * dst block i contiguous at dst + i*N*N.  (dct_t, primitives.h:153) */
+ * dst block i contiguous at dst + i*N*N.  off == NULL means contiguous source blocks (off[i] = i*N*N,
+ * use srcStride = N).  (dct_t, primitives.h:153) */
 int x265b200_dct_batch(x265b200_ctx* ctx, int kind, int N, const int16_t* src, intptr_t srcStride,
                        const int32_t* off, int n, int16_t* dst, x265b200_stream stream);
 /* inverse: src block i contiguous at src + i*N*N, dst block i at dst + off[i] with dstStride. (idct_t) */

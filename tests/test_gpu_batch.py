@@ -170,6 +170,10 @@ def test_dct_tensor_core_and_butterfly_paths_full_range(depth, torch_mod):
                         out = torch.zeros(len(off) * N * N, dtype=torch.int16, device="cuda")
                         ctx.dct_batch(pkg.TR_DCT, N, d_src, stride, dev(off), out)
                         assert np.array_equal(out.cpu().numpy(), ref), (N, stride, path)
+                        if stride == N:         # implicit contiguous descriptors (off == NULL)
+                            out.zero_()
+                            ctx.dct_batch(pkg.TR_DCT, N, d_src, N, None, out, count=len(off))
+                            assert np.array_equal(out.cpu().numpy(), ref), (N, "implicit", path)
     finally:
         ctx.set_dct_path(0)
     ctx.check()

@@ -1,0 +1,196 @@
+"""Batched DEVICE entries (n > 1) of the remaining primitive classes against the oracle:
+sse_ss / ssd_s, sa8d chroma shapes, ADS, quant / nquant / dequant, lowpass DCT, IDST, and every
+interpolation variant for luma and chroma block sizes."""
+import numpy as np
+import pytest
+
+from cpulibs import CHROMA_ONLY_420, CHROMA_ONLY_422, LUMA_PU, Oracle
+
+pytestmark = pytest.mark.gpu
+DEPTHS = [8, 10, 12]
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a).cuda()
+
+
+def pix_view(a, depth):
+    return a.view(np.int16) if depth > 8 else a
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_sse_ss_ssd_s_sa8d_batches(depth):
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(depth)
+    stride, rows, n = 192, 200, 97
+    for lo, hi in ((-orc.pmax, orc.pmax + 1), (-20000, 20000)):
+        A = rng.integers(lo, hi, stride * rows).astype(np.int16)
+        B = rng.integers(lo, hi, stride * rows).astype(np.int16)
+        for w in (4, 8, 16, 32, 64):
+            offA = (rng.integers(0, rows - w, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+            offB = (rng.integers(0, rows - w, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+            out = torch.zeros(n, dtype=torch.int64, device="cuda")
+            ctx.sse_ss_batch(w, w, dev(A), stride, dev(B), stride, dev(offA), dev(offB), out)
+            ref = np.array([orc.sse_ss(w, A, int(a), stride, B, int(b), stride) for a, b in zip(offA, offB)], np.uint64)
+            got = out.cpu().numpy().astype(np.uint64)
+            if depth == 8:
+                got &= np.uint64(0xFFFFFFFF)
+            assert np.array_equal(got, ref), w
+            ctx.ssd_s_batch(w, dev(A), stride, dev(offA), out)
+            ref = np.array([orc.ssd_s(w, A, int(a), stride) for a in offA], np.uint64)
+            got = out.cpu().numpy().astype(np.uint64)
+            if depth == 8:
+                got &= np.uint64(0xFFFFFFFF)
+            assert np.array_equal(got, ref), w
+    # sa8d with the chroma CU shapes (4:2:2 w x 2w) and satd fallbacks
+    P = rng.integers(0, orc.pmax + 1, stride * rows).astype(orc.pix)
+    Q = rng.integers(0, orc.pmax + 1, stride * rows).astype(orc.pix)
+    for (w, h) in ((4, 8), (8, 16), (16, 32), (32, 64), (8, 8), (16, 16), (32, 32), (64, 64), (4, 4), (12, 16), (24, 32)):
+        offA = (rng.integers(0, rows - h, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+        offB = (rng.integers(0, rows - h, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.pixelcmp_batch(2, w, h, dev(pix_view(P, depth)), stride, dev(pix_view(Q, depth)), stride, dev(offA), dev(offB), out)
+        ref = np.array([orc.sa8d(w, h, P, int(a), stride, Q, int(b), stride) for a, b in zip(offA, offB)], np.int32)
+        assert np.array_equal(out.cpu().numpy(), ref), (w, h)
+        # odd plane strides take the generic (non-vectorised) kernels
+        ctx.pixelcmp_batch(1, w, h, dev(pix_view(P, depth)), stride - 1, dev(pix_view(Q, depth)), stride + 1, dev(offA), dev(offB), out)
+        ref = np.array([orc.satd(w, h, P, int(a), stride - 1, Q, int(b), stride + 1) for a, b in zip(offA, offB)], np.int32)
+        assert np.array_equal(out.cpu().numpy(), ref), (w, h, "odd stride")
+    ctx.check()
+
+
+def test_ads_batch():
+    import torch
+    from gpulib import context
+    depth = 10
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(5)
+    stride = 4128
+    sums = rng.integers(0, 1 << 24, stride * 64, dtype=np.int64).astype(np.uint32)
+    cost = rng.integers(0, 4000, 4096).astype(np.uint16)
+    for (w, h) in LUMA_PU:
+        terms = {1: 1, 2: 2, 4: 4}[orc.lib.orc_ads_terms(w, h)]
+        n = 40
+        enc = rng.integers(0, 1 << 24, (n, 4)).astype(np.int32)
+        sumOff = (rng.integers(0, 20, n) * stride + rng.integers(0, 200, n)).astype(np.int32)
+        delta = np.full(n, (h >> 1) * stride, np.int32)
+        costOff = rng.integers(0, 3000, n).astype(np.int32)
+        width = (rng.integers(1, 30, n) * 4).astype(np.int32)
+        thresh = rng.integers(0, 1 << 25, n).astype(np.int32)
+        pitch = 128
+        mvs = torch.full((n * pitch,), -1, dtype=torch.int16, device="cuda")
+        cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.ads_batch(terms, (w >> 1) if terms == 4 else 0, dev(enc.ravel()), dev(sums), dev(sumOff), dev(delta), dev(cost),
+                      dev(costOff), dev(width), dev(thresh), mvs, pitch, cnt)
+        mv = mvs.cpu().numpy().reshape(n, pitch); c = cnt.cpu().numpy()
+        for i in range(n):
+            k, m = orc.ads(w, h, enc[i], sums, int(sumOff[i]), int(delta[i]), cost[costOff[i]:], int(width[i]), int(thresh[i]))
+            assert c[i] == k and np.array_equal(mv[i, :k], m), (w, h, i)
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_quant_family_batches(depth):
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(depth + 40)
+    for numCoeff, qbits in ((16, 9), (64, 14), (256, 17), (1024, 21), (24, 12)):
+        n = 53
+        coef = rng.integers(-32768, 32768, n * numCoeff).astype(np.int16)
+        for qc in (np.full(numCoeff, 26214, np.int32), rng.integers(-orc.pmax, orc.pmax + 1, numCoeff).astype(np.int32),
+                   rng.integers(1, 1 << 17, numCoeff).astype(np.int32)):
+            add = 171 << (qbits - 9)
+            q = torch.zeros(n * numCoeff, dtype=torch.int16, device="cuda")
+            du = torch.zeros(n * numCoeff, dtype=torch.int32, device="cuda")
+            sig = torch.zeros(n, dtype=torch.int32, device="cuda")
+            ctx.quant_batch(dev(coef), dev(qc), du, q, qbits, add, numCoeff, n, sig)
+            for i in (0, 1, n // 2, n - 1):
+                r, rq, rdu = orc.quant(coef[i * numCoeff:(i + 1) * numCoeff].copy(), qc, qbits, add, numCoeff)
+                assert int(sig[i]) == r
+                assert np.array_equal(q[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rq)
+                assert np.array_equal(du[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rdu)
+            ctx.quant_batch(dev(coef), dev(qc), None, q, qbits, 1 << (qbits - 1), numCoeff, n, sig)
+            for i in (0, n - 1):
+                r, rq = orc.nquant(coef[i * numCoeff:(i + 1) * numCoeff].copy(), qc, qbits, 1 << (qbits - 1), numCoeff)
+                assert int(sig[i]) == r and np.array_equal(q[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rq)
+        if numCoeff % 8 == 0:
+            out = torch.zeros(n * numCoeff, dtype=torch.int16, device="cuda")
+            for scale, shift in ((40, 1), (72 << 4, 5), (64 << 8, 10)):
+                ctx.dequant_normal_batch(dev(coef), out, n * numCoeff, scale, shift)
+                assert np.array_equal(out.cpu().numpy(), orc.dequant_normal(coef, n * numCoeff, scale, shift))
+            dq = rng.integers(1, 1 << 12, numCoeff).astype(np.int32)
+            for per, shift in ((0, 1), (3, 6), (12, 2), (8, 4)):
+                ctx.dequant_scaling_batch(dev(coef), dev(dq), out, numCoeff, n, per, shift)
+                ref = np.concatenate([orc.dequant_scaling(coef[i * numCoeff:(i + 1) * numCoeff].copy(), dq, numCoeff, per, shift) for i in range(n)])
+                assert np.array_equal(out.cpu().numpy(), ref)
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_lowpass_idst_batches(depth):
+    import torch
+    from gpulib import context, pkg
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(depth + 70)
+    n = 61
+    for src in (rng.integers(-orc.pmax, orc.pmax + 1, n * 1024 + 64).astype(np.int16), rng.integers(-32768, 32768, n * 1024 + 64).astype(np.int16)):
+        for N in (8, 16, 32):
+            off = (np.arange(n) * N * N).astype(np.int32)
+            out = torch.zeros(n * N * N, dtype=torch.int16, device="cuda")
+            ctx.dct_batch(pkg.TR_LOWPASS, N, dev(src), N, dev(off), out)
+            ref = np.concatenate([orc.lowpass_dct(N, src, int(o), N) for o in off])
+            assert np.array_equal(out.cpu().numpy(), ref), N
+        stride = 12
+        plane = torch.zeros(n * 4 * stride, dtype=torch.int16, device="cuda")
+        offD = (np.arange(n) * 4 * stride + 3).astype(np.int32)
+        ctx.idct_batch(pkg.TR_DST, 4, dev(src), plane, stride, dev(offD))
+        ref = orc.idct_batch(4, src, np.zeros(n * 4 * stride, np.int16), stride, offD, dst4=1)
+        assert np.array_equal(plane.cpu().numpy(), ref)
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_interp_batches(depth):
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(depth + 90)
+    ss, srows = 208, 160
+    P = rng.integers(0, orc.pmax + 1, ss * srows).astype(orc.pix)
+    S = rng.integers(-32768, 32768, ss * srows).astype(np.int16)
+    ds = 80
+    n = 9
+    cases = [(8, s) for s in [(4, 4), (8, 8), (16, 16), (64, 64), (12, 16), (24, 32), (48, 64), (16, 4), (8, 32), (64, 16)]] + \
+            [(4, s) for s in [(2, 4), (4, 2), (6, 8), (8, 6), (4, 4), (32, 32), (12, 32), (24, 64), (32, 48), (2, 16)]]
+    for taps, (w, h) in cases:
+        rmax = h + taps
+        offS = ((rng.integers(4, srows - rmax - 4, n)) * ss + rng.integers(4, ss - w - 8, n)).astype(np.int32)
+        offD = (np.arange(n) * (rmax * ds) + 5).astype(np.int32)
+        for kind in ("hpp", "hps", "vpp", "vps", "vsp", "vss", "hvpp", "p2s"):
+            if kind == "hvpp" and taps == 4:
+                continue
+            src = S if kind in ("vsp", "vss") else P
+            pix_out = kind in ("hpp", "vpp", "vsp", "hvpp")
+            nidx = 4 if taps == 8 else 8
+            idx = rng.integers(1 if taps == 8 else 0, nidx, n)
+            extra = rng.integers(1, 4, n) if kind == "hvpp" else rng.integers(0, 2, n) if kind == "hps" else np.zeros(n, np.int64)
+            packed = (idx | (extra << 4 if kind == "hvpp" else extra << 8)).astype(np.int32)
+            dt = orc.pix if pix_out else np.int16
+            dst0 = np.full(n * rmax * ds + 64, 77, dt)
+            d_dst = dev(pix_view(dst0.copy(), depth) if pix_out else dst0.copy())
+            d_src = dev(pix_view(src, depth) if src is P else src)
+            ctx.interp_batch(kind, taps, w, h, d_src, ss, dev(offS), d_dst, ds, dev(offD), dev(packed))
+            ref = dst0.copy()
+            for i in range(n):
+                if kind == "p2s":
+                    orc.p2s(w, h, src, int(offS[i]), ss, ref, int(offD[i]), ds)
+                else:
+                    orc.interp(kind, taps, w, h, src, int(offS[i]), ss, ref, int(offD[i]), ds, int(idx[i]), int(extra[i]))
+            got = d_dst.cpu().numpy()
+            got = got.view(dt) if pix_out and depth > 8 else got
+            assert np.array_equal(got, ref), (taps, w, h, kind)
+    ctx.check()

@@ -128,8 +128,10 @@ class Context:
         self._call("x265b200_ads_batch", terms, half, _dp(encDC), _dp(sums), _dp(sumOff), _dp(delta), _dp(cost),
                    _dp(costOff), _dp(width), _dp(thresh), int(sumOff.numel()), _dp(mvs), pitch, _dp(count), C.c_void_p(stream))
 
-    def dct_batch(self, kind, N, src, stride, off, dst, stream=0):
-        self._call("x265b200_dct_batch", kind, N, _dp(src), _ss(stride), _dp(off), int(off.numel()), _dp(dst), C.c_void_p(stream))
+    def dct_batch(self, kind, N, src, stride, off, dst, stream=0, count=None):
+        """off=None: contiguous source TUs (then `count` gives the number of TUs)"""
+        n = int(off.numel()) if off is not None else int(count)
+        self._call("x265b200_dct_batch", kind, N, _dp(src), _ss(stride), _dp(off), n, _dp(dst), C.c_void_p(stream))
 
     def idct_batch(self, kind, N, src, dst, stride, off, stream=0):
         self._call("x265b200_idct_batch", kind, N, _dp(src), int(off.numel()), _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))

@@ -189,7 +189,7 @@ fwd_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int32_t* _
 
     if (live)
     {
-        const int16_t* p = src + off[tu];
+        const int16_t* p = src + (off ? (size_t)off[tu] : (size_t)tu * (MODE == MODE_LOWPASS ? 4 * N * N : N * N));
         if (MODE == MODE_LOWPASS)
         {
             // lowpassdct.cpp:40-49: 2x2 sums truncated to int16, average = sum >> 2

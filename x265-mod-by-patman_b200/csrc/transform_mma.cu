@@ -140,6 +140,9 @@ __device__ __forceinline__ void imma16_su(int (&c)[4], const uint32_t (&a)[2], u
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
 }
 
+// element offset of TU `tu`: explicit descriptor, or contiguous TUs when no descriptor array is given
+__device__ __forceinline__ size_t tu_offset(const int32_t* off, int tu, int nn) { return off ? (size_t)off[tu] : (size_t)tu * nn; }
+
 // four consecutive int16 as two packed words, with the widest load the address allows
 // (warp-uniform: all lanes of a TU share the alignment class when srcStride % 4 == 0)
 __device__ __forceinline__ uint2 ldg_s16x4(const int16_t* p)
@@ -189,7 +192,7 @@ dct32_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int
 
     uint2 x[4][2];
     {
-        const int16_t* p = src + off[warp] + lane_off;
+        const int16_t* p = src + tu_offset(off, warp, 1024) + lane_off;
 #pragma unroll
         for (int jt = 0; jt < 4; jt++)
         {
@@ -210,7 +213,7 @@ dct32_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int
         int nxt = tu + nwarps;
         if (nxt < n)
         {
-            const int16_t* p = src + off[nxt] + lane_off;
+            const int16_t* p = src + tu_offset(off, nxt, 1024) + lane_off;
 #pragma unroll
             for (int jt = 0; jt < 4; jt++)
             {
@@ -278,7 +281,7 @@ dct16_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int
 #pragma unroll
     for (int u = 0; u < TPW; u++)
     {
-        const int16_t* p = src + off[min(warp * TPW + u, n - 1)] + lane_off;
+        const int16_t* p = src + tu_offset(off, min(warp * TPW + u, n - 1), 256) + lane_off;
         x[u][0] = ldg_s16x4(p); x[u][1] = ldg_s16x4(p + 8 * srcStride);
     }
     for (int grp = warp; grp < ngroups; grp += nwarps)
@@ -296,7 +299,7 @@ dct16_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int
 #pragma unroll
             for (int u = 0; u < TPW; u++)
             {
-                const int16_t* p = src + off[min(nxt * TPW + u, n - 1)] + lane_off;
+                const int16_t* p = src + tu_offset(off, min(nxt * TPW + u, n - 1), 256) + lane_off;
                 x[u][0] = ldg_s16x4(p); x[u][1] = ldg_s16x4(p + 8 * srcStride);
             }
         }
@@ -368,7 +371,7 @@ dct_small_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const
     for (int u = 0; u < UN; u++)
     {
         int tu = min((warp * UN + u) * TPG + ld_tu, n - 1);
-        x[u] = ldg_s16x4(src + off[tu] + ld_off);
+        x[u] = ldg_s16x4(src + tu_offset(off, tu, NN) + ld_off);
     }
     for (int grp = warp; grp < ngroups; grp += nwarps)
     {
@@ -382,7 +385,7 @@ dct_small_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const
             for (int u = 0; u < UN; u++)
             {
                 int tu = min((nxt * UN + u) * TPG + ld_tu, n - 1);
-                x[u] = ldg_s16x4(src + off[tu] + ld_off);
+                x[u] = ldg_s16x4(src + tu_offset(off, tu, NN) + ld_off);
             }
         }
 #pragma unroll
