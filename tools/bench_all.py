@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Per-primitive-class throughput on 2160p10-sized batches: achieved algorithmic GB/s vs the measured HBM peak.
+Complements bench.py (which times the SATD+DCT headline step).  Output: one JSON line per row + a markdown table.
+
+    python tools/bench_all.py [--depth 10] [--frames 8] > profiles/<name>.md
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from frames import Geometry, make_plane, tile_blocks  # noqa: E402
+
+pkg = importlib.import_module("x265-mod-by-patman_b200")
+
+
+def timeit(fn, reps=8, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--depth", type=int, default=10)
+    ap.add_argument("--frames", type=int, default=8)
+    args = ap.parse_args()
+    D, F = args.depth, args.frames
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    ctx = pkg.Context(D, 0)
+    geo = Geometry(3840, 2160)
+    b = 1 if D == 8 else 2
+    vt = np.uint8 if D == 8 else np.int16
+    pe = geo.plane_elems
+    cw, ch = geo.coded()
+    S = F * cw * ch
+    A = torch.from_numpy(np.concatenate([make_plane(geo, D, 1 + f, "natural") for f in range(F)]).view(vt)).cuda()
+    B = torch.from_numpy(np.concatenate([make_plane(geo, D, 101 + f, "natural") for f in range(F)]).view(vt)).cuda()
+    rows = []
+
+    def desc(w, h):
+        oa, ob = tile_blocks(geo, w, h, seed=1)
+        a = np.concatenate([oa.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        bb = np.concatenate([ob.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        return torch.from_numpy(a).cuda(), torch.from_numpy(bb).cuda()
+
+    def add(name, ms, nbytes, units):
+        gbs = nbytes / ms / 1e6
+        rows.append({"primitive": name, "ms": ms, "algorithmic_GB": nbytes / 1e9, "GBps": gbs, "frac_of_measured_hbm": gbs / peak,
+                     "Gunits_per_s": units / ms / 1e6})
+        print(json.dumps(rows[-1]), file=sys.stderr)
+
+    # ---- block metrics
+    for (w, h) in ((64, 64), (32, 32), (16, 16), (8, 8), (4, 4)):
+        oa, ob = desc(w, h)
+        n = oa.numel()
+        o32 = torch.empty(n, dtype=torch.int32, device="cuda"); o64 = torch.empty(n, dtype=torch.int64, device="cuda")
+        for op, nm, out, ob_ in ((0, "sad", o32, 4), (1, "satd", o32, 4), (2, "sa8d", o32, 4), (3, "sse_pp", o64, 8)):
+            ms = timeit(lambda: ctx.pixelcmp_batch(op, w, h, A, geo.stride, B, geo.stride, oa, ob, out))
+            add("%s %dx%d" % (nm, w, h), ms, S * 2 * b + n * ob_, S)
+        if w in (16, 64):
+            K = 4
+            offR = torch.stack([ob + k for k in range(K)], dim=1).reshape(-1).contiguous()
+            oK = torch.empty(n * K, dtype=torch.int32, device="cuda")
+            ms = timeit(lambda: ctx.sad_multi_batch(w, h, A, geo.stride, B, geo.stride, oa, offR, K, oK))
+            add("sad_x4 %dx%d (per candidate sample)" % (w, h), ms, S * (1 + K) * b + n * K * 4, S * K)
+    # ---- transforms on block-contiguous int16
+    res = torch.empty(S, dtype=torch.int16, device="cuda")
+    oa, ob = desc(32, 32)
+    ctx.residual_batch(32, 32, A, geo.stride, B, geo.stride, oa, ob, res)
+    ms = timeit(lambda: ctx.residual_batch(32, 32, A, geo.stride, B, geo.stride, oa, ob, res))
+    add("residual (sub_ps) 32x32", ms, S * (2 * b + 2), S)
+    coef = torch.empty(S, dtype=torch.int16, device="cuda")
+    rec = torch.empty(S, dtype=torch.int16, device="cuda")
+    for N in (32, 16, 8, 4):
+        n = S // (N * N)
+        off = torch.arange(n, dtype=torch.int32, device="cuda") * (N * N)
+        ms = timeit(lambda: ctx.dct_batch(pkg.TR_DCT, N, res, N, None, coef, count=n))
+        add("dct%d (IMMA)" % N, ms, S * 4, S)
+        ctx.set_dct_path(1)
+        ms = timeit(lambda: ctx.dct_batch(pkg.TR_DCT, N, res, N, None, coef, count=n))
+        add("dct%d (CUDA-core twin)" % N, ms, S * 4, S)
+        ctx.set_dct_path(0)
+        ms = timeit(lambda: ctx.idct_batch(pkg.TR_DCT, N, coef, rec, N, off))
+        add("idct%d" % N, ms, S * 4, S)
+    n4 = S // 16
+    ms = timeit(lambda: ctx.dct_batch(pkg.TR_DST, 4, res, 4, None, coef, count=n4))
+    add("dst4 (IMMA)", ms, S * 4, S)
+    # ---- quant family, 32x32 blocks
+    nb = S // 1024
+    qc = torch.full((1024,), 26214, dtype=torch.int32, device="cuda")
+    q = torch.empty(S, dtype=torch.int16, device="cuda"); du = torch.empty(S, dtype=torch.int32, device="cuda")
+    sig = torch.empty(nb, dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: ctx.quant_batch(coef, qc, du, q, 21, 171 << 12, 1024, nb, sig)); add("quant 32x32", ms, S * 8, S)
+    ms = timeit(lambda: ctx.quant_batch(coef, qc, None, q, 21, 1 << 20, 1024, nb, sig)); add("nquant 32x32", ms, S * 4, S)
+    ms = timeit(lambda: ctx.dequant_normal_batch(q, coef, S, 64 << 4, 5)); add("dequant_normal", ms, S * 4, S)
+    ms = timeit(lambda: ctx.dequant_scaling_batch(q, qc, coef, 1024, nb, 4, 2)); add("dequant_scaling 32x32", ms, S * 4, S)
+    # ---- interpolation, frame-tiled 64x64 and 16x16 luma, 8x8 chroma-size blocks
+    dstP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); dstS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
+    srcS = torch.randint(-8192, 8192, (F * pe,), dtype=torch.int16, device="cuda")
+    for taps, (w, h) in ((8, (64, 64)), (8, (16, 16)), (4, (8, 8))):
+        oa, _ = desc(w, h)
+        n = oa.numel()
+        idx = torch.randint(1, 4, (n,), dtype=torch.int32, device="cuda")
+        idxhv = idx | (torch.randint(1, 4, (n,), dtype=torch.int32, device="cuda") << 4)
+        tag = "%s %dx%d" % ("luma" if taps == 8 else "chroma", w, h)
+        for kind, src, dst, inb, outb in (("hpp", A, dstP, b, b), ("vpp", A, dstP, b, b), ("hps", A, dstS, b, 2), ("vps", A, dstS, b, 2),
+                                          ("vsp", srcS, dstP, 2, b), ("vss", srcS, dstS, 2, 2), ("p2s", A, dstS, b, 2)):
+            ms = timeit(lambda: ctx.interp_batch(kind, taps, w, h, src, geo.stride, oa, dst, geo.stride, oa, idx))
+            add("%s %s" % (kind, tag), ms, S * (inb + outb), S)
+        if taps == 8:
+            ms = timeit(lambda: ctx.interp_batch("hvpp", 8, w, h, A, geo.stride, oa, dstP, geo.stride, oa, idxhv))
+            add("hvpp %s" % tag, ms, S * 2 * b, S)
+    ctx.check()
+    print("| primitive (2160p%d x %d frames per launch) | ms | GB/s (algorithmic) | of measured HBM %.0f GB/s | G samples/s |" % (D, F, peak))
+    print("|---|---|---|---|---|")
+    for r in rows:
+        print("| %s | %.4f | %.0f | %.2f | %.0f |" % (r["primitive"], r["ms"], r["GBps"], r["frac_of_measured_hbm"], r["Gunits_per_s"]))
+
+
+if __name__ == "__main__":
+    main()
