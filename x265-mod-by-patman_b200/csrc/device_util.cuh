@@ -128,6 +128,56 @@ __device__ __forceinline__ void load_tile4x4(const uint8_t* p, intptr_t stride, 
     }
 }
 
+// NQ consecutive quads (4 samples each) of one row starting at p (aligned to the sample size only):
+// aligned 8-byte chunk loads, all issued first, then funnel-shift realignment.  16-bit samples.
+template<int NQ>
+__device__ __forceinline__ void load_row_quads(const uint16_t* p, uint32_t (&w)[2 * NQ])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)(a >> 1) & 3;
+    const uint2* base = (const uint2*)(a & ~(uintptr_t)7);
+    uint32_t c[2 * NQ + 2];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) { uint2 q = __ldg(base + i); c[2 * i] = q.x; c[2 * i + 1] = q.y; }
+    if (s) { uint2 q = __ldg(base + NQ); c[2 * NQ] = q.x; c[2 * NQ + 1] = q.y; }
+    else { c[2 * NQ] = 0; c[2 * NQ + 1] = 0; }
+    int sh = (s & 1) << 4;
+#pragma unroll
+    for (int i = 0; i < 2 * NQ; i++)
+    {
+        uint32_t lo = (s & 2) ? c[i + 1] : c[i];
+        uint32_t hi = (s & 2) ? c[(i + 2 <= 2 * NQ + 1) ? i + 2 : 2 * NQ + 1] : c[i + 1];
+        w[i] = __funnelshift_r(lo, hi, sh);
+    }
+}
+template<int NQ>
+__device__ __forceinline__ void load_row_quads(const int16_t* p, uint32_t (&w)[2 * NQ]) { load_row_quads<NQ>((const uint16_t*)p, w); }
+
+// 8-bit samples: 4-byte chunks, result widened to packed 16-bit pairs
+template<int NQ>
+__device__ __forceinline__ void load_row_quads(const uint8_t* p, uint32_t (&w)[2 * NQ])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)a & 3;
+    const uint32_t* base = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t c[NQ + 1];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) c[i] = __ldg(base + i);
+    c[NQ] = s ? __ldg(base + NQ) : 0;
+#pragma unroll
+    for (int i = 0; i < NQ; i++)
+    {
+        uint32_t v = __funnelshift_r(c[i], c[i + 1], s << 3);
+        w[2 * i] = __byte_perm(v, 0, 0x4140);
+        w[2 * i + 1] = __byte_perm(v, 0, 0x4342);
+    }
+}
+
+template<typename T> struct SampleTraits;
+template<> struct SampleTraits<uint8_t>  { static __device__ __forceinline__ void unpack(uint32_t w, int& x, int& y) { x = w & 0xffff; y = w >> 16; } };
+template<> struct SampleTraits<uint16_t> { static __device__ __forceinline__ void unpack(uint32_t w, int& x, int& y) { x = w & 0xffff; y = w >> 16; } };
+template<> struct SampleTraits<int16_t>  { static __device__ __forceinline__ void unpack(uint32_t w, int& x, int& y) { x = (int)(int16_t)(w & 0xffff); y = (int)w >> 16; } };
+
 // packed signed pair x + (y << 16) (as produced by subtracting two packed unsigned pairs) -> x, y
 __device__ __forceinline__ void unpack_s16x2(uint32_t w, int& x, int& y)
 {

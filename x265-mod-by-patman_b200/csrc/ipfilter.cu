@@ -68,6 +68,116 @@ fir_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restrict__
     dst[offDst[blk] + (intptr_t)y * ds + x] = (DST)v;
 }
 
+// Throughput version for blocks whose width is a multiple of 4 and strides are multiples of 4 samples:
+// one thread produces a 4x4 output tile.  Horizontal filters read 4 rows x (TAPS+3) samples, vertical
+// filters (TAPS+3) rows x 4 samples, through aligned chunk loads (device_util.cuh load_row_quads); every input
+// sample is loaded once per tile instead of once per tap.
+template<typename DST>
+__device__ __forceinline__ void store4(DST* d, const int (&v)[4])
+{
+    if (sizeof(DST) == 2)
+    {
+        uint32_t lo = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16), hi = (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16);
+        uintptr_t a = (uintptr_t)d;
+        if ((a & 7) == 0) *(uint2*)d = make_uint2(lo, hi);
+        else if ((a & 3) == 0) { ((uint32_t*)d)[0] = lo; ((uint32_t*)d)[1] = hi; }
+        else { d[0] = (DST)v[0]; d[1] = (DST)v[1]; d[2] = (DST)v[2]; d[3] = (DST)v[3]; }
+    }
+    else
+    {
+        uintptr_t a = (uintptr_t)d;
+        if ((a & 3) == 0) *(uint32_t*)d = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) | ((uint32_t)v[3] << 24);
+        else { d[0] = (DST)v[0]; d[1] = (DST)v[1]; d[2] = (DST)v[2]; d[3] = (DST)v[3]; }
+    }
+}
+
+template<typename SRC, typename DST, int TAPS, bool VERT>
+__global__ void __launch_bounds__(128)
+fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
+                DST* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst,
+                const int32_t* __restrict__ coeffIdx, int n, FirParams p)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int rowsMax = p.rowExtKind ? p.h + TAPS - 1 : p.h;
+    int tw = p.w >> 2;
+    int per = tw * ((rowsMax + 3) >> 2);
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int t = (int)(gid % per);
+    int tx = (t % tw) << 2, ty = (t / tw) << 2;
+    int ci = coeffIdx[blk];
+    int idx = ci & 15;
+    const SRC* s = src + offSrc[blk];
+    int rows = p.h;
+    if (p.rowExtKind && (ci >> 8 & 1)) { s -= (TAPS / 2 - 1) * ss; rows += TAPS - 1; }
+    if (ty >= rows) return;
+    DST* d = dst + offDst[blk] + (intptr_t)ty * ds + tx;
+    int c[TAPS];
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) c[k] = tap<TAPS>(idx, k);
+
+    if (!VERT)
+    {
+        constexpr int NQ = TAPS == 8 ? 3 : 2;                    // 4 + TAPS - 1 samples
+        s += (intptr_t)ty * ss + tx - (TAPS / 2 - 1);
+        uint32_t w[4][2 * NQ];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (ty + r < rows) load_row_quads<NQ>(s + r * ss, w[r]);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            if (ty + r >= rows) break;
+            int x[4 * NQ];
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) SampleTraits<SRC>::unpack(w[r][i], x[2 * i], x[2 * i + 1]);
+            int v[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int k = 0; k < TAPS; k++) sum += x[o + k] * c[k];
+                int q = (int)(int16_t)((sum + p.offset) >> p.shift);
+                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+            }
+            store4(d + r * ds, v);
+        }
+    }
+    else
+    {
+        s += (intptr_t)(ty - (TAPS / 2 - 1)) * ss + tx;
+        int nr = min(4, rows - ty);
+        uint32_t w[TAPS + 3][2];
+#pragma unroll
+        for (int r = 0; r < TAPS + 3; r++)
+            if (r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, w[r]);
+        int x[TAPS + 3][4];
+#pragma unroll
+        for (int r = 0; r < TAPS + 3; r++)
+        {
+            SampleTraits<SRC>::unpack(w[r][0], x[r][0], x[r][1]);
+            SampleTraits<SRC>::unpack(w[r][1], x[r][2], x[r][3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            if (r >= nr) break;
+            int v[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int k = 0; k < TAPS; k++) sum += x[r + k][o] * c[k];
+                int q = (int)(int16_t)((sum + p.offset) >> p.shift);
+                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+            }
+            store4(d + r * ds, v);
+        }
+    }
+}
+
 // hvpp: one CTA per block.  Pass 1 = hps(isRowExt=1) into smem (pitch w), pass 2 = vertical sp.
 template<typename PIX, int TAPS>
 __global__ void __launch_bounds__(256)
@@ -104,6 +214,113 @@ hv_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ 
     }
 }
 
+// hvpp throughput version (w % 4 == 0, stride % 4 == 0): one warp per block, 4 blocks per CTA.
+// Pass 1 = hps with isRowExt into a per-warp smem tile (pitch w), 4x4 tiles via load_row_quads;
+// pass 2 = vertical sp out of smem, 4x4 output tiles (8-byte aligned LDS).
+template<typename PIX, int TAPS>
+__global__ void __launch_bounds__(128)
+hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
+               PIX* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst,
+               const int32_t* __restrict__ coeffIdx, int n, int w, int h, int shift1, int offset1, int shift2, int offset2, int maxVal)
+{
+    extern __shared__ __align__(16) int16_t immed_all[];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int blk = blockIdx.x * 4 + warp;
+    if (blk >= n) return;
+    int rows = h + TAPS - 1;
+    int16_t* immed = immed_all + (size_t)warp * w * rows;
+    int ci = coeffIdx[blk];
+    int idxX = ci & 15, idxY = (ci >> 4) & 15;
+    int cx[TAPS], cy[TAPS];
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) { cx[k] = tap<TAPS>(idxX, k); cy[k] = tap<TAPS>(idxY, k); }
+    const PIX* s = src + offSrc[blk] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
+    int tw = w >> 2;
+    constexpr int NQ = TAPS == 8 ? 3 : 2;
+    int tiles1 = tw * ((rows + 3) >> 2);
+    for (int t = lane; t < tiles1; t += 32)
+    {
+        int tx = (t % tw) << 2, ty = (t / tw) << 2;
+        uint32_t wv[4][2 * NQ];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (ty + r < rows) load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, wv[r]);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            if (ty + r >= rows) break;
+            int x[4 * NQ];
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) SampleTraits<PIX>::unpack(wv[r][i], x[2 * i], x[2 * i + 1]);
+            int v[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int k = 0; k < TAPS; k++) sum += x[o + k] * cx[k];
+                v[o] = (sum + offset1) >> shift1;
+            }
+            *(uint2*)(immed + (ty + r) * w + tx) = make_uint2((uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16),
+                                                              (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16));
+        }
+    }
+    __syncwarp();
+    PIX* d = dst + offDst[blk];
+    int tiles2 = tw * (h >> 2);
+    for (int t = lane; t < tiles2; t += 32)
+    {
+        int tx = (t % tw) << 2, ty = (t / tw) << 2;
+        int x[TAPS + 3][4];
+#pragma unroll
+        for (int r = 0; r < TAPS + 3; r++)
+        {
+            uint2 q = *(const uint2*)(immed + (ty + r) * w + tx);
+            SampleTraits<int16_t>::unpack(q.x, x[r][0], x[r][1]);
+            SampleTraits<int16_t>::unpack(q.y, x[r][2], x[r][3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            int v[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                int sum = 0;
+#pragma unroll
+                for (int k = 0; k < TAPS; k++) sum += x[r + k][o] * cy[k];
+                int q = (int)(int16_t)((sum + offset2) >> shift2);
+                v[o] = min(max(q, 0), maxVal);
+            }
+            store4(d + (intptr_t)(ty + r) * ds + tx, v);
+        }
+    }
+}
+
+// p2s, 4 samples per thread
+template<typename PIX>
+__global__ void __launch_bounds__(256)
+p2s_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
+                int16_t* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst, int n, int w, int h, int shift)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int qw = w >> 2;
+    int per = qw * h;
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid % per);
+    int y = r / qw, x = (r % qw) << 2;
+    uint32_t wv[2];
+    load_row_quads<1>(src + offSrc[blk] + (intptr_t)y * ss + x, wv);
+    int a[4];
+    SampleTraits<PIX>::unpack(wv[0], a[0], a[1]);
+    SampleTraits<PIX>::unpack(wv[1], a[2], a[3]);
+    int v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = (int)(int16_t)((int)(int16_t)(a[i] << shift) - 8192);
+    store4(dst + offDst[blk] + (intptr_t)y * ds + x, v);
+}
+
 template<typename PIX>
 __global__ void __launch_bounds__(256)
 p2s_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
@@ -129,48 +346,68 @@ static int launch_interp(x265b200_ctx* ctx, int kind, int w, int h, const void* 
     FirParams p; p.w = w; p.h = h; p.rowExtKind = 0;
     long long threads = (long long)n * w * h;
     int grid = ceil_div(threads, 256);
+    const bool tiled = !(w & 3) && !(ss & 3);
+#define FIR(SRC_T, DST_T, VERT_, ROWS)                                                                          \
+    do {                                                                                                        \
+        if (tiled)                                                                                              \
+            fir_tile_kernel<SRC_T, DST_T, TAPS, VERT_><<<ceil_div((long long)n * (w >> 2) * (((ROWS) + 3) >> 2), 128), 128, 0, st>>>( \
+                (const SRC_T*)src, ss, offSrc, (DST_T*)dst, ds, offDst, coeffIdx, n, p);                         \
+        else                                                                                                    \
+            fir_kernel<SRC_T, DST_T, TAPS, VERT_><<<ceil_div((long long)n * w * (ROWS), 256), 256, 0, st>>>(     \
+                (const SRC_T*)src, ss, offSrc, (DST_T*)dst, ds, offDst, coeffIdx, n, p);                         \
+    } while (0)
     switch (kind)
     {
     case X265B200_IP_HPP:
         p.shift = 6; p.offset = 32; p.maxVal = maxVal;
-        fir_kernel<PIX, PIX, TAPS, false><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(PIX, PIX, false, h);
         break;
     case X265B200_IP_VPP:
         p.shift = 6; p.offset = 32; p.maxVal = maxVal;
-        fir_kernel<PIX, PIX, TAPS, true><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(PIX, PIX, true, h);
         break;
     case X265B200_IP_HPS:
         p.shift = 6 - headRoom; p.offset = (int)((unsigned)-8192 << p.shift); p.maxVal = -1; p.rowExtKind = 1;
-        grid = ceil_div((long long)n * w * (h + TAPS - 1), 256);
-        fir_kernel<PIX, int16_t, TAPS, false><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(PIX, int16_t, false, h + TAPS - 1);
         break;
     case X265B200_IP_VPS:
         p.shift = 6 - headRoom; p.offset = (int)((unsigned)-8192 << p.shift); p.maxVal = -1;
-        fir_kernel<PIX, int16_t, TAPS, true><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(PIX, int16_t, true, h);
         break;
     case X265B200_IP_VSP:
         p.shift = 6 + headRoom; p.offset = (1 << (p.shift - 1)) + (8192 << 6); p.maxVal = maxVal;
-        fir_kernel<int16_t, PIX, TAPS, true><<<grid, 256, 0, st>>>((const int16_t*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(int16_t, PIX, true, h);
         break;
     case X265B200_IP_VSS:
         p.shift = 6; p.offset = 0; p.maxVal = -1;
-        fir_kernel<int16_t, int16_t, TAPS, true><<<grid, 256, 0, st>>>((const int16_t*)src, ss, offSrc, (int16_t*)dst, ds, offDst, coeffIdx, n, p);
+        FIR(int16_t, int16_t, true, h);
         break;
     case X265B200_IP_HVPP:
     {
         int shift1 = 6 - headRoom, shift2 = 6 + headRoom;
         size_t smem = (size_t)w * (h + TAPS - 1) * sizeof(int16_t);
+        if (tiled && !(h & 3))
+        {
+            hv_tile_kernel<PIX, TAPS><<<ceil_div(n, 4), 128, 4 * smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, w, h,
+                                                                          shift1, (int)((unsigned)-8192 << shift1), shift2,
+                                                                          (1 << (shift2 - 1)) + (8192 << 6), maxVal);
+            break;
+        }
         hv_kernel<PIX, TAPS><<<n, 256, smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, w, h,
                                                   shift1, (int)((unsigned)-8192 << shift1), shift2,
                                                   (1 << (shift2 - 1)) + (8192 << 6), maxVal);
         break;
     }
     case X265B200_IP_P2S:
-        p2s_kernel<PIX><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);
+        if (tiled)
+            p2s_tile_kernel<PIX><<<ceil_div((long long)n * (w >> 2) * h, 256), 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);
+        else
+            p2s_kernel<PIX><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);
         break;
     default:
         return fail(ctx, X265B200_ERR_ARG, "interp: unknown kind");
     }
+#undef FIR
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }
