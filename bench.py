@@ -275,10 +275,10 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None      # sampled over warm-up + timed region + e2e (all under load)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count()
     marks = []
     t0, t1 = ev(), ev()
@@ -294,8 +294,6 @@ def run_b200_arm(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop() if sampler else None
-
     ms_per_step = ms / args.steps
     total_samples = world * launches_per_step * samples            # per step, all ranks
     value = total_samples / (ms_per_step * 1e-3) / 1e9
@@ -326,6 +324,7 @@ def run_b200_arm(args):
 
     # ---------------- e2e: same step from pinned host planes, H2D + kernels + D2H inside the timed region
     e2e = run_e2e(torch, pkg, ctx, geo, hF, hR, desc, F, args, world, dist)
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:

@@ -22,7 +22,7 @@ __global__ void fill(uint16_t* p, size_t n, uint64_t seed)
 
 typedef void (*kern_t)(const uint16_t*, intptr_t, const uint16_t*, intptr_t, const int32_t*, const int32_t*, int, int, int, int, int, int32_t*);
 
-struct Variant { const char* name; kern_t k; int threads; };
+struct Variant { const char* name; kern_t k; int threads; int gdiv; };
 
 int main(int argc, char** argv)
 {
@@ -33,14 +33,13 @@ int main(int argc, char** argv)
     fill<<<(F * pe + 255) / 256, 256>>>(A, F * pe, 1); fill<<<(F * pe + 255) / 256, 256>>>(B, F * pe, 77);
     CK(cudaDeviceSynchronize());
     Variant vars[] = {
-        { "u1 natural regs, 256 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 256 },
-        { "u1 natural regs, 128 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128 },
-        { "u1 minblk 6 (<=40 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 6>, 256 },
-        { "u1 minblk 8 (<=32 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 8>, 256 },
-        { "u2 natural regs", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 256 },
-        { "u2 minblk 4 (<=64 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 4>, 256 },
-        { "u2 minblk 5 (<=48 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 5>, 256 },
-        { "u2 minblk 6 (<=40 regs)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 6>, 256 },
+        { "u1 256 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 256, 1 },
+        { "u1 128 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 1 },
+        { "u1 64 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 64, 1 },
+        { "u1 128 thr, G/2", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 2 },
+        { "u1 128 thr, G/4", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 4 },
+        { "u2 128 thr, G/2", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 128, 2 },
+        { "u2 128 thr, G/4", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 128, 4 },
     };
     const int NV = sizeof(vars) / sizeof(vars[0]);
     for (int v = 0; v < NV; v++)
@@ -48,7 +47,7 @@ int main(int argc, char** argv)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void*)vars[v].k));
         printf("variant %d: %-28s regs %d\n", v, vars[v].name, fa.numRegs);
     }
-    int shapes[][2] = { {64, 64}, {64, 32}, {32, 32}, {16, 16}, {8, 8}, {4, 8} };
+    int shapes[][2] = { {64, 64}, {32, 32}, {32, 16}, {16, 16}, {16, 8}, {8, 8}, {4, 8} };
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (auto& sh : shapes)
     {
@@ -70,13 +69,15 @@ int main(int argc, char** argv)
         int32_t *dOA, *dOB, *out0, *out;
         CK(cudaMalloc(&dOA, n * 4)); CK(cudaMalloc(&dOB, n * 4)); CK(cudaMalloc(&out0, n * 4)); CK(cudaMalloc(&out, n * 4));
         CK(cudaMemcpy(dOA, oa.data(), n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dOB, ob.data(), n * 4, cudaMemcpyHostToDevice));
-        int T4 = (w / 4) * (h / 4), G = 1; while (G < T4 && G < 32) G <<= 1;
+        int T4 = (w / 4) * (h / 4), G0 = 1; while (G0 < T4 && G0 < 32) G0 <<= 1;
         double bytes = (double)n * w * h * 4 + n * 4.0;
+        int G = G0;
         printf("shape %dx%d  n=%d  G=%d  (roofline 6534.8 GB/s -> %.4f ms)\n", w, h, n, G, bytes / 6534.8e9 * 1e3);
         std::vector<int32_t> h0(n), h1(n);
         for (int v = 0; v < NV; v++)
         {
             int32_t* o = v == 0 ? out0 : out;
+            G = G0 / vars[v].gdiv; if (G < 1) G = 1;
             long long threads = (long long)n * G;
             int grid = (int)((threads + vars[v].threads - 1) / vars[v].threads);
             float best = 1e9f;

@@ -274,6 +274,17 @@ residual_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, i
 
 static int group_lanes(int tiles) { int g = pow2_ceil(tiles); return g > 32 ? 32 : g; }
 
+// lanes per block for the throughput kernels, tuned with tools/satd_lab.cu on B200: about four 4x4 tiles
+// per lane (two for blocks of fewer than 16 tiles) amortises the per-thread setup and the shuffle
+// reduction without starving the memory pipeline; 64x64 keeps a full warp.
+static int fast_group_lanes(int tiles)
+{
+    int per = tiles >= 16 ? 4 : 2;
+    int g = 1;
+    while (g * 2 * per <= tiles && g < 32) g <<= 1;
+    return g;
+}
+
 template<typename T>
 static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, intptr_t sa, const T* B, intptr_t sb,
                            const int32_t* offA, const int32_t* offB, int kdiv, int n, void* out, cudaStream_t st)
@@ -293,18 +304,20 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
     int grid = ceil_div(threads, 256);
     if (!((sa | sb) & 3))
     {
+        G = fast_group_lanes((w >> 2) * (h >> 2));
+        grid = ceil_div((long long)n * G, 128);
         // plane strides are multiples of 4 samples (always true for x265 planes): throughput kernels
         switch (op)
         {
         case X265B200_SAD:
-            tile4_fast_kernel<T, OP_SAD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
+            tile4_fast_kernel<T, OP_SAD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 128, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
             break;
         case X265B200_SATD:
         case X265B200_SA8D:
-            tile4_fast_kernel<T, OP_SATD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
+            tile4_fast_kernel<T, OP_SATD, int, int32_t, FAST_UNROLL, FAST_MINBLK><<<grid, 128, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (int32_t*)out);
             break;
         case X265B200_SSE_PP:
-            tile4_fast_kernel<T, OP_SSE, unsigned long long, unsigned long long, FAST_UNROLL, FAST_MINBLK><<<grid, 256, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (unsigned long long*)out);
+            tile4_fast_kernel<T, OP_SSE, unsigned long long, unsigned long long, FAST_UNROLL, FAST_MINBLK><<<grid, 128, 0, st>>>(A, sa, B, sb, offA, offB, kdiv, n, w, h, G, (unsigned long long*)out);
             break;
         default:
             return fail(ctx, X265B200_ERR_ARG, "pixelcmp: unknown op");
