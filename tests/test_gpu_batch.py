@@ -177,3 +177,33 @@ def test_dct_tensor_core_and_butterfly_paths_full_range(depth, torch_mod):
     finally:
         ctx.set_dct_path(0)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_idct_tensor_core_and_butterfly_paths_full_range(depth, torch_mod):
+    """inverse DCT 4..32 and IDST on the IMMA path and the CUDA-core twin; full-range int16 coefficients
+    exercise both saturation stages (TestBench only feeds +-PIXEL_MAX)."""
+    torch = torch_mod
+    from gpulib import context, pkg
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(199 + depth)
+    pmax = (1 << depth) - 1
+    n = 131
+    try:
+        for N in (32, 16, 8, 4):
+            inputs = [rng.integers(-pmax, pmax + 1, n * N * N).astype(np.int16), rng.integers(-32768, 32768, n * N * N).astype(np.int16),
+                      np.full(n * N * N, -32768, np.int16), np.full(n * N * N, 32767, np.int16)]
+            for src in inputs:
+                for stride, base in ((N, 0), (3 * N, 2), (3 * N + 1, 1)):
+                    offD = (np.arange(n) * N * stride + base).astype(np.int32)
+                    size = n * N * stride + 8
+                    for kind, d4 in ((pkg.TR_DCT, 0),) + (((pkg.TR_DST, 1),) if N == 4 else ()):
+                        ref = orc.idct_batch(N, src, np.full(size, 7, np.int16), stride, offD, dst4=d4)
+                        for path in (0, 1):
+                            ctx.set_dct_path(path)
+                            plane = torch.full((size,), 7, dtype=torch.int16, device="cuda")
+                            ctx.idct_batch(kind, N, dev(src), plane, stride, dev(offD))
+                            assert np.array_equal(plane.cpu().numpy(), ref), (N, stride, kind, path)
+    finally:
+        ctx.set_dct_path(0)
+    ctx.check()

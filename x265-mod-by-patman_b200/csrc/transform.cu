@@ -408,6 +408,8 @@ static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 
 bool launch_dct_imma(x265b200_ctx* ctx, int N, const int16_t* src, intptr_t srcStride, const int32_t* off, int n,
                      int16_t* dst, int shift1, int shift2, cudaStream_t st, int dst4);    // transform_mma.cu
+bool launch_idct_imma(x265b200_ctx* ctx, int N, const int16_t* src, int n, int16_t* dst, intptr_t dstStride,
+                      const int32_t* off, int shift1, int shift2, cudaStream_t st, int dst4);
 
 } // namespace b200
 
@@ -461,7 +463,12 @@ extern "C" int x265b200_idct_batch(x265b200_ctx* ctx, int kind, int N, const int
     cudaStream_t st = (cudaStream_t)stream;
     int s2 = 12 - (ctx->depth - 8);
 #define INV(NN, MODE) inv_kernel<NN, MODE><<<ceil_div(n, Tile<NN>::PER_CTA), TR_THREADS, 0, st>>>(src, n, dst, dstStride, off, 7, s2)
-    if (kind == X265B200_TR_DCT)
+    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path == 0 &&
+        launch_idct_imma(ctx, N, src, n, dst, dstStride, off, 7, s2, st, kind == X265B200_TR_DST))
+    {
+        // tensor-core path (transform_mma.cu)
+    }
+    else if (kind == X265B200_TR_DCT)
     {
         if (N == 4) INV(4, MODE_DCT); else if (N == 8) INV(8, MODE_DCT);
         else if (N == 16) INV(16, MODE_DCT); else if (N == 32) INV(32, MODE_DCT);

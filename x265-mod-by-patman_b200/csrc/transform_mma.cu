@@ -24,6 +24,16 @@ __device__ uint32_t c_A16[2][2][32];
 // N = 8 (two TUs per MMA) and N = 4 (eight TUs per MMA; [1] = DST-VII): block-diagonal A, [kind][stage][reg][lane]
 __device__ uint32_t c_A8[2][2][32];
 __device__ uint32_t c_A4[2][2][2][32];
+// inverse transforms: stage 1 uses a constant A (T^T, K order chosen for coalesced gathers), stage 2 uses the
+// stage-1 accumulators as A and a constant B.  [mt][reg][lane] / [ntile][reg][lane]
+__device__ uint32_t c_IA32[2][4][32];        // stage-1 A fragments, N = 32
+__device__ uint32_t c_IB32[4][2][32];        // stage-2 B fragments, N = 32
+__device__ uint32_t c_IA16[2][32];
+__device__ uint32_t c_IB16[2][32];
+__device__ uint32_t c_IA8[2][32];            // block-diagonal: two 8x8 TUs
+__device__ uint32_t c_IB8[32];
+__device__ uint32_t c_IA4[2][2][32];         // [kind: 0 DCT, 1 DST][reg][lane]: eight 4x4 TUs
+__device__ uint32_t c_IB4[2][32];
 
 static const short h_cosmag[32] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
                                     64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4 };
@@ -112,6 +122,82 @@ int upload_mma_tables(x265b200_ctx* ctx)
                 a4[0][stage][r][lane] = v4[0];
                 a4[1][stage][r][lane] = v4[1];
             }
+    // ---- inverse tables (see the kernels below for the index maps)
+    static uint32_t ia32[2][4][32], ib32[4][2][32], ia16[2][32], ib16[2][32], ia8[2][32], ib8[32], ia4[2][2][32], ib4[2][32];
+    for (int lane = 0; lane < 32; lane++)
+    {
+        int g = lane >> 2, t = lane & 3;
+        for (int mt = 0; mt < 2; mt++)
+            for (int r = 0; r < 4; r++)
+            {
+                int jp = mt * 16 + g + (r & 1) * 8, half = r >> 1;
+                uint32_t v = 0;
+                for (int e = 0; e < 4; e++) v |= (uint32_t)(uint8_t)(int8_t)tcoef(32, (half * 4 + e) * 4 + t, jp) << (8 * e);
+                ia32[mt][r][lane] = v;
+            }
+        for (int it = 0; it < 4; it++)
+            for (int half = 0; half < 2; half++)
+            {
+                uint32_t v = 0;
+                for (int e = 0; e < 4; e++) v |= (uint32_t)(uint8_t)(int8_t)tcoef(32, half * 16 + 4 * t + 2 * (e & 1) + (e >> 1), it * 8 + g) << (8 * e);
+                ib32[it][half][lane] = v;
+            }
+        for (int r = 0; r < 2; r++)
+        {
+            uint32_t v = 0;
+            for (int e = 0; e < 4; e++) v |= (uint32_t)(uint8_t)(int8_t)tcoef(16, e * 4 + t, g + r * 8) << (8 * e);
+            ia16[r][lane] = v;
+        }
+        for (int it = 0; it < 2; it++)
+        {
+            uint32_t v = 0;
+            for (int e = 0; e < 4; e++) v |= (uint32_t)(uint8_t)(int8_t)tcoef(16, 4 * t + 2 * (e & 1) + (e >> 1), it * 8 + g) << (8 * e);
+            ib16[it][lane] = v;
+        }
+        // N = 8: stage-1 A rows (tu = r, j' = g), slot 4t+e = (tu = t >> 1, k = 2e + (t & 1)); stage-2 B slot 4t+e = k' = 2t + e (e < 2)
+        for (int r = 0; r < 2; r++)
+        {
+            uint32_t v = 0;
+            for (int e = 0; e < 4; e++) v |= (uint32_t)(uint8_t)(int8_t)((t >> 1) == r ? tcoef(8, 2 * e + (t & 1), g) : 0) << (8 * e);
+            ia8[r][lane] = v;
+        }
+        {
+            uint32_t v = 0;
+            for (int e = 0; e < 2; e++) v |= (uint32_t)(uint8_t)(int8_t)tcoef(8, 2 * t + e, g) << (8 * e);
+            ib8[lane] = v;
+        }
+        // N = 4: stage-1 A rows (tu_r = (g >> 2) + 2r, j' = g & 3), slot 4t+e = (tu_s = t, k = e);
+        //        stage-2 B columns n = g = (set' = g >> 2, i' = g & 3), slot 4t+e = (set = t >> 1, k' = 2 (t & 1) + e) for e < 2
+        for (int kind = 0; kind < 2; kind++)
+        {
+            for (int r = 0; r < 2; r++)
+            {
+                uint32_t v = 0;
+                for (int e = 0; e < 4; e++)
+                {
+                    int c = ((g >> 2) + 2 * r) == t ? (kind ? dst4[e][g & 3] : tcoef(4, e, g & 3)) : 0;
+                    v |= (uint32_t)(uint8_t)(int8_t)c << (8 * e);
+                }
+                ia4[kind][r][lane] = v;
+            }
+            uint32_t v = 0;
+            for (int e = 0; e < 2; e++)
+            {
+                int kp = 2 * (t & 1) + e;
+                int c = (t >> 1) == (g >> 2) ? (kind ? dst4[kp][g & 3] : tcoef(4, kp, g & 3)) : 0;
+                v |= (uint32_t)(uint8_t)(int8_t)c << (8 * e);
+            }
+            ib4[kind][lane] = v;
+        }
+    }
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA32, ia32, sizeof(ia32)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB32, ib32, sizeof(ib32)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA16, ia16, sizeof(ia16)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB16, ib16, sizeof(ib16)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA8, ia8, sizeof(ia8)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB8, ib8, sizeof(ib8)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA4, ia4, sizeof(ia4)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB4, ib4, sizeof(ib4)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_A8, a8, sizeof(a8)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_A4, a4, sizeof(a4)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_A32, a32, sizeof(a32)));
@@ -142,6 +228,17 @@ __device__ __forceinline__ void imma16_su(int (&c)[4], const uint32_t (&a)[2], u
 
 // element offset of TU `tu`: explicit descriptor, or contiguous TUs when no descriptor array is given
 __device__ __forceinline__ size_t tu_offset(const int32_t* off, int tu, int nn) { return off ? (size_t)off[tu] : (size_t)tu * nn; }
+
+__device__ __forceinline__ void imma32_us(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void imma16_us(int (&c)[4], const uint32_t (&a)[2], uint32_t b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
 
 // four consecutive int16 as two packed words, with the widest load the address allows
 // (warp-uniform: all lanes of a TU share the alignment class when srcStride % 4 == 0)
@@ -408,6 +505,300 @@ dct_small_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const
             if (base + st_tu1 < n) *(uint32_t*)(dst + (size_t)(base + st_tu1) * NN + st_off) = __byte_perm(v2, v3, 0x5410);
         }
     }
+}
+
+// ================================================================== inverse transforms
+// Reference: out1[j][i] = clip16((sum_k T[k][i] * in[k][j] + 64) >> 7), out2 likewise on out1 with shift 12 - (depth - 8)
+// (dct.cpp:242-416,528-611).  With Y1 = stage-1 output:
+//     stage 1:  D1[j'][k'] = sum_k  T[k][j'] * in[k][k']       A = T^T (constant), B = in           (D1 = Y1^T)
+//     stage 2:  D2[j'][i'] = sum_k' D1[j'][k'] * T[k'][i']     A = D1 (accumulators), B = T (constant)
+// so the final accumulator is the row-major output block.  The stage-1 B operand walks DOWN the columns of
+// `in`; the contraction order (free) is chosen so that the four lanes of a quad read four consecutive rows, and
+// the column order (also free, it only renames the stage-2 contraction slots) so that one 32-bit load feeds
+// two n-tiles.
+__device__ __forceinline__ int recombine_clip(int hi, int lo, int shift)
+{
+    return min(32767, max(-32768, ((hi << 8) + lo) >> shift));
+}
+__device__ __forceinline__ void store_pair(int16_t* p, int v0, int v1)
+{
+    if (((uintptr_t)p & 3) == 0) *(uint32_t*)p = __byte_perm(v0, v1, 0x5410);
+    else { p[0] = (int16_t)v0; p[1] = (int16_t)v1; }
+}
+
+__global__ void __launch_bounds__(128)
+idct32_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, intptr_t dstStride,
+                   const int32_t* __restrict__ off, int shift1, int shift2)
+{
+    int lane = threadIdx.x & 31;
+    int warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    int nwarps = gridDim.x * 4;
+    if (warp >= n) return;
+    int g = lane >> 2, t = lane & 3;
+    uint32_t a1[2][4], b2[4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) a1[mt][r] = c_IA32[mt][r][lane];
+#pragma unroll
+    for (int it = 0; it < 4; it++) { b2[it][0] = c_IB32[it][0][lane]; b2[it][1] = c_IB32[it][1][lane]; }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+
+    // B1 gather: for (pair p, half, e): in[(half*4+e)*4 + t][p*16 + 2g .. +1] (one 32-bit load = n-tiles 2p and 2p+1)
+    uint32_t x[2][2][4];
+    {
+        const int16_t* q = src + (size_t)warp * 1024 + t * 32 + 2 * g;
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) x[p][half][e] = __ldg((const uint32_t*)(q + ((half * 4 + e) * 4) * 32 + p * 16));
+    }
+    for (int tu = warp; tu < n; tu += nwarps)
+    {
+        uint32_t blo[4][2], bhi[4][2];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+            {
+                // even columns (low halves) -> n-tile 2p, odd columns (high halves) -> n-tile 2p+1
+                uint32_t e01 = __byte_perm(x[p][half][0], x[p][half][1], 0x5140), e23 = __byte_perm(x[p][half][2], x[p][half][3], 0x5140);
+                uint32_t o01 = __byte_perm(x[p][half][0], x[p][half][1], 0x7362), o23 = __byte_perm(x[p][half][2], x[p][half][3], 0x7362);
+                blo[2 * p][half] = __byte_perm(e01, e23, 0x5410); bhi[2 * p][half] = __byte_perm(e01, e23, 0x7632);
+                blo[2 * p + 1][half] = __byte_perm(o01, o23, 0x5410); bhi[2 * p + 1][half] = __byte_perm(o01, o23, 0x7632);
+            }
+        int nxt = tu + nwarps;
+        if (nxt < n)
+        {
+            const int16_t* q = src + (size_t)nxt * 1024 + t * 32 + 2 * g;
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) x[p][half][e] = __ldg((const uint32_t*)(q + ((half * 4 + e) * 4) * 32 + p * 16));
+        }
+        int16_t* o = dst + off[tu] + (intptr_t)g * dstStride + 2 * t;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+        {
+            int v[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+            {
+                int chi[4] = { 0, 0, 0, 0 }, clo[4] = { add1, add1, add1, add1 };
+                imma32_ss(chi, a1[mt], bhi[nt][0], bhi[nt][1]);
+                imma32_su(clo, a1[mt], blo[nt][0], blo[nt][1]);
+#pragma unroll
+                for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+            }
+            // accumulators -> stage-2 A fragments (rows g: c0,c1; rows g+8: c2,c3; n-tiles 0,1 -> k 0..15, 2,3 -> 16..31)
+            uint32_t alo[4], ahi[4];
+            pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+            pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+            pack4(v[2][0], v[2][1], v[3][0], v[3][1], alo[2], ahi[2]);
+            pack4(v[2][2], v[2][3], v[3][2], v[3][3], alo[3], ahi[3]);
+#pragma unroll
+            for (int it = 0; it < 4; it++)
+            {
+                int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
+                imma32_ss(dhi, ahi, b2[it][0], b2[it][1]);
+                imma32_us(dlo, alo, b2[it][0], b2[it][1]);
+                store_pair(o + (intptr_t)(mt * 16) * dstStride + it * 8, recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
+                store_pair(o + (intptr_t)(mt * 16 + 8) * dstStride + it * 8, recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+            }
+        }
+    }
+}
+
+template<int TPW>
+__global__ void __launch_bounds__(128)
+idct16_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, intptr_t dstStride,
+                   const int32_t* __restrict__ off, int shift1, int shift2)
+{
+    int lane = threadIdx.x & 31;
+    int warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    int nwarps = gridDim.x * 4;
+    int ngroups = (n + TPW - 1) / TPW;
+    if (warp >= ngroups) return;
+    int g = lane >> 2, t = lane & 3;
+    uint32_t a1[2] = { c_IA16[0][lane], c_IA16[1][lane] };
+    uint32_t b2[2] = { c_IB16[0][lane], c_IB16[1][lane] };
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    uint32_t x[TPW][4];
+#pragma unroll
+    for (int u = 0; u < TPW; u++)
+    {
+        const int16_t* q = src + (size_t)min(warp * TPW + u, n - 1) * 256 + t * 16 + 2 * g;
+#pragma unroll
+        for (int e = 0; e < 4; e++) x[u][e] = __ldg((const uint32_t*)(q + e * 4 * 16));     // in[e*4 + t][2g .. 2g+1]
+    }
+    for (int grp = warp; grp < ngroups; grp += nwarps)
+    {
+        uint32_t blo[TPW][2], bhi[TPW][2];
+#pragma unroll
+        for (int u = 0; u < TPW; u++)
+        {
+            uint32_t e01 = __byte_perm(x[u][0], x[u][1], 0x5140), e23 = __byte_perm(x[u][2], x[u][3], 0x5140);
+            uint32_t o01 = __byte_perm(x[u][0], x[u][1], 0x7362), o23 = __byte_perm(x[u][2], x[u][3], 0x7362);
+            blo[u][0] = __byte_perm(e01, e23, 0x5410); bhi[u][0] = __byte_perm(e01, e23, 0x7632);
+            blo[u][1] = __byte_perm(o01, o23, 0x5410); bhi[u][1] = __byte_perm(o01, o23, 0x7632);
+        }
+        int nxt = grp + nwarps;
+        if (nxt < ngroups)
+        {
+#pragma unroll
+            for (int u = 0; u < TPW; u++)
+            {
+                const int16_t* q = src + (size_t)min(nxt * TPW + u, n - 1) * 256 + t * 16 + 2 * g;
+#pragma unroll
+                for (int e = 0; e < 4; e++) x[u][e] = __ldg((const uint32_t*)(q + e * 4 * 16));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TPW; u++)
+        {
+            int tu = grp * TPW + u;
+            if (tu >= n) break;
+            int v[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+            {
+                int chi[4] = { 0, 0, 0, 0 }, clo[4] = { add1, add1, add1, add1 };
+                imma16_ss(chi, a1, bhi[u][nt]);
+                imma16_su(clo, a1, blo[u][nt]);
+#pragma unroll
+                for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+            }
+            uint32_t alo[2], ahi[2];
+            pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+            pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+            int16_t* o = dst + off[tu] + (intptr_t)g * dstStride + 2 * t;
+#pragma unroll
+            for (int it = 0; it < 2; it++)
+            {
+                int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
+                imma16_ss(dhi, ahi, b2[it]);
+                imma16_us(dlo, alo, b2[it]);
+                store_pair(o + it * 8, recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
+                store_pair(o + (intptr_t)8 * dstStride + it * 8, recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+            }
+        }
+    }
+}
+
+// two 8x8 TUs (SMALL = 8) or eight 4x4 TUs (SMALL = 4) per MMA group, block-diagonal constant operands
+template<int SMALL, int UN>
+__global__ void __launch_bounds__(128)
+idct_small_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, intptr_t dstStride,
+                       const int32_t* __restrict__ off, int shift1, int shift2, int kind)
+{
+    constexpr int TPG = SMALL == 8 ? 2 : 8;
+    constexpr int NN = SMALL * SMALL;
+    int lane = threadIdx.x & 31;
+    int warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    int nwarps = gridDim.x * 4;
+    int ngroups = (n + TPG * UN - 1) / (TPG * UN);
+    if (warp >= ngroups) return;
+    int g = lane >> 2, t = lane & 3;
+    uint32_t a1[2], b2;
+    if (SMALL == 8) { a1[0] = c_IA8[0][lane]; a1[1] = c_IA8[1][lane]; b2 = c_IB8[lane]; }
+    else { a1[0] = c_IA4[kind][0][lane]; a1[1] = c_IA4[kind][1][lane]; b2 = c_IB4[kind][lane]; }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    // gather: slot 4t+e.  N = 8: TU t>>1, in[2e + (t&1)][g].  N = 4: TU (g>>2)*4 + t, in[e][g&3].
+    const int ld_tu = SMALL == 8 ? (t >> 1) : ((g >> 2) * 4 + t);
+    const int ld_off = SMALL == 8 ? (t & 1) * 8 + g : (g & 3);
+    const int ld_step = SMALL == 8 ? 16 : 4;
+    // output: accumulator rows g / g+8.  N = 8: TU 0 / 1, out[g][2t..].  N = 4: TU (t>>1)*4 + (g>>2) (+2), out[g&3][2(t&1)..]
+    const int st_tu0 = SMALL == 8 ? 0 : (t >> 1) * 4 + (g >> 2);
+    const int st_tu1 = SMALL == 8 ? 1 : (t >> 1) * 4 + (g >> 2) + 2;
+    const int st_row = SMALL == 8 ? g : (g & 3);
+    const int st_col = SMALL == 8 ? 2 * t : 2 * (t & 1);
+
+    int x[UN][4];
+#pragma unroll
+    for (int u = 0; u < UN; u++)
+    {
+        const int16_t* q = src + (size_t)min((warp * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off;
+#pragma unroll
+        for (int e = 0; e < 4; e++) x[u][e] = __ldg(q + e * ld_step);
+    }
+    for (int grp = warp; grp < ngroups; grp += nwarps)
+    {
+        uint32_t blo[UN], bhi[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) pack4(x[u][0], x[u][1], x[u][2], x[u][3], blo[u], bhi[u]);
+        int nxt = grp + nwarps;
+        if (nxt < ngroups)
+        {
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+            {
+                const int16_t* q = src + (size_t)min((nxt * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off;
+#pragma unroll
+                for (int e = 0; e < 4; e++) x[u][e] = __ldg(q + e * ld_step);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++)
+        {
+            int base = (grp * UN + u) * TPG;
+            if (base >= n) break;
+            int chi[4] = { 0, 0, 0, 0 }, clo[4] = { add1, add1, add1, add1 };
+            imma16_ss(chi, a1, bhi[u]);
+            imma16_su(clo, a1, blo[u]);
+            int v0 = recombine_clip(chi[0], clo[0], shift1), v1 = recombine_clip(chi[1], clo[1], shift1);
+            int v2 = recombine_clip(chi[2], clo[2], shift1), v3 = recombine_clip(chi[3], clo[3], shift1);
+            uint32_t alo[2], ahi[2];
+            pack4(v0, v1, 0, 0, alo[0], ahi[0]);          // slots e = 2,3 are padding (their B rows are zero)
+            pack4(v2, v3, 0, 0, alo[1], ahi[1]);
+            int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
+            imma16_ss(dhi, ahi, b2);
+            imma16_us(dlo, alo, b2);
+            if (base + st_tu0 < n)
+                store_pair(dst + off[base + st_tu0] + (intptr_t)st_row * dstStride + st_col,
+                           recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
+            if (base + st_tu1 < n)
+                store_pair(dst + off[base + st_tu1] + (intptr_t)st_row * dstStride + st_col,
+                           recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+        }
+    }
+}
+
+bool launch_idct_imma(x265b200_ctx* ctx, int N, const int16_t* src, int n, int16_t* dst, intptr_t dstStride,
+                      const int32_t* off, int shift1, int shift2, cudaStream_t st, int dst4)
+{
+    if ((uintptr_t)src & 3) return false;
+    int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    int grid = sms * 8;
+    if (N == 32)
+    {
+        if (grid > ceil_div(n, 4)) grid = ceil_div(n, 4);
+        idct32_imma_kernel<<<grid, 128, 0, st>>>(src, n, dst, dstStride, off, shift1, shift2);
+    }
+    else if (N == 16)
+    {
+        int need = ceil_div(ceil_div(n, 4), 4);
+        if (grid > need) grid = need;
+        idct16_imma_kernel<4><<<grid, 128, 0, st>>>(src, n, dst, dstStride, off, shift1, shift2);
+    }
+    else if (N == 8)
+    {
+        int need = ceil_div(ceil_div(n, 2 * 4), 4);
+        if (grid > need) grid = need;
+        idct_small_imma_kernel<8, 4><<<grid, 128, 0, st>>>(src, n, dst, dstStride, off, shift1, shift2, 0);
+    }
+    else if (N == 4)
+    {
+        int need = ceil_div(ceil_div(n, 8 * 4), 4);
+        if (grid > need) grid = need;
+        idct_small_imma_kernel<4, 4><<<grid, 128, 0, st>>>(src, n, dst, dstStride, off, shift1, shift2, dst4 ? 1 : 0);
+    }
+    else
+        return false;
+    return true;
 }
 
 // returns true if it handled the request
