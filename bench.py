@@ -313,8 +313,14 @@ def run_b200_arm(args):
     dct_bytes = samples * 4                                        # int16 in + int16 out per coefficient
     dominant = "satd" if tsum["satd"] >= tsum["dct"] else "dct"
     ach = (satd_bytes / (satd_ms * 1e-3) if dominant == "satd" else dct_bytes / (dct_ms * 1e-3)) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tile4_kernel<uint16,SATD>" if dominant == "satd" else "fwd_kernel<N,DCT>",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1f_satd_traffic.json")
+    if dominant == "satd" and os.path.exists(tp):
+        # dram__bytes_read + write per launch of this kernel from the committed ncu --set full capture of this workload
+        traffic = json.load(open(tp))["dram_bytes_per_launch_avg"]
+    roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": satd_bytes if dominant == "satd" else dct_bytes,
                 "peak_source": peak_src,
                 "share_of_step": tsum[dominant] / (ms if world == 1 else sum(tsum.values())),
                 "other": {"satd_GBps": satd_bytes / (satd_ms * 1e-3) / 1e9, "dct_GBps": dct_bytes / (dct_ms * 1e-3) / 1e9,

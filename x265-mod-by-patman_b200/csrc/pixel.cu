@@ -209,6 +209,127 @@ sa8d_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intpt
     if (live && l == 0) out[blk] = acc;
 }
 
+// Throughput sa8d for planes with strides that are multiples of 4 samples: grouped chunk loads, packed
+// differences, vertical 8-point Hadamard on packed 16-bit lanes (|value| <= 8 * 4095 < 2^15), horizontal in int32.
+template<typename T>
+__global__ void __launch_bounds__(128)
+sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
+                 const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
+                 int n, int w, int h, int G, int mode16, int32_t* __restrict__ out)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lg = __ffs(G) - 1;
+    int blk = (int)(gid >> lg);
+    int l = (int)gid & (G - 1);
+    bool live = blk < n;
+    int T8 = (w >> 3) * (h >> 3);
+    const T* a = A;
+    const T* b = B;
+    if (live) { a += offA[blk]; b += offB[blk]; }
+    int iters = (T8 + G - 1) / G;
+    int acc = 0;
+    for (int k = 0; k < iters; k++)
+    {
+        int t = l + k * G;
+        bool valid = live && t < T8;
+        int raw = 0;
+        if (valid)
+        {
+            int x, y;
+            if (mode16)
+            {
+                int b16 = t >> 2, q = t & 3, bw = w >> 4;
+                x = ((b16 % bw) << 4) + ((q & 1) << 3);
+                y = ((b16 / bw) << 4) + ((q >> 1) << 3);
+            }
+            else
+            {
+                int tw = w >> 3;
+                x = (t % tw) << 3; y = (t / tw) << 3;
+            }
+            const T* pa = a + (intptr_t)y * sa + x;
+            const T* pb = b + (intptr_t)y * sb + x;
+            uint32_t d[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+            {
+                uint32_t wa[4], wb[4];
+                load_row_quads<2>(pa + r * sa, wa);
+                load_row_quads<2>(pb + r * sb, wb);
+#pragma unroll
+                for (int c = 0; c < 4; c++) d[r][c] = wa[c] - wb[c];
+            }
+            // vertical 8-point Hadamard, packed
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            {
+#pragma unroll
+                for (int step = 1; step < 8; step <<= 1)
+#pragma unroll
+                    for (int i = 0; i < 8; i += step << 1)
+#pragma unroll
+                        for (int j = i; j < i + step; j++)
+                        {
+                            uint32_t u = d[j][c], v = d[j + step][c];
+                            d[j][c] = u + v; d[j + step][c] = u - v;
+                        }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+            {
+                int m[8];
+#pragma unroll
+                for (int c = 0; c < 4; c++) unpack_s16x2(d[r][c], m[2 * c], m[2 * c + 1]);
+#pragma unroll
+                for (int step = 1; step < 8; step <<= 1)
+#pragma unroll
+                    for (int i = 0; i < 8; i += step << 1)
+#pragma unroll
+                        for (int j = i; j < i + step; j++)
+                        {
+                            int u = m[j], v = m[j + step];
+                            m[j] = u + v; m[j + step] = u - v;
+                        }
+#pragma unroll
+                for (int c = 0; c < 8; c++) raw += abs(m[c]);
+            }
+        }
+        if (mode16)
+        {
+            raw += __shfl_xor_sync(0xffffffffu, raw, 1);
+            raw += __shfl_xor_sync(0xffffffffu, raw, 2);
+            if (valid && (t & 3) == 0) acc += (raw + 2) >> 2;
+        }
+        else if (valid)
+            acc += (raw + 2) >> 2;
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) out[blk] = acc;
+}
+
+// residual = A - B for planes with strides % 4 == 0: one thread per 4 samples, chunk loads
+template<typename T>
+__global__ void __launch_bounds__(256)
+residual_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
+                     const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
+                     int n, int w, int h, int16_t* __restrict__ dst)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int qw = w >> 2;
+    int per = qw * h;
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid % per);
+    int y = r / qw, x = (r % qw) << 2;
+    uint32_t wa[2], wb[2];
+    load_row_quads<1>(A + offA[blk] + (intptr_t)y * sa + x, wa);
+    load_row_quads<1>(B + offB[blk] + (intptr_t)y * sb + x, wb);
+    int d0, d1, d2, d3;
+    unpack_s16x2(wa[0] - wb[0], d0, d1);
+    unpack_s16x2(wa[1] - wb[1], d2, d3);
+    *(uint2*)(dst + (size_t)blk * w * h + y * w + x) = make_uint2((uint32_t)(d0 & 0xffff) | ((uint32_t)d1 << 16), (uint32_t)(d2 & 0xffff) | ((uint32_t)d3 << 16));
+}
+
 // ADS (pixel.cpp:121-165): one warp per job; ordered compaction with ballot + popc.
 __global__ void __launch_bounds__(128)
 ads_kernel(int terms, int half, const int32_t* __restrict__ encDC, const uint32_t* __restrict__ sums,
@@ -295,6 +416,12 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
         int mode16 = !((w | h) & 15);
         int G = group_lanes((w >> 3) * (h >> 3));
         long long threads = (long long)n * G;
+        if (!((sa | sb) & 3))
+        {
+            sa8d_fast_kernel<T><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
+            B200_LAUNCH_CHECK(ctx);
+            return X265B200_OK;
+        }
         sa8d_kernel<T><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
         B200_LAUNCH_CHECK(ctx);
         return X265B200_OK;
@@ -422,7 +549,14 @@ extern "C" int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const vo
     if (n == 0) return X265B200_OK;
     long long threads = (long long)n * (w >> 2) * h;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->pixbytes == 1)
+    if (!((sa | sb) & 3))
+    {
+        if (ctx->pixbytes == 1)
+            residual_fast_kernel<uint8_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint8_t*)A, sa, (const uint8_t*)B, sb, offA, offB, n, w, h, dst);
+        else
+            residual_fast_kernel<uint16_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint16_t*)A, sa, (const uint16_t*)B, sb, offA, offB, n, w, h, dst);
+    }
+    else if (ctx->pixbytes == 1)
         residual_kernel<uint8_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint8_t*)A, sa, (const uint8_t*)B, sb, offA, offB, n, w, h, dst);
     else
         residual_kernel<uint16_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint16_t*)A, sa, (const uint16_t*)B, sb, offA, offB, n, w, h, dst);

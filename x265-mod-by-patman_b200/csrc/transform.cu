@@ -388,6 +388,33 @@ dequant_normal_kernel(const int16_t* __restrict__ q, int16_t* __restrict__ coef,
     *(int4*)(coef + pos) = o;
 }
 
+// 8 coefficients per thread (num % 8 == 0): 128-bit coefficient loads, two 128-bit table loads
+__global__ void __launch_bounds__(256)
+dequant_scaling_vec_kernel(const int16_t* __restrict__ q, const int32_t* __restrict__ dq, int16_t* __restrict__ coef,
+                           int num, long long total, int per, int shift)
+{
+    long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) << 3;
+    if (pos >= total) return;
+    int tp = (int)(pos % num);
+    int4 v = __ldg((const int4*)(q + pos));
+    int4 t0 = __ldg((const int4*)(dq + tp)), t1 = __ldg((const int4*)(dq + tp + 4));
+    int c[8] = { (int16_t)(v.x & 0xffff), v.x >> 16, (int16_t)(v.y & 0xffff), v.y >> 16,
+                 (int16_t)(v.z & 0xffff), v.z >> 16, (int16_t)(v.w & 0xffff), v.w >> 16 };
+    int d[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
+    shift += 4;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        int prod = (int)((unsigned)c[i] * (unsigned)d[i]);
+        c[i] = shift > per ? clip16((int)((unsigned)prod + (1u << (shift - per - 1))) >> (shift - per))
+                           : clip16((int)((unsigned)clip16(prod) * (1u << (per - shift))));
+    }
+    int4 o;
+    o.x = (c[0] & 0xffff) | (c[1] << 16); o.y = (c[2] & 0xffff) | (c[3] << 16);
+    o.z = (c[4] & 0xffff) | (c[5] << 16); o.w = (c[6] & 0xffff) | (c[7] << 16);
+    *(int4*)(coef + pos) = o;
+}
+
 __global__ void __launch_bounds__(256)
 dequant_scaling_kernel(const int16_t* __restrict__ q, const int32_t* __restrict__ dq, int16_t* __restrict__ coef,
                        int num, long long total, int per, int shift)
@@ -522,6 +549,12 @@ extern "C" int x265b200_dequant_scaling_batch(x265b200_ctx* ctx, const int16_t* 
     if (num <= 0 || n < 0) return fail(ctx, X265B200_ERR_ARG, "dequant_scaling: bad size");
     if (n == 0) return X265B200_OK;
     long long total = (long long)num * n;
+    if (!(num & 7) && !(((uintptr_t)q | (uintptr_t)coef | (uintptr_t)dq) & 15))
+    {
+        dequant_scaling_vec_kernel<<<ceil_div(total >> 3, 256), 256, 0, (cudaStream_t)stream>>>(q, dq, coef, num, total, per, shift);
+        B200_LAUNCH_CHECK(ctx);
+        return X265B200_OK;
+    }
     dequant_scaling_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(q, dq, coef, num, total, per, shift);
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
