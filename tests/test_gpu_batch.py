@@ -207,3 +207,64 @@ def test_idct_tensor_core_and_butterfly_paths_full_range(depth, torch_mod):
     finally:
         ctx.set_dct_path(0)
     ctx.check()
+
+
+@pytest.mark.parametrize("width,height,depth", [(1920, 1080, 8), (7680, 4320, 12)])
+def test_full_size_properties_other_configs(width, height, depth, torch_mod):
+    """BASELINE configs #2 (1080p 8-bit) and #5 (4320p 12-bit) at full size: additivity over tilings vs numpy,
+    identical-block zeros, sampled oracle checks for SATD / sa8d, residual -> DCT -> IDCT round trip bounded error."""
+    torch = torch_mod
+    from gpulib import context, pkg
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(width, height)
+    A = make_plane(geo, depth, 31, "natural"); B = make_plane(geo, depth, 32, "natural")
+    vt = np.uint8 if depth == 8 else np.int16
+    dA, dB = dev(A.view(vt)), dev(B.view(vt))
+    tot = {}
+    for (w, h) in ((64, 64), (16, 16), (8, 8)):
+        offA, offMV = tile_blocks(geo, w, h, seed=2)
+        dO, dM = dev(offA), dev(offMV)
+        sad = torch.zeros(len(offA), dtype=torch.int32, device="cuda")
+        sse = torch.zeros(len(offA), dtype=torch.int64, device="cuda")
+        ctx.pixelcmp_batch(OP_SAD, w, h, dA, geo.stride, dB, geo.stride, dO, dO, sad)
+        ctx.pixelcmp_batch(OP_SSE_PP, w, h, dA, geo.stride, dB, geo.stride, dO, dO, sse)
+        tot[w] = (int(sad.sum(dtype=torch.int64)), int(sse.sum()))
+        z = torch.ones(len(offA), dtype=torch.int32, device="cuda")
+        ctx.pixelcmp_batch(OP_SA8D, w, h, dB, geo.stride, dB, geo.stride, dM, dM, z)
+        assert int(z.abs().max()) == 0
+        sel = np.linspace(0, len(offA) - 1, 48).astype(np.int64)
+        for op in (OP_SATD, OP_SA8D):
+            out = torch.zeros(len(offA), dtype=torch.int32, device="cuda")
+            ctx.pixelcmp_batch(op, w, h, dA, geo.stride, dB, geo.stride, dO, dM, out)
+            ref = orc.pixelcmp_batch(op, w, h, A, geo.stride, B, geo.stride, offA[sel].copy(), offMV[sel].copy())
+            assert np.array_equal(out.cpu().numpy()[sel], ref), (w, op)
+    assert len(set(tot.values())) == 1
+    cw, ch = geo.coded()
+    a2 = A.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + ch, geo.margin_x:geo.margin_x + cw].astype(np.int64)
+    b2 = B.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + ch, geo.margin_x:geo.margin_x + cw].astype(np.int64)
+    want_sse = int(((a2 - b2) ** 2).sum())
+    if depth == 8:
+        pass                                   # per-block values are exact; only the 64-bit total is compared
+    assert tot[64] == (int(np.abs(a2 - b2).sum()), want_sse)
+    # residual -> DCT -> IDCT: the HEVC core transform pair reconstructs the residual up to the rounding of its
+    # 16-bit intermediate (coarser at higher depth, where the forward shifts grow); loose sanity bound here, the
+    # exact values are compared with the oracle on a sample below
+    for N in (32, 8):
+        offA, offMV = tile_blocks(geo, N, N, seed=3)
+        n = len(offA)
+        res = torch.zeros(n * N * N, dtype=torch.int16, device="cuda")
+        ctx.residual_batch(N, N, dA, geo.stride, dB, geo.stride, dev(offA), dev(offMV), res)
+        coef = torch.zeros_like(res); rec = torch.zeros_like(res)
+        ctx.dct_batch(pkg.TR_DCT, N, res, N, None, coef, count=n)
+        off = torch.arange(n, dtype=torch.int32, device="cuda") * (N * N)
+        ctx.idct_batch(pkg.TR_DCT, N, coef, rec, N, off)
+        err = (rec.to(torch.int32) - res.to(torch.int32)).abs().max()
+        assert int(err) <= (4 << (depth - 8)), (N, int(err))
+        sel = np.linspace(0, n - 1, 16).astype(np.int64)
+        rres = orc.residual_batch(N, N, A, geo.stride, B, geo.stride, offA[sel].copy(), offMV[sel].copy())
+        rcoef = orc.dct_batch(N, rres, N, (np.arange(len(sel)) * N * N).astype(np.int32))
+        got = coef.cpu().numpy().reshape(n, N * N)[sel].ravel()
+        assert np.array_equal(got, rcoef), N
+        rrec = orc.idct_batch(N, rcoef, np.zeros(len(sel) * N * N, np.int16), N, (np.arange(len(sel)) * N * N).astype(np.int32))
+        assert np.array_equal(rec.cpu().numpy().reshape(n, N * N)[sel].ravel(), rrec), N
+    ctx.check()
