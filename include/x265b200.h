@@ -125,7 +125,8 @@ int x265b200_ads_batch(x265b200_ctx* ctx, int terms, int half, const int32_t* en
  * use srcStride = N).  (dct_t, primitives.h:153) */
 int x265b200_dct_batch(x265b200_ctx* ctx, int kind, int N, const int16_t* src, intptr_t srcStride,
                        const int32_t* off, int n, int16_t* dst, x265b200_stream stream);
-/* inverse: src block i contiguous at src + i*N*N, dst block i at dst + off[i] with dstStride. (idct_t) */
+/* inverse: src block i contiguous at src + i*N*N, dst block i at dst + off[i] with dstStride
+ * (off == NULL: dst + i*N*N). (idct_t) */
 int x265b200_idct_batch(x265b200_ctx* ctx, int kind, int N, const int16_t* src, int n,
                         int16_t* dst, intptr_t dstStride, const int32_t* off, x265b200_stream stream);
 
@@ -156,6 +157,19 @@ int x265b200_interp_batch(x265b200_ctx* ctx, int kind, int taps, int w, int h,
 int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const void* A, intptr_t strideA,
                             const void* B, intptr_t strideB, const int32_t* offA, const int32_t* offB,
                             int n, int16_t* dst, x265b200_stream stream);
+
+/* Inter luma TU reconstruction chain for n TUs of size N in one call: the slot sequence
+ * sub_ps -> dct -> quant -> dequant_normal -> (DC-only shortcut | idct) -> add_ps -> sse_pp that
+ * reference encoder/search.cpp:5536-5575 drives through quant.cpp:397-480 and :543-605 (no RDOQ / psy / sign hiding /
+ * transform skip, scaling lists off).  quantCoeff: N*N table; qBits/add as quant.cpp:465-466; dqScale/dqShift as
+ * quant.cpp:556,567.  Outputs: qCoef[n*N*N], numSig[n], recon blocks at recon + offR[i] (the prediction when
+ * numSig == 0), sseZero[n] = sse(fenc, pred) (may be NULL) and sseRecon[n] = sse(fenc, recon).
+ * Intermediates live in an L2-sized scratch taken from the stream-ordered allocator. */
+int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
+                            const int32_t* offF, const int32_t* offP, int n,
+                            const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                            int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
+                            uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream);
 
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 

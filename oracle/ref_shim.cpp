@@ -222,6 +222,45 @@ int ref_p2s(int w, int h, const pixel* s, intptr_t ss, int16_t* d, intptr_t ds)
     return 0;
 }
 
+/* ---- inter luma TU chain composed from the reference's own slots, in the order search.cpp:5536-5575 / quant.cpp:397-605 call them ---- */
+void ref_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* quantCoeff,
+                  int qBits, int add, int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr,
+                  uint64_t* sseZero, uint64_t* sseRecon)
+{
+    ensure();
+    int cu = trIdx(N);
+    ALIGN_VAR_32(int16_t, resi[32 * 32]);
+    ALIGN_VAR_32(int16_t, coef[32 * 32]);
+    ALIGN_VAR_32(int16_t, dq[32 * 32]);
+    ALIGN_VAR_32(int16_t, rec[32 * 32]);
+    ALIGN_VAR_32(int32_t, deltaU[32 * 32]);
+    ALIGN_VAR_32(int16_t, q[32 * 32]);
+    g_c.cu[cu].sub_ps(resi, N, fenc, pred, sf, sp);
+    g_c.cu[cu].dct(resi, coef, N);
+    uint32_t ns = g_c.quant(coef, quantCoeff, deltaU, q, qBits, add, N * N);
+    memcpy(qCoef, q, sizeof(int16_t) * N * N);
+    *numSig = ns;
+    *sseZero = g_c.cu[cu].sse_pp(fenc, sf, pred, sp);
+    if (!ns)
+    {
+        g_c.pu[cu].copy_pp(recon, sr, pred, sp);
+        *sseRecon = *sseZero;
+        return;
+    }
+    g_c.dequant_normal(q, dq, N * N, dqScale, dqShift);
+    if (ns == 1 && q[0] != 0)
+    {
+        const int shift_1st = 7 - 6, add_1st = 1 << (shift_1st - 1);
+        const int shift_2nd = 12 - (X265_DEPTH - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
+        int dc_val = (((dq[0] * (64 >> 6) + add_1st) >> shift_1st) * (64 >> 3) + add_2nd) >> shift_2nd;
+        g_c.cu[cu].blockfill_s[NONALIGNED](rec, N, (int16_t)dc_val);
+    }
+    else
+        g_c.cu[cu].idct(dq, rec, N);
+    g_c.cu[cu].add_ps[NONALIGNED](recon, sr, pred, rec, sp, N);
+    *sseRecon = g_c.cu[cu].sse_pp(fenc, sf, recon, sr);
+}
+
 /* ---- slot census for the coverage contract (SURVEY.md section 8a checklist) ---- */
 int ref_count_nonnull_slots()
 {

@@ -194,3 +194,54 @@ def test_interp_batches(depth):
             got = got.view(dt) if pix_out and depth > 8 else got
             assert np.array_equal(got, ref), (taps, w, h, kind)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_tu_chain_batch(depth):
+    """fused inter-luma TU chain vs the oracle's composition, all TU sizes, QPs from near-lossless to 51 so that
+    the cbf == 0, DC-only and full inverse paths all occur; 1080p-sized tiling so several scratch chunks run."""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane, tile_blocks
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(832, 480)
+    F = make_plane(geo, depth, 41, "natural")
+    Pn = make_plane(geo, depth, 42, "natural")
+    rng = np.random.default_rng(depth)
+    # prediction = mixture: mostly close to fenc (small residual), some areas far
+    mix = rng.integers(0, 4, geo.plane_elems)
+    P = np.where(mix == 0, Pn, np.clip(F.astype(np.int64) + rng.integers(-3, 4, geo.plane_elems) * (1 << (depth - 8)), 0, orc.pmax)).astype(orc.pix)
+    flat = [26214, 23302, 20560, 18396, 16384, 14564]; inv = [40, 45, 51, 57, 64, 72]
+    seen = set()
+    Pflat = np.clip(F.astype(np.int64) - (9 << (depth - 8)), 0, orc.pmax).astype(orc.pix)      # constant residual -> DC-only TUs
+    for N, qp in ((32, 37), (16, 27), (8, 45), (4, 22), (32, 51), (8, 4), (16, 40), (16, 30), (32, 31), (4, 33)):
+        offF, offMV = tile_blocks(geo, N, N, seed=4)
+        offP = offF.copy() if qp != 27 else offMV         # zero-MV prediction, or displaced prediction (large residual)
+        Pcur = Pflat if qp in (30, 31, 33) else P
+        n = len(offF)
+        per, rem = qp // 6, qp % 6
+        tshift = 15 - depth - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+        qbits = 14 + per + tshift
+        add = 85 << (qbits - 9)
+        qc = np.full(N * N, flat[rem], np.int32)
+        scale, shift = inv[rem] << per, 20 - 14 - tshift
+        recon0 = np.full(geo.plane_elems, 5, orc.pix)
+        rq, rns, rz, rr = orc.tu_chain_batch(N, F, geo.stride, Pcur, geo.stride, offF, offP, qc, qbits, add, scale, shift, recon0, geo.stride, offF)
+        d_recon = dev(pix_view(np.full(geo.plane_elems, 5, orc.pix), depth))
+        q = torch.zeros(n * N * N, dtype=torch.int16, device="cuda"); ns = torch.zeros(n, dtype=torch.int32, device="cuda")
+        z = torch.zeros(n, dtype=torch.int64, device="cuda"); r = torch.zeros(n, dtype=torch.int64, device="cuda")
+        ctx.tu_chain_batch(N, dev(pix_view(F, depth)), geo.stride, dev(pix_view(Pcur, depth)), geo.stride, dev(offF), dev(offP), dev(qc),
+                           qbits, add, scale, shift, q, ns, d_recon, geo.stride, dev(offF), z, r)
+        assert np.array_equal(ns.cpu().numpy().astype(np.uint32), rns), (N, qp)
+        assert np.array_equal(q.cpu().numpy(), rq), (N, qp)
+        assert np.array_equal(z.cpu().numpy().astype(np.uint64), rz), (N, qp)
+        assert np.array_equal(r.cpu().numpy().astype(np.uint64), rr), (N, qp)
+        got = d_recon.cpu().numpy()
+        got = got.view(orc.pix) if depth > 8 else got
+        assert np.array_equal(got, recon0), (N, qp)
+        qm = rq.reshape(n, N * N)
+        seen |= {"zero"} if (rns == 0).any() else set()
+        seen |= {"dc"} if ((rns == 1) & (qm[:, 0] != 0)).any() else set()
+        seen |= {"full"} if (rns > 1).any() else set()
+    assert seen == {"zero", "dc", "full"}, seen
+    ctx.check()

@@ -268,3 +268,33 @@ def test_batched_drivers(libs):
             res = o.residual_batch(w, h, A, stride, B, stride, offA, offB)
             off = (np.arange(n) * w * w).astype(np.int32)
             assert np.array_equal(o.dct_batch(w, res, w, off), r.residual_dct_batch(w, A, stride, B, stride, offA, offB, 2))
+
+
+def test_tu_chain(libs):
+    """inter luma TU chain: oracle composition vs the reference's own slots called in x265's order"""
+    o, r = libs
+    rng = np.random.default_rng(13)
+    D = o.depth
+    stride = 96
+    flat = [26214, 23302, 20560, 18396, 16384, 14564]
+    inv = [40, 45, 51, 57, 64, 72]
+    for trial in range(60):
+        N = [4, 8, 16, 32][trial % 4]
+        qp = [4, 17, 22, 27, 32, 37, 45, 51][trial % 8]
+        per, rem = qp // 6, qp % 6
+        log2 = {4: 2, 8: 3, 16: 4, 32: 5}[N]
+        tshift = 15 - D - log2
+        qbits = 14 + per + tshift
+        add = (171 if trial % 3 == 0 else 85) << (qbits - 9)
+        qc = np.full(N * N, flat[rem], np.int32)
+        base = rng.integers(0, o.pmax + 1, stride * 40).astype(np.int64)
+        noise = rng.integers(-(3 << (D - 8)) * (1 + trial % 5), (3 << (D - 8)) * (1 + trial % 5) + 1, stride * 40)
+        fenc = np.clip(base + noise, 0, o.pmax).astype(o.pix)
+        pred = base.astype(o.pix) if trial % 7 else fenc.copy()
+        if trial % 11 == 5:
+            pred = np.clip(base + 9, 0, o.pmax).astype(o.pix); fenc = base.astype(o.pix)   # DC-only residual
+        r0 = np.full(stride * 40, 3, o.pix); r1 = r0.copy()
+        a = o.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r0, 7, stride)
+        b = r.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r1, 7, stride)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (N, qp, trial)
+        assert np.array_equal(r0, r1), (N, qp, trial)

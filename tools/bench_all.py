@@ -109,6 +109,19 @@ def main():
     ms = timeit(lambda: ctx.quant_batch(coef, qc, None, q, 21, 1 << 20, 1024, nb, sig)); add("nquant 32x32", ms, S * 4, S)
     ms = timeit(lambda: ctx.dequant_normal_batch(q, coef, S, 64 << 4, 5)); add("dequant_normal", ms, S * 4, S)
     ms = timeit(lambda: ctx.dequant_scaling_batch(q, qc, coef, 1024, nb, 4, 2)); add("dequant_scaling 32x32", ms, S * 4, S)
+    # ---- fused inter-luma TU chain (sub_ps, dct, quant, dequant, idct, add_ps, sse): 3b + 2 bytes per sample
+    recon = torch.empty(F * pe, dtype=A.dtype, device="cuda")
+    for N in (32, 16, 8, 4):
+        oa, ob = desc(N, N)
+        n = oa.numel()
+        qcN = torch.full((N * N,), 16384, dtype=torch.int32, device="cuda")
+        tshift = 15 - D - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+        qbits = 14 + 4 + tshift                                  # qp 28
+        qo = torch.empty(S, dtype=torch.int16, device="cuda"); ns = torch.empty(n, dtype=torch.int32, device="cuda")
+        z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
+        ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
+                                               qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
+        add("tu_chain %dx%d (6 stage kernels, L2-resident intermediates)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
     # ---- interpolation, frame-tiled 64x64 and 16x16 luma, 8x8 chroma-size blocks
     dstP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); dstS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
     srcS = torch.randint(-8192, 8192, (F * pe,), dtype=torch.int16, device="cuda")

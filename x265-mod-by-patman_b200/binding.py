@@ -133,8 +133,9 @@ class Context:
         n = int(off.numel()) if off is not None else int(count)
         self._call("x265b200_dct_batch", kind, N, _dp(src), _ss(stride), _dp(off), n, _dp(dst), C.c_void_p(stream))
 
-    def idct_batch(self, kind, N, src, dst, stride, off, stream=0):
-        self._call("x265b200_idct_batch", kind, N, _dp(src), int(off.numel()), _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))
+    def idct_batch(self, kind, N, src, dst, stride, off, stream=0, count=None):
+        n = int(off.numel()) if off is not None else int(count)
+        self._call("x265b200_idct_batch", kind, N, _dp(src), n, _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))
 
     def quant_batch(self, coef, qc, deltaU, qCoef, qBits, add, numCoeff, n, numSig, stream=0):
         self._call("x265b200_quant_batch", _dp(coef), _dp(qc), _dp(deltaU), _dp(qCoef), qBits, add, numCoeff, n,
@@ -149,6 +150,12 @@ class Context:
     def interp_batch(self, kind, taps, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, stream=0):
         self._call("x265b200_interp_batch", IP_KINDS[kind], taps, w, h, _dp(src), _ss(ss), _dp(offSrc), _dp(dst), _ss(ds),
                    _dp(offDst), _dp(coeffIdx), int(offSrc.numel()), C.c_void_p(stream))
+
+    def tu_chain_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, dqscale, dqshift, qCoef, numSig, recon, sr, offR,
+                       sseZero, sseRecon, stream=0):
+        self._call("x265b200_tu_chain_batch", N, _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
+                   _dp(qc), qbits, add, dqscale, dqshift, _dp(qCoef), _dp(numSig), _dp(recon), _ss(sr), _dp(offR),
+                   _dp(sseZero), _dp(sseRecon), C.c_void_p(stream))
 
     def residual_batch(self, w, h, A, sa, B, sb, offA, offB, dst, stream=0):
         self._call("x265b200_residual_batch", w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),

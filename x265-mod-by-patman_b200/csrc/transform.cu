@@ -298,13 +298,13 @@ inv_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, in
         for (int i = 0; i < N; i++) ta[j * LD + i] = (int16_t)clip16((x[i] + add) >> shift2);
     }
     __syncwarp();
-    if (live) tile_store<N>(ta, dst + off[tu], dstStride, j);
+    if (live) tile_store<N>(ta, dst + (off ? (size_t)off[tu] : (size_t)tu * (N * N)), dstStride, j);
 }
 
 // ---------------------------------------------------------------- quant family
 // One thread per 8 coefficients.  numSig is accumulated with a warp-segmented sum and one atomic
 // per (warp, block) into a zeroed counter.
-template<bool NQUANT>
+template<bool NQUANT, bool STORE_DU>
 __global__ void __launch_bounds__(256)
 quant_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__ quantCoeff, int32_t* __restrict__ deltaU,
              int16_t* __restrict__ qCoef, int qBits, int add, int numCoeff, int n, uint32_t* __restrict__ numSig)
@@ -343,7 +343,7 @@ quant_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__ quant
         o.x = (lv[0] & 0xffff) | (lv[1] << 16); o.y = (lv[2] & 0xffff) | (lv[3] << 16);
         o.z = (lv[4] & 0xffff) | (lv[5] << 16); o.w = (lv[6] & 0xffff) | (lv[7] << 16);
         *(int4*)(qCoef + base) = o;
-        if (!NQUANT)
+        if (STORE_DU)
         {
             *(int4*)(deltaU + base) = make_int4(du[0], du[1], du[2], du[3]);
             *(int4*)(deltaU + base + 4) = make_int4(du[4], du[5], du[6], du[7]);
@@ -513,6 +513,25 @@ extern "C" int x265b200_idct_batch(x265b200_ctx* ctx, int kind, int N, const int
     return X265B200_OK;
 }
 
+namespace b200 {
+// mode 0 = quant (stores deltaU), 1 = nquant, 2 = quant without storing deltaU (fused TU chain)
+int launch_quant(x265b200_ctx* ctx, int mode, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef,
+                 int qBits, int add, int numCoeff, int n, uint32_t* numSig, cudaStream_t st)
+{
+    B200_CUDA(ctx, cudaMemsetAsync(numSig, 0, (size_t)n * sizeof(uint32_t), st));
+    long long threads = (long long)n * (numCoeff >> 3);
+    int grid = ceil_div(threads, 256);
+    if (mode == 0)
+        quant_kernel<false, true><<<grid, 256, 0, st>>>(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig);
+    else if (mode == 1)
+        quant_kernel<true, false><<<grid, 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
+    else
+        quant_kernel<false, false><<<grid, 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
+}
+
 extern "C" int x265b200_quant_batch(x265b200_ctx* ctx, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU,
                                     int16_t* qCoef, int qBits, int add, int numCoeff, int n, uint32_t* numSig,
                                     x265b200_stream stream)
@@ -520,15 +539,7 @@ extern "C" int x265b200_quant_batch(x265b200_ctx* ctx, const int16_t* coef, cons
     if (!ctx) return X265B200_ERR_ARG;
     if (numCoeff < 8 || (numCoeff & 7) || n < 0) return fail(ctx, X265B200_ERR_ARG, "quant: numCoeff must be a multiple of 8");
     if (n == 0) return X265B200_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    B200_CUDA(ctx, cudaMemsetAsync(numSig, 0, (size_t)n * sizeof(uint32_t), st));
-    long long threads = (long long)n * (numCoeff >> 3);
-    if (deltaU)
-        quant_kernel<false><<<ceil_div(threads, 256), 256, 0, st>>>(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig);
-    else
-        quant_kernel<true><<<ceil_div(threads, 256), 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
-    B200_LAUNCH_CHECK(ctx);
-    return X265B200_OK;
+    return launch_quant(ctx, deltaU ? 0 : 1, coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig, (cudaStream_t)stream);
 }
 
 extern "C" int x265b200_dequant_normal_batch(x265b200_ctx* ctx, const int16_t* q, int16_t* coef, int num, int scale,

@@ -580,7 +580,7 @@ idct32_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
 #pragma unroll
                     for (int e = 0; e < 4; e++) x[p][half][e] = __ldg((const uint32_t*)(q + ((half * 4 + e) * 4) * 32 + p * 16));
         }
-        int16_t* o = dst + off[tu] + (intptr_t)g * dstStride + 2 * t;
+        int16_t* o = dst + tu_offset(off, tu, 1024) + (intptr_t)g * dstStride + 2 * t;
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
         {
@@ -675,7 +675,7 @@ idct16_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
             uint32_t alo[2], ahi[2];
             pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
             pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
-            int16_t* o = dst + off[tu] + (intptr_t)g * dstStride + 2 * t;
+            int16_t* o = dst + tu_offset(off, tu, 256) + (intptr_t)g * dstStride + 2 * t;
 #pragma unroll
             for (int it = 0; it < 2; it++)
             {
@@ -758,10 +758,10 @@ idct_small_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restri
             imma16_ss(dhi, ahi, b2);
             imma16_us(dlo, alo, b2);
             if (base + st_tu0 < n)
-                store_pair(dst + off[base + st_tu0] + (intptr_t)st_row * dstStride + st_col,
+                store_pair(dst + tu_offset(off, base + st_tu0, NN) + (intptr_t)st_row * dstStride + st_col,
                            recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
             if (base + st_tu1 < n)
-                store_pair(dst + off[base + st_tu1] + (intptr_t)st_row * dstStride + st_col,
+                store_pair(dst + tu_offset(off, base + st_tu1, NN) + (intptr_t)st_row * dstStride + st_col,
                            recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
         }
     }
