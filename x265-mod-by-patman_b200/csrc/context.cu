@@ -139,6 +139,13 @@ extern "C" int x265b200_open(int device, int bit_depth, x265b200_ctx** out)
     ctx->depth = bit_depth;
     ctx->pixbytes = bit_depth == 8 ? 1 : 2;
     ctx->sm_count = prop.multiProcessorCount;
+    // stream-ordered scratch (x265b200_tu_chain_batch) must not go back to the OS at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     int r = upload_transform_tables(ctx);
     if (r == X265B200_OK) r = upload_filter_tables(ctx);
     if (r == X265B200_OK) r = upload_mma_tables(ctx);

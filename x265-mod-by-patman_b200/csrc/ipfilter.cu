@@ -91,7 +91,9 @@ __device__ __forceinline__ void store4(DST* d, const int (&v)[4])
     }
 }
 
-template<typename SRC, typename DST, int TAPS, bool VERT>
+// TW x TH output tile per thread: horizontal filters use TW in {4, 8} (TH = 4), vertical TH in {4, 8} (TW = 4);
+// the larger tiles halve the halo re-reads (15 instead of 2 x 11 input samples / rows per 8 outputs).
+template<typename SRC, typename DST, int TAPS, bool VERT, int TW, int TH>
 __global__ void __launch_bounds__(128)
 fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
                 DST* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst,
@@ -99,12 +101,12 @@ fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restr
 {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int rowsMax = p.rowExtKind ? p.h + TAPS - 1 : p.h;
-    int tw = p.w >> 2;
-    int per = tw * ((rowsMax + 3) >> 2);
+    int tw = p.w / TW;
+    int per = tw * ((rowsMax + TH - 1) / TH);
     int blk = (int)(gid / per);
     if (blk >= n) return;
     int t = (int)(gid % per);
-    int tx = (t % tw) << 2, ty = (t / tw) << 2;
+    int tx = (t % tw) * TW, ty = (t / tw) * TH;
     int ci = coeffIdx[blk];
     int idx = ci & 15;
     const SRC* s = src + offSrc[blk];
@@ -118,49 +120,54 @@ fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restr
 
     if (!VERT)
     {
-        constexpr int NQ = TAPS == 8 ? 3 : 2;                    // 4 + TAPS - 1 samples
+        constexpr int NQ = (TW + TAPS - 1 + 3) / 4;              // quads covering TW + TAPS - 1 samples
         s += (intptr_t)ty * ss + tx - (TAPS / 2 - 1);
-        uint32_t w[4][2 * NQ];
+        uint32_t w[TH][2 * NQ];
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < TH; r++)
             if (ty + r < rows) load_row_quads<NQ>(s + r * ss, w[r]);
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < TH; r++)
         {
             if (ty + r >= rows) break;
             int x[4 * NQ];
 #pragma unroll
             for (int i = 0; i < 2 * NQ; i++) SampleTraits<SRC>::unpack(w[r][i], x[2 * i], x[2 * i + 1]);
-            int v[4];
 #pragma unroll
-            for (int o = 0; o < 4; o++)
+            for (int o4 = 0; o4 < TW; o4 += 4)
             {
-                int sum = 0;
+                int v[4];
 #pragma unroll
-                for (int k = 0; k < TAPS; k++) sum += x[o + k] * c[k];
-                int q = (int)(int16_t)((sum + p.offset) >> p.shift);
-                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+                for (int o = 0; o < 4; o++)
+                {
+                    int sum = 0;
+#pragma unroll
+                    for (int k = 0; k < TAPS; k++) sum += x[o4 + o + k] * c[k];
+                    int q = (int)(int16_t)((sum + p.offset) >> p.shift);
+                    v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+                }
+                store4(d + r * ds + o4, v);
             }
-            store4(d + r * ds, v);
         }
     }
     else
     {
+        constexpr int NR = TH + TAPS - 1;
         s += (intptr_t)(ty - (TAPS / 2 - 1)) * ss + tx;
-        int nr = min(4, rows - ty);
-        uint32_t w[TAPS + 3][2];
+        int nr = min(TH, rows - ty);
+        uint32_t w[NR][2];
 #pragma unroll
-        for (int r = 0; r < TAPS + 3; r++)
+        for (int r = 0; r < NR; r++)
             if (r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, w[r]);
-        int x[TAPS + 3][4];
+        int x[NR][4];
 #pragma unroll
-        for (int r = 0; r < TAPS + 3; r++)
+        for (int r = 0; r < NR; r++)
         {
             SampleTraits<SRC>::unpack(w[r][0], x[r][0], x[r][1]);
             SampleTraits<SRC>::unpack(w[r][1], x[r][2], x[r][3]);
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < TH; r++)
         {
             if (r >= nr) break;
             int v[4];
@@ -349,8 +356,14 @@ static int launch_interp(x265b200_ctx* ctx, int kind, int w, int h, const void* 
     const bool tiled = !(w & 3) && !(ss & 3);
 #define FIR(SRC_T, DST_T, VERT_, ROWS)                                                                          \
     do {                                                                                                        \
-        if (tiled)                                                                                              \
-            fir_tile_kernel<SRC_T, DST_T, TAPS, VERT_><<<ceil_div((long long)n * (w >> 2) * (((ROWS) + 3) >> 2), 128), 128, 0, st>>>( \
+        if (tiled && !(VERT_) && !(w & 7))                                                                      \
+            fir_tile_kernel<SRC_T, DST_T, TAPS, VERT_, 8, 4><<<ceil_div((long long)n * (w >> 3) * (((ROWS) + 3) >> 2), 128), 128, 0, st>>>( \
+                (const SRC_T*)src, ss, offSrc, (DST_T*)dst, ds, offDst, coeffIdx, n, p);                         \
+        else if (tiled && (VERT_) && !((ROWS) & 7))                                                             \
+            fir_tile_kernel<SRC_T, DST_T, TAPS, VERT_, 4, 8><<<ceil_div((long long)n * (w >> 2) * ((ROWS) >> 3), 128), 128, 0, st>>>( \
+                (const SRC_T*)src, ss, offSrc, (DST_T*)dst, ds, offDst, coeffIdx, n, p);                         \
+        else if (tiled)                                                                                         \
+            fir_tile_kernel<SRC_T, DST_T, TAPS, VERT_, 4, 4><<<ceil_div((long long)n * (w >> 2) * (((ROWS) + 3) >> 2), 128), 128, 0, st>>>( \
                 (const SRC_T*)src, ss, offSrc, (DST_T*)dst, ds, offDst, coeffIdx, n, p);                         \
         else                                                                                                    \
             fir_kernel<SRC_T, DST_T, TAPS, VERT_><<<ceil_div((long long)n * w * (ROWS), 256), 256, 0, st>>>(     \
