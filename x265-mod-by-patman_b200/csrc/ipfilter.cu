@@ -12,6 +12,9 @@ namespace b200 {
 
 __constant__ short c_lumaTaps[4][8];
 __constant__ short c_chromaTaps[8][4];
+// the same taps as signed bytes for dp2a: [idx][0] = taps 0..3, [idx][1] = taps 4..7 (luma only)
+__constant__ uint32_t c_lumaTapsB[4][2];
+__constant__ uint32_t c_chromaTapsB[8];
 
 int upload_filter_tables(x265b200_ctx* ctx)
 {
@@ -20,6 +23,20 @@ int upload_filter_tables(x265b200_ctx* ctx)
                                       { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
     static const short chroma[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
                                         { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+    uint32_t lb[4][2], cb[8];
+    for (int i = 0; i < 4; i++)
+        for (int hh = 0; hh < 2; hh++)
+        {
+            lb[i][hh] = 0;
+            for (int e = 0; e < 4; e++) lb[i][hh] |= (uint32_t)(uint8_t)(int8_t)luma[i][4 * hh + e] << (8 * e);
+        }
+    for (int i = 0; i < 8; i++)
+    {
+        cb[i] = 0;
+        for (int e = 0; e < 4; e++) cb[i] |= (uint32_t)(uint8_t)(int8_t)chroma[i][e] << (8 * e);
+    }
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_lumaTapsB, lb, sizeof(lb)));
+    B200_CUDA(ctx, cudaMemcpyToSymbol(c_chromaTapsB, cb, sizeof(cb)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_lumaTaps, luma, sizeof(luma)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_chromaTaps, chroma, sizeof(chroma)));
     return X265B200_OK;
@@ -91,8 +108,108 @@ __device__ __forceinline__ void store4(DST* d, const int (&v)[4])
     }
 }
 
-// TW x TH output tile per thread: horizontal filters use TW in {4, 8} (TH = 4), vertical TH in {4, 8} (TW = 4);
-// the larger tiles halve the halo re-reads (15 instead of 2 x 11 input samples / rows per 8 outputs).
+// two-way dot product of packed 16-bit samples with two signed-byte taps (IDP.2A): the sample pair is unsigned
+// for pixels and signed for the int16 intermediates
+template<typename SRC> __device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    if (sizeof(SRC) == 2 && SRC(-1) < SRC(0)) asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template<typename SRC> __device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    if (sizeof(SRC) == 2 && SRC(-1) < SRC(0)) asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// sum over TAPS taps of four packed pair-words (luma) / two (chroma), starting value `acc`
+template<typename SRC, int TAPS>
+__device__ __forceinline__ int fir_pairs(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1, int acc)
+{
+    acc = dp2a_lo<SRC>(p0, t0, acc);
+    acc = dp2a_hi<SRC>(p1, t0, acc);
+    if (TAPS == 8)
+    {
+        acc = dp2a_lo<SRC>(p2, t1, acc);
+        acc = dp2a_hi<SRC>(p3, t1, acc);
+    }
+    return acc;
+}
+
+// TW x TH output tile per thread: horizontal filters use TW in {4, 8} (TH = 4), vertical TH in {4, 8} (TW = 4).
+// Samples stay packed two per register; taps are signed bytes, so every pair of taps is one IDP.2A
+// (pixels are widened to 16-bit lanes by the loader for 8-bit builds).  FULL = every row of the tile exists
+// (no per-row predicates); partial tiles (last rows of an isRowExt block) take the predicated variant.
+template<typename SRC, typename DST, int TAPS, bool VERT, int TW, int TH, bool FULL>
+__device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_t ss, DST* __restrict__ d, intptr_t ds,
+                                              int nr, uint32_t t0, uint32_t t1, const FirParams& p)
+{
+    if (!VERT)
+    {
+        constexpr int NQ = (TW + TAPS - 1 + 3) / 4;              // quads covering TW + TAPS - 1 samples
+        uint32_t w[TH][2 * NQ + 1];
+#pragma unroll
+        for (int r = 0; r < TH; r++)
+            if (FULL || r < nr) { load_row_quads<NQ>(s + r * ss, (uint32_t(&)[2 * NQ])w[r]); w[r][2 * NQ] = 0; }
+#pragma unroll
+        for (int r = 0; r < TH; r++)
+        {
+            if (!FULL && r >= nr) break;
+            // odd-phase words: (x[2i+1], x[2i+2])
+            uint32_t ws[2 * NQ];
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) ws[i] = __funnelshift_r(w[r][i], w[r][i + 1], 16);
+#pragma unroll
+            for (int o4 = 0; o4 < TW; o4 += 4)
+            {
+                int v[4];
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    int i = (o4 + o) >> 1;
+                    int sum = ((o4 + o) & 1) ? fir_pairs<SRC, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], t0, t1, p.offset)
+                                             : fir_pairs<SRC, TAPS>(w[r][i], w[r][i + 1], w[r][(i + 2) % (2 * NQ + 1)], w[r][(i + 3) % (2 * NQ + 1)], t0, t1, p.offset);
+                    int q = (int)(int16_t)(sum >> p.shift);
+                    v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+                }
+                store4(d + r * ds + o4, v);
+            }
+        }
+    }
+    else
+    {
+        constexpr int NR = TH + TAPS - 1;
+        uint32_t w[NR][2];
+#pragma unroll
+        for (int r = 0; r < NR; r++)
+            if (FULL || r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, w[r]);
+        // pair words of vertically adjacent rows: pr[r][c] = (x[r][c], x[r+1][c])
+        uint32_t pr[NR - 1][4];
+#pragma unroll
+        for (int r = 0; r < NR - 1; r++)
+        {
+            pr[r][0] = __byte_perm(w[r][0], w[r + 1][0], 0x5410); pr[r][1] = __byte_perm(w[r][0], w[r + 1][0], 0x7632);
+            pr[r][2] = __byte_perm(w[r][1], w[r + 1][1], 0x5410); pr[r][3] = __byte_perm(w[r][1], w[r + 1][1], 0x7632);
+        }
+#pragma unroll
+        for (int r = 0; r < TH; r++)
+        {
+            if (!FULL && r >= nr) break;
+            int v[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                int sum = fir_pairs<SRC, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], t0, t1, p.offset);
+                int q = (int)(int16_t)(sum >> p.shift);
+                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+            }
+            store4(d + r * ds, v);
+        }
+    }
+}
+
 template<typename SRC, typename DST, int TAPS, bool VERT, int TW, int TH>
 __global__ void __launch_bounds__(128)
 fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
@@ -114,75 +231,12 @@ fir_tile_kernel(const SRC* __restrict__ src, intptr_t ss, const int32_t* __restr
     if (p.rowExtKind && (ci >> 8 & 1)) { s -= (TAPS / 2 - 1) * ss; rows += TAPS - 1; }
     if (ty >= rows) return;
     DST* d = dst + offDst[blk] + (intptr_t)ty * ds + tx;
-    int c[TAPS];
-#pragma unroll
-    for (int k = 0; k < TAPS; k++) c[k] = tap<TAPS>(idx, k);
-
-    if (!VERT)
-    {
-        constexpr int NQ = (TW + TAPS - 1 + 3) / 4;              // quads covering TW + TAPS - 1 samples
-        s += (intptr_t)ty * ss + tx - (TAPS / 2 - 1);
-        uint32_t w[TH][2 * NQ];
-#pragma unroll
-        for (int r = 0; r < TH; r++)
-            if (ty + r < rows) load_row_quads<NQ>(s + r * ss, w[r]);
-#pragma unroll
-        for (int r = 0; r < TH; r++)
-        {
-            if (ty + r >= rows) break;
-            int x[4 * NQ];
-#pragma unroll
-            for (int i = 0; i < 2 * NQ; i++) SampleTraits<SRC>::unpack(w[r][i], x[2 * i], x[2 * i + 1]);
-#pragma unroll
-            for (int o4 = 0; o4 < TW; o4 += 4)
-            {
-                int v[4];
-#pragma unroll
-                for (int o = 0; o < 4; o++)
-                {
-                    int sum = 0;
-#pragma unroll
-                    for (int k = 0; k < TAPS; k++) sum += x[o4 + o + k] * c[k];
-                    int q = (int)(int16_t)((sum + p.offset) >> p.shift);
-                    v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
-                }
-                store4(d + r * ds + o4, v);
-            }
-        }
-    }
-    else
-    {
-        constexpr int NR = TH + TAPS - 1;
-        s += (intptr_t)(ty - (TAPS / 2 - 1)) * ss + tx;
-        int nr = min(TH, rows - ty);
-        uint32_t w[NR][2];
-#pragma unroll
-        for (int r = 0; r < NR; r++)
-            if (r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, w[r]);
-        int x[NR][4];
-#pragma unroll
-        for (int r = 0; r < NR; r++)
-        {
-            SampleTraits<SRC>::unpack(w[r][0], x[r][0], x[r][1]);
-            SampleTraits<SRC>::unpack(w[r][1], x[r][2], x[r][3]);
-        }
-#pragma unroll
-        for (int r = 0; r < TH; r++)
-        {
-            if (r >= nr) break;
-            int v[4];
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-            {
-                int sum = 0;
-#pragma unroll
-                for (int k = 0; k < TAPS; k++) sum += x[r + k][o] * c[k];
-                int q = (int)(int16_t)((sum + p.offset) >> p.shift);
-                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
-            }
-            store4(d + r * ds, v);
-        }
-    }
+    uint32_t t0 = TAPS == 8 ? c_lumaTapsB[idx & 3][0] : c_chromaTapsB[idx & 7];
+    uint32_t t1 = TAPS == 8 ? c_lumaTapsB[idx & 3][1] : 0;
+    s += VERT ? (intptr_t)(ty - (TAPS / 2 - 1)) * ss + tx : (intptr_t)ty * ss + tx - (TAPS / 2 - 1);
+    int nr = min(TH, rows - ty);
+    if (nr == TH) fir_tile_body<SRC, DST, TAPS, VERT, TW, TH, true>(s, ss, d, ds, nr, t0, t1, p);
+    else fir_tile_body<SRC, DST, TAPS, VERT, TW, TH, false>(s, ss, d, ds, nr, t0, t1, p);
 }
 
 // hvpp: one CTA per block.  Pass 1 = hps(isRowExt=1) into smem (pitch w), pass 2 = vertical sp.
