@@ -275,70 +275,80 @@ hv_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ 
     }
 }
 
-// hvpp throughput version (w % 4 == 0, stride % 4 == 0): one warp per block, 4 blocks per CTA.
-// Pass 1 = hps with isRowExt into a per-warp smem tile (pitch w), 4x4 tiles via load_row_quads;
-// pass 2 = vertical sp out of smem, 4x4 output tiles (8-byte aligned LDS).
+// hvpp throughput version (w % 4 == 0, h % 4 == 0, stride % 4 == 0): a group of G lanes (power of two, <= 32)
+// owns one block.  Pass 1 = hps with isRowExt into the group's smem tile (pitch w), 4x4 tiles through
+// load_row_quads + IDP.2A; pass 2 = vertical sp out of smem (8-byte aligned LDS), 4x4 output tiles.
 template<typename PIX, int TAPS>
 __global__ void __launch_bounds__(128)
 hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
                PIX* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst,
-               const int32_t* __restrict__ coeffIdx, int n, int w, int h, int shift1, int offset1, int shift2, int offset2, int maxVal)
+               const int32_t* __restrict__ coeffIdx, int n, int w, int h, int G, int shift1, int offset1, int shift2, int offset2, int maxVal)
 {
     extern __shared__ __align__(16) int16_t immed_all[];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int blk = blockIdx.x * 4 + warp;
-    if (blk >= n) return;
+    int lg = __ffs(G) - 1;
+    int grp = threadIdx.x >> lg, l = threadIdx.x & (G - 1);
+    int blk = blockIdx.x * (128 >> lg) + grp;
+    bool live = blk < n;
     int rows = h + TAPS - 1;
-    int16_t* immed = immed_all + (size_t)warp * w * rows;
-    int ci = coeffIdx[blk];
-    int idxX = ci & 15, idxY = (ci >> 4) & 15;
-    int cx[TAPS], cy[TAPS];
-#pragma unroll
-    for (int k = 0; k < TAPS; k++) { cx[k] = tap<TAPS>(idxX, k); cy[k] = tap<TAPS>(idxY, k); }
-    const PIX* s = src + offSrc[blk] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
+    int16_t* immed = immed_all + (size_t)grp * w * rows;
     int tw = w >> 2;
     constexpr int NQ = TAPS == 8 ? 3 : 2;
-    int tiles1 = tw * ((rows + 3) >> 2);
-    for (int t = lane; t < tiles1; t += 32)
+    uint32_t tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+    if (live)
     {
-        int tx = (t % tw) << 2, ty = (t / tw) << 2;
-        uint32_t wv[4][2 * NQ];
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-            if (ty + r < rows) load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, wv[r]);
-#pragma unroll
-        for (int r = 0; r < 4; r++)
+        int ci = coeffIdx[blk];
+        int idxX = ci & 15, idxY = (ci >> 4) & 15;
+        tx0 = TAPS == 8 ? c_lumaTapsB[idxX & 3][0] : c_chromaTapsB[idxX & 7];
+        tx1 = TAPS == 8 ? c_lumaTapsB[idxX & 3][1] : 0;
+        ty0 = TAPS == 8 ? c_lumaTapsB[idxY & 3][0] : c_chromaTapsB[idxY & 7];
+        ty1 = TAPS == 8 ? c_lumaTapsB[idxY & 3][1] : 0;
+        const PIX* s = src + offSrc[blk] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
+        int tiles1 = tw * ((rows + 3) >> 2);
+        for (int t = l; t < tiles1; t += G)
         {
-            if (ty + r >= rows) break;
-            int x[4 * NQ];
+            int tx = (t % tw) << 2, ty = (t / tw) << 2;
+            uint32_t wv[4][2 * NQ + 1];
 #pragma unroll
-            for (int i = 0; i < 2 * NQ; i++) SampleTraits<PIX>::unpack(wv[r][i], x[2 * i], x[2 * i + 1]);
-            int v[4];
+            for (int r = 0; r < 4; r++)
+                if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
 #pragma unroll
-            for (int o = 0; o < 4; o++)
+            for (int r = 0; r < 4; r++)
             {
-                int sum = 0;
+                if (ty + r >= rows) break;
+                uint32_t ws[2 * NQ];
 #pragma unroll
-                for (int k = 0; k < TAPS; k++) sum += x[o + k] * cx[k];
-                v[o] = (sum + offset1) >> shift1;
+                for (int i = 0; i < 2 * NQ; i++) ws[i] = __funnelshift_r(wv[r][i], wv[r][i + 1], 16);
+                int v[4];
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    int i = o >> 1;
+                    int sum = (o & 1) ? fir_pairs<PIX, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], tx0, tx1, offset1)
+                                      : fir_pairs<PIX, TAPS>(wv[r][i], wv[r][i + 1], wv[r][i + 2], wv[r][i + 3], tx0, tx1, offset1);
+                    v[o] = sum >> shift1;
+                }
+                *(uint2*)(immed + (ty + r) * w + tx) = make_uint2((uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16),
+                                                                  (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16));
             }
-            *(uint2*)(immed + (ty + r) * w + tx) = make_uint2((uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16),
-                                                              (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16));
         }
     }
     __syncwarp();
+    if (!live) return;
     PIX* d = dst + offDst[blk];
     int tiles2 = tw * (h >> 2);
-    for (int t = lane; t < tiles2; t += 32)
+    for (int t = l; t < tiles2; t += G)
     {
         int tx = (t % tw) << 2, ty = (t / tw) << 2;
-        int x[TAPS + 3][4];
+        constexpr int NR = 4 + TAPS - 1;
+        uint2 q[NR];
 #pragma unroll
-        for (int r = 0; r < TAPS + 3; r++)
+        for (int r = 0; r < NR; r++) q[r] = *(const uint2*)(immed + (ty + r) * w + tx);
+        uint32_t pr[NR - 1][4];
+#pragma unroll
+        for (int r = 0; r < NR - 1; r++)
         {
-            uint2 q = *(const uint2*)(immed + (ty + r) * w + tx);
-            SampleTraits<int16_t>::unpack(q.x, x[r][0], x[r][1]);
-            SampleTraits<int16_t>::unpack(q.y, x[r][2], x[r][3]);
+            pr[r][0] = __byte_perm(q[r].x, q[r + 1].x, 0x5410); pr[r][1] = __byte_perm(q[r].x, q[r + 1].x, 0x7632);
+            pr[r][2] = __byte_perm(q[r].y, q[r + 1].y, 0x5410); pr[r][3] = __byte_perm(q[r].y, q[r + 1].y, 0x7632);
         }
 #pragma unroll
         for (int r = 0; r < 4; r++)
@@ -347,11 +357,9 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
 #pragma unroll
             for (int o = 0; o < 4; o++)
             {
-                int sum = 0;
-#pragma unroll
-                for (int k = 0; k < TAPS; k++) sum += x[r + k][o] * cy[k];
-                int q = (int)(int16_t)((sum + offset2) >> shift2);
-                v[o] = min(max(q, 0), maxVal);
+                int sum = fir_pairs<int16_t, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], ty0, ty1, offset2);
+                int qv = (int)(int16_t)(sum >> shift2);
+                v[o] = min(max(qv, 0), maxVal);
             }
             store4(d + (intptr_t)(ty + r) * ds + tx, v);
         }
@@ -455,8 +463,12 @@ static int launch_interp(x265b200_ctx* ctx, int kind, int w, int h, const void* 
         size_t smem = (size_t)w * (h + TAPS - 1) * sizeof(int16_t);
         if (tiled && !(h & 3))
         {
-            hv_tile_kernel<PIX, TAPS><<<ceil_div(n, 4), 128, 4 * smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, w, h,
-                                                                          shift1, (int)((unsigned)-8192 << shift1), shift2,
+            int tiles2 = (w >> 2) * (h >> 2);
+            int G = 1;
+            while (G < tiles2 && G < 32) G <<= 1;
+            int perCta = 128 / G;
+            hv_tile_kernel<PIX, TAPS><<<ceil_div(n, perCta), 128, perCta * smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, w, h,
+                                                                          G, shift1, (int)((unsigned)-8192 << shift1), shift2,
                                                                           (1 << (shift2 - 1)) + (8192 << 6), maxVal);
             break;
         }
