@@ -33,13 +33,10 @@ int main(int argc, char** argv)
     fill<<<(F * pe + 255) / 256, 256>>>(A, F * pe, 1); fill<<<(F * pe + 255) / 256, 256>>>(B, F * pe, 77);
     CK(cudaDeviceSynchronize());
     Variant vars[] = {
-        { "u1 256 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 256, 1 },
-        { "u1 128 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 1 },
-        { "u1 64 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 64, 1 },
-        { "u1 128 thr, G/2", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 2 },
-        { "u1 128 thr, G/4", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 4 },
-        { "u2 128 thr, G/2", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 128, 2 },
-        { "u2 128 thr, G/4", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 128, 4 },
+        { "t4 u1 128 thr (library rule)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 0 },
+        { "t4 u1 256 thr", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 256, 0 },
+        { "t4 u1 128 thr, full-warp groups", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 1, 1>, 128, 1 },
+        { "t4 u2 128 thr (2 tiles loaded together)", tile4_fast_kernel<uint16_t, OP_SATD, int, int32_t, 2, 1>, 128, 0 },
     };
     const int NV = sizeof(vars) / sizeof(vars[0]);
     for (int v = 0; v < NV; v++)
@@ -47,7 +44,7 @@ int main(int argc, char** argv)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void*)vars[v].k));
         printf("variant %d: %-28s regs %d\n", v, vars[v].name, fa.numRegs);
     }
-    int shapes[][2] = { {64, 64}, {32, 32}, {32, 16}, {16, 16}, {16, 8}, {8, 8}, {4, 8} };
+    int shapes[][2] = { {64, 64}, {64, 32}, {32, 32}, {32, 16}, {16, 16}, {16, 8}, {8, 16}, {8, 8}, {8, 4} };
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (auto& sh : shapes)
     {
@@ -77,7 +74,11 @@ int main(int argc, char** argv)
         for (int v = 0; v < NV; v++)
         {
             int32_t* o = v == 0 ? out0 : out;
-            G = G0 / vars[v].gdiv; if (G < 1) G = 1;
+            if (vars[v].gdiv == 0)
+            {   // library rule for 4x4 tiles
+                int per = T4 >= 16 ? 4 : 2; G = 1; while (G * 2 * per <= T4 && G < 32) G <<= 1;
+            }
+            else { G = G0 / vars[v].gdiv; if (G < 1) G = 1; }
             long long threads = (long long)n * G;
             int grid = (int)((threads + vars[v].threads - 1) / vars[v].threads);
             float best = 1e9f;
