@@ -10,9 +10,11 @@ with x265's padded plane geometry.  One STEP = one pass of the hot path over tha
     shape tiling every CTU of every frame, one motion vector per block (+-57, seeded)  -> 12 launches
   * forward DCT of the prediction residual for every TU size 32/16/8/4, each size tiling every frame
     -> 4 launches
-value = (12 + 4) * F * coded_luma_samples / step_time, inputs resident in HBM (F = 8 -> 301 MB of
-planes + 133 MB residual + 133 MB coefficients per DCT pass, well above the 126 MB L2, so successive
-launches cannot be served from cache).
+value = (12 + 4) * F * coded_luma_samples / step_time, inputs resident in HBM (F = 32 -> 1.2 GB of
+planes + 535 MB residual + 535 MB coefficients per DCT pass, far above the 126 MB L2, so successive
+launches cannot be served from cache).  F = 32 because every launch carries a fixed cost of about 6 us
+(launch gap, pipeline ramp, tail) that a 33 MB frame pair (5 us at the HBM roofline) cannot amortise:
+profiles/r2_frames_per_launch.md.
 e2e = the same step driven from pinned HOST planes: H2D of the frame pair, residual, SATD, DCT, D2H of
 all costs and coefficients, pipelined over streams.
 
@@ -93,9 +95,11 @@ class ClockSampler:
 
 def build_workload(nframes, rank):
     """numpy planes + descriptors for `nframes` frame pairs (deterministic per rank)"""
+    from concurrent.futures import ThreadPoolExecutor
     geo = Geometry(WIDTH, HEIGHT)
-    fenc = [make_plane(geo, DEPTH, 0x265 + 1000 * rank + f, "natural") for f in range(nframes)]
-    ref = [make_plane(geo, DEPTH, 0x9265 + 1000 * rank + f, "natural") for f in range(nframes)]
+    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as pool:      # numpy releases the GIL in the big array ops
+        fenc = list(pool.map(lambda f: make_plane(geo, DEPTH, 0x265 + 1000 * rank + f, "natural"), range(nframes)))
+        ref = list(pool.map(lambda f: make_plane(geo, DEPTH, 0x9265 + 1000 * rank + f, "natural"), range(nframes)))
     desc = {}
     for (w, h) in SATD_SHAPES + [(n, n) for n in DCT_SIZES]:
         if (w, h) not in desc:
@@ -176,7 +180,7 @@ def workload_config(nframes, note=""):
     return {"workload": "3840x2160 10-bit 4:2:0 luma, preset slow shapes: SATD x12 PU shapes + DCT 32/16/8/4, every CTU of "
                         "%d frame pair(s) per step" % nframes,
             "frames_per_step": nframes, "satd_shapes": ["%dx%d" % s for s in SATD_SHAPES], "dct_sizes": DCT_SIZES,
-            "ctu": 64, "merange": 57, "l2_policy": "working set > L2: 8 frame pairs = 301 MB planes, each launch streams all frames",
+            "ctu": 64, "merange": 57, "l2_policy": "working set > L2: %d frame pairs = %d MB planes, each launch streams all frames" % (nframes, nframes * 2 * 18.8),
             "note": note}
 
 
@@ -427,7 +431,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="frame pairs per step per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -34,11 +34,12 @@ def make_plane(geo, depth, seed, kind="uniform"):
     idx = np.arange(geo.plane_elems, dtype=np.uint64)
     if kind == "uniform":
         return (splitmix64(idx, seed) & np.uint64(pmax)).astype(dt)
-    y = (idx // np.uint64(geo.stride)).astype(np.float64)
-    x = (idx % np.uint64(geo.stride)).astype(np.float64)
+    # separable base signal: one sin per column, one cos per row (same float64 values as evaluating it per sample)
+    sx = np.sin(np.arange(geo.stride, dtype=np.float64) / 97.0)
+    cy = np.cos(np.arange(geo.rows, dtype=np.float64) / 61.0)
     mid, amp = 1 << (depth - 1), 1 << (depth - 3)
     noise = ((splitmix64(idx, seed) & np.uint64(31)).astype(np.int64) - 16) * (1 << (depth - 8))
-    v = mid + amp * (np.sin(x / 97.0) + np.cos(y / 61.0)) + noise
+    v = (mid + amp * (sx[None, :] + cy[:, None])).ravel() + noise
     return np.clip(np.rint(v), 0, pmax).astype(dt)
 
 

@@ -21,15 +21,21 @@ from frames import Geometry, make_plane, tile_blocks  # noqa: E402
 pkg = importlib.import_module("x265-mod-by-patman_b200")
 
 
-def timeit(fn, reps=8, warm=3):
+def timeit(fn, reps=8, warm=3, burst=6):
+    """median over `reps` bursts of `burst` back-to-back launches (per-launch mean of a burst): the stream stays
+    busy, so the host's launch latency on an idle GPU is not part of the number (every launch streams > L2 bytes)"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); e1.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        fn()
+        e0.record()
+        for _ in range(burst):
+            fn()
+        e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1) / burst)
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -37,7 +43,7 @@ def timeit(fn, reps=8, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--depth", type=int, default=10)
-    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=32)
     args = ap.parse_args()
     D, F = args.depth, args.frames
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
