@@ -101,8 +101,10 @@ def main():
         ms = timeit(lambda: ctx.dct_batch(pkg.TR_DCT, N, res, N, None, coef, count=n))
         add("dct%d (CUDA-core twin)" % N, ms, S * 4, S)
         ctx.set_dct_path(0)
+        ms = timeit(lambda: ctx.idct_batch(pkg.TR_DCT, N, coef, rec, N, None, count=n))
+        add("idct%d (contiguous TUs)" % N, ms, S * 4, S)
         ms = timeit(lambda: ctx.idct_batch(pkg.TR_DCT, N, coef, rec, N, off))
-        add("idct%d" % N, ms, S * 4, S)
+        add("idct%d (per-TU offsets, +%.1f B/coef descriptor traffic)" % (N, 4.0 / (N * N)), ms, S * 4, S)
     n4 = S // 16
     ms = timeit(lambda: ctx.dct_batch(pkg.TR_DST, 4, res, 4, None, coef, count=n4))
     add("dst4 (IMMA)", ms, S * 4, S)

@@ -173,6 +173,92 @@ __device__ __forceinline__ void load_row_quads(const uint8_t* p, uint32_t (&w)[2
     }
 }
 
+// ROWS rows of eight horizontally adjacent samples as packed 16-bit pairs (w[r][i] = samples 2i, 2i+1 of row r).
+// The row stride must be a multiple of four samples, so every row shares one misalignment class: all aligned
+// chunk loads of the strip are issued before the first use (ROWS * 16 bytes per thread in flight), then realigned.
+template<int ROWS>
+__device__ __forceinline__ void load_rows8(const uint16_t* p, intptr_t stride, uint32_t (&w)[ROWS][4])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)(a >> 1) & 3;
+    const uint2* base = (const uint2*)(a & ~(uintptr_t)7);
+    intptr_t cs = stride >> 2;
+    uint2 q0[ROWS], q1[ROWS], q2[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) { q0[r] = __ldg(base + r * cs); q1[r] = __ldg(base + r * cs + 1); }
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) q2[r] = __ldg(base + r * cs + 2);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) q2[r] = make_uint2(0, 0);
+    }
+    int sh = (s & 1) << 4;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+    {
+        uint32_t c0 = q0[r].x, c1 = q0[r].y, c2 = q1[r].x, c3 = q1[r].y, c4 = q2[r].x, c5 = q2[r].y;
+        if (s & 2) { c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; }
+        w[r][0] = __funnelshift_r(c0, c1, sh);
+        w[r][1] = __funnelshift_r(c1, c2, sh);
+        w[r][2] = __funnelshift_r(c2, c3, sh);
+        w[r][3] = __funnelshift_r(c3, c4, sh);
+    }
+}
+template<int ROWS>
+__device__ __forceinline__ void load_rows8(const int16_t* p, intptr_t stride, uint32_t (&w)[ROWS][4]) { load_rows8<ROWS>((const uint16_t*)p, stride, w); }
+
+// 8-bit samples: 4-byte chunks, widened to packed 16-bit pairs
+template<int ROWS>
+__device__ __forceinline__ void load_rows8(const uint8_t* p, intptr_t stride, uint32_t (&w)[ROWS][4])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)a & 3;
+    const uint32_t* base = (const uint32_t*)(a & ~(uintptr_t)3);
+    intptr_t cs = stride >> 2;
+    uint32_t c0[ROWS], c1[ROWS], c2[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) { c0[r] = __ldg(base + r * cs); c1[r] = __ldg(base + r * cs + 1); }
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) c2[r] = __ldg(base + r * cs + 2);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) c2[r] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+    {
+        uint32_t v0 = __funnelshift_r(c0[r], c1[r], s << 3), v1 = __funnelshift_r(c1[r], c2[r], s << 3);
+        w[r][0] = __byte_perm(v0, 0, 0x4140); w[r][1] = __byte_perm(v0, 0, 0x4342);
+        w[r][2] = __byte_perm(v1, 0, 0x4140); w[r][3] = __byte_perm(v1, 0, 0x4342);
+    }
+}
+
+// eight int16 (four packed words) to `d`, with the widest stores its alignment allows
+__device__ __forceinline__ void store8_s16(int16_t* d, const uint32_t (&w)[4])
+{
+    uintptr_t a = (uintptr_t)d;
+    if ((a & 15) == 0) *(uint4*)d = make_uint4(w[0], w[1], w[2], w[3]);
+    else if ((a & 7) == 0) { *(uint2*)d = make_uint2(w[0], w[1]); *(uint2*)(d + 4) = make_uint2(w[2], w[3]); }
+    else if ((a & 3) == 0) { uint32_t* q = (uint32_t*)d; q[0] = w[0]; q[1] = w[1]; q[2] = w[2]; q[3] = w[3]; }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { d[2 * i] = (int16_t)(w[i] & 0xffff); d[2 * i + 1] = (int16_t)(w[i] >> 16); }
+    }
+}
+
+// lane-wise a - b of packed 16-bit pairs when every a, b is in [0, 32767]: setting bit 15 of each a-lane
+// keeps the low lane from borrowing into the high one; the final xor removes it again (mod 2^16 per lane)
+__device__ __forceinline__ uint32_t psub16(uint32_t a, uint32_t b) { return ((a | 0x80008000u) - b) ^ 0x80008000u; }
+
 template<typename T> struct SampleTraits;
 template<> struct SampleTraits<uint8_t>  { static __device__ __forceinline__ void unpack(uint32_t w, int& x, int& y) { x = w & 0xffff; y = w >> 16; } };
 template<> struct SampleTraits<uint16_t> { static __device__ __forceinline__ void unpack(uint32_t w, int& x, int& y) { x = w & 0xffff; y = w >> 16; } };

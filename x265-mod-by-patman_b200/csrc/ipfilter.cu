@@ -108,6 +108,32 @@ __device__ __forceinline__ void store4(DST* d, const int (&v)[4])
     }
 }
 
+// Filter epilogue on sample pairs: the byte permute that packs two sums keeps their low 16 bits, which IS the
+// reference's cast to int16_t before clipping (ipfilter.cpp:108-112); the clip to [0, maxVal] is one VIMNMX.S16x2.RELU
+// for both samples.  mx = maxVal | maxVal << 16, or 0 for int16 outputs (stored as they are: they wrap, never saturate).
+__device__ __forceinline__ uint32_t pack_clip2(int q0, int q1, uint32_t mx)
+{
+    uint32_t p = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
+    return mx ? __vimin_s16x2_relu(p, mx) : p;
+}
+template<typename DST>
+__device__ __forceinline__ void store4p(DST* d, uint32_t p01, uint32_t p23)
+{
+    uintptr_t a = (uintptr_t)d;
+    if (sizeof(DST) == 2)
+    {
+        if ((a & 7) == 0) *(uint2*)d = make_uint2(p01, p23);
+        else if ((a & 3) == 0) { ((uint32_t*)d)[0] = p01; ((uint32_t*)d)[1] = p23; }
+        else { d[0] = (DST)(p01 & 0xffff); d[1] = (DST)(p01 >> 16); d[2] = (DST)(p23 & 0xffff); d[3] = (DST)(p23 >> 16); }
+    }
+    else
+    {
+        uint32_t b = __byte_perm(p01, p23, 0x6420);
+        if ((a & 3) == 0) *(uint32_t*)d = b;
+        else { d[0] = (DST)(b & 0xff); d[1] = (DST)((b >> 8) & 0xff); d[2] = (DST)((b >> 16) & 0xff); d[3] = (DST)(b >> 24); }
+    }
+}
+
 // two-way dot product of packed 16-bit samples with two signed-byte taps (IDP.2A): the sample pair is unsigned
 // for pixels and signed for the int16 intermediates
 template<typename SRC> __device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c)
@@ -146,6 +172,7 @@ template<typename SRC, typename DST, int TAPS, bool VERT, int TW, int TH, bool F
 __device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_t ss, DST* __restrict__ d, intptr_t ds,
                                               int nr, uint32_t t0, uint32_t t1, const FirParams& p)
 {
+    const uint32_t mx = p.maxVal >= 0 ? (uint32_t)p.maxVal * 0x10001u : 0u;
     if (!VERT)
     {
         constexpr int NQ = (TW + TAPS - 1 + 3) / 4;              // quads covering TW + TAPS - 1 samples
@@ -171,10 +198,9 @@ __device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_
                     int i = (o4 + o) >> 1;
                     int sum = ((o4 + o) & 1) ? fir_pairs<SRC, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], t0, t1, p.offset)
                                              : fir_pairs<SRC, TAPS>(w[r][i], w[r][i + 1], w[r][(i + 2) % (2 * NQ + 1)], w[r][(i + 3) % (2 * NQ + 1)], t0, t1, p.offset);
-                    int q = (int)(int16_t)(sum >> p.shift);
-                    v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
+                    v[o] = sum >> p.shift;
                 }
-                store4(d + r * ds + o4, v);
+                store4p(d + r * ds + o4, pack_clip2(v[0], v[1], mx), pack_clip2(v[2], v[3], mx));
             }
         }
     }
@@ -200,12 +226,8 @@ __device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_
             int v[4];
 #pragma unroll
             for (int o = 0; o < 4; o++)
-            {
-                int sum = fir_pairs<SRC, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], t0, t1, p.offset);
-                int q = (int)(int16_t)(sum >> p.shift);
-                v[o] = p.maxVal >= 0 ? min(max(q, 0), p.maxVal) : q;
-            }
-            store4(d + r * ds, v);
+                v[o] = fir_pairs<SRC, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], t0, t1, p.offset) >> p.shift;
+            store4p(d + r * ds, pack_clip2(v[0], v[1], mx), pack_clip2(v[2], v[3], mx));
         }
     }
 }
@@ -276,9 +298,10 @@ hv_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ 
 }
 
 // hvpp throughput version (w % 4 == 0, h % 4 == 0, stride % 4 == 0): a group of G lanes (power of two, <= 32)
-// owns one block.  Pass 1 = hps with isRowExt into the group's smem tile (pitch w), 4x4 tiles through
-// load_row_quads + IDP.2A; pass 2 = vertical sp out of smem (8-byte aligned LDS), 4x4 output tiles.
-template<typename PIX, int TAPS>
+// owns one block.  Pass 1 = hps with isRowExt into the group's smem tile (pitch w), TW1 x 4 tiles through
+// load_row_quads + IDP.2A; pass 2 = vertical sp out of smem (8-byte aligned LDS), 4 x TH2 output tiles.
+// TW1 = 8 / TH2 = 8 (when the block allows) halve the loads per output sample of the respective pass.
+template<typename PIX, int TAPS, int TW1, int TH2>
 __global__ void __launch_bounds__(128)
 hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
                PIX* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst,
@@ -291,8 +314,7 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
     bool live = blk < n;
     int rows = h + TAPS - 1;
     int16_t* immed = immed_all + (size_t)grp * w * rows;
-    int tw = w >> 2;
-    constexpr int NQ = TAPS == 8 ? 3 : 2;
+    constexpr int NQ = (TW1 + TAPS - 1 + 3) / 4;
     uint32_t tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
     if (live)
     {
@@ -303,10 +325,11 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
         ty0 = TAPS == 8 ? c_lumaTapsB[idxY & 3][0] : c_chromaTapsB[idxY & 7];
         ty1 = TAPS == 8 ? c_lumaTapsB[idxY & 3][1] : 0;
         const PIX* s = src + offSrc[blk] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
+        int tw = w / TW1;
         int tiles1 = tw * ((rows + 3) >> 2);
         for (int t = l; t < tiles1; t += G)
         {
-            int tx = (t % tw) << 2, ty = (t / tw) << 2;
+            int tx = (t % tw) * TW1, ty = (t / tw) << 2;
             uint32_t wv[4][2 * NQ + 1];
 #pragma unroll
             for (int r = 0; r < 4; r++)
@@ -318,28 +341,34 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
                 uint32_t ws[2 * NQ];
 #pragma unroll
                 for (int i = 0; i < 2 * NQ; i++) ws[i] = __funnelshift_r(wv[r][i], wv[r][i + 1], 16);
-                int v[4];
 #pragma unroll
-                for (int o = 0; o < 4; o++)
+                for (int o4 = 0; o4 < TW1; o4 += 4)
                 {
-                    int i = o >> 1;
-                    int sum = (o & 1) ? fir_pairs<PIX, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], tx0, tx1, offset1)
-                                      : fir_pairs<PIX, TAPS>(wv[r][i], wv[r][i + 1], wv[r][i + 2], wv[r][i + 3], tx0, tx1, offset1);
-                    v[o] = sum >> shift1;
+                    int v[4];
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                    {
+                        int i = (o4 + o) >> 1;
+                        int sum = ((o4 + o) & 1) ? fir_pairs<PIX, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], tx0, tx1, offset1)
+                                                 : fir_pairs<PIX, TAPS>(wv[r][i], wv[r][i + 1], wv[r][(i + 2) % (2 * NQ + 1)], wv[r][(i + 3) % (2 * NQ + 1)], tx0, tx1, offset1);
+                        v[o] = sum >> shift1;
+                    }
+                    *(uint2*)(immed + (ty + r) * w + tx + o4) = make_uint2(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x5410),
+                                                                           __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x5410));
                 }
-                *(uint2*)(immed + (ty + r) * w + tx) = make_uint2((uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16),
-                                                                  (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16));
             }
         }
     }
     __syncwarp();
     if (!live) return;
     PIX* d = dst + offDst[blk];
-    int tiles2 = tw * (h >> 2);
+    int tw = w >> 2;
+    int tiles2 = tw * (h / TH2);
+    const uint32_t mx = (uint32_t)maxVal * 0x10001u;
     for (int t = l; t < tiles2; t += G)
     {
-        int tx = (t % tw) << 2, ty = (t / tw) << 2;
-        constexpr int NR = 4 + TAPS - 1;
+        int tx = (t % tw) << 2, ty = (t / tw) * TH2;
+        constexpr int NR = TH2 + TAPS - 1;
         uint2 q[NR];
 #pragma unroll
         for (int r = 0; r < NR; r++) q[r] = *(const uint2*)(immed + (ty + r) * w + tx);
@@ -351,17 +380,13 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
             pr[r][2] = __byte_perm(q[r].y, q[r + 1].y, 0x5410); pr[r][3] = __byte_perm(q[r].y, q[r + 1].y, 0x7632);
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < TH2; r++)
         {
             int v[4];
 #pragma unroll
             for (int o = 0; o < 4; o++)
-            {
-                int sum = fir_pairs<int16_t, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], ty0, ty1, offset2);
-                int qv = (int)(int16_t)(sum >> shift2);
-                v[o] = min(max(qv, 0), maxVal);
-            }
-            store4(d + (intptr_t)(ty + r) * ds + tx, v);
+                v[o] = fir_pairs<int16_t, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], ty0, ty1, offset2) >> shift2;
+            store4p(d + (intptr_t)(ty + r) * ds + tx, pack_clip2(v[0], v[1], mx), pack_clip2(v[2], v[3], mx));
         }
     }
 }
@@ -388,6 +413,34 @@ p2s_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restr
 #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = (int)(int16_t)((int)(int16_t)(a[i] << shift) - 8192);
     store4(dst + offDst[blk] + (intptr_t)y * ds + x, v);
+}
+
+// p2s for blocks whose width is a multiple of 8 and height a multiple of 4: one thread per 8x4 strip.
+// (pix << shift) - 8192 runs on packed pairs: pix << shift < 2^14, and the lane-wise subtraction is borrow-free
+// (device_util.cuh psub16).
+template<typename PIX>
+__global__ void __launch_bounds__(256)
+p2s_wide_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restrict__ offSrc,
+                int16_t* __restrict__ dst, intptr_t ds, const int32_t* __restrict__ offDst, int n, int w, int h, int shift)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int sw = w >> 3;
+    int per = sw * (h >> 2);
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid - (long long)blk * per);
+    int y = (r / sw) << 2, x = (r % sw) << 3;
+    uint32_t wv[4][4];
+    load_rows8<4>(src + offSrc[blk] + (intptr_t)y * ss + x, ss, wv);
+    int16_t* d = dst + offDst[blk] + (intptr_t)y * ds + x;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = psub16(wv[i][k] << shift, 0x20002000u);
+        store8_s16(d + i * ds, o);
+    }
 }
 
 template<typename PIX>
@@ -463,13 +516,16 @@ static int launch_interp(x265b200_ctx* ctx, int kind, int w, int h, const void* 
         size_t smem = (size_t)w * (h + TAPS - 1) * sizeof(int16_t);
         if (tiled && !(h & 3))
         {
-            int tiles2 = (w >> 2) * (h >> 2);
+            // lanes per block: about two pass-2 tiles (4 x 8 or 4 x 4) per lane
+            const bool wide = !(w & 7), tall = !(h & 7);
+            int tiles2 = (w >> 2) * (tall ? h >> 3 : h >> 2);
             int G = 1;
-            while (G < tiles2 && G < 32) G <<= 1;
+            while (G * 2 <= tiles2 / 2 && G < 32) G <<= 1;
             int perCta = 128 / G;
-            hv_tile_kernel<PIX, TAPS><<<ceil_div(n, perCta), 128, perCta * smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, w, h,
-                                                                          G, shift1, (int)((unsigned)-8192 << shift1), shift2,
-                                                                          (1 << (shift2 - 1)) + (8192 << 6), maxVal);
+#define HV(TW1_, TH2_) hv_tile_kernel<PIX, TAPS, TW1_, TH2_><<<ceil_div(n, perCta), 128, perCta * smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, n, w, h, \
+                                                                          G, shift1, (int)((unsigned)-8192 << shift1), shift2, (1 << (shift2 - 1)) + (8192 << 6), maxVal)
+            if (wide && tall) HV(8, 8); else if (wide) HV(8, 4); else if (tall) HV(4, 8); else HV(4, 4);
+#undef HV
             break;
         }
         hv_kernel<PIX, TAPS><<<n, 256, smem, st>>>((const PIX*)src, ss, offSrc, (PIX*)dst, ds, offDst, coeffIdx, w, h,
@@ -478,7 +534,9 @@ static int launch_interp(x265b200_ctx* ctx, int kind, int w, int h, const void* 
         break;
     }
     case X265B200_IP_P2S:
-        if (tiled)
+        if (tiled && !(w & 7) && !(h & 3))
+            p2s_wide_kernel<PIX><<<ceil_div((long long)n * (w >> 3) * (h >> 2), 256), 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);
+        else if (tiled)
             p2s_tile_kernel<PIX><<<ceil_div((long long)n * (w >> 2) * h, 256), 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);
         else
             p2s_kernel<PIX><<<grid, 256, 0, st>>>((const PIX*)src, ss, offSrc, (int16_t*)dst, ds, offDst, n, w, h, headRoom);

@@ -209,9 +209,12 @@ sa8d_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intpt
     if (live && l == 0) out[blk] = acc;
 }
 
-// Throughput sa8d for planes with strides that are multiples of 4 samples: grouped chunk loads, packed
-// differences, vertical 8-point Hadamard on packed 16-bit lanes (|value| <= 8 * 4095 < 2^15), horizontal in int32.
-template<typename T>
+// Throughput sa8d for planes with strides that are multiples of 4 samples: thread = one 8x8 tile, loaded as two 8x4
+// strips of grouped chunk loads.  Differences and the vertical 8-point Hadamard run on packed 16-bit lanes
+// (|value| <= 8 * 4095 < 2^15).  PKH (depth <= 10): the two horizontal stages that pair different words (distance 4
+// and 2) stay packed as well (8 * 1023 * 4 < 2^15), and the last stage, which pairs the two lanes of a word, is folded
+// into the sum of magnitudes: |a + b| + |a - b| = 2 max(|a|, |b|).  Otherwise the horizontal pass runs in int32.
+template<typename T, bool PKH>
 __global__ void __launch_bounds__(128)
 sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
@@ -251,13 +254,15 @@ sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, 
             const T* pb = b + (intptr_t)y * sb + x;
             uint32_t d[8][4];
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int half = 0; half < 2; half++)
             {
-                uint32_t wa[4], wb[4];
-                load_row_quads<2>(pa + r * sa, wa);
-                load_row_quads<2>(pb + r * sb, wb);
+                uint32_t wa[4][4], wb[4][4];
+                load_rows8<4>(pa + (intptr_t)(half * 4) * sa, sa, wa);
+                load_rows8<4>(pb + (intptr_t)(half * 4) * sb, sb, wb);
 #pragma unroll
-                for (int c = 0; c < 4; c++) d[r][c] = wa[c] - wb[c];
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) d[half * 4 + r][c] = wa[r][c] - wb[r][c];
             }
             // vertical 8-point Hadamard, packed
 #pragma unroll
@@ -274,24 +279,46 @@ sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, 
                             d[j][c] = u + v; d[j + step][c] = u - v;
                         }
             }
-#pragma unroll
-            for (int r = 0; r < 8; r++)
+            if (PKH)
             {
-                int m[8];
+                int half = 0;
 #pragma unroll
-                for (int c = 0; c < 4; c++) unpack_s16x2(d[r][c], m[2 * c], m[2 * c + 1]);
+                for (int r = 0; r < 8; r++)
+                {
+                    // columns (0,1) (2,3) (4,5) (6,7): distance-4 pairs words 0/2 and 1/3, distance-2 pairs 0/1 and 2/3
+                    uint32_t e0 = d[r][0] + d[r][2], e1 = d[r][1] + d[r][3], e2 = d[r][0] - d[r][2], e3 = d[r][1] - d[r][3];
+                    uint32_t f[4] = { e0 + e1, e0 - e1, e2 + e3, e2 - e3 };
 #pragma unroll
-                for (int step = 1; step < 8; step <<= 1)
+                    for (int c = 0; c < 4; c++)
+                    {
+                        int p, q;
+                        unpack_s16x2(f[c], p, q);
+                        half += max(abs(p), abs(q));
+                    }
+                }
+                raw = half << 1;
+            }
+            else
+            {
 #pragma unroll
-                    for (int i = 0; i < 8; i += step << 1)
+                for (int r = 0; r < 8; r++)
+                {
+                    int m[8];
 #pragma unroll
-                        for (int j = i; j < i + step; j++)
-                        {
-                            int u = m[j], v = m[j + step];
-                            m[j] = u + v; m[j + step] = u - v;
-                        }
+                    for (int c = 0; c < 4; c++) unpack_s16x2(d[r][c], m[2 * c], m[2 * c + 1]);
 #pragma unroll
-                for (int c = 0; c < 8; c++) raw += abs(m[c]);
+                    for (int step = 1; step < 8; step <<= 1)
+#pragma unroll
+                        for (int i = 0; i < 8; i += step << 1)
+#pragma unroll
+                            for (int j = i; j < i + step; j++)
+                            {
+                                int u = m[j], v = m[j + step];
+                                m[j] = u + v; m[j + step] = u - v;
+                            }
+#pragma unroll
+                    for (int c = 0; c < 8; c++) raw += abs(m[c]);
+                }
             }
         }
         if (mode16)
@@ -328,6 +355,30 @@ residual_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__
     unpack_s16x2(wa[0] - wb[0], d0, d1);
     unpack_s16x2(wa[1] - wb[1], d2, d3);
     *(uint2*)(dst + (size_t)blk * w * h + y * w + x) = make_uint2((uint32_t)(d0 & 0xffff) | ((uint32_t)d1 << 16), (uint32_t)(d2 & 0xffff) | ((uint32_t)d3 << 16));
+}
+
+// residual for blocks whose width is a multiple of 8 and height a multiple of 4: one thread per 8x4 strip,
+// 24 chunk loads issued up front, lane-wise packed subtraction, 16-byte stores into the block-contiguous output
+template<typename T>
+__global__ void __launch_bounds__(256)
+residual_wide_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
+                     const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
+                     int n, int w, int h, int16_t* __restrict__ dst)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int sw = w >> 3;
+    int per = sw * (h >> 2);
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid - (long long)blk * per);
+    int y = (r / sw) << 2, x = (r % sw) << 3;
+    uint32_t wa[4][4], wb[4][4];
+    load_rows8<4>(A + offA[blk] + (intptr_t)y * sa + x, sa, wa);
+    load_rows8<4>(B + offB[blk] + (intptr_t)y * sb + x, sb, wb);
+    int16_t* d = dst + (size_t)blk * w * h + y * w + x;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        *(uint4*)(d + i * w) = make_uint4(psub16(wa[i][0], wb[i][0]), psub16(wa[i][1], wb[i][1]), psub16(wa[i][2], wb[i][2]), psub16(wa[i][3], wb[i][3]));
 }
 
 // ADS (pixel.cpp:121-165): one warp per job; ordered compaction with ballot + popc.
@@ -418,7 +469,10 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
         long long threads = (long long)n * G;
         if (!((sa | sb) & 3))
         {
-            sa8d_fast_kernel<T><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
+            if (ctx->depth <= 10)
+                sa8d_fast_kernel<T, true><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
+            else
+                sa8d_fast_kernel<T, false><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
             B200_LAUNCH_CHECK(ctx);
             return X265B200_OK;
         }
@@ -549,7 +603,15 @@ extern "C" int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const vo
     if (n == 0) return X265B200_OK;
     long long threads = (long long)n * (w >> 2) * h;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!((sa | sb) & 3))
+    if (!((sa | sb) & 3) && !(w & 7) && !((uintptr_t)dst & 15))
+    {
+        long long strips = (long long)n * (w >> 3) * (h >> 2);
+        if (ctx->pixbytes == 1)
+            residual_wide_kernel<uint8_t><<<ceil_div(strips, 256), 256, 0, st>>>((const uint8_t*)A, sa, (const uint8_t*)B, sb, offA, offB, n, w, h, dst);
+        else
+            residual_wide_kernel<uint16_t><<<ceil_div(strips, 256), 256, 0, st>>>((const uint16_t*)A, sa, (const uint16_t*)B, sb, offA, offB, n, w, h, dst);
+    }
+    else if (!((sa | sb) & 3))
     {
         if (ctx->pixbytes == 1)
             residual_fast_kernel<uint8_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint8_t*)A, sa, (const uint8_t*)B, sb, offA, offB, n, w, h, dst);

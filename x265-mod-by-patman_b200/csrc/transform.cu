@@ -304,6 +304,81 @@ inv_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, in
 // ---------------------------------------------------------------- quant family
 // One thread per 8 coefficients.  numSig is accumulated with a warp-segmented sum and one atomic
 // per (warp, block) into a zeroed counter.
+// Throughput version for numCoeff = 16 / 64 / 256 / 1024: one thread owns the same eight coefficient positions of NB
+// consecutive blocks, so the quantCoeff entries are fetched once per NB blocks and NB 16-byte coefficient loads are in
+// flight per thread.  Blocks of <= 256 coefficients are reduced inside one lane group and numSig is stored directly
+// (no zeroing pass, no atomics); 32x32 blocks span four warps and use one atomic per warp.
+template<bool NQUANT, bool STORE_DU, int NB>
+__global__ void __launch_bounds__(256)
+quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__ quantCoeff, int32_t* __restrict__ deltaU,
+                   int16_t* __restrict__ qCoef, int qBits, int add, int numCoeff, int n, uint32_t* __restrict__ numSig)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int per = numCoeff >> 3;                       // power of two
+    int lgper = __ffs(per) - 1;
+    int grp = (int)(gid >> lgper);
+    int pos = ((int)gid & (per - 1)) << 3;
+    int blk0 = grp * NB;
+    bool live = blk0 < n;
+    int sig[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) sig[j] = 0;
+    if (live)
+    {
+        int4 cv[NB];
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+            cv[j] = blk0 + j < n ? __ldg((const int4*)(coef + (size_t)(blk0 + j) * numCoeff + pos)) : make_int4(0, 0, 0, 0);
+        int4 q0 = __ldg((const int4*)(quantCoeff + pos));
+        int4 q1 = __ldg((const int4*)(quantCoeff + pos + 4));
+        int q[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        int qBits8 = qBits - 8;
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+        {
+            if (blk0 + j >= n) break;
+            int c[8] = { (int16_t)(cv[j].x & 0xffff), cv[j].x >> 16, (int16_t)(cv[j].y & 0xffff), cv[j].y >> 16,
+                         (int16_t)(cv[j].z & 0xffff), cv[j].z >> 16, (int16_t)(cv[j].w & 0xffff), cv[j].w >> 16 };
+            int lv[8], du[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                int level = c[i];
+                int sign = level < 0 ? -1 : 1;
+                int tmplevel = (int)((unsigned)abs(level) * (unsigned)q[i]);          // int32 wrap, dct.cpp:678
+                level = (int)((unsigned)tmplevel + (unsigned)add) >> qBits;
+                du[i] = (int)((unsigned)tmplevel - ((unsigned)level << qBits)) >> qBits8;
+                sig[j] += level != 0;
+                level = (int)((unsigned)level * (unsigned)sign);
+                level = clip16(level);
+                lv[i] = NQUANT ? abs(level) : level;                                  // nquant: (int16)abs(clip), dct.cpp:711
+            }
+            size_t base = (size_t)(blk0 + j) * numCoeff + pos;
+            int4 o;
+            o.x = (lv[0] & 0xffff) | (lv[1] << 16); o.y = (lv[2] & 0xffff) | (lv[3] << 16);
+            o.z = (lv[4] & 0xffff) | (lv[5] << 16); o.w = (lv[6] & 0xffff) | (lv[7] << 16);
+            *(int4*)(qCoef + base) = o;
+            if (STORE_DU)
+            {
+                *(int4*)(deltaU + base) = make_int4(du[0], du[1], du[2], du[3]);
+                *(int4*)(deltaU + base + 4) = make_int4(du[4], du[5], du[6], du[7]);
+            }
+        }
+    }
+    int lane = threadIdx.x & 31;
+    int G = per < 32 ? per : 32;
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+    {
+        int sum = group_sum(sig[j], G);
+        if (live && blk0 + j < n && (lane & (G - 1)) == 0)
+        {
+            if (per <= 32) numSig[blk0 + j] = (uint32_t)sum;
+            else if (sum) atomicAdd(numSig + blk0 + j, (uint32_t)sum);
+        }
+    }
+}
+
 template<bool NQUANT, bool STORE_DU>
 __global__ void __launch_bounds__(256)
 quant_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__ quantCoeff, int32_t* __restrict__ deltaU,
@@ -518,7 +593,23 @@ namespace b200 {
 int launch_quant(x265b200_ctx* ctx, int mode, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef,
                  int qBits, int add, int numCoeff, int n, uint32_t* numSig, cudaStream_t st)
 {
-    B200_CUDA(ctx, cudaMemsetAsync(numSig, 0, (size_t)n * sizeof(uint32_t), st));
+    int per = numCoeff >> 3;
+    const bool pow2 = (per & (per - 1)) == 0 && !(((uintptr_t)coef | (uintptr_t)qCoef | (uintptr_t)quantCoeff | (uintptr_t)deltaU) & 15);
+    if (!pow2 || per > 32) B200_CUDA(ctx, cudaMemsetAsync(numSig, 0, (size_t)n * sizeof(uint32_t), st));
+    if (pow2)
+    {
+        constexpr int NB = 4;
+        long long threads = (long long)ceil_div(n, NB) * per;
+        int grid = ceil_div(threads, 256);
+        if (mode == 0)
+            quant_multi_kernel<false, true, NB><<<grid, 256, 0, st>>>(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig);
+        else if (mode == 1)
+            quant_multi_kernel<true, false, NB><<<grid, 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
+        else
+            quant_multi_kernel<false, false, NB><<<grid, 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
+        B200_LAUNCH_CHECK(ctx);
+        return X265B200_OK;
+    }
     long long threads = (long long)n * (numCoeff >> 3);
     int grid = ceil_div(threads, 256);
     if (mode == 0)

@@ -689,6 +689,20 @@ idct16_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
     }
 }
 
+// 4x4 transpose of int16 across the four lanes {l, l^4, l^8, l^12} (row index r = (lane >> 2) & 3): lane r passes
+// its row (a_r0..a_r3 as two packed words) and returns column r (a_0r..a_3r).  Two shuffles, four byte permutes.
+__device__ __forceinline__ uint2 transpose4x4_s16(uint2 v, int r)
+{
+    // exchange with r ^ 2: afterwards the lane holds the 2x2 block rows {r & 1, (r & 1) + 2} x cols {2 (r >> 1), +1}
+    uint32_t recv = __shfl_xor_sync(0xffffffffu, (r & 2) ? v.x : v.y, 8);
+    uint32_t p0 = (r & 2) ? recv : v.x, p1 = (r & 2) ? v.y : recv;
+    // exchange with r ^ 1: even lanes keep the low halves (their column) and pass the high ones, odd lanes the reverse
+    uint32_t lows = __byte_perm(p0, p1, 0x5410), highs = __byte_perm(p0, p1, 0x7632);
+    uint32_t got = __shfl_xor_sync(0xffffffffu, (r & 1) ? lows : highs, 4);
+    uint32_t ev = (r & 1) ? got : lows, od = (r & 1) ? highs : got;      // (row 0, row 2) and (row 1, row 3) of the column
+    return make_uint2(__byte_perm(ev, od, 0x5410), __byte_perm(ev, od, 0x7632));
+}
+
 // two 8x8 TUs (SMALL = 8) or eight 4x4 TUs (SMALL = 4) per MMA group, block-diagonal constant operands
 template<int SMALL, int UN>
 __global__ void __launch_bounds__(128)
@@ -707,39 +721,33 @@ idct_small_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restri
     if (SMALL == 8) { a1[0] = c_IA8[0][lane]; a1[1] = c_IA8[1][lane]; b2 = c_IB8[lane]; }
     else { a1[0] = c_IA4[kind][0][lane]; a1[1] = c_IA4[kind][1][lane]; b2 = c_IB4[kind][lane]; }
     const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
-    // gather: slot 4t+e.  N = 8: TU t>>1, in[2e + (t&1)][g].  N = 4: TU (g>>2)*4 + t, in[e][g&3].
+    // stage-1 B operand, slot 4t+e.  N = 8: TU t>>1, in[2e + (t&1)][g].  N = 4: TU (g>>2)*4 + t, in[e][g&3].
+    // Each lane fetches ONE 8-byte row piece -- N = 8: row 2r + (t&1), columns 4(g>>2)..+3 of TU t>>1; N = 4: row r of
+    // TU (g>>2)*4 + t, with r = g & 3 -- so a warp reads the group's 256 contiguous bytes with one instruction, and
+    // the lanes {g&3 = 0..3} transpose their 4x4 among themselves (transpose4x4_s16) to get the column they need.
     const int ld_tu = SMALL == 8 ? (t >> 1) : ((g >> 2) * 4 + t);
-    const int ld_off = SMALL == 8 ? (t & 1) * 8 + g : (g & 3);
-    const int ld_step = SMALL == 8 ? 16 : 4;
+    const int ld_off = SMALL == 8 ? (2 * (g & 3) + (t & 1)) * 8 + 4 * (g >> 2) : (g & 3) * 4;
     // output: accumulator rows g / g+8.  N = 8: TU 0 / 1, out[g][2t..].  N = 4: TU (t>>1)*4 + (g>>2) (+2), out[g&3][2(t&1)..]
     const int st_tu0 = SMALL == 8 ? 0 : (t >> 1) * 4 + (g >> 2);
     const int st_tu1 = SMALL == 8 ? 1 : (t >> 1) * 4 + (g >> 2) + 2;
     const int st_row = SMALL == 8 ? g : (g & 3);
     const int st_col = SMALL == 8 ? 2 * t : 2 * (t & 1);
 
-    int x[UN][4];
+    uint2 x[UN];
 #pragma unroll
     for (int u = 0; u < UN; u++)
-    {
-        const int16_t* q = src + (size_t)min((warp * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off;
-#pragma unroll
-        for (int e = 0; e < 4; e++) x[u][e] = __ldg(q + e * ld_step);
-    }
+        x[u] = __ldg((const uint2*)(src + (size_t)min((warp * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off));
     for (int grp = warp; grp < ngroups; grp += nwarps)
     {
         uint32_t blo[UN], bhi[UN];
 #pragma unroll
-        for (int u = 0; u < UN; u++) pack4(x[u][0], x[u][1], x[u][2], x[u][3], blo[u], bhi[u]);
+        for (int u = 0; u < UN; u++) split4(transpose4x4_s16(x[u], g & 3), blo[u], bhi[u]);
         int nxt = grp + nwarps;
         if (nxt < ngroups)
         {
 #pragma unroll
             for (int u = 0; u < UN; u++)
-            {
-                const int16_t* q = src + (size_t)min((nxt * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off;
-#pragma unroll
-                for (int e = 0; e < 4; e++) x[u][e] = __ldg(q + e * ld_step);
-            }
+                x[u] = __ldg((const uint2*)(src + (size_t)min((nxt * UN + u) * TPG + ld_tu, n - 1) * NN + ld_off));
         }
 #pragma unroll
         for (int u = 0; u < UN; u++)
@@ -770,7 +778,7 @@ idct_small_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restri
 bool launch_idct_imma(x265b200_ctx* ctx, int N, const int16_t* src, int n, int16_t* dst, intptr_t dstStride,
                       const int32_t* off, int shift1, int shift2, cudaStream_t st, int dst4)
 {
-    if ((uintptr_t)src & 3) return false;
+    if ((uintptr_t)src & 7) return false;
     int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     int grid = sms * 8;
     if (N == 32)
