@@ -318,10 +318,11 @@ def run_b200_arm(args):
     dominant = "satd" if tsum["satd"] >= tsum["dct"] else "dct"
     ach = (satd_bytes / (satd_ms * 1e-3) if dominant == "satd" else dct_bytes / (dct_ms * 1e-3)) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1f_satd_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_satd_traffic.json")
     if dominant == "satd" and os.path.exists(tp):
         # dram__bytes_read + write per launch of this kernel from the committed ncu --set full capture of this workload
-        traffic = json.load(open(tp))["dram_bytes_per_launch_avg"]
+        tj = json.load(open(tp))
+        traffic = tj["dram_bytes_per_launch_avg"] if tj.get("frames_per_launch") == F else None
     roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": satd_bytes if dominant == "satd" else dct_bytes,

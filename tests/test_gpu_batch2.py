@@ -223,7 +223,8 @@ def test_tu_chain_batch(depth):
         tshift = 15 - depth - {4: 2, 8: 3, 16: 4, 32: 5}[N]
         qbits = 14 + per + tshift
         add = 85 << (qbits - 9)
-        qc = np.full(N * N, flat[rem], np.int32)
+        # position-dependent table (as with scaling lists) so that a wrong coefficient-position map cannot hide behind a flat one
+        qc = (flat[rem] + rng.integers(-3000, 3001, N * N)).astype(np.int32) if qp not in (37, 45) else np.full(N * N, flat[rem], np.int32)
         scale, shift = inv[rem] << per, 20 - 14 - tshift
         recon0 = np.full(geo.plane_elems, 5, orc.pix)
         rq, rns, rz, rr = orc.tu_chain_batch(N, F, geo.stride, Pcur, geo.stride, offF, offP, qc, qbits, add, scale, shift, recon0, geo.stride, offF)

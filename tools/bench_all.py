@@ -129,7 +129,7 @@ def main():
         z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
         ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
                                                qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
-        add("tu_chain %dx%d (6 stage kernels, L2-resident intermediates)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
+        add("tu_chain %dx%d (two fused tensor-core kernels)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
     # ---- interpolation, frame-tiled 64x64 and 16x16 luma, 8x8 chroma-size blocks
     dstP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); dstS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
     srcS = torch.randint(-8192, 8192, (F * pe,), dtype=torch.int16, device="cuda")

@@ -63,6 +63,16 @@ def main():
                 ctx.dct_batch(pkg.TR_DCT, N, res, N, None, coef, count=S // (N * N))
             elif kind == "idct":
                 ctx.idct_batch(pkg.TR_DCT, N, res, rec, N, None, count=S // (N * N))
+            elif kind == "tuchain":
+                oa, ob = desc(N, N)
+                n = oa.numel()
+                qcN = torch.full((N * N,), 16384, dtype=torch.int32, device="cuda")
+                tshift = 15 - D - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+                qbits = 14 + 4 + tshift
+                qo = torch.empty(S, dtype=torch.int16, device="cuda"); ns = torch.empty(n, dtype=torch.int32, device="cuda")
+                z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
+                ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
+                                   qo, ns, dstP, geo.stride, oa, z, r)
             elif kind == "residual":
                 oa, ob = desc(N, N)
                 ctx.residual_batch(N, N, A, geo.stride, B, geo.stride, oa, ob, res)

@@ -13,7 +13,9 @@
 // accumulator fragment of stage 1 is, element for element, a B-operand fragment of stage 2 once the
 // contraction index j is enumerated in the order the accumulator layout delivers it; that
 // permutation is folded into the constant A operand of stage 2 (table built on the host).
+#include <stdlib.h>
 #include "internal.h"
+#include "device_util.cuh"
 
 namespace b200 {
 
@@ -846,5 +848,7 @@ bool launch_dct_imma(x265b200_ctx* ctx, int N, const int16_t* src, intptr_t srcS
         return false;
     return true;
 }
+
+#include "tu_fused.cuh"
 
 } // namespace b200

@@ -7,6 +7,7 @@
 // B200 mapping: the stage kernels are the batched primitives of this library (tensor-core DCT/IDCT); the chain is
 // walked in chunks whose int16 intermediates (residual, coefficients, dequantised coefficients, reconstructed
 // residual) total a few MB, so they never leave the 126 MB L2: HBM sees fenc + pred in, qCoef + recon + costs out.
+#include <stdlib.h>
 #include "internal.h"
 #include "device_util.cuh"
 
@@ -14,6 +15,10 @@ namespace b200 {
 
 int launch_quant(x265b200_ctx* ctx, int mode, const int16_t* coef, const int32_t* quantCoeff, int32_t* deltaU, int16_t* qCoef,
                  int qBits, int add, int numCoeff, int n, uint32_t* numSig, cudaStream_t st);       // transform.cu
+bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
+                     const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
+                     int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
+                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);   // tu_fused.cuh (transform_mma.cu)
 
 // recon = clip(pred + resi') with the cbf == 0 and DC-only cases, plus both distortions; 4 samples per thread
 template<typename T>
@@ -99,8 +104,14 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int NN = N * N;
-    // chunk so that the two int16 scratch planes (2 x 16 MB) plus the chunk's qCoef (16 MB) stay L2-resident
-    // while each stage kernel is still long enough (>= 10 us) to hide launch latency
+    // Default: two fused tensor-core kernels over all TUs, no scratch (tu_fused.cuh).
+    // dct_path == 1 (validation twin): the six stage kernels of the batched primitives, walked in chunks whose two
+    // int16 scratch planes stay L2-resident.
+    if (ctx->dct_path == 0 &&
+        launch_tu_fused(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
+                        qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
+        return X265B200_OK;
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_chain fused launch");
     const int chunkTUs = (8 << 20) / NN;
     int16_t* scratch = nullptr;
     size_t chunkElems = (size_t)(n < chunkTUs ? n : chunkTUs) * NN;
