@@ -70,6 +70,14 @@ enum {
     X265B200_IP_P2S = 7                 /* filter_p2s_t   convert_p2s / p2s       ipfilter.cpp:40-57   */
 };
 
+/* two-input block operations for x265b200_blockop_batch (slots adjacent to the hot path) */
+enum {
+    X265B200_BOP_SUB_PS = 0,            /* pixel_sub_ps_t  cu[].sub_ps       pixel.cpp:806-818  int16 = pixel - pixel */
+    X265B200_BOP_ADD_PS = 1,            /* pixel_add_ps_t  cu[].add_ps       pixel.cpp:820-832  pixel = clip(pixel + int16) */
+    X265B200_BOP_PIXELAVG = 2,          /* pixelavg_pp_t   pu[].pixelavg_pp  pixel.cpp:537-549  pixel = (pixel + pixel + 1) >> 1 */
+    X265B200_BOP_ADDAVG = 3             /* addAvg_t        pu[].addAvg       pixel.cpp:834-855  pixel = clip((int16 + int16 + offset) >> shift) */
+};
+
 /* ------------------------------------------------------------------ lifecycle */
 
 /* bit_depth in {8, 10, 12}: fixes sizeof(pixel) and every depth-dependent shift, exactly as
@@ -171,6 +179,17 @@ int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t
                             int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
                             uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream);
 
+/* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
+ * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
+int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,
+                           const void* B, intptr_t strideB, const int32_t* offB, void* D, intptr_t strideD, const int32_t* offD,
+                           int n, x265b200_stream stream);
+
+/* downscale_t frameInitLowres (pixel.cpp:595-620) over one plane: width x height are the LOWRES dimensions; reads
+ * 2 * width + 1 columns of 2 * height + 1 rows of src, writes the four half-resolution planes. */
+int x265b200_lowres_batch(x265b200_ctx* ctx, const void* src, intptr_t srcStride, void* dst0, void* dsth, void* dstv, void* dstc,
+                          intptr_t dstStride, int width, int height, x265b200_stream stream);
+
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 
 int x265b200_sad(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
@@ -194,6 +213,14 @@ void x265b200_dequant_scaling(x265b200_ctx*, const int16_t* src, const int32_t* 
 /* kind = X265B200_IP_*; extra = isRowExt for HPS, idxY for HVPP (coeffIdx is then idxX), else ignored */
 void x265b200_interp(x265b200_ctx*, int kind, int taps, int w, int h, const void* src, intptr_t srcStride,
                      void* dst, intptr_t dstStride, int coeffIdx, int extra);
+
+/* adjacent slots: argument order of primitives.h:189-192 and :168 */
+void x265b200_sub_ps(x265b200_ctx*, int w, int h, int16_t* dst, intptr_t dstride, const void* src0, const void* src1, intptr_t sstride0, intptr_t sstride1);
+void x265b200_add_ps(x265b200_ctx*, int w, int h, void* dst, intptr_t dstride, const void* src0, const int16_t* src1, intptr_t sstride0, intptr_t sstride1);
+void x265b200_pixelavg_pp(x265b200_ctx*, int w, int h, void* dst, intptr_t dstride, const void* src0, intptr_t sstride0, const void* src1, intptr_t sstride1, int weight);
+void x265b200_addAvg(x265b200_ctx*, int w, int h, const int16_t* src0, const int16_t* src1, void* dst, intptr_t src0Stride, intptr_t src1Stride, intptr_t dstStride);
+void x265b200_frame_init_lowres(x265b200_ctx*, const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
+                                intptr_t srcStride, intptr_t dstStride, int width, int height);
 
 #ifdef __cplusplus
 }

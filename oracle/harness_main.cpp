@@ -81,7 +81,22 @@ static int coverage()
     SLOT(dst4x4); SLOT(idst4x4); SLOT(quant); SLOT(nquant); SLOT(dequant_normal); SLOT(dequant_scaling);
     printf("coverage: %d hot-path slots in the C table, %d bound to B200 entries, %d missing, %d still C, %d extra\n",
            want, bound, missing, same, extra);
-    return missing + same + extra;
+    int hot = missing + same + extra;
+    /* adjacent slots: same chains, not named by the north star */
+    want = bound = missing = same = extra = 0;
+    for (int i = 0; i < NUM_PU_SIZES; i++)
+    {
+        SLOT(pu[i].pixelavg_pp[0]); SLOT(pu[i].pixelavg_pp[1]); SLOT(pu[i].addAvg[0]); SLOT(pu[i].addAvg[1]);
+        for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].pu[i].addAvg[0]); SLOT(chroma[c].pu[i].addAvg[1]); }
+    }
+    for (int i = 0; i < NUM_CU_SIZES; i++)
+    {
+        SLOT(cu[i].sub_ps); SLOT(cu[i].add_ps[0]); SLOT(cu[i].add_ps[1]);
+        for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].sub_ps); SLOT(chroma[c].cu[i].add_ps[0]); SLOT(chroma[c].cu[i].add_ps[1]); }
+    }
+    SLOT(frameInitLowres);
+    printf("adjacent: %d slots in the C table, %d bound to B200 entries, %d missing, %d still C, %d extra\n", want, bound, missing, same, extra);
+    return hot + missing + same + extra;
 }
 
 int main(int argc, char** argv)

@@ -322,4 +322,53 @@ int ref_dct_batch(int N, const int16_t* src, intptr_t srcStride, const int32_t* 
     return 0;
 }
 
+
+/* ---- adjacent slots through the reference's own table ---- */
+int ref_blockop(int op, int w, int h, const void* A, intptr_t sa, const void* B, intptr_t sb, void* D, intptr_t sd)
+{
+    ensure();
+    if (op == 2 || op == 3)
+    {
+        int p = lumaPart(w, h), csp = 0;
+        if (p < 0 && op == 3)
+        {
+            if (!chromaSlot(w, h, csp, p, false)) return -1;
+            g_c.chroma[csp].pu[p].addAvg[NONALIGNED]((const int16_t*)A, (const int16_t*)B, (pixel*)D, sa, sb, sd);
+            return 0;
+        }
+        if (p < 0) return -1;
+        if (op == 2) g_c.pu[p].pixelavg_pp[NONALIGNED]((pixel*)D, sd, (const pixel*)A, sa, (const pixel*)B, sb, 32);
+        else g_c.pu[p].addAvg[NONALIGNED]((const int16_t*)A, (const int16_t*)B, (pixel*)D, sa, sb, sd);
+        return 0;
+    }
+    /* cu slots: square luma sizes, 4:2:0 (w == h, half size) shares them; 4:2:2 chroma CUs are w x 2w */
+    int cu = -1;
+    for (int i = 0; i < NUM_CU_SIZES; i++) if ((4 << i) == w) cu = i;
+    if (w == h && cu >= 0)
+    {
+        if (op == 0) g_c.cu[cu].sub_ps((int16_t*)D, sd, (const pixel*)A, (const pixel*)B, sa, sb);
+        else g_c.cu[cu].add_ps[NONALIGNED]((pixel*)D, sd, (const pixel*)A, (const int16_t*)B, sa, sb);
+        return 0;
+    }
+    for (int i = 0; i < NUM_CU_SIZES; i++)
+    {
+        if (w == h && (2 << i) == w)
+        {
+            if (op == 0) g_c.chroma[X265_CSP_I420].cu[i].sub_ps((int16_t*)D, sd, (const pixel*)A, (const pixel*)B, sa, sb);
+            else g_c.chroma[X265_CSP_I420].cu[i].add_ps[NONALIGNED]((pixel*)D, sd, (const pixel*)A, (const int16_t*)B, sa, sb);
+            return 0;
+        }
+        if (h == 2 * w && (2 << i) == w)
+        {
+            if (op == 0) g_c.chroma[X265_CSP_I422].cu[i].sub_ps((int16_t*)D, sd, (const pixel*)A, (const pixel*)B, sa, sb);
+            else g_c.chroma[X265_CSP_I422].cu[i].add_ps[NONALIGNED]((pixel*)D, sd, (const pixel*)A, (const int16_t*)B, sa, sb);
+            return 0;
+        }
+    }
+    return -1;
+}
+
+void ref_lowres(const pixel* src, intptr_t ss, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ds, int width, int height)
+{ ensure(); g_c.frameInitLowres(src, d0, dh, dv, dc, ss, ds, width, height); }
+
 } // extern "C"

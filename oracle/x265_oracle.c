@@ -697,3 +697,54 @@ EXPORT void orc_idct_batch(int N, int dst4, const int16_t* src, int n, int16_t* 
     for (int i = 0; i < n; i++)
         inv_transform(N, dst4, src + (size_t)i * N * N, dst + off[i], dstStride);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Adjacent slots: two-input block operations and the lookahead's lowres downscale.
+ * op: 0 sub_ps (pixel.cpp:806-818), 1 add_ps (pixel.cpp:820-832), 2 pixelavg_pp (pixel.cpp:537-549),
+ *     3 addAvg (pixel.cpp:834-855).  Element types follow the op.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void orc_blockop(int op, int w, int h, const void* A, intptr_t sa, const void* B, intptr_t sb, void* D, intptr_t sd)
+{
+    const int pmax = (1 << X265_DEPTH) - 1;
+    const int shift = 14 + 1 - X265_DEPTH, offset = (1 << (shift - 1)) + 2 * 8192;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+        {
+            if (op == 0)
+                ((int16_t*)D)[y * sd + x] = (int16_t)((int)((const pixel*)A)[y * sa + x] - (int)((const pixel*)B)[y * sb + x]);
+            else if (op == 1)
+                ((pixel*)D)[y * sd + x] = (pixel)clip3(0, pmax, (int)((const pixel*)A)[y * sa + x] + (int)((const int16_t*)B)[y * sb + x]);
+            else if (op == 2)
+                ((pixel*)D)[y * sd + x] = (pixel)(((int)((const pixel*)A)[y * sa + x] + (int)((const pixel*)B)[y * sb + x] + 1) >> 1);
+            else
+                ((pixel*)D)[y * sd + x] = (pixel)clip3(0, pmax, ((int)((const int16_t*)A)[y * sa + x] + (int)((const int16_t*)B)[y * sb + x] + offset) >> shift);
+        }
+}
+
+EXPORT void orc_blockop_batch(int op, int w, int h, const void* A, intptr_t sa, const int32_t* offA, const void* B, intptr_t sb,
+                              const int32_t* offB, void* D, intptr_t sd, const int32_t* offD, int n)
+{
+    const size_t ea = op == 3 ? 2 : sizeof(pixel), eb = (op == 1 || op == 3) ? 2 : sizeof(pixel), ed = op == 0 ? 2 : sizeof(pixel);
+    for (int i = 0; i < n; i++)
+        orc_blockop(op, w, h, (const char*)A + (size_t)offA[i] * ea, sa, (const char*)B + (size_t)offB[i] * eb, sb, (char*)D + (size_t)offD[i] * ed, sd);
+}
+
+/* frame_init_lowres_core (pixel.cpp:595-620): rounding-average cascade, "slower than naive bilinear, but matches asm" */
+static inline int avg2(int a, int b) { return (a + b + 1) >> 1; }
+EXPORT void orc_lowres(const pixel* src, intptr_t ss, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ds, int width, int height)
+{
+    for (int y = 0; y < height; y++)
+    {
+        const pixel* r0 = src + (intptr_t)(2 * y) * ss;
+        const pixel* r1 = r0 + ss;
+        const pixel* r2 = r1 + ss;
+        for (int x = 0; x < width; x++)
+        {
+            int c = 2 * x;
+            d0[y * ds + x] = (pixel)avg2(avg2(r0[c], r1[c]), avg2(r0[c + 1], r1[c + 1]));
+            dh[y * ds + x] = (pixel)avg2(avg2(r0[c + 1], r1[c + 1]), avg2(r0[c + 2], r1[c + 2]));
+            dv[y * ds + x] = (pixel)avg2(avg2(r1[c], r2[c]), avg2(r1[c + 1], r2[c + 1]));
+            dc[y * ds + x] = (pixel)avg2(avg2(r1[c + 1], r2[c + 1]), avg2(r1[c + 2], r2[c + 2]));
+        }
+    }
+}

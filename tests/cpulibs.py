@@ -135,6 +135,13 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- adjacent slots: sub_ps / add_ps / pixelavg_pp / addAvg (op 0..3) and the lowres downscale -------------
+    def blockop(self, op, w, h, A, oa, sa, B, ob, sb, D, od, sd):
+        return self._f("blockop")(op, w, h, _ptr(A, oa), C.c_ssize_t(sa), _ptr(B, ob), C.c_ssize_t(sb), _ptr(D, od), C.c_ssize_t(sd))
+
+    def lowres(self, src, os_, ss, d0, dh, dv, dc, ds, width, height):
+        self._f("lowres", None)(_ptr(src, os_), C.c_ssize_t(ss), _ptr(d0), _ptr(dh), _ptr(dv), _ptr(dc), C.c_ssize_t(ds), width, height)
+
     # ---- inter luma TU chain (sub_ps, dct, quant, dequant, DC shortcut / idct, add_ps, sse) ---------------
     def tu_chain(self, N, fenc, of, sf, pred, op_, sp, qc, qbits, add, dqscale, dqshift, recon, orr, sr):
         q = np.zeros(N * N, np.int16)
@@ -214,6 +221,11 @@ class Oracle(_Base):
                                         _ptr(qc), qbits, add, dqscale, dqshift, _ptr(q), _ptr(ns), _ptr(recon), C.c_ssize_t(sr),
                                         _ptr(offR), _ptr(z), _ptr(r))
         return q, ns, z, r
+
+    def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD):
+        self._f("blockop_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(offA), _ptr(B), C.c_ssize_t(sb), _ptr(offB),
+                                       _ptr(D), C.c_ssize_t(sd), _ptr(offD), len(offA))
+        return D
 
     def idct_batch(self, N, src, dst, stride, off, dst4=0):
         n = len(off)

@@ -246,3 +246,54 @@ def test_tu_chain_batch(depth):
         seen |= {"full"} if (rns > 1).any() else set()
     assert seen == {"zero", "dc", "full"}, seen
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_blockop_and_lowres_batches(depth):
+    """adjacent slots: sub_ps / add_ps / pixelavg_pp / addAvg over descriptor batches (luma and odd chroma
+    shapes, misaligned offsets, odd strides) and the whole-plane lowres downscale, element-wise vs the oracle"""
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(100 + depth)
+    stride, rows, n = 200, 180, 61
+    N = stride * rows
+    pixA = rng.integers(0, orc.pmax + 1, N).astype(orc.pix); pixB = rng.integers(0, orc.pmax + 1, N).astype(orc.pix)
+    s16A = rng.integers(-32768, 32768, N).astype(np.int16); s16B = rng.integers(-32768, 32768, N).astype(np.int16)
+    shapes = [(64, 64), (32, 8), (16, 16), (8, 8), (4, 4), (12, 16), (6, 8), (2, 4), (2, 2), (24, 32), (8, 2)]
+    for op, A, B, dt in ((0, pixA, pixB, np.int16), (1, pixA, s16B, orc.pix), (2, pixA, pixB, orc.pix), (3, s16A, s16B, orc.pix)):
+        for (w, h) in shapes:
+            for sa, sb, sd in ((stride, stride, stride), (stride - 3, stride, stride - 1)):
+                offA = (rng.integers(0, rows - h - 2, n) * sa + rng.integers(0, sa - w, n)).astype(np.int32)
+                offB = (rng.integers(0, rows - h - 2, n) * sb + rng.integers(0, sb - w, n)).astype(np.int32)
+                # destination blocks must not overlap: one block per 64 x 64 cell of a destination plane of its own
+                per_row = sd // 64
+                ND = sd * 64 * ((n + per_row - 1) // per_row) + 64
+                cells = rng.permutation(n)
+                offD = ((cells // per_row) * 64 * sd + (cells % per_row) * 64 + rng.integers(0, min(3, 64 - w + 1), n)).astype(np.int32)
+                ref = orc.blockop_batch(op, w, h, A, sa, offA, B, sb, offB, np.full(ND, 7, dt), sd, offD)
+                dA = dev(A.view(np.int16) if A.dtype == np.uint16 else A); dB = dev(B.view(np.int16) if B.dtype == np.uint16 else B)
+                dD = dev(np.full(ND, 7, dt).view(np.int16) if np.dtype(dt) == np.uint16 else np.full(ND, 7, dt))
+                ctx.blockop_batch(op, w, h, dA, sa, dev(offA), dB, sb, dev(offB), dD, sd, dev(offD), n)
+                got = dD.cpu().numpy()
+                got = got.view(np.uint16) if np.dtype(dt) == np.uint16 else got
+                assert np.array_equal(got, ref), (op, w, h, sa)
+    # contiguous blocks (NULL offset arrays)
+    w = h = 8
+    ref = np.zeros(n * 64, np.int16)
+    orc.blockop_batch(0, w, h, pixA, w, (np.arange(n) * 64).astype(np.int32), pixB, w, (np.arange(n) * 64).astype(np.int32), ref, w,
+                      (np.arange(n) * 64).astype(np.int32))
+    dD = torch.zeros(n * 64, dtype=torch.int16, device="cuda")
+    ctx.blockop_batch(0, w, h, dev(pix_view(pixA, depth)), w, None, dev(pix_view(pixB, depth)), w, None, dD, w, None, n)
+    assert np.array_equal(dD.cpu().numpy(), ref)
+    # lowres of a 352x288-like plane with odd dimensions
+    lw, lh, ds = 87, 71, 96
+    outs = [np.full(ds * lh, 3, orc.pix) for _ in range(4)]
+    orc.lowres(pixA, 5, stride, *outs, ds, lw, lh)
+    douts = [dev(pix_view(np.full(ds * lh, 3, orc.pix), depth)) for _ in range(4)]
+    src = dev(pix_view(pixA, depth))
+    ctx.lowres_batch(src[5:], stride, *douts, ds, lw, lh)
+    for a, b in zip(outs, douts):
+        g = b.cpu().numpy()
+        assert np.array_equal(g.view(np.uint16) if depth > 8 else g, a)
+    ctx.check()

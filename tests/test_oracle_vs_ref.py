@@ -298,3 +298,31 @@ def test_tu_chain(libs):
         b = r.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r1, 7, stride)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (N, qp, trial)
         assert np.array_equal(r0, r1), (N, qp, trial)
+
+
+def test_adjacent_slots(libs):
+    """sub_ps / add_ps / pixelavg_pp / addAvg through the reference's luma, 4:2:0 and 4:2:2 slots, and frameInitLowres"""
+    o, r = libs
+    rng = np.random.default_rng(21)
+    D = o.depth
+    stride, rows = 100, 140
+    n = stride * rows
+    pixA = rng.integers(0, o.pmax + 1, n).astype(o.pix); pixB = rng.integers(0, o.pmax + 1, n).astype(o.pix)
+    # add_ps residuals up to the full int16 range so the clip is exercised; addAvg inputs like ps-filter outputs and extremes
+    s16A = rng.integers(-32768, 32768, n).astype(np.int16); s16B = rng.integers(-32768, 32768, n).astype(np.int16)
+    cu_shapes = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (2, 2), (2, 4), (4, 8), (8, 16), (16, 32), (32, 64)]
+    pu_shapes = list(LUMA_PU) + list(CHROMA_ONLY_420) + list(CHROMA_ONLY_422)
+    for op, shapes, A, B, dt in ((0, cu_shapes, pixA, pixB, np.int16), (1, cu_shapes, pixA, s16B, o.pix),
+                                 (2, LUMA_PU, pixA, pixB, o.pix), (3, pu_shapes, s16A, s16B, o.pix)):
+        for (w, h) in shapes:
+            for oa, ob, od, sa, sb, sd in ((0, 0, 0, stride, stride, stride), (7, 301, 5, 97, stride, 83)):
+                d0 = np.full(n, 5, dt); d1 = d0.copy()
+                assert r.blockop(op, w, h, A, oa, sa, B, ob, sb, d1, od, sd) == 0, (op, w, h)
+                o.blockop(op, w, h, A, oa, sa, B, ob, sb, d0, od, sd)
+                assert np.array_equal(d0, d1), (op, w, h)
+    for (lw, lh) in ((32, 32), (45, 17), (8, 60)):
+        outs = [[np.full(64 * 64, 9, o.pix) for _ in range(4)] for _ in range(2)]
+        o.lowres(pixA, 3, stride, *outs[0], 64, lw, lh)
+        r.lowres(pixA, 3, stride, *outs[1], 64, lw, lh)
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b), (lw, lh)

@@ -130,6 +130,23 @@ def main():
         ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
                                                qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
         add("tu_chain %dx%d (two fused tensor-core kernels)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
+    # ---- adjacent slots: residual add / bi-prediction averages over a 32x32 tiling, and the lowres downscale
+    oa, ob = desc(32, 32)
+    n = oa.numel()
+    s16 = torch.randint(-2000, 2000, (F * pe,), dtype=torch.int16, device="cuda")
+    outP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); outS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
+    for op, nm, a_, b_, d_, nb_ in ((0, "sub_ps", A, B, outS, 2 * b + 2), (1, "add_ps", A, s16, outP, 2 * b + 2),
+                                   (2, "pixelavg_pp", A, B, outP, 3 * b), (3, "addAvg", s16, s16, outP, 4 + b)):
+        ms = timeit(lambda: ctx.blockop_batch(op, 32, 32, a_, geo.stride, oa, b_, geo.stride, ob, d_, geo.stride, oa, n))
+        add("%s 32x32 (adjacent slot)" % nm, ms, S * nb_, S)
+    lw, lh = cw // 2, ch // 2
+    low = [torch.empty(F * lw * lh, dtype=A.dtype, device="cuda") for _ in range(4)]
+
+    def lowres_all():
+        for f in range(F):
+            ctx.lowres_batch(A[f * pe + geo.origin:], geo.stride, *[t[f * lw * lh:] for t in low], lw, lw, lh)
+    ms = timeit(lowres_all, reps=4, warm=1, burst=2)
+    add("frameInitLowres (one launch per frame, %d launches)" % F, ms, S * 2 * b, S)
     # ---- interpolation, frame-tiled 64x64 and 16x16 luma, 8x8 chroma-size blocks
     dstP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); dstS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
     srcS = torch.randint(-8192, 8192, (F * pe,), dtype=torch.int16, device="cuda")

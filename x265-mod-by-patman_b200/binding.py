@@ -45,7 +45,8 @@ def load_library():
         for name in ("x265b200_quant", "x265b200_nquant"):
             getattr(_lib, name).restype = C.c_uint32
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
-                     "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp"):
+                     "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
+                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -136,6 +137,13 @@ class Context:
     def idct_batch(self, kind, N, src, dst, stride, off, stream=0, count=None):
         n = int(off.numel()) if off is not None else int(count)
         self._call("x265b200_idct_batch", kind, N, _dp(src), n, _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))
+
+    def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD, n, stream=0):
+        self._call("x265b200_blockop_batch", op, w, h, _dp(A), _ss(sa), _dp(offA), _dp(B), _ss(sb), _dp(offB), _dp(D), _ss(sd), _dp(offD),
+                   int(n), C.c_void_p(stream))
+
+    def lowres_batch(self, src, ss, d0, dh, dv, dc, ds, width, height, stream=0):
+        self._call("x265b200_lowres_batch", _dp(src), _ss(ss), _dp(d0), _dp(dh), _dp(dv), _dp(dc), _ss(ds), width, height, C.c_void_p(stream))
 
     def quant_batch(self, coef, qc, deltaU, qCoef, qBits, add, numCoeff, n, numSig, stream=0):
         self._call("x265b200_quant_batch", _dp(coef), _dp(qc), _dp(deltaU), _dp(qCoef), qBits, add, numCoeff, n,

@@ -427,3 +427,56 @@ extern "C" void x265b200_interp(x265b200_ctx* ctx, int kind, int taps, int w, in
     if (!c.download(oD, (size_t)w * outRows * db)) return;
     unpack(dst, c.h<void>(oD), outRows, w * db, dstStride * db);
 }
+
+// ------------------------------------------------------------------ host entries: adjacent slots (blockops.cu)
+
+static void host_blockop(x265b200_ctx* ctx, int op, int w, int h, const void* a, intptr_t sa, size_t ab, const void* b, intptr_t sb, size_t bb,
+                         void* d, intptr_t sd, size_t db)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t oA = c.alloc((size_t)w * h * ab), oB = c.alloc((size_t)w * h * bb);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc((size_t)w * h * db);
+    if (!c.ok()) return;
+    pack(c.h<void>(oA), a, h, w * ab, sa * (intptr_t)ab);
+    pack(c.h<void>(oB), b, h, w * bb, sb * (intptr_t)bb);
+    if (!c.upload(0, inEnd)) return;
+    if (x265b200_blockop_batch(ctx, op, w, h, c.d<void>(oA), w, nullptr, c.d<void>(oB), w, nullptr, c.d<void>(oD), w, nullptr, 1, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)w * h * db)) return;
+    unpack(d, c.h<void>(oD), h, w * db, sd * (intptr_t)db);
+}
+
+extern "C" void x265b200_sub_ps(x265b200_ctx* ctx, int w, int h, int16_t* dst, intptr_t dstride, const void* src0, const void* src1, intptr_t sstride0, intptr_t sstride1)
+{ if (ctx) host_blockop(ctx, X265B200_BOP_SUB_PS, w, h, src0, sstride0, ctx->pixbytes, src1, sstride1, ctx->pixbytes, dst, dstride, 2); }
+extern "C" void x265b200_add_ps(x265b200_ctx* ctx, int w, int h, void* dst, intptr_t dstride, const void* src0, const int16_t* src1, intptr_t sstride0, intptr_t sstride1)
+{ if (ctx) host_blockop(ctx, X265B200_BOP_ADD_PS, w, h, src0, sstride0, ctx->pixbytes, src1, sstride1, 2, dst, dstride, ctx->pixbytes); }
+extern "C" void x265b200_pixelavg_pp(x265b200_ctx* ctx, int w, int h, void* dst, intptr_t dstride, const void* src0, intptr_t sstride0, const void* src1, intptr_t sstride1, int)
+{ if (ctx) host_blockop(ctx, X265B200_BOP_PIXELAVG, w, h, src0, sstride0, ctx->pixbytes, src1, sstride1, ctx->pixbytes, dst, dstride, ctx->pixbytes); }
+extern "C" void x265b200_addAvg(x265b200_ctx* ctx, int w, int h, const int16_t* src0, const int16_t* src1, void* dst, intptr_t src0Stride, intptr_t src1Stride, intptr_t dstStride)
+{ if (ctx) host_blockop(ctx, X265B200_BOP_ADDAVG, w, h, src0, src0Stride, 2, src1, src1Stride, 2, dst, dstStride, ctx->pixbytes); }
+
+extern "C" void x265b200_frame_init_lowres(x265b200_ctx* ctx, const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
+                                           intptr_t srcStride, intptr_t dstStride, int width, int height)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const size_t pb = ctx->pixbytes;
+    // the reference reads 2 * width + 1 columns of 2 * height + 1 rows (pixel.cpp:600-612)
+    const int pw = 2 * width + 1, ph = 2 * height + 1;
+    size_t oS = c.alloc((size_t)pw * ph * pb);
+    size_t inEnd = c.used;
+    size_t plane = (size_t)width * height * pb;
+    size_t oD = c.alloc(4 * plane);
+    if (!c.ok()) return;
+    pack(c.h<void>(oS), src0, ph, pw * pb, srcStride * (intptr_t)pb);
+    if (!c.upload(0, inEnd)) return;
+    uint8_t* dd = c.d<uint8_t>(oD);
+    if (x265b200_lowres_batch(ctx, c.d<void>(oS), pw, dd, dd + plane, dd + 2 * plane, dd + 3 * plane, width, width, height, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, 4 * plane)) return;
+    uint8_t* hd = c.h<uint8_t>(oD);
+    unpack(dst0, hd, height, width * pb, dstStride * (intptr_t)pb);
+    unpack(dsth, hd + plane, height, width * pb, dstStride * (intptr_t)pb);
+    unpack(dstv, hd + 2 * plane, height, width * pb, dstStride * (intptr_t)pb);
+    unpack(dstc, hd + 3 * plane, height, width * pb, dstStride * (intptr_t)pb);
+}

@@ -58,8 +58,17 @@ template<int T, int W, int H> void t_vss(const int16_t* s, intptr_t ss, int16_t*
 template<int W, int H> void t_hvpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int ix, int iy) { x265b200_interp(g_b200, X265B200_IP_HVPP, 8, W, H, s, ss, d, ds, ix, iy); }
 template<int W, int H> void t_p2s(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds) { x265b200_interp(g_b200, X265B200_IP_P2S, 8, W, H, s, ss, d, ds, 0, 0); }
 
+// ---- adjacent slots: same chains, not named by the north star
+template<int W, int H> void t_sub_ps(int16_t* d, intptr_t ds, const pixel* a, const pixel* b, intptr_t sa, intptr_t sb) { x265b200_sub_ps(g_b200, W, H, d, ds, a, b, sa, sb); }
+template<int W, int H> void t_add_ps(pixel* d, intptr_t ds, const pixel* a, const int16_t* b, intptr_t sa, intptr_t sb) { x265b200_add_ps(g_b200, W, H, d, ds, a, b, sa, sb); }
+template<int W, int H> void t_pixelavg(pixel* d, intptr_t ds, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb, int wt) { x265b200_pixelavg_pp(g_b200, W, H, d, ds, a, sa, b, sb, wt); }
+template<int W, int H> void t_addAvg(const int16_t* a, const int16_t* b, pixel* d, intptr_t sa, intptr_t sb, intptr_t ds) { x265b200_addAvg(g_b200, W, H, a, b, d, sa, sb, ds); }
+void t_lowres(const pixel* s, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ss, intptr_t ds, int w, int h) { x265b200_frame_init_lowres(g_b200, s, d0, dh, dv, dc, ss, ds, w, h); }
+
 template<int W, int H> void lumaPU(EncoderPrimitives::PU& pu)
 {
+    pu.pixelavg_pp[NONALIGNED] = t_pixelavg<W, H>; pu.pixelavg_pp[ALIGNED] = t_pixelavg<W, H>;
+    pu.addAvg[NONALIGNED] = t_addAvg<W, H>; pu.addAvg[ALIGNED] = t_addAvg<W, H>;
     pu.sad = t_sad<W, H>; pu.sad_x3 = t_sad_x3<W, H>; pu.sad_x4 = t_sad_x4<W, H>; pu.ads = t_ads<W, H>; pu.satd = t_satd<W, H>;
     pu.luma_hpp = t_hpp<8, W, H>; pu.luma_hps = t_hps<8, W, H>; pu.luma_vpp = t_vpp<8, W, H>; pu.luma_vps = t_vps<8, W, H>;
     pu.luma_vsp = t_vsp<8, W, H>; pu.luma_vss = t_vss<8, W, H>; pu.luma_hvpp = t_hvpp<W, H>;
@@ -72,6 +81,7 @@ template<int W, int H> void chromaPU(EncoderPrimitives::Chroma::PUChroma& pu)
     pu.filter_hpp = t_hpp<4, W, H>; pu.filter_hps = t_hps<4, W, H>; pu.filter_vpp = t_vpp<4, W, H>; pu.filter_vps = t_vps<4, W, H>;
     pu.filter_vsp = t_vsp<4, W, H>; pu.filter_vss = t_vss<4, W, H>;
     pu.p2s[NONALIGNED] = t_p2s<W, H>; pu.p2s[ALIGNED] = t_p2s<W, H>;
+    pu.addAvg[NONALIGNED] = t_addAvg<W, H>; pu.addAvg[ALIGNED] = t_addAvg<W, H>;
     pu.satd = (W % 4 == 0 && H % 4 == 0) ? (pixelcmp_t)t_satd<(W % 4 ? 4 : W), (H % 4 ? 4 : H)> : NULL;
 }
 
@@ -79,10 +89,12 @@ template<int W> void lumaCU(EncoderPrimitives::CU& cu)
 {
     cu.sse_pp = t_sse_pp<W, W>; cu.sse_ss = t_sse_ss<W, W>; cu.sa8d = t_sa8d<W, W>;
     cu.ssd_s[NONALIGNED] = t_ssd_s<W>; cu.ssd_s[ALIGNED] = t_ssd_s<W>;
+    cu.sub_ps = t_sub_ps<W, W>; cu.add_ps[NONALIGNED] = t_add_ps<W, W>; cu.add_ps[ALIGNED] = t_add_ps<W, W>;
 }
 template<int W, int H> void chromaCU(EncoderPrimitives::Chroma::CUChroma& cu)
 {
     cu.sa8d = t_sa8d<W, H>; cu.sse_pp = t_sse_pp<W, H>;
+    cu.sub_ps = t_sub_ps<W, H>; cu.add_ps[NONALIGNED] = t_add_ps<W, H>; cu.add_ps[ALIGNED] = t_add_ps<W, H>;
 }
 
 } // anonymous namespace
@@ -120,6 +132,14 @@ void setupB200Primitives(EncoderPrimitives& p)
     chromaCU<4, 8>(p.chroma[X265_CSP_I422].cu[BLOCK_8x8]);   chromaCU<8, 16>(p.chroma[X265_CSP_I422].cu[BLOCK_16x16]);
     chromaCU<16, 32>(p.chroma[X265_CSP_I422].cu[BLOCK_32x32]); chromaCU<32, 64>(p.chroma[X265_CSP_I422].cu[BLOCK_64x64]);
 
+    // 4:2:0 chroma of the 4x4 luma PU: no filters (ipfilter.cpp:414-462) but a bi-prediction average (pixel.cpp:1191)
+    p.chroma[X265_CSP_I420].pu[LUMA_4x4].addAvg[NONALIGNED] = t_addAvg<2, 2>; p.chroma[X265_CSP_I420].pu[LUMA_4x4].addAvg[ALIGNED] = t_addAvg<2, 2>;
+    // chroma of the 4x4 luma CU: only the residual slots exist (pixel.cpp:1254, 1333)
+    p.chroma[X265_CSP_I420].cu[BLOCK_4x4].sub_ps = t_sub_ps<2, 2>;
+    p.chroma[X265_CSP_I420].cu[BLOCK_4x4].add_ps[NONALIGNED] = t_add_ps<2, 2>; p.chroma[X265_CSP_I420].cu[BLOCK_4x4].add_ps[ALIGNED] = t_add_ps<2, 2>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_4x4].sub_ps = t_sub_ps<2, 4>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_4x4].add_ps[NONALIGNED] = t_add_ps<2, 4>; p.chroma[X265_CSP_I422].cu[BLOCK_4x4].add_ps[ALIGNED] = t_add_ps<2, 4>;
+
     p.cu[BLOCK_4x4].dct = t_dct<4>;     p.cu[BLOCK_4x4].idct = t_idct<4>;
     p.cu[BLOCK_8x8].dct = t_dct<8>;     p.cu[BLOCK_8x8].idct = t_idct<8>;
     p.cu[BLOCK_16x16].dct = t_dct<16>;  p.cu[BLOCK_16x16].idct = t_idct<16>;
@@ -130,6 +150,7 @@ void setupB200Primitives(EncoderPrimitives& p)
     p.dst4x4 = t_dst4;  p.idst4x4 = t_idst4;
     p.quant = t_quant;  p.nquant = t_nquant;
     p.dequant_normal = t_dequant_normal;  p.dequant_scaling = t_dequant_scaling;
+    p.frameInitLowres = t_lowres;
 }
 
 } // namespace X265_NS
