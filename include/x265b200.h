@@ -179,6 +179,16 @@ int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t
                             int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
                             uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream);
 
+/* Sub-pel candidate cost, interpolation fused with the metric (reference encoder/motion.cpp:1780-1821,
+ * MotionEstimate::subpelCompare, luma part): for candidate i of block i / K (n blocks, K candidates each),
+ *   cost[i] = cmp(fenc + offF[i / K], strideF, interp(ref + offR[i], xFrac, yFrac), w)
+ * where interp is a copy / luma_hpp / luma_vpp / luma_hvpp exactly as subpelCompare selects them; frac[i] = xFrac | yFrac << 4
+ * (0..3 each) and offR[i] already contains the integer part (qmv >> 2) of the candidate.  op = X265B200_SAD or X265B200_SATD.
+ * The interpolated block stays on chip. */
+int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                              const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
+                              x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

@@ -371,4 +371,20 @@ int ref_blockop(int op, int w, int h, const void* A, intptr_t sa, const void* B,
 void ref_lowres(const pixel* src, intptr_t ss, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ds, int width, int height)
 { ensure(); g_c.frameInitLowres(src, d0, dh, dv, dc, ss, ds, width, height); }
 
+
+/* subpelCompare's slot sequence (encoder/motion.cpp:1795-1811) through the reference table */
+int ref_subpel_cmp(int op, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr, int xFrac, int yFrac)
+{
+    ensure();
+    int part = lumaPart(w, h);
+    if (part < 0) return -1;
+    pixelcmp_t cmp = op ? g_c.pu[part].satd : g_c.pu[part].sad;
+    if (!(yFrac | xFrac)) return cmp(fenc, sf, fref, sr);
+    ALIGN_VAR_32(pixel, subpelbuf[64 * 64]);
+    if (!yFrac) g_c.pu[part].luma_hpp(fref, sr, subpelbuf, w, xFrac);
+    else if (!xFrac) g_c.pu[part].luma_vpp(fref, sr, subpelbuf, w, yFrac);
+    else g_c.pu[part].luma_hvpp(fref, sr, subpelbuf, w, xFrac, yFrac);
+    return cmp(fenc, sf, subpelbuf, w);
+}
+
 } // extern "C"

@@ -748,3 +748,25 @@ EXPORT void orc_lowres(const pixel* src, intptr_t ss, pixel* d0, pixel* dh, pixe
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Sub-pel candidate cost: MotionEstimate::subpelCompare, luma part (encoder/motion.cpp:1780-1821):
+ * copy / luma_hpp / luma_vpp / luma_hvpp into a width-stride buffer, then sad (op 0) or satd (op 1) against fenc.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT int orc_subpel_cmp(int op, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr, int xFrac, int yFrac)
+{
+    if (!(xFrac | yFrac))
+        return op ? orc_satd(w, h, fenc, sf, fref, sr) : orc_sad(w, h, fenc, sf, fref, sr);
+    pixel buf[64 * 64];
+    if (!yFrac) orc_interp_hpp(8, w, h, fref, sr, buf, w, xFrac);
+    else if (!xFrac) orc_interp_vpp(8, w, h, fref, sr, buf, w, yFrac);
+    else orc_interp_hvpp(8, w, h, fref, sr, buf, w, xFrac, yFrac);
+    return op ? orc_satd(w, h, fenc, sf, buf, w) : orc_sad(w, h, fenc, sf, buf, w);
+}
+
+EXPORT void orc_subpel_cmp_batch(int op, int w, int h, const pixel* fenc, intptr_t sf, const pixel* ref, intptr_t sr,
+                                 const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost)
+{
+    for (int i = 0; i < n * K; i++)
+        cost[i] = orc_subpel_cmp(op, w, h, fenc + offF[i / K], sf, ref + offR[i], sr, frac[i] & 3, (frac[i] >> 4) & 3);
+}

@@ -135,6 +135,10 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- sub-pel candidate cost (subpelCompare): interpolation + sad (op 0) / satd (op 1) ----------------------
+    def subpel_cmp(self, op, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
+        return self._f("subpel_cmp")(op, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
+
     # ---- adjacent slots: sub_ps / add_ps / pixelavg_pp / addAvg (op 0..3) and the lowres downscale -------------
     def blockop(self, op, w, h, A, oa, sa, B, ob, sb, D, od, sd):
         return self._f("blockop")(op, w, h, _ptr(A, oa), C.c_ssize_t(sa), _ptr(B, ob), C.c_ssize_t(sb), _ptr(D, od), C.c_ssize_t(sd))
@@ -221,6 +225,12 @@ class Oracle(_Base):
                                         _ptr(qc), qbits, add, dqscale, dqshift, _ptr(q), _ptr(ns), _ptr(recon), C.c_ssize_t(sr),
                                         _ptr(offR), _ptr(z), _ptr(r))
         return q, ns, z, r
+
+    def subpel_cmp_batch(self, op, w, h, fenc, sf, ref, sr, offF, offR, frac, K):
+        n = len(offF)
+        cost = np.zeros(n * K, np.int32)
+        self._f("subpel_cmp_batch", None)(op, w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(ref), C.c_ssize_t(sr), _ptr(offF), _ptr(offR), _ptr(frac), K, n, _ptr(cost))
+        return cost
 
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD):
         self._f("blockop_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(offA), _ptr(B), C.c_ssize_t(sb), _ptr(offB),

@@ -297,3 +297,33 @@ def test_blockop_and_lowres_batches(depth):
         g = b.cpu().numpy()
         assert np.array_equal(g.view(np.uint16) if depth > 8 else g, a)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_subpel_cmp_batch(depth):
+    """fused interpolation + SAD / SATD (subpelCompare) vs the oracle: every luma PU shape, all 16 fractions, K candidates
+    per block sharing one fenc block, candidate origins at arbitrary (misaligned) integer positions"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    F = make_plane(geo, depth, 51, "natural"); R = make_plane(geo, depth, 52, "natural")
+    Ru = make_plane(geo, depth, 53, "uniform")
+    rng = np.random.default_rng(200 + depth)
+    cw, ch = geo.coded()
+    dF = dev(pix_view(F, depth))
+    for (w, h) in LUMA_PU:
+        n, K = 37, 4
+        x = rng.integers(0, cw - w, n); y = rng.integers(0, ch - h, n)
+        offF = (geo.origin + y * geo.stride + x).astype(np.int32)
+        mvx = rng.integers(-40, 41, n * K); mvy = rng.integers(-40, 41, n * K)
+        offR = (geo.origin + (np.repeat(y, K) + mvy) * geo.stride + np.repeat(x, K) + mvx).astype(np.int32)
+        frac = (rng.integers(0, 4, n * K) | (rng.integers(0, 4, n * K) << 4)).astype(np.int32)
+        frac[:8] = [0, 1, 2, 3, 0x10, 0x20, 0x30, 0x33]
+        for op, ref_plane in ((0, R), (1, R), (1, Ru)):
+            want = orc.subpel_cmp_batch(op, w, h, F, geo.stride, ref_plane, geo.stride, offF, offR, frac, K)
+            cost = torch.zeros(n * K, dtype=torch.int32, device="cuda")
+            ctx.subpel_cmp_batch(op, w, h, dF, geo.stride, dev(pix_view(ref_plane, depth)), geo.stride, dev(offF), dev(offR), dev(frac), K, cost)
+            assert np.array_equal(cost.cpu().numpy(), want), (w, h, op)
+    ctx.check()

@@ -326,3 +326,18 @@ def test_adjacent_slots(libs):
         r.lowres(pixA, 3, stride, *outs[1], 64, lw, lh)
         for a, b in zip(*outs):
             assert np.array_equal(a, b), (lw, lh)
+
+
+def test_subpel_cmp(libs):
+    """sub-pel candidate cost: oracle composition vs subpelCompare's slot sequence on the reference table"""
+    o, r = libs
+    rng = np.random.default_rng(31)
+    stride, rows = 160, 160
+    for fenc, ref in pixel_bufs(rng, o.depth, stride * rows):
+        for (w, h) in LUMA_PU:
+            for op in (0, 1):
+                xf, yf = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+                for (xF, yF) in ((xf, yf), (0, yf), (xf, 0), (0, 0)):
+                    a = o.subpel_cmp(op, w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, xF, yF)
+                    b = r.subpel_cmp(op, w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, xF, yF)
+                    assert a == b and a >= 0, (w, h, op, xF, yF)

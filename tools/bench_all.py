@@ -130,6 +130,17 @@ def main():
         ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
                                                qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
         add("tu_chain %dx%d (two fused tensor-core kernels)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
+    # ---- sub-pel candidate cost (interpolation fused with SATD): K = 4 quarter-pel candidates per block
+    for (w, h) in ((64, 64), (16, 16), (8, 8)):
+        oa, ob = desc(w, h)
+        n = oa.numel()
+        K = 4
+        offR = torch.stack([ob + k for k in range(K)], dim=1).reshape(-1).contiguous()
+        frac = (torch.randint(0, 4, (n * K,), dtype=torch.int32, device="cuda") | (torch.randint(0, 4, (n * K,), dtype=torch.int32, device="cuda") << 4))
+        cost = torch.empty(n * K, dtype=torch.int32, device="cuda")
+        ms = timeit(lambda: ctx.subpel_cmp_batch(1, w, h, A, geo.stride, B, geo.stride, oa, offR, frac, K, cost), reps=4, warm=2, burst=3)
+        add("subpel satd %dx%d (fused hv interp + satd, per candidate sample; window + fenc/K bytes)" % (w, h), ms,
+            S * K * b * ((w + 7) * (h + 7) / (w * h) + 1.0 / K) + n * K * 4, S * K)
     # ---- adjacent slots: residual add / bi-prediction averages over a 32x32 tiling, and the lowres downscale
     oa, ob = desc(32, 32)
     n = oa.numel()

@@ -138,6 +138,10 @@ class Context:
         n = int(off.numel()) if off is not None else int(count)
         self._call("x265b200_idct_batch", kind, N, _dp(src), n, _dp(dst), _ss(stride), _dp(off), C.c_void_p(stream))
 
+    def subpel_cmp_batch(self, op, w, h, fenc, sf, ref, sr, offF, offR, frac, K, cost, stream=0):
+        self._call("x265b200_subpel_cmp_batch", op, w, h, _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(frac), K,
+                   int(offF.numel()), _dp(cost), C.c_void_p(stream))
+
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD, n, stream=0):
         self._call("x265b200_blockop_batch", op, w, h, _dp(A), _ss(sa), _dp(offA), _dp(B), _ss(sb), _dp(offB), _dp(D), _ss(sd), _dp(offD),
                    int(n), C.c_void_p(stream))

@@ -7,6 +7,7 @@
 // out of it inside one CTA (the reference does the same through a stack buffer, ipfilter.cpp:362-369).
 #include "internal.h"
 #include "device_util.cuh"
+#include "tile_kernels.cuh"
 
 namespace b200 {
 
@@ -391,6 +392,116 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
     }
 }
 
+// Sub-pel candidate cost = interpolation fused with the block metric (reference encoder/motion.cpp:1780-1821,
+// MotionEstimate::subpelCompare: luma_hpp / luma_vpp / luma_hvpp into a stack buffer, then sad or satd against the cached
+// fenc block).  One lane group per candidate, same two passes as hv_tile_kernel, but the vertical pass leaves its 4 x TH2
+// output tile in registers as packed sample pairs and feeds it straight into tile4_accumulate() with the matching fenc
+// tile: the interpolated block never exists in memory.  A zero fraction runs through the identity taps {0,0,0,64,0,0,0,0}:
+// for pixel inputs hps(0) == p2s and the two-pass result equals luma_vpp / luma_hpp / a plain copy bit for bit (the
+// rounding offsets cancel), so one code path serves all sixteen (xFrac, yFrac) pairs.
+template<typename PIX, int OP, int TW1, int TH2>
+__global__ void __launch_bounds__(128)
+subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restrict__ ref, intptr_t ss,
+                  const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ frac,
+                  int K, int n, int w, int h, int G, int shift1, int offset1, int shift2, int offset2, int maxVal, int32_t* __restrict__ cost)
+{
+    constexpr int TAPS = 8;
+    extern __shared__ __align__(16) int16_t immed_all[];
+    int lg = __ffs(G) - 1;
+    int grp = threadIdx.x >> lg, l = threadIdx.x & (G - 1);
+    int cand = blockIdx.x * (128 >> lg) + grp;
+    bool live = cand < n;
+    int rows = h + TAPS - 1;
+    int16_t* immed = immed_all + (size_t)grp * w * rows;
+    constexpr int NQ = (TW1 + TAPS - 1 + 3) / 4;
+    uint32_t tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+    if (live)
+    {
+        int ci = frac[cand];
+        int idxX = ci & 3, idxY = (ci >> 4) & 3;
+        tx0 = c_lumaTapsB[idxX][0]; tx1 = c_lumaTapsB[idxX][1];
+        ty0 = c_lumaTapsB[idxY][0]; ty1 = c_lumaTapsB[idxY][1];
+        const PIX* s = ref + offR[cand] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
+        int tw = w / TW1;
+        int tiles1 = tw * ((rows + 3) >> 2);
+        for (int t = l; t < tiles1; t += G)
+        {
+            int tx = (t % tw) * TW1, ty = (t / tw) << 2;
+            uint32_t wv[4][2 * NQ + 1];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                if (ty + r >= rows) break;
+                uint32_t ws[2 * NQ];
+#pragma unroll
+                for (int i = 0; i < 2 * NQ; i++) ws[i] = __funnelshift_r(wv[r][i], wv[r][i + 1], 16);
+#pragma unroll
+                for (int o4 = 0; o4 < TW1; o4 += 4)
+                {
+                    int v[4];
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                    {
+                        int i = (o4 + o) >> 1;
+                        int sum = ((o4 + o) & 1) ? fir_pairs<PIX, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], tx0, tx1, offset1)
+                                                 : fir_pairs<PIX, TAPS>(wv[r][i], wv[r][i + 1], wv[r][(i + 2) % (2 * NQ + 1)], wv[r][(i + 3) % (2 * NQ + 1)], tx0, tx1, offset1);
+                        v[o] = sum >> shift1;
+                    }
+                    *(uint2*)(immed + (ty + r) * w + tx + o4) = make_uint2(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x5410),
+                                                                           __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x5410));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    int acc = 0;
+    if (live)
+    {
+        const PIX* f = fenc + offF[K > 1 ? cand / K : cand];
+        int tw = w >> 2;
+        int tiles2 = tw * (h / TH2);
+        const uint32_t mx = (uint32_t)maxVal * 0x10001u;
+        for (int t = l; t < tiles2; t += G)
+        {
+            int tx = (t % tw) << 2, ty = (t / tw) * TH2;
+            constexpr int NR = TH2 + TAPS - 1;
+            uint2 q[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) q[r] = *(const uint2*)(immed + (ty + r) * w + tx);
+            uint32_t pr[NR - 1][4];
+#pragma unroll
+            for (int r = 0; r < NR - 1; r++)
+            {
+                pr[r][0] = __byte_perm(q[r].x, q[r + 1].x, 0x5410); pr[r][1] = __byte_perm(q[r].x, q[r + 1].x, 0x7632);
+                pr[r][2] = __byte_perm(q[r].y, q[r + 1].y, 0x5410); pr[r][3] = __byte_perm(q[r].y, q[r + 1].y, 0x7632);
+            }
+#pragma unroll
+            for (int r4 = 0; r4 < TH2; r4 += 4)
+            {
+                uint32_t blo[4], bhi[4], alo[4], ahi[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++)
+                {
+                    int r = r4 + rr;
+                    int v[4];
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                        v[o] = fir_pairs<int16_t, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], ty0, ty1, offset2) >> shift2;
+                    blo[rr] = pack_clip2(v[0], v[1], mx);
+                    bhi[rr] = pack_clip2(v[2], v[3], mx);
+                }
+                load_tile4x4(f + (intptr_t)(ty + r4) * sf + tx, sf, alo, ahi);
+                tile4_accumulate<OP, int>(alo, ahi, blo, bhi, acc);
+            }
+        }
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) cost[cand] = acc;
+}
+
 // p2s, 4 samples per thread
 template<typename PIX>
 __global__ void __launch_bounds__(256)
@@ -567,4 +678,36 @@ extern "C" int x265b200_interp_batch(x265b200_ctx* ctx, int kind, int taps, int 
                          : launch_interp<uint8_t, 4>(ctx, kind, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, n, st);
     return taps == 8 ? launch_interp<uint16_t, 8>(ctx, kind, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, n, st)
                      : launch_interp<uint16_t, 4>(ctx, kind, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, n, st);
+}
+
+extern "C" int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h, const void* fenc, intptr_t sf, const void* ref, intptr_t sr,
+                                         const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
+                                         x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || h < 4 || (w & 3) || (h & 3) || w > 64 || h > 64 || n < 0 || K < 1 || (op != X265B200_SAD && op != X265B200_SATD))
+        return fail(ctx, X265B200_ERR_ARG, "subpel_cmp: bad shape / op");
+    if ((sf | sr) & 3) return fail(ctx, X265B200_ERR_ARG, "subpel_cmp: plane strides must be multiples of 4 samples");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int headRoom = 14 - ctx->depth, maxVal = (1 << ctx->depth) - 1;
+    const int shift1 = 6 - headRoom, shift2 = 6 + headRoom;
+    const int offset1 = (int)((unsigned)-8192 << shift1), offset2 = (1 << (shift2 - 1)) + (8192 << 6);
+    const size_t smem = (size_t)w * (h + 7) * sizeof(int16_t);
+    const bool wide = !(w & 7), tall = !(h & 7);
+    int tiles2 = (w >> 2) * (tall ? h >> 3 : h >> 2);
+    int G = 1;
+    while (G * 2 <= tiles2 / 2 && G < 32) G <<= 1;
+    int perCta = 128 / G;
+    long long cands = (long long)n * K;
+    if (cands > 0x7fffffff) return fail(ctx, X265B200_ERR_ARG, "subpel_cmp: too many candidates");
+#define SP(PIX, OP_, TW1_, TH2_) subpel_cmp_kernel<PIX, OP_, TW1_, TH2_><<<ceil_div(cands, perCta), 128, perCta * smem, st>>>(            \
+        (const PIX*)fenc, sf, (const PIX*)ref, sr, offF, offR, frac, K, (int)cands, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost)
+#define SP_SHAPE(PIX, OP_) do { if (wide && tall) SP(PIX, OP_, 8, 8); else if (wide) SP(PIX, OP_, 8, 4); else if (tall) SP(PIX, OP_, 4, 8); else SP(PIX, OP_, 4, 4); } while (0)
+    if (ctx->pixbytes == 1) { if (op == X265B200_SAD) SP_SHAPE(uint8_t, OP_SAD); else SP_SHAPE(uint8_t, OP_SATD); }
+    else { if (op == X265B200_SAD) SP_SHAPE(uint16_t, OP_SAD); else SP_SHAPE(uint16_t, OP_SATD); }
+#undef SP_SHAPE
+#undef SP
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
 }
