@@ -11,15 +11,34 @@ enum { OP_SAD = 0, OP_SATD = 1, OP_SA8D = 2, OP_SSE = 3, OP_SSD = 4 };
 constexpr int FAST_UNROLL = 1;
 constexpr int FAST_MINBLK = 1;
 
+// One 4x4 tile: a = fenc rows, b = reference rows, each row as packed 16-bit pairs (lo = samples 0,1; hi = samples 2,3).
+//   SAD : |a - b| per lane as max - min (VIMNMX.U16x2 twice; the lane-wise difference of max and min never borrows),
+//         lane sums stay packed for the tile (<= 4 * 4095) and are widened once with a dot product against (1, 1).
+//   SATD: differences by plain 32-bit subtraction (a borrow from the low lane is undone when the word is unpacked, and
+//         word-wise adds keep that representation exact), the vertical 4-point Hadamard and the horizontal stage that
+//         pairs the two words of a row on packed lanes (|value| <= 8 * 4095 < 2^15), and the last stage -- it pairs the
+//         two lanes of a word -- folded into the magnitude sum: |p + q| + |p - q| = 2 max(|p|, |q|), so the per-tile
+//         (sum >> 1) of the reference (pixel.cpp:236-241, raw sums are even) is the plain sum of the maxima.
 template<int OP, typename ACC>
 __device__ __forceinline__ void tile4_accumulate(const uint32_t (&alo)[4], const uint32_t (&ahi)[4],
                                                  const uint32_t (&blo)[4], const uint32_t (&bhi)[4], ACC& acc)
 {
-    uint32_t dl[4], dh[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) { dl[r] = alo[r] - blo[r]; dh[r] = ahi[r] - bhi[r]; }
-    if (OP == OP_SATD)
+    if constexpr (OP == OP_SAD)
     {
+        uint32_t s = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            s += __vmaxu2(alo[r], blo[r]) - __vminu2(alo[r], blo[r]);
+            s += __vmaxu2(ahi[r], bhi[r]) - __vminu2(ahi[r], bhi[r]);
+        }
+        acc += (ACC)((s & 0xffffu) + (s >> 16));
+    }
+    else if constexpr (OP == OP_SATD)
+    {
+        uint32_t dl[4], dh[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) { dl[r] = alo[r] - blo[r]; dh[r] = ahi[r] - bhi[r]; }
         // vertical Hadamard on packed columns (0,1) and (2,3)
         uint32_t s0 = dl[0] + dl[1], s1 = dl[0] - dl[1], s2 = dl[2] + dl[3], s3 = dl[2] - dl[3];
         dl[0] = s0 + s2; dl[1] = s1 + s3; dl[2] = s0 - s2; dl[3] = s1 - s3;
@@ -29,13 +48,12 @@ __device__ __forceinline__ void tile4_accumulate(const uint32_t (&alo)[4], const
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
-            int x0, x1, x2, x3;
-            unpack_s16x2(dl[r], x0, x1);
-            unpack_s16x2(dh[r], x2, x3);
-            int u0 = x0 + x1, u1 = x0 - x1, u2 = x2 + x3, u3 = x2 - x3;
-            sum += abs(u0 + u2) + abs(u1 + u3) + abs(u0 - u2) + abs(u1 - u3);
+            int p0, q0, p1, q1;
+            unpack_s16x2(dl[r] + dh[r], p0, q0);          // columns (0 + 2, 1 + 3)
+            unpack_s16x2(dl[r] - dh[r], p1, q1);          // columns (0 - 2, 1 - 3)
+            sum += max(abs(p0), abs(q0)) + max(abs(p1), abs(q1));
         }
-        acc += sum >> 1;       // per-tile halving == the reference's 8x4 pairing (raw tile sums are even)
+        acc += sum;
     }
     else
     {
@@ -43,10 +61,9 @@ __device__ __forceinline__ void tile4_accumulate(const uint32_t (&alo)[4], const
         for (int r = 0; r < 4; r++)
         {
             int x0, x1, x2, x3;
-            unpack_s16x2(dl[r], x0, x1);
-            unpack_s16x2(dh[r], x2, x3);
-            if (OP == OP_SAD) acc += abs(x0) + abs(x1) + abs(x2) + abs(x3);
-            else acc += (ACC)(x0 * x0 + x1 * x1) + (ACC)(x2 * x2 + x3 * x3);   // |x| <= 4095: no int overflow
+            unpack_s16x2(alo[r] - blo[r], x0, x1);
+            unpack_s16x2(ahi[r] - bhi[r], x2, x3);
+            acc += (ACC)(x0 * x0 + x1 * x1) + (ACC)(x2 * x2 + x3 * x3);   // |x| <= 4095: no int overflow
         }
     }
 }
