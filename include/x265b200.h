@@ -200,6 +200,18 @@ int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* 
 int x265b200_lowres_batch(x265b200_ctx* ctx, const void* src, intptr_t srcStride, void* dst0, void* dsth, void* dstv, void* dstc,
                           intptr_t dstStride, int width, int height, x265b200_stream stream);
 
+/* SEA integral planes, the input of `ads` (encoder/framefilter.cpp:38-140 driven by FrameFilter::computeMEIntegral,
+ * framefilter.cpp:737-835) for nframes padded pictures of `rows` x `stride` samples stored back to back.  Output: twelve
+ * uint32 planes per picture in the reference's order (32x32, 32x24, 32x8, 24x32, 16x16, 16x12, 16x4, 12x16, 8x32, 8x8, 4x16,
+ * 4x4), plane k of picture f at sums + (f * 12 + k) * planePitch, same stride as the picture:
+ *   sum[r][x] = sum of the W x H box with top-left sample (x, r)   for 1 <= r <= rows - 1 - H, x < stride - W,
+ * 0 elsewhere (the reference leaves prefix sums / uninitialised memory there; the search never reads them). */
+int x265b200_me_integral_batch(x265b200_ctx* ctx, const void* pix, intptr_t stride, int rows, int nframes,
+                               uint32_t* sums, size_t planePitch, x265b200_stream stream);
+/* one row of integral_init{4..32}h (vertical = 0: out[x] = hsum_size(pix, x) + a[x]) or ..v (vertical = 1: out[x] = b[x] - a[x]) */
+int x265b200_integral_row_batch(x265b200_ctx* ctx, int vertical, int size, const void* pix, const uint32_t* a, const uint32_t* b,
+                                uint32_t* out, int count, x265b200_stream stream);
+
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 
 int x265b200_sad(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
@@ -231,6 +243,9 @@ void x265b200_pixelavg_pp(x265b200_ctx*, int w, int h, void* dst, intptr_t dstri
 void x265b200_addAvg(x265b200_ctx*, int w, int h, const int16_t* src0, const int16_t* src1, void* dst, intptr_t src0Stride, intptr_t src1Stride, intptr_t dstStride);
 void x265b200_frame_init_lowres(x265b200_ctx*, const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
                                 intptr_t srcStride, intptr_t dstStride, int width, int height);
+/* integralh_t / integralv_t (primitives.h:227-228) with the box width / height prepended */
+void x265b200_integral_inith(x265b200_ctx*, int W, uint32_t* sum, const void* pix, intptr_t stride);
+void x265b200_integral_initv(x265b200_ctx*, int H, uint32_t* sum, intptr_t stride);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,6 @@
  * these is reachable from a hot-path slot. */
 namespace X265_NS {
 void setupSaoPrimitives_c(EncoderPrimitives&) {}
-void setupSeaIntegralPrimitives_c(EncoderPrimitives&) {}
 void setupMCSTFPrimitives_scalar(MCSTFPrimitives&) {}
 MCSTFPrimitives mcstfPrim;
 const uint32_t g_entropyBits[128] = { 0 };
@@ -385,6 +384,30 @@ int ref_subpel_cmp(int op, int w, int h, const pixel* fenc, intptr_t sf, const p
     else if (!xFrac) g_c.pu[part].luma_vpp(fref, sr, subpelbuf, w, yFrac);
     else g_c.pu[part].luma_hvpp(fref, sr, subpelbuf, w, xFrac, yFrac);
     return cmp(fenc, sf, subpelbuf, w);
+}
+
+
+/* ---- SEA integral primitives: the reference's own functions (framefilter.cpp via ref_framefilter.cpp) ---- */
+static int integralIdx(int size) { return size == 4 ? INTEGRAL_4 : size == 8 ? INTEGRAL_8 : size == 12 ? INTEGRAL_12 : size == 16 ? INTEGRAL_16 : size == 24 ? INTEGRAL_24 : size == 32 ? INTEGRAL_32 : -1; }
+int ref_integral_inith(int W, uint32_t* sum, pixel* pix, intptr_t stride)
+{ ensure(); int i = integralIdx(W); if (i < 0 || !g_c.integral_inith[i]) return -1; g_c.integral_inith[i](sum, pix, stride); return 0; }
+int ref_integral_initv(int H, uint32_t* sum, intptr_t stride)
+{ ensure(); int i = integralIdx(H); if (i < 0 || !g_c.integral_initv[i]) return -1; g_c.integral_initv[i](sum, stride); return 0; }
+/* the row loop of FrameFilter::computeMEIntegral (framefilter.cpp:770-832) over one padded picture, t = y + padY */
+int ref_me_integral(pixel* pix, intptr_t stride, int rows, uint32_t* sums, size_t planePitch)
+{
+    ensure();
+    static const int W[12] = { 32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4 }, H[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+    if (!g_c.integral_inith[INTEGRAL_4]) return -1;
+    for (int k = 0; k < 12; k++) memset(sums + k * planePitch, 0, stride * sizeof(uint32_t));
+    for (int t = 0; t < rows - 1; t++)
+        for (int k = 0; k < 12; k++)
+        {
+            uint32_t* S = sums + k * planePitch;
+            g_c.integral_inith[integralIdx(W[k])](S + (intptr_t)(t + 1) * stride, pix + (intptr_t)t * stride, stride);
+            if (t >= H[k]) g_c.integral_initv[integralIdx(H[k])](S + (intptr_t)(t + 1 - H[k]) * stride, stride);
+        }
+    return 0;
 }
 
 } // extern "C"

@@ -770,3 +770,36 @@ EXPORT void orc_subpel_cmp_batch(int op, int w, int h, const pixel* fenc, intptr
     for (int i = 0; i < n * K; i++)
         cost[i] = orc_subpel_cmp(op, w, h, fenc + offF[i / K], sf, ref + offR[i], sr, frac[i] & 3, (frac[i] >> 4) & 3);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SEA integral planes (encoder/framefilter.cpp:38-140; row loop of FrameFilter::computeMEIntegral, :737-835).
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void orc_integral_inith(int W, uint32_t* sum, const pixel* pix, intptr_t stride)
+{
+    /* framefilter.cpp:39-103: running W-wide horizontal sum added to the row above */
+    for (intptr_t x = 0; x < stride - W; x++)
+    {
+        uint32_t v = 0;
+        for (int i = 0; i < W; i++) v += pix[x + i];
+        sum[x] = v + sum[x - stride];
+    }
+}
+EXPORT void orc_integral_initv(int H, uint32_t* sum, intptr_t stride)
+{
+    /* framefilter.cpp:106-140 */
+    for (intptr_t x = 0; x < stride; x++) sum[x] = sum[x + H * stride] - sum[x];
+}
+static const int k_intW[12] = { 32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4 };   /* framefilter.cpp:776-787 */
+static const int k_intH[12] = { 32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4 };
+/* whole padded picture of `rows` rows: row t = y + padY of the picture feeds row t + 1 of every plane (framefilter.cpp:770-832) */
+EXPORT void orc_me_integral(const pixel* pix, intptr_t stride, int rows, uint32_t* sums, size_t planePitch)
+{
+    for (int k = 0; k < 12; k++) memset(sums + k * planePitch, 0, (size_t)stride * sizeof(uint32_t));
+    for (int t = 0; t < rows - 1; t++)
+        for (int k = 0; k < 12; k++)
+        {
+            uint32_t* S = sums + k * planePitch;
+            orc_integral_inith(k_intW[k], S + (intptr_t)(t + 1) * stride, pix + (intptr_t)t * stride, stride);
+            if (t >= k_intH[k]) orc_integral_initv(k_intH[k], S + (intptr_t)(t + 1 - k_intH[k]) * stride, stride);
+        }
+}

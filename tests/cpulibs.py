@@ -135,6 +135,16 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- SEA integral planes ---------------------------------------------------------------------------------
+    def integral_inith(self, W, sum_, osum, pix, opix, stride):
+        return self._f("integral_inith")(W, _ptr(sum_, osum), _ptr(pix, opix), C.c_ssize_t(stride))
+
+    def integral_initv(self, H, sum_, osum, stride):
+        return self._f("integral_initv")(H, _ptr(sum_, osum), C.c_ssize_t(stride))
+
+    def me_integral(self, pix, stride, rows, sums, plane_pitch):
+        return self._f("me_integral")(_ptr(pix), C.c_ssize_t(stride), rows, _ptr(sums), C.c_size_t(plane_pitch))
+
     # ---- sub-pel candidate cost (subpelCompare): interpolation + sad (op 0) / satd (op 1) ----------------------
     def subpel_cmp(self, op, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp")(op, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)

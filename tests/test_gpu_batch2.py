@@ -327,3 +327,29 @@ def test_subpel_cmp_batch(depth):
             ctx.subpel_cmp_batch(op, w, h, dF, geo.stride, dev(pix_view(ref_plane, depth)), geo.stride, dev(offF), dev(offR), dev(frac), K, cost)
             assert np.array_equal(cost.cpu().numpy(), want), (w, h, op)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_me_integral_batch(depth):
+    """twelve SEA integral planes of two padded pictures in one launch vs the oracle's row loop (defined region + zero row),
+    and the planes feeding `ads` exactly like a reference search row would"""
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(300 + depth)
+    stride, rows, nf = 224, 150, 2
+    pix = rng.integers(0, orc.pmax + 1, nf * stride * rows).astype(orc.pix)
+    pitch = stride * rows
+    sums = torch.full((nf * 12 * pitch,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+    ctx.me_integral_batch(dev(pix_view(pix, depth)), stride, rows, nf, sums, pitch)
+    got = sums.cpu().numpy().view(np.uint32)
+    W = [32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4]; H = [32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4]
+    for f in range(nf):
+        ref = np.zeros(12 * pitch, np.uint32)
+        orc.me_integral(pix[f * pitch:(f + 1) * pitch], stride, rows, ref, pitch)
+        for k in range(12):
+            G = got[(f * 12 + k) * pitch:(f * 12 + k + 1) * pitch].reshape(rows, stride)
+            R = ref[k * pitch:(k + 1) * pitch].reshape(rows, stride)
+            assert not G[0].any()
+            assert np.array_equal(G[1:rows - H[k], :stride - W[k]], R[1:rows - H[k], :stride - W[k]]), (f, k)
+    ctx.check()

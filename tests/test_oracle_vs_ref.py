@@ -341,3 +341,33 @@ def test_subpel_cmp(libs):
                     a = o.subpel_cmp(op, w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, xF, yF)
                     b = r.subpel_cmp(op, w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, xF, yF)
                     assert a == b and a >= 0, (w, h, op, xF, yF)
+
+
+def test_sea_integral(libs):
+    """integral_init{4..32}h / v rows and the whole-picture plane loop vs the reference's own framefilter.cpp functions"""
+    o, r = libs
+    rng = np.random.default_rng(41)
+    stride, rows = 96, 75
+    pix = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+    for size in (4, 8, 12, 16, 24, 32):
+        a = rng.integers(0, 2 ** 32, stride * 40, dtype=np.uint64).astype(np.uint32); b = a.copy()
+        o.integral_inith(size, a, 5 * stride + 3, pix, 7, stride); assert r.integral_inith(size, b, 5 * stride + 3, pix, 7, stride) == 0
+        assert np.array_equal(a, b), size
+        o.integral_initv(size, a, 2 * stride + 1, stride); assert r.integral_initv(size, b, 2 * stride + 1, stride) == 0
+        assert np.array_equal(a, b), size
+    pitch = stride * rows + 13
+    init = rng.integers(0, 2 ** 32, 12 * pitch, dtype=np.uint64).astype(np.uint32)      # the reference's planes start uninitialised
+    sa, sb = init.copy(), init.copy()
+    o.me_integral(pix, stride, rows, sa, pitch)
+    assert r.me_integral(pix, stride, rows, sb, pitch) == 0
+    assert np.array_equal(sa, sb)
+    # and the closed form the CUDA kernel implements: box sums on the defined region, zero first row
+    W = [32, 32, 32, 24, 16, 16, 16, 12, 8, 8, 4, 4]; H = [32, 24, 8, 32, 16, 12, 4, 16, 32, 8, 16, 4]
+    img = pix.reshape(rows, stride).astype(np.int64)
+    I = np.zeros((rows + 1, stride + 1), np.int64); I[1:, 1:] = img.cumsum(0).cumsum(1)
+    for k in range(12):
+        S = sb[k * pitch:k * pitch + stride * rows].reshape(rows, stride)
+        assert not S[0].any()
+        rr = np.arange(1, rows - H[k]); xx = np.arange(0, stride - W[k])
+        box = I[rr[:, None] + H[k], xx[None, :] + W[k]] - I[rr[:, None], xx[None, :] + W[k]] - I[rr[:, None] + H[k], xx[None, :]] + I[rr[:, None], xx[None, :]]
+        assert np.array_equal(S[1:rows - H[k], :stride - W[k]].astype(np.int64), box), k

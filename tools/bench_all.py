@@ -158,6 +158,12 @@ def main():
             ctx.lowres_batch(A[f * pe + geo.origin:], geo.stride, *[t[f * lw * lh:] for t in low], lw, lw, lh)
     ms = timeit(lowres_all, reps=4, warm=1, burst=2)
     add("frameInitLowres (one launch per frame, %d launches)" % F, ms, S * 2 * b, S)
+    # ---- SEA integral planes: 12 uint32 planes per picture from one read of the picture (4 frames per launch: 1.8 GB out)
+    nfi = min(F, 4)
+    isum = torch.empty(nfi * 12 * pe, dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: ctx.me_integral_batch(A, geo.stride, geo.rows, nfi, isum, pe), reps=4, warm=1, burst=3)
+    add("me_integral (12 SEA planes, %d padded frames per launch; b + 48 B per padded sample)" % nfi, ms, nfi * pe * (b + 48), nfi * pe)
+    del isum
     # ---- interpolation, frame-tiled 64x64 and 16x16 luma, 8x8 chroma-size blocks
     dstP = torch.empty(F * pe, dtype=A.dtype, device="cuda"); dstS = torch.empty(F * pe, dtype=torch.int16, device="cuda")
     srcS = torch.randint(-8192, 8192, (F * pe,), dtype=torch.int16, device="cuda")

@@ -87,6 +87,56 @@ blockop_quad_kernel(const TA* __restrict__ A, intptr_t sa, const int32_t* __rest
     }
 }
 
+// sub_ps / add_ps / pixelavg_pp on packed sample pairs, one thread per 8x4 strip (width % 8 == 0, height % 4 == 0,
+// source strides % 4 == 0): grouped chunk loads for both inputs, 16-byte stores.
+//   sub_ps   : lane-wise borrow-free subtraction (device_util.cuh psub16)
+//   add_ps   : clip(p + r, 0, max) == clip(p + clamp(r, -max, max), 0, max) for p in [0, max] -> VIADDMNMX.S16x2.RELU
+//   pixelavg : (a + b + 1) >> 1 per lane; a + b + 1 < 2^14 never carries into the neighbour lane
+template<int OP, typename TA, typename TB, typename TD>
+__global__ void __launch_bounds__(256)
+blockop_wide_kernel(const TA* __restrict__ A, intptr_t sa, const int32_t* __restrict__ offA, const TB* __restrict__ B, intptr_t sb,
+                    const int32_t* __restrict__ offB, TD* __restrict__ D, intptr_t sd, const int32_t* __restrict__ offD,
+                    int n, int w, int h, int maxv)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int sw = w >> 3;
+    int per = sw * (h >> 2);
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid - (long long)blk * per);
+    int y = (r / sw) << 2, x = (r % sw) << 3;
+    uint32_t wa[4][4], wb[4][4];
+    load_rows8<4>(A + blk_off(offA, blk, w * h) + (intptr_t)y * sa + x, sa, wa);
+    load_rows8<4>(B + blk_off(offB, blk, w * h) + (intptr_t)y * sb + x, sb, wb);
+    TD* d = D + blk_off(offD, blk, w * h) + (intptr_t)y * sd + x;
+    const uint32_t mx = (uint32_t)maxv * 0x10001u, negmx = (uint32_t)(-maxv & 0xffff) * 0x10001u;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            if (OP == BOP_SUB_PS) o[k] = psub16(wa[i][k], wb[i][k]);
+            else if (OP == BOP_ADD_PS) o[k] = __viaddmin_s16x2_relu(wa[i][k], __vmins2(__vmaxs2(wb[i][k], negmx), mx), mx);
+            else o[k] = ((wa[i][k] + wb[i][k] + 0x00010001u) >> 1) & 0x7fff7fffu;
+        }
+        TD* q = d + (intptr_t)i * sd;
+        if (sizeof(TD) == 2) store8_s16((int16_t*)q, o);
+        else
+        {
+            uint32_t b0 = __byte_perm(o[0], o[1], 0x6420), b1 = __byte_perm(o[2], o[3], 0x6420);
+            if (((uintptr_t)q & 7) == 0) *(uint2*)q = make_uint2(b0, b1);
+            else if (((uintptr_t)q & 3) == 0) { ((uint32_t*)q)[0] = b0; ((uint32_t*)q)[1] = b1; }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { q[k] = (TD)((b0 >> (8 * k)) & 0xff); q[4 + k] = (TD)((b1 >> (8 * k)) & 0xff); }
+            }
+        }
+    }
+}
+
 // frame_init_lowres_core: one thread per lowres position (pixel.cpp:604-612; "slower than naive bilinear, but matches asm")
 template<typename T>
 __global__ void __launch_bounds__(256)
@@ -113,7 +163,10 @@ template<int OP, typename TA, typename TB, typename TD>
 static void launch_bop(const void* A, intptr_t sa, const int32_t* offA, const void* B, intptr_t sb, const int32_t* offB,
                        void* D, intptr_t sd, const int32_t* offD, int n, int w, int h, int maxv, int shift, int offset, cudaStream_t st)
 {
-    if (!(w & 3) && !(h & 1))
+    if (OP != BOP_ADDAVG && !(w & 7) && !(h & 3) && !((sa | sb) & 3))
+        blockop_wide_kernel<OP, TA, TB, TD><<<ceil_div((long long)n * (w >> 3) * (h >> 2), 256), 256, 0, st>>>(
+            (const TA*)A, sa, offA, (const TB*)B, sb, offB, (TD*)D, sd, offD, n, w, h, maxv);
+    else if (!(w & 3) && !(h & 1))
         blockop_quad_kernel<OP, TA, TB, TD><<<ceil_div((long long)n * (w >> 2) * (h >> 1), 256), 256, 0, st>>>(
             (const TA*)A, sa, offA, (const TB*)B, sb, offB, (TD*)D, sd, offD, n, w, h, maxv, shift, offset);
     else

@@ -480,3 +480,44 @@ extern "C" void x265b200_frame_init_lowres(x265b200_ctx* ctx, const void* src0, 
     unpack(dstv, hd + 2 * plane, height, width * pb, dstStride * (intptr_t)pb);
     unpack(dstc, hd + 3 * plane, height, width * pb, dstStride * (intptr_t)pb);
 }
+
+// ------------------------------------------------------------------ host entries: SEA integral rows (integral.cu)
+
+// integralh_t (framefilter.cpp:39-103): sum[x] = hsum_W(pix, x) + sum[x - stride] for x < stride - W
+extern "C" void x265b200_integral_inith(x265b200_ctx* ctx, int W, uint32_t* sum, const void* pix, intptr_t stride)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const int count = (int)stride - W;
+    if (count <= 0) return;
+    const size_t pb = ctx->pixbytes;
+    size_t oP = c.alloc((size_t)stride * pb), oA = c.alloc((size_t)count * 4);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc((size_t)count * 4);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oP), pix, (size_t)stride * pb);
+    memcpy(c.h<void>(oA), sum - stride, (size_t)count * 4);
+    if (!c.upload(0, inEnd)) return;
+    if (x265b200_integral_row_batch(ctx, 0, W, c.d<void>(oP), c.d<uint32_t>(oA), nullptr, c.d<uint32_t>(oD), count, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)count * 4)) return;
+    memcpy(sum, c.h<void>(oD), (size_t)count * 4);
+}
+
+// integralv_t (framefilter.cpp:106-140): sum[x] = sum[x + H * stride] - sum[x] for x < stride
+extern "C" void x265b200_integral_initv(x265b200_ctx* ctx, int H, uint32_t* sum, intptr_t stride)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const int count = (int)stride;
+    if (count <= 0) return;
+    size_t oA = c.alloc((size_t)count * 4), oB = c.alloc((size_t)count * 4);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc((size_t)count * 4);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oA), sum, (size_t)count * 4);
+    memcpy(c.h<void>(oB), sum + (intptr_t)H * stride, (size_t)count * 4);
+    if (!c.upload(0, inEnd)) return;
+    if (x265b200_integral_row_batch(ctx, 1, H, nullptr, c.d<uint32_t>(oA), c.d<uint32_t>(oB), c.d<uint32_t>(oD), count, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)count * 4)) return;
+    memcpy(sum, c.h<void>(oD), (size_t)count * 4);
+}

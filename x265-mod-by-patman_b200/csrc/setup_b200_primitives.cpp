@@ -63,6 +63,8 @@ template<int W, int H> void t_sub_ps(int16_t* d, intptr_t ds, const pixel* a, co
 template<int W, int H> void t_add_ps(pixel* d, intptr_t ds, const pixel* a, const int16_t* b, intptr_t sa, intptr_t sb) { x265b200_add_ps(g_b200, W, H, d, ds, a, b, sa, sb); }
 template<int W, int H> void t_pixelavg(pixel* d, intptr_t ds, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb, int wt) { x265b200_pixelavg_pp(g_b200, W, H, d, ds, a, sa, b, sb, wt); }
 template<int W, int H> void t_addAvg(const int16_t* a, const int16_t* b, pixel* d, intptr_t sa, intptr_t sb, intptr_t ds) { x265b200_addAvg(g_b200, W, H, a, b, d, sa, sb, ds); }
+template<int W> void t_integral_h(uint32_t* sum, pixel* pix, intptr_t stride) { x265b200_integral_inith(g_b200, W, sum, pix, stride); }
+template<int H> void t_integral_v(uint32_t* sum, intptr_t stride) { x265b200_integral_initv(g_b200, H, sum, stride); }
 void t_lowres(const pixel* s, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ss, intptr_t ds, int w, int h) { x265b200_frame_init_lowres(g_b200, s, d0, dh, dv, dc, ss, ds, w, h); }
 
 template<int W, int H> void lumaPU(EncoderPrimitives::PU& pu)
@@ -151,6 +153,12 @@ void setupB200Primitives(EncoderPrimitives& p)
     p.quant = t_quant;  p.nquant = t_nquant;
     p.dequant_normal = t_dequant_normal;  p.dequant_scaling = t_dequant_scaling;
     p.frameInitLowres = t_lowres;
+    p.integral_inith[INTEGRAL_4] = t_integral_h<4>;   p.integral_initv[INTEGRAL_4] = t_integral_v<4>;
+    p.integral_inith[INTEGRAL_8] = t_integral_h<8>;   p.integral_initv[INTEGRAL_8] = t_integral_v<8>;
+    p.integral_inith[INTEGRAL_12] = t_integral_h<12>; p.integral_initv[INTEGRAL_12] = t_integral_v<12>;
+    p.integral_inith[INTEGRAL_16] = t_integral_h<16>; p.integral_initv[INTEGRAL_16] = t_integral_v<16>;
+    p.integral_inith[INTEGRAL_24] = t_integral_h<24>; p.integral_initv[INTEGRAL_24] = t_integral_v<24>;
+    p.integral_inith[INTEGRAL_32] = t_integral_h<32>; p.integral_initv[INTEGRAL_32] = t_integral_v<32>;
 }
 
 } // namespace X265_NS
