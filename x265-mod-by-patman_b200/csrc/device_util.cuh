@@ -173,6 +173,98 @@ __device__ __forceinline__ void load_row_quads(const uint8_t* p, uint32_t (&w)[2
     }
 }
 
+// ROWS rows of NQ quads each (row r starts at p + r * stride), like load_row_quads but with ONE misalignment class for
+// the whole strip (stride % 4 == 0): the base pointer, the shift and the word selection are computed once, all chunk loads
+// are issued before the first use, and the (s & 2) word selection is a branch around two straight-line realign blocks
+// instead of per-word selects.  w[r] gets 2 * NQ packed words (+ one zero word of padding for the FIR's odd-phase shifts).
+template<int NQ, int ROWS>
+__device__ __forceinline__ void load_rows_quads(const uint16_t* p, intptr_t stride, uint32_t (&w)[ROWS][2 * NQ + 1])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)(a >> 1) & 3;
+    const uint2* base = (const uint2*)(a & ~(uintptr_t)7);
+    intptr_t cs = stride >> 2;
+    uint32_t c[ROWS][2 * NQ + 2];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+    {
+#pragma unroll
+        for (int i = 0; i < NQ; i++) { uint2 q = __ldg(base + r * cs + i); c[r][2 * i] = q.x; c[r][2 * i + 1] = q.y; }
+    }
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) { uint2 q = __ldg(base + r * cs + NQ); c[r][2 * NQ] = q.x; c[r][2 * NQ + 1] = q.y; }
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) { c[r][2 * NQ] = 0; c[r][2 * NQ + 1] = 0; }
+    }
+    int sh = (s & 1) << 4;
+    if (s & 2)
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+        {
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) w[r][i] = __funnelshift_r(c[r][i + 1], c[r][(i + 2 <= 2 * NQ + 1) ? i + 2 : 2 * NQ + 1], sh);
+            w[r][2 * NQ] = 0;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+        {
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) w[r][i] = __funnelshift_r(c[r][i], c[r][i + 1], sh);
+            w[r][2 * NQ] = 0;
+        }
+    }
+}
+template<int NQ, int ROWS>
+__device__ __forceinline__ void load_rows_quads(const int16_t* p, intptr_t stride, uint32_t (&w)[ROWS][2 * NQ + 1])
+{ load_rows_quads<NQ, ROWS>((const uint16_t*)p, stride, w); }
+
+template<int NQ, int ROWS>
+__device__ __forceinline__ void load_rows_quads(const uint8_t* p, intptr_t stride, uint32_t (&w)[ROWS][2 * NQ + 1])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)a & 3;
+    const uint32_t* base = (const uint32_t*)(a & ~(uintptr_t)3);
+    intptr_t cs = stride >> 2;
+    uint32_t c[ROWS][NQ + 1];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+    {
+#pragma unroll
+        for (int i = 0; i < NQ; i++) c[r][i] = __ldg(base + r * cs + i);
+    }
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) c[r][NQ] = __ldg(base + r * cs + NQ);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) c[r][NQ] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+    {
+#pragma unroll
+        for (int i = 0; i < NQ; i++)
+        {
+            uint32_t v = __funnelshift_r(c[r][i], c[r][i + 1], s << 3);
+            w[r][2 * i] = __byte_perm(v, 0, 0x4140);
+            w[r][2 * i + 1] = __byte_perm(v, 0, 0x4342);
+        }
+        w[r][2 * NQ] = 0;
+    }
+}
+
 // ROWS rows of eight horizontally adjacent samples as packed 16-bit pairs (w[r][i] = samples 2i, 2i+1 of row r).
 // The row stride must be a multiple of four samples, so every row shares one misalignment class: all aligned
 // chunk loads of the strip are issued before the first use (ROWS * 16 bytes per thread in flight), then realigned.

@@ -178,9 +178,14 @@ __device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_
     {
         constexpr int NQ = (TW + TAPS - 1 + 3) / 4;              // quads covering TW + TAPS - 1 samples
         uint32_t w[TH][2 * NQ + 1];
+        if (FULL)
+            load_rows_quads<NQ, TH>(s, ss, w);
+        else
+        {
 #pragma unroll
-        for (int r = 0; r < TH; r++)
-            if (FULL || r < nr) { load_row_quads<NQ>(s + r * ss, (uint32_t(&)[2 * NQ])w[r]); w[r][2 * NQ] = 0; }
+            for (int r = 0; r < TH; r++)
+                if (r < nr) { load_row_quads<NQ>(s + r * ss, (uint32_t(&)[2 * NQ])w[r]); w[r][2 * NQ] = 0; }
+        }
 #pragma unroll
         for (int r = 0; r < TH; r++)
         {
@@ -208,10 +213,15 @@ __device__ __forceinline__ void fir_tile_body(const SRC* __restrict__ s, intptr_
     else
     {
         constexpr int NR = TH + TAPS - 1;
-        uint32_t w[NR][2];
+        uint32_t w[NR][3];
+        if (FULL)
+            load_rows_quads<1, NR>(s, ss, w);
+        else
+        {
 #pragma unroll
-        for (int r = 0; r < NR; r++)
-            if (FULL || r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, w[r]);
+            for (int r = 0; r < NR; r++)
+                if (r < nr + TAPS - 1) load_row_quads<1>(s + r * ss, (uint32_t(&)[2])w[r]);
+        }
         // pair words of vertically adjacent rows: pr[r][c] = (x[r][c], x[r+1][c])
         uint32_t pr[NR - 1][4];
 #pragma unroll
@@ -332,9 +342,14 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
         {
             int tx = (t % tw) * TW1, ty = (t / tw) << 2;
             uint32_t wv[4][2 * NQ + 1];
+            if (ty + 4 <= rows)
+                load_rows_quads<NQ, 4>(s + (intptr_t)ty * ss + tx, ss, wv);
+            else
+            {
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+                for (int r = 0; r < 4; r++)
+                    if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++)
             {
@@ -428,9 +443,14 @@ subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restri
         {
             int tx = (t % tw) * TW1, ty = (t / tw) << 2;
             uint32_t wv[4][2 * NQ + 1];
+            if (ty + 4 <= rows)
+                load_rows_quads<NQ, 4>(s + (intptr_t)ty * ss + tx, ss, wv);
+            else
+            {
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+                for (int r = 0; r < 4; r++)
+                    if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++)
             {
