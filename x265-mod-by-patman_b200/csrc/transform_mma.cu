@@ -527,6 +527,28 @@ __device__ __forceinline__ void store_pair(int16_t* p, int v0, int v1)
     if (((uintptr_t)p & 3) == 0) *(uint32_t*)p = __byte_perm(v0, v1, 0x5410);
     else { p[0] = (int16_t)v0; p[1] = (int16_t)v1; }
 }
+// two int32 -> packed int16 pair with signed saturation in one instruction (I2IP.S16.S32.SAT): the inverse transform's
+// clip3(-32768, 32767, .) of both stages (dct.cpp:257, 272)
+__device__ __forceinline__ uint32_t pack_sat_s16(int lo, int hi)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t recombine_sat2(int h0, int l0, int h1, int l1, int shift)
+{
+    return pack_sat_s16(recombine(h0, l0, shift), recombine(h1, l1, shift));
+}
+// low bytes / high bytes of four saturated values (the stage-2 operand of the inverse transform)
+__device__ __forceinline__ void pack4_sat(int v0, int v1, int v2, int v3, uint32_t& lo, uint32_t& hi)
+{
+    split4(make_uint2(pack_sat_s16(v0, v1), pack_sat_s16(v2, v3)), lo, hi);
+}
+__device__ __forceinline__ void store_pair_packed(int16_t* p, uint32_t w)
+{
+    if (((uintptr_t)p & 3) == 0) *(uint32_t*)p = w;
+    else { p[0] = (int16_t)(w & 0xffff); p[1] = (int16_t)(w >> 16); }
+}
 
 __global__ void __launch_bounds__(128)
 idct32_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__ dst, intptr_t dstStride,
@@ -594,22 +616,22 @@ idct32_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
                 imma32_ss(chi, a1[mt], bhi[nt][0], bhi[nt][1]);
                 imma32_su(clo, a1[mt], blo[nt][0], blo[nt][1]);
 #pragma unroll
-                for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+                for (int r = 0; r < 4; r++) v[nt][r] = recombine(chi[r], clo[r], shift1);
             }
             // accumulators -> stage-2 A fragments (rows g: c0,c1; rows g+8: c2,c3; n-tiles 0,1 -> k 0..15, 2,3 -> 16..31)
             uint32_t alo[4], ahi[4];
-            pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
-            pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
-            pack4(v[2][0], v[2][1], v[3][0], v[3][1], alo[2], ahi[2]);
-            pack4(v[2][2], v[2][3], v[3][2], v[3][3], alo[3], ahi[3]);
+            pack4_sat(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+            pack4_sat(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+            pack4_sat(v[2][0], v[2][1], v[3][0], v[3][1], alo[2], ahi[2]);
+            pack4_sat(v[2][2], v[2][3], v[3][2], v[3][3], alo[3], ahi[3]);
 #pragma unroll
             for (int it = 0; it < 4; it++)
             {
                 int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
                 imma32_ss(dhi, ahi, b2[it][0], b2[it][1]);
                 imma32_us(dlo, alo, b2[it][0], b2[it][1]);
-                store_pair(o + (intptr_t)(mt * 16) * dstStride + it * 8, recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
-                store_pair(o + (intptr_t)(mt * 16 + 8) * dstStride + it * 8, recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+                store_pair_packed(o + (intptr_t)(mt * 16) * dstStride + it * 8, recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2));
+                store_pair_packed(o + (intptr_t)(mt * 16 + 8) * dstStride + it * 8, recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2));
             }
         }
     }
@@ -672,11 +694,11 @@ idct16_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
                 imma16_ss(chi, a1, bhi[u][nt]);
                 imma16_su(clo, a1, blo[u][nt]);
 #pragma unroll
-                for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+                for (int r = 0; r < 4; r++) v[nt][r] = recombine(chi[r], clo[r], shift1);
             }
             uint32_t alo[2], ahi[2];
-            pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
-            pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+            pack4_sat(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+            pack4_sat(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
             int16_t* o = dst + tu_offset(off, tu, 256) + (intptr_t)g * dstStride + 2 * t;
 #pragma unroll
             for (int it = 0; it < 2; it++)
@@ -684,8 +706,8 @@ idct16_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restrict__
                 int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
                 imma16_ss(dhi, ahi, b2[it]);
                 imma16_us(dlo, alo, b2[it]);
-                store_pair(o + it * 8, recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
-                store_pair(o + (intptr_t)8 * dstStride + it * 8, recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+                store_pair_packed(o + it * 8, recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2));
+                store_pair_packed(o + (intptr_t)8 * dstStride + it * 8, recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2));
             }
         }
     }
@@ -759,20 +781,18 @@ idct_small_imma_kernel(const int16_t* __restrict__ src, int n, int16_t* __restri
             int chi[4] = { 0, 0, 0, 0 }, clo[4] = { add1, add1, add1, add1 };
             imma16_ss(chi, a1, bhi[u]);
             imma16_su(clo, a1, blo[u]);
-            int v0 = recombine_clip(chi[0], clo[0], shift1), v1 = recombine_clip(chi[1], clo[1], shift1);
-            int v2 = recombine_clip(chi[2], clo[2], shift1), v3 = recombine_clip(chi[3], clo[3], shift1);
             uint32_t alo[2], ahi[2];
-            pack4(v0, v1, 0, 0, alo[0], ahi[0]);          // slots e = 2,3 are padding (their B rows are zero)
-            pack4(v2, v3, 0, 0, alo[1], ahi[1]);
+            split4(make_uint2(recombine_sat2(chi[0], clo[0], chi[1], clo[1], shift1), 0u), alo[0], ahi[0]);   // slots e = 2,3 are padding (their B rows are zero)
+            split4(make_uint2(recombine_sat2(chi[2], clo[2], chi[3], clo[3], shift1), 0u), alo[1], ahi[1]);
             int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
             imma16_ss(dhi, ahi, b2);
             imma16_us(dlo, alo, b2);
             if (base + st_tu0 < n)
-                store_pair(dst + tu_offset(off, base + st_tu0, NN) + (intptr_t)st_row * dstStride + st_col,
-                           recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
+                store_pair_packed(dst + tu_offset(off, base + st_tu0, NN) + (intptr_t)st_row * dstStride + st_col,
+                                  recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2));
             if (base + st_tu1 < n)
-                store_pair(dst + tu_offset(off, base + st_tu1, NN) + (intptr_t)st_row * dstStride + st_col,
-                           recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+                store_pair_packed(dst + tu_offset(off, base + st_tu1, NN) + (intptr_t)st_row * dstStride + st_col,
+                                  recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2));
         }
     }
 }

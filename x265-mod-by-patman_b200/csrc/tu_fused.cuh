@@ -42,15 +42,15 @@ __device__ __forceinline__ uint32_t pack2(int v0, int v1) { return __byte_perm((
 
 struct QuantP { int qBits, qAdd, dqScale, dqAdd, dqShift; };
 
-// quant of one coefficient (the low 16 bits of c are the DCT output); returns level != 0
+// quant of one coefficient (the low 16 bits of c are the DCT output); returns level != 0.  The clip3(-32768, 32767, .)
+// of dct.cpp:683 happens when two levels are packed (pack_sat_s16 = I2IP.S16.S32.SAT).
 __device__ __forceinline__ int quant_one(int c, int q, const QuantP& P, int& level)
 {
     int sign = c < 0 ? -1 : 1;
     int tmplevel = (int)((unsigned)abs(c) * (unsigned)q);                       // int32 wrap, dct.cpp:678
     int lv = (int)((unsigned)tmplevel + (unsigned)P.qAdd) >> P.qBits;
-    int nz = lv != 0;
-    level = min(32767, max(-32768, (int)((unsigned)lv * (unsigned)sign)));
-    return nz;
+    level = (int)((unsigned)lv * (unsigned)sign);
+    return lv != 0;
 }
 // four horizontally adjacent coefficients at TU position pos (a multiple of 4): quantise, store the levels
 __device__ __forceinline__ int quant_quad_store(uint2 c, const int32_t* __restrict__ quantCoeff, int pos, const QuantP& P, int16_t* __restrict__ qTu)
@@ -59,16 +59,17 @@ __device__ __forceinline__ int quant_quad_store(uint2 c, const int32_t* __restri
     int l0, l1, l2, l3;
     int nz = quant_one((int)(int16_t)(c.x & 0xffff), q.x, P, l0) + quant_one((int)c.x >> 16, q.y, P, l1)
            + quant_one((int)(int16_t)(c.y & 0xffff), q.z, P, l2) + quant_one((int)c.y >> 16, q.w, P, l3);
-    *(uint2*)(qTu + pos) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+    *(uint2*)(qTu + pos) = make_uint2(pack_sat_s16(l0, l1), pack_sat_s16(l2, l3));
     return nz;
 }
-__device__ __forceinline__ int dequant_one(int lv, const QuantP& P)
+__device__ __forceinline__ int dequant_raw(int lv, const QuantP& P)
 {
-    return min(32767, max(-32768, (int)((unsigned)lv * (unsigned)P.dqScale + (unsigned)P.dqAdd) >> P.dqShift));
+    return (int)((unsigned)lv * (unsigned)P.dqScale + (unsigned)P.dqAdd) >> P.dqShift;
 }
+__device__ __forceinline__ int dequant_one(int lv, const QuantP& P) { return min(32767, max(-32768, dequant_raw(lv, P))); }
 __device__ __forceinline__ uint32_t dequant_pair(uint32_t w, const QuantP& P)
 {
-    return pack2(dequant_one((int)(int16_t)(w & 0xffff), P), dequant_one((int)w >> 16, P));
+    return pack_sat_s16(dequant_raw((int)(int16_t)(w & 0xffff), P), dequant_raw((int)w >> 16, P));
 }
 
 // DC-only reconstruction value (quant.cpp:588-598)
@@ -309,12 +310,12 @@ tu_inv32_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restrict__ 
                     imma32_ss(chi, a1[mt], bhi[nt][0], bhi[nt][1]);
                     imma32_su(clo, a1[mt], blo[nt][0], blo[nt][1]);
 #pragma unroll
-                    for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+                    for (int r = 0; r < 4; r++) v[nt][r] = recombine(chi[r], clo[r], shift1);
                 }
-                pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
-                pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
-                pack4(v[2][0], v[2][1], v[3][0], v[3][1], alo[2], ahi[2]);
-                pack4(v[2][2], v[2][3], v[3][2], v[3][3], alo[3], ahi[3]);
+                pack4_sat(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+                pack4_sat(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+                pack4_sat(v[2][0], v[2][1], v[3][0], v[3][1], alo[2], ahi[2]);
+                pack4_sat(v[2][2], v[2][3], v[3][2], v[3][3], alo[3], ahi[3]);
             }
 #pragma unroll
             for (int ip = 0; ip < 2; ip++)
@@ -329,8 +330,8 @@ tu_inv32_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restrict__ 
                         int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
                         imma32_ss(dhi, ahi, b2[2 * ip + k][0], b2[2 * ip + k][1]);
                         imma32_us(dlo, alo, b2[2 * ip + k][0], b2[2 * ip + k][1]);
-                        uint32_t top = pack2(recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
-                        uint32_t bot = pack2(recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+                        uint32_t top = recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2);
+                        uint32_t bot = recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2);
                         if (k == 0) { pa[0] = top; pa[1] = bot; } else { pb[0] = top; pb[1] = bot; }
                     }
                     qa = pair_to_quad(pa[0], pb[0], t);
@@ -507,11 +508,11 @@ tu_inv16_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restrict__ 
                     imma16_ss(chi, a1, bhi[u][nt]);
                     imma16_su(clo, a1, blo[u][nt]);
 #pragma unroll
-                    for (int r = 0; r < 4; r++) v[nt][r] = recombine_clip(chi[r], clo[r], shift1);
+                    for (int r = 0; r < 4; r++) v[nt][r] = recombine(chi[r], clo[r], shift1);
                 }
                 uint32_t alo[2], ahi[2];
-                pack4(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
-                pack4(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
+                pack4_sat(v[0][0], v[0][1], v[1][0], v[1][1], alo[0], ahi[0]);
+                pack4_sat(v[0][2], v[0][3], v[1][2], v[1][3], alo[1], ahi[1]);
                 uint32_t pa[2], pb[2];
 #pragma unroll
                 for (int k = 0; k < 2; k++)
@@ -519,8 +520,8 @@ tu_inv16_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restrict__ 
                     int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
                     imma16_ss(dhi, ahi, b2[k]);
                     imma16_us(dlo, alo, b2[k]);
-                    uint32_t top = pack2(recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2));
-                    uint32_t bot = pack2(recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2));
+                    uint32_t top = recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2);
+                    uint32_t bot = recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2);
                     if (k == 0) { pa[0] = top; pa[1] = bot; } else { pb[0] = top; pb[1] = bot; }
                 }
                 qa = pair_to_quad(pa[0], pb[0], t);
@@ -686,16 +687,14 @@ tu_inv_small_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restric
             int chi[4] = { 0, 0, 0, 0 }, clo[4] = { add1, add1, add1, add1 };
             imma16_ss(chi, a1, bhi[u]);
             imma16_su(clo, a1, blo[u]);
-            int v0 = recombine_clip(chi[0], clo[0], shift1), v1 = recombine_clip(chi[1], clo[1], shift1);
-            int v2 = recombine_clip(chi[2], clo[2], shift1), v3 = recombine_clip(chi[3], clo[3], shift1);
             uint32_t alo[2], ahi[2];
-            pack4(v0, v1, 0, 0, alo[0], ahi[0]);
-            pack4(v2, v3, 0, 0, alo[1], ahi[1]);
+            split4(make_uint2(recombine_sat2(chi[0], clo[0], chi[1], clo[1], shift1), 0u), alo[0], ahi[0]);
+            split4(make_uint2(recombine_sat2(chi[2], clo[2], chi[3], clo[3], shift1), 0u), alo[1], ahi[1]);
             int dhi[4] = { 0, 0, 0, 0 }, dlo[4] = { add2, add2, add2, add2 };
             imma16_ss(dhi, ahi, b2);
             imma16_us(dlo, alo, b2);
-            uint2 quad = pair_to_quad(pack2(recombine_clip(dhi[0], dlo[0], shift2), recombine_clip(dhi[1], dlo[1], shift2)),
-                                      pack2(recombine_clip(dhi[2], dlo[2], shift2), recombine_clip(dhi[3], dlo[3], shift2)), t);
+            uint2 quad = pair_to_quad(recombine_sat2(dhi[0], dlo[0], dhi[1], dlo[1], shift2),
+                                      recombine_sat2(dhi[2], dlo[2], dhi[3], dlo[3], shift2), t);
             int tu = base + st_tu;
             uint32_t d = 0;
             if (tu < n)
