@@ -24,6 +24,17 @@ template<typename T> __device__ __forceinline__ uint2 res_quad(const T* f, const
     return make_uint2(psub16(wf[0], wp[0]), psub16(wf[1], wp[1]));
 }
 
+// ROWS quads, `rowStep` rows apart (strip loader: one misalignment class, all loads issued first)
+template<typename T, int ROWS>
+__device__ __forceinline__ void res_quads(const T* f, intptr_t fStep, const T* p, intptr_t pStep, uint2 (&x)[ROWS])
+{
+    uint32_t wf[ROWS][3], wp[ROWS][3];
+    load_rows_quads<1, ROWS>(f, fStep, wf);
+    load_rows_quads<1, ROWS>(p, pStep, wp);
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) x[r] = make_uint2(psub16(wf[r][0], wp[r][0]), psub16(wf[r][1], wp[r][1]));
+}
+
 // sum of squares of the four lane-exact int16 in q
 __device__ __forceinline__ uint32_t sumsq4(uint2 q)
 {
@@ -145,12 +156,11 @@ tu_fwd32_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ p
     {
         const T* f = fenc + offF[warp] + lf;
         const T* p = pred + offP[warp] + lp;
+        uint2 xa[4], xb[4];
+        res_quads<T, 4>(f, 8 * sf, p, 8 * sp, xa);
+        res_quads<T, 4>(f + 16, 8 * sf, p + 16, 8 * sp, xb);
 #pragma unroll
-        for (int jt = 0; jt < 4; jt++)
-        {
-            x[jt][0] = res_quad(f + (intptr_t)(jt * 8) * sf, p + (intptr_t)(jt * 8) * sp);
-            x[jt][1] = res_quad(f + (intptr_t)(jt * 8) * sf + 16, p + (intptr_t)(jt * 8) * sp + 16);
-        }
+        for (int jt = 0; jt < 4; jt++) { x[jt][0] = xa[jt]; x[jt][1] = xb[jt]; }
     }
     for (int tu = warp; tu < n; tu += nwarps)
     {
@@ -168,12 +178,11 @@ tu_fwd32_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ p
         {
             const T* f = fenc + offF[nxt] + lf;
             const T* p = pred + offP[nxt] + lp;
+            uint2 xa[4], xb[4];
+            res_quads<T, 4>(f, 8 * sf, p, 8 * sp, xa);
+            res_quads<T, 4>(f + 16, 8 * sf, p + 16, 8 * sp, xb);
 #pragma unroll
-            for (int jt = 0; jt < 4; jt++)
-            {
-                x[jt][0] = res_quad(f + (intptr_t)(jt * 8) * sf, p + (intptr_t)(jt * 8) * sp);
-                x[jt][1] = res_quad(f + (intptr_t)(jt * 8) * sf + 16, p + (intptr_t)(jt * 8) * sp + 16);
-            }
+            for (int jt = 0; jt < 4; jt++) { x[jt][0] = xa[jt]; x[jt][1] = xb[jt]; }
         }
         uint32_t b2lo[4][2], b2hi[4][2];
 #pragma unroll
@@ -373,7 +382,7 @@ tu_fwd16_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ p
         int tu = min(warp * TPW + u, n - 1);
         const T* f = fenc + offF[tu] + lf;
         const T* p = pred + offP[tu] + lp;
-        x[u][0] = res_quad(f, p); x[u][1] = res_quad(f + 8 * sf, p + 8 * sp);
+        res_quads<T, 2>(f, 8 * sf, p, 8 * sp, x[u]);
     }
     for (int grp = warp; grp < ngroups; grp += nwarps)
     {
@@ -394,7 +403,7 @@ tu_fwd16_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ p
                 int tu = min(nxt * TPW + u, n - 1);
                 const T* f = fenc + offF[tu] + lf;
                 const T* p = pred + offP[tu] + lp;
-                x[u][0] = res_quad(f, p); x[u][1] = res_quad(f + 8 * sf, p + 8 * sp);
+                res_quads<T, 2>(f, 8 * sf, p, 8 * sp, x[u]);
             }
         }
 #pragma unroll
