@@ -212,6 +212,16 @@ int x265b200_me_integral_batch(x265b200_ctx* ctx, const void* pix, intptr_t stri
 int x265b200_integral_row_batch(x265b200_ctx* ctx, int vertical, int size, const void* pix, const uint32_t* a, const uint32_t* b,
                                 uint32_t* out, int count, x265b200_stream stream);
 
+/* weightp_pp_t / weightp_sp_t (pixel.cpp:485-535) over a width x height plane region; sp = 0: pixel source, sp = 1: int16 source */
+int x265b200_weight_batch(x265b200_ctx* ctx, int sp, const void* src, intptr_t srcStride, void* dst, intptr_t dstStride,
+                          int width, int height, int w0, int round, int shift, int offset, x265b200_stream stream);
+/* Lookahead weighted-prediction cost (encoder/slicetype.cpp:866-897 weightCostLuma; weightPrediction.cpp:171-222 luma branch)
+ * for K candidate weights in one pass: weights = K x {w0, round, shift, offset} as passed to weight_pp (shift < 0: unweighted);
+ * cost[k] = sum over the 8x8 blocks of the width x height picture of min(satd_8x8(weight_k(ref), fenc), intraCost[block])
+ * (intraCost may be NULL: no cap).  fenc and ref share `stride` (a multiple of 4 samples). */
+int x265b200_weight_cost_batch(x265b200_ctx* ctx, const void* fenc, const void* ref, intptr_t stride, int width, int height,
+                               const int32_t* intraCost, const int32_t* weights, int K, uint32_t* cost, x265b200_stream stream);
+
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 
 int x265b200_sad(x265b200_ctx*, int w, int h, const void* fenc, intptr_t fencstride, const void* fref, intptr_t frefstride);
@@ -244,6 +254,8 @@ void x265b200_addAvg(x265b200_ctx*, int w, int h, const int16_t* src0, const int
 void x265b200_frame_init_lowres(x265b200_ctx*, const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
                                 intptr_t srcStride, intptr_t dstStride, int width, int height);
 /* integralh_t / integralv_t (primitives.h:227-228) with the box width / height prepended */
+void x265b200_weight_pp(x265b200_ctx*, const void* src, void* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset);
+void x265b200_weight_sp(x265b200_ctx*, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset);
 void x265b200_integral_inith(x265b200_ctx*, int W, uint32_t* sum, const void* pix, intptr_t stride);
 void x265b200_integral_initv(x265b200_ctx*, int H, uint32_t* sum, intptr_t stride);
 

@@ -94,7 +94,7 @@ static int coverage()
         SLOT(cu[i].sub_ps); SLOT(cu[i].add_ps[0]); SLOT(cu[i].add_ps[1]);
         for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].sub_ps); SLOT(chroma[c].cu[i].add_ps[0]); SLOT(chroma[c].cu[i].add_ps[1]); }
     }
-    SLOT(frameInitLowres);
+    SLOT(frameInitLowres); SLOT(weight_pp); SLOT(weight_sp);
     for (int i = 0; i < NUM_INTEGRAL_SIZE; i++) { SLOT(integral_inith[i]); SLOT(integral_initv[i]); }
     printf("adjacent: %d slots in the C table, %d bound to B200 entries, %d missing, %d still C, %d extra\n", want, bound, missing, same, extra);
     return hot + missing + same + extra;

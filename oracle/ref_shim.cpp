@@ -410,4 +410,32 @@ int ref_me_integral(pixel* pix, intptr_t stride, int rows, uint32_t* sums, size_
     return 0;
 }
 
+
+/* ---- weighted prediction slots and the lookahead's weightCostLuma composition (slicetype.cpp:866-897) ---- */
+void ref_weight_pp(const pixel* src, pixel* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset)
+{ ensure(); g_c.weight_pp(src, dst, stride, width, height, w0, round, shift, offset); }
+void ref_weight_sp(const int16_t* src, pixel* dst, intptr_t ss, intptr_t ds, int width, int height, int w0, int round, int shift, int offset)
+{ ensure(); g_c.weight_sp(src, dst, ss, ds, width, height, w0, round, shift, offset); }
+void ref_weight_cost(const pixel* fenc, const pixel* ref, intptr_t stride, int width, int height, const int32_t* intraCost,
+                     const int32_t* weights, int K, uint32_t* cost, pixel* tmp)
+{
+    ensure();
+    int pw = (width + 7) & ~7, ph = (height + 7) & ~7;
+    for (int k = 0; k < K; k++)
+    {
+        const int32_t* w = weights + 4 * k;
+        const pixel* src = ref;
+        if (w[2] >= 0) { g_c.weight_pp(ref, tmp, stride, pw, ph, w[0], w[1], w[2], w[3]); src = tmp; }
+        uint32_t c = 0;
+        int mb = 0;
+        for (int y = 0; y < height; y += 8)
+            for (int x = 0; x < width; x += 8, mb++)
+            {
+                int satd = g_c.pu[LUMA_8x8].satd(src + y * stride + x, stride, fenc + y * stride + x, stride);
+                c += intraCost ? X265_MIN(satd, intraCost[mb]) : satd;
+            }
+        cost[k] = c;
+    }
+}
+
 } // extern "C"

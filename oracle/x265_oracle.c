@@ -803,3 +803,46 @@ EXPORT void orc_me_integral(const pixel* pix, intptr_t stride, int rows, uint32_
             if (t >= k_intH[k]) orc_integral_initv(k_intH[k], S + (intptr_t)(t + 1 - k_intH[k]) * stride, stride);
         }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Weighted prediction (pixel.cpp:485-535) and the lookahead's weighted-prediction cost
+ * (slicetype.cpp:866-897 weightCostLuma / weightPrediction.cpp:171-222 luma branch).
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void orc_weight_pp(const pixel* src, pixel* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset)
+{
+    const int correction = 14 - X265_DEPTH, pmax = (1 << X265_DEPTH) - 1;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+        {
+            int16_t val = (int16_t)(src[y * stride + x] << correction);
+            dst[y * stride + x] = (pixel)clip3(0, pmax, ((w0 * val + round) >> shift) + offset);
+        }
+}
+EXPORT void orc_weight_sp(const int16_t* src, pixel* dst, intptr_t ss, intptr_t ds, int width, int height, int w0, int round, int shift, int offset)
+{
+    const int pmax = (1 << X265_DEPTH) - 1;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+            dst[y * ds + x] = (pixel)clip3(0, pmax, ((w0 * (src[y * ss + x] + 8192) + round) >> shift) + offset);
+}
+/* weights: K x {w0, round, shift, offset}, shift < 0 = unweighted; tmp: scratch plane like the reference's weighted plane */
+EXPORT void orc_weight_cost(const pixel* fenc, const pixel* ref, intptr_t stride, int width, int height, const int32_t* intraCost,
+                            const int32_t* weights, int K, uint32_t* cost, pixel* tmp)
+{
+    int pw = (width + 7) & ~7, ph = (height + 7) & ~7;
+    for (int k = 0; k < K; k++)
+    {
+        const int32_t* w = weights + 4 * k;
+        const pixel* src = ref;
+        if (w[2] >= 0) { orc_weight_pp(ref, tmp, stride, pw, ph, w[0], w[1], w[2], w[3]); src = tmp; }
+        uint32_t c = 0;
+        int mb = 0;
+        for (int y = 0; y < height; y += 8)
+            for (int x = 0; x < width; x += 8, mb++)
+            {
+                int s = orc_satd(8, 8, src + y * stride + x, stride, fenc + y * stride + x, stride);
+                c += (uint32_t)((intraCost && intraCost[mb] < s) ? intraCost[mb] : s);
+            }
+        cost[k] = c;
+    }
+}

@@ -135,6 +135,21 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- weighted prediction + lookahead weight cost -----------------------------------------------------------
+    def weight_pp(self, src, osrc, dst, odst, stride, width, height, w0, rnd, shift, offset):
+        self._f("weight_pp", None)(_ptr(src, osrc), _ptr(dst, odst), C.c_ssize_t(stride), width, height, w0, rnd, shift, offset)
+
+    def weight_sp(self, src, osrc, dst, odst, ss, ds, width, height, w0, rnd, shift, offset):
+        self._f("weight_sp", None)(_ptr(src, osrc), _ptr(dst, odst), C.c_ssize_t(ss), C.c_ssize_t(ds), width, height, w0, rnd, shift, offset)
+
+    def weight_cost(self, fenc, of, ref, orf, stride, width, height, intra, weights):
+        K = len(weights) // 4
+        cost = np.zeros(K, np.uint32)
+        tmp = np.zeros(len(ref), ref.dtype)
+        self._f("weight_cost", None)(_ptr(fenc, of), _ptr(ref, orf), C.c_ssize_t(stride), width, height, _ptr(intra) if intra is not None else None,
+                                     _ptr(weights), K, _ptr(cost), _ptr(tmp))
+        return cost
+
     # ---- SEA integral planes ---------------------------------------------------------------------------------
     def integral_inith(self, W, sum_, osum, pix, opix, stride):
         return self._f("integral_inith")(W, _ptr(sum_, osum), _ptr(pix, opix), C.c_ssize_t(stride))

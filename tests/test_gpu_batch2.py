@@ -353,3 +353,44 @@ def test_me_integral_batch(depth):
             assert not G[0].any()
             assert np.array_equal(G[1:rows - H[k], :stride - W[k]], R[1:rows - H[k], :stride - W[k]]), (f, k)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_weight_and_weight_cost_batches(depth):
+    """weight_pp / weight_sp planes and the fused K-candidate weighted-prediction cost vs the oracle"""
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(400 + depth)
+    corr = 14 - depth
+    stride, rows = 480, 300
+    pix = rng.integers(0, orc.pmax + 1, stride * rows).astype(orc.pix)
+    s16 = rng.integers(-8192, 8192, stride * rows).astype(np.int16)
+    for trial in range(4):
+        shift = int(rng.integers(1, 7)); w0 = int(rng.integers(1, 127)); offset = int(rng.integers(-128, 128)) << (depth - 8)
+        rnd = 1 << (shift - 1)
+        want = np.full(stride * rows, 3, orc.pix)
+        orc.weight_pp(pix, 0, want, 0, stride, 464, 290, w0, rnd << corr, shift + corr, offset)
+        got = dev(pix_view(np.full(stride * rows, 3, orc.pix), depth))
+        ctx.weight_batch(0, dev(pix_view(pix, depth)), stride, got, stride, 464, 290, w0, rnd << corr, shift + corr, offset)
+        g = got.cpu().numpy()
+        assert np.array_equal(g.view(np.uint16) if depth > 8 else g, want)
+        want = np.full(stride * rows, 3, orc.pix)
+        orc.weight_sp(s16, 0, want, 0, stride, stride, 301, 177, w0, rnd << corr, shift + corr, offset)
+        got = dev(pix_view(np.full(stride * rows, 3, orc.pix), depth))
+        ctx.weight_batch(1, dev(s16), stride, got, stride, 301, 177, w0, rnd << corr, shift + corr, offset)
+        g = got.cpu().numpy()
+        assert np.array_equal(g.view(np.uint16) if depth > 8 else g, want)
+    fenc = rng.integers(0, orc.pmax + 1, stride * rows).astype(orc.pix)
+    ref = np.clip(fenc.astype(np.int64) * 3 // 4 + rng.integers(-20, 21, stride * rows), 0, orc.pmax).astype(orc.pix)
+    W, H = 444, 270
+    intra = rng.integers(0, 3000 << (depth - 8), ((W + 7) // 8) * ((H + 7) // 8)).astype(np.int32)
+    weights = np.array([0, 0, -1, 0] + [64, 32 << corr, 6 + corr, 0] + [85, 32 << corr, 6 + corr, 3 << (depth - 8)]
+                       + [43, 16 << corr, 5 + corr, -(2 << (depth - 8))] + [100, 1 << corr, 1 + corr, 0], np.int32)
+    K = len(weights) // 4
+    for ic in (intra, None):
+        want = orc.weight_cost(fenc, 0, ref, 0, stride, W, H, ic, weights)
+        cost = torch.zeros(K, dtype=torch.int32, device="cuda")
+        ctx.weight_cost_batch(dev(pix_view(fenc, depth)), dev(pix_view(ref, depth)), stride, W, H, dev(ic) if ic is not None else None, dev(weights), K, cost)
+        assert np.array_equal(cost.cpu().numpy().view(np.uint32), want)
+    ctx.check()

@@ -371,3 +371,29 @@ def test_sea_integral(libs):
         rr = np.arange(1, rows - H[k]); xx = np.arange(0, stride - W[k])
         box = I[rr[:, None] + H[k], xx[None, :] + W[k]] - I[rr[:, None], xx[None, :] + W[k]] - I[rr[:, None] + H[k], xx[None, :]] + I[rr[:, None], xx[None, :]]
         assert np.array_equal(S[1:rows - H[k], :stride - W[k]].astype(np.int64), box), k
+
+
+def test_weighted_prediction(libs):
+    """weight_pp / weight_sp slots and the lookahead's weightCostLuma composition"""
+    o, r = libs
+    rng = np.random.default_rng(51)
+    D = o.depth
+    corr = 14 - D
+    stride, rows = 128, 90
+    pix = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+    s16 = rng.integers(-8192, 8192, stride * rows).astype(np.int16)
+    for trial in range(12):
+        shift = int(rng.integers(1, 7)); w0 = int(rng.integers(1, 127)); offset = int(rng.integers(-128, 128)) << (D - 8)
+        rnd = 1 << (shift - 1)
+        a = np.full(stride * rows, 3, o.pix); b = a.copy()
+        o.weight_pp(pix, 5, a, 9, stride, 64, 40, w0, rnd << corr, shift + corr, offset); r.weight_pp(pix, 5, b, 9, stride, 64, 40, w0, rnd << corr, shift + corr, offset)
+        assert np.array_equal(a, b)
+        o.weight_sp(s16, 7, a, 2, stride, 100, 37, 21, w0, rnd << corr, shift + corr, offset); r.weight_sp(s16, 7, b, 2, stride, 100, 37, 21, w0, rnd << corr, shift + corr, offset)
+        assert np.array_equal(a, b)
+    fenc = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+    ref = np.clip(fenc.astype(np.int64) * 3 // 4 + rng.integers(-20, 21, stride * rows), 0, o.pmax).astype(o.pix)
+    W, H = 104, 72
+    intra = rng.integers(0, 3000 << (D - 8), ((W + 7) // 8) * ((H + 7) // 8)).astype(np.int32)
+    weights = np.array([0, 0, -1, 0] + [64, 32 << corr, 6 + corr, 0] + [85, 32 << corr, 6 + corr, 3 << (D - 8)] + [43, 16 << corr, 5 + corr, -2 << (D - 8)], np.int32)
+    for ic in (intra, None):
+        assert np.array_equal(o.weight_cost(fenc, 0, ref, 0, stride, W, H, ic, weights), r.weight_cost(fenc, 0, ref, 0, stride, W, H, ic, weights))

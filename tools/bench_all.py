@@ -158,6 +158,18 @@ def main():
             ctx.lowres_batch(A[f * pe + geo.origin:], geo.stride, *[t[f * lw * lh:] for t in low], lw, lw, lh)
     ms = timeit(lowres_all, reps=4, warm=1, burst=2)
     add("frameInitLowres (one launch per frame, %d launches)" % F, ms, S * 2 * b, S)
+    # ---- lookahead weighted-prediction cost: K = 8 candidate weights over one frame pair per launch (8 frames per timing call)
+    K = 8
+    wts = torch.tensor(sum([[64 + k, 32 << (14 - D), 6 + 14 - D, k - 3] for k in range(K)], []), dtype=torch.int32, device="cuda")
+    wcost = torch.empty(K, dtype=torch.int32, device="cuda")
+    intra = torch.randint(0, 1 << 20, ((cw // 8) * (ch // 8),), dtype=torch.int32, device="cuda")
+    nfw = min(F, 8)
+
+    def wc_all():
+        for f in range(nfw):
+            ctx.weight_cost_batch(A[f * pe + geo.origin:], B[f * pe + geo.origin:], geo.stride, cw, ch, intra, wts, K, wcost)
+    ms = timeit(wc_all, reps=4, warm=1, burst=2)
+    add("weight_cost (K = 8 weights fused with 8x8 SATD, per candidate sample; 2b bytes per sample for all K)", ms, nfw * cw * ch * 2 * b, nfw * cw * ch * K)
     # ---- SEA integral planes: 12 uint32 planes per picture from one read of the picture (4 frames per launch: 1.8 GB out)
     nfi = min(F, 4)
     isum = torch.empty(nfi * 12 * pe, dtype=torch.int32, device="cuda")

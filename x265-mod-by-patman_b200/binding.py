@@ -46,7 +46,7 @@ def load_library():
             getattr(_lib, name).restype = C.c_uint32
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
                      "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
-                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv"):
+                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -141,6 +141,12 @@ class Context:
     def subpel_cmp_batch(self, op, w, h, fenc, sf, ref, sr, offF, offR, frac, K, cost, stream=0):
         self._call("x265b200_subpel_cmp_batch", op, w, h, _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(frac), K,
                    int(offF.numel()), _dp(cost), C.c_void_p(stream))
+
+    def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
+        self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
+
+    def weight_cost_batch(self, fenc, ref, stride, width, height, intra, weights, K, cost, stream=0):
+        self._call("x265b200_weight_cost_batch", _dp(fenc), _dp(ref), _ss(stride), width, height, _dp(intra), _dp(weights), int(K), _dp(cost), C.c_void_p(stream))
 
     def me_integral_batch(self, pix, stride, rows, nframes, sums, plane_pitch, stream=0):
         self._call("x265b200_me_integral_batch", _dp(pix), _ss(stride), int(rows), int(nframes), _dp(sums), C.c_size_t(int(plane_pitch)), C.c_void_p(stream))

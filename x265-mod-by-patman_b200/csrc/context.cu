@@ -521,3 +521,26 @@ extern "C" void x265b200_integral_initv(x265b200_ctx* ctx, int H, uint32_t* sum,
     if (!c.download(oD, (size_t)count * 4)) return;
     memcpy(sum, c.h<void>(oD), (size_t)count * 4);
 }
+
+// ------------------------------------------------------------------ host entries: weighted prediction (weight.cu)
+
+static void host_weight(x265b200_ctx* ctx, int sp, const void* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height,
+                        int w0, int round, int shift, int offset)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const size_t sb = sp ? 2 : ctx->pixbytes, db = ctx->pixbytes;
+    size_t oS = c.alloc((size_t)width * height * sb);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc((size_t)width * height * db);
+    if (!c.ok()) return;
+    pack(c.h<void>(oS), src, height, width * sb, srcStride * (intptr_t)sb);
+    if (!c.upload(0, inEnd)) return;
+    if (x265b200_weight_batch(ctx, sp, c.d<void>(oS), width, c.d<void>(oD), width, width, height, w0, round, shift, offset, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)width * height * db)) return;
+    unpack(dst, c.h<void>(oD), height, width * db, dstStride * (intptr_t)db);
+}
+extern "C" void x265b200_weight_pp(x265b200_ctx* ctx, const void* src, void* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset)
+{ if (ctx) host_weight(ctx, 0, src, dst, stride, stride, width, height, w0, round, shift, offset); }
+extern "C" void x265b200_weight_sp(x265b200_ctx* ctx, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset)
+{ if (ctx) host_weight(ctx, 1, src, dst, srcStride, dstStride, width, height, w0, round, shift, offset); }

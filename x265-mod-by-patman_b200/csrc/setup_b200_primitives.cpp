@@ -65,6 +65,8 @@ template<int W, int H> void t_pixelavg(pixel* d, intptr_t ds, const pixel* a, in
 template<int W, int H> void t_addAvg(const int16_t* a, const int16_t* b, pixel* d, intptr_t sa, intptr_t sb, intptr_t ds) { x265b200_addAvg(g_b200, W, H, a, b, d, sa, sb, ds); }
 template<int W> void t_integral_h(uint32_t* sum, pixel* pix, intptr_t stride) { x265b200_integral_inith(g_b200, W, sum, pix, stride); }
 template<int H> void t_integral_v(uint32_t* sum, intptr_t stride) { x265b200_integral_initv(g_b200, H, sum, stride); }
+void t_weight_pp(const pixel* s, pixel* d, intptr_t st, int w, int h, int w0, int rnd, int sh, int off) { x265b200_weight_pp(g_b200, s, d, st, w, h, w0, rnd, sh, off); }
+void t_weight_sp(const int16_t* s, pixel* d, intptr_t ss, intptr_t ds, int w, int h, int w0, int rnd, int sh, int off) { x265b200_weight_sp(g_b200, s, d, ss, ds, w, h, w0, rnd, sh, off); }
 void t_lowres(const pixel* s, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr_t ss, intptr_t ds, int w, int h) { x265b200_frame_init_lowres(g_b200, s, d0, dh, dv, dc, ss, ds, w, h); }
 
 template<int W, int H> void lumaPU(EncoderPrimitives::PU& pu)
@@ -153,6 +155,7 @@ void setupB200Primitives(EncoderPrimitives& p)
     p.quant = t_quant;  p.nquant = t_nquant;
     p.dequant_normal = t_dequant_normal;  p.dequant_scaling = t_dequant_scaling;
     p.frameInitLowres = t_lowres;
+    p.weight_pp = t_weight_pp;  p.weight_sp = t_weight_sp;
     p.integral_inith[INTEGRAL_4] = t_integral_h<4>;   p.integral_initv[INTEGRAL_4] = t_integral_v<4>;
     p.integral_inith[INTEGRAL_8] = t_integral_h<8>;   p.integral_initv[INTEGRAL_8] = t_integral_v<8>;
     p.integral_inith[INTEGRAL_12] = t_integral_h<12>; p.integral_initv[INTEGRAL_12] = t_integral_v<12>;
