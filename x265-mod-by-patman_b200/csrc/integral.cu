@@ -10,7 +10,7 @@
 // the whole-plane entry writes 0 there.
 //
 // Whole-plane kernel: a CTA owns a 64 x 32 tile of outputs, builds the 2-D inclusive prefix sum of the 96 x 64 pixels the
-// tile's largest box (32 x 32) can reach in shared memory (row scans by warp shuffles, column scans one thread per column),
+// tile's largest box (32 x 32) can reach in shared memory (row and column scans by warp shuffles),
 // and then emits all TWELVE planes from it with four shared-memory reads per value: the picture is read once.
 #include "internal.h"
 
@@ -25,7 +25,8 @@ me_integral_kernel(const T* __restrict__ pix, intptr_t stride, int rows, size_t 
                    uint32_t* __restrict__ sums, size_t planePitch, size_t frameSums)
 {
     constexpr int TX = 64, TY = 32, PW = TX + 32, PH = TY + 32;
-    __shared__ uint32_t P[PH + 1][PW + 1];
+    constexpr int PP = PW + 4;                        // row pitch: a multiple of four words so that quads of prefix values load as one LDS.128
+    __shared__ __align__(16) uint32_t P[PH + 1][PP];
     const int x0 = blockIdx.x * TX, r0 = blockIdx.y * TY;
     const T* src = pix + (size_t)blockIdx.z * framePixels;
     uint32_t* dst = sums + (size_t)blockIdx.z * frameSums;
@@ -59,26 +60,54 @@ me_integral_kernel(const T* __restrict__ pix, intptr_t stride, int rows, size_t 
         }
     }
     __syncthreads();
-    // column-wise scans: one thread per column
-    if (tid < PW)
+    // column-wise inclusive scans, again by warp shuffles: lane = row inside a 32-row chunk, warp w takes columns w, w + 8, ...
+    for (int c = warp; c < PW; c += 8)
     {
-        uint32_t run = 0;
-        for (int j = 1; j <= PH; j++) { run += P[j][tid + 1]; P[j][tid + 1] = run; }
+        uint32_t carry = 0;
+#pragma unroll
+        for (int j0 = 0; j0 < PH; j0 += 32)
+        {
+            uint32_t v = P[j0 + 1 + lane][c + 1];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += u;
+            }
+            v += carry;
+            P[j0 + 1 + lane][c + 1] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
     }
     __syncthreads();
     for (int k = 0; k < 12; k++)
     {
         const int W = c_intW[k], H = c_intH[k];
         uint32_t* out = dst + (size_t)k * planePitch;
-        for (int i = tid; i < TX * TY; i += 256)
+        // four adjacent outputs per thread: box(x) = P[y+H][x+W] - P[y][x+W] - P[y+H][x] + P[y][x], x and x + W multiples of 4
+        for (int i = tid; i < (TX / 4) * TY; i += 256)
         {
-            int y = i / TX, x = i - y * TX;
+            int y = i / (TX / 4), x = (i - y * (TX / 4)) * 4;
             int gx = x0 + x, gr = r0 + y;
             if (gx >= stride || gr >= rows) continue;
-            uint32_t v = 0;
-            if (gr >= 1 && gr <= rows - 1 - H && gx < stride - W)
-                v = P[y + H][x + W] - P[y][x + W] - P[y + H][x] + P[y][x];
-            out[(size_t)gr * stride + gx] = v;
+            uint4 a = *(const uint4*)&P[y + H][x + W], b = *(const uint4*)&P[y][x + W];
+            uint4 c = *(const uint4*)&P[y + H][x], d = *(const uint4*)&P[y][x];
+            bool rowOk = gr >= 1 && gr <= rows - 1 - H;
+            int lim = (int)stride - W;                   // columns gx < lim are defined
+            uint4 v;
+            v.x = rowOk && gx + 0 < lim ? a.x - b.x - c.x + d.x : 0u;
+            v.y = rowOk && gx + 1 < lim ? a.y - b.y - c.y + d.y : 0u;
+            v.z = rowOk && gx + 2 < lim ? a.z - b.z - c.z + d.z : 0u;
+            v.w = rowOk && gx + 3 < lim ? a.w - b.w - c.w + d.w : 0u;
+            uint32_t* o = out + (size_t)gr * stride + gx;
+            if (gx + 3 < stride && (((uintptr_t)o) & 15) == 0) *(uint4*)o = v;
+            else
+            {
+                o[0] = v.x;
+                if (gx + 1 < stride) o[1] = v.y;
+                if (gx + 2 < stride) o[2] = v.z;
+                if (gx + 3 < stride) o[3] = v.w;
+            }
         }
     }
 }
