@@ -45,7 +45,7 @@ int main(int argc, char** argv)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void*)vars[v].k));
         printf("variant %d: %-28s regs %d\n", v, vars[v].name, fa.numRegs);
     }
-    int shapes[][2] = { {64, 64}, {64, 32}, {32, 32}, {32, 16}, {16, 16}, {16, 8}, {8, 16}, {8, 8}, {8, 4} };
+    int shapes[][2] = { {64, 64}, {32, 32}, {16, 32}, {16, 16}, {16, 8}, {8, 16}, {8, 8}, {8, 4}, {4, 8} };
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (auto& sh : shapes)
     {
@@ -101,6 +101,33 @@ int main(int argc, char** argv)
                 for (int i = 0; i < n; i++) if (h0[i] != h1[i]) { same = false; break; }
             }
             printf("   v%d %-28s %.4f ms  %.0f GB/s  %.2f of roofline %s\n", v, vars[v].name, best, bytes / best / 1e6, bytes / best / 1e6 / 6534.8, same ? "" : "MISMATCH");
+        }
+
+        // 8x4-strip variants with 16-byte chunk loads (narrow blocks)
+        if (w <= 16)
+        {
+            int S = (w / 8) * (h / 4);
+            for (int Gs = 1; Gs <= S && Gs <= 32; Gs <<= 1)
+            {
+                long long threads = (long long)n * Gs;
+                int grid = (int)((threads + 127) / 128);
+                float best = 1e9f;
+                for (int rep = 0; rep < 3; rep++)
+                {
+                    strip8_fast_kernel<OP_SATD, int, int32_t><<<grid, 128>>>(A, stride, B, stride, dOA, dOB, 1, n, w, h, Gs, out);
+                    CK(cudaEventRecord(e0));
+                    for (int k = 0; k < 6; k++) strip8_fast_kernel<OP_SATD, int, int32_t><<<grid, 128>>>(A, stride, B, stride, dOA, dOB, 1, n, w, h, Gs, out);
+                    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                    ms /= 6;
+                    if (ms < best) best = ms;
+                }
+                CK(cudaGetLastError());
+                CK(cudaMemcpy(h0.data(), out0, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h1.data(), out, n * 4, cudaMemcpyDeviceToHost));
+                int bad = 0;
+                for (int i = 0; i < n; i++) if (h0[i] != h1[i]) bad++;
+                printf("   strip8x4 v16 loads, G = %2d lanes/block  %.4f ms  %.0f GB/s  %.2f of roofline %s\n", Gs, best, bytes / best / 1e6, bytes / best / 1e6 / 6534.8, bad ? "MISMATCH" : "");
+            }
         }
 
         // TMA-staged variants: jobBytes per plane per stage, stages, warps per CTA, L2 promotion

@@ -333,6 +333,43 @@ __device__ __forceinline__ void load_rows8(const uint8_t* p, intptr_t stride, ui
     }
 }
 
+// Four rows of eight samples through 16-byte aligned chunk loads (narrow blocks: a row of an 8-wide block is 16 bytes at an
+// arbitrary 2-byte offset, i.e. it lies inside two aligned 16-byte chunks = at most two 32-byte sectors; 8-byte chunk loads
+// touch the same sectors with three instructions).  stride % 8 == 0, 16-bit samples.  The per-lane sample offset (0..7)
+// is resolved with two select stages (word offset bits 1 and 0) and one funnel shift per word.
+__device__ __forceinline__ void load_rows8_v16(const uint16_t* p, intptr_t stride, uint32_t (&w)[4][4])
+{
+    uintptr_t a = (uintptr_t)p;
+    int s = (int)(a >> 1) & 7;
+    const uint4* base = (const uint4*)(a & ~(uintptr_t)15);
+    intptr_t cs = stride >> 3;
+    uint4 q0[4], q1[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) q0[r] = __ldg(base + r * cs);
+    if (s)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) q1[r] = __ldg(base + r * cs + 1);
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) q1[r] = make_uint4(0, 0, 0, 0);
+    }
+    int sh = (s & 1) << 4;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        uint32_t c0 = q0[r].x, c1 = q0[r].y, c2 = q0[r].z, c3 = q0[r].w, c4 = q1[r].x, c5 = q1[r].y, c6 = q1[r].z, c7 = q1[r].w;
+        if (s & 4) { c0 = c2; c1 = c3; c2 = c4; c3 = c5; c4 = c6; c5 = c7; }
+        if (s & 2) { c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; }
+        w[r][0] = __funnelshift_r(c0, c1, sh);
+        w[r][1] = __funnelshift_r(c1, c2, sh);
+        w[r][2] = __funnelshift_r(c2, c3, sh);
+        w[r][3] = __funnelshift_r(c3, c4, sh);
+    }
+}
+
 // eight int16 (four packed words) to `d`, with the widest stores its alignment allows
 __device__ __forceinline__ void store8_s16(int16_t* d, const uint32_t (&w)[4])
 {

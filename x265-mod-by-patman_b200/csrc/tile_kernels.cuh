@@ -130,4 +130,44 @@ tile4_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B,
     if (live && l == 0) out[blk] = (OUT)acc;
 }
 
+// Narrow blocks (w = 8 or 16, 16-bit samples, strides % 8 == 0): thread = 8x4 strip loaded with 16-byte chunk loads
+// (device_util.cuh load_rows8_v16), two 4x4 tiles per strip; G lanes (power of two, the strips of one block) reduce together.
+template<int OP, typename ACC, typename OUT>
+__global__ void __launch_bounds__(128)
+strip8_fast_kernel(const uint16_t* __restrict__ A, intptr_t sa, const uint16_t* __restrict__ B, intptr_t sb,
+                   const int32_t* __restrict__ offA, const int32_t* __restrict__ offB, int kdiv,
+                   int n, int w, int h, int G, OUT* __restrict__ out)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lg = __ffs(G) - 1;
+    int blk = (int)(gid >> lg);
+    int l = (int)gid & (G - 1);
+    bool live = blk < n;
+    int sw = w >> 3;
+    int S = sw * (h >> 2);
+    ACC acc = 0;
+    if (live)
+    {
+        const uint16_t* a = A + offA[kdiv > 1 ? blk / kdiv : blk];
+        const uint16_t* b = B + offB[blk];
+        for (int t = l; t < S; t += G)
+        {
+            int sx = (t % sw) << 3, sy = (t / sw) << 2;
+            uint32_t wa[4][4], wb[4][4];
+            load_rows8_v16(a + (intptr_t)sy * sa + sx, sa, wa);
+            load_rows8_v16(b + (intptr_t)sy * sb + sx, sb, wb);
+            uint32_t alo[4], ahi[4], blo[4], bhi[4];
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+            {
+#pragma unroll
+                for (int r = 0; r < 4; r++) { alo[r] = wa[r][2 * half]; ahi[r] = wa[r][2 * half + 1]; blo[r] = wb[r][2 * half]; bhi[r] = wb[r][2 * half + 1]; }
+                tile4_accumulate<OP, ACC>(alo, ahi, blo, bhi, acc);
+            }
+        }
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) out[blk] = (OUT)acc;
+}
+
 } // namespace b200

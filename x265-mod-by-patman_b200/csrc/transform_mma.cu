@@ -272,7 +272,8 @@ __device__ __forceinline__ int recombine(int hi, int lo, int shift) { return ((h
 
 // persistent warps: each warp keeps the 16 A-fragment registers of both stages resident and walks
 // 32x32 TUs with a grid stride; the next TU's rows are requested before the current one is transformed.
-__global__ void __launch_bounds__(128)
+template<int MINB>
+__global__ void __launch_bounds__(128, MINB)
 dct32_imma_kernel(const int16_t* __restrict__ src, intptr_t srcStride, const int32_t* __restrict__ off, int n,
                   int16_t* __restrict__ dst, int shift1, int shift2)
 {
@@ -842,7 +843,8 @@ bool launch_dct_imma(x265b200_ctx* ctx, int N, const int16_t* src, intptr_t srcS
     {
         int grid = sms * 8;
         if (grid > ceil_div(n, 4)) grid = ceil_div(n, 4);
-        dct32_imma_kernel<<<grid, 128, 0, st>>>(src, srcStride, off, n, dst, shift1, shift2);
+        // 5 resident CTAs per SM (96 registers, no spills): 6 / 7 / 8 spill and measured 10 / 23 / 27 % slower
+        dct32_imma_kernel<5><<<grid, 128, 0, st>>>(src, srcStride, off, n, dst, shift1, shift2);
     }
     else if (N == 16)
     {
