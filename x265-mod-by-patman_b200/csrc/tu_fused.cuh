@@ -730,28 +730,32 @@ static void launch_tu_fwd(int sms, int N, const T* fenc, intptr_t sf, const T* p
                           const int32_t* quantCoeff, QuantP P, int shift1, int shift2, int16_t* qCoef, uint32_t* numSig,
                           unsigned long long* sseZero, cudaStream_t st)
 {
-    int grid = sms * 8;
+    int grid;
     if (N == 32)
     {
         // 4 resident CTAs per SM (106 registers): forcing 5 or 6 spills and measured 20-45 % slower
+        grid = PGRID((tu_fwd32_kernel<T, 4>));
         if (grid > ceil_div(n, 4)) grid = ceil_div(n, 4);
         tu_fwd32_kernel<T, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
     }
     else if (N == 16)
     {
         int need = ceil_div(ceil_div(n, 4), 4);
+        grid = PGRID((tu_fwd16_kernel<T, 4>));
         if (grid > need) grid = need;
         tu_fwd16_kernel<T, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
     }
     else if (N == 8)
     {
         int need = ceil_div(ceil_div(n, 2 * 4), 4);
+        grid = PGRID((tu_fwd_small_kernel<T, 8, 4>));
         if (grid > need) grid = need;
         tu_fwd_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
     }
     else
     {
         int need = ceil_div(ceil_div(n, 8 * 4), 4);
+        grid = PGRID((tu_fwd_small_kernel<T, 4, 4>));
         if (grid > need) grid = need;
         tu_fwd_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
     }
@@ -762,27 +766,31 @@ static void launch_tu_inv(int sms, int N, const int16_t* qCoef, const uint32_t* 
                           const T* pred, intptr_t sp, const int32_t* offF, const int32_t* offP, T* recon, intptr_t sr, const int32_t* offR,
                           unsigned long long* sseRecon, int shift1, int shift2, int depth, cudaStream_t st)
 {
-    int grid = sms * 8;
+    int grid;
     if (N == 32)
     {
+        grid = PGRID((tu_inv32_kernel<T, 4>));
         if (grid > ceil_div(n, 4)) grid = ceil_div(n, 4);
         tu_inv32_kernel<T, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
     }
     else if (N == 16)
     {
         int need = ceil_div(ceil_div(n, 4), 4);
+        grid = PGRID((tu_inv16_kernel<T, 4>));
         if (grid > need) grid = need;
         tu_inv16_kernel<T, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
     }
     else if (N == 8)
     {
         int need = ceil_div(ceil_div(n, 2 * 4), 4);
+        grid = PGRID((tu_inv_small_kernel<T, 8, 4>));
         if (grid > need) grid = need;
         tu_inv_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
     }
     else
     {
         int need = ceil_div(ceil_div(n, 8 * 4), 4);
+        grid = PGRID((tu_inv_small_kernel<T, 4, 4>));
         if (grid > need) grid = need;
         tu_inv_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
     }
