@@ -337,7 +337,7 @@ def run_b200_arm(args):
         # dram__bytes_read + write per launch of this kernel from the committed ncu --set full capture of this workload
         tj = json.load(open(tp))
         traffic = tj["dram_bytes_per_launch_avg"] if tj.get("frames_per_launch") == F else None
-    roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
+    roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (10 shapes) + strip8_fast_kernel<SATD> (8x4, 16x8) (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": satd_bytes if dominant == "satd" else dct_bytes,
                 "peak_source": peak_src,
