@@ -50,7 +50,7 @@ def test_sad_multi_and_ragged(torch_mod):
     geo = Geometry(256, 128)
     A = make_plane(geo, depth, 1); B = make_plane(geo, depth, 2)
     dA, dB = dev(A.view(np.int16)), dev(B.view(np.int16))
-    for (w, h), K in (((16, 16), 4), ((8, 8), 3), ((64, 32), 9), ((12, 16), 5)):
+    for (w, h), K in (((16, 16), 4), ((8, 8), 3), ((64, 32), 9), ((12, 16), 5), ((8, 4), 4), ((16, 8), 3)):   # last two: strip kernel
         offA, offB0 = tile_blocks(geo, w, h, seed=5)
         n = len(offA)
         offR = np.stack([offB0 + k * 3 - (k % 2) * geo.stride for k in range(K)], axis=1).astype(np.int32).ravel()
@@ -62,6 +62,14 @@ def test_sad_multi_and_ragged(torch_mod):
     e = torch.zeros(0, dtype=torch.int32, device="cuda")
     ctx.pixelcmp_batch(OP_SATD, 8, 8, dA, geo.stride, dB, geo.stride, e, e, e)
     # n = 1 and n not a multiple of the lane-group packing
+    for (w, h) in ((8, 4), (16, 8)):                     # strip kernel: ragged counts, SAD / SATD / SSE
+        offA, offB = tile_blocks(geo, w, h, seed=11)
+        for n in (1, 5, 130):
+            for op, dt in ((OP_SAD, torch.int32), (OP_SATD, torch.int32), (3, torch.int64)):
+                out = torch.zeros(n, dtype=dt, device="cuda")
+                ctx.pixelcmp_batch(op, w, h, dA, geo.stride, dB, geo.stride, dev(offA[:n].copy()), dev(offB[:n].copy()), out)
+                ref = orc.pixelcmp_batch(op, w, h, A, geo.stride, B, geo.stride, offA[:n].copy(), offB[:n].copy())
+                assert np.array_equal(out.cpu().numpy().astype(np.uint64), np.asarray(ref).astype(np.uint64)), (w, h, n, op)
     for n in (1, 3, 33):
         offA, offB = tile_blocks(geo, 8, 8, seed=9)
         out = torch.zeros(n, dtype=torch.int32, device="cuda")
