@@ -195,6 +195,13 @@ int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* 
                            const void* B, intptr_t strideB, const int32_t* offB, void* D, intptr_t strideD, const int32_t* offD,
                            int n, x265b200_stream stream);
 
+/* copy family over n blocks of w x h (offset arrays may be NULL = contiguous blocks).  kind: 0 copy_pp (pixel.cpp:751-762),
+ * 1 copy_ss, 2 copy_sp ((pixel) cast), 3 copy_ps (pixel.cpp:764-804), 4 blockfill_s (param = value, src unused; pixel.cpp:385-391),
+ * 5 shift left: (int16)((uint32)x << param) = cpy2Dto1D_shl / cpy1Dto2D_shl (pixel.cpp:393-408, 428-443; the 1-D side uses
+ * stride = w), 6 rounding shift right: (x + (1 << (param - 1))) >> param = cpy2Dto1D_shr / cpy1Dto2D_shr (pixel.cpp:410-461). */
+int x265b200_blockcopy_batch(x265b200_ctx* ctx, int kind, int w, int h, const void* src, intptr_t srcStride, const int32_t* offS,
+                             void* dst, intptr_t dstStride, const int32_t* offD, int n, int param, x265b200_stream stream);
+
 /* downscale_t frameInitLowres (pixel.cpp:595-620) over one plane: width x height are the LOWRES dimensions; reads
  * 2 * width + 1 columns of 2 * height + 1 rows of src, writes the four half-resolution planes. */
 int x265b200_lowres_batch(x265b200_ctx* ctx, const void* src, intptr_t srcStride, void* dst0, void* dsth, void* dstv, void* dstc,
@@ -253,6 +260,8 @@ void x265b200_pixelavg_pp(x265b200_ctx*, int w, int h, void* dst, intptr_t dstri
 void x265b200_addAvg(x265b200_ctx*, int w, int h, const int16_t* src0, const int16_t* src1, void* dst, intptr_t src0Stride, intptr_t src1Stride, intptr_t dstStride);
 void x265b200_frame_init_lowres(x265b200_ctx*, const void* src0, void* dst0, void* dsth, void* dstv, void* dstc,
                                 intptr_t srcStride, intptr_t dstStride, int width, int height);
+/* copy_pp/ss/sp/ps, blockfill_s, cpy2Dto1D_shl/shr, cpy1Dto2D_shl/shr (primitives.h:141-150, 184-187); kind as in x265b200_blockcopy_batch */
+void x265b200_blockcopy(x265b200_ctx*, int kind, int w, int h, void* dst, intptr_t dstStride, const void* src, intptr_t srcStride, int param);
 /* integralh_t / integralv_t (primitives.h:227-228) with the box width / height prepended */
 void x265b200_weight_pp(x265b200_ctx*, const void* src, void* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset);
 void x265b200_weight_sp(x265b200_ctx*, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset);

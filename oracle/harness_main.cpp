@@ -86,13 +86,21 @@ static int coverage()
     want = bound = missing = same = extra = 0;
     for (int i = 0; i < NUM_PU_SIZES; i++)
     {
-        SLOT(pu[i].pixelavg_pp[0]); SLOT(pu[i].pixelavg_pp[1]); SLOT(pu[i].addAvg[0]); SLOT(pu[i].addAvg[1]);
-        for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].pu[i].addAvg[0]); SLOT(chroma[c].pu[i].addAvg[1]); }
+        SLOT(pu[i].pixelavg_pp[0]); SLOT(pu[i].pixelavg_pp[1]); SLOT(pu[i].addAvg[0]); SLOT(pu[i].addAvg[1]); SLOT(pu[i].copy_pp);
+        for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].pu[i].addAvg[0]); SLOT(chroma[c].pu[i].addAvg[1]); SLOT(chroma[c].pu[i].copy_pp); }
     }
     for (int i = 0; i < NUM_CU_SIZES; i++)
     {
         SLOT(cu[i].sub_ps); SLOT(cu[i].add_ps[0]); SLOT(cu[i].add_ps[1]);
+        SLOT(cu[i].blockfill_s[0]); SLOT(cu[i].blockfill_s[1]); SLOT(cu[i].calcresidual[0]); SLOT(cu[i].calcresidual[1]);
+        SLOT(cu[i].cpy2Dto1D_shl); SLOT(cu[i].cpy2Dto1D_shr); SLOT(cu[i].cpy1Dto2D_shl[0]); SLOT(cu[i].cpy1Dto2D_shl[1]); SLOT(cu[i].cpy1Dto2D_shr);
         for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].sub_ps); SLOT(chroma[c].cu[i].add_ps[0]); SLOT(chroma[c].cu[i].add_ps[1]); }
+#if HIGH_BIT_DEPTH
+        aliasOK = true;     /* copy_ps/sp/ss (and the cu copy_pp alias) are shared trampolines onto pu[].copy_pp at HBD (primitives.cpp:106-168) */
+#endif
+        SLOT(cu[i].copy_ss); SLOT(cu[i].copy_sp); SLOT(cu[i].copy_ps); SLOT(cu[i].copy_pp);
+        for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].copy_ss); SLOT(chroma[c].cu[i].copy_sp); SLOT(chroma[c].cu[i].copy_ps); SLOT(chroma[c].cu[i].copy_pp); }
+        aliasOK = false;
     }
     SLOT(frameInitLowres); SLOT(weight_pp); SLOT(weight_sp);
     for (int i = 0; i < NUM_INTEGRAL_SIZE; i++) { SLOT(integral_inith[i]); SLOT(integral_initv[i]); }

@@ -438,4 +438,34 @@ void ref_weight_cost(const pixel* fenc, const pixel* ref, intptr_t stride, int w
     }
 }
 
+
+/* ---- copy family through the reference table: luma cu[] slots for square sizes, pu[].copy_pp for any luma PU ---- */
+int ref_blockcopy(int kind, int w, int h, void* dst, intptr_t ds, const void* src, intptr_t ss, int param)
+{
+    ensure();
+    if (kind == 0)
+    {
+        int p = lumaPart(w, h);
+        if (p < 0) return -1;
+        g_c.pu[p].copy_pp((pixel*)dst, ds, (const pixel*)src, ss);
+        return 0;
+    }
+    int cu = -1;
+    for (int i = 0; i < NUM_CU_SIZES; i++) if ((4 << i) == w) cu = i;
+    if (w != h || cu < 0) return -1;
+    switch (kind)
+    {
+    case 1: g_c.cu[cu].copy_ss((int16_t*)dst, ds, (const int16_t*)src, ss); break;
+    case 2: g_c.cu[cu].copy_sp((pixel*)dst, ds, (const int16_t*)src, ss); break;
+    case 3: g_c.cu[cu].copy_ps((int16_t*)dst, ds, (const pixel*)src, ss); break;
+    case 4: g_c.cu[cu].blockfill_s[NONALIGNED]((int16_t*)dst, ds, (int16_t)param); break;
+    case 5: if (ds == w) g_c.cu[cu].cpy2Dto1D_shl((int16_t*)dst, (const int16_t*)src, ss, param);
+            else if (ss == w) g_c.cu[cu].cpy1Dto2D_shl[NONALIGNED]((int16_t*)dst, (const int16_t*)src, ds, param); else return -1; break;
+    case 6: if (ds == w) g_c.cu[cu].cpy2Dto1D_shr((int16_t*)dst, (const int16_t*)src, ss, param);
+            else if (ss == w) g_c.cu[cu].cpy1Dto2D_shr((int16_t*)dst, (const int16_t*)src, ds, param); else return -1; break;
+    default: return -1;
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -846,3 +846,30 @@ EXPORT void orc_weight_cost(const pixel* fenc, const pixel* ref, intptr_t stride
         cost[k] = c;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Copy family (pixel.cpp:385-461, 751-804).  kind: 0 copy_pp, 1 copy_ss, 2 copy_sp, 3 copy_ps, 4 blockfill_s (param = value),
+ * 5 shift left (cpy2Dto1D_shl / cpy1Dto2D_shl), 6 rounding shift right (cpy2Dto1D_shr / cpy1Dto2D_shr).
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void orc_blockcopy(int kind, int w, int h, void* dst, intptr_t ds, const void* src, intptr_t ss, int param)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            switch (kind)
+            {
+            case 0: ((pixel*)dst)[y * ds + x] = ((const pixel*)src)[y * ss + x]; break;
+            case 1: ((int16_t*)dst)[y * ds + x] = ((const int16_t*)src)[y * ss + x]; break;
+            case 2: ((pixel*)dst)[y * ds + x] = (pixel)((const int16_t*)src)[y * ss + x]; break;
+            case 3: ((int16_t*)dst)[y * ds + x] = (int16_t)((const pixel*)src)[y * ss + x]; break;
+            case 4: ((int16_t*)dst)[y * ds + x] = (int16_t)param; break;
+            case 5: ((int16_t*)dst)[y * ds + x] = (int16_t)((uint32_t)((const int16_t*)src)[y * ss + x] << param); break;
+            default: ((int16_t*)dst)[y * ds + x] = (int16_t)((((const int16_t*)src)[y * ss + x] + (int16_t)(1 << (param - 1))) >> param); break;
+            }
+}
+EXPORT void orc_blockcopy_batch(int kind, int w, int h, const void* src, intptr_t ss, const int32_t* offS, void* dst, intptr_t ds,
+                                const int32_t* offD, int n, int param)
+{
+    const size_t es = (kind == 0 || kind == 3) ? sizeof(pixel) : 2, ed = (kind == 0 || kind == 2) ? sizeof(pixel) : 2;
+    for (int i = 0; i < n; i++)
+        orc_blockcopy(kind, w, h, (char*)dst + (size_t)offD[i] * ed, ds, kind == 4 ? NULL : (const char*)src + (size_t)offS[i] * es, ss, param);
+}

@@ -135,6 +135,10 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- copy family (kind 0..6, see include/x265b200.h x265b200_blockcopy_batch) -------------------------------
+    def blockcopy(self, kind, w, h, dst, od, ds, src, os_, ss, param=0):
+        return self._f("blockcopy")(kind, w, h, _ptr(dst, od), C.c_ssize_t(ds), _ptr(src, os_) if src is not None else None, C.c_ssize_t(ss), param)
+
     # ---- weighted prediction + lookahead weight cost -----------------------------------------------------------
     def weight_pp(self, src, osrc, dst, odst, stride, width, height, w0, rnd, shift, offset):
         self._f("weight_pp", None)(_ptr(src, osrc), _ptr(dst, odst), C.c_ssize_t(stride), width, height, w0, rnd, shift, offset)
@@ -250,6 +254,10 @@ class Oracle(_Base):
                                         _ptr(qc), qbits, add, dqscale, dqshift, _ptr(q), _ptr(ns), _ptr(recon), C.c_ssize_t(sr),
                                         _ptr(offR), _ptr(z), _ptr(r))
         return q, ns, z, r
+
+    def blockcopy_batch(self, kind, w, h, S, ss, offS, D, sd, offD, param=0):
+        self._f("blockcopy_batch", None)(kind, w, h, _ptr(S) if S is not None else None, C.c_ssize_t(ss), _ptr(offS), _ptr(D), C.c_ssize_t(sd), _ptr(offD), len(offD), param)
+        return D
 
     def subpel_cmp_batch(self, op, w, h, fenc, sf, ref, sr, offF, offR, frac, K):
         n = len(offF)

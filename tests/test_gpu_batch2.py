@@ -394,3 +394,33 @@ def test_weight_and_weight_cost_batches(depth):
         ctx.weight_cost_batch(dev(pix_view(fenc, depth)), dev(pix_view(ref, depth)), stride, W, H, dev(ic) if ic is not None else None, dev(weights), K, cost)
         assert np.array_equal(cost.cpu().numpy().view(np.uint32), want)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_blockcopy_batch(depth):
+    """copy family over descriptor batches vs the oracle (odd chroma shapes, misaligned offsets, NULL offset arrays)"""
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(500 + depth)
+    stride, rows, n = 200, 160, 45
+    N = stride * rows
+    pix = rng.integers(0, orc.pmax + 1, N).astype(orc.pix)
+    s16 = rng.integers(-32768, 32768, N).astype(np.int16)
+    s16pix = rng.integers(0, orc.pmax + 1, N).astype(np.int16)
+    for kind, src, dt, param in ((0, pix, orc.pix, 0), (1, s16, np.int16, 0), (2, s16pix, orc.pix, 0), (3, pix, np.int16, 0), (4, None, np.int16, -77),
+                                 (5, s16, np.int16, 3), (6, s16, np.int16, 5)):
+        for (w, h) in ((64, 64), (32, 8), (12, 16), (6, 8), (2, 4), (4, 4)):
+            offS = (rng.integers(0, rows - h, n) * stride + rng.integers(0, stride - w, n)).astype(np.int32)
+            per_row = stride // 64
+            ND = stride * 64 * ((n + per_row - 1) // per_row) + 64
+            cells = rng.permutation(n)
+            offD = ((cells // per_row) * 64 * stride + (cells % per_row) * 64 + rng.integers(0, min(3, 64 - w + 1), n)).astype(np.int32)
+            want = orc.blockcopy_batch(kind, w, h, src, stride, offS, np.full(ND, 7, dt), stride, offD, param)
+            dS = dev(pix_view(src, depth) if src is not None and src.dtype == np.uint16 else src) if src is not None else None
+            dD = dev(np.full(ND, 7, dt).view(np.int16) if np.dtype(dt) == np.uint16 else np.full(ND, 7, dt))
+            ctx.blockcopy_batch(kind, w, h, dS, stride, dev(offS), dD, stride, dev(offD), n, param)
+            got = dD.cpu().numpy()
+            got = got.view(np.uint16) if np.dtype(dt) == np.uint16 else got
+            assert np.array_equal(got, want), (kind, w, h)
+    ctx.check()

@@ -397,3 +397,29 @@ def test_weighted_prediction(libs):
     weights = np.array([0, 0, -1, 0] + [64, 32 << corr, 6 + corr, 0] + [85, 32 << corr, 6 + corr, 3 << (D - 8)] + [43, 16 << corr, 5 + corr, -2 << (D - 8)], np.int32)
     for ic in (intra, None):
         assert np.array_equal(o.weight_cost(fenc, 0, ref, 0, stride, W, H, ic, weights), r.weight_cost(fenc, 0, ref, 0, stride, W, H, ic, weights))
+
+
+def test_copy_family(libs):
+    """copy_pp/ss/sp/ps, blockfill_s, cpy2Dto1D_shl/shr, cpy1Dto2D_shl/shr vs the reference slots"""
+    o, r = libs
+    rng = np.random.default_rng(61)
+    stride, rows = 100, 100
+    n = stride * rows
+    pix = rng.integers(0, o.pmax + 1, n).astype(o.pix)
+    s16 = rng.integers(-32768, 32768, n).astype(np.int16)
+    s16pix = rng.integers(0, o.pmax + 1, n).astype(np.int16)            # copy_sp inputs are pixel-valued (pixel.cpp:784)
+    for (w, h) in LUMA_PU:
+        a = np.full(n, 7, o.pix); b = a.copy()
+        o.blockcopy(0, w, h, a, 3, stride, pix, 11, 97); assert r.blockcopy(0, w, h, b, 3, stride, pix, 11, 97) == 0
+        assert np.array_equal(a, b), (w, h)
+    for w in (4, 8, 16, 32, 64):
+        for kind, src, dt in ((1, s16, np.int16), (2, s16pix, o.pix), (3, pix, np.int16), (4, None, np.int16)):
+            a = np.full(n, 7, dt); b = a.copy()
+            o.blockcopy(kind, w, w, a, 3, stride, src, 11, 97, -1234); assert r.blockcopy(kind, w, w, b, 3, stride, src, 11, 97, -1234) == 0
+            assert np.array_equal(a, b), (kind, w)
+        for kind in (5, 6):
+            for shift in (1, 3, 6):
+                for (ds, ss) in ((w, 97), (stride, w)):                 # 2-D -> 1-D and 1-D -> 2-D
+                    a = np.full(n, 7, np.int16); b = a.copy()
+                    o.blockcopy(kind, w, w, a, 0, ds, s16, 8, ss, shift); assert r.blockcopy(kind, w, w, b, 0, ds, s16, 8, ss, shift) == 0
+                    assert np.array_equal(a, b), (kind, w, shift, ds)

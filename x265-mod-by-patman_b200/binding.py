@@ -46,7 +46,7 @@ def load_library():
             getattr(_lib, name).restype = C.c_uint32
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
                      "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
-                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp"):
+                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -150,6 +150,9 @@ class Context:
 
     def me_integral_batch(self, pix, stride, rows, nframes, sums, plane_pitch, stream=0):
         self._call("x265b200_me_integral_batch", _dp(pix), _ss(stride), int(rows), int(nframes), _dp(sums), C.c_size_t(int(plane_pitch)), C.c_void_p(stream))
+
+    def blockcopy_batch(self, kind, w, h, S, ss, offS, D, sd, offD, n, param=0, stream=0):
+        self._call("x265b200_blockcopy_batch", kind, w, h, _dp(S), _ss(ss), _dp(offS), _dp(D), _ss(sd), _dp(offD), int(n), int(param), C.c_void_p(stream))
 
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD, n, stream=0):
         self._call("x265b200_blockop_batch", op, w, h, _dp(A), _ss(sa), _dp(offA), _dp(B), _ss(sb), _dp(offB), _dp(D), _ss(sd), _dp(offD),

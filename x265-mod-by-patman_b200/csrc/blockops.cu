@@ -137,6 +137,31 @@ blockop_wide_kernel(const TA* __restrict__ A, intptr_t sa, const int32_t* __rest
     }
 }
 
+// copy family (pixel.cpp:386-461, 751-804): one thread per sample.  kind: 0 copy_pp, 1 copy_ss, 2 copy_sp ((pixel) cast),
+// 3 copy_ps, 4 blockfill_s (param = value), 5 shl ((int16)((uint32)x << param): cpy2Dto1D_shl / cpy1Dto2D_shl),
+// 6 shr ((x + (1 << (param - 1))) >> param: cpy2Dto1D_shr / cpy1Dto2D_shr)
+template<typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+blockcopy_kernel(int kind, const TS* __restrict__ S, intptr_t ss, const int32_t* __restrict__ offS, TD* __restrict__ D, intptr_t sd,
+                 const int32_t* __restrict__ offD, int n, int w, int h, int param)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int per = w * h;
+    int blk = (int)(gid / per);
+    if (blk >= n) return;
+    int r = (int)(gid - (long long)blk * per);
+    int y = r / w, x = r - y * w;
+    int v;
+    if (kind == 4) v = param;
+    else
+    {
+        v = (int)S[blk_off(offS, blk, per) + (intptr_t)y * ss + x];
+        if (kind == 5) v = (int)(int16_t)((uint32_t)v << param);
+        else if (kind == 6) v = (v + (int)(int16_t)(1 << (param - 1))) >> param;
+    }
+    D[blk_off(offD, blk, per) + (intptr_t)y * sd + x] = (TD)v;
+}
+
 // frame_init_lowres_core: one thread per lowres position (pixel.cpp:604-612; "slower than naive bilinear, but matches asm")
 template<typename T>
 __global__ void __launch_bounds__(256)
@@ -216,6 +241,29 @@ extern "C" int x265b200_lowres_batch(x265b200_ctx* ctx, const void* src, intptr_
         lowres_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, srcStride, (uint8_t*)dst0, (uint8_t*)dsth, (uint8_t*)dstv, (uint8_t*)dstc, dstStride, width, height);
     else
         lowres_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, srcStride, (uint16_t*)dst0, (uint16_t*)dsth, (uint16_t*)dstv, (uint16_t*)dstc, dstStride, width, height);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
+
+extern "C" int x265b200_blockcopy_batch(x265b200_ctx* ctx, int kind, int w, int h, const void* src, intptr_t ss, const int32_t* offS,
+                                        void* dst, intptr_t sd, const int32_t* offD, int n, int param, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 1 || h < 1 || w > 64 || h > 64 || n < 0 || kind < 0 || kind > 6 || ((kind == 5 || kind == 6) && (param < (kind == 6) || param > 15)))
+        return fail(ctx, X265B200_ERR_ARG, "blockcopy: bad shape / kind");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ceil_div((long long)n * w * h, 256);
+    const bool p8 = ctx->pixbytes == 1;
+#define BC(TS, TD) blockcopy_kernel<TS, TD><<<grid, 256, 0, st>>>(kind, (const TS*)src, ss, offS, (TD*)dst, sd, offD, n, w, h, param)
+    switch (kind)
+    {
+    case 0: if (p8) BC(uint8_t, uint8_t); else BC(uint16_t, uint16_t); break;
+    case 2: if (p8) BC(int16_t, uint8_t); else BC(int16_t, uint16_t); break;
+    case 3: if (p8) BC(uint8_t, int16_t); else BC(uint16_t, int16_t); break;
+    default: BC(int16_t, int16_t); break;
+    }
+#undef BC
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }

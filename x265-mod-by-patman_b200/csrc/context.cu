@@ -544,3 +544,25 @@ extern "C" void x265b200_weight_pp(x265b200_ctx* ctx, const void* src, void* dst
 { if (ctx) host_weight(ctx, 0, src, dst, stride, stride, width, height, w0, round, shift, offset); }
 extern "C" void x265b200_weight_sp(x265b200_ctx* ctx, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset)
 { if (ctx) host_weight(ctx, 1, src, dst, srcStride, dstStride, width, height, w0, round, shift, offset); }
+
+// ------------------------------------------------------------------ host entries: copy family (blockops.cu)
+
+extern "C" void x265b200_blockcopy(x265b200_ctx* ctx, int kind, int w, int h, void* dst, intptr_t dstStride, const void* src, intptr_t srcStride, int param)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const size_t pb = ctx->pixbytes;
+    const size_t sb = (kind == 0 || kind == 3) ? pb : 2, db = (kind == 0 || kind == 2) ? pb : 2;
+    size_t oS = c.alloc((size_t)w * h * sb);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc((size_t)w * h * db);
+    if (!c.ok()) return;
+    if (kind != 4)
+    {
+        pack(c.h<void>(oS), src, h, w * sb, srcStride * (intptr_t)sb);
+        if (!c.upload(0, inEnd)) return;
+    }
+    if (x265b200_blockcopy_batch(ctx, kind, w, h, c.d<void>(oS), w, nullptr, c.d<void>(oD), w, nullptr, 1, param, c.st()) != X265B200_OK) return;
+    if (!c.download(oD, (size_t)w * h * db)) return;
+    unpack(dst, c.h<void>(oD), h, w * db, dstStride * (intptr_t)db);
+}

@@ -63,6 +63,16 @@ template<int W, int H> void t_sub_ps(int16_t* d, intptr_t ds, const pixel* a, co
 template<int W, int H> void t_add_ps(pixel* d, intptr_t ds, const pixel* a, const int16_t* b, intptr_t sa, intptr_t sb) { x265b200_add_ps(g_b200, W, H, d, ds, a, b, sa, sb); }
 template<int W, int H> void t_pixelavg(pixel* d, intptr_t ds, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb, int wt) { x265b200_pixelavg_pp(g_b200, W, H, d, ds, a, sa, b, sb, wt); }
 template<int W, int H> void t_addAvg(const int16_t* a, const int16_t* b, pixel* d, intptr_t sa, intptr_t sb, intptr_t ds) { x265b200_addAvg(g_b200, W, H, a, b, d, sa, sb, ds); }
+template<int W, int H> void t_copy_pp(pixel* d, intptr_t ds, const pixel* a, intptr_t sa) { x265b200_blockcopy(g_b200, 0, W, H, d, ds, a, sa, 0); }
+template<int W, int H> void t_copy_ss(int16_t* d, intptr_t ds, const int16_t* a, intptr_t sa) { x265b200_blockcopy(g_b200, 1, W, H, d, ds, a, sa, 0); }
+template<int W, int H> void t_copy_sp(pixel* d, intptr_t ds, const int16_t* a, intptr_t sa) { x265b200_blockcopy(g_b200, 2, W, H, d, ds, a, sa, 0); }
+template<int W, int H> void t_copy_ps(int16_t* d, intptr_t ds, const pixel* a, intptr_t sa) { x265b200_blockcopy(g_b200, 3, W, H, d, ds, a, sa, 0); }
+template<int W> void t_blockfill(int16_t* d, intptr_t ds, int16_t val) { x265b200_blockcopy(g_b200, 4, W, W, d, ds, NULL, 0, val); }
+template<int W> void t_2Dto1D_shl(int16_t* d, const int16_t* a, intptr_t sa, int sh) { x265b200_blockcopy(g_b200, 5, W, W, d, W, a, sa, sh); }
+template<int W> void t_2Dto1D_shr(int16_t* d, const int16_t* a, intptr_t sa, int sh) { x265b200_blockcopy(g_b200, 6, W, W, d, W, a, sa, sh); }
+template<int W> void t_1Dto2D_shl(int16_t* d, const int16_t* a, intptr_t ds, int sh) { x265b200_blockcopy(g_b200, 5, W, W, d, ds, a, W, sh); }
+template<int W> void t_1Dto2D_shr(int16_t* d, const int16_t* a, intptr_t ds, int sh) { x265b200_blockcopy(g_b200, 6, W, W, d, ds, a, W, sh); }
+template<int W> void t_calcresidual(const pixel* f, const pixel* p, int16_t* r, intptr_t st) { x265b200_sub_ps(g_b200, W, W, r, st, f, p, st, st); }
 template<int W> void t_integral_h(uint32_t* sum, pixel* pix, intptr_t stride) { x265b200_integral_inith(g_b200, W, sum, pix, stride); }
 template<int H> void t_integral_v(uint32_t* sum, intptr_t stride) { x265b200_integral_initv(g_b200, H, sum, stride); }
 void t_weight_pp(const pixel* s, pixel* d, intptr_t st, int w, int h, int w0, int rnd, int sh, int off) { x265b200_weight_pp(g_b200, s, d, st, w, h, w0, rnd, sh, off); }
@@ -72,6 +82,7 @@ void t_lowres(const pixel* s, pixel* d0, pixel* dh, pixel* dv, pixel* dc, intptr
 template<int W, int H> void lumaPU(EncoderPrimitives::PU& pu)
 {
     pu.pixelavg_pp[NONALIGNED] = t_pixelavg<W, H>; pu.pixelavg_pp[ALIGNED] = t_pixelavg<W, H>;
+    pu.copy_pp = t_copy_pp<W, H>;
     pu.addAvg[NONALIGNED] = t_addAvg<W, H>; pu.addAvg[ALIGNED] = t_addAvg<W, H>;
     pu.sad = t_sad<W, H>; pu.sad_x3 = t_sad_x3<W, H>; pu.sad_x4 = t_sad_x4<W, H>; pu.ads = t_ads<W, H>; pu.satd = t_satd<W, H>;
     pu.luma_hpp = t_hpp<8, W, H>; pu.luma_hps = t_hps<8, W, H>; pu.luma_vpp = t_vpp<8, W, H>; pu.luma_vps = t_vps<8, W, H>;
@@ -86,6 +97,7 @@ template<int W, int H> void chromaPU(EncoderPrimitives::Chroma::PUChroma& pu)
     pu.filter_vsp = t_vsp<4, W, H>; pu.filter_vss = t_vss<4, W, H>;
     pu.p2s[NONALIGNED] = t_p2s<W, H>; pu.p2s[ALIGNED] = t_p2s<W, H>;
     pu.addAvg[NONALIGNED] = t_addAvg<W, H>; pu.addAvg[ALIGNED] = t_addAvg<W, H>;
+    pu.copy_pp = t_copy_pp<W, H>;
     pu.satd = (W % 4 == 0 && H % 4 == 0) ? (pixelcmp_t)t_satd<(W % 4 ? 4 : W), (H % 4 ? 4 : H)> : NULL;
 }
 
@@ -94,11 +106,21 @@ template<int W> void lumaCU(EncoderPrimitives::CU& cu)
     cu.sse_pp = t_sse_pp<W, W>; cu.sse_ss = t_sse_ss<W, W>; cu.sa8d = t_sa8d<W, W>;
     cu.ssd_s[NONALIGNED] = t_ssd_s<W>; cu.ssd_s[ALIGNED] = t_ssd_s<W>;
     cu.sub_ps = t_sub_ps<W, W>; cu.add_ps[NONALIGNED] = t_add_ps<W, W>; cu.add_ps[ALIGNED] = t_add_ps<W, W>;
+    cu.copy_ss = t_copy_ss<W, W>; cu.copy_sp = t_copy_sp<W, W>; cu.copy_ps = t_copy_ps<W, W>;
+    cu.blockfill_s[NONALIGNED] = t_blockfill<W>; cu.blockfill_s[ALIGNED] = t_blockfill<W>;
+    cu.calcresidual[NONALIGNED] = t_calcresidual<W>; cu.calcresidual[ALIGNED] = t_calcresidual<W>;
+}
+// the 1-D <-> 2-D coefficient copies (pixel.cpp:1081-1085, all five CU sizes)
+template<int W> void lumaTU(EncoderPrimitives::CU& cu)
+{
+    cu.cpy2Dto1D_shl = t_2Dto1D_shl<W>; cu.cpy2Dto1D_shr = t_2Dto1D_shr<W>;
+    cu.cpy1Dto2D_shl[NONALIGNED] = t_1Dto2D_shl<W>; cu.cpy1Dto2D_shl[ALIGNED] = t_1Dto2D_shl<W>; cu.cpy1Dto2D_shr = t_1Dto2D_shr<W>;
 }
 template<int W, int H> void chromaCU(EncoderPrimitives::Chroma::CUChroma& cu)
 {
     cu.sa8d = t_sa8d<W, H>; cu.sse_pp = t_sse_pp<W, H>;
     cu.sub_ps = t_sub_ps<W, H>; cu.add_ps[NONALIGNED] = t_add_ps<W, H>; cu.add_ps[ALIGNED] = t_add_ps<W, H>;
+    cu.copy_ss = t_copy_ss<W, H>; cu.copy_sp = t_copy_sp<W, H>; cu.copy_ps = t_copy_ps<W, H>;
 }
 
 } // anonymous namespace
@@ -129,6 +151,7 @@ void setupB200Primitives(EncoderPrimitives& p)
 
     lumaCU<4>(p.cu[BLOCK_4x4]); lumaCU<8>(p.cu[BLOCK_8x8]); lumaCU<16>(p.cu[BLOCK_16x16]);
     lumaCU<32>(p.cu[BLOCK_32x32]); lumaCU<64>(p.cu[BLOCK_64x64]);
+    lumaTU<4>(p.cu[BLOCK_4x4]); lumaTU<8>(p.cu[BLOCK_8x8]); lumaTU<16>(p.cu[BLOCK_16x16]); lumaTU<32>(p.cu[BLOCK_32x32]); lumaTU<64>(p.cu[BLOCK_64x64]);
 
     // chroma CU slots the alias pass does not derive from luma (pixel.cpp:1260-1263,1325,1339-1342)
     chromaCU<4, 4>(p.chroma[X265_CSP_I420].cu[BLOCK_8x8]);   chromaCU<8, 8>(p.chroma[X265_CSP_I420].cu[BLOCK_16x16]);
@@ -139,6 +162,11 @@ void setupB200Primitives(EncoderPrimitives& p)
     // 4:2:0 chroma of the 4x4 luma PU: no filters (ipfilter.cpp:414-462) but a bi-prediction average (pixel.cpp:1191)
     p.chroma[X265_CSP_I420].pu[LUMA_4x4].addAvg[NONALIGNED] = t_addAvg<2, 2>; p.chroma[X265_CSP_I420].pu[LUMA_4x4].addAvg[ALIGNED] = t_addAvg<2, 2>;
     // chroma of the 4x4 luma CU: only the residual slots exist (pixel.cpp:1254, 1333)
+    p.chroma[X265_CSP_I420].pu[LUMA_4x4].copy_pp = t_copy_pp<2, 2>;
+    p.chroma[X265_CSP_I420].cu[BLOCK_4x4].copy_ss = t_copy_ss<2, 2>; p.chroma[X265_CSP_I420].cu[BLOCK_4x4].copy_sp = t_copy_sp<2, 2>;
+    p.chroma[X265_CSP_I420].cu[BLOCK_4x4].copy_ps = t_copy_ps<2, 2>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_4x4].copy_ss = t_copy_ss<2, 4>; p.chroma[X265_CSP_I422].cu[BLOCK_4x4].copy_sp = t_copy_sp<2, 4>;
+    p.chroma[X265_CSP_I422].cu[BLOCK_4x4].copy_ps = t_copy_ps<2, 4>;
     p.chroma[X265_CSP_I420].cu[BLOCK_4x4].sub_ps = t_sub_ps<2, 2>;
     p.chroma[X265_CSP_I420].cu[BLOCK_4x4].add_ps[NONALIGNED] = t_add_ps<2, 2>; p.chroma[X265_CSP_I420].cu[BLOCK_4x4].add_ps[ALIGNED] = t_add_ps<2, 2>;
     p.chroma[X265_CSP_I422].cu[BLOCK_4x4].sub_ps = t_sub_ps<2, 4>;
