@@ -202,6 +202,19 @@ int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* 
 int x265b200_blockcopy_batch(x265b200_ctx* ctx, int kind, int w, int h, const void* src, intptr_t srcStride, const int32_t* offS,
                              void* dst, intptr_t dstStride, const int32_t* offD, int n, int param, x265b200_stream stream);
 
+/* per-block scalars (offset arrays may be NULL = contiguous size x size blocks); size in {4, 8, 16, 32, 64}:
+ * var (pixel.cpp:695-712): out[i] = sum | (uint64)sumsq << 32, both uint32 and wrapping like the reference;
+ * psy_cost_pp (pixel.cpp:718-749): |AC energy(source) - AC energy(recon)| summed over the 8x8 sub-blocks (4x4: satd based);
+ * count_nonzero / copy_cnt (dct.cpp:716-744): count[i] = non-zero int16 in block i; coeff != NULL additionally receives the
+ *   blocks contiguously (copy_cnt); denoiseDct (dct.cpp:746-757) over n blocks of numCoeff sharing one resSum / offset table
+ *   (resSum[i] accumulates |level| of every block, order-independent). */
+int x265b200_var_batch(x265b200_ctx* ctx, int size, const void* pix, intptr_t stride, const int32_t* off, int n, uint64_t* out, x265b200_stream stream);
+int x265b200_psy_cost_batch(x265b200_ctx* ctx, int size, const void* src, intptr_t srcStride, const int32_t* offS, const void* rec, intptr_t recStride,
+                            const int32_t* offR, int n, int32_t* out, x265b200_stream stream);
+int x265b200_count_nonzero_batch(x265b200_ctx* ctx, int size, const int16_t* src, intptr_t stride, const int32_t* off, int n,
+                                 int16_t* coeff, uint32_t* count, x265b200_stream stream);
+int x265b200_denoise_dct_batch(x265b200_ctx* ctx, int16_t* dct, uint32_t* resSum, const uint16_t* offset, int numCoeff, int n, x265b200_stream stream);
+
 /* downscale_t frameInitLowres (pixel.cpp:595-620) over one plane: width x height are the LOWRES dimensions; reads
  * 2 * width + 1 columns of 2 * height + 1 rows of src, writes the four half-resolution planes. */
 int x265b200_lowres_batch(x265b200_ctx* ctx, const void* src, intptr_t srcStride, void* dst0, void* dsth, void* dstv, void* dstc,
@@ -262,6 +275,11 @@ void x265b200_frame_init_lowres(x265b200_ctx*, const void* src0, void* dst0, voi
                                 intptr_t srcStride, intptr_t dstStride, int width, int height);
 /* copy_pp/ss/sp/ps, blockfill_s, cpy2Dto1D_shl/shr, cpy1Dto2D_shl/shr (primitives.h:141-150, 184-187); kind as in x265b200_blockcopy_batch */
 void x265b200_blockcopy(x265b200_ctx*, int kind, int w, int h, void* dst, intptr_t dstStride, const void* src, intptr_t srcStride, int param);
+/* var_t, pixelcmp_t psy_cost_pp, count_nonzero_t / copy_cnt_t (coeff == NULL: count only), denoiseDct_t with the size prepended */
+uint64_t x265b200_var(x265b200_ctx*, int size, const void* pix, intptr_t stride);
+int x265b200_psy_cost_pp(x265b200_ctx*, int size, const void* source, intptr_t sstride, const void* recon, intptr_t rstride);
+uint32_t x265b200_copy_cnt(x265b200_ctx*, int size, int16_t* coeff, const int16_t* residual, intptr_t resiStride);
+void x265b200_denoise_dct(x265b200_ctx*, int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff);
 /* integralh_t / integralv_t (primitives.h:227-228) with the box width / height prepended */
 void x265b200_weight_pp(x265b200_ctx*, const void* src, void* dst, intptr_t stride, int width, int height, int w0, int round, int shift, int offset);
 void x265b200_weight_sp(x265b200_ctx*, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset);

@@ -92,6 +92,7 @@ static int coverage()
     for (int i = 0; i < NUM_CU_SIZES; i++)
     {
         SLOT(cu[i].sub_ps); SLOT(cu[i].add_ps[0]); SLOT(cu[i].add_ps[1]);
+        SLOT(cu[i].var); SLOT(cu[i].psy_cost_pp); SLOT(cu[i].count_nonzero); SLOT(cu[i].copy_cnt);
         SLOT(cu[i].blockfill_s[0]); SLOT(cu[i].blockfill_s[1]); SLOT(cu[i].calcresidual[0]); SLOT(cu[i].calcresidual[1]);
         SLOT(cu[i].cpy2Dto1D_shl); SLOT(cu[i].cpy2Dto1D_shr); SLOT(cu[i].cpy1Dto2D_shl[0]); SLOT(cu[i].cpy1Dto2D_shl[1]); SLOT(cu[i].cpy1Dto2D_shr);
         for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].sub_ps); SLOT(chroma[c].cu[i].add_ps[0]); SLOT(chroma[c].cu[i].add_ps[1]); }
@@ -102,7 +103,7 @@ static int coverage()
         for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].copy_ss); SLOT(chroma[c].cu[i].copy_sp); SLOT(chroma[c].cu[i].copy_ps); SLOT(chroma[c].cu[i].copy_pp); }
         aliasOK = false;
     }
-    SLOT(frameInitLowres); SLOT(weight_pp); SLOT(weight_sp);
+    SLOT(frameInitLowres); SLOT(weight_pp); SLOT(weight_sp); SLOT(denoiseDct);
     for (int i = 0; i < NUM_INTEGRAL_SIZE; i++) { SLOT(integral_inith[i]); SLOT(integral_initv[i]); }
     printf("adjacent: %d slots in the C table, %d bound to B200 entries, %d missing, %d still C, %d extra\n", want, bound, missing, same, extra);
     return hot + missing + same + extra;

@@ -468,4 +468,18 @@ int ref_blockcopy(int kind, int w, int h, void* dst, intptr_t ds, const void* sr
     return 0;
 }
 
+
+/* ---- per-block scalars through the reference table ---- */
+static int cuIdx(int size) { for (int i = 0; i < NUM_CU_SIZES; i++) if ((4 << i) == size) return i; return -1; }
+uint64_t ref_var(int size, const pixel* pix, intptr_t stride) { ensure(); return g_c.cu[cuIdx(size)].var(pix, stride); }
+int ref_psy_cost_pp(int size, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { ensure(); return g_c.cu[cuIdx(size)].psy_cost_pp(a, sa, b, sb); }
+uint32_t ref_copy_cnt(int size, int16_t* coeff, const int16_t* resi, intptr_t stride)
+{
+    ensure();
+    int i = cuIdx(size);
+    if (coeff) return g_c.cu[i].copy_cnt(coeff, resi, stride);
+    return (uint32_t)g_c.cu[i].count_nonzero(resi);          /* contiguous size x size input */
+}
+void ref_denoise_dct(int16_t* dct, uint32_t* resSum, const uint16_t* offset, int numCoeff) { ensure(); g_c.denoiseDct(dct, resSum, offset, numCoeff); }
+
 } // extern "C"

@@ -873,3 +873,68 @@ EXPORT void orc_blockcopy_batch(int kind, int w, int h, const void* src, intptr_
     for (int i = 0; i < n; i++)
         orc_blockcopy(kind, w, h, (char*)dst + (size_t)offD[i] * ed, ds, kind == 4 ? NULL : (const char*)src + (size_t)offS[i] * es, ss, param);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-block scalars: var (pixel.cpp:695-712), psy_cost_pp (pixel.cpp:718-749), count_nonzero / copy_cnt (dct.cpp:716-744),
+ * denoiseDct (dct.cpp:746-757).
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT uint64_t orc_var(int size, const pixel* pix, intptr_t stride)
+{
+    uint32_t sum = 0, sqr = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) { uint32_t v = pix[y * stride + x]; sum += v; sqr += v * v; }
+    return (uint64_t)sum + ((uint64_t)sqr << 32);
+}
+static int ac_energy(int n, const pixel* p, intptr_t stride)
+{
+    /* n x n Hadamard magnitude of the block itself (the reference differences it against a zero row), minus its DC */
+    int m[8][8], t[8][8], sad = 0, raw = 0;
+    for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) { m[y][x] = p[y * stride + x]; sad += m[y][x]; }
+    for (int y = 0; y < n; y++)
+        for (int k = 0; k < n; k++)
+        {
+            int acc = 0;
+            for (int x = 0; x < n; x++) acc += (__builtin_popcount(k & x) & 1) ? -m[y][x] : m[y][x];
+            t[y][k] = acc;
+        }
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < n; j++)
+        {
+            int acc = 0;
+            for (int y = 0; y < n; y++) acc += (__builtin_popcount(j & y) & 1) ? -t[y][k] : t[y][k];
+            raw += iabs(acc);
+        }
+    return (n == 8 ? (raw + 2) >> 2 : raw >> 1) - (sad >> 2);
+}
+EXPORT int orc_psy_cost_pp(int size, const pixel* src, intptr_t ss, const pixel* rec, intptr_t sr)
+{
+    if (size == 4) return iabs(ac_energy(4, src, ss) - ac_energy(4, rec, sr));
+    uint32_t tot = 0;
+    for (int i = 0; i < size; i += 8)
+        for (int j = 0; j < size; j += 8)
+            tot += (uint32_t)iabs(ac_energy(8, src + i * ss + j, ss) - ac_energy(8, rec + i * sr + j, sr));
+    return (int)tot;
+}
+EXPORT uint32_t orc_copy_cnt(int size, int16_t* coeff, const int16_t* resi, intptr_t stride)
+{
+    uint32_t n = 0;
+    for (int k = 0; k < size; k++)
+        for (int j = 0; j < size; j++)
+        {
+            if (coeff) coeff[k * size + j] = resi[k * stride + j];
+            n += resi[k * stride + j] != 0;
+        }
+    return n;
+}
+EXPORT void orc_denoise_dct(int16_t* dct, uint32_t* resSum, const uint16_t* offset, int numCoeff)
+{
+    for (int i = 0; i < numCoeff; i++)
+    {
+        int level = dct[i];
+        int sign = level >> 31;
+        level = (level + sign) ^ sign;
+        resSum[i] += (uint32_t)level;
+        level -= offset[i];
+        dct[i] = (int16_t)(level < 0 ? 0 : (level ^ sign) - sign);
+    }
+}

@@ -135,6 +135,19 @@ class _Base:
     def p2s(self, w, h, src, os_, ss, dst, od, ds):
         return self._f("p2s")(w, h, _ptr(src, os_), C.c_ssize_t(ss), _ptr(dst, od), C.c_ssize_t(ds))
 
+    # ---- per-block scalars -------------------------------------------------------------------------------------
+    def var(self, size, pix, op_, stride):
+        return int(self._f("var", C.c_uint64)(size, _ptr(pix, op_), C.c_ssize_t(stride)))
+
+    def psy_cost_pp(self, size, a, oa, sa, b, ob, sb):
+        return self._f("psy_cost_pp")(size, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))
+
+    def copy_cnt(self, size, coeff, resi, or_, stride):
+        return int(self._f("copy_cnt", C.c_uint32)(size, _ptr(coeff) if coeff is not None else None, _ptr(resi, or_), C.c_ssize_t(stride)))
+
+    def denoise_dct(self, dct, res_sum, offset, num):
+        self._f("denoise_dct", None)(_ptr(dct), _ptr(res_sum), _ptr(offset), num)
+
     # ---- copy family (kind 0..6, see include/x265b200.h x265b200_blockcopy_batch) -------------------------------
     def blockcopy(self, kind, w, h, dst, od, ds, src, os_, ss, param=0):
         return self._f("blockcopy")(kind, w, h, _ptr(dst, od), C.c_ssize_t(ds), _ptr(src, os_) if src is not None else None, C.c_ssize_t(ss), param)

@@ -424,3 +424,43 @@ def test_blockcopy_batch(depth):
             got = got.view(np.uint16) if np.dtype(dt) == np.uint16 else got
             assert np.array_equal(got, want), (kind, w, h)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_block_scalar_batches(depth):
+    """var / psy_cost_pp / count_nonzero / copy_cnt / denoiseDct batches vs the oracle"""
+    import torch
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(600 + depth)
+    stride, rows, n = 200, 200, 53
+    N = stride * rows
+    A = rng.integers(0, orc.pmax + 1, N).astype(orc.pix); B = rng.integers(0, orc.pmax + 1, N).astype(orc.pix)
+    A[:N // 2] = orc.pmax                                   # saturated half: the uint32 sum of squares wraps at 12 bit, 64 x 64
+    dA, dB = dev(pix_view(A, depth)), dev(pix_view(B, depth))
+    resi = (rng.integers(-300, 300, N) * (rng.integers(0, 3, N) == 0)).astype(np.int16)
+    for size in (4, 8, 16, 32, 64):
+        offA = (rng.integers(0, rows - size, n) * stride + rng.integers(0, stride - size, n)).astype(np.int32)
+        offB = (rng.integers(0, rows - size, n) * stride + rng.integers(0, stride - size, n)).astype(np.int32)
+        out = torch.zeros(n, dtype=torch.int64, device="cuda")
+        ctx.var_batch(size, dA, stride, dev(offA), n, out)
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), np.array([orc.var(size, A, int(a), stride) for a in offA], np.uint64)), size
+        cost = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.psy_cost_batch(size, dA, stride, dev(offA), dB, stride, dev(offB), n, cost)
+        assert np.array_equal(cost.cpu().numpy(), np.array([orc.psy_cost_pp(size, A, int(a), stride, B, int(b), stride) for a, b in zip(offA, offB)], np.int32)), size
+        if size <= 32:
+            coeff = torch.zeros(n * size * size, dtype=torch.int16, device="cuda"); cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+            ctx.count_nonzero_batch(size, dev(resi), stride, dev(offA), n, coeff, cnt)
+            want_c = np.zeros(n * size * size, np.int16)
+            want_n = np.array([orc.copy_cnt(size, want_c[i * size * size:(i + 1) * size * size], resi, int(a), stride) for i, a in enumerate(offA)], np.uint32)
+            assert np.array_equal(cnt.cpu().numpy().view(np.uint32), want_n) and np.array_equal(coeff.cpu().numpy(), want_c), size
+            num = size * size
+            d0 = rng.integers(-32768, 32768, n * num).astype(np.int16)
+            rs0 = rng.integers(0, 1 << 20, num).astype(np.uint32); offs = rng.integers(0, 65535, num).astype(np.uint16)
+            wd = d0.copy(); wr = rs0.copy()
+            for i in range(n):
+                orc.denoise_dct(wd[i * num:(i + 1) * num], wr, offs, num)
+            gd = dev(d0.copy()); gr = dev(rs0.view(np.int32).copy())
+            ctx.denoise_dct_batch(gd, gr, dev(offs.view(np.int16)), num, n)
+            assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gr.cpu().numpy().view(np.uint32), wr), size
+    ctx.check()

@@ -423,3 +423,27 @@ def test_copy_family(libs):
                     a = np.full(n, 7, np.int16); b = a.copy()
                     o.blockcopy(kind, w, w, a, 0, ds, s16, 8, ss, shift); assert r.blockcopy(kind, w, w, b, 0, ds, s16, 8, ss, shift) == 0
                     assert np.array_equal(a, b), (kind, w, shift, ds)
+
+
+def test_block_scalars(libs):
+    """var, psy_cost_pp, count_nonzero / copy_cnt, denoiseDct vs the reference slots"""
+    o, r = libs
+    rng = np.random.default_rng(71)
+    stride, rows = 100, 100
+    n = stride * rows
+    for a, b in pixel_bufs(rng, o.depth, n):
+        for size in (4, 8, 16, 32, 64):
+            assert o.var(size, a, 7, stride) == r.var(size, a, 7, stride), size
+            assert o.psy_cost_pp(size, a, 3, stride, b, 11, 97) == r.psy_cost_pp(size, a, 3, stride, b, 11, 97), size
+    resi = (rng.integers(-300, 300, n) * (rng.integers(0, 3, n) == 0)).astype(np.int16)
+    for size in (4, 8, 16, 32):
+        ca = np.zeros(size * size, np.int16); cb = ca.copy()
+        assert o.copy_cnt(size, ca, resi, 13, stride) == r.copy_cnt(size, cb, resi, 13, stride)
+        assert np.array_equal(ca, cb)
+        assert o.copy_cnt(size, None, resi, 13, size) == r.copy_cnt(size, None, resi, 13, size)
+        num = size * size
+        da = rng.integers(-32768, 32768, num).astype(np.int16); db = da.copy()
+        ra = rng.integers(0, 1 << 31, num).astype(np.uint32); rb = ra.copy()
+        offs = rng.integers(0, 65535, num).astype(np.uint16)
+        o.denoise_dct(da, ra, offs, num); r.denoise_dct(db, rb, offs, num)
+        assert np.array_equal(da, db) and np.array_equal(ra, rb)

@@ -40,13 +40,13 @@ def load_library():
         _lib = C.CDLL(LIB_PATH)
         _lib.x265b200_last_error.restype = C.c_char_p
         _lib.x265b200_launch_count.restype = C.c_uint64
-        for name in ("x265b200_sse_pp", "x265b200_sse_ss", "x265b200_ssd_s"):
+        for name in ("x265b200_sse_pp", "x265b200_sse_ss", "x265b200_ssd_s", "x265b200_var"):
             getattr(_lib, name).restype = C.c_uint64
-        for name in ("x265b200_quant", "x265b200_nquant"):
+        for name in ("x265b200_quant", "x265b200_nquant", "x265b200_copy_cnt"):
             getattr(_lib, name).restype = C.c_uint32
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
                      "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
-                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy"):
+                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy", "x265b200_denoise_dct"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -150,6 +150,18 @@ class Context:
 
     def me_integral_batch(self, pix, stride, rows, nframes, sums, plane_pitch, stream=0):
         self._call("x265b200_me_integral_batch", _dp(pix), _ss(stride), int(rows), int(nframes), _dp(sums), C.c_size_t(int(plane_pitch)), C.c_void_p(stream))
+
+    def var_batch(self, size, pix, stride, off, n, out, stream=0):
+        self._call("x265b200_var_batch", size, _dp(pix), _ss(stride), _dp(off), int(n), _dp(out), C.c_void_p(stream))
+
+    def psy_cost_batch(self, size, src, ss, offS, rec, sr, offR, n, out, stream=0):
+        self._call("x265b200_psy_cost_batch", size, _dp(src), _ss(ss), _dp(offS), _dp(rec), _ss(sr), _dp(offR), int(n), _dp(out), C.c_void_p(stream))
+
+    def count_nonzero_batch(self, size, src, stride, off, n, coeff, count, stream=0):
+        self._call("x265b200_count_nonzero_batch", size, _dp(src), _ss(stride), _dp(off), int(n), _dp(coeff), _dp(count), C.c_void_p(stream))
+
+    def denoise_dct_batch(self, dct, res_sum, offset, num_coeff, n, stream=0):
+        self._call("x265b200_denoise_dct_batch", _dp(dct), _dp(res_sum), _dp(offset), int(num_coeff), int(n), C.c_void_p(stream))
 
     def blockcopy_batch(self, kind, w, h, S, ss, offS, D, sd, offD, n, param=0, stream=0):
         self._call("x265b200_blockcopy_batch", kind, w, h, _dp(S), _ss(ss), _dp(offS), _dp(D), _ss(sd), _dp(offD), int(n), int(param), C.c_void_p(stream))

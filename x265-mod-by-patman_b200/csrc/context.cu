@@ -566,3 +566,72 @@ extern "C" void x265b200_blockcopy(x265b200_ctx* ctx, int kind, int w, int h, vo
     if (!c.download(oD, (size_t)w * h * db)) return;
     unpack(dst, c.h<void>(oD), h, w * db, dstStride * (intptr_t)db);
 }
+
+// ------------------------------------------------------------------ host entries: per-block scalars (blockstats.cu)
+
+extern "C" uint64_t x265b200_var(x265b200_ctx* ctx, int size, const void* pix, intptr_t stride)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    const size_t pb = ctx->pixbytes;
+    size_t oS = c.alloc((size_t)size * size * pb);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc(8);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oS), pix, size, size * pb, stride * (intptr_t)pb);
+    if (!c.upload(0, inEnd)) return 0;
+    if (x265b200_var_batch(ctx, size, c.d<void>(oS), size, nullptr, 1, c.d<uint64_t>(oD), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oD, 8)) return 0;
+    return *c.h<uint64_t>(oD);
+}
+
+extern "C" int x265b200_psy_cost_pp(x265b200_ctx* ctx, int size, const void* source, intptr_t sstride, const void* recon, intptr_t rstride)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    const size_t pb = ctx->pixbytes;
+    size_t oS = c.alloc((size_t)size * size * pb), oR = c.alloc((size_t)size * size * pb);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc(4);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oS), source, size, size * pb, sstride * (intptr_t)pb);
+    pack(c.h<void>(oR), recon, size, size * pb, rstride * (intptr_t)pb);
+    if (!c.upload(0, inEnd)) return 0;
+    if (x265b200_psy_cost_batch(ctx, size, c.d<void>(oS), size, nullptr, c.d<void>(oR), size, nullptr, 1, c.d<int32_t>(oD), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oD, 4)) return 0;
+    return *c.h<int32_t>(oD);
+}
+
+// count_nonzero (coeff == NULL, contiguous size x size input) and copy_cnt (strided residual -> contiguous coeff)
+extern "C" uint32_t x265b200_copy_cnt(x265b200_ctx* ctx, int size, int16_t* coeff, const int16_t* residual, intptr_t resiStride)
+{
+    Call c(ctx);
+    if (!c.ok()) return 0;
+    size_t bytes = (size_t)size * size * 2;
+    size_t oS = c.alloc(bytes);
+    size_t inEnd = c.used;
+    size_t oC = c.alloc(bytes), oD = c.alloc(4);
+    if (!c.ok()) return 0;
+    pack(c.h<void>(oS), residual, size, (size_t)size * 2, resiStride * 2);
+    if (!c.upload(0, inEnd)) return 0;
+    if (x265b200_count_nonzero_batch(ctx, size, c.d<int16_t>(oS), size, nullptr, 1, coeff ? c.d<int16_t>(oC) : nullptr, c.d<uint32_t>(oD), c.st()) != X265B200_OK) return 0;
+    if (!c.download(oC, (oD + 4) - oC)) return 0;
+    if (coeff) memcpy(coeff, c.h<void>(oC), bytes);
+    return *c.h<uint32_t>(oD);
+}
+
+extern "C" void x265b200_denoise_dct(x265b200_ctx* ctx, int16_t* dctCoef, uint32_t* resSum, const uint16_t* offset, int numCoeff)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    size_t oC = c.alloc((size_t)numCoeff * 2), oR = c.alloc((size_t)numCoeff * 4), oO = c.alloc((size_t)numCoeff * 2);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oC), dctCoef, (size_t)numCoeff * 2);
+    memcpy(c.h<void>(oR), resSum, (size_t)numCoeff * 4);
+    memcpy(c.h<void>(oO), offset, (size_t)numCoeff * 2);
+    if (!c.upload(0, c.used)) return;
+    if (x265b200_denoise_dct_batch(ctx, c.d<int16_t>(oC), c.d<uint32_t>(oR), c.d<uint16_t>(oO), numCoeff, 1, c.st()) != X265B200_OK) return;
+    if (!c.download(0, oO)) return;
+    memcpy(dctCoef, c.h<void>(oC), (size_t)numCoeff * 2);
+    memcpy(resSum, c.h<void>(oR), (size_t)numCoeff * 4);
+}

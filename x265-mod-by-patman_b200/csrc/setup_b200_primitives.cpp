@@ -73,6 +73,11 @@ template<int W> void t_2Dto1D_shr(int16_t* d, const int16_t* a, intptr_t sa, int
 template<int W> void t_1Dto2D_shl(int16_t* d, const int16_t* a, intptr_t ds, int sh) { x265b200_blockcopy(g_b200, 5, W, W, d, ds, a, W, sh); }
 template<int W> void t_1Dto2D_shr(int16_t* d, const int16_t* a, intptr_t ds, int sh) { x265b200_blockcopy(g_b200, 6, W, W, d, ds, a, W, sh); }
 template<int W> void t_calcresidual(const pixel* f, const pixel* p, int16_t* r, intptr_t st) { x265b200_sub_ps(g_b200, W, W, r, st, f, p, st, st); }
+template<int W> uint64_t t_var(const pixel* p, intptr_t st) { return x265b200_var(g_b200, W, p, st); }
+template<int W> int t_psy_cost(const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return x265b200_psy_cost_pp(g_b200, W, a, sa, b, sb); }
+template<int W> int t_count_nonzero(const int16_t* q) { return (int)x265b200_copy_cnt(g_b200, W, NULL, q, W); }
+template<int W> uint32_t t_copy_cnt(int16_t* c, const int16_t* r, intptr_t st) { return x265b200_copy_cnt(g_b200, W, c, r, st); }
+void t_denoise(int16_t* d, uint32_t* rs, const uint16_t* off, int n) { x265b200_denoise_dct(g_b200, d, rs, off, n); }
 template<int W> void t_integral_h(uint32_t* sum, pixel* pix, intptr_t stride) { x265b200_integral_inith(g_b200, W, sum, pix, stride); }
 template<int H> void t_integral_v(uint32_t* sum, intptr_t stride) { x265b200_integral_initv(g_b200, H, sum, stride); }
 void t_weight_pp(const pixel* s, pixel* d, intptr_t st, int w, int h, int w0, int rnd, int sh, int off) { x265b200_weight_pp(g_b200, s, d, st, w, h, w0, rnd, sh, off); }
@@ -109,6 +114,7 @@ template<int W> void lumaCU(EncoderPrimitives::CU& cu)
     cu.copy_ss = t_copy_ss<W, W>; cu.copy_sp = t_copy_sp<W, W>; cu.copy_ps = t_copy_ps<W, W>;
     cu.blockfill_s[NONALIGNED] = t_blockfill<W>; cu.blockfill_s[ALIGNED] = t_blockfill<W>;
     cu.calcresidual[NONALIGNED] = t_calcresidual<W>; cu.calcresidual[ALIGNED] = t_calcresidual<W>;
+    cu.var = t_var<W>; cu.psy_cost_pp = t_psy_cost<W>;
 }
 // the 1-D <-> 2-D coefficient copies (pixel.cpp:1081-1085, all five CU sizes)
 template<int W> void lumaTU(EncoderPrimitives::CU& cu)
@@ -116,6 +122,7 @@ template<int W> void lumaTU(EncoderPrimitives::CU& cu)
     cu.cpy2Dto1D_shl = t_2Dto1D_shl<W>; cu.cpy2Dto1D_shr = t_2Dto1D_shr<W>;
     cu.cpy1Dto2D_shl[NONALIGNED] = t_1Dto2D_shl<W>; cu.cpy1Dto2D_shl[ALIGNED] = t_1Dto2D_shl<W>; cu.cpy1Dto2D_shr = t_1Dto2D_shr<W>;
 }
+template<int W> void lumaCoef(EncoderPrimitives::CU& cu) { cu.count_nonzero = t_count_nonzero<W>; cu.copy_cnt = t_copy_cnt<W>; }   // dct.cpp:1100-1108
 template<int W, int H> void chromaCU(EncoderPrimitives::Chroma::CUChroma& cu)
 {
     cu.sa8d = t_sa8d<W, H>; cu.sse_pp = t_sse_pp<W, H>;
@@ -182,6 +189,8 @@ void setupB200Primitives(EncoderPrimitives& p)
     p.dst4x4 = t_dst4;  p.idst4x4 = t_idst4;
     p.quant = t_quant;  p.nquant = t_nquant;
     p.dequant_normal = t_dequant_normal;  p.dequant_scaling = t_dequant_scaling;
+    lumaCoef<4>(p.cu[BLOCK_4x4]); lumaCoef<8>(p.cu[BLOCK_8x8]); lumaCoef<16>(p.cu[BLOCK_16x16]); lumaCoef<32>(p.cu[BLOCK_32x32]);
+    p.denoiseDct = t_denoise;
     p.frameInitLowres = t_lowres;
     p.weight_pp = t_weight_pp;  p.weight_sp = t_weight_sp;
     p.integral_inith[INTEGRAL_4] = t_integral_h<4>;   p.integral_initv[INTEGRAL_4] = t_integral_v<4>;
