@@ -189,6 +189,21 @@ int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h, const voi
                               const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
                               x265b200_stream stream);
 
+/* Exhaustive integer motion search (reference encoder/motion.cpp:1593-1637, the X265_FULL_SEARCH case of
+ * MotionEstimate::motionEstimate) for n prediction units of w x h (4..64, multiples of 4) at once.  For PU i every
+ * full-pel vector (x, y) with range[4i] <= x <= range[4i+2], range[4i+1] <= y <= range[4i+3] is costed as
+ *   sad(fenc + offF[i], ref + offR[i] + y * strideR + x) + (uint16_t)(costTab[(x << 2) - mvp[2i]] + costTab[(y << 2) - mvp[2i+1]])
+ * (BitCost::mvcost, encoder/bitcost.h:53-56: costTab is the DEVICE copy of the lambda-scaled table, pointing at its
+ * centre element; mvp is in quarter pels) and (bmv[2i..2i+1], bcost[i]) -- in/out, the search's starting point -- is
+ * replaced by the cheapest candidate if that is strictly cheaper; among equal candidates the first in raster order
+ * wins, exactly as the reference's COPY2_IF_LT sequence leaves it.  offR[i] addresses the co-located block (vector 0,0);
+ * the caller clips range to the padded picture as MotionEstimate::setSearchRange does.  An empty range leaves PU i untouched.
+ * merange (the encoder's searchRange) only sizes the on-chip window staging: windows wider than 2 * merange + 1 are still
+ * searched completely, in several pieces. */
+int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                           const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
+                           const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

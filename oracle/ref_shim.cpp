@@ -482,4 +482,41 @@ uint32_t ref_copy_cnt(int size, int16_t* coeff, const int16_t* resi, intptr_t st
 }
 void ref_denoise_dct(int16_t* dct, uint32_t* resSum, const uint16_t* offset, int numCoeff) { ensure(); g_c.denoiseDct(dct, resSum, offset, numCoeff); }
 
+/* ---- exhaustive integer search with the reference's own sad / sad_x4 slots, in the shape of motion.cpp's X265_FULL_SEARCH loop ---- */
+void ref_me_full_search(int w, int h, const pixel* fencIn, intptr_t sf, const pixel* fref, intptr_t stride,
+                        const int32_t* range, const int32_t* mvp, const uint16_t* costTab, int32_t* bmvIO, int32_t* bcostIO)
+{
+    ensure();
+    int part = lumaPart(w, h);
+    ALIGN_VAR_32(pixel, fenc[64 * 64]);                       /* the encoder keeps fenc at FENC_STRIDE */
+    for (int y = 0; y < h; y++) memcpy(fenc + y * FENC_STRIDE, fencIn + y * sf, w * sizeof(pixel));
+    pixelcmp_t sad = g_c.pu[part].sad;
+    pixelcmp_x4_t sad_x4 = g_c.pu[part].sad_x4;
+    const uint16_t* cx = costTab - mvp[0];
+    const uint16_t* cy = costTab - mvp[1];
+    int bcost = *bcostIO, bx = bmvIO[0], by = bmvIO[1];
+    int32_t costs[4];
+    for (int ty = range[1]; ty <= range[3]; ty++)
+        for (int tx = range[0]; tx <= range[2]; tx++)
+        {
+            if (tx + 3 <= range[2])
+            {
+                const pixel* base = fref + (intptr_t)ty * stride + tx;
+                sad_x4(fenc, base, base + 1, base + 2, base + 3, stride, costs);
+                for (int k = 0; k < 4; k++)
+                {
+                    int c = costs[k] + (uint16_t)(cx[(tx + k) << 2] + cy[ty << 2]);
+                    if (c < bcost) { bcost = c; bx = tx + k; by = ty; }
+                }
+                tx += 3;
+            }
+            else
+            {
+                int c = sad(fenc, FENC_STRIDE, fref + (intptr_t)ty * stride + tx, stride) + (uint16_t)(cx[tx << 2] + cy[ty << 2]);
+                if (c < bcost) { bcost = c; bx = tx; by = ty; }
+            }
+        }
+    *bcostIO = bcost; bmvIO[0] = bx; bmvIO[1] = by;
+}
+
 } // extern "C"

@@ -938,3 +938,35 @@ EXPORT void orc_denoise_dct(int16_t* dct, uint32_t* resSum, const uint16_t* offs
         dct[i] = (int16_t)(level < 0 ? 0 : (level ^ sign) - sign);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Exhaustive integer motion search (encoder/motion.cpp:1593-1637, the X265_FULL_SEARCH case of
+ * MotionEstimate::motionEstimate; cost of a vector = SAD + mvcost, encoder/bitcost.h:53-56).
+ * Candidates are visited in raster order (y outer, x inner) and a candidate replaces the running best only
+ * when it is strictly cheaper (COPY2_IF_LT, common.h:193-198), so the initial (bmv, bcost) wins every tie
+ * and, among candidates, the first in raster order does.
+ *   range = { mvmin.x, mvmin.y, mvmax.x, mvmax.y } in full pels; mvp in quarter pels;
+ *   costTab points at the centre of the lambda-scaled table BitCost::setQP builds (bitcost.cpp:44-54):
+ *   mvcost(mv) = (uint16_t)(costTab[mv.x - mvp.x] + costTab[mv.y - mvp.y]) with mv = candidate << 2.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void orc_me_full_search(int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                               const int32_t* range, const int32_t* mvp, const uint16_t* costTab,
+                               int32_t* bmv /* in/out x,y */, int32_t* bcost /* in/out */)
+{
+    int best = *bcost, bx = bmv[0], by = bmv[1];
+    for (int y = range[1]; y <= range[3]; y++)
+        for (int x = range[0]; x <= range[2]; x++)
+        {
+            int cost = orc_sad(w, h, fenc, sf, fref + (intptr_t)y * sr + x, sr);
+            cost += (uint16_t)(costTab[(x << 2) - mvp[0]] + costTab[(y << 2) - mvp[1]]);
+            if (cost < best) { best = cost; bx = x; by = y; }
+        }
+    *bcost = best; bmv[0] = bx; bmv[1] = by;
+}
+EXPORT void orc_me_full_batch(int w, int h, const pixel* fenc, intptr_t sf, const pixel* ref, intptr_t sr,
+                              const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
+                              const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost)
+{
+    for (int i = 0; i < n; i++)
+        orc_me_full_search(w, h, fenc + offF[i], sf, ref + offR[i], sr, range + 4 * i, mvp + 2 * i, costTab, bmv + 2 * i, bcost + i);
+}

@@ -177,6 +177,16 @@ class _Base:
     def me_integral(self, pix, stride, rows, sums, plane_pitch):
         return self._f("me_integral")(_ptr(pix), C.c_ssize_t(stride), rows, _ptr(sums), C.c_size_t(plane_pitch))
 
+    # ---- exhaustive integer motion search of one PU (motion.cpp X265_FULL_SEARCH) -----------------------------
+    def me_full_search(self, w, h, fenc, of, sf, ref, orf, sr, rng, mvp, cost_tab, centre, bmv, bcost):
+        """rng = [minx, miny, maxx, maxy] full pel, mvp qpel (int32 arrays); cost_tab uint16 with its centre at `centre`;
+        returns (bmv_x, bmv_y, bcost)"""
+        mv = np.array(bmv, np.int32); bc = C.c_int32(int(bcost))
+        rng = np.ascontiguousarray(rng, np.int32); mvp = np.ascontiguousarray(mvp, np.int32)
+        self._f("me_full_search", None)(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), _ptr(rng), _ptr(mvp),
+                                        _ptr(cost_tab, centre), _ptr(mv), C.byref(bc))
+        return int(mv[0]), int(mv[1]), int(bc.value)
+
     # ---- sub-pel candidate cost (subpelCompare): interpolation + sad (op 0) / satd (op 1) ----------------------
     def subpel_cmp(self, op, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp")(op, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
@@ -277,6 +287,11 @@ class Oracle(_Base):
         cost = np.zeros(n * K, np.int32)
         self._f("subpel_cmp_batch", None)(op, w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(ref), C.c_ssize_t(sr), _ptr(offF), _ptr(offR), _ptr(frac), K, n, _ptr(cost))
         return cost
+
+    def me_full_batch(self, w, h, fenc, sf, ref, sr, offF, offR, rng, mvp, cost_tab, centre, bmv, bcost):
+        """bmv (n x 2 int32) and bcost (n int32) are updated in place"""
+        self._f("me_full_batch", None)(w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(ref), C.c_ssize_t(sr), _ptr(offF), _ptr(offR), _ptr(rng), _ptr(mvp),
+                                       _ptr(cost_tab, centre), len(offF), _ptr(bmv), _ptr(bcost))
 
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD):
         self._f("blockop_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(offA), _ptr(B), C.c_ssize_t(sb), _ptr(offB),

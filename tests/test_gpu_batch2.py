@@ -464,3 +464,52 @@ def test_block_scalar_batches(depth):
             ctx.denoise_dct_batch(gd, gr, dev(offs.view(np.int16)), num, n)
             assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gr.cpu().numpy().view(np.uint32), wr), size
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_me_full_batch(depth):
+    """exhaustive integer search of a batch of PUs vs the oracle's raster loop: windows larger and smaller than a candidate
+    tile, single-column / single-row / empty windows, lambda-scaled and random (wrapping) cost tables, and flat pictures
+    where every candidate ties and the tie-break order decides the vector"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane
+    from test_oracle_vs_ref import mv_cost_table
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    F = make_plane(geo, depth, 61, "natural"); R = make_plane(geo, depth, 62, "natural")
+    flat = np.full_like(F, orc.pmax // 3)
+    rng = np.random.default_rng(400 + depth)
+    cw, ch = geo.coded()
+    RAD = 2048
+    tabs = [mv_cost_table(12.6992, RAD), rng.integers(0, 65536, 2 * RAD + 1).astype(np.uint16), np.zeros(2 * RAD + 1, np.uint16)]
+    dtabs = [dev(t.view(np.int16)) for t in tabs]
+    for (w, h) in LUMA_PU:
+        n = 14
+        x = rng.integers(0, cw - w + 1, n); y = rng.integers(0, ch - h + 1, n)
+        offF = (geo.origin + y * geo.stride + x).astype(np.int32)
+        x2 = rng.integers(0, cw - w + 1, n); y2 = rng.integers(0, ch - h + 1, n)        # co-located block of the reference picture
+        offR = (geo.origin + y2 * geo.stride + x2).astype(np.int32)
+        # windows clipped to the padded picture like setSearchRange: up to +-70 columns, +-45 rows
+        minx = -np.minimum(rng.integers(0, 71, n), x2 + geo.margin_x - 8); maxx = np.minimum(rng.integers(0, 71, n), cw + geo.margin_x - 8 - w - x2)
+        miny = -np.minimum(rng.integers(0, 46, n), y2 + geo.margin_y - 8); maxy = np.minimum(rng.integers(0, 46, n), ch + geo.margin_y - 8 - h - y2)
+        maxx[0] = minx[0]; maxy[1] = miny[1]                  # one column, one row
+        maxx[2] = minx[2] - 1                                 # empty: PU stays untouched
+        minx[3], maxx[3], miny[3], maxy[3] = 0, 0, 0, 0       # a single candidate
+        rngs = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        mvp = rng.integers(-200, 201, (n, 2)).astype(np.int32)
+        bmv0 = np.stack([rng.integers(minx, np.maximum(maxx, minx) + 1), rng.integers(miny, maxy + 1)], 1).astype(np.int32)
+        for ti, tab in enumerate(tabs):
+            merange = (70, 16, 0)[ti]                         # staging hint: whole window, super-tiles, minimum
+            for fe, rf in ((F, R), (flat, flat)):
+                bc0 = np.full(n, 0x7fffffff, np.int32)
+                bc0[4] = 0                                    # nothing can beat the starting point
+                if fe is flat: bc0[5::3] = int(tab[RAD - int(mvp[5, 0])]) if ti == 2 else 37       # ties / low starting costs
+                want_mv, want_c = bmv0.copy(), bc0.copy()
+                orc.me_full_batch(w, h, fe, geo.stride, rf, geo.stride, offF, offR, rngs, mvp, tab, RAD, want_mv, want_c)
+                gmv, gc = dev(bmv0.copy()), dev(bc0.copy())
+                ctx.me_full_batch(w, h, merange, dev(pix_view(fe, depth)), geo.stride, dev(pix_view(rf, depth)), geo.stride, dev(offF), dev(offR),
+                                  dev(rngs), dev(mvp), dtabs[ti].data_ptr() + 2 * RAD, gmv, gc)
+                assert np.array_equal(gc.cpu().numpy(), want_c), (w, h, ti)
+                assert np.array_equal(gmv.cpu().numpy(), want_mv), (w, h, ti)
+    ctx.check()

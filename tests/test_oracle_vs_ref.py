@@ -447,3 +447,53 @@ def test_block_scalars(libs):
         offs = rng.integers(0, 65535, num).astype(np.uint16)
         o.denoise_dct(da, ra, offs, num); r.denoise_dct(db, rb, offs, num)
         assert np.array_equal(da, db) and np.array_equal(ra, rb)
+
+
+def mv_cost_table(lam, radius):
+    """BitCost::setQP's table (bitcost.cpp:44-54, 91-101) for one lambda, as a uint16 array centred at `radius`"""
+    i = np.arange(radius + 1, dtype=np.float32)
+    bits = np.log(i + np.float32(1)).astype(np.float32) * np.float32(2.0 / np.log(np.float32(2.0))) + np.float32(1.718)
+    bits[0] = np.float32(0.718)
+    half = np.minimum(bits.astype(np.float64) * lam + 0.5, (1 << 15) - 1).astype(np.uint16)
+    return np.concatenate([half[:0:-1], half])
+
+
+def test_me_full_search(libs):
+    """exhaustive integer search: oracle loop vs the reference's sad / sad_x4 slots driven in motion.cpp's order"""
+    o, r = libs
+    rng = np.random.default_rng(53)
+    stride, rows = 192, 160
+    R = 1024
+    tabs = [mv_cost_table(4.0, R), mv_cost_table(57.0175, R), rng.integers(0, 65536, 2 * R + 1).astype(np.uint16),
+            np.zeros(2 * R + 1, np.uint16)]
+    for bi, (fenc, ref) in enumerate(pixel_bufs(rng, o.depth, stride * rows)):
+        if bi == 0:
+            ref[:] = fenc                      # a natural-looking match somewhere in the window
+            ref[1:] = np.where(rng.random(ref.size - 1) < 0.3, fenc[:-1], ref[1:])
+        for (w, h) in ((64, 64), (32, 24), (16, 16), (16, 4), (12, 16), (8, 8), (4, 8), (4, 4)):
+            for tab in tabs:
+                minx, miny = -int(rng.integers(0, 20)), -int(rng.integers(0, 14))
+                maxx, maxy = int(rng.integers(0, 20)), int(rng.integers(0, 14))
+                if rng.random() < 0.15: maxx = minx + int(rng.integers(0, 3))          # the x4 tail path only
+                mvp = rng.integers(-60, 61, 2).astype(np.int32)
+                bmv0 = (int(rng.integers(minx, maxx + 1)), int(rng.integers(miny, maxy + 1)))
+                of, orf = 7 * stride + 5, 40 * stride + 60
+                for bcost0 in (0x7fffffff, 0, None):
+                    if bcost0 is None:          # the cost of some candidate: exercises the tie with the starting point
+                        bcost0 = o.me_full_search(w, h, fenc, of, stride, ref, orf, stride, [bmv0[0], bmv0[1], bmv0[0], bmv0[1]], mvp, tab, R,
+                                                  (0, 0), 0x7fffffff)[2]
+                    a = o.me_full_search(w, h, fenc, of, stride, ref, orf, stride, [minx, miny, maxx, maxy], mvp, tab, R, bmv0, bcost0)
+                    b = r.me_full_search(w, h, fenc, of, stride, ref, orf, stride, [minx, miny, maxx, maxy], mvp, tab, R, bmv0, bcost0)
+                    assert a == b, (w, h, a, b)
+                    assert minx <= a[0] <= maxx and miny <= a[1] <= maxy
+    # closed form on one case: every candidate's cost in numpy, first minimum in raster order
+    fenc, ref = next(pixel_bufs(rng, o.depth, stride * rows))
+    w, h, of, orf = 8, 8, 3 * stride + 9, 50 * stride + 70
+    tab = tabs[1]; mvp = np.array([5, -9], np.int32)
+    F = fenc.reshape(rows, stride)[3:3 + h, 9:9 + w].astype(np.int64)
+    P = ref.reshape(rows, stride).astype(np.int64)
+    costs = np.array([[np.abs(F - P[50 + y:50 + y + h, 70 + x:70 + x + w]).sum() + ((int(tab[R + 4 * x - 5]) + int(tab[R + 4 * y + 9])) & 0xffff)
+                       for x in range(-9, 12)] for y in range(-6, 8)])
+    k = int(costs.argmin())
+    got = o.me_full_search(w, h, fenc, of, stride, ref, orf, stride, [-9, -6, 11, 7], mvp, tab, R, (0, 0), 0x7fffffff)
+    assert got == (k % 21 - 9, k // 21 - 6, int(costs.min()))

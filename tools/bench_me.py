@@ -1,0 +1,85 @@
+"""Exhaustive integer search (x265b200_me_full_batch) over one 2160p frame tiled into w x h PUs, +-merange window.
+The kernel is issue-bound (one VABSDIFF per sample-candidate), not HBM-bound: the table reports sample-candidates/s and
+the fraction of the SMs' integer issue rate (148 SMs x 128 lanes x SM clock), next to the reference's C loop on one host core.
+usage: python tools/bench_me.py [--depth 10] [--merange 57] [--cpu]"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from frames import Geometry, make_plane, tile_blocks          # noqa: E402
+from test_oracle_vs_ref import mv_cost_table                  # noqa: E402
+pkg = importlib.import_module("x265-mod-by-patman_b200")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--depth", type=int, default=10)
+    ap.add_argument("--merange", type=int, default=57)
+    ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
+    args = ap.parse_args()
+    D, M = args.depth, args.merange
+    ctx = pkg.Context(D, 0)
+    geo = Geometry(3840, 2160)
+    cw, ch = geo.coded()
+    vt = np.uint8 if D == 8 else np.int16
+    Fh = make_plane(geo, D, 1, "natural"); Rh = make_plane(geo, D, 2, "natural")
+    A = torch.from_numpy(Fh.view(vt)).cuda(); B = torch.from_numpy(Rh.view(vt)).cuda()
+    RAD = 4096
+    tab = mv_cost_table(12.6992, RAD)
+    dtab = torch.from_numpy(tab.view(np.int16)).cuda()
+    sm_clock = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 0
+    rows = []
+    for (w, h) in ((64, 64), (32, 32), (16, 16), (8, 8)):
+        oa, _ = tile_blocks(geo, w, h, seed=1)
+        n = oa.size
+        px = (oa - geo.origin) % geo.stride; py = (oa - geo.origin) // geo.stride
+        minx = -np.minimum(M, px + geo.margin_x - 8); maxx = np.minimum(M, cw + geo.margin_x - 8 - w - px)
+        miny = -np.minimum(M, py + geo.margin_y - 8); maxy = np.minimum(M, ch + geo.margin_y - 8 - h - py)
+        rng = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        mvp = np.zeros((n, 2), np.int32)
+        cands = int(((maxx - minx + 1) * (maxy - miny + 1)).sum())
+        d = [torch.from_numpy(a).cuda() for a in (oa.astype(np.int32), rng, mvp)]
+        bmv = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); bc = torch.full((n,), 0x7fffffff, dtype=torch.int32, device="cuda")
+
+        def run():
+            bc.fill_(0x7fffffff)
+            ctx.me_full_batch(w, h, M, A, geo.stride, B, geo.stride, d[0], d[0], d[1], d[2], dtab.data_ptr() + 2 * RAD, bmv, bc)
+        run(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[1]
+        row = {"pu": "%dx%d" % (w, h), "n_pu": int(n), "merange": M, "candidates": cands, "ms_per_frame": ms,
+               "G_sample_candidates_per_s": cands * w * h / ms / 1e6, "M_candidates_per_s": cands / ms / 1e3}
+        if args.cpu:
+            import cpulibs
+            orc = cpulibs.Oracle(D)
+            k = max(1, min(n, int(2e9 / (cands / n * w * h))))       # ~2 G sample-candidates of CPU work
+            sel = np.linspace(0, n - 1, k).astype(np.int64)
+            mv = np.zeros((k, 2), np.int32); c = np.full(k, 0x7fffffff, np.int32)
+            t0 = time.perf_counter()
+            orc.me_full_batch(w, h, Fh, geo.stride, Rh, geo.stride, oa[sel].astype(np.int32), oa[sel].astype(np.int32), rng[sel].copy(), mvp[sel].copy(),
+                              tab, RAD, mv, c)
+            dt = time.perf_counter() - t0
+            cc = int(((maxx - minx + 1) * (maxy - miny + 1))[sel].sum())
+            row["cpu_port_1core_G_sample_candidates_per_s"] = cc * w * h / dt / 1e9
+            got_mv = bmv.cpu().numpy()[sel]; got_c = bc.cpu().numpy()[sel]
+            row["cpu_sample_matches"] = bool(np.array_equal(got_mv, mv) and np.array_equal(got_c, c))
+        rows.append(row)
+        print(json.dumps(row), file=sys.stderr)
+    ctx.check()
+    print(json.dumps({"depth": D, "rows": rows}))
+
+
+if __name__ == "__main__":
+    main()

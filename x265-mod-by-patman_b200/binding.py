@@ -142,6 +142,11 @@ class Context:
         self._call("x265b200_subpel_cmp_batch", op, w, h, _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(frac), K,
                    int(offF.numel()), _dp(cost), C.c_void_p(stream))
 
+    def me_full_batch(self, w, h, merange, fenc, sf, ref, sr, offF, offR, rng, mvp, cost_tab_centre, bmv, bcost, stream=0):
+        """cost_tab_centre: integer device address of the centre element of the uint16 mv-cost table"""
+        self._call("x265b200_me_full_batch", w, h, int(merange), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(rng), _dp(mvp),
+                   C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(bmv), _dp(bcost), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

@@ -1,0 +1,232 @@
+// mesearch.cu -- exhaustive integer motion search for a batch of prediction units (reference encoder/motion.cpp:1593-1637,
+// the X265_FULL_SEARCH case of MotionEstimate::motionEstimate; vector cost from encoder/bitcost.h:53-56).
+//
+// The reference walks the search window in raster order calling sad_x4 on four neighbouring candidates at a time, so
+// every candidate re-reads the whole block from cache.  Here one CTA owns one PU: the part of the reference picture its
+// search window touches is staged in shared memory once (in one piece when it fits, else in super-tiles), a warp takes
+// work items of 32 candidate columns (one per lane) x J candidate rows, and register-tiles the J rows: a window sample
+// fetched from shared memory is compared against J different fenc rows held in a register ring, so the inner loop is
+// ~one VABSDIFF per sample-candidate (8-bit pictures: one VABSDIFF4 per four).  The kernel is integer-issue bound, not
+// HBM bound: a PU reads its window once (tens of KB) and spends ~10^5..10^7 ALU operations on it.
+// Raster-order tie-breaking (COPY2_IF_LT keeps the first strictly-smaller cost) is carried by the reduction key
+// (cost << 32 | raster index + 1); index 0 is the caller's initial vector, which therefore wins every tie.
+#include "internal.h"
+#include "device_util.cuh"
+
+namespace b200 {
+
+constexpr int ME_WARPS = 8;
+constexpr int ME_SMEM_CAP = 74 * 1024;          // per CTA: three CTAs (24 warps) per SM
+
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// One (window row, fenc row) meeting for a lane: 16-bit samples one at a time, 8-bit samples four at a time.
+template<typename PIX> struct MeStep;
+template<> struct MeStep<uint16_t>
+{
+    static constexpr int XSTEP = 1;
+    typedef uint16_t cell;
+    __device__ static __forceinline__ const cell* win_ptr(const uint16_t* win, int lane, int x, unsigned&) { return win + lane + x; }
+    __device__ static __forceinline__ unsigned load_win(const cell* p, unsigned) { return *p; }
+    __device__ static __forceinline__ unsigned acc(unsigned r, unsigned f, unsigned a) { return __usad(r, f, a); }
+};
+template<> struct MeStep<uint8_t>
+{
+    static constexpr int XSTEP = 4;
+    typedef uint32_t cell;
+    // a lane's four samples at byte offset lane + x straddle two aligned words; the realigning shift is a per-lane constant
+    __device__ static __forceinline__ const cell* win_ptr(const uint8_t* win, int lane, int x, unsigned& sh)
+    {
+        sh = (lane & 3) * 8;
+        return (const cell*)(win + (lane & ~3) + x);
+    }
+    __device__ static __forceinline__ unsigned load_win(const cell* p, unsigned sh) { return __funnelshift_r(p[0], p[1], sh); }
+    __device__ static __forceinline__ unsigned acc(unsigned r, unsigned f, unsigned a) { return sad4_acc(r, f, a); }
+};
+
+// SX x SY: candidates staged per super-tile; pitch: window row pitch in samples (a multiple of 4); fenc is kept at pitch w.
+template<typename PIX, int J>
+__global__ void __launch_bounds__(ME_WARPS * 32)
+me_full_kernel(const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
+               const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
+               const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int w, int h, int SX, int SY, int pitch,
+               int32_t* __restrict__ bmv, int32_t* __restrict__ bcost)
+{
+    typedef MeStep<PIX> S;
+    typedef typename S::cell cell;
+    extern __shared__ __align__(16) uint8_t me_smem[];
+    __shared__ unsigned long long red[ME_WARPS];
+    PIX* fencS = (PIX*)me_smem;
+    PIX* win = fencS + w * h;                                   // w * h * sizeof(PIX) is a multiple of 16
+
+    const int pu = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
+    if (maxx < minx || maxy < miny) return;                     // empty window: (bmv, bcost) stay as they are
+    const int mvpx = mvp[2 * pu], mvpy = mvp[2 * pu + 1];
+    const PIX* f = fenc + offF[pu];
+    const PIX* r0 = ref + offR[pu];
+    const unsigned RW = (unsigned)(maxx - minx + 1);
+
+    for (int y = warp; y < h; y += ME_WARPS)
+        for (int x = lane; x < w; x += 32) fencS[y * w + x] = f[(intptr_t)y * strideF + x];
+
+    unsigned long long best = ~0ull;
+    const int fpitch = w / S::XSTEP, wpitch = pitch / S::XSTEP; // in cells
+    for (int sy0 = miny; sy0 <= maxy; sy0 += SY)
+        for (int sx0 = minx; sx0 <= maxx; sx0 += SX)
+        {
+            const int ncx = min(SX, maxx - sx0 + 1), ncy = min(SY, maxy - sy0 + 1);
+            const int rows = ncy + h - 1, cols = ncx + w - 1;
+            __syncthreads();                                    // the previous super-tile has been consumed (and fencS is written)
+            const PIX* src = r0 + (intptr_t)sy0 * strideR + sx0;
+            for (int y = warp; y < rows; y += ME_WARPS)
+            {
+#pragma unroll 4
+                for (int x = lane; x < cols; x += 32) win[y * pitch + x] = src[(intptr_t)y * strideR + x];
+            }
+            __syncthreads();
+
+            const int ngx = (ncx + 31) >> 5, items = ngx * ((ncy + J - 1) / J);
+            for (int item = warp; item < items; item += ME_WARPS)
+            {
+                const int gy = item / ngx, cx0 = (item - gy * ngx) * 32, dy0 = gy * J;
+                unsigned acc[J];
+#pragma unroll
+                for (int j = 0; j < J; j++) acc[j] = 0;
+                for (int x = 0; x < w; x += S::XSTEP)
+                {
+                    unsigned sh = 0;
+                    const cell* wp = S::win_ptr(win + dy0 * pitch + cx0, lane, x, sh);
+                    const cell* fp = (const cell*)(fencS + x);
+                    unsigned ring[J];
+                    // window row ry (relative to dy0) meets fenc row ry - j for candidate row j
+                    if (h >= J)
+                    {
+#pragma unroll
+                        for (int k = 0; k < J; k++)
+                        {   // first rows: candidate rows j > k have not started yet
+                            unsigned R = S::load_win(wp + k * wpitch, sh);
+                            ring[k] = fp[k * fpitch];
+#pragma unroll
+                            for (int j = 0; j <= k; j++) acc[j] = S::acc(R, ring[k - j], acc[j]);
+                        }
+                        for (int ry0 = J; ry0 < h; ry0 += J)
+                        {
+#pragma unroll
+                            for (int k = 0; k < J; k++)
+                            {
+                                unsigned R = S::load_win(wp + (ry0 + k) * wpitch, sh);
+                                ring[k] = fp[(ry0 + k) * fpitch];
+#pragma unroll
+                                for (int j = 0; j < J; j++) acc[j] = S::acc(R, ring[(k - j + J) % J], acc[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < J - 1; k++)
+                        {   // rows below the block of candidate rows 0 .. k
+                            unsigned R = S::load_win(wp + (h + k) * wpitch, sh);
+#pragma unroll
+                            for (int j = k + 1; j < J; j++) acc[j] = S::acc(R, ring[(k - j + J) % J], acc[j]);
+                        }
+                    }
+                }
+
+                const int dx = sx0 + cx0 + lane;
+                if (cx0 + lane < ncx)
+                {
+                    const unsigned cx = costTab[(dx << 2) - mvpx];
+#pragma unroll
+                    for (int j = 0; j < J; j++)
+                        if (dy0 + j < ncy)
+                        {
+                            const int dy = sy0 + dy0 + j;
+                            unsigned cost = acc[j] + (uint16_t)(cx + costTab[(dy << 2) - mvpy]);   // bitcost.h:56 returns uint16_t
+                            unsigned idx = (unsigned)(dy - miny) * RW + (unsigned)(dx - minx) + 1u;
+                            unsigned long long key = ((unsigned long long)cost << 32) | idx;
+                            best = key < best ? key : best;
+                        }
+                }
+            }
+        }
+
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) red[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 1; k < ME_WARPS; k++) best = red[k] < best ? red[k] : best;
+        const long long cost = (long long)(best >> 32);
+        if (cost < (long long)bcost[pu])                        // strictly cheaper than the caller's starting point
+        {
+            unsigned idx = (unsigned)best - 1u;
+            bcost[pu] = (int32_t)cost;
+            bmv[2 * pu] = minx + (int)(idx % RW);
+            bmv[2 * pu + 1] = miny + (int)(idx / RW);
+        }
+    }
+}
+
+template<typename PIX, int J>
+static cudaError_t launch_me_full(const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR,
+                                  const int32_t* range, const int32_t* mvp, const uint16_t* costTab, int w, int h, int span, int n,
+                                  int32_t* bmv, int32_t* bcost, cudaStream_t st)
+{
+    // stage the whole span x span window when it fits; otherwise halve the super-tile rows, then the columns
+    const int pb = (int)sizeof(PIX);
+    int SX = span, SY = span, pitch, rows;
+    size_t bytes;
+    for (;;)
+    {
+        pitch = (SX + w + 3) & ~3;                              // covers SX + w - 1 samples (+ the 8-bit path's second word)
+        rows = (SY + J - 1) / J * J + h - 1;
+        bytes = (size_t)w * h * pb + ((size_t)rows * pitch + 64) * pb;      // + 64: lanes past the last candidate column read on
+        if (bytes <= (size_t)ME_SMEM_CAP) break;
+        if (SY > 32) SY = ((SY + 1) / 2 + J - 1) / J * J;
+        else if (SX > 32) SX = ((SX + 1) / 2 + 31) & ~31;
+        else break;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void*)me_full_kernel<PIX, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_CAP);
+    if (e != cudaSuccess) return e;
+    me_full_kernel<PIX, J><<<n, ME_WARPS * 32, bytes, st>>>((const PIX*)fenc, strideF, (const PIX*)ref, strideR, offF, offR, range, mvp, costTab,
+                                                           w, h, SX, SY, pitch, bmv, bcost);
+    return cudaSuccess;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                      const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
+                                      const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0) return fail(ctx, X265B200_ERR_ARG, "me_full: bad geometry");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int span = 2 * (merange > 512 ? 512 : merange) + 1;   // sizing hint only: larger windows are walked in super-tiles
+    cudaError_t e;
+    // eight candidate rows per work item wherever the PU height allows: half the shared-memory loads per VABSDIFF
+    if (ctx->pixbytes == 1 && (h & 7))
+        e = launch_me_full<uint8_t, 4>(fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, w, h, span, n, bmv, bcost, st);
+    else if (ctx->pixbytes == 1)
+        e = launch_me_full<uint8_t, 8>(fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, w, h, span, n, bmv, bcost, st);
+    else if (h & 7)
+        e = launch_me_full<uint16_t, 4>(fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, w, h, span, n, bmv, bcost, st);
+    else
+        e = launch_me_full<uint16_t, 8>(fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, w, h, span, n, bmv, bcost, st);
+    if (e != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "me_full: shared memory attribute", e);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
