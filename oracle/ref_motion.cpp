@@ -1,0 +1,46 @@
+/* ref_motion.cpp -- compiles the reference's MotionEstimate (encoder/motion.cpp), BitCost (encoder/bitcost.cpp) and the
+ * Yuv block cache (common/yuv.cpp) into oracle/_ref/libx265ref_<depth>.so and drives
+ * MotionEstimate::motionEstimate through the lookahead-style setSourcePU (luma only, no PicYuv), so the oracle's
+ * restatement of the search is pinned against the reference's own search code, not just its SAD slots.
+ * The sources are included from where they lie; nothing is copied.  Built like ref_framefilter.cpp
+ * (-ffunction-sections, --gc-sections): whatever of those files needs the rest of the encoder is never linked.
+ * x265_malloc / x265_free / general_log come from ref_shim.cpp's stand-ins (common/common.cpp would drag in the
+ * parameter parser).  Test infrastructure, never shipped. */
+#include "motion.cpp"
+#include "bitcost.cpp"
+#include "yuv.cpp"
+
+using namespace X265_NS;
+
+extern "C" void ref_ensure(void);        /* ref_shim.cpp: C primitives into the global table */
+
+extern "C" __attribute__((visibility("default")))
+int ref_motion_estimate(int method, int subme, int w, int h, pixel* fencPlane, intptr_t strideF, intptr_t offF,
+                        pixel* refPlane, intptr_t strideR, intptr_t offR, const int32_t* range /* mvmin.x, mvmin.y, mvmax.x, mvmax.y */,
+                        const int32_t* qmvp, int numCand, const int32_t* mvc, int merange, int qp, int32_t* outQMv)
+{
+    static bool scales = false;
+    if (!scales) { ref_ensure(); MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setQP(qp);
+    me.setSourcePU(fencPlane, strideF, offF, w, h, method, subme);
+    ReferencePlanes ref;
+    ref.fpelPlane[0] = refPlane + offR;          /* setSourcePU's offset also shifts the reference block; offR is the rest */
+    ref.lumaStride = strideR;
+    MV mvmin(range[0], range[1]), mvmax(range[2], range[3]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[16];
+    for (int i = 0; i < numCand && i < 16; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mvmin, mvmax, mvp, numCand, cands, merange, out, 1, false);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
+/* the lambda-scaled mv cost table BitCost::setQP builds, copied out for the other implementations: [-radius, radius] */
+extern "C" __attribute__((visibility("default")))
+void ref_mvcost_table(int qp, int radius, uint16_t* out)
+{
+    struct Peek : BitCost { const uint16_t* tab() const { return m_cost; } } bc;
+    bc.setQP(qp);
+    for (int i = -radius; i <= radius; i++) out[i + radius] = bc.tab()[i];
+}

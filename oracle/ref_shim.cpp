@@ -111,6 +111,9 @@ void ref_get_dct_matrix(int N, int16_t* out)
 void ref_get_luma_taps(int16_t* out) { memcpy(out, g_lumaFilter, sizeof(int16_t) * 4 * 8); }
 void ref_get_chroma_taps(int16_t* out) { memcpy(out, g_chromaFilter, sizeof(int16_t) * 8 * 4); }
 
+/* fills the process-global table too (ref_motion.cpp's MotionEstimate reads it) */
+void ref_ensure(void) { ensure(); }
+
 /* ---- pixel metrics ---- */
 int ref_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
 { ensure(); int p = lumaPart(w, h); return p < 0 ? -1 : g_c.pu[p].sad(a, sa, b, sb); }

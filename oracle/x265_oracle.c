@@ -970,3 +970,119 @@ EXPORT void orc_me_full_batch(int w, int h, const pixel* fenc, intptr_t sf, cons
     for (int i = 0; i < n; i++)
         orc_me_full_search(w, h, fenc + offF[i], sf, ref + offR[i], sr, range + 4 * i, mvp + 2 * i, costTab, bmv + 2 * i, bcost + i);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * MotionEstimate::motionEstimate with searchMethod = X265_FULL_SEARCH on full-resolution planes, luma only
+ * (encoder/motion.cpp:923-1013 start point, :1593-1637 search, :1643-1773 sub-pel refinement; one slice, no vertical
+ * restriction, no chroma SATD -- the setSourcePU variant of motion.cpp:166-189).  Returns the cost, writes the qpel vector.
+ *   fref: the co-located block (vector 0,0); range: mvmin.x, mvmin.y, mvmax.x, mvmax.y in full pels;
+ *   qmvp and mvc[] in quarter pels; costTab as in orc_me_full_search.
+ * ------------------------------------------------------------------------------------------------ */
+static const int k_subpel_workload[8][5] = {      /* motion.cpp:48-58: hpel_iters, hpel_dirs, qpel_iters, qpel_dirs, hpel_satd */
+    { 1, 4, 0, 4, 0 }, { 1, 4, 1, 4, 0 }, { 1, 4, 1, 4, 1 }, { 2, 4, 1, 4, 1 },
+    { 2, 4, 2, 4, 1 }, { 1, 8, 1, 8, 1 }, { 2, 8, 1, 8, 1 }, { 2, 8, 2, 8, 1 } };
+static const int k_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };   /* motion.cpp:67 */
+
+typedef struct { int w, h; const pixel* fenc; intptr_t sf; const pixel* fref; intptr_t sr; const uint16_t* cx; const uint16_t* cy; } me_ctx;
+static int me_subpel(const me_ctx* c, int qx, int qy, int op)   /* subpelCompare, motion.cpp:1775-1803 */
+{
+    return orc_subpel_cmp(op, c->w, c->h, c->fenc, c->sf, c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->sr, c->sr, qx & 3, qy & 3);
+}
+static int me_mvcost(const me_ctx* c, int qx, int qy) { return (uint16_t)(c->cx[qx] + c->cy[qy]); }   /* bitcost.h:56 */
+static int clip3i(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+
+EXPORT int orc_motion_estimate_full(int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                                    const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                                    const uint16_t* costTab, int32_t* outQMv)
+{
+    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1] };
+    const int qminx = range[0] * 4, qminy = range[1] * 4, qmaxx = range[2] * 4, qmaxy = range[3] * 4;
+
+    /* :954-975 SAD at the clipped predictor, then at its full-pel rounding */
+    int pmvx = clip3i(qminx, qmaxx, qmvp[0]), pmvy = clip3i(qminy, qmaxy, qmvp[1]);
+    int bestprex = pmvx, bestprey = pmvy;
+    int bprecost = me_subpel(&c, pmvx, pmvy, 0);
+    int bmvx = (pmvx + 2) >> 2, bmvy = (pmvy + 2) >> 2;
+    int bcost = bprecost;
+    if ((pmvx | pmvy) & 3)
+        bcost = orc_sad(w, h, fenc, sf, fref + bmvx + (intptr_t)bmvy * sr, sr) + me_mvcost(&c, bmvx * 4, bmvy * 4);
+    /* :978-988 the zero vector */
+    if (pmvx | pmvy)
+    {
+        int cost = orc_sad(w, h, fenc, sf, fref, sr) + me_mvcost(&c, 0, 0);
+        if (cost < bcost)
+        {
+            bcost = cost; bmvx = 0;
+            bmvy = range[3] < 0 ? range[3] : 0;
+            if (bmvy < range[1]) bmvy = range[1];
+        }
+    }
+    /* :992-1004 neighbour candidates compete for the sub-pel starting point only */
+    for (int i = 0; i < numCand; i++)
+    {
+        int mx = clip3i(qminx, qmaxx, mvc[2 * i]), my = clip3i(qminy, qmaxy, mvc[2 * i + 1]);
+        if ((mx | my) && (mx != pmvx || my != pmvy) && (mx != bestprex || my != bestprey))
+        {
+            int cost = me_subpel(&c, mx, my, 0) + me_mvcost(&c, mx, my);
+            if (cost < bprecost) { bprecost = cost; bestprex = mx; bestprey = my; }
+        }
+    }
+    if (bcost == 0)
+    {   /* :1008-1012 */
+        outQMv[0] = bmvx * 4; outQMv[1] = bmvy * 4;
+        return me_mvcost(&c, bmvx * 4, bmvy * 4);
+    }
+    /* :1593-1637 */
+    {
+        int32_t mv[2] = { bmvx, bmvy }, bc = bcost;
+        orc_me_full_search(w, h, fenc, sf, fref, sr, range, qmvp, costTab, mv, &bc);
+        bmvx = mv[0]; bmvy = mv[1]; bcost = bc;
+    }
+    /* :1643-1650 */
+    if (bprecost < bcost) { bmvx = bestprex; bmvy = bestprey; bcost = bprecost; }
+    else { bmvx *= 4; bmvy *= 4; }
+
+    const int* wl = k_subpel_workload[subme];
+    if (!bcost)
+        bcost = me_mvcost(&c, bmvx, bmvy);              /* :1661-1666 */
+    else
+    {   /* :1700-1757 */
+        int hpelop = 0;
+        if (wl[4]) { bcost = me_subpel(&c, bmvx, bmvy, 1) + me_mvcost(&c, bmvx, bmvy); hpelop = 1; }
+        for (int iter = 0; iter < wl[0]; iter++)
+        {
+            int bdir = 0;
+            for (int i = 1; i <= wl[1]; i++)
+            {
+                int qx = bmvx + k_square1[i][0] * 2, qy = bmvy + k_square1[i][1] * 2;
+                if (qy < qminy || qy > qmaxy) continue;
+                int cost = me_subpel(&c, qx, qy, hpelop) + me_mvcost(&c, qx, qy);
+                if (cost < bcost) { bcost = cost; bdir = i; }
+            }
+            if (!bdir) break;
+            bmvx += k_square1[bdir][0] * 2; bmvy += k_square1[bdir][1] * 2;
+        }
+        if (!wl[4]) bcost = me_subpel(&c, bmvx, bmvy, 1) + me_mvcost(&c, bmvx, bmvy);
+        for (int iter = 0; iter < wl[2]; iter++)
+        {
+            int bdir = 0;
+            for (int i = 1; i <= wl[3]; i++)
+            {
+                int qx = bmvx + k_square1[i][0], qy = bmvy + k_square1[i][1];
+                if (qy < qminy || qy > qmaxy) continue;
+                int cost = me_subpel(&c, qx, qy, 1) + me_mvcost(&c, qx, qy);
+                if (cost < bcost) { bcost = cost; bdir = i; }
+            }
+            if (!bdir) break;
+            bmvx += k_square1[bdir][0]; bmvy += k_square1[bdir][1];
+        }
+    }
+    /* :1762-1768 the zero vector gets a last chance; the returned cost stays the winner's */
+    if (bmvx | bmvy)
+    {
+        int cost = me_subpel(&c, 0, 0, 1) + me_mvcost(&c, 0, 0);
+        if (cost <= bcost) { bmvx = 0; bmvy = 0; }
+    }
+    outQMv[0] = bmvx; outQMv[1] = bmvy;
+    return bcost;
+}

@@ -187,6 +187,16 @@ class _Base:
                                         _ptr(cost_tab, centre), _ptr(mv), C.byref(bc))
         return int(mv[0]), int(mv[1]), int(bc.value)
 
+    # ---- MotionEstimate::motionEstimate, full search + sub-pel refinement ---------------------------------------
+    def motion_estimate_full(self, subme, w, h, fenc, of, sf, ref, orf, sr, rng, qmvp, mvc, cost_tab, centre):
+        """oracle restatement; returns (qmv_x, qmv_y, cost)"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self._f("motion_estimate_full")(subme, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), _ptr(rng), _ptr(qmvp),
+                                            len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
+
     # ---- sub-pel candidate cost (subpelCompare): interpolation + sad (op 0) / satd (op 1) ----------------------
     def subpel_cmp(self, op, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp")(op, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
@@ -312,6 +322,22 @@ class Reference(_Base):
         path = os.path.join(ORACLE_DIR, "_ref", "libx265ref_%d.so" % depth)
         self.lib = C.CDLL(path)
         assert self.lib.ref_depth() == depth
+
+    ME_FULL = 5         # x265.h:513-518 X265_DIA_SEARCH .. X265_FULL_SEARCH
+
+    def motion_estimate(self, method, subme, w, h, fenc, of, sf, ref, orf, sr, rng, qmvp, mvc, merange, qp):
+        """the reference's own MotionEstimate::motionEstimate (oracle/ref_motion.cpp); returns (qmv_x, qmv_y, cost)"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self.lib.ref_motion_estimate(method, subme, w, h, _ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(ref), C.c_ssize_t(sr),
+                                         C.c_ssize_t(orf - of), _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), merange, qp, _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
+
+    def mvcost_table(self, qp, radius):
+        out = np.zeros(2 * radius + 1, np.uint16)
+        self.lib.ref_mvcost_table(qp, radius, _ptr(out))
+        return out
 
     def sa8d(self, w, h, a, oa, sa, b, ob, sb, chroma=0):
         return self._f("sa8d")(chroma, w, h, _ptr(a, oa), C.c_ssize_t(sa), _ptr(b, ob), C.c_ssize_t(sb))

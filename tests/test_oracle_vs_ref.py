@@ -497,3 +497,41 @@ def test_me_full_search(libs):
     k = int(costs.argmin())
     got = o.me_full_search(w, h, fenc, of, stride, ref, orf, stride, [-9, -6, 11, 7], mvp, tab, R, (0, 0), 0x7fffffff)
     assert got == (k % 21 - 9, k // 21 - 6, int(costs.min()))
+
+
+def test_motion_estimate_full(libs):
+    """the oracle's motionEstimate(FULL) restatement vs the reference's MotionEstimate::motionEstimate itself
+    (compiled from encoder/motion.cpp), every subme level, with neighbour candidates and predictors inside / outside the range"""
+    o, r = libs
+    from frames import Geometry, make_plane
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(61)
+    F = make_plane(geo, o.depth, 71, "natural"); R = make_plane(geo, o.depth, 72, "natural")
+    R2 = np.roll(F, 3 * geo.stride + 5)                   # a real match at (+5, +3): zero-cost exits and tight refinement
+    RAD = 2048
+    cw, ch = geo.coded()
+    nonzero_exit = 0
+    for case in range(160):
+        w, h = [(8, 8), (16, 16), (16, 8), (32, 32), (8, 16), (64, 64), (24, 32), (12, 16)][case % 8]
+        subme = case % 8 if case < 128 else int(rng.integers(0, 8))
+        qp = int(rng.integers(0, 52))
+        tab = r.mvcost_table(qp, RAD)
+        ref = R2 if case % 5 == 0 else R
+        x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
+        of = geo.origin + y * geo.stride + x
+        m = int(rng.integers(1, 13))
+        # keep block + 8-tap margins inside the padded plane
+        minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 8 - w - x)
+        miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 8 - h - y)
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, 2)
+        if case % 7 == 0: qmvp[:] = 0
+        if case % 11 == 0: qmvp = (qmvp // 4) * 4
+        if case % 5 == 0 and case % 2 == 0: qmvp[:] = (20, 12)          # exactly the shifted copy: bcost == 0 at the start
+        nc = int(rng.integers(0, 5))
+        mvc = rng.integers(-4 * m - 6, 4 * m + 7, (nc, 2))
+        if nc > 1: mvc[1] = qmvp
+        a = o.motion_estimate_full(subme, w, h, F, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD)
+        b = r.motion_estimate(r.ME_FULL, subme, w, h, F, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, m, qp)
+        assert a == b, (case, w, h, subme, a, b)
+        nonzero_exit += a[2] > 0
+    assert nonzero_exit > 100
