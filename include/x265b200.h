@@ -204,6 +204,21 @@ int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const v
                            const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
                            const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
+/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod = X265_FULL_SEARCH for n
+ * PUs of w x h on full-resolution luma planes: SAD at the clipped predictor qmvp / its full-pel rounding / the zero vector
+ * and at numCand (0..16, the same count for every PU; pad with 0,0) neighbour vectors mvc[(i * numCand + k) * 2 ..] in
+ * quarter pels, the exhaustive integer search of x265b200_me_full_batch, then the half-pel / quarter-pel refinement of
+ * SubpelWorkload[subpelRefine] (0..7, motion.cpp:48-58) through the fused interpolation + SAD/SATD kernels, and the
+ * zero vector's last chance.  outQMv[2i..2i+1] (quarter pel) and outCost[i] are what the reference returns in outQMv and
+ * as its result, including the early exits on zero residual.  Luma only, one slice (the lookahead-style setSourcePU,
+ * motion.cpp:166-189).  range, qmvp, costTab, offR as in x265b200_me_full_batch; plane strides multiples of 4.
+ * The batch advances in lock step, one launch per step over all PUs; per-PU decisions live in stream-ordered scratch. */
+int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+                                   const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                   const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                   int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
+                                   int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

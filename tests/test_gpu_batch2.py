@@ -513,3 +513,51 @@ def test_me_full_batch(depth):
                 assert np.array_equal(gc.cpu().numpy(), want_c), (w, h, ti)
                 assert np.array_equal(gmv.cpu().numpy(), want_mv), (w, h, ti)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_batch(depth):
+    """whole motionEstimate (predictor candidates, exhaustive search, sub-pel refinement, zero-vector chance) for a batch of
+    PUs vs the oracle's restatement -- itself pinned to the reference's MotionEstimate::motionEstimate by the CPU suite --
+    for every SubpelWorkload level, with and without neighbour candidates, including PUs that leave early on zero residual"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane
+    from test_oracle_vs_ref import mv_cost_table
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    F = make_plane(geo, depth, 81, "natural"); R = make_plane(geo, depth, 82, "natural")
+    R2 = np.roll(F, 2 * geo.stride + 3)                   # exact copy displaced by (+3, +2)
+    rng = np.random.default_rng(500 + depth)
+    cw, ch = geo.coded()
+    RAD = 2048
+    tab = mv_cost_table(8.9797, RAD); dtab = dev(tab.view(np.int16))
+    dF = dev(pix_view(F, depth))
+    shapes = [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 24), (12, 16), (64, 32), (16, 4), (8, 4), (24, 32), (4, 8), (4, 4)]
+    for si, (w, h) in enumerate(shapes):
+        subme = si % 8
+        n, nc = 40, (0, 2, 5)[si % 3]
+        x = rng.integers(0, cw - w + 1, n); y = rng.integers(0, ch - h + 1, n)
+        off = (geo.origin + y * geo.stride + x).astype(np.int32)
+        m = int(rng.integers(3, 20))
+        minx = -np.minimum(m, x + geo.margin_x - 8); maxx = np.minimum(m, cw + geo.margin_x - 8 - w - x)
+        miny = -np.minimum(m, y + geo.margin_y - 8); maxy = np.minimum(m, ch + geo.margin_y - 8 - h - y)
+        rngs = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, (n, 2)).astype(np.int32)
+        qmvp[::7] = 0; qmvp[1::9] = (12, 8)               # (12, 8) q-pel is the displaced copy: zero residual on R2
+        mvc = rng.integers(-4 * m - 6, 4 * m + 7, (n, max(nc, 1), 2)).astype(np.int32)
+        mvc[::4, 0] = (12, 8)
+        for ref_plane in (R, R2):
+            want_mv = np.zeros((n, 2), np.int32); want_c = np.zeros(n, np.int32)
+            for i in range(n):
+                a = orc.motion_estimate_full(subme, w, h, F, int(off[i]), geo.stride, ref_plane, int(off[i]), geo.stride, rngs[i], qmvp[i],
+                                             mvc[i, :nc], tab, RAD)
+                want_mv[i] = a[:2]; want_c[i] = a[2]
+            gmv = torch.full((n, 2), -7777, dtype=torch.int32, device="cuda"); gc = torch.full((n,), -7777, dtype=torch.int32, device="cuda")
+            ctx.motion_estimate_batch(w, h, m, subme, dF, geo.stride, dev(pix_view(ref_plane, depth)), geo.stride, dev(off), dev(off), dev(rngs),
+                                      dev(qmvp), nc, dev(np.ascontiguousarray(mvc[:, :nc])) if nc else None, dtab.data_ptr() + 2 * RAD, gmv, gc)
+            assert np.array_equal(gc.cpu().numpy(), want_c), (w, h, subme)
+            assert np.array_equal(gmv.cpu().numpy(), want_mv), (w, h, subme)
+        if si == 0:
+            assert (want_c < 200).any()                   # the displaced copy produced early exits / tight matches
+    ctx.check()

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--depth", type=int, default=10)
     ap.add_argument("--merange", type=int, default=57)
+    ap.add_argument("--subme", type=int, default=2)
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
     D, M = args.depth, args.merange
@@ -61,6 +62,21 @@ def main():
         ms = sorted(ts)[1]
         row = {"pu": "%dx%d" % (w, h), "n_pu": int(n), "merange": M, "candidates": cands, "ms_per_frame": ms,
                "G_sample_candidates_per_s": cands * w * h / ms / 1e6, "M_candidates_per_s": cands / ms / 1e3}
+        # the whole motionEstimate chain (2 neighbour candidates, subme 2 = the medium preset's workload)
+        qmvp = torch.randint(-40, 41, (n, 2), dtype=torch.int32, device="cuda")
+        mvc = torch.randint(-40, 41, (n, 2, 2), dtype=torch.int32, device="cuda")
+        oq = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); oc = torch.zeros((n,), dtype=torch.int32, device="cuda")
+
+        def run_me():
+            ctx.motion_estimate_batch(w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc, dtab.data_ptr() + 2 * RAD, oq, oc)
+        run_me(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); run_me(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        row["motion_estimate_ms_per_frame"] = sorted(ts)[1]
+        row["motion_estimate_subme"] = args.subme
         if args.cpu:
             import cpulibs
             orc = cpulibs.Oracle(D)

@@ -147,6 +147,12 @@ class Context:
         self._call("x265b200_me_full_batch", w, h, int(merange), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(rng), _dp(mvp),
                    C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(bmv), _dp(bcost), C.c_void_p(stream))
 
+    def motion_estimate_batch(self, w, h, merange, subme, fenc, sf, ref, sr, offF, offR, rng, qmvp, num_cand, mvc, cost_tab_centre,
+                              out_qmv, out_cost, stream=0):
+        self._call("x265b200_motion_estimate_batch", w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR),
+                   _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(out_qmv), _dp(out_cost),
+                   C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

@@ -1,0 +1,251 @@
+// motion.cu -- MotionEstimate::motionEstimate for a batch of prediction units, searchMethod = X265_FULL_SEARCH, luma only
+// (reference encoder/motion.cpp:923-1013 start point, :1593-1637 integer search, :1643-1773 sub-pel refinement and the
+// zero-vector last chance; the setSourcePU variant of motion.cpp:166-189: one slice, no vertical restriction).
+//
+// The reference runs this per PU as a chain of data-dependent steps.  Across thousands of PUs the steps line up: every
+// PU measures its predictor candidates, then searches its window, then takes the same number of half-pel and
+// quarter-pel rounds (SubpelWorkload, motion.cpp:48-58).  So the batch advances in lock step, each step one launch over
+// all PUs, with the per-PU decisions (COPY2_IF_LT chains, early `break`s, the bcost == 0 exits) kept in small state
+// arrays and taken by one thread per PU between the heavy launches:
+//     start_gen -> subpel_cmp_batch(SAD) -> start_select -> me_full_batch -> [round: select+gen -> subpel_cmp_batch] x R -> finish
+// The heavy launches are the library's own batched entries (fused interpolation + SAD/SATD, exhaustive search).
+// A PU that left the chain early (zero residual) or whose refinement loop broke keeps producing harmless candidates at
+// its current vector so the launches stay dense; its state no longer changes.
+#include "internal.h"
+
+namespace b200 {
+
+enum { ME_FIN = 1, ME_SKIP = 2, ME_STOP = 4 };
+constexpr int ME_MAX_CAND = 16;
+
+// one refinement round: `dirs` neighbours at distance `step` (2 = half pel, 1 = quarter pel) around the running best
+struct MeRound { int step, dirs, remeasure, newPhase, zeroSlot, K; };
+
+__constant__ int c_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };   // motion.cpp:67
+
+struct MeState
+{
+    int32_t* pmv;       // 2n  clipped predictor, quarter pel
+    int32_t* bestpre;   // 2n
+    int32_t* bprecost;  // n
+    int32_t* bmv;       // 2n  full pel until the search is over, quarter pel afterwards
+    int32_t* bcost;     // n
+    int32_t* flags;     // n
+    int32_t* eff;       // 4n  search window handed to the exhaustive search (empty for finished PUs)
+    int32_t* candOff;   // n * KMAX
+    int32_t* candFrac;  // n * KMAX
+    int32_t* candCost;  // n * KMAX
+};
+
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+__device__ __forceinline__ int mvcost(const uint16_t* tab, int mvpx, int mvpy, int qx, int qy)
+{
+    return (uint16_t)(tab[qx - mvpx] + tab[qy - mvpy]);       // bitcost.h:56
+}
+__device__ __forceinline__ void put_cand(const MeState& s, size_t slot, int base, intptr_t strideR, int qx, int qy)
+{
+    s.candOff[slot] = base + (qx >> 2) + (qy >> 2) * (int)strideR;      // subpelCompare, motion.cpp:1777-1781
+    s.candFrac[slot] = (qx & 3) | ((qy & 3) << 4);
+}
+
+__global__ void me_start_gen(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
+                             const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, MeState s)
+{
+    int pu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pu >= n) return;
+    const int qminx = range[4 * pu] * 4, qminy = range[4 * pu + 1] * 4, qmaxx = range[4 * pu + 2] * 4, qmaxy = range[4 * pu + 3] * 4;
+    const int px = clip3(qminx, qmaxx, qmvp[2 * pu]), py = clip3(qminy, qmaxy, qmvp[2 * pu + 1]);
+    s.pmv[2 * pu] = px; s.pmv[2 * pu + 1] = py;
+    const int base = offR[pu];
+    const size_t o = (size_t)pu * K;
+    put_cand(s, o, base, strideR, px, py);
+    put_cand(s, o + 1, base, strideR, ((px + 2) >> 2) * 4, ((py + 2) >> 2) * 4);
+    put_cand(s, o + 2, base, strideR, 0, 0);
+    for (int i = 0; i < nc; i++)
+        put_cand(s, o + 3 + i, base, strideR, clip3(qminx, qmaxx, mvc[((size_t)pu * nc + i) * 2]), clip3(qminy, qmaxy, mvc[((size_t)pu * nc + i) * 2 + 1]));
+}
+
+__global__ void me_start_select(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
+                                const int32_t* __restrict__ range, const uint16_t* __restrict__ tab, MeState s,
+                                int32_t* __restrict__ outQMv, int32_t* __restrict__ outCost)
+{
+    int pu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pu >= n) return;
+    const int mvpx = qmvp[2 * pu], mvpy = qmvp[2 * pu + 1];
+    const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
+    const int pmvx = s.pmv[2 * pu], pmvy = s.pmv[2 * pu + 1];
+    const int32_t* cost = s.candCost + (size_t)pu * K;
+    // motion.cpp:954-975
+    int bestprex = pmvx, bestprey = pmvy, bprecost = cost[0];
+    int bmvx = (pmvx + 2) >> 2, bmvy = (pmvy + 2) >> 2, bcost = bprecost;
+    if ((pmvx | pmvy) & 3) bcost = cost[1] + mvcost(tab, mvpx, mvpy, bmvx * 4, bmvy * 4);
+    if (pmvx | pmvy)
+    {   // :978-988
+        int c = cost[2] + mvcost(tab, mvpx, mvpy, 0, 0);
+        if (c < bcost) { bcost = c; bmvx = 0; bmvy = max(min(0, maxy), miny); }
+    }
+    for (int i = 0; i < nc; i++)
+    {   // :992-1004
+        int mx = clip3(minx * 4, maxx * 4, mvc[((size_t)pu * nc + i) * 2]), my = clip3(miny * 4, maxy * 4, mvc[((size_t)pu * nc + i) * 2 + 1]);
+        if ((mx | my) && (mx != pmvx || my != pmvy) && (mx != bestprex || my != bestprey))
+        {
+            int c = cost[3 + i] + mvcost(tab, mvpx, mvpy, mx, my);
+            if (c < bprecost) { bprecost = c; bestprex = mx; bestprey = my; }
+        }
+    }
+    s.bestpre[2 * pu] = bestprex; s.bestpre[2 * pu + 1] = bestprey; s.bprecost[pu] = bprecost;
+    s.bmv[2 * pu] = bmvx; s.bmv[2 * pu + 1] = bmvy; s.bcost[pu] = bcost;
+    const bool fin = bcost == 0;                               // :1008-1012
+    s.flags[pu] = fin ? ME_FIN : 0;
+    if (fin)
+    {
+        outQMv[2 * pu] = bmvx * 4; outQMv[2 * pu + 1] = bmvy * 4;
+        outCost[pu] = mvcost(tab, mvpx, mvpy, bmvx * 4, bmvy * 4);
+    }
+    s.eff[4 * pu] = fin ? 1 : minx; s.eff[4 * pu + 1] = miny; s.eff[4 * pu + 2] = fin ? 0 : maxx; s.eff[4 * pu + 3] = maxy;
+}
+
+// mode bit 0: the step after the integer search (:1643-1666); bit 1: take the decisions of round `prev` (:1700-1757);
+// bit 2: emit the candidates of round `next`; bit 3: zero-vector last chance and outputs (:1762-1772)
+__global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, const int32_t* __restrict__ qmvp,
+                                const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR,
+                                const uint16_t* __restrict__ tab, MeState s, int32_t* __restrict__ outQMv, int32_t* __restrict__ outCost)
+{
+    int pu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pu >= n) return;
+    int flags = s.flags[pu];
+    const int mvpx = qmvp[2 * pu], mvpy = qmvp[2 * pu + 1];
+    const int qminy = range[4 * pu + 1] * 4, qmaxy = range[4 * pu + 3] * 4;
+    int bmvx = s.bmv[2 * pu], bmvy = s.bmv[2 * pu + 1], bcost = s.bcost[pu];
+    int zcost = 0;
+
+    if ((mode & 1) && !(flags & ME_FIN))
+    {
+        const int bprecost = s.bprecost[pu];
+        if (bprecost < bcost) { bmvx = s.bestpre[2 * pu]; bmvy = s.bestpre[2 * pu + 1]; bcost = bprecost; }
+        else { bmvx *= 4; bmvy *= 4; }
+        if (!bcost) { bcost = mvcost(tab, mvpx, mvpy, bmvx, bmvy); flags |= ME_SKIP; }
+    }
+    if (mode & 2)
+    {
+        const int32_t* cost = s.candCost + (size_t)pu * prev.K;
+        if (prev.zeroSlot) zcost = cost[prev.K - 1];
+        if (prev.newPhase) flags &= ~ME_STOP;
+        if (!(flags & (ME_FIN | ME_SKIP | ME_STOP)))
+        {
+            if (prev.remeasure) bcost = cost[0] + mvcost(tab, mvpx, mvpy, bmvx, bmvy);
+            int bdir = 0;
+            for (int i = 1; i <= prev.dirs; i++)
+            {
+                int qx = bmvx + c_square1[i][0] * prev.step, qy = bmvy + c_square1[i][1] * prev.step;
+                if (qy < qminy || qy > qmaxy) continue;
+                int c = cost[i] + mvcost(tab, mvpx, mvpy, qx, qy);
+                if (c < bcost) { bcost = c; bdir = i; }
+            }
+            if (bdir) { bmvx += c_square1[bdir][0] * prev.step; bmvy += c_square1[bdir][1] * prev.step; }
+            else if (prev.dirs) flags |= ME_STOP;
+        }
+    }
+    if (mode & 4)
+    {
+        const size_t o = (size_t)pu * next.K;
+        const int base = offR[pu];
+        const bool live = !(flags & ME_FIN);                   // a finished PU's bmv is still in full pels: park it on the zero vector
+        const int cx = live ? bmvx : 0, cy = live ? bmvy : 0;
+        put_cand(s, o, base, strideR, cx, cy);
+        for (int i = 1; i <= next.dirs; i++)
+        {
+            int qx = cx + c_square1[i][0] * next.step, qy = cy + c_square1[i][1] * next.step;
+            if (!live || qy < qminy || qy > qmaxy) { qx = cx; qy = cy; }      // never measured by the reference: stay on a valid block
+            put_cand(s, o + i, base, strideR, qx, qy);
+        }
+        if (next.zeroSlot) put_cand(s, o + next.K - 1, base, strideR, 0, 0);
+    }
+    if ((mode & 8) && !(flags & ME_FIN))
+    {
+        if (bmvx | bmvy)
+        {
+            int c = zcost + mvcost(tab, mvpx, mvpy, 0, 0);
+            if (c <= bcost) { bmvx = 0; bmvy = 0; }             // the returned cost stays the winner's
+        }
+        outQMv[2 * pu] = bmvx; outQMv[2 * pu + 1] = bmvy; outCost[pu] = bcost;
+    }
+    s.bmv[2 * pu] = bmvx; s.bmv[2 * pu + 1] = bmvy; s.bcost[pu] = bcost; s.flags[pu] = flags;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+                                              const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                              const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                              int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
+                                              int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (subpelRefine < 0 || subpelRefine > 7 || numCand < 0 || numCand > ME_MAX_CAND || n < 0 || (numCand && !mvc))
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: bad arguments");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // SubpelWorkload, motion.cpp:48-58
+    static const int workload[8][5] = { { 1, 4, 0, 4, 0 }, { 1, 4, 1, 4, 0 }, { 1, 4, 1, 4, 1 }, { 2, 4, 1, 4, 1 },
+                                        { 2, 4, 2, 4, 1 }, { 1, 8, 1, 8, 1 }, { 2, 8, 1, 8, 1 }, { 2, 8, 2, 8, 1 } };
+    const int* wl = workload[subpelRefine];
+    MeRound rounds[8]; int ops[8]; int R = 0;
+    for (int it = 0; it < wl[0]; it++)
+    {
+        rounds[R] = MeRound{ 2, wl[1], it == 0 && wl[4], it == 0, 0, 0 };
+        ops[R++] = wl[4] ? X265B200_SATD : X265B200_SAD;
+    }
+    for (int it = 0; it < (wl[2] ? wl[2] : 1); it++)
+    {   // with no quarter-pel iterations a SAD half-pel search is still re-measured with SATD (:1729-1731)
+        if (!wl[2] && wl[4]) break;
+        rounds[R] = MeRound{ 1, wl[2] ? wl[3] : 0, it == 0 && !wl[4], it == 0, 0, 0 };
+        ops[R++] = X265B200_SATD;
+    }
+    rounds[R - 1].zeroSlot = 1;                                // the last round is always a SATD round
+    int KMAX = 3 + numCand;
+    for (int r = 0; r < R; r++)
+    {
+        rounds[r].K = 1 + rounds[r].dirs + rounds[r].zeroSlot;
+        if (rounds[r].K > KMAX) KMAX = rounds[r].K;
+    }
+
+    int32_t* scratch = nullptr;
+    const size_t per = 2 + 2 + 1 + 2 + 1 + 1 + 4 + 3 * (size_t)KMAX;
+    B200_CUDA(ctx, cudaMallocAsync((void**)&scratch, per * n * sizeof(int32_t), st));
+    MeState s;
+    int32_t* p = scratch;
+    s.pmv = p; p += 2 * (size_t)n; s.bestpre = p; p += 2 * (size_t)n; s.bprecost = p; p += n; s.bmv = p; p += 2 * (size_t)n;
+    s.bcost = p; p += n; s.flags = p; p += n; s.eff = p; p += 4 * (size_t)n;
+    s.candOff = p; p += (size_t)KMAX * n; s.candFrac = p; p += (size_t)KMAX * n; s.candCost = p;
+
+    const int T = 128, G = ceil_div(n, T);
+    int rc = X265B200_OK;
+    auto bail = [&](int code) { cudaFreeAsync(scratch, st); return code; };
+
+    const int K0 = 3 + numCand;
+    me_start_gen<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, offR, strideR, s);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    if ((rc = x265b200_subpel_cmp_batch(ctx, X265B200_SAD, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K0, n, s.candCost, stream)))
+        return bail(rc);
+    me_start_select<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, costTab, s, outQMv, outCost);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    if ((rc = x265b200_me_full_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream)))
+        return bail(rc);
+    for (int r = 0; r <= R; r++)
+    {
+        const int mode = (r == 0 ? 1 : 2) | (r < R ? 4 : 8);
+        me_round_kernel<<<G, T, 0, st>>>(n, mode, rounds[r ? r - 1 : 0], rounds[r < R ? r : R - 1], qmvp, range, offR, strideR, costTab, s, outQMv, outCost);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        if (r < R && (rc = x265b200_subpel_cmp_batch(ctx, ops[r], w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, rounds[r].K, n,
+                                                     s.candCost, stream)))
+            return bail(rc);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "motion_estimate launch", e);
+    return X265B200_OK;
+}
