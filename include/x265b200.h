@@ -204,16 +204,29 @@ int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const v
                            const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
                            const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
-/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod = X265_FULL_SEARCH for n
+/* search methods, numbered as x265.h:511-519 (X265_DIA_SEARCH .. X265_FULL_SEARCH); UMH, STAR and SEA are not built */
+enum { X265B200_ME_DIA = 0, X265B200_ME_HEX = 1, X265B200_ME_FULL = 5 };
+
+/* The data-dependent integer searches for n PUs at once, one warp walking each PU: diamond (reference
+ * encoder/motion.cpp:1016-1039) and hexagon + square refinement (:1041-1138), replaying the reference's decision
+ * sequence step by step (same candidate order, strict-less updates, only the candidate's row range-checked, the walk
+ * ending when its centre leaves the window or after merange / merange/2 - 1 steps).  Arguments as in
+ * x265b200_me_full_batch; merange here is the reference's step budget, not a hint.  The window must be padded by two
+ * samples horizontally, as the reference's planes are. */
+int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, int h, int merange, const void* fenc, intptr_t strideF,
+                              const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR, const int32_t* range,
+                              const int32_t* mvp, const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
+
+/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod DIA, HEX or FULL for n
  * PUs of w x h on full-resolution luma planes: SAD at the clipped predictor qmvp / its full-pel rounding / the zero vector
  * and at numCand (0..16, the same count for every PU; pad with 0,0) neighbour vectors mvc[(i * numCand + k) * 2 ..] in
- * quarter pels, the exhaustive integer search of x265b200_me_full_batch, then the half-pel / quarter-pel refinement of
+ * quarter pels, the integer search (x265b200_me_pattern_batch or x265b200_me_full_batch), then the half-pel / quarter-pel refinement of
  * SubpelWorkload[subpelRefine] (0..7, motion.cpp:48-58) through the fused interpolation + SAD/SATD kernels, and the
  * zero vector's last chance.  outQMv[2i..2i+1] (quarter pel) and outCost[i] are what the reference returns in outQMv and
  * as its result, including the early exits on zero residual.  Luma only, one slice (the lookahead-style setSourcePU,
  * motion.cpp:166-189).  range, qmvp, costTab, offR as in x265b200_me_full_batch; plane strides multiples of 4.
  * The batch advances in lock step, one launch per step over all PUs; per-PU decisions live in stream-ordered scratch. */
-int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
                                    const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
                                    const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                                    int numCand, const int32_t* mvc, const uint16_t* costTab, int n,

@@ -972,8 +972,8 @@ EXPORT void orc_me_full_batch(int w, int h, const pixel* fenc, intptr_t sf, cons
 }
 
 /* ------------------------------------------------------------------------------------------------
- * MotionEstimate::motionEstimate with searchMethod = X265_FULL_SEARCH on full-resolution planes, luma only
- * (encoder/motion.cpp:923-1013 start point, :1593-1637 search, :1643-1773 sub-pel refinement; one slice, no vertical
+ * MotionEstimate::motionEstimate with searchMethod = DIA, HEX or FULL on full-resolution planes, luma only
+ * (encoder/motion.cpp:923-1013 start point, :1016-1138 / :1593-1637 search, :1643-1773 sub-pel refinement; one slice, no vertical
  * restriction, no chroma SATD -- the setSourcePU variant of motion.cpp:166-189).  Returns the cost, writes the qpel vector.
  *   fref: the co-located block (vector 0,0); range: mvmin.x, mvmin.y, mvmax.x, mvmax.y in full pels;
  *   qmvp and mvc[] in quarter pels; costTab as in orc_me_full_search.
@@ -991,10 +991,90 @@ static int me_subpel(const me_ctx* c, int qx, int qy, int op)   /* subpelCompare
 static int me_mvcost(const me_ctx* c, int qx, int qy) { return (uint16_t)(c->cx[qx] + c->cy[qy]); }   /* bitcost.h:56 */
 static int clip3i(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
 
-EXPORT int orc_motion_estimate_full(int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
-                                    const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
-                                    const uint16_t* costTab, int32_t* outQMv)
+/* full-pel candidate: SAD + mvcost(mv << 2), the COST_MV family of macros (motion.cpp:263-330) */
+static int me_fpel(const me_ctx* c, int x, int y)
 {
+    return orc_sad(c->w, c->h, c->fenc, c->sf, c->fref + x + (intptr_t)y * c->sr, c->sr) + me_mvcost(c, x * 4, y * 4);
+}
+static int me_in_range(const int32_t* range, int x, int y) { return x >= range[0] && x <= range[2] && y >= range[1] && y <= range[3]; }
+
+/* Diamond search, radius 1 (motion.cpp:1016-1039).  The reference packs "which neighbour won" into the low bits of the
+ * cost (tags 1, 3, 4, 12), which also fixes the tie-break: a neighbour replaces the centre only when strictly cheaper,
+ * and among equal neighbours the earlier one in the order up, down, left, right stays.  Only the candidate's row is
+ * range-checked; a step may leave the window horizontally, which then ends the walk. */
+static void me_dia_search(const me_ctx* c, const int32_t* range, int merange, int* bx, int* by, int* bcost)
+{
+    static const int nb[4][2] = { {0, -1}, {0, 1}, {-1, 0}, {1, 0} };
+    int x = *bx, y = *by, best = *bcost, i = merange;
+    do
+    {
+        int win = -1;
+        for (int k = 0; k < 4; k++)
+        {
+            int cy = y + nb[k][1];
+            if (k < 2 && (cy < range[1] || cy > range[3])) continue;
+            int cost = me_fpel(c, x + nb[k][0], cy);
+            if (cost < best) { best = cost; win = k; }
+        }
+        if (win < 0) break;
+        x += nb[win][0]; y += nb[win][1];
+    }
+    while (--i && me_in_range(range, x, y));
+    *bx = x; *by = y; *bcost = best;
+}
+
+/* Hexagon search, radius 2, then a one-step square refinement (motion.cpp:1041-1138).  First the six corners of the
+ * hexagon around the start, in the order of k_hex2[1..6]; then up to merange/2 - 1 steps that test only the three corners
+ * not covered by the previous hexagon; candidates outside the vertical range are ignored, the walk stops when the centre
+ * leaves the window.  Equal costs keep the earlier candidate (the reference's tag-in-low-bits comparison). */
+static const int k_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };   /* motion.cpp:65 */
+static void me_hex_search(const me_ctx* c, const int32_t* range, int merange, int* bx, int* by, int* bcost)
+{
+    int x = *bx, y = *by, best = *bcost, win = 0;
+    for (int t = 2; t <= 7; t++)
+    {
+        int cx = x + k_hex2[t - 1][0], cy = y + k_hex2[t - 1][1];
+        if (cy < range[1] || cy > range[3]) continue;
+        int cost = me_fpel(c, cx, cy);
+        if (cost < best) { best = cost; win = t; }
+    }
+    if (win)
+    {
+        int dir = win - 2;
+        x += k_hex2[dir + 1][0]; y += k_hex2[dir + 1][1];       /* the winner passed the row check above */
+        for (int i = (merange >> 1) - 1; i > 0 && me_in_range(range, x, y); i--)
+        {
+            win = 0;
+            for (int t = 1; t <= 3; t++)
+            {
+                int cx = x + k_hex2[dir + t - 1][0], cy = y + k_hex2[dir + t - 1][1];
+                if (cy < range[1] || cy > range[3]) continue;
+                int cost = me_fpel(c, cx, cy);
+                if (cost < best) { best = cost; win = t; }
+            }
+            if (!win) break;
+            dir = (dir + win - 2 + 6) % 6;                      /* mod6m1[dir + 1], motion.cpp:66 */
+            x += k_hex2[dir + 1][0]; y += k_hex2[dir + 1][1];
+        }
+    }
+    /* square refine: all eight neighbours of the final centre, first the cross then the corners (square1 order) */
+    win = 0;
+    for (int d = 1; d <= 8; d++)
+    {
+        int cx = x + k_square1[d][0], cy = y + k_square1[d][1];
+        if (k_square1[d][1] && (cy < range[1] || cy > range[3])) continue;
+        int cost = me_fpel(c, cx, cy);
+        if (cost < best) { best = cost; win = d; }
+    }
+    *bx = x + k_square1[win][0]; *by = y + k_square1[win][1]; *bcost = best;
+}
+
+/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
+EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                               const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                               const uint16_t* costTab, int32_t* outQMv)
+{
+    if (method != 0 && method != 1 && method != 5) return -1;
     me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1] };
     const int qminx = range[0] * 4, qminy = range[1] * 4, qmaxx = range[2] * 4, qmaxy = range[3] * 4;
 
@@ -1032,8 +1112,10 @@ EXPORT int orc_motion_estimate_full(int subme, int w, int h, const pixel* fenc, 
         outQMv[0] = bmvx * 4; outQMv[1] = bmvy * 4;
         return me_mvcost(&c, bmvx * 4, bmvy * 4);
     }
-    /* :1593-1637 */
-    {
+    if (method == 0) me_dia_search(&c, range, merange, &bmvx, &bmvy, &bcost);
+    else if (method == 1) me_hex_search(&c, range, merange, &bmvx, &bmvy, &bcost);
+    else
+    {   /* :1593-1637 */
         int32_t mv[2] = { bmvx, bmvy }, bc = bcost;
         orc_me_full_search(w, h, fenc, sf, fref, sr, range, qmvp, costTab, mv, &bc);
         bmvx = mv[0]; bmvy = mv[1]; bcost = bc;

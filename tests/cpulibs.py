@@ -188,12 +188,12 @@ class _Base:
         return int(mv[0]), int(mv[1]), int(bc.value)
 
     # ---- MotionEstimate::motionEstimate, full search + sub-pel refinement ---------------------------------------
-    def motion_estimate_full(self, subme, w, h, fenc, of, sf, ref, orf, sr, rng, qmvp, mvc, cost_tab, centre):
-        """oracle restatement; returns (qmv_x, qmv_y, cost)"""
+    def motion_estimate_full(self, subme, w, h, fenc, of, sf, ref, orf, sr, rng, qmvp, mvc, cost_tab, centre, method=5, merange=0):
+        """oracle restatement (method: 0 DIA, 1 HEX, 5 FULL); returns (qmv_x, qmv_y, cost)"""
         out = np.zeros(2, np.int32)
         rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
         mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
-        c = self._f("motion_estimate_full")(subme, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), _ptr(rng), _ptr(qmvp),
+        c = self._f("motion_estimate")(method, merange, subme, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), _ptr(rng), _ptr(qmvp),
                                             len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 

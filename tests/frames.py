@@ -61,3 +61,16 @@ def tile_blocks(geo, w, h, seed, merange=57):
     offA = (geo.origin + Y * geo.stride + X).astype(np.int32)
     offB = (geo.origin + RY * geo.stride + RX).astype(np.int32)
     return offA, offB
+
+
+def smooth_field(geo, depth, seed, box=9):
+    """a box-blurred random field over the padded plane: smooth enough that pattern searches walk many steps towards a
+    displaced copy, textured enough that the match is unique"""
+    rng = np.random.default_rng(seed)
+    f = rng.normal(0.0, 1.0, (geo.rows + box, geo.stride + box))
+    c = np.cumsum(np.cumsum(f, 0), 1)
+    b = c[box:, box:] - c[:-box, box:] - c[box:, :-box] + c[:-box, :-box]
+    b = b[:geo.rows, :geo.stride]
+    b = (b - b.min()) / (b.max() - b.min())
+    dt = np.uint8 if depth == 8 else np.uint16
+    return np.rint(b * ((1 << depth) - 1)).astype(dt).ravel()

@@ -517,7 +517,7 @@ def test_me_full_batch(depth):
 
 @pytest.mark.parametrize("depth", DEPTHS)
 def test_motion_estimate_batch(depth):
-    """whole motionEstimate (predictor candidates, exhaustive search, sub-pel refinement, zero-vector chance) for a batch of
+    """whole motionEstimate (predictor candidates, full / hexagon / diamond search, sub-pel refinement, zero-vector chance) for a batch of
     PUs vs the oracle's restatement -- itself pinned to the reference's MotionEstimate::motionEstimate by the CPU suite --
     for every SubpelWorkload level, with and without neighbour candidates, including PUs that leave early on zero residual"""
     import torch
@@ -529,6 +529,10 @@ def test_motion_estimate_batch(depth):
     F = make_plane(geo, depth, 81, "natural"); R = make_plane(geo, depth, 82, "natural")
     R2 = np.roll(F, 2 * geo.stride + 3)                   # exact copy displaced by (+3, +2)
     rng = np.random.default_rng(500 + depth)
+    from frames import smooth_field
+    S = smooth_field(geo, depth, 83)                      # smooth texture: hexagon / diamond walks take many steps
+    S2 = np.clip(np.roll(S, -6 * geo.stride + 9) + rng.integers(0, 3, S.size).astype(S.dtype), 0, orc.pmax).astype(S.dtype)
+    walked = 0
     cw, ch = geo.coded()
     RAD = 2048
     tab = mv_cost_table(8.9797, RAD); dtab = dev(tab.view(np.int16))
@@ -547,17 +551,20 @@ def test_motion_estimate_batch(depth):
         qmvp[::7] = 0; qmvp[1::9] = (12, 8)               # (12, 8) q-pel is the displaced copy: zero residual on R2
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (n, max(nc, 1), 2)).astype(np.int32)
         mvc[::4, 0] = (12, 8)
-        for ref_plane in (R, R2):
+        for fen, ref_plane, method in ((F, R, 5), (F, R2, 5), (F, R2, 1), (S, S2, 1), (S, S2, 0), (F, R, 0), (S, S2, 5)):
+            merange = m if method == 5 else int(rng.integers(1, 40))
             want_mv = np.zeros((n, 2), np.int32); want_c = np.zeros(n, np.int32)
             for i in range(n):
-                a = orc.motion_estimate_full(subme, w, h, F, int(off[i]), geo.stride, ref_plane, int(off[i]), geo.stride, rngs[i], qmvp[i],
-                                             mvc[i, :nc], tab, RAD)
+                a = orc.motion_estimate_full(subme, w, h, fen, int(off[i]), geo.stride, ref_plane, int(off[i]), geo.stride, rngs[i], qmvp[i],
+                                             mvc[i, :nc], tab, RAD, method, merange)
                 want_mv[i] = a[:2]; want_c[i] = a[2]
             gmv = torch.full((n, 2), -7777, dtype=torch.int32, device="cuda"); gc = torch.full((n,), -7777, dtype=torch.int32, device="cuda")
-            ctx.motion_estimate_batch(w, h, m, subme, dF, geo.stride, dev(pix_view(ref_plane, depth)), geo.stride, dev(off), dev(off), dev(rngs),
-                                      dev(qmvp), nc, dev(np.ascontiguousarray(mvc[:, :nc])) if nc else None, dtab.data_ptr() + 2 * RAD, gmv, gc)
-            assert np.array_equal(gc.cpu().numpy(), want_c), (w, h, subme)
-            assert np.array_equal(gmv.cpu().numpy(), want_mv), (w, h, subme)
-        if si == 0:
-            assert (want_c < 200).any()                   # the displaced copy produced early exits / tight matches
+            ctx.motion_estimate_batch(method, w, h, merange, subme, dev(pix_view(fen, depth)), geo.stride, dev(pix_view(ref_plane, depth)), geo.stride,
+                                      dev(off), dev(off), dev(rngs), dev(qmvp), nc, dev(np.ascontiguousarray(mvc[:, :nc])) if nc else None,
+                                      dtab.data_ptr() + 2 * RAD, gmv, gc)
+            assert np.array_equal(gc.cpu().numpy(), want_c), (w, h, subme, method)
+            assert np.array_equal(gmv.cpu().numpy(), want_mv), (w, h, subme, method)
+            if method != 5 and fen is S:
+                walked += int((np.abs(want_mv - np.clip(qmvp, 4 * rngs[:, :2], 4 * rngs[:, 2:])).max(1) >= 16).sum())
+    assert walked > 100                                   # pattern searches ended four or more pels from their start
     ctx.check()

@@ -499,8 +499,8 @@ def test_me_full_search(libs):
     assert got == (k % 21 - 9, k // 21 - 6, int(costs.min()))
 
 
-def test_motion_estimate_full(libs):
-    """the oracle's motionEstimate(FULL) restatement vs the reference's MotionEstimate::motionEstimate itself
+def test_motion_estimate(libs):
+    """the oracle's motionEstimate restatement (full, hexagon and diamond searches) vs the reference's MotionEstimate::motionEstimate itself
     (compiled from encoder/motion.cpp), every subme level, with neighbour candidates and predictors inside / outside the range"""
     o, r = libs
     from frames import Geometry, make_plane
@@ -508,6 +508,11 @@ def test_motion_estimate_full(libs):
     rng = np.random.default_rng(61)
     F = make_plane(geo, o.depth, 71, "natural"); R = make_plane(geo, o.depth, 72, "natural")
     R2 = np.roll(F, 3 * geo.stride + 5)                   # a real match at (+5, +3): zero-cost exits and tight refinement
+    from frames import smooth_field
+    S = smooth_field(geo, o.depth, 73)                    # smooth texture: the pattern searches walk many steps
+    S2 = np.roll(S, -6 * geo.stride + 9) + (rng.integers(0, 3, S.size)).astype(S.dtype)
+    np.clip(S2, 0, o.pmax, out=S2)
+    moved = 0
     RAD = 2048
     cw, ch = geo.coded()
     nonzero_exit = 0
@@ -517,9 +522,11 @@ def test_motion_estimate_full(libs):
         qp = int(rng.integers(0, 52))
         tab = r.mvcost_table(qp, RAD)
         ref = R2 if case % 5 == 0 else R
+        fen = F
+        if case % 3 == 1: fen, ref = S, S2
         x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
         of = geo.origin + y * geo.stride + x
-        m = int(rng.integers(1, 13))
+        m = int(rng.integers(1, 17))
         # keep block + 8-tap margins inside the padded plane
         minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 8 - w - x)
         miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 8 - h - y)
@@ -530,8 +537,13 @@ def test_motion_estimate_full(libs):
         nc = int(rng.integers(0, 5))
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (nc, 2))
         if nc > 1: mvc[1] = qmvp
-        a = o.motion_estimate_full(subme, w, h, F, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD)
-        b = r.motion_estimate(r.ME_FULL, subme, w, h, F, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, m, qp)
-        assert a == b, (case, w, h, subme, a, b)
-        nonzero_exit += a[2] > 0
-    assert nonzero_exit > 100
+        for method in (5, 1, 0):                          # X265_FULL_SEARCH, X265_HEX_SEARCH, X265_DIA_SEARCH
+            merange = m if method == 5 else int(rng.integers(1, 40))
+            a = o.motion_estimate_full(subme, w, h, fen, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD,
+                                       method, merange)
+            b = r.motion_estimate(method, subme, w, h, fen, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+            assert a == b, (case, method, w, h, subme, a, b)
+            nonzero_exit += a[2] > 0
+            if method != 5:
+                moved += max(abs(a[0] - int(np.clip(qmvp[0], 4 * minx, 4 * maxx))), abs(a[1] - int(np.clip(qmvp[1], 4 * miny, 4 * maxy)))) >= 16
+    assert nonzero_exit > 300 and moved > 40              # dozens of pattern walks ended four or more pels from their start

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--depth", type=int, default=10)
     ap.add_argument("--merange", type=int, default=57)
     ap.add_argument("--subme", type=int, default=2)
+    ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 5 FULL")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
     D, M = args.depth, args.merange
@@ -67,15 +68,17 @@ def main():
         mvc = torch.randint(-40, 41, (n, 2, 2), dtype=torch.int32, device="cuda")
         oq = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); oc = torch.zeros((n,), dtype=torch.int32, device="cuda")
 
-        def run_me():
-            ctx.motion_estimate_batch(w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc, dtab.data_ptr() + 2 * RAD, oq, oc)
-        run_me(); torch.cuda.synchronize()
-        ts = []
-        for _ in range(3):
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); run_me(); e1.record(); e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        row["motion_estimate_ms_per_frame"] = sorted(ts)[1]
+        for method in [int(v) for v in args.methods.split(",")]:
+            def run_me():
+                ctx.motion_estimate_batch(method, w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc,
+                                          dtab.data_ptr() + 2 * RAD, oq, oc)
+            run_me(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); run_me(); e1.record(); e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            row["motion_estimate_%s_ms_per_frame" % {0: "dia", 1: "hex", 5: "full"}[method]] = sorted(ts)[1]
         row["motion_estimate_subme"] = args.subme
         if args.cpu:
             import cpulibs

@@ -147,9 +147,13 @@ class Context:
         self._call("x265b200_me_full_batch", w, h, int(merange), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(rng), _dp(mvp),
                    C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(bmv), _dp(bcost), C.c_void_p(stream))
 
-    def motion_estimate_batch(self, w, h, merange, subme, fenc, sf, ref, sr, offF, offR, rng, qmvp, num_cand, mvc, cost_tab_centre,
+    def me_pattern_batch(self, method, w, h, merange, fenc, sf, ref, sr, offF, offR, rng, mvp, cost_tab_centre, bmv, bcost, stream=0):
+        self._call("x265b200_me_pattern_batch", int(method), w, h, int(merange), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(rng),
+                   _dp(mvp), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(bmv), _dp(bcost), C.c_void_p(stream))
+
+    def motion_estimate_batch(self, method, w, h, merange, subme, fenc, sf, ref, sr, offF, offR, rng, qmvp, num_cand, mvc, cost_tab_centre,
                               out_qmv, out_cost, stream=0):
-        self._call("x265b200_motion_estimate_batch", w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR),
+        self._call("x265b200_motion_estimate_batch", int(method), w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR),
                    _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(out_qmv), _dp(out_cost),
                    C.c_void_p(stream))
 

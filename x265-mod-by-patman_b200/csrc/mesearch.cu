@@ -203,6 +203,148 @@ static cudaError_t launch_me_full(const void* fenc, intptr_t strideF, const void
     return cudaSuccess;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pattern searches: diamond (motion.cpp:1016-1039) and hexagon + square refinement (motion.cpp:1041-1138).
+// Each step depends on the previous best, so a PU is a sequential walk; one warp owns one PU (fenc block in shared
+// memory, the lanes split the block's samples, up to four candidates of a step are measured in one pass) and the
+// batch supplies the parallelism.  Only a candidate's row is range-checked, as in the reference; a step may leave the
+// window horizontally, which ends the walk.  Equal costs keep the earlier candidate (the reference's tag-in-low-bits
+// comparison reduces to a strict `<` in evaluation order).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MP_WARPS = 4;
+__constant__ int c_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };      // motion.cpp:65
+__constant__ int c_sq1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} }; // motion.cpp:67
+
+template<typename PIX>
+struct PatternPU
+{
+    const PIX* fs;              // fenc block, pitch w (shared)
+    const PIX* r0;              // co-located block of the reference picture
+    intptr_t strideR;
+    const uint16_t* cx;         // cost table shifted by the predictor (BitCost::setMVP)
+    const uint16_t* cy;
+    int w, h, lane, px0, py0, dq, dr;     // a lane's sample walks 32 positions per step: dq rows and dr columns
+    int miny, maxy;
+
+    // SAD + mvcost of up to four full-pel candidates in one pass over the block; rows outside the window are not read
+    __device__ void eval(int nc, const int (&cand)[4][2], int (&cost)[4], bool (&ok)[4]) const
+    {
+        const PIX* rp[4];
+        unsigned acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            ok[k] = k < nc && cand[k][1] >= miny && cand[k][1] <= maxy;
+            rp[k] = r0 + (ok[k] ? cand[k][0] + (intptr_t)cand[k][1] * strideR : 0);
+            acc[k] = 0;
+        }
+        int px = px0, py = py0;
+        for (int idx = lane; idx < w * h; idx += 32)
+        {
+            const unsigned f = fs[idx];
+            const intptr_t o = (intptr_t)py * strideR + px;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < nc) acc[k] = __usad(f, (unsigned)rp[k][o], acc[k]);
+            px += dr; py += dq;
+            if (px >= w) { px -= w; py++; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            cost[k] = (int)__reduce_add_sync(0xffffffffu, acc[k]) + (ok[k] ? (int)(uint16_t)(cx[cand[k][0] << 2] + cy[cand[k][1] << 2]) : 0);
+    }
+};
+
+template<typename PIX>
+__global__ void __launch_bounds__(MP_WARPS * 32)
+me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
+                  const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
+                  const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int n, int w, int h,
+                  int32_t* __restrict__ bmv, int32_t* __restrict__ bcost)
+{
+    extern __shared__ __align__(16) uint8_t mp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pu = blockIdx.x * MP_WARPS + warp;
+    if (pu >= n) return;                                        // whole warps leave; only __syncwarp below
+    const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
+    if (maxx < minx || maxy < miny) return;
+    PIX* fs = (PIX*)mp_smem + (size_t)warp * w * h;
+    {
+        const PIX* f = fenc + offF[pu];
+        int px = lane % w, py = lane / w;
+        for (int idx = lane; idx < w * h; idx += 32)
+        {
+            fs[idx] = f[(intptr_t)py * strideF + px];
+            px += 32 % w; py += 32 / w;
+            if (px >= w) { px -= w; py++; }
+        }
+    }
+    __syncwarp();
+    PatternPU<PIX> P;
+    P.fs = fs; P.r0 = ref + offR[pu]; P.strideR = strideR;
+    P.cx = costTab - mvp[2 * pu]; P.cy = costTab - mvp[2 * pu + 1];
+    P.w = w; P.h = h; P.lane = lane; P.px0 = lane % w; P.py0 = lane / w; P.dq = 32 / w; P.dr = 32 % w; P.miny = miny; P.maxy = maxy;
+
+    int x = bmv[2 * pu], y = bmv[2 * pu + 1], best = bcost[pu];
+    int cand[4][2], cost[4]; bool ok[4];
+    auto in_range = [&](int cx, int cy) { return cx >= minx && cx <= maxx && cy >= miny && cy <= maxy; };
+
+    if (method == 0)
+    {   // diamond, radius 1: up, down, left, right
+        int i = merange;
+        do
+        {
+            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[k + 1][0]; cand[k][1] = y + c_sq1[k + 1][1]; }
+            P.eval(4, cand, cost, ok);
+            int win = -1;
+            for (int k = 0; k < 4; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; win = k; }
+            if (win < 0) break;
+            x = cand[win][0]; y = cand[win][1];
+        }
+        while (--i && in_range(x, y));
+    }
+    else
+    {   // hexagon: the six corners around the start, in hex2[1..6] order
+        int win = 0;
+        for (int half = 0; half < 2; half++)
+        {
+            for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[half * 3 + k + 1][0]; cand[k][1] = y + c_hex2[half * 3 + k + 1][1]; }
+            P.eval(3, cand, cost, ok);
+            for (int k = 0; k < 3; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 3 + k + 2; }
+        }
+        if (win)
+        {
+            int dir = win - 2;
+            x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
+            for (int i = (merange >> 1) - 1; i > 0 && in_range(x, y); i--)
+            {   // the three corners the previous hexagon did not cover
+                for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[dir + k][0]; cand[k][1] = y + c_hex2[dir + k][1]; }
+                P.eval(3, cand, cost, ok);
+                win = 0;
+                for (int k = 0; k < 3; k++)
+                    if (ok[k] && cost[k] < best) { best = cost[k]; win = k + 1; }
+                if (!win) break;
+                dir = (dir + win - 2 + 6) % 6;                  // mod6m1[dir + 1]
+                x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
+            }
+        }
+        // square refinement around the final centre: the cross, then the corners
+        win = 0;
+        for (int half = 0; half < 2; half++)
+        {
+            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[half * 4 + k + 1][0]; cand[k][1] = y + c_sq1[half * 4 + k + 1][1]; }
+            P.eval(4, cand, cost, ok);
+            for (int k = 0; k < 4; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 4 + k + 1; }
+        }
+        x += c_sq1[win][0]; y += c_sq1[win][1];
+    }
+    if (lane == 0) { bmv[2 * pu] = x; bmv[2 * pu + 1] = y; bcost[pu] = best; }
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -227,6 +369,26 @@ extern "C" int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int meran
     else
         e = launch_me_full<uint16_t, 8>(fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, w, h, span, n, bmv, bcost, st);
     if (e != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "me_full: shared memory attribute", e);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
+
+extern "C" int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, int h, int merange, const void* fenc, intptr_t strideF,
+                                         const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR, const int32_t* range,
+                                         const int32_t* mvp, const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0) return fail(ctx, X265B200_ERR_ARG, "me_pattern: bad geometry");
+    if (method != X265B200_ME_DIA && method != X265B200_ME_HEX) return fail(ctx, X265B200_ERR_ARG, "me_pattern: method must be DIA or HEX");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes;
+    if (ctx->pixbytes == 1)
+        me_pattern_kernel<uint8_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR,
+                                                                                     offF, offR, range, mvp, costTab, n, w, h, bmv, bcost);
+    else
+        me_pattern_kernel<uint16_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR,
+                                                                                      offF, offR, range, mvp, costTab, n, w, h, bmv, bcost);
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }

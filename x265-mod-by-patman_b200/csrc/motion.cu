@@ -1,5 +1,5 @@
-// motion.cu -- MotionEstimate::motionEstimate for a batch of prediction units, searchMethod = X265_FULL_SEARCH, luma only
-// (reference encoder/motion.cpp:923-1013 start point, :1593-1637 integer search, :1643-1773 sub-pel refinement and the
+// motion.cu -- MotionEstimate::motionEstimate for a batch of prediction units, searchMethod DIA / HEX / FULL, luma only
+// (reference encoder/motion.cpp:923-1013 start point, :1016-1138 / :1593-1637 integer search, :1643-1773 sub-pel refinement and the
 // zero-vector last chance; the setSourcePU variant of motion.cpp:166-189: one slice, no vertical restriction).
 //
 // The reference runs this per PU as a chain of data-dependent steps.  Across thousands of PUs the steps line up: every
@@ -7,7 +7,7 @@
 // quarter-pel rounds (SubpelWorkload, motion.cpp:48-58).  So the batch advances in lock step, each step one launch over
 // all PUs, with the per-PU decisions (COPY2_IF_LT chains, early `break`s, the bcost == 0 exits) kept in small state
 // arrays and taken by one thread per PU between the heavy launches:
-//     start_gen -> subpel_cmp_batch(SAD) -> start_select -> me_full_batch -> [round: select+gen -> subpel_cmp_batch] x R -> finish
+//     start_gen -> subpel_cmp_batch(SAD) -> start_select -> me_pattern_batch | me_full_batch -> [round: select+gen -> subpel_cmp_batch] x R -> finish
 // The heavy launches are the library's own batched entries (fused interpolation + SAD/SATD, exhaustive search).
 // A PU that left the chain early (zero residual) or whose refinement loop broke keeps producing harmless candidates at
 // its current vector so the launches stay dense; its state no longer changes.
@@ -177,7 +177,7 @@ __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, con
 
 using namespace b200;
 
-extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
                                               const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
                                               const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                                               int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
@@ -186,6 +186,8 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, i
     if (!ctx) return X265B200_ERR_ARG;
     if (subpelRefine < 0 || subpelRefine > 7 || numCand < 0 || numCand > ME_MAX_CAND || n < 0 || (numCand && !mvc))
         return fail(ctx, X265B200_ERR_ARG, "motion_estimate: bad arguments");
+    if (searchMethod != X265B200_ME_DIA && searchMethod != X265B200_ME_HEX && searchMethod != X265B200_ME_FULL)
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: search method not built (DIA, HEX, FULL are)");
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -233,8 +235,11 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int w, int h, i
         return bail(rc);
     me_start_select<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, costTab, s, outQMv, outCost);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    if ((rc = x265b200_me_full_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream)))
-        return bail(rc);
+    if (searchMethod == X265B200_ME_FULL)
+        rc = x265b200_me_full_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream);
+    else
+        rc = x265b200_me_pattern_batch(ctx, searchMethod, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream);
+    if (rc) return bail(rc);
     for (int r = 0; r <= R; r++)
     {
         const int mode = (r == 0 ? 1 : 2) | (r < R ? 4 : 8);
