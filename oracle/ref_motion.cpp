@@ -9,6 +9,8 @@
 #include "motion.cpp"
 #include "bitcost.cpp"
 #include "yuv.cpp"
+#include <thread>
+#include <vector>
 
 using namespace X265_NS;
 
@@ -43,4 +45,44 @@ void ref_mvcost_table(int qp, int radius, uint16_t* out)
     struct Peek : BitCost { const uint16_t* tab() const { return m_cost; } } bc;
     bc.setQP(qp);
     for (int i = -radius; i <= radius; i++) out[i + radius] = bc.tab()[i];
+}
+
+/* the same call for n PUs on nthreads host threads, one MotionEstimate object per thread (as the encoder's worker threads
+ * hold one each): the CPU arm of tools/bench_me.py */
+extern "C" __attribute__((visibility("default")))
+void ref_motion_estimate_batch(int method, int subme, int w, int h, pixel* fencPlane, intptr_t strideF, const int32_t* offF,
+                               pixel* refPlane, intptr_t strideR, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                               int numCand, const int32_t* mvc, int merange, int qp, int n, int32_t* outQMv, int32_t* outCost, int nthreads)
+{
+    static bool scales = false;
+    if (!scales) { ref_ensure(); MotionEstimate::initScales(); scales = true; }
+    { BitCost warm; warm.setQP(qp); }                       /* build the shared cost table before the threads race for it */
+    auto work = [&](int lo, int hi)
+    {
+        MotionEstimate me;
+        me.init(X265_CSP_I400);
+        me.setQP(qp);
+        for (int i = lo; i < hi; i++)
+        {
+            me.setSourcePU(fencPlane, strideF, offF[i], w, h, method, subme);
+            ReferencePlanes ref;
+            ref.fpelPlane[0] = refPlane + (offR[i] - offF[i]);
+            ref.lumaStride = strideR;
+            MV mvmin(range[4 * i], range[4 * i + 1]), mvmax(range[4 * i + 2], range[4 * i + 3]), mvp(qmvp[2 * i], qmvp[2 * i + 1]), out;
+            MV cands[16];
+            for (int k = 0; k < numCand && k < 16; k++) cands[k] = MV(mvc[((size_t)i * numCand + k) * 2], mvc[((size_t)i * numCand + k) * 2 + 1]);
+            outCost[i] = me.motionEstimate(&ref, mvmin, mvmax, mvp, numCand, cands, merange, out, 1, false);
+            outQMv[2 * i] = out.x; outQMv[2 * i + 1] = out.y;
+        }
+    };
+    if (nthreads <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    int chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++)
+    {
+        int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) break;
+        th.emplace_back(work, lo, hi);
+    }
+    for (auto& t : th) t.join();
 }

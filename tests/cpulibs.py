@@ -334,6 +334,13 @@ class Reference(_Base):
                                          C.c_ssize_t(orf - of), _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), merange, qp, _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    def motion_estimate_batch(self, method, subme, w, h, fenc, sf, offF, ref, sr, offR, rng, qmvp, nc, mvc, merange, qp, nthreads=1):
+        n = len(offF)
+        mv = np.zeros((n, 2), np.int32); cost = np.zeros(n, np.int32)
+        self.lib.ref_motion_estimate_batch(method, subme, w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(offF), _ptr(ref), C.c_ssize_t(sr), _ptr(offR),
+                                           _ptr(rng), _ptr(qmvp), nc, _ptr(mvc) if nc else None, merange, qp, n, _ptr(mv), _ptr(cost), nthreads)
+        return mv, cost
+
     def mvcost_table(self, qp, radius):
         out = np.zeros(2 * radius + 1, np.uint16)
         self.lib.ref_mvcost_table(qp, radius, _ptr(out))

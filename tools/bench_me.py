@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--merange", type=int, default=57)
     ap.add_argument("--subme", type=int, default=2)
     ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 5 FULL")
+    ap.add_argument("--shapes", default="64,32,16,8", help="square PU sizes to run")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
     D, M = args.depth, args.merange
@@ -35,11 +36,17 @@ def main():
     Fh = make_plane(geo, D, 1, "natural"); Rh = make_plane(geo, D, 2, "natural")
     A = torch.from_numpy(Fh.view(vt)).cuda(); B = torch.from_numpy(Rh.view(vt)).cuda()
     RAD = 4096
-    tab = mv_cost_table(12.6992, RAD)
+    QP = 30
+    refl = None
+    if args.cpu:
+        import cpulibs
+        if cpulibs.have_reference(D):
+            refl = cpulibs.Reference(D)
+    tab = refl.mvcost_table(QP, RAD) if refl else mv_cost_table(12.6992, RAD)      # the reference's own table when it is built
     dtab = torch.from_numpy(tab.view(np.int16)).cuda()
     sm_clock = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 0
     rows = []
-    for (w, h) in ((64, 64), (32, 32), (16, 16), (8, 8)):
+    for (w, h) in [(int(v), int(v)) for v in args.shapes.split(",")]:
         oa, _ = tile_blocks(geo, w, h, seed=1)
         n = oa.size
         px = (oa - geo.origin) % geo.stride; py = (oa - geo.origin) // geo.stride
@@ -78,10 +85,24 @@ def main():
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(); run_me(); e1.record(); e1.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            row["motion_estimate_%s_ms_per_frame" % {0: "dia", 1: "hex", 5: "full"}[method]] = sorted(ts)[1]
+            name = {0: "dia", 1: "hex", 5: "full"}[method]
+            row["motion_estimate_%s_ms_per_frame" % name] = sorted(ts)[1]
+            if refl:
+                # the reference's own MotionEstimate::motionEstimate on every host core, on a sample of the same PUs
+                k = min(n, 400 if method == 5 else 40000)
+                if method == 5: k = max(8, min(k, int(4e9 / (cands / n * w * h))))
+                sel = np.linspace(0, n - 1, k).astype(np.int64)
+                hq = qmvp.cpu().numpy()[sel].copy(); hm = mvc.cpu().numpy()[sel].copy()
+                so = oa[sel].astype(np.int32)
+                nt = os.cpu_count() or 1
+                t0 = time.perf_counter()
+                rmv, rc = refl.motion_estimate_batch(method, args.subme, w, h, Fh, geo.stride, so, Rh, geo.stride, so, rng[sel].copy(), hq, 2, hm, M, QP, nt)
+                dt = time.perf_counter() - t0
+                row["ref_%s_us_per_pu_%d_threads" % (name, nt)] = dt / k * 1e6
+                row["ref_%s_ms_per_frame_extrapolated" % name] = dt / k * n * 1e3
+                row["ref_%s_sample_matches" % name] = bool(np.array_equal(oq.cpu().numpy()[sel], rmv) and np.array_equal(oc.cpu().numpy()[sel], rc))
         row["motion_estimate_subme"] = args.subme
         if args.cpu:
-            import cpulibs
             orc = cpulibs.Oracle(D)
             k = max(1, min(n, int(2e9 / (cands / n * w * h))))       # ~2 G sample-candidates of CPU work
             sel = np.linspace(0, n - 1, k).astype(np.int64)
