@@ -204,11 +204,12 @@ int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const v
                            const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
                            const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
-/* search methods, numbered as x265.h:511-519 (X265_DIA_SEARCH .. X265_FULL_SEARCH); UMH, STAR and SEA are not built */
-enum { X265B200_ME_DIA = 0, X265B200_ME_HEX = 1, X265B200_ME_FULL = 5 };
+/* search methods, numbered as x265.h:511-519 (X265_DIA_SEARCH .. X265_FULL_SEARCH); UMH and SEA are not built */
+enum { X265B200_ME_DIA = 0, X265B200_ME_HEX = 1, X265B200_ME_STAR = 3, X265B200_ME_FULL = 5 };
 
 /* The data-dependent integer searches for n PUs at once, one warp walking each PU: diamond (reference
- * encoder/motion.cpp:1016-1039) and hexagon + square refinement (:1041-1138), replaying the reference's decision
+ * encoder/motion.cpp:1016-1039), hexagon + square refinement (:1041-1138) and star (:386-630, :1327-1435, with its
+ * stride-5 raster pass and the mvcost(mv << 3) it charges every fourth column), replaying the reference's decision
  * sequence step by step (same candidate order, strict-less updates, only the candidate's row range-checked, the walk
  * ending when its centre leaves the window or after merange / merange/2 - 1 steps).  Arguments as in
  * x265b200_me_full_batch; merange here is the reference's step budget, not a hint.  The window must be padded by two
@@ -217,7 +218,7 @@ int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, int h, int m
                               const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR, const int32_t* range,
                               const int32_t* mvp, const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
-/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod DIA, HEX or FULL for n
+/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod DIA, HEX, STAR or FULL for n
  * PUs of w x h on full-resolution luma planes: SAD at the clipped predictor qmvp / its full-pel rounding / the zero vector
  * and at numCand (0..16, the same count for every PU; pad with 0,0) neighbour vectors mvc[(i * numCand + k) * 2 ..] in
  * quarter pels, the integer search (x265b200_me_pattern_batch or x265b200_me_full_batch), then the half-pel / quarter-pel refinement of

@@ -1069,12 +1069,129 @@ static void me_hex_search(const me_ctx* c, const int32_t* range, int merange, in
     *bx = x + k_square1[win][0]; *by = y + k_square1[win][1]; *bcost = best;
 }
 
-/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
+/* Star search (motion.cpp:386-630 StarPatternSearch, :1327-1435 the X265_STAR_SEARCH case; adapted from HM).
+ * One pattern pass tests rings around a fixed centre: distance 1 (4 points), 2 / 4 / 8 (8 points: the four axis points at
+ * the distance, the four diagonal ones at half of it), 16 .. merange (16 points on a diamond).  The reference has a fast
+ * path when the whole ring is inside the window and a per-point checked path otherwise; both visit the same points in
+ * the same order and a point is measured exactly when it lies inside the window, which is what is restated here.  A pass
+ * ends early after `earlyExit` consecutive rings without improvement.  Point numbers (1..8, 0 for the big rings) and the
+ * distance of the best point steer what follows. */
+typedef struct { int x, y, cost, point, dist; } me_star_t;
+static void me_star_try(const me_ctx* c, const int32_t* range, me_star_t* b, int x, int y, int point, int dist)
+{
+    if (!me_in_range(range, x, y)) return;
+    int cost = me_fpel(c, x, y);
+    if (cost < b->cost) { b->cost = cost; b->x = x; b->y = y; b->point = point; b->dist = dist; }
+}
+static void me_star_pattern(const me_ctx* c, const int32_t* range, me_star_t* b, int earlyExit, int merange)
+{
+    const int ox = b->x, oy = b->y;
+    int rounds = 0, saved = b->cost;
+    for (int dist = 1; dist <= 8 || dist <= (int16_t)merange; dist <<= 1)
+    {
+        if (dist > 8 && dist > (int16_t)merange) break;
+        if (dist > 1) saved = b->cost;
+        if (dist == 1)
+        {
+            me_star_try(c, range, b, ox, oy - 1, 2, 1); me_star_try(c, range, b, ox - 1, oy, 4, 1);
+            me_star_try(c, range, b, ox + 1, oy, 5, 1); me_star_try(c, range, b, ox, oy + 1, 7, 1);
+        }
+        else if (dist <= 8)
+        {
+            const int h = dist >> 1;
+            me_star_try(c, range, b, ox, oy - dist, 2, dist); me_star_try(c, range, b, ox - h, oy - h, 1, h);
+            me_star_try(c, range, b, ox + h, oy - h, 3, h);   me_star_try(c, range, b, ox - dist, oy, 4, dist);
+            me_star_try(c, range, b, ox + dist, oy, 5, dist); me_star_try(c, range, b, ox - h, oy + h, 6, h);
+            me_star_try(c, range, b, ox + h, oy + h, 8, h);   me_star_try(c, range, b, ox, oy + dist, 7, dist);
+        }
+        else
+        {
+            const int q = dist >> 2;
+            me_star_try(c, range, b, ox, oy - dist, 0, dist); me_star_try(c, range, b, ox - dist, oy, 0, dist);
+            me_star_try(c, range, b, ox + dist, oy, 0, dist); me_star_try(c, range, b, ox, oy + dist, 0, dist);
+            for (int i = 1; i < 4; i++)
+            {
+                me_star_try(c, range, b, ox - q * i, oy - dist + q * i, 0, dist); me_star_try(c, range, b, ox + q * i, oy - dist + q * i, 0, dist);
+                me_star_try(c, range, b, ox - q * i, oy + dist - q * i, 0, dist); me_star_try(c, range, b, ox + q * i, oy + dist - q * i, 0, dist);
+            }
+        }
+        if (b->cost < saved) rounds = 0;
+        else if (++rounds >= earlyExit) return;
+    }
+}
+/* the two outer neighbours of a distance-1 winner, indexed by its point number (motion.cpp:76-86 `offsets`) */
+static const int k_two_point[16][2] = { {-1, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {-1, -1},
+                                        {1, -1}, {1, 1}, {-1, 0}, {0, 1}, {-1, 1}, {1, 1}, {1, 0}, {0, 1} };
+static void me_two_point(const me_ctx* c, const int32_t* range, me_star_t* b)
+{
+    const int x = b->x, y = b->y, p = (b->point - 1) * 2;      /* both neighbours are taken around the winner as it was */
+    for (int k = 0; k < 2; k++)
+    {
+        int cx = x + k_two_point[p + k][0], cy = y + k_two_point[p + k][1];
+        if (!me_in_range(range, cx, cy)) continue;
+        int cost = me_fpel(c, cx, cy);
+        if (cost < b->cost) { b->cost = cost; b->x = cx; b->y = cy; }
+    }
+}
+static void me_star_search(const me_ctx* c, const int32_t* range, int merange, int* bx, int* by, int* bcost)
+{
+    me_star_t b = { *bx, *by, *bcost, 0, 0 };
+    me_star_pattern(c, range, &b, 3, merange);
+    int done = 0;
+    if (b.dist == 1)
+    {   /* :1336-1362 */
+        if (!b.point) done = 1;
+        else
+        {
+            int saved = b.cost;
+            me_two_point(c, range, &b);
+            if (b.cost == saved) done = 1;
+        }
+    }
+    if (!done)
+    {
+        if (b.dist > 5)
+        {   /* :1364-1399 raster over the window in steps of 5; the reference measures four columns per sad_x4 call and
+             * charges the fourth one mvcost(mv << 3) instead of mv << 2 -- reproduced, it decides vectors */
+            for (int y = range[1]; y <= range[3]; y += 5)
+                for (int x = range[0]; x <= range[2]; x += 5)
+                {
+                    if (x + 15 <= range[2])
+                    {
+                        for (int k = 0; k < 4; k++, x += (k < 4 ? 5 : 0))
+                        {
+                            int cost = orc_sad(c->w, c->h, c->fenc, c->sf, c->fref + x + (intptr_t)y * c->sr, c->sr)
+                                     + (k < 3 ? me_mvcost(c, x * 4, y * 4) : me_mvcost(c, x * 8, y * 8));
+                            if (cost < b.cost) { b.cost = cost; b.x = x; b.y = y; }
+                        }
+                    }
+                    else
+                    {
+                        int cost = me_fpel(c, x, y);
+                        if (cost < b.cost) { b.cost = cost; b.x = x; b.y = y; }
+                    }
+                }
+        }
+        while (b.dist > 0)
+        {   /* :1401-1433 re-centred passes until one brings nothing */
+            b.dist = 0; b.point = 0;
+            me_star_pattern(c, range, &b, 32, merange);
+            if (b.dist == 1)
+            {
+                if (b.point) me_two_point(c, range, &b);
+                break;
+            }
+        }
+    }
+    *bx = b.x; *by = b.y; *bcost = b.cost;
+}
+
+/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_STAR_SEARCH 3, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
 EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
                                const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
                                const uint16_t* costTab, int32_t* outQMv)
 {
-    if (method != 0 && method != 1 && method != 5) return -1;
+    if (method != 0 && method != 1 && method != 3 && method != 5) return -1;
     me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1] };
     const int qminx = range[0] * 4, qminy = range[1] * 4, qmaxx = range[2] * 4, qmaxy = range[3] * 4;
 
@@ -1114,6 +1231,7 @@ EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h,
     }
     if (method == 0) me_dia_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 1) me_hex_search(&c, range, merange, &bmvx, &bmvy, &bcost);
+    else if (method == 3) me_star_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else
     {   /* :1593-1637 */
         int32_t mv[2] = { bmvx, bmvy }, bc = bcost;

@@ -517,7 +517,7 @@ def test_me_full_batch(depth):
 
 @pytest.mark.parametrize("depth", DEPTHS)
 def test_motion_estimate_batch(depth):
-    """whole motionEstimate (predictor candidates, full / hexagon / diamond search, sub-pel refinement, zero-vector chance) for a batch of
+    """whole motionEstimate (predictor candidates, full / hexagon / diamond / star search, sub-pel refinement, zero-vector chance) for a batch of
     PUs vs the oracle's restatement -- itself pinned to the reference's MotionEstimate::motionEstimate by the CPU suite --
     for every SubpelWorkload level, with and without neighbour candidates, including PUs that leave early on zero residual"""
     import torch
@@ -532,6 +532,7 @@ def test_motion_estimate_batch(depth):
     from frames import smooth_field
     S = smooth_field(geo, depth, 83)                      # smooth texture: hexagon / diamond walks take many steps
     S2 = np.clip(np.roll(S, -6 * geo.stride + 9) + rng.integers(0, 3, S.size).astype(S.dtype), 0, orc.pmax).astype(S.dtype)
+    S3 = np.roll(S, 11 * geo.stride - 14)                 # far match (-14, +11): star rings of 8 / 16, the raster pass
     walked = 0
     cw, ch = geo.coded()
     RAD = 2048
@@ -551,8 +552,10 @@ def test_motion_estimate_batch(depth):
         qmvp[::7] = 0; qmvp[1::9] = (12, 8)               # (12, 8) q-pel is the displaced copy: zero residual on R2
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (n, max(nc, 1), 2)).astype(np.int32)
         mvc[::4, 0] = (12, 8)
-        for fen, ref_plane, method in ((F, R, 5), (F, R2, 5), (F, R2, 1), (S, S2, 1), (S, S2, 0), (F, R, 0), (S, S2, 5)):
+        for fen, ref_plane, method in ((F, R, 5), (F, R2, 5), (F, R2, 1), (S, S2, 1), (S, S2, 0), (F, R, 0), (S, S2, 5),
+                                       (S, S2, 3), (S, S3, 3), (F, R, 3), (F, R2, 3)):
             merange = m if method == 5 else int(rng.integers(1, 40))
+            if ref_plane is S3: merange = int(rng.integers(16, 64))
             want_mv = np.zeros((n, 2), np.int32); want_c = np.zeros(n, np.int32)
             for i in range(n):
                 a = orc.motion_estimate_full(subme, w, h, fen, int(off[i]), geo.stride, ref_plane, int(off[i]), geo.stride, rngs[i], qmvp[i],

@@ -500,7 +500,7 @@ def test_me_full_search(libs):
 
 
 def test_motion_estimate(libs):
-    """the oracle's motionEstimate restatement (full, hexagon and diamond searches) vs the reference's MotionEstimate::motionEstimate itself
+    """the oracle's motionEstimate restatement (full, hexagon, diamond and star searches) vs the reference's MotionEstimate::motionEstimate itself
     (compiled from encoder/motion.cpp), every subme level, with neighbour candidates and predictors inside / outside the range"""
     o, r = libs
     from frames import Geometry, make_plane
@@ -526,7 +526,7 @@ def test_motion_estimate(libs):
         if case % 3 == 1: fen, ref = S, S2
         x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
         of = geo.origin + y * geo.stride + x
-        m = int(rng.integers(1, 17))
+        m = int(rng.integers(1, 17)) if case % 4 else int(rng.integers(17, 40))      # big windows: star rings of 16 / 32, raster pass
         # keep block + 8-tap margins inside the padded plane
         minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 8 - w - x)
         miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 8 - h - y)
@@ -537,7 +537,7 @@ def test_motion_estimate(libs):
         nc = int(rng.integers(0, 5))
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (nc, 2))
         if nc > 1: mvc[1] = qmvp
-        for method in (5, 1, 0):                          # X265_FULL_SEARCH, X265_HEX_SEARCH, X265_DIA_SEARCH
+        for method in (5, 1, 0, 3):                       # X265_FULL_SEARCH, X265_HEX_SEARCH, X265_DIA_SEARCH, X265_STAR_SEARCH
             merange = m if method == 5 else int(rng.integers(1, 40))
             a = o.motion_estimate_full(subme, w, h, fen, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD,
                                        method, merange)
@@ -546,4 +546,36 @@ def test_motion_estimate(libs):
             nonzero_exit += a[2] > 0
             if method != 5:
                 moved += max(abs(a[0] - int(np.clip(qmvp[0], 4 * minx, 4 * maxx))), abs(a[1] - int(np.clip(qmvp[1], 4 * miny, 4 * maxy)))) >= 16
-    assert nonzero_exit > 300 and moved > 40              # dozens of pattern walks ended four or more pels from their start
+    assert nonzero_exit > 400 and moved > 60              # dozens of pattern walks ended four or more pels from their start
+
+
+def test_motion_estimate_star_far(libs):
+    """star search with the match far from the start: big rings, the stride-5 raster pass (with the reference's
+    `mvcost(tmv << 3)` on every fourth column) and re-centred passes all decide the result"""
+    o, r = libs
+    from frames import Geometry, smooth_field
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(67)
+    S = smooth_field(geo, o.depth, 91, box=21)
+    RAD = 2048
+    cw, ch = geo.coded()
+    far = 0
+    for case in range(90):
+        dx, dy = int(rng.integers(-30, 31)), int(rng.integers(-24, 25))
+        S2 = np.roll(S, dy * geo.stride + dx)              # block content found at (+dx, +dy)
+        w, h = [(16, 16), (8, 8), (32, 32), (16, 8), (64, 64), (8, 16)][case % 6]
+        qp = int(rng.integers(0, 40))
+        tab = r.mvcost_table(qp, RAD)
+        x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
+        of = geo.origin + y * geo.stride + x
+        m = int(rng.integers(20, 48))
+        minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 8 - w - x)
+        miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 8 - h - y)
+        qmvp = rng.integers(-12, 13, 2)
+        mvc = rng.integers(-40, 41, (int(rng.integers(0, 3)), 2))
+        merange = int(rng.integers(8, 64))
+        a = o.motion_estimate_full(2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD, 3, merange)
+        b = r.motion_estimate(3, 2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+        assert a == b, (case, w, h, a, b)
+        far += max(abs(a[0] - qmvp[0]), abs(a[1] - qmvp[1])) >= 40
+    assert far > 30

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--depth", type=int, default=10)
     ap.add_argument("--merange", type=int, default=57)
     ap.add_argument("--subme", type=int, default=2)
-    ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 5 FULL")
+    ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 3 STAR, 5 FULL")
     ap.add_argument("--shapes", default="64,32,16,8", help="square PU sizes to run")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
@@ -85,7 +85,7 @@ def main():
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(); run_me(); e1.record(); e1.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            name = {0: "dia", 1: "hex", 5: "full"}[method]
+            name = {0: "dia", 1: "hex", 3: "star", 5: "full"}[method]
             row["motion_estimate_%s_ms_per_frame" % name] = sorted(ts)[1]
             if refl:
                 # the reference's own MotionEstimate::motionEstimate on every host core, on a sample of the same PUs

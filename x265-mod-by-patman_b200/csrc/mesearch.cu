@@ -205,7 +205,8 @@ static cudaError_t launch_me_full(const void* fenc, intptr_t strideF, const void
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Pattern searches: diamond (motion.cpp:1016-1039) and hexagon + square refinement (motion.cpp:1041-1138).
+// Pattern searches: diamond (motion.cpp:1016-1039), hexagon + square refinement (motion.cpp:1041-1138) and star
+// (motion.cpp:386-630, 1327-1435).
 // Each step depends on the previous best, so a PU is a sequential walk; one warp owns one PU (fenc block in shared
 // memory, the lanes split the block's samples, up to four candidates of a step are measured in one pass) and the
 // batch supplies the parallelism.  Only a candidate's row is range-checked, as in the reference; a step may leave the
@@ -225,18 +226,23 @@ struct PatternPU
     const uint16_t* cx;         // cost table shifted by the predictor (BitCost::setMVP)
     const uint16_t* cy;
     int w, h, lane, px0, py0, dq, dr;     // a lane's sample walks 32 positions per step: dq rows and dr columns
-    int miny, maxy;
+    int minx, maxx, miny, maxy;
 
-    // SAD + mvcost of up to four full-pel candidates in one pass over the block; rows outside the window are not read
-    __device__ void eval(int nc, const int (&cand)[4][2], int (&cost)[4], bool (&ok)[4]) const
+    __device__ bool row_ok(int y) const { return y >= miny && y <= maxy; }
+    __device__ bool inside(int x, int y) const { return x >= minx && x <= maxx && y >= miny && y <= maxy; }
+
+    // SAD + mvcost of up to four full-pel candidates in one pass over the block.  ok[k] says whether the reference
+    // measures candidate k at all (it is not read otherwise); q3 marks a candidate charged mvcost(mv << 3), the
+    // reference's raster quirk (motion.cpp:1392), instead of mv << 2.
+    __device__ void eval(int nc, const int (&cand)[4][2], const bool (&ok)[4], int (&cost)[4], int q3 = -1) const
     {
         const PIX* rp[4];
         unsigned acc[4];
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-            ok[k] = k < nc && cand[k][1] >= miny && cand[k][1] <= maxy;
-            rp[k] = r0 + (ok[k] ? cand[k][0] + (intptr_t)cand[k][1] * strideR : 0);
+            const bool use = k < nc && ok[k];
+            rp[k] = r0 + (use ? cand[k][0] + (intptr_t)cand[k][1] * strideR : 0);
             acc[k] = 0;
         }
         int px = px0, py = py0;
@@ -252,9 +258,140 @@ struct PatternPU
         }
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            cost[k] = (int)__reduce_add_sync(0xffffffffu, acc[k]) + (ok[k] ? (int)(uint16_t)(cx[cand[k][0] << 2] + cy[cand[k][1] << 2]) : 0);
+        {
+            const int sh = k == q3 ? 3 : 2;
+            const bool use = k < nc && ok[k];
+            cost[k] = (int)__reduce_add_sync(0xffffffffu, acc[k]) + (use ? (int)(uint16_t)(cx[cand[k][0] << sh] + cy[cand[k][1] << sh]) : 0);
+        }
     }
 };
+
+// running best of the star search: vector, cost, and the point number / distance of the ring point that set it
+struct StarBest { int x, y, cost, point, dist; };
+
+// ring point idx of the pattern at distance dist (motion.cpp:405-628): offset, point number, and the distance it reports
+__device__ __forceinline__ void star_point(int dist, int idx, int& dx, int& dy, int& point, int& d)
+{
+    if (dist == 1)
+    {   // 2 4 5 7
+        const int px[4] = { 0, -1, 1, 0 }, py[4] = { -1, 0, 0, 1 }, pn[4] = { 2, 4, 5, 7 };
+        dx = px[idx]; dy = py[idx]; point = pn[idx]; d = 1;
+    }
+    else if (dist <= 8)
+    {   // 2 1 3 4 5 6 8 7: axis points at dist, diagonal points at dist / 2
+        const int sx[8] = { 0, -1, 1, -2, 2, -1, 1, 0 }, sy[8] = { -2, -1, -1, 0, 0, 1, 1, 2 }, pn[8] = { 2, 1, 3, 4, 5, 6, 8, 7 };
+        const int h = dist >> 1;
+        dx = sx[idx] * h; dy = sy[idx] * h; point = pn[idx]; d = (idx == 0 || idx == 3 || idx == 4 || idx == 7) ? dist : h;
+    }
+    else
+    {   // top, left, right, bottom, then three points on each edge of the diamond, quarter by quarter
+        const int q = dist >> 2;
+        point = 0; d = dist;
+        if (idx < 4) { dx = idx == 1 ? -dist : idx == 2 ? dist : 0; dy = idx == 0 ? -dist : idx == 3 ? dist : 0; }
+        else
+        {
+            const int i = ((idx - 4) >> 2) + 1, c = (idx - 4) & 3;
+            dx = (c & 1) ? q * i : -q * i;
+            dy = (c & 2) ? dist - q * i : -dist + q * i;
+        }
+    }
+}
+
+template<typename PIX>
+__device__ void star_pattern(const PatternPU<PIX>& P, StarBest& b, int earlyExit, int merange)
+{
+    const int ox = b.x, oy = b.y;
+    int rounds = 0, saved = b.cost;
+    int cand[4][2], cost[4], pt[4], dd[4]; bool ok[4];
+    for (int dist = 1; dist <= 8 || dist <= (int)(int16_t)merange; dist <<= 1)
+    {
+        if (dist > 1) saved = b.cost;
+        const int npts = dist == 1 ? 4 : dist <= 8 ? 8 : 16;
+        for (int i0 = 0; i0 < npts; i0 += 4)
+        {
+            for (int k = 0; k < 4; k++)
+            {
+                int dx, dy;
+                star_point(dist, i0 + k, dx, dy, pt[k], dd[k]);
+                cand[k][0] = ox + dx; cand[k][1] = oy + dy;
+                ok[k] = P.inside(cand[k][0], cand[k][1]);
+            }
+            if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+            P.eval(4, cand, ok, cost);
+            for (int k = 0; k < 4; k++)
+                if (ok[k] && cost[k] < b.cost) { b.cost = cost[k]; b.x = cand[k][0]; b.y = cand[k][1]; b.point = pt[k]; b.dist = dd[k]; }
+        }
+        if (b.cost < saved) rounds = 0;
+        else if (++rounds >= earlyExit) return;
+    }
+}
+
+// the two outer neighbours of a distance-1 winner (motion.cpp:76-86 `offsets`), both taken around the winner as it was
+__constant__ int c_two_point[16][2] = { {-1, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {-1, -1},
+                                        {1, -1}, {1, 1}, {-1, 0}, {0, 1}, {-1, 1}, {1, 1}, {1, 0}, {0, 1} };
+template<typename PIX>
+__device__ void star_two_point(const PatternPU<PIX>& P, StarBest& b)
+{
+    int cand[4][2], cost[4]; bool ok[4] = { false, false, false, false };
+    const int p = (b.point - 1) * 2;
+    for (int k = 0; k < 2; k++)
+    {
+        cand[k][0] = b.x + c_two_point[p + k][0]; cand[k][1] = b.y + c_two_point[p + k][1];
+        ok[k] = P.inside(cand[k][0], cand[k][1]);
+    }
+    cand[2][0] = cand[3][0] = b.x; cand[2][1] = cand[3][1] = b.y;
+    if (!(ok[0] | ok[1])) return;
+    P.eval(2, cand, ok, cost);
+    for (int k = 0; k < 2; k++)
+        if (ok[k] && cost[k] < b.cost) { b.cost = cost[k]; b.x = cand[k][0]; b.y = cand[k][1]; }
+}
+
+// X265_STAR_SEARCH, motion.cpp:1327-1435
+template<typename PIX>
+__device__ void star_search(const PatternPU<PIX>& P, int merange, int& x, int& y, int& best)
+{
+    StarBest b = { x, y, best, 0, 0 };
+    star_pattern(P, b, 3, merange);
+    bool done = false;
+    if (b.dist == 1)
+    {
+        if (!b.point) done = true;
+        else
+        {
+            const int saved = b.cost;
+            star_two_point(P, b);
+            done = b.cost == saved;
+        }
+    }
+    if (!done)
+    {
+        if (b.dist > 5)
+        {   // raster over the window in steps of 5, four columns per pass where the reference uses sad_x4
+            int cand[4][2], cost[4]; bool ok[4];
+            for (int ty = P.miny; ty <= P.maxy; ty += 5)
+                for (int tx = P.minx; tx <= P.maxx; tx += 5)
+                {
+                    const bool quad = tx + 15 <= P.maxx;
+                    for (int k = 0; k < 4; k++) { cand[k][0] = tx + (quad ? 5 * k : 0); cand[k][1] = ty; ok[k] = quad || k == 0; }
+                    P.eval(quad ? 4 : 1, cand, ok, cost, quad ? 3 : -1);
+                    for (int k = 0; k < (quad ? 4 : 1); k++)
+                        if (cost[k] < b.cost) { b.cost = cost[k]; b.x = cand[k][0]; b.y = cand[k][1]; }
+                    if (quad) tx += 15;
+                }
+        }
+        while (b.dist > 0)
+        {   // re-centred passes until one brings nothing
+            b.dist = 0; b.point = 0;
+            star_pattern(P, b, 32, merange);
+            if (b.dist == 1)
+            {
+                if (b.point) star_two_point(P, b);
+                break;
+            }
+        }
+    }
+    x = b.x; y = b.y; best = b.cost;
+}
 
 template<typename PIX>
 __global__ void __launch_bounds__(MP_WARPS * 32)
@@ -284,19 +421,20 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
     PatternPU<PIX> P;
     P.fs = fs; P.r0 = ref + offR[pu]; P.strideR = strideR;
     P.cx = costTab - mvp[2 * pu]; P.cy = costTab - mvp[2 * pu + 1];
-    P.w = w; P.h = h; P.lane = lane; P.px0 = lane % w; P.py0 = lane / w; P.dq = 32 / w; P.dr = 32 % w; P.miny = miny; P.maxy = maxy;
+    P.w = w; P.h = h; P.lane = lane; P.px0 = lane % w; P.py0 = lane / w; P.dq = 32 / w; P.dr = 32 % w; P.minx = minx; P.maxx = maxx; P.miny = miny; P.maxy = maxy;
 
     int x = bmv[2 * pu], y = bmv[2 * pu + 1], best = bcost[pu];
-    int cand[4][2], cost[4]; bool ok[4];
+    int cand[4][2] = { {0, 0}, {0, 0}, {0, 0}, {0, 0} }, cost[4]; bool ok[4] = { false, false, false, false };
     auto in_range = [&](int cx, int cy) { return cx >= minx && cx <= maxx && cy >= miny && cy <= maxy; };
 
-    if (method == 0)
+    if (method == X265B200_ME_STAR) star_search(P, merange, x, y, best);
+    else if (method == 0)
     {   // diamond, radius 1: up, down, left, right
         int i = merange;
         do
         {
-            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[k + 1][0]; cand[k][1] = y + c_sq1[k + 1][1]; }
-            P.eval(4, cand, cost, ok);
+            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[k + 1][0]; cand[k][1] = y + c_sq1[k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
+            P.eval(4, cand, ok, cost);
             int win = -1;
             for (int k = 0; k < 4; k++)
                 if (ok[k] && cost[k] < best) { best = cost[k]; win = k; }
@@ -310,8 +448,8 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
         int win = 0;
         for (int half = 0; half < 2; half++)
         {
-            for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[half * 3 + k + 1][0]; cand[k][1] = y + c_hex2[half * 3 + k + 1][1]; }
-            P.eval(3, cand, cost, ok);
+            for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[half * 3 + k + 1][0]; cand[k][1] = y + c_hex2[half * 3 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
+            P.eval(3, cand, ok, cost);
             for (int k = 0; k < 3; k++)
                 if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 3 + k + 2; }
         }
@@ -321,8 +459,8 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
             x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
             for (int i = (merange >> 1) - 1; i > 0 && in_range(x, y); i--)
             {   // the three corners the previous hexagon did not cover
-                for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[dir + k][0]; cand[k][1] = y + c_hex2[dir + k][1]; }
-                P.eval(3, cand, cost, ok);
+                for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[dir + k][0]; cand[k][1] = y + c_hex2[dir + k][1]; ok[k] = P.row_ok(cand[k][1]); }
+                P.eval(3, cand, ok, cost);
                 win = 0;
                 for (int k = 0; k < 3; k++)
                     if (ok[k] && cost[k] < best) { best = cost[k]; win = k + 1; }
@@ -335,8 +473,8 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
         win = 0;
         for (int half = 0; half < 2; half++)
         {
-            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[half * 4 + k + 1][0]; cand[k][1] = y + c_sq1[half * 4 + k + 1][1]; }
-            P.eval(4, cand, cost, ok);
+            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[half * 4 + k + 1][0]; cand[k][1] = y + c_sq1[half * 4 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
+            P.eval(4, cand, ok, cost);
             for (int k = 0; k < 4; k++)
                 if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 4 + k + 1; }
         }
@@ -379,7 +517,8 @@ extern "C" int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, i
 {
     if (!ctx) return X265B200_ERR_ARG;
     if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0) return fail(ctx, X265B200_ERR_ARG, "me_pattern: bad geometry");
-    if (method != X265B200_ME_DIA && method != X265B200_ME_HEX) return fail(ctx, X265B200_ERR_ARG, "me_pattern: method must be DIA or HEX");
+    if (method != X265B200_ME_DIA && method != X265B200_ME_HEX && method != X265B200_ME_STAR)
+        return fail(ctx, X265B200_ERR_ARG, "me_pattern: method must be DIA, HEX or STAR");
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes;

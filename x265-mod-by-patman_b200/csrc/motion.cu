@@ -1,4 +1,4 @@
-// motion.cu -- MotionEstimate::motionEstimate for a batch of prediction units, searchMethod DIA / HEX / FULL, luma only
+// motion.cu -- MotionEstimate::motionEstimate for a batch of prediction units, searchMethod DIA / HEX / STAR / FULL, luma only
 // (reference encoder/motion.cpp:923-1013 start point, :1016-1138 / :1593-1637 integer search, :1643-1773 sub-pel refinement and the
 // zero-vector last chance; the setSourcePU variant of motion.cpp:166-189: one slice, no vertical restriction).
 //
@@ -186,8 +186,8 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
     if (!ctx) return X265B200_ERR_ARG;
     if (subpelRefine < 0 || subpelRefine > 7 || numCand < 0 || numCand > ME_MAX_CAND || n < 0 || (numCand && !mvc))
         return fail(ctx, X265B200_ERR_ARG, "motion_estimate: bad arguments");
-    if (searchMethod != X265B200_ME_DIA && searchMethod != X265B200_ME_HEX && searchMethod != X265B200_ME_FULL)
-        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: search method not built (DIA, HEX, FULL are)");
+    if (searchMethod != X265B200_ME_DIA && searchMethod != X265B200_ME_HEX && searchMethod != X265B200_ME_STAR && searchMethod != X265B200_ME_FULL)
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: search method not built (DIA, HEX, STAR, FULL are)");
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
 
