@@ -38,6 +38,30 @@ int ref_motion_estimate(int method, int subme, int w, int h, pixel* fencPlane, i
     return cost;
 }
 
+/* the lookahead's use (slicetype.cpp:4484-4566): a lowres reference = four half-pel planes `pitch` samples apart,
+ * ref->isLowres set, no neighbour candidates */
+extern "C" __attribute__((visibility("default")))
+int ref_lowres_motion_estimate(int method, int subme, int w, int h, pixel* fencPlane, intptr_t strideF, intptr_t offF,
+                               pixel* planes, intptr_t strideR, size_t pitch, intptr_t offR, const int32_t* range,
+                               const int32_t* qmvp, int merange, int qp, int32_t* outQMv)
+{
+    static bool scales = false;
+    if (!scales) { ref_ensure(); MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setQP(qp);
+    me.setSourcePU(fencPlane, strideF, offF, w, h, method, subme);
+    ReferencePlanes ref;
+    for (int k = 0; k < 4; k++) ref.lowresPlane[k] = planes + k * pitch + (offR - offF);
+    ref.fpelPlane[0] = ref.lowresPlane[0];
+    ref.lumaStride = strideR;
+    ref.isLowres = true;
+    MV mvmin(range[0], range[1]), mvmax(range[2], range[3]), mvp(qmvp[0], qmvp[1]), out;
+    int cost = me.motionEstimate(&ref, mvmin, mvmax, mvp, 0, NULL, merange, out, 1, false);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
 /* the lambda-scaled mv cost table BitCost::setQP builds, copied out for the other implementations: [-radius, radius] */
 extern "C" __attribute__((visibility("default")))
 void ref_mvcost_table(int qp, int radius, uint16_t* out)

@@ -983,9 +983,28 @@ static const int k_subpel_workload[8][5] = {      /* motion.cpp:48-58: hpel_iter
     { 2, 4, 2, 4, 1 }, { 1, 8, 1, 8, 1 }, { 2, 8, 1, 8, 1 }, { 2, 8, 2, 8, 1 } };
 static const int k_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };   /* motion.cpp:67 */
 
-typedef struct { int w, h; const pixel* fenc; intptr_t sf; const pixel* fref; intptr_t sr; const uint16_t* cx; const uint16_t* cy; } me_ctx;
+typedef struct { int w, h; const pixel* fenc; intptr_t sf; const pixel* fref; intptr_t sr; const uint16_t* cx; const uint16_t* cy;
+                 const pixel* hpel[4]; /* lowres: the four half-pel planes at the co-located block, else NULL */ } me_ctx;
+/* ReferencePlanes::lowresQPelCost (common/lowres.h:95-119): a quarter-pel position of a lowres reference is the rounded
+ * average of the two nearest half-pel planes (pixelavg_pp, pixel.cpp:586-594), a half / full-pel one is a plane itself */
+static int me_lowres_cost(const me_ctx* c, int qx, int qy, int op)
+{
+    pixel buf[64 * 64];
+    const pixel* a = c->hpel[(qy & 2) | ((qx & 2) >> 1)] + (qx >> 2) + (intptr_t)(qy >> 2) * c->sr;
+    const pixel* src = a; intptr_t ss = c->sr;
+    if ((qx | qy) & 1)
+    {
+        int bx = qx + (qx & 1), by = qy + (qy & 1);
+        const pixel* b = c->hpel[(by & 2) | ((bx & 2) >> 1)] + (bx >> 2) + (intptr_t)(by >> 2) * c->sr;
+        for (int y = 0; y < c->h; y++)
+            for (int x = 0; x < c->w; x++) buf[y * c->w + x] = (pixel)((a[y * c->sr + x] + b[y * c->sr + x] + 1) >> 1);
+        src = buf; ss = c->w;
+    }
+    return op ? orc_satd(c->w, c->h, c->fenc, c->sf, src, ss) : orc_sad(c->w, c->h, c->fenc, c->sf, src, ss);
+}
 static int me_subpel(const me_ctx* c, int qx, int qy, int op)   /* subpelCompare, motion.cpp:1775-1803 */
 {
+    if (c->hpel[0]) return me_lowres_cost(c, qx, qy, op);
     return orc_subpel_cmp(op, c->w, c->h, c->fenc, c->sf, c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->sr, c->sr, qx & 3, qy & 3);
 }
 static int me_mvcost(const me_ctx* c, int qx, int qy) { return (uint16_t)(c->cx[qx] + c->cy[qy]); }   /* bitcost.h:56 */
@@ -1187,12 +1206,13 @@ static void me_star_search(const me_ctx* c, const int32_t* range, int merange, i
 }
 
 /* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_STAR_SEARCH 3, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
-EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
-                               const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
-                               const uint16_t* costTab, int32_t* outQMv)
+static int me_estimate(me_ctx cc, int method, int merange, int subme, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                       const uint16_t* costTab, int32_t* outQMv)
 {
     if (method != 0 && method != 1 && method != 3 && method != 5) return -1;
-    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1] };
+    const me_ctx c = cc;
+    const int w = c.w, h = c.h; const pixel* fenc = c.fenc; const pixel* fref = c.fref; const intptr_t sf = c.sf, sr = c.sr;
+    const int lowres = c.hpel[0] != 0;
     const int qminx = range[0] * 4, qminy = range[1] * 4, qmaxx = range[2] * 4, qmaxy = range[3] * 4;
 
     /* :954-975 SAD at the clipped predictor, then at its full-pel rounding */
@@ -1245,6 +1265,28 @@ EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h,
     const int* wl = k_subpel_workload[subme];
     if (!bcost)
         bcost = me_mvcost(&c, bmvx, bmvy);              /* :1661-1666 */
+    else if (lowres)
+    {   /* :1667-1698: one half-pel step judged by SAD, re-measured with SATD, one quarter-pel step */
+        int bdir = 0;
+        for (int i = 1; i <= wl[1]; i++)
+        {
+            int qx = bmvx + k_square1[i][0] * 2, qy = bmvy + k_square1[i][1] * 2;
+            if (qy < qminy || qy > qmaxy) continue;
+            int cost = me_subpel(&c, qx, qy, 0) + me_mvcost(&c, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmvx += k_square1[bdir][0] * 2; bmvy += k_square1[bdir][1] * 2;
+        bcost = me_subpel(&c, bmvx, bmvy, 1) + me_mvcost(&c, bmvx, bmvy);
+        bdir = 0;
+        for (int i = 1; i <= wl[3]; i++)
+        {
+            int qx = bmvx + k_square1[i][0], qy = bmvy + k_square1[i][1];
+            if (qy < qminy || qy > qmaxy) continue;
+            int cost = me_subpel(&c, qx, qy, 1) + me_mvcost(&c, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmvx += k_square1[bdir][0]; bmvy += k_square1[bdir][1];
+    }
     else
     {   /* :1700-1757 */
         int hpelop = 0;
@@ -1285,4 +1327,22 @@ EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h,
     }
     outQMv[0] = bmvx; outQMv[1] = bmvy;
     return bcost;
+}
+
+EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                               const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                               const uint16_t* costTab, int32_t* outQMv)
+{
+    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 } };
+    return me_estimate(c, method, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
+}
+/* the lookahead's call (encoder/slicetype.cpp:4484-4566): lowres reference = four half-pel planes `pitch` samples apart
+ * (frameInitLowres), 8x8 blocks, no neighbour candidates; refBlock points at the co-located block in plane 0 */
+EXPORT int orc_lowres_motion_estimate(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf,
+                                      const pixel* refBlock, intptr_t sr, size_t pitch, const int32_t* range, const int32_t* qmvp,
+                                      const uint16_t* costTab, int32_t* outQMv)
+{
+    me_ctx c = { w, h, fenc, sf, refBlock, sr, costTab - qmvp[0], costTab - qmvp[1],
+                 { refBlock, refBlock + pitch, refBlock + 2 * pitch, refBlock + 3 * pitch } };
+    return me_estimate(c, method, merange, subme, range, qmvp, 0, 0, costTab, outQMv);
 }

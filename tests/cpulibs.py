@@ -197,6 +197,14 @@ class _Base:
                                             len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    def lowres_motion_estimate(self, method, merange, subme, w, h, fenc, of, sf, planes, orf, sr, pitch, rng, qmvp, cost_tab, centre):
+        """oracle: the lookahead's motionEstimate on a lowres reference (four half-pel planes `pitch` apart)"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        c = self._f("lowres_motion_estimate")(method, merange, subme, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(planes, orf), C.c_ssize_t(sr),
+                                              C.c_size_t(pitch), _ptr(rng), _ptr(qmvp), _ptr(cost_tab, centre), _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
+
     # ---- sub-pel candidate cost (subpelCompare): interpolation + sad (op 0) / satd (op 1) ----------------------
     def subpel_cmp(self, op, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp")(op, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
@@ -340,6 +348,13 @@ class Reference(_Base):
         self.lib.ref_motion_estimate_batch(method, subme, w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(offF), _ptr(ref), C.c_ssize_t(sr), _ptr(offR),
                                            _ptr(rng), _ptr(qmvp), nc, _ptr(mvc) if nc else None, merange, qp, n, _ptr(mv), _ptr(cost), nthreads)
         return mv, cost
+
+    def lowres_motion_estimate_ref(self, method, subme, w, h, fenc, of, sf, planes, orf, sr, pitch, rng, qmvp, merange, qp):
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        c = self.lib.ref_lowres_motion_estimate(method, subme, w, h, _ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(planes), C.c_ssize_t(sr),
+                                                C.c_size_t(pitch), C.c_ssize_t(orf), _ptr(rng), _ptr(qmvp), merange, qp, _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
 
     def mvcost_table(self, qp, radius):
         out = np.zeros(2 * radius + 1, np.uint16)

@@ -579,3 +579,49 @@ def test_motion_estimate_star_far(libs):
         assert a == b, (case, w, h, a, b)
         far += max(abs(a[0] - qmvp[0]), abs(a[1] - qmvp[1])) >= 40
     assert far > 30
+
+
+def lowres_planes(geo, depth, seed):
+    """four half-pel planes of a smooth field, `geo.plane_elems` apart, shaped like frameInitLowres's output
+    (full-pel, half-pel right, half-pel down, half-pel diagonal) over the padded geometry"""
+    from frames import smooth_field
+    S = smooth_field(geo, depth, seed, box=7).reshape(geo.rows, geo.stride).astype(np.int64)
+    right = np.roll(S, -1, 1); down = np.roll(S, -1, 0); diag = np.roll(right, -1, 0)
+    H = (S + right + 1) >> 1; V = (S + down + 1) >> 1; Cc = (S + right + down + diag + 2) >> 2
+    dt = np.uint8 if depth == 8 else np.uint16
+    return np.concatenate([p.astype(dt).ravel() for p in (S, H, V, Cc)])
+
+
+def test_lowres_motion_estimate(libs):
+    """the lookahead's motionEstimate (lowres reference, 8x8 blocks, quarter-pel cost = average of two half-pel planes) vs the
+    reference's MotionEstimate::motionEstimate with ref->isLowres"""
+    o, r = libs
+    from frames import Geometry
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(71)
+    P = lowres_planes(geo, o.depth, 95)
+    pitch = geo.plane_elems
+    RAD = 2048
+    cw, ch = geo.coded()
+    sub = 0
+    for case in range(240):
+        dx, dy = int(rng.integers(-12, 13)), int(rng.integers(-10, 11))
+        src = P[(case % 4) * pitch:(case % 4 + 1) * pitch] if case % 3 == 0 else P[:pitch]      # fenc sits on a half-pel phase sometimes
+        F = np.clip(np.roll(src, dy * geo.stride + dx).astype(np.int64) + rng.integers(-2, 3, pitch), 0, o.pmax).astype(P.dtype)
+        qp = int(rng.integers(0, 52))
+        tab = r.mvcost_table(qp, RAD)
+        x = int(rng.integers(0, cw - 8 + 1)); y = int(rng.integers(0, ch - 8 + 1))
+        of = geo.origin + y * geo.stride + x
+        m = int(rng.integers(2, 30))
+        minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 16 - x)
+        miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 16 - y)
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, 2)
+        if case % 7 == 0: qmvp[:] = 0
+        method = (1, 1, 0, 3, 5)[case % 5]
+        subme = (1, 1, 2, 0, 5, 7)[case % 6]
+        merange = m if method == 5 else int(rng.integers(1, 33))
+        a = o.lowres_motion_estimate(method, merange, subme, 8, 8, F, of, geo.stride, P, of, geo.stride, pitch, [minx, miny, maxx, maxy], qmvp, tab, RAD)
+        b = r.lowres_motion_estimate_ref(method, subme, 8, 8, F, of, geo.stride, P, of, geo.stride, pitch, [minx, miny, maxx, maxy], qmvp, merange, qp)
+        assert a == b, (case, method, subme, a, b)
+        sub += (a[0] | a[1]) & 1
+    assert sub > 40                                       # quarter-pel winners: the two-plane average decided them
