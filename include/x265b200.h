@@ -233,6 +233,18 @@ int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, i
                                    int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
                                    int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
 
+/* The lookahead's motionEstimate (reference encoder/slicetype.cpp:4484-4566 -> motion.cpp:923-1773 with ref->isLowres): the
+ * reference picture is a lowres frame = four half-pel planes (full-pel, half-pel x, half-pel y, half-pel xy, as
+ * x265b200_lowres_batch / frameInitLowres writes them) planePitch samples apart starting at `planes`; a quarter-pel vector
+ * is costed on the rounded average of the two nearest planes (ReferencePlanes::lowresQPelCost, common/lowres.h:95-119),
+ * refinement is one SAD half-pel step, a SATD re-measure and one SATD quarter-pel step (motion.cpp:1667-1698), and there
+ * are no neighbour candidates.  Other arguments and outputs as x265b200_motion_estimate_batch.  The reference runs this
+ * on 8x8 blocks (its averaging buffer is 8x8); other sizes follow the same definition. */
+int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
+                                          const void* fenc, intptr_t strideF, const void* planes, intptr_t strideR, size_t planePitch,
+                                          const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                          const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

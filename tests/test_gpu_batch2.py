@@ -571,3 +571,54 @@ def test_motion_estimate_batch(depth):
                 walked += int((np.abs(want_mv - np.clip(qmvp, 4 * rngs[:, :2], 4 * rngs[:, 2:])).max(1) >= 16).sum())
     assert walked > 100                                   # pattern searches ended four or more pels from their start
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_lowres_motion_estimate_batch(depth):
+    """the lookahead's motionEstimate on a lowres reference (four half-pel planes, quarter-pel cost on the average of two)
+    for batches of 8x8 blocks vs the oracle (pinned to the reference with ref->isLowres by the CPU suite): every search
+    method built, several subme levels, fenc on full- and half-pel phases, windows clipped at the picture edge"""
+    import torch
+    from gpulib import context
+    from frames import Geometry
+    from test_oracle_vs_ref import lowres_planes, mv_cost_table
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    rng = np.random.default_rng(600 + depth)
+    P = lowres_planes(geo, depth, 97)
+    pitch = geo.plane_elems
+    cw, ch = geo.coded()
+    RAD = 2048
+    tab = mv_cost_table(6.3496, RAD); dtab = dev(tab.view(np.int16))
+    dP = dev(pix_view(P, depth))
+    sub = 0
+    for case in range(12):
+        method = (1, 0, 3, 5)[case % 4]
+        subme = (1, 2, 0, 5, 7, 1)[case % 6]
+        dx, dy = int(rng.integers(-12, 13)), int(rng.integers(-10, 11))
+        src = P[(case % 4) * pitch:(case % 4 + 1) * pitch]
+        F = np.clip(np.roll(src, dy * geo.stride + dx).astype(np.int64) + rng.integers(-2, 3, pitch), 0, orc.pmax).astype(P.dtype)
+        n = 150
+        x = rng.integers(0, cw - 8 + 1, n); y = rng.integers(0, ch - 8 + 1, n)
+        x[:10] = 0; y[10:20] = ch - 8                      # blocks on the picture edge
+        off = (geo.origin + y * geo.stride + x).astype(np.int32)
+        m = int(rng.integers(4, 26))
+        minx = -np.minimum(m, x + geo.margin_x - 8); maxx = np.minimum(m, cw + geo.margin_x - 16 - x)
+        miny = -np.minimum(m, y + geo.margin_y - 8); maxy = np.minimum(m, ch + geo.margin_y - 16 - y)
+        rngs = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, (n, 2)).astype(np.int32)
+        qmvp[::6] = 0
+        merange = m if method == 5 else int(rng.integers(1, 33))
+        want_mv = np.zeros((n, 2), np.int32); want_c = np.zeros(n, np.int32)
+        for i in range(n):
+            a = orc.lowres_motion_estimate(method, merange, subme, 8, 8, F, int(off[i]), geo.stride, P, int(off[i]), geo.stride, pitch, rngs[i],
+                                           qmvp[i], tab, RAD)
+            want_mv[i] = a[:2]; want_c[i] = a[2]
+        gmv = torch.full((n, 2), -7777, dtype=torch.int32, device="cuda"); gc = torch.full((n,), -7777, dtype=torch.int32, device="cuda")
+        ctx.lowres_motion_estimate_batch(method, 8, 8, merange, subme, dev(pix_view(F, depth)), geo.stride, dP, geo.stride, pitch, dev(off), dev(off),
+                                         dev(rngs), dev(qmvp), dtab.data_ptr() + 2 * RAD, gmv, gc)
+        assert np.array_equal(gc.cpu().numpy(), want_c), (case, method, subme)
+        assert np.array_equal(gmv.cpu().numpy(), want_mv), (case, method, subme)
+        sub += int(((want_mv[:, 0] | want_mv[:, 1]) & 1).sum())
+    assert sub > 100                                      # quarter-pel winners: the two-plane average decided them
+    ctx.check()

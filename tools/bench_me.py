@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--subme", type=int, default=2)
     ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 3 STAR, 5 FULL")
     ap.add_argument("--shapes", default="64,32,16,8", help="square PU sizes to run")
+    ap.add_argument("--lowres", action="store_true", help="also time the lookahead's lowres search")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
     D, M = args.depth, args.merange
@@ -115,6 +116,44 @@ def main():
             row["cpu_port_1core_G_sample_candidates_per_s"] = cc * w * h / dt / 1e9
             got_mv = bmv.cpu().numpy()[sel]; got_c = bc.cpu().numpy()[sel]
             row["cpu_sample_matches"] = bool(np.array_equal(got_mv, mv) and np.array_equal(got_c, c))
+        rows.append(row)
+        print(json.dumps(row), file=sys.stderr)
+    if args.lowres:
+        # the lookahead's search: 1920x1080 lowres frame, every 8x8 block, HEX, subme 1, merange 16 (slicetype.cpp:4484-4566)
+        from test_oracle_vs_ref import lowres_planes
+        lgeo = Geometry(1920, 1080)
+        P = lowres_planes(lgeo, D, 7); pitch = lgeo.plane_elems
+        Fl = np.roll(P[:pitch], 3 * lgeo.stride - 5).copy()
+        dPl = torch.from_numpy(P.view(vt)).cuda(); dFl = torch.from_numpy(Fl.view(vt)).cuda()
+        oa, _ = tile_blocks(lgeo, 8, 8, seed=1)
+        n = oa.size; lcw, lch = lgeo.coded(); LM = 16
+        px = (oa - lgeo.origin) % lgeo.stride; py = (oa - lgeo.origin) // lgeo.stride
+        rng = np.stack([-np.minimum(LM, px + lgeo.margin_x - 8), -np.minimum(LM, py + lgeo.margin_y - 8),
+                        np.minimum(LM, lcw + lgeo.margin_x - 16 - px), np.minimum(LM, lch + lgeo.margin_y - 16 - py)], 1).astype(np.int32).copy()
+        hq = np.random.default_rng(3).integers(-12, 13, (n, 2)).astype(np.int32)
+        d = [torch.from_numpy(a).cuda() for a in (oa.astype(np.int32), rng, hq)]
+        oq = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); oc = torch.zeros((n,), dtype=torch.int32, device="cuda")
+
+        def run_lr():
+            ctx.lowres_motion_estimate_batch(1, 8, 8, LM, 1, dFl, lgeo.stride, dPl, lgeo.stride, pitch, d[0], d[0], d[1], d[2], dtab.data_ptr() + 2 * RAD, oq, oc)
+        run_lr(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); run_lr(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        row = {"lowres": "1920x1080, 8x8, HEX, subme 1, merange 16", "n_cu": int(n), "ms_per_frame": sorted(ts)[2]}
+        if refl:
+            k = 3000
+            sel = np.linspace(0, n - 1, k).astype(np.int64)
+            gq = oq.cpu().numpy(); gcst = oc.cpu().numpy()
+            t0 = time.perf_counter(); ok = True
+            for i in sel:
+                a = refl.lowres_motion_estimate_ref(1, 1, 8, 8, Fl, int(oa[i]), lgeo.stride, P, int(oa[i]), lgeo.stride, pitch, rng[i], hq[i], LM, QP)
+                ok = ok and a == (int(gq[i, 0]), int(gq[i, 1]), int(gcst[i]))
+            dt = time.perf_counter() - t0
+            row["ref_us_per_cu_1_thread_incl_ctypes"] = dt / k * 1e6
+            row["ref_sample_matches"] = bool(ok)
         rows.append(row)
         print(json.dumps(row), file=sys.stderr)
     ctx.check()

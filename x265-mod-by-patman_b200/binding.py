@@ -157,6 +157,12 @@ class Context:
                    _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(out_qmv), _dp(out_cost),
                    C.c_void_p(stream))
 
+    def lowres_motion_estimate_batch(self, method, w, h, merange, subme, fenc, sf, planes, sr, plane_pitch, offF, offR, rng, qmvp,
+                                     cost_tab_centre, out_qmv, out_cost, stream=0):
+        self._call("x265b200_lowres_motion_estimate_batch", int(method), w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(planes), _ss(sr),
+                   C.c_size_t(int(plane_pitch)), _dp(offF), _dp(offR), _dp(rng), _dp(qmvp), C.c_void_p(int(cost_tab_centre)), int(offF.numel()),
+                   _dp(out_qmv), _dp(out_cost), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

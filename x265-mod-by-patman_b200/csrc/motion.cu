@@ -12,6 +12,8 @@
 // A PU that left the chain early (zero residual) or whose refinement loop broke keeps producing harmless candidates at
 // its current vector so the launches stay dense; its state no longer changes.
 #include "internal.h"
+#include "device_util.cuh"
+#include "tile_kernels.cuh"
 
 namespace b200 {
 
@@ -42,14 +44,84 @@ __device__ __forceinline__ int mvcost(const uint16_t* tab, int mvpx, int mvpy, i
 {
     return (uint16_t)(tab[qx - mvpx] + tab[qy - mvpy]);       // bitcost.h:56
 }
-__device__ __forceinline__ void put_cand(const MeState& s, size_t slot, int base, intptr_t strideR, int qx, int qy)
+// pitch == 0: full-resolution reference, candidate = (integer offset, xFrac | yFrac << 4) for the interpolating kernel.
+// pitch > 0: lowres reference of four half-pel planes `pitch` samples apart; candidate = the two plane blocks whose
+// rounded average is the prediction (ReferencePlanes::lowresQPelCost, lowres.h:95-119), equal for half / full-pel vectors.
+__device__ __forceinline__ void put_cand(const MeState& s, size_t slot, int base, intptr_t strideR, int pitch, int qx, int qy)
 {
-    s.candOff[slot] = base + (qx >> 2) + (qy >> 2) * (int)strideR;      // subpelCompare, motion.cpp:1777-1781
-    s.candFrac[slot] = (qx & 3) | ((qy & 3) << 4);
+    if (!pitch)
+    {
+        s.candOff[slot] = base + (qx >> 2) + (qy >> 2) * (int)strideR;      // subpelCompare, motion.cpp:1777-1781
+        s.candFrac[slot] = (qx & 3) | ((qy & 3) << 4);
+        return;
+    }
+    const int a = ((qy & 2) | ((qx & 2) >> 1)) * pitch + base + (qx >> 2) + (qy >> 2) * (int)strideR;
+    int b = a;
+    if ((qx | qy) & 1)
+    {
+        const int bx = qx + (qx & 1), by = qy + (qy & 1);
+        b = ((by & 2) | ((bx & 2) >> 1)) * pitch + base + (bx >> 2) + (by >> 2) * (int)strideR;
+    }
+    s.candOff[slot] = a;
+    s.candFrac[slot] = b;
+}
+
+// cost[i] = SAD / SATD(fenc block i / K, (A_i + B_i + 1) >> 1): G lanes share a candidate, a lane takes 4x4 tiles
+template<typename T, int OP>
+__global__ void __launch_bounds__(256)
+lowres_cmp_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ planes, intptr_t sr, const int32_t* __restrict__ offF,
+                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB, int K, int ncand, int w, int h, int G,
+                  int32_t* __restrict__ cost)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lg = __ffs(G) - 1;
+    const int cand = (int)(gid >> lg), l = (int)gid & (G - 1);
+    const bool live = cand < ncand;
+    const int tw = w >> 2, T4 = tw * (h >> 2);
+    int acc = 0;
+    if (live)
+    {
+        const T* f = fenc + offF[cand / K];
+        const T* a = planes + offA[cand];
+        const T* b = planes + offB[cand];
+        for (int t = l; t < T4; t += G)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            uint32_t flo[4], fhi[4], alo[4], ahi[4], blo[4], bhi[4];
+            load_tile4x4(f + (intptr_t)(ty << 2) * sf + (tx << 2), sf, flo, fhi);
+            load_tile4x4(a + (intptr_t)(ty << 2) * sr + (tx << 2), sr, alo, ahi);
+            load_tile4x4(b + (intptr_t)(ty << 2) * sr + (tx << 2), sr, blo, bhi);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {   // pixelavg_pp (pixel.cpp:586-594) on packed pairs: samples < 2^15, so the halves cannot carry into each other
+                alo[r] = ((alo[r] + blo[r] + 0x00010001u) >> 1) & 0x7fff7fffu;
+                ahi[r] = ((ahi[r] + bhi[r] + 0x00010001u) >> 1) & 0x7fff7fffu;
+            }
+            tile4_accumulate<OP, int>(flo, fhi, alo, ahi, acc);
+        }
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) cost[cand] = acc;
+}
+
+static int launch_lowres_cmp(x265b200_ctx* ctx, int op, int w, int h, const void* fenc, intptr_t sf, const void* planes, intptr_t sr,
+                             const int32_t* offF, const int32_t* offA, const int32_t* offB, int K, int n, int32_t* cost, cudaStream_t st)
+{
+    const int T4 = (w >> 2) * (h >> 2), per = T4 >= 16 ? 4 : 2;
+    int G = 1;
+    while (G * 2 * per <= T4 && G < 32) G <<= 1;
+    const long long cands = (long long)n * K;
+    const int grid = ceil_div(cands * G, 256);
+#define LC(T, OP_) lowres_cmp_kernel<T, OP_><<<grid, 256, 0, st>>>((const T*)fenc, sf, (const T*)planes, sr, offF, offA, offB, K, (int)cands, w, h, G, cost)
+    if (ctx->pixbytes == 1) { if (op == X265B200_SAD) LC(uint8_t, OP_SAD); else LC(uint8_t, OP_SATD); }
+    else { if (op == X265B200_SAD) LC(uint16_t, OP_SAD); else LC(uint16_t, OP_SATD); }
+#undef LC
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
 }
 
 __global__ void me_start_gen(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
-                             const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, MeState s)
+                             const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, int pitch, MeState s)
 {
     int pu = blockIdx.x * blockDim.x + threadIdx.x;
     if (pu >= n) return;
@@ -58,11 +130,11 @@ __global__ void me_start_gen(int n, int nc, int K, const int32_t* __restrict__ q
     s.pmv[2 * pu] = px; s.pmv[2 * pu + 1] = py;
     const int base = offR[pu];
     const size_t o = (size_t)pu * K;
-    put_cand(s, o, base, strideR, px, py);
-    put_cand(s, o + 1, base, strideR, ((px + 2) >> 2) * 4, ((py + 2) >> 2) * 4);
-    put_cand(s, o + 2, base, strideR, 0, 0);
+    put_cand(s, o, base, strideR, pitch, px, py);
+    put_cand(s, o + 1, base, strideR, pitch, ((px + 2) >> 2) * 4, ((py + 2) >> 2) * 4);
+    put_cand(s, o + 2, base, strideR, pitch, 0, 0);
     for (int i = 0; i < nc; i++)
-        put_cand(s, o + 3 + i, base, strideR, clip3(qminx, qmaxx, mvc[((size_t)pu * nc + i) * 2]), clip3(qminy, qmaxy, mvc[((size_t)pu * nc + i) * 2 + 1]));
+        put_cand(s, o + 3 + i, base, strideR, pitch, clip3(qminx, qmaxx, mvc[((size_t)pu * nc + i) * 2]), clip3(qminy, qmaxy, mvc[((size_t)pu * nc + i) * 2 + 1]));
 }
 
 __global__ void me_start_select(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
@@ -108,7 +180,7 @@ __global__ void me_start_select(int n, int nc, int K, const int32_t* __restrict_
 // mode bit 0: the step after the integer search (:1643-1666); bit 1: take the decisions of round `prev` (:1700-1757);
 // bit 2: emit the candidates of round `next`; bit 3: zero-vector last chance and outputs (:1762-1772)
 __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, const int32_t* __restrict__ qmvp,
-                                const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR,
+                                const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, int pitch,
                                 const uint16_t* __restrict__ tab, MeState s, int32_t* __restrict__ outQMv, int32_t* __restrict__ outCost)
 {
     int pu = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,14 +224,14 @@ __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, con
         const int base = offR[pu];
         const bool live = !(flags & ME_FIN);                   // a finished PU's bmv is still in full pels: park it on the zero vector
         const int cx = live ? bmvx : 0, cy = live ? bmvy : 0;
-        put_cand(s, o, base, strideR, cx, cy);
+        put_cand(s, o, base, strideR, pitch, cx, cy);
         for (int i = 1; i <= next.dirs; i++)
         {
             int qx = cx + c_square1[i][0] * next.step, qy = cy + c_square1[i][1] * next.step;
             if (!live || qy < qminy || qy > qmaxy) { qx = cx; qy = cy; }      // never measured by the reference: stay on a valid block
-            put_cand(s, o + i, base, strideR, qx, qy);
+            put_cand(s, o + i, base, strideR, pitch, qx, qy);
         }
-        if (next.zeroSlot) put_cand(s, o + next.K - 1, base, strideR, 0, 0);
+        if (next.zeroSlot) put_cand(s, o + next.K - 1, base, strideR, pitch, 0, 0);
     }
     if ((mode & 8) && !(flags & ME_FIN))
     {
@@ -177,11 +249,12 @@ __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, con
 
 using namespace b200;
 
-extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
-                                              const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
-                                              const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
-                                              int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
-                                              int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+// pitch == 0: full-resolution reference (interpolating sub-pel costs); pitch > 0: lowres reference, four half-pel planes
+static int motion_chain(x265b200_ctx* ctx, int pitch, int searchMethod, int w, int h, int merange, int subpelRefine,
+                        const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                        const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                        int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
+                        int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
 {
     if (!ctx) return X265B200_ERR_ARG;
     if (subpelRefine < 0 || subpelRefine > 7 || numCand < 0 || numCand > ME_MAX_CAND || n < 0 || (numCand && !mvc))
@@ -196,16 +269,24 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
                                         { 2, 4, 2, 4, 1 }, { 1, 8, 1, 8, 1 }, { 2, 8, 1, 8, 1 }, { 2, 8, 2, 8, 1 } };
     const int* wl = workload[subpelRefine];
     MeRound rounds[8]; int ops[8]; int R = 0;
-    for (int it = 0; it < wl[0]; it++)
-    {
-        rounds[R] = MeRound{ 2, wl[1], it == 0 && wl[4], it == 0, 0, 0 };
-        ops[R++] = wl[4] ? X265B200_SATD : X265B200_SAD;
+    if (pitch)
+    {   // lowres reference (:1667-1698): one SAD half-pel step, SATD re-measure, one SATD quarter-pel step
+        rounds[R] = MeRound{ 2, wl[1], 0, 1, 0, 0 }; ops[R++] = X265B200_SAD;
+        rounds[R] = MeRound{ 1, wl[3], 1, 1, 0, 0 }; ops[R++] = X265B200_SATD;
     }
-    for (int it = 0; it < (wl[2] ? wl[2] : 1); it++)
-    {   // with no quarter-pel iterations a SAD half-pel search is still re-measured with SATD (:1729-1731)
-        if (!wl[2] && wl[4]) break;
-        rounds[R] = MeRound{ 1, wl[2] ? wl[3] : 0, it == 0 && !wl[4], it == 0, 0, 0 };
-        ops[R++] = X265B200_SATD;
+    else
+    {
+        for (int it = 0; it < wl[0]; it++)
+        {
+            rounds[R] = MeRound{ 2, wl[1], it == 0 && wl[4], it == 0, 0, 0 };
+            ops[R++] = wl[4] ? X265B200_SATD : X265B200_SAD;
+        }
+        for (int it = 0; it < (wl[2] ? wl[2] : 1); it++)
+        {   // with no quarter-pel iterations a SAD half-pel search is still re-measured with SATD (:1729-1731)
+            if (!wl[2] && wl[4]) break;
+            rounds[R] = MeRound{ 1, wl[2] ? wl[3] : 0, it == 0 && !wl[4], it == 0, 0, 0 };
+            ops[R++] = X265B200_SATD;
+        }
     }
     rounds[R - 1].zeroSlot = 1;                                // the last round is always a SATD round
     int KMAX = 3 + numCand;
@@ -229,10 +310,14 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
     auto bail = [&](int code) { cudaFreeAsync(scratch, st); return code; };
 
     const int K0 = 3 + numCand;
-    me_start_gen<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, offR, strideR, s);
+    auto cand_costs = [&](int op, int K)
+    {
+        if (pitch) return launch_lowres_cmp(ctx, op, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K, n, s.candCost, st);
+        return x265b200_subpel_cmp_batch(ctx, op, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K, n, s.candCost, stream);
+    };
+    me_start_gen<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, offR, strideR, pitch, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    if ((rc = x265b200_subpel_cmp_batch(ctx, X265B200_SAD, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K0, n, s.candCost, stream)))
-        return bail(rc);
+    if ((rc = cand_costs(X265B200_SAD, K0))) return bail(rc);
     me_start_select<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, costTab, s, outQMv, outCost);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     if (searchMethod == X265B200_ME_FULL)
@@ -243,14 +328,34 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
     for (int r = 0; r <= R; r++)
     {
         const int mode = (r == 0 ? 1 : 2) | (r < R ? 4 : 8);
-        me_round_kernel<<<G, T, 0, st>>>(n, mode, rounds[r ? r - 1 : 0], rounds[r < R ? r : R - 1], qmvp, range, offR, strideR, costTab, s, outQMv, outCost);
+        me_round_kernel<<<G, T, 0, st>>>(n, mode, rounds[r ? r - 1 : 0], rounds[r < R ? r : R - 1], qmvp, range, offR, strideR, pitch, costTab, s, outQMv, outCost);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
-        if (r < R && (rc = x265b200_subpel_cmp_batch(ctx, ops[r], w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, rounds[r].K, n,
-                                                     s.candCost, stream)))
-            return bail(rc);
+        if (r < R && (rc = cand_costs(ops[r], rounds[r].K))) return bail(rc);
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "motion_estimate launch", e);
     return X265B200_OK;
+}
+
+extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
+                                              const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                              const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                              int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
+                                              int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+{
+    return motion_chain(ctx, 0, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR, offF, offR, range, qmvp, numCand, mvc,
+                        costTab, n, outQMv, outCost, stream);
+}
+
+extern "C" int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
+                                                     const void* fenc, intptr_t strideF, const void* planes, intptr_t strideR, size_t planePitch,
+                                                     const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                                     const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (planePitch == 0 || planePitch > 0x1fffffff || ((strideF | strideR) & 3) || w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3))
+        return fail(ctx, X265B200_ERR_ARG, "lowres_motion_estimate: bad geometry");
+    return motion_chain(ctx, (int)planePitch, searchMethod, w, h, merange, subpelRefine, fenc, strideF, planes, strideR, offF, offR, range, qmvp,
+                        0, nullptr, costTab, n, outQMv, outCost, stream);
 }
