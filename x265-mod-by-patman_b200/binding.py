@@ -13,6 +13,7 @@ HEADER = os.path.join(ROOT, "include", "x265b200.h")
 
 OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP = 0, 1, 2, 3
 TR_DCT, TR_DST, TR_LOWPASS = 0, 1, 2
+ME_DIA, ME_HEX, ME_STAR, ME_FULL = 0, 1, 3, 5       # search methods, numbered as x265.h:511-519
 IP_KINDS = {"hpp": 0, "hps": 1, "vpp": 2, "vps": 3, "vsp": 4, "vss": 5, "hvpp": 6, "p2s": 7}
 
 _lib = None
