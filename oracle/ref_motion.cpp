@@ -9,6 +9,7 @@
 #include "motion.cpp"
 #include "bitcost.cpp"
 #include "yuv.cpp"
+#include <stdlib.h>
 #include <thread>
 #include <vector>
 
@@ -60,6 +61,50 @@ int ref_lowres_motion_estimate(int method, int subme, int w, int h, pixel* fencP
     int cost = me.motionEstimate(&ref, mvmin, mvmax, mvp, 0, NULL, merange, out, 1, false);
     outQMv[0] = out.x; outQMv[1] = out.y;
     return cost;
+}
+
+/* the encoder's call: setSourcePU(const Yuv&, ctuAddr, cuPartIdx, puPartIdx, ..., bChroma) (motion.cpp:222-247), which
+ * turns on the chroma SATD term of subpelCompare from subme 3.  The PU is handed over as the top-left block of a 64x64
+ * CU-sized Yuv; the reference picture is a PicYuv whose CTU / partition offset tables are all zero, so every
+ * get*Addr(ctuAddr = 0, absPartIdx = 0) lands on the co-located blocks given here.  csp: X265_CSP_I420 or I444. */
+extern "C" __attribute__((visibility("default")))
+int ref_motion_estimate_chroma(int method, int subme, int csp, int w, int h, const pixel* fencY, intptr_t sfY, const pixel* fencCb, const pixel* fencCr,
+                               intptr_t sfC, pixel* refY, intptr_t srY, pixel* refCb, pixel* refCr, intptr_t srC, const int32_t* range,
+                               const int32_t* qmvp, int numCand, const int32_t* mvc, int merange, int qp, int32_t* outQMv)
+{
+    static bool scales = false;
+    if (!scales) { ref_ensure(); MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(csp);
+    me.setQP(qp);
+    Yuv src;
+    src.create(64, csp);
+    const int hs = CHROMA_H_SHIFT(csp), vs = CHROMA_V_SHIFT(csp);
+    for (int y = 0; y < h; y++) memcpy(src.m_buf[0] + y * src.m_size, fencY + y * sfY, w * sizeof(pixel));
+    for (int y = 0; y < (h >> vs); y++)
+    {
+        memcpy(src.m_buf[1] + y * src.m_csize, fencCb + y * sfC, (w >> hs) * sizeof(pixel));
+        memcpy(src.m_buf[2] + y * src.m_csize, fencCr + y * sfC, (w >> hs) * sizeof(pixel));
+    }
+    me.setSourcePU(src, 0, 0, 0, w, h, method, subme, true);
+    static intptr_t zeros[4] = { 0, 0, 0, 0 };
+    PicYuv* pic = (PicYuv*)calloc(1, sizeof(PicYuv));          /* plain data: only strides, origins and offset tables are read */
+    pic->m_stride = srY; pic->m_strideC = srC;
+    pic->m_picOrg[0] = refY; pic->m_picOrg[1] = refCb; pic->m_picOrg[2] = refCr;
+    pic->m_cuOffsetY = pic->m_cuOffsetC = pic->m_buOffsetY = pic->m_buOffsetC = zeros;
+    ReferencePlanes ref;
+    ref.reconPic = pic;
+    ref.fpelPlane[0] = refY; ref.fpelPlane[1] = refCb; ref.fpelPlane[2] = refCr;
+    ref.lumaStride = srY; ref.chromaStride = srC;
+    MV mvmin(range[0], range[1]), mvmax(range[2], range[3]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[16];
+    for (int i = 0; i < numCand && i < 16; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mvmin, mvmax, mvp, numCand, cands, merange, out, 1, false);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    int on = me.bChromaSATD ? 1 : 0;
+    src.destroy();
+    free(pic);
+    return on ? cost : -1 - cost;                              /* negative: the chroma term was off for this PU (caller checks) */
 }
 
 /* the lambda-scaled mv cost table BitCost::setQP builds, copied out for the other implementations: [-radius, radius] */

@@ -984,7 +984,28 @@ static const int k_subpel_workload[8][5] = {      /* motion.cpp:48-58: hpel_iter
 static const int k_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };   /* motion.cpp:67 */
 
 typedef struct { int w, h; const pixel* fenc; intptr_t sf; const pixel* fref; intptr_t sr; const uint16_t* cx; const uint16_t* cy;
-                 const pixel* hpel[4]; /* lowres: the four half-pel planes at the co-located block, else NULL */ } me_ctx;
+                 const pixel* hpel[4]; /* lowres: the four half-pel planes at the co-located block, else NULL */
+                 /* chroma residual term of subpelCompare (bChromaSATD): co-located chroma blocks, or chroma == 0 */
+                 int chroma, hshift, vshift; const pixel* fencC[2]; intptr_t sfc; const pixel* frefC[2]; intptr_t src; } me_ctx;
+/* chroma part of subpelCompare (motion.cpp:1805-1865): the vector in 1/8 chroma samples, 4-tap filters, always SATD */
+static int me_chroma_cost(const me_ctx* c, int qx, int qy)
+{
+    const int mvx = (int32_t)((uint32_t)qx << (1 - c->hshift)), mvy = (int32_t)((uint32_t)qy << (1 - c->vshift));
+    const intptr_t off = (mvx >> 3) + (intptr_t)(mvy >> 3) * c->src;
+    const int xFrac = mvx & 7, yFrac = mvy & 7, cw = c->w >> c->hshift, ch = c->h >> c->vshift;
+    int cost = 0;
+    for (int k = 0; k < 2; k++)
+    {
+        const pixel* r = c->frefC[k] + off;
+        if (!(xFrac | yFrac)) { cost += orc_satd(cw, ch, c->fencC[k], c->sfc, r, c->src); continue; }
+        pixel buf[64 * 64];
+        if (!yFrac) orc_interp_hpp(4, cw, ch, r, c->src, buf, cw, xFrac);
+        else if (!xFrac) orc_interp_vpp(4, cw, ch, r, c->src, buf, cw, yFrac);
+        else orc_interp_hvpp(4, cw, ch, r, c->src, buf, cw, xFrac, yFrac);
+        cost += orc_satd(cw, ch, c->fencC[k], c->sfc, buf, cw);
+    }
+    return cost;
+}
 /* ReferencePlanes::lowresQPelCost (common/lowres.h:95-119): a quarter-pel position of a lowres reference is the rounded
  * average of the two nearest half-pel planes (pixelavg_pp, pixel.cpp:586-594), a half / full-pel one is a plane itself */
 static int me_lowres_cost(const me_ctx* c, int qx, int qy, int op)
@@ -1005,7 +1026,8 @@ static int me_lowres_cost(const me_ctx* c, int qx, int qy, int op)
 static int me_subpel(const me_ctx* c, int qx, int qy, int op)   /* subpelCompare, motion.cpp:1775-1803 */
 {
     if (c->hpel[0]) return me_lowres_cost(c, qx, qy, op);
-    return orc_subpel_cmp(op, c->w, c->h, c->fenc, c->sf, c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->sr, c->sr, qx & 3, qy & 3);
+    int cost = orc_subpel_cmp(op, c->w, c->h, c->fenc, c->sf, c->fref + (qx >> 2) + (intptr_t)(qy >> 2) * c->sr, c->sr, qx & 3, qy & 3);
+    return c->chroma ? cost + me_chroma_cost(c, qx, qy) : cost;
 }
 static int me_mvcost(const me_ctx* c, int qx, int qy) { return (uint16_t)(c->cx[qx] + c->cy[qy]); }   /* bitcost.h:56 */
 static int clip3i(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
@@ -1333,7 +1355,20 @@ EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h,
                                const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
                                const uint16_t* costTab, int32_t* outQMv)
 {
-    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 } };
+    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 }, 0, 0, 0, { 0, 0 }, 0, { 0, 0 }, 0 };
+    return me_estimate(c, method, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
+}
+/* the encoder's call (setSourcePU of motion.cpp:222-247 with bChroma): from subme 3 on every subpelCompare also charges the
+ * SATD of both chroma blocks, when the chroma block is a multiple of 4x4 (non-NULL chroma satd slot, pixel.cpp:1217-1243).
+ * fencC / frefC: co-located Cb and Cr blocks; hshift / vshift: 1,1 for 4:2:0, 0,0 for 4:4:4. */
+EXPORT int orc_motion_estimate_chroma(int method, int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                                      const pixel* fencCb, const pixel* fencCr, intptr_t sfc, const pixel* frefCb, const pixel* frefCr, intptr_t src,
+                                      int hshift, int vshift, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                                      const uint16_t* costTab, int32_t* outQMv)
+{
+    const int on = subme > 2 && !((w >> hshift) & 3) && !((h >> vshift) & 3);
+    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 },
+                 on, hshift, vshift, { fencCb, fencCr }, sfc, { frefCb, frefCr }, src };
     return me_estimate(c, method, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
 }
 /* the lookahead's call (encoder/slicetype.cpp:4484-4566): lowres reference = four half-pel planes `pitch` samples apart
@@ -1343,6 +1378,6 @@ EXPORT int orc_lowres_motion_estimate(int method, int merange, int subme, int w,
                                       const uint16_t* costTab, int32_t* outQMv)
 {
     me_ctx c = { w, h, fenc, sf, refBlock, sr, costTab - qmvp[0], costTab - qmvp[1],
-                 { refBlock, refBlock + pitch, refBlock + 2 * pitch, refBlock + 3 * pitch } };
+                 { refBlock, refBlock + pitch, refBlock + 2 * pitch, refBlock + 3 * pitch }, 0, 0, 0, { 0, 0 }, 0, { 0, 0 }, 0 };
     return me_estimate(c, method, merange, subme, range, qmvp, 0, 0, costTab, outQMv);
 }

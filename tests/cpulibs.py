@@ -197,6 +197,17 @@ class _Base:
                                             len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    def motion_estimate_chroma(self, method, merange, subme, w, h, fY, ofY, sfY, rY, orY, srY, fCb, fCr, ofC, sfC, rCb, rCr, orC, srC,
+                               hshift, vshift, rng, qmvp, mvc, cost_tab, centre):
+        """oracle: motionEstimate with the chroma SATD term of subme > 2 (co-located luma / Cb / Cr blocks at the given offsets)"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self._f("motion_estimate_chroma")(method, merange, subme, w, h, _ptr(fY, ofY), C.c_ssize_t(sfY), _ptr(rY, orY), C.c_ssize_t(srY),
+                                              _ptr(fCb, ofC), _ptr(fCr, ofC), C.c_ssize_t(sfC), _ptr(rCb, orC), _ptr(rCr, orC), C.c_ssize_t(srC),
+                                              hshift, vshift, _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
+
     def lowres_motion_estimate(self, method, merange, subme, w, h, fenc, of, sf, planes, orf, sr, pitch, rng, qmvp, cost_tab, centre):
         """oracle: the lookahead's motionEstimate on a lowres reference (four half-pel planes `pitch` apart)"""
         out = np.zeros(2, np.int32)
@@ -355,6 +366,19 @@ class Reference(_Base):
         c = self.lib.ref_lowres_motion_estimate(method, subme, w, h, _ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(planes), C.c_ssize_t(sr),
                                                 C.c_size_t(pitch), C.c_ssize_t(orf), _ptr(rng), _ptr(qmvp), merange, qp, _ptr(out))
         return int(out[0]), int(out[1]), int(c)
+
+    def motion_estimate_chroma_ref(self, method, subme, csp, w, h, fY, ofY, sfY, rY, orY, srY, fCb, fCr, ofC, sfC, rCb, rCr, orC, srC,
+                                   rng, qmvp, mvc, merange, qp):
+        """the reference's motionEstimate through the encoder-style setSourcePU (chroma SATD from subme 3);
+        returns (qmv_x, qmv_y, cost, chroma_term_was_on)"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self.lib.ref_motion_estimate_chroma(method, subme, csp, w, h, _ptr(fY, ofY), C.c_ssize_t(sfY), _ptr(fCb, ofC), _ptr(fCr, ofC),
+                                                C.c_ssize_t(sfC), _ptr(rY, orY), C.c_ssize_t(srY), _ptr(rCb, orC), _ptr(rCr, orC), C.c_ssize_t(srC),
+                                                _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), merange, qp, _ptr(out))
+        on = c >= 0
+        return int(out[0]), int(out[1]), int(c if on else -1 - c), bool(on)
 
     def mvcost_table(self, qp, radius):
         out = np.zeros(2 * radius + 1, np.uint16)

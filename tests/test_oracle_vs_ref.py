@@ -625,3 +625,60 @@ def test_lowres_motion_estimate(libs):
         assert a == b, (case, method, subme, a, b)
         sub += (a[0] | a[1]) & 1
     assert sub > 40                                       # quarter-pel winners: the two-plane average decided them
+
+
+def yuv420_planes(geo, depth, seed, shift=(0, 0)):
+    """luma plane over `geo` plus Cb / Cr planes over the half-size geometry (same relative margins), all displaced by
+    `shift` luma samples (even) so that a displaced copy matches in all three planes"""
+    from frames import Geometry, smooth_field
+    cgeo = Geometry(geo.width // 2, geo.height // 2, geo.ctu // 2)
+    Y = np.roll(smooth_field(geo, depth, seed, box=9), shift[1] * geo.stride + shift[0])
+    Cb = np.roll(smooth_field(cgeo, depth, seed + 1, box=5), (shift[1] // 2) * cgeo.stride + shift[0] // 2)
+    Cr = np.roll(smooth_field(cgeo, depth, seed + 2, box=5), (shift[1] // 2) * cgeo.stride + shift[0] // 2)
+    return cgeo, Y, Cb, Cr
+
+
+def test_motion_estimate_chroma(libs):
+    """from subme 3 the encoder's motionEstimate charges chroma SATD in every sub-pel cost: oracle vs the reference driven
+    through the encoder-style setSourcePU (Yuv source, PicYuv reference), 4:2:0, incl. PU shapes whose chroma block has
+    no SATD slot (term off) and subme <= 2 (term off)"""
+    o, r = libs
+    from frames import Geometry
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(73)
+    cgeo, FY, FCb, FCr = yuv420_planes(geo, o.depth, 101)
+    refs = [yuv420_planes(geo, o.depth, 101, shift=(6, -4))[1:], yuv420_planes(geo, o.depth, 201)[1:]]
+    for k in range(2):      # sensor noise so that costs are not all zero at the match
+        refs[k] = tuple(np.clip(p.astype(np.int64) + rng.integers(-3, 4, p.size), 0, o.pmax).astype(p.dtype) for p in refs[k])
+    RAD = 2048
+    cw, ch = geo.coded()
+    on_count = 0; chroma_decided = 0
+    for case in range(200):
+        w, h = [(16, 16), (8, 8), (32, 32), (16, 8), (64, 64), (8, 16), (32, 24), (16, 12), (12, 16), (16, 4), (64, 32), (24, 32)][case % 12]
+        subme = (3, 4, 5, 7, 6, 2, 3, 5)[case % 8]
+        method = (1, 3, 0, 5, 1)[case % 5]
+        qp = int(rng.integers(10, 45))
+        tab = r.mvcost_table(qp, RAD)
+        RY, RCb, RCr = refs[case % 3 == 2]
+        x = int(rng.integers(0, (cw - w) // 2 + 1)) * 2; y = int(rng.integers(0, (ch - h) // 2 + 1)) * 2
+        ofY = geo.origin + y * geo.stride + x
+        ofC = cgeo.origin + (y // 2) * cgeo.stride + x // 2
+        m = int(rng.integers(2, 14))
+        minx = -min(m, x + geo.margin_x - 16); maxx = min(m, cw + geo.margin_x - 16 - w - x)
+        miny = -min(m, y + geo.margin_y - 16); maxy = min(m, ch + geo.margin_y - 16 - h - y)
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, 2)
+        if case % 7 == 0: qmvp[:] = 0
+        mvc = rng.integers(-4 * m - 6, 4 * m + 7, (int(rng.integers(0, 4)), 2))
+        merange = m if method == 5 else int(rng.integers(1, 33))
+        a = o.motion_estimate_chroma(method, merange, subme, w, h, FY, ofY, geo.stride, RY, ofY, geo.stride, FCb, FCr, ofC, cgeo.stride,
+                                     RCb, RCr, ofC, cgeo.stride, 1, 1, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD)
+        b = r.motion_estimate_chroma_ref(method, subme, 1, w, h, FY, ofY, geo.stride, RY, ofY, geo.stride, FCb, FCr, ofC, cgeo.stride,
+                                         RCb, RCr, ofC, cgeo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+        assert a == b[:3], (case, method, w, h, subme, a, b)
+        assert b[3] == (subme > 2 and (w // 2) % 4 == 0 and (h // 2) % 4 == 0), (w, h, subme)
+        on_count += b[3]
+        if b[3]:
+            luma_only = o.motion_estimate_full(subme, w, h, FY, ofY, geo.stride, RY, ofY, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD,
+                                               method, merange)
+            chroma_decided += luma_only[:2] != a[:2]
+    assert on_count > 100 and chroma_decided > 5          # the chroma term changed winners, not only costs
