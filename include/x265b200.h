@@ -245,6 +245,29 @@ int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, i
                                           const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                                           const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
 
+/* Chroma term of MotionEstimate::subpelCompare (reference encoder/motion.cpp:1805-1865): SATD of the 4-tap interpolated chroma
+ * block against the chroma fenc block, fused like x265b200_subpel_cmp_batch.  w x h is the CHROMA block; frac[i] =
+ * xFrac | yFrac << 4 in eighths (0..7 each), a negative frac[i] contributes nothing; accumulate != 0 adds onto cost[i]
+ * (call it for Cb and Cr after the luma entry), else cost[i] is overwritten. */
+int x265b200_subpel_cmp_chroma_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                     const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
+                                     int accumulate, x265b200_stream stream);
+
+/* x265b200_motion_estimate_batch as the encoder proper runs it (setSourcePU of motion.cpp:222-247 with bChroma): from
+ * subpelRefine 3 on, every sub-pel cost -- the predictor candidates, the refinement rounds, the zero vector's last chance
+ * -- also charges the SATD of the Cb and Cr blocks at the vector scaled to chroma (bChromaSATD), provided the chroma block
+ * is a multiple of 4x4 (the reference's non-NULL chroma satd slots); otherwise, and below subme 3, the result equals the
+ * luma-only entry.  offFC / offRC: the PU's co-located block in the Cb / Cr planes (both planes share strides and offsets);
+ * hshift, vshift = 1, 1 (4:2:0) or 0, 0 (4:4:4).  w x h is the luma PU. */
+int x265b200_motion_estimate_chroma_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
+                                          const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                          const int32_t* offF, const int32_t* offR,
+                                          const void* fencCb, const void* fencCr, intptr_t strideFC,
+                                          const void* refCb, const void* refCr, intptr_t strideRC,
+                                          const int32_t* offFC, const int32_t* offRC, int hshift, int vshift,
+                                          const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                                          const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

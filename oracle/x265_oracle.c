@@ -1358,6 +1358,16 @@ EXPORT int orc_motion_estimate(int method, int merange, int subme, int w, int h,
     me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 }, 0, 0, 0, { 0, 0 }, 0, { 0, 0 }, 0 };
     return me_estimate(c, method, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
 }
+/* one chroma block of that term, for the kernel test: SATD(fenc, 4-tap interpolation of fref at xFrac, yFrac eighths) */
+EXPORT int orc_subpel_cmp_chroma(int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr, int xFrac, int yFrac)
+{
+    if (!(xFrac | yFrac)) return orc_satd(w, h, fenc, sf, fref, sr);
+    pixel buf[64 * 64];
+    if (!yFrac) orc_interp_hpp(4, w, h, fref, sr, buf, w, xFrac);
+    else if (!xFrac) orc_interp_vpp(4, w, h, fref, sr, buf, w, yFrac);
+    else orc_interp_hvpp(4, w, h, fref, sr, buf, w, xFrac, yFrac);
+    return orc_satd(w, h, fenc, sf, buf, w);
+}
 /* the encoder's call (setSourcePU of motion.cpp:222-247 with bChroma): from subme 3 on every subpelCompare also charges the
  * SATD of both chroma blocks, when the chroma block is a multiple of 4x4 (non-NULL chroma satd slot, pixel.cpp:1217-1243).
  * fencC / frefC: co-located Cb and Cr blocks; hshift / vshift: 1,1 for 4:2:0, 0,0 for 4:4:4. */

@@ -208,6 +208,9 @@ class _Base:
                                               hshift, vshift, _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    def subpel_cmp_chroma(self, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
+        return self._f("subpel_cmp_chroma")(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
+
     def lowres_motion_estimate(self, method, merange, subme, w, h, fenc, of, sf, planes, orf, sr, pitch, rng, qmvp, cost_tab, centre):
         """oracle: the lookahead's motionEstimate on a lowres reference (four half-pel planes `pitch` apart)"""
         out = np.zeros(2, np.int32)

@@ -622,3 +622,95 @@ def test_lowres_motion_estimate_batch(depth):
         sub += int(((want_mv[:, 0] | want_mv[:, 1]) & 1).sum())
     assert sub > 100                                      # quarter-pel winners: the two-plane average decided them
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_subpel_cmp_chroma_batch(depth):
+    """chroma term of subpelCompare: fused 4-tap interpolation + SATD vs the oracle for every chroma block shape with a SATD
+    slot, all 64 fractions, overwrite and accumulate modes, skipped candidates (negative frac)"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    F = make_plane(geo, depth, 91, "natural"); R = make_plane(geo, depth, 92, "natural"); Ru = make_plane(geo, depth, 93, "uniform")
+    rng = np.random.default_rng(700 + depth)
+    cw, ch = geo.coded()
+    dF = dev(pix_view(F, depth))
+    shapes = [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 8), (16, 8), (8, 16), (32, 16), (16, 32), (16, 12), (12, 16), (16, 4), (4, 16),
+              (32, 24), (24, 32), (32, 8), (8, 32)]
+    for (w, h) in shapes:
+        n, K = 23, 5
+        x = rng.integers(0, cw - w, n); y = rng.integers(0, ch - h, n)
+        offF = (geo.origin + y * geo.stride + x).astype(np.int32)
+        mvx = rng.integers(-30, 31, n * K); mvy = rng.integers(-30, 31, n * K)
+        offR = (geo.origin + (np.repeat(y, K) + mvy) * geo.stride + np.repeat(x, K) + mvx).astype(np.int32)
+        frac = (rng.integers(0, 8, n * K) | (rng.integers(0, 8, n * K) << 4)).astype(np.int32)
+        frac[:10] = [0, 1, 7, 0x10, 0x70, 0x77, 0x34, 4, 0x40, 0x44]
+        skip = rng.random(n * K) < 0.15
+        for ref_plane in (R, Ru):
+            want = np.array([orc.subpel_cmp_chroma(w, h, F, int(offF[i // K]), geo.stride, ref_plane, int(offR[i]), geo.stride,
+                                                   int(frac[i] & 7), int(frac[i] >> 4)) for i in range(n * K)], np.int32)
+            dR = dev(pix_view(ref_plane, depth))
+            cost = torch.full((n * K,), -5, dtype=torch.int32, device="cuda")
+            ctx.subpel_cmp_chroma_batch(w, h, dF, geo.stride, dR, geo.stride, dev(offF), dev(offR), dev(frac), K, cost)
+            assert np.array_equal(cost.cpu().numpy(), want), (w, h)
+            base = rng.integers(0, 1000, n * K).astype(np.int32)
+            cost = dev(base.copy())
+            ctx.subpel_cmp_chroma_batch(w, h, dF, geo.stride, dR, geo.stride, dev(offF), dev(offR), dev(np.where(skip, -1, frac).astype(np.int32)), K,
+                                        cost, accumulate=1)
+            assert np.array_equal(cost.cpu().numpy(), base + np.where(skip, 0, want)), (w, h, "accumulate")
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_chroma_batch(depth):
+    """motionEstimate with the chroma SATD term (subme > 2, 4:2:0) for batches of PUs vs the oracle (pinned to the reference's
+    encoder-style setSourcePU path by the CPU suite), incl. shapes / subme levels where the term is off"""
+    import torch
+    from gpulib import context
+    from frames import Geometry
+    from test_oracle_vs_ref import mv_cost_table, yuv420_planes
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    rng = np.random.default_rng(800 + depth)
+    cgeo, FY, FCb, FCr = yuv420_planes(geo, depth, 111)
+    refs = [yuv420_planes(geo, depth, 111, shift=(6, -4))[1:], yuv420_planes(geo, depth, 211)[1:]]
+    refs = [tuple(np.clip(p.astype(np.int64) + rng.integers(-3, 4, p.size), 0, orc.pmax).astype(p.dtype) for p in r3) for r3 in refs]
+    cw, ch = geo.coded()
+    RAD = 2048
+    tab = mv_cost_table(10.0794, RAD); dtab = dev(tab.view(np.int16))
+    dFY, dFCb, dFCr = (dev(pix_view(p, depth)) for p in (FY, FCb, FCr))
+    cases = [((16, 16), 3, 1), ((8, 8), 5, 3), ((32, 32), 4, 1), ((64, 64), 7, 5), ((16, 8), 3, 0), ((32, 24), 6, 3), ((16, 12), 3, 1),
+             ((12, 16), 4, 1), ((8, 16), 2, 1), ((24, 32), 5, 3), ((64, 32), 3, 1), ((16, 4), 3, 1)]
+    decided = 0
+    for ci, ((w, h), subme, method) in enumerate(cases):
+        RY, RCb, RCr = refs[ci % 3 == 2]
+        n, nc = 30, ci % 3
+        x = rng.integers(0, (cw - w) // 2 + 1, n) * 2; y = rng.integers(0, (ch - h) // 2 + 1, n) * 2
+        offY = (geo.origin + y * geo.stride + x).astype(np.int32)
+        offC = (cgeo.origin + (y // 2) * cgeo.stride + x // 2).astype(np.int32)
+        m = int(rng.integers(3, 14))
+        minx = -np.minimum(m, x + geo.margin_x - 16); maxx = np.minimum(m, cw + geo.margin_x - 16 - w - x)
+        miny = -np.minimum(m, y + geo.margin_y - 16); maxy = np.minimum(m, ch + geo.margin_y - 16 - h - y)
+        rngs = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        qmvp = rng.integers(-4 * m - 6, 4 * m + 7, (n, 2)).astype(np.int32); qmvp[::7] = 0
+        mvc = rng.integers(-4 * m - 6, 4 * m + 7, (n, max(nc, 1), 2)).astype(np.int32)
+        merange = m if method == 5 else int(rng.integers(1, 33))
+        want = np.array([orc.motion_estimate_chroma(method, merange, subme, w, h, FY, int(offY[i]), geo.stride, RY, int(offY[i]), geo.stride,
+                                                    FCb, FCr, int(offC[i]), cgeo.stride, RCb, RCr, int(offC[i]), cgeo.stride, 1, 1,
+                                                    rngs[i], qmvp[i], mvc[i, :nc], tab, RAD) for i in range(n)], np.int32)
+        luma = np.array([orc.motion_estimate_full(subme, w, h, FY, int(offY[i]), geo.stride, RY, int(offY[i]), geo.stride, rngs[i], qmvp[i],
+                                                  mvc[i, :nc], tab, RAD, method, merange) for i in range(n)], np.int32)
+        gmv = torch.full((n, 2), -7777, dtype=torch.int32, device="cuda"); gc = torch.full((n,), -7777, dtype=torch.int32, device="cuda")
+        ctx.motion_estimate_chroma_batch(method, w, h, merange, subme, dFY, geo.stride, dev(pix_view(RY, depth)), geo.stride, dev(offY), dev(offY),
+                                         dFCb, dFCr, cgeo.stride, dev(pix_view(RCb, depth)), dev(pix_view(RCr, depth)), cgeo.stride,
+                                         dev(offC), dev(offC), 1, 1, dev(rngs), dev(qmvp), nc,
+                                         dev(np.ascontiguousarray(mvc[:, :nc])) if nc else None, dtab.data_ptr() + 2 * RAD, gmv, gc)
+        assert np.array_equal(gc.cpu().numpy(), want[:, 2]), (w, h, subme, method)
+        assert np.array_equal(gmv.cpu().numpy(), want[:, :2]), (w, h, subme, method)
+        on = subme > 2 and (w // 2) % 4 == 0 and (h // 2) % 4 == 0
+        if not on: assert np.array_equal(want, luma)
+        else: decided += int((want[:, :2] != luma[:, :2]).any(1).sum())
+    assert decided > 5                                    # the chroma term moved vectors, not only costs
+    ctx.check()

@@ -164,6 +164,17 @@ class Context:
                    C.c_size_t(int(plane_pitch)), _dp(offF), _dp(offR), _dp(rng), _dp(qmvp), C.c_void_p(int(cost_tab_centre)), int(offF.numel()),
                    _dp(out_qmv), _dp(out_cost), C.c_void_p(stream))
 
+    def motion_estimate_chroma_batch(self, method, w, h, merange, subme, fenc, sf, ref, sr, offF, offR, fcb, fcr, sfc, rcb, rcr, src, offFC, offRC,
+                                     hshift, vshift, rng, qmvp, num_cand, mvc, cost_tab_centre, out_qmv, out_cost, stream=0):
+        self._call("x265b200_motion_estimate_chroma_batch", int(method), w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr),
+                   _dp(offF), _dp(offR), _dp(fcb), _dp(fcr), _ss(sfc), _dp(rcb), _dp(rcr), _ss(src), _dp(offFC), _dp(offRC), int(hshift), int(vshift),
+                   _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(out_qmv), _dp(out_cost),
+                   C.c_void_p(stream))
+
+    def subpel_cmp_chroma_batch(self, w, h, fenc, sf, ref, sr, offF, offR, frac, K, cost, accumulate=0, stream=0):
+        self._call("x265b200_subpel_cmp_chroma_batch", w, h, _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(frac), int(K),
+                   int(offF.numel()), _dp(cost), int(accumulate), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

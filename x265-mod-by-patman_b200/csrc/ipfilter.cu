@@ -414,18 +414,21 @@ hv_tile_kernel(const PIX* __restrict__ src, intptr_t ss, const int32_t* __restri
 // tile: the interpolated block never exists in memory.  A zero fraction runs through the identity taps {0,0,0,64,0,0,0,0}:
 // for pixel inputs hps(0) == p2s and the two-pass result equals luma_vpp / luma_hpp / a plain copy bit for bit (the
 // rounding offsets cancel), so one code path serves all sixteen (xFrac, yFrac) pairs.
-template<typename PIX, int OP, int TW1, int TH2>
+// TAPS = 4: the chroma term of subpelCompare (motion.cpp:1805-1865), fractions in eighths (xFrac | yFrac << 4, 0..7 each);
+// a negative frac marks a candidate the reference costs without its chroma term, and `accumulate` adds onto the luma cost.
+template<typename PIX, int OP, int TW1, int TH2, int TAPS = 8>
 __global__ void __launch_bounds__(128)
 subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restrict__ ref, intptr_t ss,
                   const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ frac,
-                  int K, int n, int w, int h, int G, int shift1, int offset1, int shift2, int offset2, int maxVal, int32_t* __restrict__ cost)
+                  int K, int n, int w, int h, int G, int shift1, int offset1, int shift2, int offset2, int maxVal, int32_t* __restrict__ cost,
+                  int accumulate = 0)
 {
-    constexpr int TAPS = 8;
     extern __shared__ __align__(16) int16_t immed_all[];
     int lg = __ffs(G) - 1;
     int grp = threadIdx.x >> lg, l = threadIdx.x & (G - 1);
     int cand = blockIdx.x * (128 >> lg) + grp;
-    bool live = cand < n;
+    const bool exists = cand < n;
+    bool live = exists && frac[cand] >= 0;
     int rows = h + TAPS - 1;
     int16_t* immed = immed_all + (size_t)grp * w * rows;
     constexpr int NQ = (TW1 + TAPS - 1 + 3) / 4;
@@ -433,9 +436,9 @@ subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restri
     if (live)
     {
         int ci = frac[cand];
-        int idxX = ci & 3, idxY = (ci >> 4) & 3;
-        tx0 = c_lumaTapsB[idxX][0]; tx1 = c_lumaTapsB[idxX][1];
-        ty0 = c_lumaTapsB[idxY][0]; ty1 = c_lumaTapsB[idxY][1];
+        int idxX = ci & 15, idxY = (ci >> 4) & 15;
+        tx0 = TAPS == 8 ? c_lumaTapsB[idxX & 3][0] : c_chromaTapsB[idxX & 7]; tx1 = TAPS == 8 ? c_lumaTapsB[idxX & 3][1] : 0;
+        ty0 = TAPS == 8 ? c_lumaTapsB[idxY & 3][0] : c_chromaTapsB[idxY & 7]; ty1 = TAPS == 8 ? c_lumaTapsB[idxY & 3][1] : 0;
         const PIX* s = ref + offR[cand] - (TAPS / 2 - 1) * ss - (TAPS / 2 - 1);
         int tw = w / TW1;
         int tiles1 = tw * ((rows + 3) >> 2);
@@ -519,7 +522,11 @@ subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restri
         }
     }
     acc = group_sum(acc, G);
-    if (live && l == 0) cost[cand] = acc;
+    if (exists && l == 0)
+    {
+        if (!accumulate) cost[cand] = acc;
+        else if (live) cost[cand] += acc;
+    }
 }
 
 // p2s, 4 samples per thread
@@ -700,9 +707,8 @@ extern "C" int x265b200_interp_batch(x265b200_ctx* ctx, int kind, int taps, int 
                      : launch_interp<uint16_t, 4>(ctx, kind, w, h, src, ss, offSrc, dst, ds, offDst, coeffIdx, n, st);
 }
 
-extern "C" int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h, const void* fenc, intptr_t sf, const void* ref, intptr_t sr,
-                                         const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
-                                         x265b200_stream stream)
+static int subpel_cmp_launch(x265b200_ctx* ctx, int taps, int accumulate, int op, int w, int h, const void* fenc, intptr_t sf, const void* ref, intptr_t sr,
+                             const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost, x265b200_stream stream)
 {
     if (!ctx) return X265B200_ERR_ARG;
     if (w < 4 || h < 4 || (w & 3) || (h & 3) || w > 64 || h > 64 || n < 0 || K < 1 || (op != X265B200_SAD && op != X265B200_SATD))
@@ -713,7 +719,7 @@ extern "C" int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h
     const int headRoom = 14 - ctx->depth, maxVal = (1 << ctx->depth) - 1;
     const int shift1 = 6 - headRoom, shift2 = 6 + headRoom;
     const int offset1 = (int)((unsigned)-8192 << shift1), offset2 = (1 << (shift2 - 1)) + (8192 << 6);
-    const size_t smem = (size_t)w * (h + 7) * sizeof(int16_t);
+    const size_t smem = (size_t)w * (h + taps - 1) * sizeof(int16_t);
     const bool wide = !(w & 7), tall = !(h & 7);
     int tiles2 = (w >> 2) * (tall ? h >> 3 : h >> 2);
     int G = 1;
@@ -721,13 +727,32 @@ extern "C" int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h
     int perCta = 128 / G;
     long long cands = (long long)n * K;
     if (cands > 0x7fffffff) return fail(ctx, X265B200_ERR_ARG, "subpel_cmp: too many candidates");
-#define SP(PIX, OP_, TW1_, TH2_) subpel_cmp_kernel<PIX, OP_, TW1_, TH2_><<<ceil_div(cands, perCta), 128, perCta * smem, st>>>(            \
-        (const PIX*)fenc, sf, (const PIX*)ref, sr, offF, offR, frac, K, (int)cands, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost)
-#define SP_SHAPE(PIX, OP_) do { if (wide && tall) SP(PIX, OP_, 8, 8); else if (wide) SP(PIX, OP_, 8, 4); else if (tall) SP(PIX, OP_, 4, 8); else SP(PIX, OP_, 4, 4); } while (0)
-    if (ctx->pixbytes == 1) { if (op == X265B200_SAD) SP_SHAPE(uint8_t, OP_SAD); else SP_SHAPE(uint8_t, OP_SATD); }
-    else { if (op == X265B200_SAD) SP_SHAPE(uint16_t, OP_SAD); else SP_SHAPE(uint16_t, OP_SATD); }
+#define SP(PIX, OP_, TW1_, TH2_, TAPS_) subpel_cmp_kernel<PIX, OP_, TW1_, TH2_, TAPS_><<<ceil_div(cands, perCta), 128, perCta * smem, st>>>(  \
+        (const PIX*)fenc, sf, (const PIX*)ref, sr, offF, offR, frac, K, (int)cands, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost, accumulate)
+#define SP_SHAPE(PIX, OP_, TAPS_) do { if (wide && tall) SP(PIX, OP_, 8, 8, TAPS_); else if (wide) SP(PIX, OP_, 8, 4, TAPS_); \
+                                       else if (tall) SP(PIX, OP_, 4, 8, TAPS_); else SP(PIX, OP_, 4, 4, TAPS_); } while (0)
+    if (taps == 4)
+    {   // chroma term: always SATD
+        if (ctx->pixbytes == 1) SP_SHAPE(uint8_t, OP_SATD, 4); else SP_SHAPE(uint16_t, OP_SATD, 4);
+    }
+    else if (ctx->pixbytes == 1) { if (op == X265B200_SAD) SP_SHAPE(uint8_t, OP_SAD, 8); else SP_SHAPE(uint8_t, OP_SATD, 8); }
+    else { if (op == X265B200_SAD) SP_SHAPE(uint16_t, OP_SAD, 8); else SP_SHAPE(uint16_t, OP_SATD, 8); }
 #undef SP_SHAPE
 #undef SP
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
+}
+
+extern "C" int x265b200_subpel_cmp_batch(x265b200_ctx* ctx, int op, int w, int h, const void* fenc, intptr_t sf, const void* ref, intptr_t sr,
+                                         const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
+                                         x265b200_stream stream)
+{
+    return subpel_cmp_launch(ctx, 8, 0, op, w, h, fenc, sf, ref, sr, offF, offR, frac, K, n, cost, stream);
+}
+
+extern "C" int x265b200_subpel_cmp_chroma_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t sf, const void* ref, intptr_t sr,
+                                                const int32_t* offF, const int32_t* offR, const int32_t* frac, int K, int n, int32_t* cost,
+                                                int accumulate, x265b200_stream stream)
+{
+    return subpel_cmp_launch(ctx, 4, accumulate ? 1 : 0, X265B200_SATD, w, h, fenc, sf, ref, sr, offF, offR, frac, K, n, cost, stream);
 }

@@ -37,7 +37,12 @@ struct MeState
     int32_t* candOff;   // n * KMAX
     int32_t* candFrac;  // n * KMAX
     int32_t* candCost;  // n * KMAX
+    int32_t* candOffC;  // n * KMAX  chroma block of the candidate (chroma term on)
+    int32_t* candFracC; // n * KMAX  xFrac | yFrac << 4 in eighths, -1 = costed without the chroma term
 };
+
+// chroma residual term of subpelCompare (bChromaSATD, motion.cpp:1805-1865); on == 0: luma only
+struct MeChroma { int on, hshift, vshift; intptr_t strideRC; const int32_t* offRC; };
 
 __device__ __forceinline__ int clip3(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
 __device__ __forceinline__ int mvcost(const uint16_t* tab, int mvpx, int mvpy, int qx, int qy)
@@ -47,8 +52,15 @@ __device__ __forceinline__ int mvcost(const uint16_t* tab, int mvpx, int mvpy, i
 // pitch == 0: full-resolution reference, candidate = (integer offset, xFrac | yFrac << 4) for the interpolating kernel.
 // pitch > 0: lowres reference of four half-pel planes `pitch` samples apart; candidate = the two plane blocks whose
 // rounded average is the prediction (ReferencePlanes::lowresQPelCost, lowres.h:95-119), equal for half / full-pel vectors.
-__device__ __forceinline__ void put_cand(const MeState& s, size_t slot, int base, intptr_t strideR, int pitch, int qx, int qy)
+__device__ __forceinline__ void put_cand(const MeState& s, size_t slot, int base, intptr_t strideR, int pitch, int qx, int qy,
+                                         const MeChroma& c = MeChroma{ 0, 0, 0, 0, nullptr }, int baseC = 0, bool chromaTerm = true)
 {
+    if (c.on)
+    {
+        const int mvx = (int)((unsigned)qx << (1 - c.hshift)), mvy = (int)((unsigned)qy << (1 - c.vshift));
+        s.candOffC[slot] = chromaTerm ? baseC + (mvx >> 3) + (mvy >> 3) * (int)c.strideRC : baseC;
+        s.candFracC[slot] = chromaTerm ? (mvx & 7) | ((mvy & 7) << 4) : -1;
+    }
     if (!pitch)
     {
         s.candOff[slot] = base + (qx >> 2) + (qy >> 2) * (int)strideR;      // subpelCompare, motion.cpp:1777-1781
@@ -121,20 +133,22 @@ static int launch_lowres_cmp(x265b200_ctx* ctx, int op, int w, int h, const void
 }
 
 __global__ void me_start_gen(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
-                             const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, int pitch, MeState s)
+                             const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, int pitch, MeState s, MeChroma c)
 {
     int pu = blockIdx.x * blockDim.x + threadIdx.x;
     if (pu >= n) return;
+    const int baseC = c.on ? c.offRC[pu] : 0;
     const int qminx = range[4 * pu] * 4, qminy = range[4 * pu + 1] * 4, qmaxx = range[4 * pu + 2] * 4, qmaxy = range[4 * pu + 3] * 4;
     const int px = clip3(qminx, qmaxx, qmvp[2 * pu]), py = clip3(qminy, qmaxy, qmvp[2 * pu + 1]);
     s.pmv[2 * pu] = px; s.pmv[2 * pu + 1] = py;
     const int base = offR[pu];
     const size_t o = (size_t)pu * K;
-    put_cand(s, o, base, strideR, pitch, px, py);
-    put_cand(s, o + 1, base, strideR, pitch, ((px + 2) >> 2) * 4, ((py + 2) >> 2) * 4);
-    put_cand(s, o + 2, base, strideR, pitch, 0, 0);
+    put_cand(s, o, base, strideR, pitch, px, py, c, baseC, true);
+    put_cand(s, o + 1, base, strideR, pitch, ((px + 2) >> 2) * 4, ((py + 2) >> 2) * 4, c, baseC, false);    // plain sad()
+    put_cand(s, o + 2, base, strideR, pitch, 0, 0, c, baseC, false);                                          // plain sad()
     for (int i = 0; i < nc; i++)
-        put_cand(s, o + 3 + i, base, strideR, pitch, clip3(qminx, qmaxx, mvc[((size_t)pu * nc + i) * 2]), clip3(qminy, qmaxy, mvc[((size_t)pu * nc + i) * 2 + 1]));
+        put_cand(s, o + 3 + i, base, strideR, pitch, clip3(qminx, qmaxx, mvc[((size_t)pu * nc + i) * 2]), clip3(qminy, qmaxy, mvc[((size_t)pu * nc + i) * 2 + 1]),
+                 c, baseC, true);
 }
 
 __global__ void me_start_select(int n, int nc, int K, const int32_t* __restrict__ qmvp, const int32_t* __restrict__ mvc,
@@ -181,10 +195,11 @@ __global__ void me_start_select(int n, int nc, int K, const int32_t* __restrict_
 // bit 2: emit the candidates of round `next`; bit 3: zero-vector last chance and outputs (:1762-1772)
 __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, const int32_t* __restrict__ qmvp,
                                 const int32_t* __restrict__ range, const int32_t* __restrict__ offR, intptr_t strideR, int pitch,
-                                const uint16_t* __restrict__ tab, MeState s, int32_t* __restrict__ outQMv, int32_t* __restrict__ outCost)
+                                const uint16_t* __restrict__ tab, MeState s, int32_t* __restrict__ outQMv, int32_t* __restrict__ outCost, MeChroma c)
 {
     int pu = blockIdx.x * blockDim.x + threadIdx.x;
     if (pu >= n) return;
+    const int baseC = c.on ? c.offRC[pu] : 0;
     int flags = s.flags[pu];
     const int mvpx = qmvp[2 * pu], mvpy = qmvp[2 * pu + 1];
     const int qminy = range[4 * pu + 1] * 4, qmaxy = range[4 * pu + 3] * 4;
@@ -224,14 +239,14 @@ __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, con
         const int base = offR[pu];
         const bool live = !(flags & ME_FIN);                   // a finished PU's bmv is still in full pels: park it on the zero vector
         const int cx = live ? bmvx : 0, cy = live ? bmvy : 0;
-        put_cand(s, o, base, strideR, pitch, cx, cy);
+        put_cand(s, o, base, strideR, pitch, cx, cy, c, baseC);
         for (int i = 1; i <= next.dirs; i++)
         {
             int qx = cx + c_square1[i][0] * next.step, qy = cy + c_square1[i][1] * next.step;
             if (!live || qy < qminy || qy > qmaxy) { qx = cx; qy = cy; }      // never measured by the reference: stay on a valid block
-            put_cand(s, o + i, base, strideR, pitch, qx, qy);
+            put_cand(s, o + i, base, strideR, pitch, qx, qy, c, baseC);
         }
-        if (next.zeroSlot) put_cand(s, o + next.K - 1, base, strideR, pitch, 0, 0);
+        if (next.zeroSlot) put_cand(s, o + next.K - 1, base, strideR, pitch, 0, 0, c, baseC);
     }
     if ((mode & 8) && !(flags & ME_FIN))
     {
@@ -250,7 +265,10 @@ __global__ void me_round_kernel(int n, int mode, MeRound prev, MeRound next, con
 using namespace b200;
 
 // pitch == 0: full-resolution reference (interpolating sub-pel costs); pitch > 0: lowres reference, four half-pel planes
-static int motion_chain(x265b200_ctx* ctx, int pitch, int searchMethod, int w, int h, int merange, int subpelRefine,
+struct MeChromaArgs { const void* fencCb; const void* fencCr; intptr_t strideFC; const void* refCb; const void* refCr; const int32_t* offFC; };
+
+static int motion_chain(x265b200_ctx* ctx, int pitch, const MeChroma& chroma, const MeChromaArgs& cargs,
+                        int searchMethod, int w, int h, int merange, int subpelRefine,
                         const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
                         const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                         int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
@@ -297,13 +315,14 @@ static int motion_chain(x265b200_ctx* ctx, int pitch, int searchMethod, int w, i
     }
 
     int32_t* scratch = nullptr;
-    const size_t per = 2 + 2 + 1 + 2 + 1 + 1 + 4 + 3 * (size_t)KMAX;
+    const size_t per = 2 + 2 + 1 + 2 + 1 + 1 + 4 + 5 * (size_t)KMAX;
     B200_CUDA(ctx, cudaMallocAsync((void**)&scratch, per * n * sizeof(int32_t), st));
     MeState s;
     int32_t* p = scratch;
     s.pmv = p; p += 2 * (size_t)n; s.bestpre = p; p += 2 * (size_t)n; s.bprecost = p; p += n; s.bmv = p; p += 2 * (size_t)n;
     s.bcost = p; p += n; s.flags = p; p += n; s.eff = p; p += 4 * (size_t)n;
-    s.candOff = p; p += (size_t)KMAX * n; s.candFrac = p; p += (size_t)KMAX * n; s.candCost = p;
+    s.candOff = p; p += (size_t)KMAX * n; s.candFrac = p; p += (size_t)KMAX * n; s.candCost = p; p += (size_t)KMAX * n;
+    s.candOffC = p; p += (size_t)KMAX * n; s.candFracC = p;
 
     const int T = 128, G = ceil_div(n, T);
     int rc = X265B200_OK;
@@ -313,9 +332,16 @@ static int motion_chain(x265b200_ctx* ctx, int pitch, int searchMethod, int w, i
     auto cand_costs = [&](int op, int K)
     {
         if (pitch) return launch_lowres_cmp(ctx, op, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K, n, s.candCost, st);
-        return x265b200_subpel_cmp_batch(ctx, op, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K, n, s.candCost, stream);
+        int r = x265b200_subpel_cmp_batch(ctx, op, w, h, fenc, strideF, ref, strideR, offF, s.candOff, s.candFrac, K, n, s.candCost, stream);
+        if (r || !chroma.on) return r;
+        const int cw = w >> chroma.hshift, ch = h >> chroma.vshift;      // + SATD of both chroma blocks, whatever `op` is
+        r = x265b200_subpel_cmp_chroma_batch(ctx, cw, ch, cargs.fencCb, cargs.strideFC, cargs.refCb, chroma.strideRC, cargs.offFC, s.candOffC,
+                                             s.candFracC, K, n, s.candCost, 1, stream);
+        if (r) return r;
+        return x265b200_subpel_cmp_chroma_batch(ctx, cw, ch, cargs.fencCr, cargs.strideFC, cargs.refCr, chroma.strideRC, cargs.offFC, s.candOffC,
+                                                s.candFracC, K, n, s.candCost, 1, stream);
     };
-    me_start_gen<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, offR, strideR, pitch, s);
+    me_start_gen<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, offR, strideR, pitch, s, chroma);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     if ((rc = cand_costs(X265B200_SAD, K0))) return bail(rc);
     me_start_select<<<G, T, 0, st>>>(n, numCand, K0, qmvp, mvc, range, costTab, s, outQMv, outCost);
@@ -328,7 +354,7 @@ static int motion_chain(x265b200_ctx* ctx, int pitch, int searchMethod, int w, i
     for (int r = 0; r <= R; r++)
     {
         const int mode = (r == 0 ? 1 : 2) | (r < R ? 4 : 8);
-        me_round_kernel<<<G, T, 0, st>>>(n, mode, rounds[r ? r - 1 : 0], rounds[r < R ? r : R - 1], qmvp, range, offR, strideR, pitch, costTab, s, outQMv, outCost);
+        me_round_kernel<<<G, T, 0, st>>>(n, mode, rounds[r ? r - 1 : 0], rounds[r < R ? r : R - 1], qmvp, range, offR, strideR, pitch, costTab, s, outQMv, outCost, chroma);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         if (r < R && (rc = cand_costs(ops[r], rounds[r].K))) return bail(rc);
     }
@@ -344,8 +370,8 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
                                               int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
                                               int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
 {
-    return motion_chain(ctx, 0, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR, offF, offR, range, qmvp, numCand, mvc,
-                        costTab, n, outQMv, outCost, stream);
+    return motion_chain(ctx, 0, MeChroma{ 0, 0, 0, 0, nullptr }, MeChromaArgs{}, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR,
+                        offF, offR, range, qmvp, numCand, mvc, costTab, n, outQMv, outCost, stream);
 }
 
 extern "C" int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
@@ -356,6 +382,26 @@ extern "C" int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int sear
     if (!ctx) return X265B200_ERR_ARG;
     if (planePitch == 0 || planePitch > 0x1fffffff || ((strideF | strideR) & 3) || w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3))
         return fail(ctx, X265B200_ERR_ARG, "lowres_motion_estimate: bad geometry");
-    return motion_chain(ctx, (int)planePitch, searchMethod, w, h, merange, subpelRefine, fenc, strideF, planes, strideR, offF, offR, range, qmvp,
-                        0, nullptr, costTab, n, outQMv, outCost, stream);
+    return motion_chain(ctx, (int)planePitch, MeChroma{ 0, 0, 0, 0, nullptr }, MeChromaArgs{}, searchMethod, w, h, merange, subpelRefine, fenc, strideF,
+                        planes, strideR, offF, offR, range, qmvp, 0, nullptr, costTab, n, outQMv, outCost, stream);
+}
+
+extern "C" int x265b200_motion_estimate_chroma_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,
+                                                     const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                                     const int32_t* offF, const int32_t* offR,
+                                                     const void* fencCb, const void* fencCr, intptr_t strideFC,
+                                                     const void* refCb, const void* refCr, intptr_t strideRC,
+                                                     const int32_t* offFC, const int32_t* offRC, int hshift, int vshift,
+                                                     const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                                                     const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (!((hshift == 1 && vshift == 1) || (hshift == 0 && vshift == 0)) || ((strideFC | strideRC) & 3))
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate_chroma: 4:2:0 or 4:4:4 planes with strides that are multiples of 4");
+    // bChromaSATD (motion.cpp:240): subme > 2 and a chroma block that has a SATD slot (a multiple of 4x4, pixel.cpp:1217-1243)
+    const int on = subpelRefine > 2 && !((w >> hshift) & 3) && !((h >> vshift) & 3);
+    MeChroma c{ on, hshift, vshift, strideRC, offRC };
+    MeChromaArgs a{ fencCb, fencCr, strideFC, refCb, refCr, offFC };
+    return motion_chain(ctx, 0, c, a, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR, offF, offR, range, qmvp, numCand, mvc,
+                        costTab, n, outQMv, outCost, stream);
 }
