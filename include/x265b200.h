@@ -268,6 +268,15 @@ int x265b200_motion_estimate_chroma_batch(x265b200_ctx* ctx, int searchMethod, i
                                           const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
                                           const uint16_t* costTab, int n, int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
 
+/* Bi-prediction candidate cost (reference encoder/search.cpp:442-448 in Search::predInterSearch): for PU i, both lists'
+ * motion-compensated luma blocks (Predict::predInterLumaPixel, common/predict.cpp:279-300; off0/off1 hold the integer part
+ * of each vector, frac0/frac1 = xFrac | yFrac << 4), their rounded average (pixelavg_pp) and SATD against the fenc block;
+ * neither prediction nor average is written to memory. */
+int x265b200_bidir_satd_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t strideF, const int32_t* offF,
+                              const void* ref0, intptr_t stride0, const int32_t* off0, const int32_t* frac0,
+                              const void* ref1, intptr_t stride1, const int32_t* off1, const int32_t* frac1,
+                              int n, int32_t* cost, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

@@ -522,4 +522,25 @@ void ref_me_full_search(int w, int h, const pixel* fencIn, intptr_t sf, const pi
     *bcostIO = bcost; bmvIO[0] = bx; bmvIO[1] = by;
 }
 
+/* ---- bi-prediction cost through the reference table, in search.cpp:442-448's slot sequence ---- */
+static void ref_mc_luma(int part, int w, const pixel* fref, intptr_t sr, int xFrac, int yFrac, pixel* dst)
+{
+    if (!(xFrac | yFrac)) g_c.pu[part].copy_pp(dst, 64, fref, sr);
+    else if (!yFrac) g_c.pu[part].luma_hpp(fref, sr, dst, 64, xFrac);
+    else if (!xFrac) g_c.pu[part].luma_vpp(fref, sr, dst, 64, yFrac);
+    else g_c.pu[part].luma_hvpp(fref, sr, dst, 64, xFrac, yFrac);
+}
+int ref_bidir_satd(int w, int h, const pixel* fenc, intptr_t sf, const pixel* ref0, intptr_t sr0, int frac0,
+                   const pixel* ref1, intptr_t sr1, int frac1)
+{
+    ensure();
+    int part = lumaPart(w, h);
+    if (part < 0) return -1;
+    ALIGN_VAR_32(pixel, p0[64 * 64]); ALIGN_VAR_32(pixel, p1[64 * 64]); ALIGN_VAR_32(pixel, avg[64 * 64]);
+    ref_mc_luma(part, w, ref0, sr0, frac0 & 3, (frac0 >> 4) & 3, p0);
+    ref_mc_luma(part, w, ref1, sr1, frac1 & 3, (frac1 >> 4) & 3, p1);
+    g_c.pu[part].pixelavg_pp[NONALIGNED](avg, 64, p0, 64, p1, 64, 32);
+    return g_c.pu[part].satd(fenc, sf, avg, 64);
+}
+
 } // extern "C"

@@ -772,6 +772,35 @@ EXPORT void orc_subpel_cmp_batch(int op, int w, int h, const pixel* fenc, intptr
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Bi-prediction candidate cost (encoder/search.cpp:442-448 in Search::predInterSearch): both motion-compensated luma
+ * blocks (Predict::predInterLumaPixel, common/predict.cpp:279-300: copy / luma_hpp / luma_vpp / luma_hvpp by the vector's
+ * fraction), their rounded average (pixelavg_pp, pixel.cpp:537-549), SATD against fenc.
+ * ------------------------------------------------------------------------------------------------ */
+static void mc_luma(int w, int h, const pixel* fref, intptr_t sr, int xFrac, int yFrac, pixel* dst)
+{
+    if (!(xFrac | yFrac)) { for (int y = 0; y < h; y++) memcpy(dst + y * w, fref + y * sr, w * sizeof(pixel)); }
+    else if (!yFrac) orc_interp_hpp(8, w, h, fref, sr, dst, w, xFrac);
+    else if (!xFrac) orc_interp_vpp(8, w, h, fref, sr, dst, w, yFrac);
+    else orc_interp_hvpp(8, w, h, fref, sr, dst, w, xFrac, yFrac);
+}
+EXPORT int orc_bidir_satd(int w, int h, const pixel* fenc, intptr_t sf, const pixel* ref0, intptr_t sr0, int frac0,
+                          const pixel* ref1, intptr_t sr1, int frac1)
+{
+    pixel p0[64 * 64], p1[64 * 64];
+    mc_luma(w, h, ref0, sr0, frac0 & 3, (frac0 >> 4) & 3, p0);
+    mc_luma(w, h, ref1, sr1, frac1 & 3, (frac1 >> 4) & 3, p1);
+    for (int i = 0; i < w * h; i++) p0[i] = (pixel)((p0[i] + p1[i] + 1) >> 1);
+    return orc_satd(w, h, fenc, sf, p0, w);
+}
+EXPORT void orc_bidir_satd_batch(int w, int h, const pixel* fenc, intptr_t sf, const int32_t* offF, const pixel* ref0, intptr_t sr0,
+                                 const int32_t* off0, const int32_t* frac0, const pixel* ref1, intptr_t sr1, const int32_t* off1,
+                                 const int32_t* frac1, int n, int32_t* cost)
+{
+    for (int i = 0; i < n; i++)
+        cost[i] = orc_bidir_satd(w, h, fenc + offF[i], sf, ref0 + off0[i], sr0, frac0[i], ref1 + off1[i], sr1, frac1[i]);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * SEA integral planes (encoder/framefilter.cpp:38-140; row loop of FrameFilter::computeMEIntegral, :737-835).
  * ------------------------------------------------------------------------------------------------ */
 EXPORT void orc_integral_inith(int W, uint32_t* sum, const pixel* pix, intptr_t stride)

@@ -208,6 +208,9 @@ class _Base:
                                               hshift, vshift, _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    def bidir_satd(self, w, h, fenc, of, sf, ref0, o0, sr0, frac0, ref1, o1, sr1, frac1):
+        return self._f("bidir_satd")(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref0, o0), C.c_ssize_t(sr0), frac0, _ptr(ref1, o1), C.c_ssize_t(sr1), frac1)
+
     def subpel_cmp_chroma(self, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp_chroma")(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
 
@@ -324,6 +327,13 @@ class Oracle(_Base):
         """bmv (n x 2 int32) and bcost (n int32) are updated in place"""
         self._f("me_full_batch", None)(w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(ref), C.c_ssize_t(sr), _ptr(offF), _ptr(offR), _ptr(rng), _ptr(mvp),
                                        _ptr(cost_tab, centre), len(offF), _ptr(bmv), _ptr(bcost))
+
+    def bidir_satd_batch(self, w, h, fenc, sf, offF, ref0, sr0, off0, frac0, ref1, sr1, off1, frac1):
+        n = len(offF)
+        cost = np.zeros(n, np.int32)
+        self._f("bidir_satd_batch", None)(w, h, _ptr(fenc), C.c_ssize_t(sf), _ptr(offF), _ptr(ref0), C.c_ssize_t(sr0), _ptr(off0), _ptr(frac0),
+                                          _ptr(ref1), C.c_ssize_t(sr1), _ptr(off1), _ptr(frac1), n, _ptr(cost))
+        return cost
 
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD):
         self._f("blockop_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(offA), _ptr(B), C.c_ssize_t(sb), _ptr(offB),

@@ -714,3 +714,33 @@ def test_motion_estimate_chroma_batch(depth):
         else: decided += int((want[:, :2] != luma[:, :2]).any(1).sum())
     assert decided > 5                                    # the chroma term moved vectors, not only costs
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_bidir_satd_batch(depth):
+    """bi-prediction candidate cost (two motion-compensated blocks, rounded average, SATD) vs the oracle's composition --
+    pinned to predInterSearch's slot sequence on the reference table by the CPU suite -- for every luma PU shape, all
+    fraction pairs incl. zero fractions, different reference planes and strides for the two lists"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240); geo1 = Geometry(480, 256)
+    F = make_plane(geo, depth, 121, "natural"); R0 = make_plane(geo, depth, 122, "natural"); R1 = make_plane(geo1, depth, 123, "uniform")
+    rng = np.random.default_rng(900 + depth)
+    cw, ch = geo.coded()
+    dF, dR0, dR1 = dev(pix_view(F, depth)), dev(pix_view(R0, depth)), dev(pix_view(R1, depth))
+    for (w, h) in LUMA_PU:
+        n = 41
+        x = rng.integers(0, cw - w, n); y = rng.integers(0, ch - h, n)
+        offF = (geo.origin + y * geo.stride + x).astype(np.int32)
+        off0 = (geo.origin + (y + rng.integers(-30, 31, n)) * geo.stride + x + rng.integers(-30, 31, n)).astype(np.int32)
+        off1 = (geo1.origin + (y + rng.integers(-30, 31, n)) * geo1.stride + x + rng.integers(-30, 31, n)).astype(np.int32)
+        f0 = (rng.integers(0, 4, n) | (rng.integers(0, 4, n) << 4)).astype(np.int32)
+        f1 = (rng.integers(0, 4, n) | (rng.integers(0, 4, n) << 4)).astype(np.int32)
+        f0[:6] = [0, 0, 1, 0x20, 0x33, 0]; f1[:6] = [0, 0x12, 0, 0, 0x33, 3]
+        want = orc.bidir_satd_batch(w, h, F, geo.stride, offF, R0, geo.stride, off0, f0, R1, geo1.stride, off1, f1)
+        cost = torch.full((n,), -3, dtype=torch.int32, device="cuda")
+        ctx.bidir_satd_batch(w, h, dF, geo.stride, dev(offF), dR0, geo.stride, dev(off0), dev(f0), dR1, geo1.stride, dev(off1), dev(f1), cost)
+        assert np.array_equal(cost.cpu().numpy(), want), (w, h)
+    ctx.check()

@@ -682,3 +682,20 @@ def test_motion_estimate_chroma(libs):
                                                method, merange)
             chroma_decided += luma_only[:2] != a[:2]
     assert on_count > 100 and chroma_decided > 5          # the chroma term changed winners, not only costs
+
+
+def test_bidir_satd(libs):
+    """bi-prediction candidate cost: the oracle's composition vs predInterSearch's slot sequence on the reference table
+    (motion compensation of both lists by vector fraction, pixelavg_pp, satd)"""
+    o, r = libs
+    rng = np.random.default_rng(83)
+    stride, rows = 192, 176
+    for fenc, ref in pixel_bufs(rng, o.depth, stride * rows):
+        ref1 = np.roll(ref, 7 * stride + 3)
+        for (w, h) in LUMA_PU:
+            for _ in range(3):
+                f0 = int(rng.integers(0, 4)) | (int(rng.integers(0, 4)) << 4); f1 = int(rng.integers(0, 4)) | (int(rng.integers(0, 4)) << 4)
+                for (a0, a1) in ((f0, f1), (0, f1), (f0, 0), (0, 0), (f0 & 3, f1 & 0x30)):
+                    x = o.bidir_satd(w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, a0, ref1, 31 * stride + 40, stride, a1)
+                    y = r.bidir_satd(w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, a0, ref1, 31 * stride + 40, stride, a1)
+                    assert x == y and x >= 0, (w, h, a0, a1)

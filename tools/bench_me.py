@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--subme", type=int, default=2)
     ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 3 STAR, 5 FULL")
     ap.add_argument("--shapes", default="64,32,16,8", help="square PU sizes to run")
+    ap.add_argument("--bidir", action="store_true", help="also time the bi-prediction cost entry")
     ap.add_argument("--lowres", action="store_true", help="also time the lookahead's lowres search")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle's loop on a sample of PUs (one core)")
     args = ap.parse_args()
@@ -116,6 +117,29 @@ def main():
             row["cpu_port_1core_G_sample_candidates_per_s"] = cc * w * h / dt / 1e9
             got_mv = bmv.cpu().numpy()[sel]; got_c = bc.cpu().numpy()[sel]
             row["cpu_sample_matches"] = bool(np.array_equal(got_mv, mv) and np.array_equal(got_c, c))
+        rows.append(row)
+        print(json.dumps(row), file=sys.stderr)
+    if args.bidir:
+        # bi-prediction cost of every 16x16 PU of the frame: two quarter-pel vectors per PU (search.cpp:442-448)
+        oa, ob = tile_blocks(geo, 16, 16, seed=1)
+        _, oc_ = tile_blocks(geo, 16, 16, seed=2)
+        n = oa.size
+        g = np.random.default_rng(4)
+        f0 = torch.from_numpy((g.integers(0, 4, n) | (g.integers(0, 4, n) << 4)).astype(np.int32)).cuda()
+        f1 = torch.from_numpy((g.integers(0, 4, n) | (g.integers(0, 4, n) << 4)).astype(np.int32)).cuda()
+        dA, dB0, dB1 = (torch.from_numpy(a.astype(np.int32)).cuda() for a in (oa, ob, oc_))
+        cost = torch.zeros(n, dtype=torch.int32, device="cuda")
+
+        def run_bi():
+            ctx.bidir_satd_batch(16, 16, A, geo.stride, dA, B, geo.stride, dB0, f0, B, geo.stride, dB1, f1, cost)
+        run_bi(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); run_bi(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        row = {"bidir_satd": "16x16 PUs of one 2160p frame, random quarter-pel vectors", "n_pu": int(n), "ms_per_frame": sorted(ts)[2],
+               "G_samples_per_s": n * 256 / sorted(ts)[2] / 1e6}
         rows.append(row)
         print(json.dumps(row), file=sys.stderr)
     if args.lowres:

@@ -175,6 +175,10 @@ class Context:
         self._call("x265b200_subpel_cmp_chroma_batch", w, h, _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR), _dp(frac), int(K),
                    int(offF.numel()), _dp(cost), int(accumulate), C.c_void_p(stream))
 
+    def bidir_satd_batch(self, w, h, fenc, sf, offF, ref0, sr0, off0, frac0, ref1, sr1, off1, frac1, cost, stream=0):
+        self._call("x265b200_bidir_satd_batch", w, h, _dp(fenc), _ss(sf), _dp(offF), _dp(ref0), _ss(sr0), _dp(off0), _dp(frac0),
+                   _dp(ref1), _ss(sr1), _dp(off1), _dp(frac1), int(offF.numel()), _dp(cost), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

@@ -529,6 +529,147 @@ subpel_cmp_kernel(const PIX* __restrict__ fenc, intptr_t sf, const PIX* __restri
     }
 }
 
+// Bi-prediction candidate cost (reference encoder/search.cpp:442-448): both lists' motion-compensated luma blocks
+// (predInterLumaPixel = the same copy / hpp / vpp / hvpp choice as subpelCompare, through the identity taps here), their
+// rounded average (pixelavg_pp) and SATD against fenc.  Same two-pass structure as subpel_cmp_kernel with two
+// intermediate tiles in shared memory; the average is taken on packed pairs between the vertical pass and the SATD.
+template<typename PIX, int TW1>
+__device__ __forceinline__ void bidir_stage1(const PIX* __restrict__ s, intptr_t ss, int16_t* immed, int w, int rows, int l, int G,
+                                             uint32_t tx0, uint32_t tx1, int shift1, int offset1)
+{
+    constexpr int TAPS = 8;
+    constexpr int NQ = (TW1 + TAPS - 1 + 3) / 4;
+    int tw = w / TW1;
+    int tiles1 = tw * ((rows + 3) >> 2);
+    for (int t = l; t < tiles1; t += G)
+    {
+        int tx = (t % tw) * TW1, ty = (t / tw) << 2;
+        uint32_t wv[4][2 * NQ + 1];
+        if (ty + 4 <= rows)
+            load_rows_quads<NQ, 4>(s + (intptr_t)ty * ss + tx, ss, wv);
+        else
+        {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (ty + r < rows) { load_row_quads<NQ>(s + (intptr_t)(ty + r) * ss + tx, (uint32_t(&)[2 * NQ])wv[r]); wv[r][2 * NQ] = 0; }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            if (ty + r >= rows) break;
+            uint32_t ws[2 * NQ];
+#pragma unroll
+            for (int i = 0; i < 2 * NQ; i++) ws[i] = __funnelshift_r(wv[r][i], wv[r][i + 1], 16);
+#pragma unroll
+            for (int o4 = 0; o4 < TW1; o4 += 4)
+            {
+                int v[4];
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    int i = (o4 + o) >> 1;
+                    int sum = ((o4 + o) & 1) ? fir_pairs<PIX, TAPS>(ws[i], ws[i + 1], ws[(i + 2) % (2 * NQ)], ws[(i + 3) % (2 * NQ)], tx0, tx1, offset1)
+                                             : fir_pairs<PIX, TAPS>(wv[r][i], wv[r][i + 1], wv[r][(i + 2) % (2 * NQ + 1)], wv[r][(i + 3) % (2 * NQ + 1)], tx0, tx1, offset1);
+                    v[o] = sum >> shift1;
+                }
+                *(uint2*)(immed + (ty + r) * w + tx + o4) = make_uint2(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x5410),
+                                                                       __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x5410));
+            }
+        }
+    }
+}
+
+// vertical pass of one 4 x TH2 tile out of the intermediate tile: packed, clipped pixel pairs per row
+template<int TH2>
+__device__ __forceinline__ void bidir_stage2(const int16_t* immed, int w, int tx, int ty, uint32_t ty0, uint32_t ty1, int shift2, int offset2,
+                                             uint32_t mx, uint32_t (&lo)[TH2], uint32_t (&hi)[TH2])
+{
+    constexpr int TAPS = 8;
+    constexpr int NR = TH2 + TAPS - 1;
+    uint2 q[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) q[r] = *(const uint2*)(immed + (ty + r) * w + tx);
+    uint32_t pr[NR - 1][4];
+#pragma unroll
+    for (int r = 0; r < NR - 1; r++)
+    {
+        pr[r][0] = __byte_perm(q[r].x, q[r + 1].x, 0x5410); pr[r][1] = __byte_perm(q[r].x, q[r + 1].x, 0x7632);
+        pr[r][2] = __byte_perm(q[r].y, q[r + 1].y, 0x5410); pr[r][3] = __byte_perm(q[r].y, q[r + 1].y, 0x7632);
+    }
+#pragma unroll
+    for (int r = 0; r < TH2; r++)
+    {
+        int v[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+            v[o] = fir_pairs<int16_t, TAPS>(pr[r][o], pr[r + 2][o], pr[(r + 4) % (NR - 1)][o], pr[(r + 6) % (NR - 1)][o], ty0, ty1, offset2) >> shift2;
+        lo[r] = pack_clip2(v[0], v[1], mx);
+        hi[r] = pack_clip2(v[2], v[3], mx);
+    }
+}
+
+template<typename PIX, int TW1, int TH2>
+__global__ void __launch_bounds__(128)
+bidir_satd_kernel(const PIX* __restrict__ fenc, intptr_t sf, const int32_t* __restrict__ offF,
+                  const PIX* __restrict__ ref0, intptr_t ss0, const int32_t* __restrict__ off0, const int32_t* __restrict__ frac0,
+                  const PIX* __restrict__ ref1, intptr_t ss1, const int32_t* __restrict__ off1, const int32_t* __restrict__ frac1,
+                  int n, int w, int h, int G, int shift1, int offset1, int shift2, int offset2, int maxVal, int32_t* __restrict__ cost)
+{
+    constexpr int TAPS = 8;
+    extern __shared__ __align__(16) int16_t immed_all[];
+    int lg = __ffs(G) - 1;
+    int grp = threadIdx.x >> lg, l = threadIdx.x & (G - 1);
+    int cand = blockIdx.x * (128 >> lg) + grp;
+    bool live = cand < n;
+    int rows = h + TAPS - 1;
+    int16_t* immed0 = immed_all + (size_t)grp * 2 * w * rows;
+    int16_t* immed1 = immed0 + (size_t)w * rows;
+    uint32_t ty00 = 0, ty01 = 0, ty10 = 0, ty11 = 0;
+    if (live)
+    {
+        int c0 = frac0[cand], c1 = frac1[cand];
+        ty00 = c_lumaTapsB[(c0 >> 4) & 3][0]; ty01 = c_lumaTapsB[(c0 >> 4) & 3][1];
+        ty10 = c_lumaTapsB[(c1 >> 4) & 3][0]; ty11 = c_lumaTapsB[(c1 >> 4) & 3][1];
+        bidir_stage1<PIX, TW1>(ref0 + off0[cand] - (TAPS / 2 - 1) * ss0 - (TAPS / 2 - 1), ss0, immed0, w, rows, l, G,
+                               c_lumaTapsB[c0 & 3][0], c_lumaTapsB[c0 & 3][1], shift1, offset1);
+        bidir_stage1<PIX, TW1>(ref1 + off1[cand] - (TAPS / 2 - 1) * ss1 - (TAPS / 2 - 1), ss1, immed1, w, rows, l, G,
+                               c_lumaTapsB[c1 & 3][0], c_lumaTapsB[c1 & 3][1], shift1, offset1);
+    }
+    __syncwarp();
+    int acc = 0;
+    if (live)
+    {
+        const PIX* f = fenc + offF[cand];
+        int tw = w >> 2;
+        int tiles2 = tw * (h / TH2);
+        const uint32_t mx = (uint32_t)maxVal * 0x10001u;
+        for (int t = l; t < tiles2; t += G)
+        {
+            int tx = (t % tw) << 2, ty = (t / tw) * TH2;
+            uint32_t alo[TH2], ahi[TH2], blo[TH2], bhi[TH2];
+            bidir_stage2<TH2>(immed0, w, tx, ty, ty00, ty01, shift2, offset2, mx, alo, ahi);
+            bidir_stage2<TH2>(immed1, w, tx, ty, ty10, ty11, shift2, offset2, mx, blo, bhi);
+#pragma unroll
+            for (int r = 0; r < TH2; r++)
+            {   // pixelavg_pp on packed pairs (samples < 2^15: the halves cannot carry into each other)
+                alo[r] = ((alo[r] + blo[r] + 0x00010001u) >> 1) & 0x7fff7fffu;
+                ahi[r] = ((ahi[r] + bhi[r] + 0x00010001u) >> 1) & 0x7fff7fffu;
+            }
+#pragma unroll
+            for (int r4 = 0; r4 < TH2; r4 += 4)
+            {
+                uint32_t flo[4], fhi[4], plo[4], phi[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) { plo[rr] = alo[r4 + rr]; phi[rr] = ahi[r4 + rr]; }
+                load_tile4x4(f + (intptr_t)(ty + r4) * sf + tx, sf, flo, fhi);
+                tile4_accumulate<OP_SATD, int>(flo, fhi, plo, phi, acc);
+            }
+        }
+    }
+    acc = group_sum(acc, G);
+    if (live && l == 0) cost[cand] = acc;
+}
+
 // p2s, 4 samples per thread
 template<typename PIX>
 __global__ void __launch_bounds__(256)
@@ -755,4 +896,37 @@ extern "C" int x265b200_subpel_cmp_chroma_batch(x265b200_ctx* ctx, int w, int h,
                                                 int accumulate, x265b200_stream stream)
 {
     return subpel_cmp_launch(ctx, 4, accumulate ? 1 : 0, X265B200_SATD, w, h, fenc, sf, ref, sr, offF, offR, frac, K, n, cost, stream);
+}
+
+extern "C" int x265b200_bidir_satd_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t sf, const int32_t* offF,
+                                         const void* ref0, intptr_t sr0, const int32_t* off0, const int32_t* frac0,
+                                         const void* ref1, intptr_t sr1, const int32_t* off1, const int32_t* frac1,
+                                         int n, int32_t* cost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || h < 4 || (w & 3) || (h & 3) || w > 64 || h > 64 || n < 0) return fail(ctx, X265B200_ERR_ARG, "bidir_satd: bad shape");
+    if ((sf | sr0 | sr1) & 3) return fail(ctx, X265B200_ERR_ARG, "bidir_satd: plane strides must be multiples of 4 samples");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int headRoom = 14 - ctx->depth, maxVal = (1 << ctx->depth) - 1;
+    const int shift1 = 6 - headRoom, shift2 = 6 + headRoom;
+    const int offset1 = (int)((unsigned)-8192 << shift1), offset2 = (1 << (shift2 - 1)) + (8192 << 6);
+    const size_t smem = 2 * (size_t)w * (h + 7) * sizeof(int16_t);
+    const bool wide = !(w & 7), tall = !(h & 7);
+    int tiles2 = (w >> 2) * (tall ? h >> 3 : h >> 2);
+    int G = 1;
+    while (G * 2 <= tiles2 / 2 && G < 32) G <<= 1;
+    int perCta = 128 / G;
+    const size_t total = perCta * smem;
+#define BD(PIX, TW1_, TH2_) do {                                                                                                        \
+        if (total > 48 * 1024)                                                                                                          \
+            B200_CUDA(ctx, cudaFuncSetAttribute((const void*)bidir_satd_kernel<PIX, TW1_, TH2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total)); \
+        bidir_satd_kernel<PIX, TW1_, TH2_><<<ceil_div(n, perCta), 128, total, st>>>((const PIX*)fenc, sf, offF, (const PIX*)ref0, sr0, off0, frac0, \
+            (const PIX*)ref1, sr1, off1, frac1, n, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost); } while (0)
+#define BD_SHAPE(PIX) do { if (wide && tall) BD(PIX, 8, 8); else if (wide) BD(PIX, 8, 4); else if (tall) BD(PIX, 4, 8); else BD(PIX, 4, 4); } while (0)
+    if (ctx->pixbytes == 1) BD_SHAPE(uint8_t); else BD_SHAPE(uint16_t);
+#undef BD_SHAPE
+#undef BD
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
 }
