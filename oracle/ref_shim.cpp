@@ -543,4 +543,55 @@ int ref_bidir_satd(int w, int h, const pixel* fenc, intptr_t sf, const pixel* re
     return g_c.pu[part].satd(fenc, sf, avg, 64);
 }
 
+/* ---- intra prediction slots and the lookahead's intra estimate in lowresIntraEstimate's slot sequence (slicetype.cpp:781-841) ---- */
+void ref_intra_filter(int N, const pixel* s, pixel* f) { ensure(); g_c.cu[cuIdx(N)].intra_filter(s, f); }
+void ref_intra_pred(int N, int mode, const pixel* s, int bFilter, pixel* dst, intptr_t ds) { ensure(); g_c.cu[cuIdx(N)].intra_pred[mode](dst, ds, s, mode, bFilter); }
+void ref_intra_allangs(int N, pixel* dest, pixel* refPix, pixel* filtPix, int bLuma) { ensure(); g_c.cu[cuIdx(N)].intra_pred_allangs(dest, refPix, filtPix, bLuma); }
+int ref_lowres_intra_cu(const pixel* plane, intptr_t stride, int cuX, int cuY, int penalty, int32_t* modeOut)
+{
+    ensure();
+    const int cuSize = X265_LOWRES_CU_SIZE, cuSize2 = cuSize << 1, sizeIdx = X265_LOWRES_CU_BITS - 2;
+    ALIGN_VAR_32(pixel, prediction[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE]);
+    pixel fencIntra[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE];
+    pixel neighbours[2][X265_LOWRES_CU_SIZE * 4 + 1];
+    pixel* samples = neighbours[0], *filtered = neighbours[1];
+    pixelcmp_t satd = g_c.pu[sizeIdx].satd;
+    const pixel* pixCur = plane + cuSize * cuX + (intptr_t)cuSize * cuY * stride;
+    g_c.cu[sizeIdx].copy_pp(fencIntra, cuSize, pixCur, stride);
+    pixCur -= stride + 1;
+    memcpy(samples, pixCur, (2 * cuSize + 1) * sizeof(pixel));
+    for (int i = 1; i <= 2 * cuSize; i++) samples[cuSize2 + i] = pixCur[i * stride];
+    g_c.cu[sizeIdx].intra_filter(samples, filtered);
+    int cost, icost = 1 << 28, ilowmode = 0;
+    g_c.cu[sizeIdx].intra_pred[DC_IDX](prediction, cuSize, samples, 0, cuSize <= 16);
+    cost = satd(fencIntra, cuSize, prediction, cuSize);
+    if (cost < icost) { icost = cost; ilowmode = DC_IDX; }
+    g_c.cu[sizeIdx].intra_pred[PLANAR_IDX](prediction, cuSize, neighbours[cuSize >= 8], 0, 0);
+    cost = satd(fencIntra, cuSize, prediction, cuSize);
+    if (cost < icost) { icost = cost; ilowmode = PLANAR_IDX; }
+    int acost = 1 << 28, alowmode = 4, filter;
+    for (int mode = 5; mode < 35; mode += 5)
+    {
+        filter = !!(g_intraFilterFlags[mode] & cuSize);
+        g_c.cu[sizeIdx].intra_pred[mode](prediction, cuSize, neighbours[filter], mode, cuSize <= 16);
+        cost = satd(fencIntra, cuSize, prediction, cuSize);
+        if (cost < acost) { acost = cost; alowmode = mode; }
+    }
+    for (int dist = 2; dist >= 1; dist--)
+    {
+        int two[2] = { alowmode - dist, alowmode + dist };
+        for (int k = 0; k < 2; k++)
+        {
+            int mode = two[k];
+            filter = !!(g_intraFilterFlags[mode] & cuSize);
+            g_c.cu[sizeIdx].intra_pred[mode](prediction, cuSize, neighbours[filter], mode, cuSize <= 16);
+            cost = satd(fencIntra, cuSize, prediction, cuSize);
+            if (cost < acost) { acost = cost; alowmode = mode; }
+        }
+    }
+    if (acost < icost) { icost = acost; ilowmode = alowmode; }
+    *modeOut = ilowmode;
+    return icost + penalty;
+}
+
 } // extern "C"

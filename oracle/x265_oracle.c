@@ -1420,3 +1420,139 @@ EXPORT int orc_lowres_motion_estimate(int method, int merange, int subme, int w,
                  { refBlock, refBlock + pitch, refBlock + 2 * pitch, refBlock + 3 * pitch }, 0, 0, 0, { 0, 0 }, 0, { 0, 0 }, 0 };
     return me_estimate(c, method, merange, subme, range, qmvp, 0, 0, costTab, outQMv);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Intra prediction (common/intrapred.cpp:31-234): reference-sample smoothing, DC, planar and the 33 angular modes, and
+ * the lookahead's intra cost estimate built on them (encoder/slicetype.cpp:755-864 LookaheadTLD::lowresIntraEstimate).
+ * Neighbour array layout (intrapred.cpp:36-50): [0] top-left, [1 .. 2N] above and above-right, [2N+1 .. 4N] left and
+ * below-left.  Written per output sample instead of per row / with a flip at the end: a horizontal mode (< 18) is the
+ * vertical mode 36 - m... i.e. the same angular rule with above and left swapped and the block transposed.
+ * ------------------------------------------------------------------------------------------------ */
+static const uint8_t k_intra_filter_flags[35] = {       /* constants.cpp:561-567 */
+    0x38, 0x00,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38 };
+static const int k_intra_angle[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };   /* intrapred.cpp:122 */
+static const int k_intra_inv_angle[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };                         /* intrapred.cpp:123 */
+
+EXPORT void orc_intra_filter(int N, const pixel* s, pixel* f)       /* intrapred.cpp:31-51 */
+{
+    const int n2 = 2 * N;
+    for (int i = 1; i < 2 * n2; i++)
+        f[i] = (pixel)((2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2);
+    /* the two chains meet at the corner: top-left sees above[0] and left[0], left[0] sees the top-left */
+    f[0] = (pixel)((2 * s[0] + s[1] + s[n2 + 1] + 2) >> 2);
+    f[n2 + 1] = (pixel)((2 * s[n2 + 1] + s[0] + s[n2 + 2] + 2) >> 2);
+    f[n2] = s[n2]; f[2 * n2] = s[2 * n2];
+}
+/* neighbour j as a horizontal mode sees it: above and left exchanged (intrapred.cpp:111-119) */
+static int intra_nb(const pixel* s, int N, int hor, int j)
+{
+    if (!hor || j == 0) return s[j];
+    return j <= 2 * N ? s[2 * N + j] : s[j - 2 * N];
+}
+/* reference sample i of the angular rule (intrapred.cpp:147-171): the above row, extended to the left by the left
+ * column projected along the inverse angle when the angle is negative */
+static int intra_ref(const pixel* s, int N, int hor, int angleOffset, int i)
+{
+    if (i >= -1) return intra_nb(s, N, hor, i + 1);
+    const int k = -2 - i;
+    return intra_nb(s, N, hor, 2 * N + ((128 + (k + 1) * k_intra_inv_angle[-angleOffset - 1]) >> 8));
+}
+EXPORT void orc_intra_pred(int N, int mode, const pixel* s, int bFilter, pixel* dst, intptr_t ds)
+{
+    if (mode == 0)
+    {   /* planar, intrapred.cpp:87-100 */
+        int lg = 0; while ((1 << lg) < N) lg++;
+        const pixel* above = s + 1; const pixel* left = s + 2 * N + 1;
+        for (int y = 0; y < N; y++)
+            for (int x = 0; x < N; x++)
+                dst[y * ds + x] = (pixel)(((N - 1 - x) * left[y] + (N - 1 - y) * above[x] + (x + 1) * above[N] + (y + 1) * left[N] + N) >> (lg + 1));
+        return;
+    }
+    if (mode == 1)
+    {   /* DC with optional edge smoothing, intrapred.cpp:53-85 */
+        int dc = N;
+        for (int i = 0; i < N; i++) dc += s[1 + i] + s[2 * N + 1 + i];
+        dc /= 2 * N;
+        for (int y = 0; y < N; y++)
+            for (int x = 0; x < N; x++)
+            {
+                int v = dc;
+                if (bFilter)
+                {
+                    if (!x && !y) v = (s[1] + s[2 * N + 1] + 2 * dc + 2) >> 2;
+                    else if (!y) v = (s[1 + x] + 3 * dc + 2) >> 2;
+                    else if (!x) v = (s[2 * N + 1 + y] + 3 * dc + 2) >> 2;
+                }
+                dst[y * ds + x] = (pixel)v;
+            }
+        return;
+    }
+    /* angular, intrapred.cpp:102-204 */
+    const int hor = mode < 18;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = k_intra_angle[8 + angleOffset];
+    for (int r = 0; r < N; r++)
+        for (int c = 0; c < N; c++)
+        {
+            const int y = hor ? c : r, x = hor ? r : c;         /* position in the un-flipped (vertical) frame */
+            int v;
+            if (!angle)
+            {
+                v = intra_nb(s, N, hor, 1 + x);
+                if (bFilter && x == 0)
+                {
+                    v = (int16_t)(intra_nb(s, N, hor, 1) + ((intra_nb(s, N, hor, 2 * N + 1 + y) - intra_nb(s, N, hor, 0)) >> 1));
+                    v = v < 0 ? 0 : v > PIXEL_MAX ? PIXEL_MAX : v;
+                }
+            }
+            else
+            {
+                const int sum = (y + 1) * angle, off = sum >> 5, frac = sum & 31;
+                v = intra_ref(s, N, hor, angleOffset, off + x);
+                if (frac) v = ((32 - frac) * v + frac * intra_ref(s, N, hor, angleOffset, off + x + 1) + 16) >> 5;
+            }
+            dst[r * ds + c] = (pixel)v;
+        }
+}
+
+/* One lowres CU of LookaheadTLD::lowresIntraEstimate (slicetype.cpp:781-841): neighbours from the plane itself, DC, planar,
+ * then the angular modes coarse to fine (5, 10, .. 30; best +-2; best +-1), SATD cost, first-best on ties.
+ * Returns icost (with the signalling penalty added) and writes the mode. */
+EXPORT int orc_lowres_intra_cu(const pixel* plane, intptr_t stride, int cuX, int cuY, int penalty, int32_t* modeOut)
+{
+    enum { N = 8 };
+    pixel nb[2][4 * N + 1], pred[N * N];
+    const pixel* cur = plane + (intptr_t)N * cuY * stride + N * cuX;
+    const pixel* p = cur - stride - 1;
+    memcpy(nb[0], p, (2 * N + 1) * sizeof(pixel));
+    for (int i = 1; i <= 2 * N; i++) nb[0][2 * N + i] = p[i * stride];
+    orc_intra_filter(N, nb[0], nb[1]);
+    int icost = 1 << 28, imode = 0, cost;                       /* MotionEstimate::COST_MAX, motion.h:68 */
+    orc_intra_pred(N, 1, nb[0], 1, pred, N); cost = orc_satd(N, N, cur, stride, pred, N);
+    if (cost < icost) { icost = cost; imode = 1; }
+    orc_intra_pred(N, 0, nb[1], 0, pred, N); cost = orc_satd(N, N, cur, stride, pred, N);
+    if (cost < icost) { icost = cost; imode = 0; }
+    int acost = 1 << 28, amode = 4;
+#define ORC_TRY_ANG(m) do { int m_ = (m); orc_intra_pred(N, m_, nb[!!(k_intra_filter_flags[m_] & N)], 1, pred, N); \
+                            cost = orc_satd(N, N, cur, stride, pred, N); if (cost < acost) { acost = cost; amode = m_; } } while (0)
+    for (int m = 5; m < 35; m += 5) ORC_TRY_ANG(m);
+    for (int dist = 2; dist >= 1; dist--)
+    {
+        const int minus = amode - dist, plus = amode + dist;    /* both around the best BEFORE this round */
+        ORC_TRY_ANG(minus);
+        ORC_TRY_ANG(plus);
+    }
+#undef ORC_TRY_ANG
+    if (acost < icost) { icost = acost; imode = amode; }
+    *modeOut = imode;
+    return icost + penalty;
+}
+EXPORT void orc_lowres_intra_frame(const pixel* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty, int32_t* cost, int32_t* mode)
+{
+    for (int y = 0; y < heightInCU; y++)
+        for (int x = 0; x < widthInCU; x++)
+            cost[y * widthInCU + x] = orc_lowres_intra_cu(plane, stride, x, y, penalty, mode + y * widthInCU + x);
+}

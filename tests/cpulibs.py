@@ -208,6 +208,22 @@ class _Base:
                                               hshift, vshift, _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), _ptr(cost_tab, centre), _ptr(out))
         return int(out[0]), int(out[1]), int(c)
 
+    # ---- intra prediction (intrapred.cpp) and the lookahead's intra estimate (slicetype.cpp lowresIntraEstimate) ---------
+    def intra_filter(self, N, samples):
+        out = np.zeros(4 * N + 1, samples.dtype)
+        self._f("intra_filter", None)(N, _ptr(samples), _ptr(out))
+        return out
+
+    def intra_pred(self, N, mode, samples, bFilter):
+        out = np.zeros(N * N, samples.dtype)
+        self._f("intra_pred", None)(N, mode, _ptr(samples), int(bFilter), _ptr(out), C.c_ssize_t(N))
+        return out
+
+    def lowres_intra_cu(self, plane, origin, stride, cuX, cuY, penalty):
+        m = C.c_int32(0)
+        c = self._f("lowres_intra_cu")(_ptr(plane, origin), C.c_ssize_t(stride), cuX, cuY, penalty, C.byref(m))
+        return int(c), int(m.value)
+
     def bidir_satd(self, w, h, fenc, of, sf, ref0, o0, sr0, frac0, ref1, o1, sr1, frac1):
         return self._f("bidir_satd")(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref0, o0), C.c_ssize_t(sr0), frac0, _ptr(ref1, o1), C.c_ssize_t(sr1), frac1)
 
@@ -335,6 +351,11 @@ class Oracle(_Base):
                                           _ptr(ref1), C.c_ssize_t(sr1), _ptr(off1), _ptr(frac1), n, _ptr(cost))
         return cost
 
+    def lowres_intra_frame(self, plane, origin, stride, wcu, hcu, penalty):
+        cost = np.zeros(wcu * hcu, np.int32); mode = np.zeros(wcu * hcu, np.int32)
+        self._f("lowres_intra_frame", None)(_ptr(plane, origin), C.c_ssize_t(stride), wcu, hcu, penalty, _ptr(cost), _ptr(mode))
+        return cost, mode
+
     def blockop_batch(self, op, w, h, A, sa, offA, B, sb, offB, D, sd, offD):
         self._f("blockop_batch", None)(op, w, h, _ptr(A), C.c_ssize_t(sa), _ptr(offA), _ptr(B), C.c_ssize_t(sb), _ptr(offB),
                                        _ptr(D), C.c_ssize_t(sd), _ptr(offD), len(offA))
@@ -392,6 +413,11 @@ class Reference(_Base):
                                                 _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), merange, qp, _ptr(out))
         on = c >= 0
         return int(out[0]), int(out[1]), int(c if on else -1 - c), bool(on)
+
+    def intra_allangs(self, N, ref_pix, filt_pix, bLuma):
+        out = np.zeros(33 * N * N, ref_pix.dtype)
+        self.lib.ref_intra_allangs(N, _ptr(out), _ptr(ref_pix), _ptr(filt_pix), int(bLuma))
+        return out
 
     def mvcost_table(self, qp, radius):
         out = np.zeros(2 * radius + 1, np.uint16)

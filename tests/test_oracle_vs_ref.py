@@ -699,3 +699,46 @@ def test_bidir_satd(libs):
                     x = o.bidir_satd(w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, a0, ref1, 31 * stride + 40, stride, a1)
                     y = r.bidir_satd(w, h, fenc, 64 * 5 + 3, 64, ref, 20 * stride + 21, stride, a0, ref1, 31 * stride + 40, stride, a1)
                     assert x == y and x >= 0, (w, h, a0, a1)
+
+
+def test_intra_pred(libs):
+    """reference-sample smoothing and all 35 intra predictors, 4x4 .. 32x32, with and without edge filtering, vs the
+    reference's intrapred.cpp slots; the all-angles slot as a cross-check of the filter-flag table"""
+    o, r = libs
+    rng = np.random.default_rng(89)
+    flags = [0x38, 0x00] + ([0x38] + [0x30] * 6 + [0x20, 0x00, 0x20] + [0x30] * 6) * 2 + [0x38]
+    for N in (4, 8, 16, 32):
+        for kind in range(4):
+            if kind == 0: s = rng.integers(0, o.pmax + 1, 4 * N + 1).astype(o.pix)
+            elif kind == 1: s = np.full(4 * N + 1, o.pmax, o.pix)
+            elif kind == 2: s = (np.arange(4 * N + 1) % 2 * o.pmax).astype(o.pix)
+            else: s = np.clip(np.cumsum(rng.integers(-6, 7, 4 * N + 1)) + o.pmax // 2, 0, o.pmax).astype(o.pix)
+            f = o.intra_filter(N, s)
+            assert np.array_equal(f, r.intra_filter(N, s)), N
+            for mode in range(35):
+                for bf in (0, 1):
+                    for src in (s, f):
+                        assert np.array_equal(o.intra_pred(N, mode, src, bf), r.intra_pred(N, mode, src, bf)), (N, mode, bf)
+            allang = r.intra_allangs(N, s.copy(), f.copy(), 1)
+            for mode in range(2, 35):
+                want = o.intra_pred(N, mode, f if flags[mode] & N else s, 1).reshape(N, N)
+                got = allang[(mode - 2) * N * N:(mode - 1) * N * N].reshape(N, N)
+                assert np.array_equal(got if mode >= 18 else got.T, want), (N, mode)     # all_angs leaves horizontal modes transposed
+
+
+def test_lowres_intra_estimate(libs):
+    """the lookahead's intra cost / mode per 8x8 lowres CU: oracle vs lowresIntraEstimate's slot sequence on the reference table"""
+    o, r = libs
+    from frames import Geometry, make_plane, smooth_field
+    geo = Geometry(128, 64)
+    modes = set()
+    for seed, kind in ((1, "natural"), (2, "uniform"), (3, "smooth")):
+        P = smooth_field(geo, o.depth, seed, box=5) if kind == "smooth" else make_plane(geo, o.depth, seed, kind)
+        cw, ch = geo.coded()
+        for cy in range(ch // 8):
+            for cx in range(cw // 8):
+                a = o.lowres_intra_cu(P, geo.origin, geo.stride, cx, cy, 24)
+                b = r.lowres_intra_cu(P, geo.origin, geo.stride, cx, cy, 24)
+                assert a == b, (kind, cx, cy, a, b)
+                modes.add(a[1])
+    assert len(modes) > 12                                 # DC, planar and a spread of angular winners
