@@ -277,6 +277,15 @@ int x265b200_bidir_satd_batch(x265b200_ctx* ctx, int w, int h, const void* fenc,
                               const void* ref1, intptr_t stride1, const int32_t* off1, const int32_t* frac1,
                               int n, int32_t* cost, x265b200_stream stream);
 
+/* The lookahead's intra estimate (reference encoder/slicetype.cpp:755-864, LookaheadTLD::lowresIntraEstimate) for every 8x8
+ * CU of a lowres frame: neighbours taken from the plane itself (the plane must be padded, as lowres planes are), 1:2:1
+ * smoothing, DC / planar / the angular modes searched coarse to fine exactly as the reference does, 8x8 SATD.
+ * `plane` points at the picture's first sample.  cost[cuY * widthInCU + cuX] = the reference's fenc.intraCost (icost +
+ * penalty, penalty = intraPenalty + lowresPenalty), mode[..] = fenc.intraMode.  The per-frame sums and the AQ-weighted
+ * costs (slicetype.cpp:843-863) are reductions over this array and stay with the caller. */
+int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty,
+                                int32_t* cost, int32_t* mode, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

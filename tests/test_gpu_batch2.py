@@ -744,3 +744,27 @@ def test_bidir_satd_batch(depth):
         ctx.bidir_satd_batch(w, h, dF, geo.stride, dev(offF), dR0, geo.stride, dev(off0), dev(f0), dR1, geo1.stride, dev(off1), dev(f1), cost)
         assert np.array_equal(cost.cpu().numpy(), want), (w, h)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_lowres_intra_batch(depth):
+    """the lookahead's intra estimate (cost + mode per 8x8 lowres CU, all CUs of a frame in one launch) vs the oracle, which the
+    CPU suite pins to lowresIntraEstimate's slot sequence: natural, noise and smooth pictures, picture-edge CUs included"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane, smooth_field
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    cw, ch = geo.coded()
+    wcu, hcu = cw // 8, ch // 8
+    modes = set()
+    for seed, kind in ((1, "natural"), (2, "uniform"), (3, "smooth")):
+        P = smooth_field(geo, depth, seed, box=5) if kind == "smooth" else make_plane(geo, depth, seed, kind)
+        want_c, want_m = orc.lowres_intra_frame(P, geo.origin, geo.stride, wcu, hcu, 37)
+        cost = torch.full((wcu * hcu,), -1, dtype=torch.int32, device="cuda"); mode = torch.full((wcu * hcu,), -1, dtype=torch.int32, device="cuda")
+        ctx.lowres_intra_batch(dev(pix_view(P, depth)), geo.origin, geo.stride, wcu, hcu, 37, cost, mode)
+        assert np.array_equal(cost.cpu().numpy(), want_c), kind
+        assert np.array_equal(mode.cpu().numpy(), want_m), kind
+        modes |= set(want_m.tolist())
+    assert len(modes) > 12
+    ctx.check()

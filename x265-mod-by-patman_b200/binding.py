@@ -179,6 +179,10 @@ class Context:
         self._call("x265b200_bidir_satd_batch", w, h, _dp(fenc), _ss(sf), _dp(offF), _dp(ref0), _ss(sr0), _dp(off0), _dp(frac0),
                    _dp(ref1), _ss(sr1), _dp(off1), _dp(frac1), int(offF.numel()), _dp(cost), C.c_void_p(stream))
 
+    def lowres_intra_batch(self, plane, origin, stride, width_in_cu, height_in_cu, penalty, cost, mode, stream=0):
+        self._call("x265b200_lowres_intra_batch", _dp(plane, origin), _ss(stride), int(width_in_cu), int(height_in_cu), int(penalty),
+                   _dp(cost), _dp(mode), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

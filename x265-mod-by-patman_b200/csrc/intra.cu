@@ -1,0 +1,189 @@
+// intra.cu -- the lookahead's intra cost estimate per 8x8 lowres CU (reference encoder/slicetype.cpp:755-864,
+// LookaheadTLD::lowresIntraEstimate) on top of the intra predictors of common/intrapred.cpp:31-204.
+//
+// The reference evaluates DC, planar and then walks the angular modes coarse to fine (5, 10 .. 30; best +-2; best +-1),
+// one 8x8 prediction + SATD at a time.  A mode's cost does not depend on the walk, so here one warp owns a CU, every
+// lane costs one mode (all 35 of them: prediction samples are computed straight from the neighbour arrays in shared
+// memory, per 4x4 tile, and go into a scalar 4x4 Hadamard without ever forming the predicted block in memory), and
+// lane 0 then replays the reference's decision sequence on the 35 costs -- same order, same strict-less updates.
+#include "internal.h"
+
+namespace b200 {
+
+constexpr int IN_N = 8;                                  // X265_LOWRES_CU_SIZE, common.h:227
+constexpr int IN_WARPS = 4;
+constexpr int IN_COST_MAX = 1 << 28;                      // MotionEstimate::COST_MAX, motion.h:68
+
+__constant__ uint8_t c_intraFilterFlags[35] = {          // constants.cpp:561-567
+    0x38, 0x00,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38 };
+__constant__ int c_intraAngle[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };     // intrapred.cpp:122
+__constant__ int c_intraInvAngle[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };                           // intrapred.cpp:123
+
+// neighbour j as a horizontal mode sees it: above and left exchanged (intrapred.cpp:111-119)
+__device__ __forceinline__ int intra_nb(const uint16_t* s, int hor, int j)
+{
+    if (!hor || j == 0) return s[j];
+    return j <= 2 * IN_N ? s[2 * IN_N + j] : s[j - 2 * IN_N];
+}
+// reference sample i of the angular rule (intrapred.cpp:147-171): the above row, extended to the left by the left column
+// projected along the inverse angle when the angle is negative
+__device__ __forceinline__ int intra_ref(const uint16_t* s, int hor, int angleOffset, int i)
+{
+    if (i >= -1) return intra_nb(s, hor, i + 1);
+    const int k = -2 - i;
+    return intra_nb(s, hor, 2 * IN_N + ((128 + (k + 1) * c_intraInvAngle[-angleOffset - 1]) >> 8));
+}
+
+// predicted sample (r, c) of `mode` for an 8x8 block with edge filtering on (bFilter = cuSize <= 16)
+struct IntraMode
+{
+    int mode, hor, angleOffset, angle, dc;
+    const uint16_t* s;                                   // unfiltered or smoothed neighbours, as g_intraFilterFlags says
+    __device__ int px(int r, int c, int pmax) const
+    {
+        if (mode == 0)      // planar, intrapred.cpp:87-100
+            return ((IN_N - 1 - c) * s[2 * IN_N + 1 + r] + (IN_N - 1 - r) * s[1 + c] + (c + 1) * s[1 + IN_N] + (r + 1) * s[2 * IN_N + 1 + IN_N] + IN_N) >> 4;
+        if (mode == 1)
+        {                   // DC + edge smoothing, intrapred.cpp:53-85
+            if (!r && !c) return (s[1] + s[2 * IN_N + 1] + 2 * dc + 2) >> 2;
+            if (!r) return (s[1 + c] + 3 * dc + 2) >> 2;
+            if (!c) return (s[2 * IN_N + 1 + r] + 3 * dc + 2) >> 2;
+            return dc;
+        }
+        const int y = hor ? c : r, x = hor ? r : c;       // position in the un-flipped (vertical) frame
+        if (!angle)
+        {
+            if (x) return intra_nb(s, hor, 1 + x);
+            int v = (int)(int16_t)(intra_nb(s, hor, 1) + ((intra_nb(s, hor, 2 * IN_N + 1 + y) - intra_nb(s, hor, 0)) >> 1));
+            return min(max(v, 0), pmax);
+        }
+        const int sum = (y + 1) * angle, off = sum >> 5, frac = sum & 31;
+        int v = intra_ref(s, hor, angleOffset, off + x);
+        if (frac) v = ((32 - frac) * v + frac * intra_ref(s, hor, angleOffset, off + x + 1) + 16) >> 5;
+        return v;
+    }
+};
+
+// sum of |H4 d H4^T| over a 4x4 tile of differences (twice the reference's satd_4x4, which halves an always even sum)
+__device__ __forceinline__ int hadamard4x4_abs(int (&d)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        int a0 = d[4 * r] + d[4 * r + 1], a1 = d[4 * r] - d[4 * r + 1], a2 = d[4 * r + 2] + d[4 * r + 3], a3 = d[4 * r + 2] - d[4 * r + 3];
+        d[4 * r] = a0 + a2; d[4 * r + 1] = a1 + a3; d[4 * r + 2] = a0 - a2; d[4 * r + 3] = a1 - a3;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+    {
+        int a0 = d[c] + d[4 + c], a1 = d[c] - d[4 + c], a2 = d[8 + c] + d[12 + c], a3 = d[8 + c] - d[12 + c];
+        sum += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+    }
+    return sum;
+}
+
+template<typename PIX>
+__global__ void __launch_bounds__(IN_WARPS * 32)
+lowres_intra_kernel(const PIX* __restrict__ plane, intptr_t stride, int widthInCU, int ncu, int penalty, int pmax,
+                    int32_t* __restrict__ costOut, int32_t* __restrict__ modeOut)
+{
+    __shared__ uint16_t nb[IN_WARPS][2][4 * IN_N + 1 + 3];
+    __shared__ uint16_t fencS[IN_WARPS][IN_N * IN_N];
+    __shared__ int costs[IN_WARPS][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cu = blockIdx.x * IN_WARPS + warp;
+    if (cu >= ncu) return;                               // whole warps leave; only __syncwarp below
+    const int cuY = cu / widthInCU, cuX = cu - cuY * widthInCU;
+    const PIX* cur = plane + (intptr_t)IN_N * cuY * stride + IN_N * cuX;
+    const PIX* p = cur - stride - 1;
+    uint16_t* s = nb[warp][0];
+    uint16_t* f = nb[warp][1];
+    // reference samples: top-left + 16 above, 16 left (slicetype.cpp:789-792)
+    if (lane <= 2 * IN_N) s[lane] = p[lane];
+    if (lane >= 1 && lane <= 2 * IN_N) s[2 * IN_N + lane] = p[(intptr_t)lane * stride];
+    fencS[warp][lane] = cur[(intptr_t)(lane >> 3) * stride + (lane & 7)];
+    fencS[warp][32 + lane] = cur[(intptr_t)(4 + (lane >> 3)) * stride + (lane & 7)];
+    __syncwarp();
+    // 1:2:1 smoothing, intrapred.cpp:31-51
+    for (int i = lane; i <= 4 * IN_N; i += 32)
+    {
+        int v;
+        if (i == 0) v = (2 * s[0] + s[1] + s[2 * IN_N + 1] + 2) >> 2;
+        else if (i == 2 * IN_N || i == 4 * IN_N) v = s[i];
+        else if (i == 2 * IN_N + 1) v = (2 * s[i] + s[0] + s[i + 1] + 2) >> 2;
+        else v = (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
+        f[i] = (uint16_t)v;
+    }
+    int dc = IN_N;
+    for (int i = 0; i < IN_N; i++) dc += s[1 + i] + s[2 * IN_N + 1 + i];
+    dc /= 2 * IN_N;
+    __syncwarp();
+
+    for (int mode = lane; mode < 35; mode += 32)
+    {
+        IntraMode m;
+        m.mode = mode; m.dc = dc;
+        m.hor = mode >= 2 && mode < 18;
+        m.angleOffset = mode < 2 ? 0 : (m.hor ? 10 - mode : mode - 26);
+        m.angle = c_intraAngle[8 + m.angleOffset];
+        // DC reads the unfiltered samples, planar the smoothed ones (cuSize >= 8), angular modes follow the flag table
+        m.s = mode == 1 ? s : mode == 0 ? f : ((c_intraFilterFlags[mode] & IN_N) ? f : s);
+        int sum = 0;
+#pragma unroll 1
+        for (int t = 0; t < 4; t++)
+        {
+            const int r0 = (t >> 1) * 4, c0 = (t & 1) * 4;
+            int d[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                d[i] = (int)fencS[warp][(r0 + (i >> 2)) * IN_N + c0 + (i & 3)] - m.px(r0 + (i >> 2), c0 + (i & 3), pmax);
+            sum += hadamard4x4_abs(d);
+        }
+        costs[warp][mode] = sum >> 1;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {   // slicetype.cpp:796-841
+        const int* c = costs[warp];
+        int icost = IN_COST_MAX, imode = 0;
+        if (c[1] < icost) { icost = c[1]; imode = 1; }
+        if (c[0] < icost) { icost = c[0]; imode = 0; }
+        int acost = IN_COST_MAX, amode = 4;
+        for (int mode = 5; mode < 35; mode += 5)
+            if (c[mode] < acost) { acost = c[mode]; amode = mode; }
+        for (int dist = 2; dist >= 1; dist--)
+        {
+            const int minus = amode - dist, plus = amode + dist;    // both around the best before this round
+            if (c[minus] < acost) { acost = c[minus]; amode = minus; }
+            if (c[plus] < acost) { acost = c[plus]; amode = plus; }
+        }
+        if (acost < icost) { icost = acost; imode = amode; }
+        costOut[cu] = icost + penalty;
+        modeOut[cu] = imode;
+    }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty,
+                                           int32_t* cost, int32_t* mode, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (widthInCU < 0 || heightInCU < 0 || (long long)widthInCU * heightInCU > 0x7fffffff) return fail(ctx, X265B200_ERR_ARG, "lowres_intra: bad geometry");
+    const int ncu = widthInCU * heightInCU;
+    if (ncu == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pmax = (1 << ctx->depth) - 1;
+    if (ctx->pixbytes == 1)
+        lowres_intra_kernel<uint8_t><<<ceil_div(ncu, IN_WARPS), IN_WARPS * 32, 0, st>>>((const uint8_t*)plane, stride, widthInCU, ncu, penalty, pmax, cost, mode);
+    else
+        lowres_intra_kernel<uint16_t><<<ceil_div(ncu, IN_WARPS), IN_WARPS * 32, 0, st>>>((const uint16_t*)plane, stride, widthInCU, ncu, penalty, pmax, cost, mode);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
