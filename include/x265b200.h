@@ -286,6 +286,13 @@ int x265b200_bidir_satd_batch(x265b200_ctx* ctx, int w, int h, const void* fenc,
 int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty,
                                 int32_t* cost, int32_t* mode, x265b200_stream stream);
 
+/* All 35 luma intra predictions of n TUs of N x N (4, 8, 16, 32) as the analysis forms them before costing the modes
+ * (reference encoder/search.cpp:1703-1727 on common/intrapred.cpp): neighbours[i * (4N+1) ..] = top-left, 2N above, 2N left
+ * (unfiltered; the 1:2:1 smoothed copy is made on chip), DC with edge smoothing for N <= 16, planar from the smoothed
+ * samples for N >= 8, angular modes per g_intraFilterFlags.  dst[(i * 35 + mode) * N * N ..] = the N x N prediction, every
+ * mode in picture orientation.  Feed dst to x265b200_pixelcmp_batch (sa8d / satd) for the mode costs. */
+int x265b200_intra_pred_batch(x265b200_ctx* ctx, int N, const void* neighbours, int n, void* dst, x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,

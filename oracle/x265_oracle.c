@@ -1556,3 +1556,18 @@ EXPORT void orc_lowres_intra_frame(const pixel* plane, intptr_t stride, int widt
         for (int x = 0; x < widthInCU; x++)
             cost[y * widthInCU + x] = orc_lowres_intra_cu(plane, stride, x, y, penalty, mode + y * widthInCU + x);
 }
+
+/* All 35 luma predictions of one TU the way the analysis forms them (encoder/search.cpp:1703-1727): DC from the unfiltered
+ * neighbours with edge smoothing for N <= 16, planar from the smoothed ones for N >= 8, the angular modes from smoothed or
+ * unfiltered neighbours per g_intraFilterFlags with edge filtering for N <= 16.  dst: 35 blocks of N x N, mode-major,
+ * every mode in picture orientation (the reference's all-angles slot leaves modes < 18 transposed and compares them with a
+ * transposed fenc; the Hadamard costs are the same). */
+EXPORT void orc_intra_pred_all(int N, const pixel* s, pixel* dst)
+{
+    pixel f[4 * 32 + 1];
+    orc_intra_filter(N, s, f);
+    orc_intra_pred(N, 1, s, N <= 16, dst + N * N, N);
+    orc_intra_pred(N, 0, N >= 8 ? f : s, 0, dst, N);
+    for (int m = 2; m < 35; m++)
+        orc_intra_pred(N, m, (k_intra_filter_flags[m] & N) ? f : s, N <= 16, dst + m * N * N, N);
+}

@@ -219,6 +219,11 @@ class _Base:
         self._f("intra_pred", None)(N, mode, _ptr(samples), int(bFilter), _ptr(out), C.c_ssize_t(N))
         return out
 
+    def intra_pred_all(self, N, samples):
+        out = np.zeros(35 * N * N, samples.dtype)
+        self._f("intra_pred_all", None)(N, _ptr(samples), _ptr(out))
+        return out
+
     def lowres_intra_cu(self, plane, origin, stride, cuX, cuY, penalty):
         m = C.c_int32(0)
         c = self._f("lowres_intra_cu")(_ptr(plane, origin), C.c_ssize_t(stride), cuX, cuY, penalty, C.byref(m))

@@ -768,3 +768,38 @@ def test_lowres_intra_batch(depth):
         modes |= set(want_m.tolist())
     assert len(modes) > 12
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_intra_pred_batch(depth):
+    """all 35 luma intra predictions of a batch of TUs (4x4 .. 32x32) vs the oracle composite (pinned to intrapred.cpp's slots
+    and the analysis' filter rules by the CPU suite), then the mode costs the analysis takes from them: sa8d of every
+    prediction against the TU's source block through the batched metric entry"""
+    import torch
+    from gpulib import context
+    from cpulibs import OP_SA8D
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(1000 + depth)
+    for N in (4, 8, 16, 32):
+        n, L = 14, 4 * N + 1
+        nbs = np.zeros((n, L), orc.pix)
+        for i in range(n):
+            k = i % 4
+            if k == 0: nbs[i] = rng.integers(0, orc.pmax + 1, L)
+            elif k == 1: nbs[i] = np.clip(np.cumsum(rng.integers(-9, 10, L)) + orc.pmax // 2, 0, orc.pmax)
+            elif k == 2: nbs[i] = (np.arange(L) % 2) * orc.pmax
+            else: nbs[i] = orc.pmax if i % 8 == 3 else 0
+        want = np.concatenate([orc.intra_pred_all(N, nbs[i]) for i in range(n)])
+        dst = torch.zeros(n * 35 * N * N, dtype=torch.uint8 if depth == 8 else torch.int16, device="cuda")
+        ctx.intra_pred_batch(N, dev(pix_view(nbs.ravel(), depth)), n, dst)
+        got = dst.cpu().numpy()
+        assert np.array_equal(got.view(np.uint16) if depth > 8 else got, want), N
+        if N >= 8:
+            fenc = rng.integers(0, orc.pmax + 1, n * N * N).astype(orc.pix)
+            offA = np.repeat(np.arange(n) * N * N, 35).astype(np.int32)
+            offB = (np.arange(n * 35) * N * N).astype(np.int32)
+            cost = torch.zeros(n * 35, dtype=torch.int32, device="cuda")
+            ctx.pixelcmp_batch(OP_SA8D, N, N, dev(pix_view(fenc, depth)), N, dst, N, dev(offA), dev(offB), cost)
+            ref = np.array([orc.sa8d(N, N, fenc, int(a), N, want, int(b), N) for a, b in zip(offA, offB)], np.int32)
+            assert np.array_equal(cost.cpu().numpy(), ref), (N, "sa8d")
+    ctx.check()

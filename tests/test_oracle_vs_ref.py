@@ -724,6 +724,14 @@ def test_intra_pred(libs):
                 want = o.intra_pred(N, mode, f if flags[mode] & N else s, 1).reshape(N, N)
                 got = allang[(mode - 2) * N * N:(mode - 1) * N * N].reshape(N, N)
                 assert np.array_equal(got if mode >= 18 else got.T, want), (N, mode)     # all_angs leaves horizontal modes transposed
+            # the analysis' 35 predictions of a TU (search.cpp:1703-1727) from the reference's slots vs the oracle's composite
+            every = o.intra_pred_all(N, s).reshape(35, N, N)
+            assert np.array_equal(every[1].ravel(), r.intra_pred(N, 1, s, int(N <= 16)))
+            assert np.array_equal(every[0].ravel(), r.intra_pred(N, 0, f if N >= 8 else s, 0))
+            allang = r.intra_allangs(N, s.copy(), f.copy(), int(N <= 16))
+            for mode in range(2, 35):
+                got = allang[(mode - 2) * N * N:(mode - 1) * N * N].reshape(N, N)
+                assert np.array_equal(got if mode >= 18 else got.T, every[mode]), (N, mode)
 
 
 def test_lowres_intra_estimate(libs):

@@ -183,6 +183,9 @@ class Context:
         self._call("x265b200_lowres_intra_batch", _dp(plane, origin), _ss(stride), int(width_in_cu), int(height_in_cu), int(penalty),
                    _dp(cost), _dp(mode), C.c_void_p(stream))
 
+    def intra_pred_batch(self, N, neighbours, n, dst, stream=0):
+        self._call("x265b200_intra_pred_batch", int(N), _dp(neighbours), int(n), _dp(dst), C.c_void_p(stream))
+
     def weight_batch(self, sp, src, ss, dst, ds, width, height, w0, rnd, shift, offset, stream=0):
         self._call("x265b200_weight_batch", int(sp), _dp(src), _ss(ss), _dp(dst), _ss(ds), width, height, w0, rnd, shift, offset, C.c_void_p(stream))
 

@@ -167,6 +167,83 @@ lowres_intra_kernel(const PIX* __restrict__ plane, intptr_t stride, int widthInC
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// All 35 luma predictions of a TU, N = 4 .. 32, the way the analysis forms them before costing the modes with sa8d
+// (reference encoder/search.cpp:1703-1727): same per-sample rules as above with N as a run-time value.  One CTA per TU:
+// neighbours and their smoothed copy in shared memory, the threads sweep the 35 * N * N output samples.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int intra_nb_n(const uint16_t* s, int N, int hor, int j)
+{
+    if (!hor || j == 0) return s[j];
+    return j <= 2 * N ? s[2 * N + j] : s[j - 2 * N];
+}
+__device__ __forceinline__ int intra_ref_n(const uint16_t* s, int N, int hor, int angleOffset, int i)
+{
+    if (i >= -1) return intra_nb_n(s, N, hor, i + 1);
+    const int k = -2 - i;
+    return intra_nb_n(s, N, hor, 2 * N + ((128 + (k + 1) * c_intraInvAngle[-angleOffset - 1]) >> 8));
+}
+__device__ int intra_px_n(const uint16_t* s, int N, int lgN, int mode, int bFilter, int dc, int r, int c, int pmax)
+{
+    if (mode == 0)
+        return ((N - 1 - c) * s[2 * N + 1 + r] + (N - 1 - r) * s[1 + c] + (c + 1) * s[1 + N] + (r + 1) * s[3 * N + 1] + N) >> (lgN + 1);
+    if (mode == 1)
+    {
+        if (!bFilter) return dc;
+        if (!r && !c) return (s[1] + s[2 * N + 1] + 2 * dc + 2) >> 2;
+        if (!r) return (s[1 + c] + 3 * dc + 2) >> 2;
+        if (!c) return (s[2 * N + 1 + r] + 3 * dc + 2) >> 2;
+        return dc;
+    }
+    const int hor = mode < 18;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = c_intraAngle[8 + angleOffset];
+    const int y = hor ? c : r, x = hor ? r : c;
+    if (!angle)
+    {
+        if (x || !bFilter) return intra_nb_n(s, N, hor, 1 + x);
+        int v = (int)(int16_t)(intra_nb_n(s, N, hor, 1) + ((intra_nb_n(s, N, hor, 2 * N + 1 + y) - intra_nb_n(s, N, hor, 0)) >> 1));
+        return min(max(v, 0), pmax);
+    }
+    const int sum = (y + 1) * angle, off = sum >> 5, frac = sum & 31;
+    int v = intra_ref_n(s, N, hor, angleOffset, off + x);
+    if (frac) v = ((32 - frac) * v + frac * intra_ref_n(s, N, hor, angleOffset, off + x + 1) + 16) >> 5;
+    return v;
+}
+
+template<typename PIX>
+__global__ void __launch_bounds__(256)
+intra_pred_all_kernel(const PIX* __restrict__ neighbours, int N, int lgN, int pmax, PIX* __restrict__ dst)
+{
+    __shared__ uint16_t s[4 * 32 + 1 + 3], f[4 * 32 + 1 + 3];
+    const int tu = blockIdx.x, L = 4 * N + 1;
+    const PIX* nb = neighbours + (size_t)tu * L;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s[i] = nb[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x)
+    {   // intrapred.cpp:31-51
+        int v;
+        if (i == 0) v = (2 * s[0] + s[1] + s[2 * N + 1] + 2) >> 2;
+        else if (i == 2 * N || i == 4 * N) v = s[i];
+        else if (i == 2 * N + 1) v = (2 * s[i] + s[0] + s[i + 1] + 2) >> 2;
+        else v = (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
+        f[i] = (uint16_t)v;
+    }
+    int dc = N;
+    for (int i = 0; i < N; i++) dc += s[1 + i] + s[2 * N + 1 + i];
+    dc /= 2 * N;
+    __syncthreads();
+    const int bFilter = N <= 16, NN = N * N;
+    PIX* out = dst + (size_t)tu * 35 * NN;
+    for (int o = threadIdx.x; o < 35 * NN; o += blockDim.x)
+    {
+        const int mode = o >> (2 * lgN), rc = o & (NN - 1), r = rc >> lgN, c = rc & (N - 1);
+        const uint16_t* src = mode == 1 ? s : mode == 0 ? (N >= 8 ? f : s) : ((c_intraFilterFlags[mode] & N) ? f : s);
+        out[o] = (PIX)intra_px_n(src, N, lgN, mode, bFilter, dc, r, c, pmax);
+    }
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -184,6 +261,19 @@ extern "C" int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane,
         lowres_intra_kernel<uint8_t><<<ceil_div(ncu, IN_WARPS), IN_WARPS * 32, 0, st>>>((const uint8_t*)plane, stride, widthInCU, ncu, penalty, pmax, cost, mode);
     else
         lowres_intra_kernel<uint16_t><<<ceil_div(ncu, IN_WARPS), IN_WARPS * 32, 0, st>>>((const uint16_t*)plane, stride, widthInCU, ncu, penalty, pmax, cost, mode);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
+
+extern "C" int x265b200_intra_pred_batch(x265b200_ctx* ctx, int N, const void* neighbours, int n, void* dst, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if ((N != 4 && N != 8 && N != 16 && N != 32) || n < 0) return fail(ctx, X265B200_ERR_ARG, "intra_pred: N must be 4, 8, 16 or 32");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lgN = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5, pmax = (1 << ctx->depth) - 1;
+    if (ctx->pixbytes == 1) intra_pred_all_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t*)neighbours, N, lgN, pmax, (uint8_t*)dst);
+    else intra_pred_all_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t*)neighbours, N, lgN, pmax, (uint16_t*)dst);
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }
