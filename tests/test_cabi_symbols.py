@@ -37,3 +37,14 @@ def test_product_does_not_reference_oracle():
                 assert "x265_oracle" not in text and "liboracle" not in text and "cpulibs" not in text, os.path.join(dp, f)
     out = os.popen("ldd %s" % pkg.LIB_PATH).read()
     assert "oracle" not in out and "x265ref" not in out
+
+
+def test_docs_quote_the_current_entry_point_count():
+    """README / DESIGN / INTEGRATION state how many C entry points the header declares; keep them honest"""
+    import re
+    n = len(pkg.declared_symbols())
+    repo = os.path.dirname(os.path.dirname(os.path.dirname(pkg.LIB_PATH)))
+    for doc in ("README.md", "DESIGN.md", "INTEGRATION.md"):
+        text = open(os.path.join(repo, doc)).read()
+        counts = [int(m) for m in re.findall(r"(\d+) entry points", text)]
+        assert counts and all(c == n for c in counts), (doc, counts, n)

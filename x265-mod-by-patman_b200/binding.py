@@ -30,7 +30,7 @@ def declared_symbols():
     """every function name include/x265b200.h declares"""
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(x265b200_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(x265b200_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def load_library():
