@@ -1256,11 +1256,156 @@ static void me_star_search(const me_ctx* c, const int32_t* range, int merange, i
     *bx = b.x; *by = b.y; *bcost = b.cost;
 }
 
-/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_STAR_SEARCH 3, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
+/* Uneven multi-hexagon search (motion.cpp:1142-1324, from x264): small diamonds around the predictor, the zero vector and
+ * the running best; an early-termination ladder driven by SAD thresholds scaled by the PU height (sizeScale = H*H >> 4,
+ * motion.cpp:124-152); a cross whose reach adapts to how much the neighbour vectors disagree; a 5x5 corner check; rings
+ * of the 16-point hexagon at radius i = 1 .. merange/4; and finally the plain hexagon search from wherever that ended.
+ * `x4` candidates are judged around a fixed origin with only their row range-checked; single candidates of the cross
+ * are checked on the side they move to.  Written with small helpers instead of the reference's macro cascade. */
+typedef struct { const me_ctx* c; const int32_t* range; int x, y, cost; } me_umh_t;
+static void umh_try(me_umh_t* u, int x, int y)                 /* COST_MV */
+{
+    int cost = me_fpel(u->c, x, y);
+    if (cost < u->cost) { u->cost = cost; u->x = x; u->y = y; }
+}
+static void umh_x4(me_umh_t* u, int ox, int oy, const int (*d)[2]) /* COST_MV_X4 around (ox, oy) */
+{
+    for (int k = 0; k < 4; k++)
+    {
+        int y = oy + d[k][1];
+        if (y < u->range[1] || y > u->range[3]) continue;
+        umh_try(u, ox + d[k][0], y);
+    }
+}
+static void umh_cross(me_umh_t* u, int ox, int oy, int start, int x_max, int y_max)   /* CROSS, motion.cpp:359-385 */
+{
+    const int32_t* r = u->range;
+    int i = start;
+    int roomx = r[2] - ox < ox - r[0] ? r[2] - ox : ox - r[0];
+    if (x_max <= roomx)
+        for (; i < x_max - 2; i += 4)
+        {
+            const int d[4][2] = { {i, 0}, {-i, 0}, {i + 2, 0}, {-i - 2, 0} };
+            umh_x4(u, ox, oy, d);
+        }
+    for (; i < x_max; i += 2)
+    {
+        if (ox + i <= r[2]) umh_try(u, ox + i, oy);
+        if (ox - i >= r[0]) umh_try(u, ox - i, oy);
+    }
+    i = start;
+    int roomy = r[3] - oy < oy - r[1] ? r[3] - oy : oy - r[1];
+    if (y_max <= roomy)
+        for (; i < y_max - 2; i += 4)
+        {
+            const int d[4][2] = { {0, i}, {0, -i}, {0, i + 2}, {0, -i - 2} };
+            umh_x4(u, ox, oy, d);
+        }
+    for (; i < y_max; i += 2)
+    {
+        if (oy + i <= r[3]) umh_try(u, ox, oy + i);
+        if (oy - i >= r[1]) umh_try(u, ox, oy - i);
+    }
+}
+static const int k_hex4[16][2] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4, -2}, {-4, -1}, {4, -1},
+                                   {-4, 0}, {4, 0}, {-4, 1}, {4, 1}, {-4, 2}, {4, 2}, {-2, 3}, {2, 3} };   /* motion.cpp:68-74 */
+static const int k_dia1[4][2] = { {0, -1}, {0, 1}, {-1, 0}, {1, 0} };
+/* returns 1 when the search goes on into the hexagon stage (me_hex2), 0 when it ended inside UMH */
+static int me_umh_search(const me_ctx* c, const int32_t* range, int* merangeIO, int pmvx, int pmvy /* full pel */,
+                         const int32_t* qmvp, int numCand, const int32_t* mvc, int* bx, int* by, int* bcost)
+{
+    me_umh_t u = { c, range, *bx, *by, *bcost };
+    int merange = *merangeIO;
+    const int scale = (c->h * c->h) >> 4;
+#define UMH_THRESH(v) (u.cost < (((v) >> 4) * scale))
+    int cross_start = 1;
+    const int ucost1 = u.cost;
+    umh_x4(&u, pmvx, pmvy, k_dia1);
+    if (pmvx | pmvy) umh_x4(&u, 0, 0, k_dia1);
+    const int ucost2 = u.cost;
+    if ((u.x | u.y) && (u.x != pmvx || u.y != pmvy)) umh_x4(&u, u.x, u.y, k_dia1);
+    if (u.cost == ucost2) cross_start = 3;
+
+    int ox = u.x, oy = u.y;
+    if (u.cost == ucost2 && UMH_THRESH(2000))
+    {
+        static const int oct_a[4][2] = { {0, -2}, {-1, -1}, {1, -1}, {-2, 0} }, oct_b[4][2] = { {2, 0}, {-1, 1}, {1, 1}, {0, 2} };
+        umh_x4(&u, ox, oy, oct_a); umh_x4(&u, ox, oy, oct_b);
+        if (u.cost == ucost1 && UMH_THRESH(500)) { *bx = u.x; *by = u.y; *bcost = u.cost; return 0; }
+        if (u.cost == ucost2)
+        {
+            static const int k2a[4][2] = { {-1, -2}, {1, -2}, {-2, -1}, {2, -1} }, k2b[4][2] = { {-2, 1}, {2, 1}, {-1, 2}, {1, 2} };
+            const int reach = (int16_t)(merange >> 1) | 1;
+            umh_cross(&u, ox, oy, 3, reach, reach);
+            umh_x4(&u, ox, oy, k2a); umh_x4(&u, ox, oy, k2b);
+            if (u.cost == ucost2) { *bx = u.x; *by = u.y; *bcost = u.cost; return 0; }
+            cross_start = reach + 2;
+        }
+    }
+    if (numCand)
+    {   /* search range scaled by the disagreement of the predictors and by how good the match already is */
+        static const uint8_t range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };
+        const int is64 = c->w == 64 && c->h == 64;
+        int mvd, denom = 1;
+        if (numCand == 1)
+            mvd = is64 ? 25 : iabs(qmvp[0] - mvc[0]) + iabs(qmvp[1] - mvc[1]);
+        else
+        {
+            denom = numCand - 1;
+            mvd = 0;
+            if (!is64) { mvd = iabs(qmvp[0] - mvc[0]) + iabs(qmvp[1] - mvc[1]); denom++; }
+            for (int i = 0; i < numCand - 1; i++)
+                mvd += iabs(mvc[2 * i] - mvc[2 * i + 2]) + iabs(mvc[2 * i + 1] - mvc[2 * i + 3]);
+        }
+        const int sad_ctx = UMH_THRESH(1000) ? 0 : UMH_THRESH(2000) ? 1 : UMH_THRESH(4000) ? 2 : 3;
+        const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+        merange = (merange * range_mul[mvd_ctx][sad_ctx]) >> 2;
+    }
+    {   /* the cross and the corners stay centred where the diamonds ended (the reference's FIXME) */
+        static const int corners[4][2] = { {-2, -2}, {-2, 2}, {2, -2}, {2, 2} };
+        umh_cross(&u, ox, oy, cross_start, merange, merange >> 1);
+        umh_x4(&u, ox, oy, corners);
+    }
+    /* hexagon grid around the new best */
+    ox = u.x; oy = u.y;
+    uint16_t i = 1;
+    do
+    {
+        int room = range[2] - ox;
+        if (ox - range[0] < room) room = ox - range[0];
+        if (range[3] - oy < room) room = range[3] - oy;
+        if (oy - range[1] < room) room = oy - range[1];
+        if (4 * i > room)
+        {
+            for (int j = 0; j < 16; j++)
+            {
+                int x = ox + k_hex4[j][0] * i, y = oy + k_hex4[j][1] * i;
+                if (me_in_range(range, x, y)) umh_try(&u, x, y);
+            }
+        }
+        else
+        {   /* whole ring inside the window: all sixteen judged against the best before the ring, first-best wins */
+            int best = u.cost, dir = -1;
+            for (int j = 0; j < 16; j++)
+            {
+                int x = ox + k_hex4[j][0] * i, y = oy + k_hex4[j][1] * i;
+                int cost = orc_sad(c->w, c->h, c->fenc, c->sf, c->fref + x + (intptr_t)y * c->sr, c->sr) + c->cx[x * 4] + c->cy[y * 4];
+                if (cost < best) { best = cost; dir = j; }
+            }
+            if (dir >= 0) { u.cost = best; u.x = ox + k_hex4[dir][0] * i; u.y = oy + k_hex4[dir][1] * i; }
+        }
+    }
+    while (++i <= merange >> 2);
+#undef UMH_THRESH
+    *bx = u.x; *by = u.y; *bcost = u.cost; *merangeIO = merange;
+    return me_in_range(range, u.x, u.y);
+}
+
+/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_UMH_SEARCH 2, X265_STAR_SEARCH 3, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
 static int me_estimate(me_ctx cc, int method, int merange, int subme, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
                        const uint16_t* costTab, int32_t* outQMv)
 {
-    if (method != 0 && method != 1 && method != 3 && method != 5) return -1;
+    if (method != 0 && method != 1 && method != 2 && method != 3 && method != 5) return -1;
     const me_ctx c = cc;
     const int w = c.w, h = c.h; const pixel* fenc = c.fenc; const pixel* fref = c.fref; const intptr_t sf = c.sf, sr = c.sr;
     const int lowres = c.hpel[0] != 0;
@@ -1300,7 +1445,13 @@ static int me_estimate(me_ctx cc, int method, int merange, int subme, const int3
         outQMv[0] = bmvx * 4; outQMv[1] = bmvy * 4;
         return me_mvcost(&c, bmvx * 4, bmvy * 4);
     }
-    if (method == 0) me_dia_search(&c, range, merange, &bmvx, &bmvy, &bcost);
+    if (method == 2)
+    {   /* :1142-1324, falling through to the hexagon search when it ends inside the window */
+        int mr = merange;
+        if (me_umh_search(&c, range, &mr, (pmvx + 2) >> 2, (pmvy + 2) >> 2, qmvp, numCand, mvc, &bmvx, &bmvy, &bcost))
+            me_hex_search(&c, range, mr, &bmvx, &bmvy, &bcost);
+    }
+    else if (method == 0) me_dia_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 1) me_hex_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 3) me_star_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else

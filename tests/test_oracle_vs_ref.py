@@ -537,7 +537,7 @@ def test_motion_estimate(libs):
         nc = int(rng.integers(0, 5))
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (nc, 2))
         if nc > 1: mvc[1] = qmvp
-        for method in (5, 1, 0, 3):                       # X265_FULL_SEARCH, X265_HEX_SEARCH, X265_DIA_SEARCH, X265_STAR_SEARCH
+        for method in (5, 1, 0, 3, 2):                    # X265_FULL_SEARCH, X265_HEX_SEARCH, X265_DIA_SEARCH, X265_STAR_SEARCH, X265_UMH_SEARCH
             merange = m if method == 5 else int(rng.integers(1, 40))
             a = o.motion_estimate_full(subme, w, h, fen, of, geo.stride, ref, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD,
                                        method, merange)
@@ -546,7 +546,7 @@ def test_motion_estimate(libs):
             nonzero_exit += a[2] > 0
             if method != 5:
                 moved += max(abs(a[0] - int(np.clip(qmvp[0], 4 * minx, 4 * maxx))), abs(a[1] - int(np.clip(qmvp[1], 4 * miny, 4 * maxy)))) >= 16
-    assert nonzero_exit > 400 and moved > 60              # dozens of pattern walks ended four or more pels from their start
+    assert nonzero_exit > 500 and moved > 80              # dozens of pattern walks ended four or more pels from their start
 
 
 def test_motion_estimate_star_far(libs):
@@ -577,6 +577,9 @@ def test_motion_estimate_star_far(libs):
         a = o.motion_estimate_full(2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD, 3, merange)
         b = r.motion_estimate(3, 2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
         assert a == b, (case, w, h, a, b)
+        u = o.motion_estimate_full(2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD, 2, merange)
+        v = r.motion_estimate(2, 2, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+        assert u == v, ("umh", case, w, h, u, v)
         far += max(abs(a[0] - qmvp[0]), abs(a[1] - qmvp[1])) >= 40
     assert far > 30
 
@@ -750,3 +753,36 @@ def test_lowres_intra_estimate(libs):
                 assert a == b, (kind, cx, cy, a, b)
                 modes.add(a[1])
     assert len(modes) > 12                                 # DC, planar and a spread of angular winners
+
+
+def test_motion_estimate_umh_ladder(libs):
+    """UMH's early-termination ladder and adaptive cross: predictors at / near the true displacement and noise levels that
+    put the start cost on either side of the 500 / 1000 / 2000 / 4000 thresholds (scaled by the PU height)"""
+    o, r = libs
+    from frames import Geometry, smooth_field
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(97)
+    S = smooth_field(geo, o.depth, 131, box=11)
+    RAD = 2048
+    cw, ch = geo.coded()
+    for case in range(320):
+        dx, dy = int(rng.integers(-9, 10)), int(rng.integers(-7, 8))
+        amp = (0, 1, 2, 3, 5, 8, 12, 20)[case % 8] << (o.depth - 8)
+        S2 = np.clip(np.roll(S, dy * geo.stride + dx).astype(np.int64) + rng.integers(-amp, amp + 1, S.size), 0, o.pmax).astype(S.dtype)
+        w, h = [(16, 16), (8, 8), (32, 32), (16, 8), (64, 64), (8, 16), (32, 16), (16, 32)][(case // 8) % 8]
+        qp = int(rng.integers(0, 30))
+        tab = r.mvcost_table(qp, RAD)
+        x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
+        of = geo.origin + y * geo.stride + x
+        m = int(rng.integers(12, 40))
+        minx = -min(m, x + geo.margin_x - 8); maxx = min(m, cw + geo.margin_x - 8 - w - x)
+        miny = -min(m, y + geo.margin_y - 8); maxy = min(m, ch + geo.margin_y - 8 - h - y)
+        off = int(rng.integers(0, 4))
+        qmvp = np.array([4 * dx + int(rng.integers(-off, off + 1)) * 4, 4 * dy + int(rng.integers(-off, off + 1)) * 4])
+        nc = int(rng.integers(0, 4))
+        mvc = qmvp + rng.integers(-30, 31, (nc, 2)) * int(rng.integers(0, 3))
+        merange = int(rng.integers(8, 64))
+        subme = case % 3
+        a = o.motion_estimate_full(subme, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD, 2, merange)
+        b = r.motion_estimate(2, subme, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+        assert a == b, (case, w, h, amp, a, b)
