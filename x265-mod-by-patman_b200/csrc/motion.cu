@@ -123,6 +123,8 @@ static int launch_lowres_cmp(x265b200_ctx* ctx, int op, int w, int h, const void
     int G = 1;
     while (G * 2 * per <= T4 && G < 32) G <<= 1;
     const long long cands = (long long)n * K;
+    if (cands * G > 0x7fffffffLL * 256) return fail(ctx, X265B200_ERR_ARG, "lowres cost: too many candidates");
+    if (cands > 0x7fffffff) return fail(ctx, X265B200_ERR_ARG, "lowres cost: too many candidates");
     const int grid = ceil_div(cands * G, 256);
 #define LC(T, OP_) lowres_cmp_kernel<T, OP_><<<grid, 256, 0, st>>>((const T*)fenc, sf, (const T*)planes, sr, offF, offA, offB, K, (int)cands, w, h, G, cost)
     if (ctx->pixbytes == 1) { if (op == X265B200_SAD) LC(uint8_t, OP_SAD); else LC(uint8_t, OP_SATD); }
@@ -400,6 +402,8 @@ extern "C" int x265b200_motion_estimate_chroma_batch(x265b200_ctx* ctx, int sear
         return fail(ctx, X265B200_ERR_ARG, "motion_estimate_chroma: 4:2:0 or 4:4:4 planes with strides that are multiples of 4");
     // bChromaSATD (motion.cpp:240): subme > 2 and a chroma block that has a SATD slot (a multiple of 4x4, pixel.cpp:1217-1243)
     const int on = subpelRefine > 2 && !((w >> hshift) & 3) && !((h >> vshift) & 3);
+    if (on && n > 0 && (!fencCb || !fencCr || !refCb || !refCr || !offFC || !offRC))
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate_chroma: chroma planes and offsets are required from subme 3 on");
     MeChroma c{ on, hshift, vshift, strideRC, offRC };
     MeChromaArgs a{ fencCb, fencCr, strideFC, refCb, refCr, offFC };
     return motion_chain(ctx, 0, c, a, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR, offF, offR, range, qmvp, numCand, mvc,
