@@ -107,6 +107,33 @@ int ref_motion_estimate_chroma(int method, int subme, int csp, int w, int h, con
     return on ? cost : -1 - cost;                              /* negative: the chroma term was off for this PU (caller checks) */
 }
 
+/* X265_SEA: as ref_motion_estimate, plus the twelve SEA integral planes (`sums`, planePitch apart, computed over the padded
+ * reference picture by ref_me_integral) handed to MotionEstimate::integral[] at the PU's co-located block, as
+ * Search::predInterSearch does (search.cpp:2700) */
+extern "C" __attribute__((visibility("default")))
+int ref_motion_estimate_sea(int subme, int w, int h, pixel* fencPlane, intptr_t strideF, intptr_t offF,
+                            pixel* refPlane, intptr_t strideR, intptr_t offR, uint32_t* sums, size_t planePitch,
+                            const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc, int merange, int qp, int32_t* outQMv)
+{
+    static bool scales = false;
+    if (!scales) { ref_ensure(); MotionEstimate::initScales(); scales = true; }
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    memset(me.fencPUYuv.m_buf[0], 0, 64 * 64 * sizeof(pixel));   /* SEA's DC sums read the whole 64-stride cache */
+    me.setQP(qp);
+    me.setSourcePU(fencPlane, strideF, offF, w, h, X265_SEA, subme);
+    ReferencePlanes ref;
+    ref.fpelPlane[0] = refPlane + (offR - offF);
+    ref.lumaStride = strideR;
+    for (int k = 0; k < INTEGRAL_PLANE_NUM; k++) me.integral[k] = sums + k * planePitch + offR;
+    MV mvmin(range[0], range[1]), mvmax(range[2], range[3]), mvp(qmvp[0], qmvp[1]), out;
+    MV cands[16];
+    for (int i = 0; i < numCand && i < 16; i++) cands[i] = MV(mvc[2 * i], mvc[2 * i + 1]);
+    int cost = me.motionEstimate(&ref, mvmin, mvmax, mvp, numCand, cands, merange, out, 1, false);
+    outQMv[0] = out.x; outQMv[1] = out.y;
+    return cost;
+}
+
 /* the lambda-scaled mv cost table BitCost::setQP builds, copied out for the other implementations: [-radius, radius] */
 extern "C" __attribute__((visibility("default")))
 void ref_mvcost_table(int qp, int radius, uint16_t* out)

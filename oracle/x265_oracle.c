@@ -1015,7 +1015,9 @@ static const int k_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {
 typedef struct { int w, h; const pixel* fenc; intptr_t sf; const pixel* fref; intptr_t sr; const uint16_t* cx; const uint16_t* cy;
                  const pixel* hpel[4]; /* lowres: the four half-pel planes at the co-located block, else NULL */
                  /* chroma residual term of subpelCompare (bChromaSATD): co-located chroma blocks, or chroma == 0 */
-                 int chroma, hshift, vshift; const pixel* fencC[2]; intptr_t sfc; const pixel* frefC[2]; intptr_t src; } me_ctx;
+                 int chroma, hshift, vshift; const pixel* fencC[2]; intptr_t sfc; const pixel* frefC[2]; intptr_t src;
+                 /* SEA: the twelve integral planes at the co-located block (framefilter.cpp:770-832 order), or NULL */
+                 const uint32_t* const* integral; const uint16_t* costTab; const int32_t* qmvp; } me_ctx;
 /* chroma part of subpelCompare (motion.cpp:1805-1865): the vector in 1/8 chroma samples, 4-tap filters, always SATD */
 static int me_chroma_cost(const me_ctx* c, int qx, int qy)
 {
@@ -1401,11 +1403,102 @@ static int me_umh_search(const me_ctx* c, const int32_t* range, int* merangeIO, 
     return me_in_range(range, u.x, u.y);
 }
 
-/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_UMH_SEARCH 2, X265_STAR_SEARCH 3, X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
+/* Successive elimination (motion.cpp:1438-1591): every row of the window (start +- merange, clipped) is pre-filtered with
+ * `ads` -- |DC of the PU's sub-blocks - box sums of the reference| + the row's x-cost against a threshold -- and only the
+ * survivors get a real SAD.  Restated with the reference's cost bookkeeping as it is: the row cost is taken from the table
+ * shifted by the predictor a second time and indexed by the full-pel y, then << 2; candidates measured three at a time
+ * are charged only that shifted x-cost while the row cost is temporarily subtracted from the running best; the window
+ * width is rounded up to a multiple of 4, so up to three columns right of it are examined too. */
+static void me_sea_search(const me_ctx* c, const int32_t* range, int merange, int* bx, int* by, int* bcostIO)
+{
+    const int w = c->w, h = c->h;
+    const int ox = *bx, oy = *by;
+    const int minX = ox - merange > range[0] ? ox - merange : range[0], minY = oy - merange > range[1] ? oy - merange : range[1];
+    const int maxX = ox + merange < range[2] ? ox + merange : range[2], maxY = oy + merange < range[3] ? oy + merange : range[3];
+    const uint16_t* pcx = c->cx - c->qmvp[0];
+    const uint16_t* pcy = c->cy - c->qmvp[1];
+    const int width = (maxX - minX + 3) & ~3;
+    int deltaX = w <= 8 ? w : w >> 1, deltaY = h <= 8 ? h : h >> 1;
+    const int vertical = (w == 32 && h == 64) || (w == 16 && h == 32) || (w == 8 && h == 16) || (w == 4 && h == 8);
+    const int horizontal = (w == 64 && h == 32) || (w == 32 && h == 16) || (w == 16 && h == 8) || (w == 8 && h == 4);
+    const int smallRect = (w == 4 && h == 4) || (w == 16 && h == 12) || (w == 12 && h == 16) || (w == 16 && h == 4) || (w == 4 && h == 16);
+    const int asym = (w == 12 && h == 16) || (w == 4 && h == 16) || (w == 24 && h == 32) || (w == 8 && h == 32) || (w == 48 && h == 64) ||
+                     (w == 16 && h == 64) || (w == 16 && h == 12) || (w == 16 && h == 4) || (w == 32 && h == 24) || (w == 32 && h == 8) ||
+                     (w == 64 && h == 48) || (w == 64 && h == 16);
+    int tw, th;                                                 /* the block whose DC each of the four sad_x4 references takes */
+    if (vertical) { tw = w; th = h >> 1; }
+    else if (horizontal) { tw = w >> 1; th = h; }
+    else if (asym) { tw = smallRect ? w : w >> 1; th = smallRect ? h : h >> 1; }
+    else { tw = w <= 8 ? w : w >> 1; th = w <= 8 ? h : h >> 1; }
+    int encDC[4];
+    {
+        const int offs[4][2] = { {0, 0}, {deltaX, 0}, {0, deltaY}, {deltaX, deltaY} };
+        for (int k = 0; k < 4; k++)
+        {   /* sad against a zero block = sum of the samples; the reference reads past the PU inside its 64-stride cache,
+               where the rest of a previous, larger PU may still lie -- only in-block sums are ever used by ads */
+            int sum = 0;
+            for (int y = 0; y < th; y++)
+                for (int x = 0; x < tw; x++)
+                {
+                    int yy = offs[k][1] + y, xx = offs[k][0] + x;
+                    sum += (yy < h && xx < w) ? c->fenc[yy * c->sf + xx] : 0;
+                }
+            encDC[k] = sum;
+        }
+    }
+    int plane;
+    switch (deltaX)
+    {
+    case 32: plane = deltaY % 24 == 0 ? 1 : deltaY == 8 ? 2 : 0; break;
+    case 24: plane = 3; break;
+    case 16: plane = deltaY % 12 == 0 ? 5 : deltaY == 4 ? 6 : 4; break;
+    case 12: plane = 7; break;
+    case 8: plane = deltaY == 32 ? 8 : 9; break;
+    case 4: plane = deltaY == 16 ? 10 : 11; break;
+    default: plane = 11; break;
+    }
+    const uint32_t* sumsBase = c->integral[plane];
+    if ((w == h && w >= 16) || vertical || (w == 12 && h == 16) || (w == 4 && h == 16) || (w == 24 && h == 32) || (w == 8 && h == 32) ||
+        (w == 48 && h == 64) || (w == 16 && h == 64))
+        deltaY *= (int)c->sr;
+    if (vertical) encDC[1] = encDC[2];
+    if (horizontal) deltaY = deltaX;
+
+    int x = *bx, y = *by, bcost = *bcostIO;
+    uint16_t* rowCost = (uint16_t*)malloc((size_t)(width + 4) * sizeof(uint16_t));
+    int16_t* mvs = (int16_t*)malloc((size_t)(2 * merange + 8 + width) * sizeof(int16_t));
+    for (int i = 0; i < width; i++) rowCost[i] = c->cx[(minX + i) * 4];       /* m_fpelMvCosts: the x-cost at full-pel columns */
+    for (int ty = minY; ty <= maxY; ty++)
+    {
+        const int ycost = pcy[ty] << 2;
+        if (bcost <= ycost) continue;
+        bcost -= ycost;
+        const int xn = orc_ads(w, h, encDC, sumsBase + minX + (intptr_t)ty * c->sr, deltaY, rowCost, mvs, width, bcost);
+        int i = 0;
+        for (; i < xn - 2; i += 3)
+            for (int k = 0; k < 3; k++)
+            {
+                const int mx = minX + mvs[i + k];
+                int cost = orc_sad(w, h, c->fenc, c->sf, c->fref + mx + (intptr_t)ty * c->sr, c->sr) + pcx[mx * 4];
+                if (cost < bcost) { bcost = cost; x = mx; y = ty; }
+            }
+        bcost += ycost;
+        for (; i < xn; i++)
+        {
+            const int mx = minX + mvs[i];
+            int cost = me_fpel(c, mx, ty);
+            if (cost < bcost) { bcost = cost; x = mx; y = ty; }
+        }
+    }
+    free(rowCost); free(mvs);
+    *bx = x; *by = y; *bcostIO = bcost;
+}
+
+/* method: X265_DIA_SEARCH 0, X265_HEX_SEARCH 1, X265_UMH_SEARCH 2, X265_STAR_SEARCH 3, X265_SEA 4 (needs the integral planes), X265_FULL_SEARCH 5 (x265.h:511-519); others return -1 */
 static int me_estimate(me_ctx cc, int method, int merange, int subme, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
                        const uint16_t* costTab, int32_t* outQMv)
 {
-    if (method != 0 && method != 1 && method != 2 && method != 3 && method != 5) return -1;
+    if (method < 0 || method > 5 || (method == 4 && !cc.integral)) return -1;
     const me_ctx c = cc;
     const int w = c.w, h = c.h; const pixel* fenc = c.fenc; const pixel* fref = c.fref; const intptr_t sf = c.sf, sr = c.sr;
     const int lowres = c.hpel[0] != 0;
@@ -1451,6 +1544,7 @@ static int me_estimate(me_ctx cc, int method, int merange, int subme, const int3
         if (me_umh_search(&c, range, &mr, (pmvx + 2) >> 2, (pmvy + 2) >> 2, qmvp, numCand, mvc, &bmvx, &bmvy, &bcost))
             me_hex_search(&c, range, mr, &bmvx, &bmvy, &bcost);
     }
+    else if (method == 4) me_sea_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 0) me_dia_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 1) me_hex_search(&c, range, merange, &bmvx, &bmvy, &bcost);
     else if (method == 3) me_star_search(&c, range, merange, &bmvx, &bmvy, &bcost);
@@ -1721,4 +1815,17 @@ EXPORT void orc_intra_pred_all(int N, const pixel* s, pixel* dst)
     orc_intra_pred(N, 0, N >= 8 ? f : s, 0, dst, N);
     for (int m = 2; m < 35; m++)
         orc_intra_pred(N, m, (k_intra_filter_flags[m] & N) ? f : s, N <= 16, dst + m * N * N, N);
+}
+
+/* SEA through the whole motionEstimate: integral = twelve planes as orc_me_integral writes them, each addressed at the PU's
+ * co-located block (plane k of the padded reference picture + the block's element offset) */
+EXPORT int orc_motion_estimate_sea(int merange, int subme, int w, int h, const pixel* fenc, intptr_t sf, const pixel* fref, intptr_t sr,
+                                   const uint32_t* sums, size_t planePitch, intptr_t blockOffset, const int32_t* range, const int32_t* qmvp,
+                                   int numCand, const int32_t* mvc, const uint16_t* costTab, int32_t* outQMv)
+{
+    const uint32_t* planes[12];
+    for (int k = 0; k < 12; k++) planes[k] = sums + k * planePitch + blockOffset;
+    me_ctx c = { w, h, fenc, sf, fref, sr, costTab - qmvp[0], costTab - qmvp[1], { 0, 0, 0, 0 }, 0, 0, 0, { 0, 0 }, 0, { 0, 0 }, 0,
+                 planes, costTab, qmvp };
+    return me_estimate(c, 4, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
 }

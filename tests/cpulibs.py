@@ -235,6 +235,16 @@ class _Base:
     def subpel_cmp_chroma(self, w, h, fenc, of, sf, ref, orf, sr, xFrac, yFrac):
         return self._f("subpel_cmp_chroma")(w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), xFrac, yFrac)
 
+    def motion_estimate_sea(self, merange, subme, w, h, fenc, of, sf, ref, orf, sr, sums, pitch, rng, qmvp, mvc, cost_tab, centre):
+        """oracle: motionEstimate with X265_SEA; sums = 12 integral planes over the padded reference buffer, `pitch` apart"""
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self._f("motion_estimate_sea")(merange, subme, w, h, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(ref, orf), C.c_ssize_t(sr), _ptr(sums),
+                                           C.c_size_t(pitch), C.c_ssize_t(orf), _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc),
+                                           _ptr(cost_tab, centre), _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
+
     def lowres_motion_estimate(self, method, merange, subme, w, h, fenc, of, sf, planes, orf, sr, pitch, rng, qmvp, cost_tab, centre):
         """oracle: the lookahead's motionEstimate on a lowres reference (four half-pel planes `pitch` apart)"""
         out = np.zeros(2, np.int32)
@@ -423,6 +433,14 @@ class Reference(_Base):
         out = np.zeros(33 * N * N, ref_pix.dtype)
         self.lib.ref_intra_allangs(N, _ptr(out), _ptr(ref_pix), _ptr(filt_pix), int(bLuma))
         return out
+
+    def motion_estimate_sea_ref(self, subme, w, h, fenc, of, sf, ref, orf, sr, sums, pitch, rng, qmvp, mvc, merange, qp):
+        out = np.zeros(2, np.int32)
+        rng = np.ascontiguousarray(rng, np.int32); qmvp = np.ascontiguousarray(qmvp, np.int32)
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        c = self.lib.ref_motion_estimate_sea(subme, w, h, _ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(ref), C.c_ssize_t(sr), C.c_ssize_t(orf),
+                                             _ptr(sums), C.c_size_t(pitch), _ptr(rng), _ptr(qmvp), len(mvc) // 2, _ptr(mvc), merange, qp, _ptr(out))
+        return int(out[0]), int(out[1]), int(c)
 
     def mvcost_table(self, qp, radius):
         out = np.zeros(2 * radius + 1, np.uint16)

@@ -786,3 +786,47 @@ def test_motion_estimate_umh_ladder(libs):
         a = o.motion_estimate_full(subme, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD, 2, merange)
         b = r.motion_estimate(2, subme, w, h, S, of, geo.stride, S2, of, geo.stride, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
         assert a == b, (case, w, h, amp, a, b)
+
+
+def test_motion_estimate_sea(libs):
+    """successive elimination (X265_SEA) through the whole motionEstimate: oracle vs the reference, both reading the same
+    twelve integral planes; PU shapes whose DC sub-blocks lie inside the PU (the reference's 32x8, 8x32, 8x4 and 4x8 cases
+    read beyond the block in its cache and are left out)"""
+    o, r = libs
+    from frames import Geometry, make_plane, smooth_field
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(101)
+    S = smooth_field(geo, o.depth, 141, box=9)
+    N = make_plane(geo, o.depth, 142, "natural")
+    RAD = 4096
+    cw, ch = geo.coded()
+    pitch = geo.plane_elems
+    shapes = [(16, 16), (8, 8), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64), (32, 24), (24, 32),
+              (64, 48), (48, 64), (64, 16), (16, 64), (16, 12), (12, 16), (16, 4), (4, 16)]
+    moved = 0
+    for case in range(120):
+        dx, dy = int(rng.integers(-10, 11)), int(rng.integers(-8, 9))
+        if case % 3 == 2: F, R = N, make_plane(geo, o.depth, 143, "natural")
+        else:
+            F = S
+            R = np.clip(np.roll(S, dy * geo.stride + dx).astype(np.int64) + rng.integers(-3, 4, S.size), 0, o.pmax).astype(S.dtype)
+        sums = np.zeros(12 * pitch, np.uint32)
+        assert r.me_integral(R, geo.stride, geo.rows, sums, pitch) == 0
+        w, h = shapes[case % len(shapes)]
+        qp = int(rng.integers(0, 40))
+        tab = r.mvcost_table(qp, RAD)
+        x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
+        of = geo.origin + y * geo.stride + x
+        m = int(rng.integers(4, 24))
+        minx = -min(m, x + geo.margin_x - 12); maxx = min(m, cw + geo.margin_x - 12 - w - x)
+        miny = -min(m, y + geo.margin_y - 12); maxy = min(m, ch + geo.margin_y - 12 - h - y)
+        qmvp = rng.integers(-4 * m, 4 * m + 1, 2)
+        if case % 5 == 0: qmvp[:] = 0
+        mvc = rng.integers(-4 * m, 4 * m + 1, (int(rng.integers(0, 3)), 2))
+        merange = int(rng.integers(2, 24))
+        subme = case % 4
+        a = o.motion_estimate_sea(merange, subme, w, h, F, of, geo.stride, R, of, geo.stride, sums, pitch, [minx, miny, maxx, maxy], qmvp, mvc, tab, RAD)
+        b = r.motion_estimate_sea_ref(subme, w, h, F, of, geo.stride, R, of, geo.stride, sums, pitch, [minx, miny, maxx, maxy], qmvp, mvc, merange, qp)
+        assert a == b, (case, w, h, a, b)
+        moved += max(abs(a[0] - int(np.clip(qmvp[0], 4 * minx, 4 * maxx))), abs(a[1] - int(np.clip(qmvp[1], 4 * miny, 4 * maxy)))) >= 8
+    assert moved > 25
