@@ -8,27 +8,37 @@ Workload (BASELINE.json configs[2]/[3], "3840x2160 10-bit --preset slow"): F fra
 with x265's padded plane geometry.  One STEP = one pass of the hot path over that batch:
   * SATD of every PU shape preset `slow` analyses (2Nx2N, 2NxN, Nx2N for CU 64..8 -> 12 shapes), each
     shape tiling every CTU of every frame, one motion vector per block (+-57, seeded)  -> 12 launches
-  * forward DCT of the prediction residual for every TU size 32/16/8/4, each size tiling every frame
+  * forward DCT of a prediction residual for every TU size 32/16/8/4, each size tiling every frame
     -> 4 launches
 value = (12 + 4) * F * coded_luma_samples / step_time, inputs resident in HBM (F = 32 -> 1.2 GB of
 planes + 535 MB residual + 535 MB coefficients per DCT pass, far above the 126 MB L2, so successive
 launches cannot be served from cache).  F = 32 because every launch carries a fixed cost of about 6 us
 (launch gap, pipeline ramp, tail) that a 33 MB frame pair (5 us at the HBM roofline) cannot amortise:
-profiles/r2_frames_per_launch.md.
-e2e = the same step driven from pinned HOST planes: H2D of the frame pair, residual, SATD, DCT, D2H of
-all costs and coefficients, pipelined over streams.
+profiles/r2_frames_per_launch.md.  Both arms time the DCT passes on a residual that is already there
+(the reference arm through its dct slots on a precomputed residual, as the B200 arm does).
 
---impl reference times the reference's own C primitives (oracle/_ref, built from /root/reference by
-`make -C oracle ref`; falls back to the oracle port) on all host cores for one frame pair per step.
+verified = after the timed region every SATD cost of all 12 shapes and every DCT coefficient of all four
+sizes of the FIRST and the LAST frame of the batch are compared with the reference's own C primitives
+(oracle/_ref, or the oracle port where that library is absent); a mismatch makes the run fail.
+
+e2e = the same passes driven through the C ABI's host-buffer layer (x265b200_plane_* / x265b200_frame_job_*,
+include/x265b200.h): pinned HOST planes in, HOST results out, the library owning device memory, streams and
+copies.  Headline e2e returns what the encoder consumes after transformNxN -- SATD costs, numSig per TU,
+a significance bit per coefficient and the non-zero levels (DCT + quant at QP 32) -- and `e2e.dense`
+repeats the run returning every raw DCT coefficient (2 bytes per sample, the round-1 contract).
+
+--impl reference times the reference's own C primitives plus its SSE-intrinsic DCT tier (oracle/_ref, built
+from /root/reference by `make -C oracle ref`; falls back to the oracle port) on all host cores for one
+frame pair per step.
 """
 import argparse
+import ctypes
 import importlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -36,6 +46,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from frames import Geometry, make_plane, tile_blocks  # noqa: E402
 
@@ -45,6 +56,8 @@ WIDTH, HEIGHT = 3840, 2160
 # preset slow: rect on, amp off (reference param.cpp:572-587); min CU 8 -> PUs down to 8x4 / 4x8
 SATD_SHAPES = [(64, 64), (64, 32), (32, 64), (32, 32), (32, 16), (16, 32), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8)]
 DCT_SIZES = [32, 16, 8, 4]
+E2E_QP = 32             # slice QP of the e2e run's DCT + quant passes (preset slow's default CRF 28 lands around QP 30-34)
+FLAT_QUANT = [26214, 23302, 20560, 18396, 16384, 14564]
 
 
 def peaks():
@@ -52,6 +65,15 @@ def peaks():
     if os.path.exists(p):
         return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def quant_params(N, qp):
+    """Quant::transformNxN for an inter luma TU (reference common/quant.cpp:221-243, 465-466): flat table, qBits, rounding"""
+    q = qp + 6 * (DEPTH - 8)                                    # qp + QP_BD_OFFSET
+    per, rem = q // 6, q % 6
+    tshift = 15 - DEPTH - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+    qbits = 14 + per + tshift
+    return np.full(N * N, FLAT_QUANT[rem], np.int32), qbits, 171 << (qbits - 9)
 
 
 class ClockSampler:
@@ -97,7 +119,7 @@ def build_workload(nframes, rank):
     """numpy planes + descriptors for `nframes` frame pairs (deterministic per rank)"""
     from concurrent.futures import ThreadPoolExecutor
     geo = Geometry(WIDTH, HEIGHT)
-    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as pool:      # numpy releases the GIL in the big array ops
+    with ThreadPoolExecutor(max(1, min(8, len(os.sched_getaffinity(0))))) as pool:      # numpy releases the GIL in the big array ops
         fenc = list(pool.map(lambda f: make_plane(geo, DEPTH, 0x265 + 1000 * rank + f, "natural"), range(nframes)))
         ref = list(pool.map(lambda f: make_plane(geo, DEPTH, 0x9265 + 1000 * rank + f, "natural"), range(nframes)))
     desc = {}
@@ -107,58 +129,97 @@ def build_workload(nframes, rank):
     return geo, fenc, ref, desc
 
 
+ORIGINAL_AFFINITY = None
+
+
+def bind_to_gpu(local, world):
+    """Pin this rank's threads to the CPUs next to its GPU (NVML's ideal affinity), split between the ranks that share them, and
+    prefer that NUMA node for the pinned buffers allocated afterwards.  Best effort: reports what it did."""
+    info = {"cpus": None, "numa_node": None}
+    global ORIGINAL_AFFINITY
+    ORIGINAL_AFFINITY = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [i for i in range(os.cpu_count()) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        if world > 1 and len(allowed) >= world:
+            share = len(allowed) // world
+            allowed = allowed[local * share:(local + 1) * share]
+        os.sched_setaffinity(0, allowed)
+        info["cpus"] = "%d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node_path = "/sys/bus/pci/devices/%s/numa_node" % bus[-12:].lower()
+        node = int(open(node_path).read()) if os.path.exists(node_path) else -1
+        info["numa_node"] = node
+        if node >= 0:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy (x86_64)
+    except Exception as e:      # noqa: BLE001
+        info["error"] = str(e)[:80]
+    return info
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 
-def cpu_step_fn():
-    """returns (fn(geo, fenc, ref, desc, nthreads) -> samples processed, kind)"""
-    from cpulibs import OP_SATD, Oracle, Reference, have_reference
+def cpu_libs():
+    from cpulibs import Oracle, Reference, have_reference
     if have_reference(DEPTH):
         lib = Reference(DEPTH)
+        lib.set_tier(1)
+        return lib, "reference"
+    return Oracle(DEPTH), "port"
 
-        def step(geo, fenc, ref, desc, nthreads):
-            total = 0
-            for (w, h) in SATD_SHAPES:
-                oa, ob = desc[(w, h)]
-                lib.pixelcmp_batch(OP_SATD, w, h, fenc, geo.stride, ref, geo.stride, oa, ob, nthreads)
-                total += len(oa) * w * h
-            for n in DCT_SIZES:
-                oa, ob = desc[(n, n)]
-                lib.residual_dct_batch(n, fenc, geo.stride, ref, geo.stride, oa, ob, nthreads)
-                total += len(oa) * n * n
-            return total
-        return step, "reference"
-    lib = Oracle(DEPTH)
 
-    def step(geo, fenc, ref, desc, nthreads):
+def cpu_step_fn():
+    """returns (fn(geo, fenc, ref, desc, resid, nthreads) -> samples processed, kind)"""
+    from cpulibs import OP_SATD
+    lib, kind = cpu_libs()
+    contig = {n: (np.arange((Geometry(WIDTH, HEIGHT).coded()[0] * Geometry(WIDTH, HEIGHT).coded()[1]) // (n * n)) * n * n).astype(np.int32) for n in DCT_SIZES}
+
+    def step(geo, fenc, ref, desc, resid, nthreads):
         total = 0
         for (w, h) in SATD_SHAPES:
             oa, ob = desc[(w, h)]
-            lib.pixelcmp_batch(OP_SATD, w, h, fenc, geo.stride, ref, geo.stride, oa, ob)
+            if kind == "reference":
+                lib.pixelcmp_batch(OP_SATD, w, h, fenc, geo.stride, ref, geo.stride, oa, ob, nthreads)
+            else:
+                lib.pixelcmp_batch(OP_SATD, w, h, fenc, geo.stride, ref, geo.stride, oa, ob)
             total += len(oa) * w * h
         for n in DCT_SIZES:
-            oa, ob = desc[(n, n)]
-            res = lib.residual_batch(n, n, fenc, geo.stride, ref, geo.stride, oa, ob)
-            lib.dct_batch(n, res, n, (np.arange(len(oa)) * n * n).astype(np.int32))
-            total += len(oa) * n * n
+            if kind == "reference":
+                lib.dct_batch(n, resid, n, contig[n], nthreads)
+            else:
+                lib.dct_batch(n, resid, n, contig[n])
+            total += len(contig[n]) * n * n
         return total
-    return step, "port"
+    return step, kind, lib
 
 
 def time_cpu(steps, warmup):
+    from cpulibs import Oracle
     geo, fenc, ref, desc = build_workload(1, 0)
-    step, kind = cpu_step_fn()
-    cores = os.cpu_count() if kind == "reference" else 1
+    step, kind, lib = cpu_step_fn()
+    cores = len(os.sched_getaffinity(0)) if kind == "reference" else 1
+    oa, ob = desc[(32, 32)]
+    resid = Oracle(DEPTH).residual_batch(32, 32, fenc[0], geo.stride, ref[0], geo.stride, oa, ob)     # outside the timed region, as on the GPU
     for _ in range(warmup):
-        step(geo, fenc[0], ref[0], desc, cores)
+        step(geo, fenc[0], ref[0], desc, resid, cores)
     t0 = time.perf_counter()
     total = 0
     for _ in range(steps):
-        total += step(geo, fenc[0], ref[0], desc, cores)
+        total += step(geo, fenc[0], ref[0], desc, resid, cores)
     dt = time.perf_counter() - t0
-    label = ("x265 C reference primitives (pixel.cpp/dct.cpp compiled -O3 -march=native, GCC auto-vectorised; the NASM "
-             "AVX2/AVX-512 tier cannot be assembled in this image)") if kind == "reference" else "oracle C port, scalar"
+    label = ("x265 C reference primitives (pixel.cpp / dct.cpp compiled -O3 -march=native, GCC auto-vectorised) with the reference's "
+             "SSE3/SSSE3/SSE4.1 intrinsic DCT tier (common/vec/) layered on top as x265_setup_primitives does, persistent thread pool; "
+             "the NASM AVX2/AVX-512 tier cannot be assembled in this image (no nasm/yasm)") if kind == "reference" else "oracle C port, scalar"
     return {"value": total / dt / 1e9, "unit": "GPixels/s", "cores": cores, "kind": kind,
-            "sample": "%d steps x 1 frame pair 3840x2160 10-bit (12 SATD shape passes + residual+DCT 32/16/8/4 passes); %s" % (steps, label)}, dt / steps * 1e3
+            "sample": "%d steps x 1 frame pair 3840x2160 10-bit (12 SATD shape passes + DCT 32/16/8/4 passes on a precomputed residual); %s" % (steps, label)}, dt / steps * 1e3
 
 
 def run_reference_arm(args):
@@ -166,6 +227,9 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cb, ms = time_cpu(args.steps, max(1, min(args.warmup, 3)))
+    enc = encoder_fps(args)
+    if enc:
+        cb["encoder_fps"] = enc
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GPixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -174,6 +238,19 @@ def run_reference_arm(args):
             "e2e": {"value": cb["value"], "unit": "GPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def encoder_fps(args):
+    """the encoder-level half of BASELINE.json's metric ("ref CPU fps same box"): the reference CLI built without assembly by
+    oracle/Makefile (`make cli`), --preset slow on a synthetic 2160p 10-bit clip, bounded to a few frames"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "x265_ref_cli_10")
+    if not os.path.exists(exe) or args.no_encoder:
+        return None
+    try:
+        from encoder_clip import run_reference_cli
+        return run_reference_cli(exe, WIDTH, HEIGHT, DEPTH, frames=args.encoder_frames, preset="slow")
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def workload_config(nframes, note=""):
@@ -185,6 +262,34 @@ def workload_config(nframes, note=""):
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
+
+def measure_traffic(F):
+    """dram__bytes_read + dram__bytes_write per SATD launch, measured now on this GPU by running tools/measure_traffic.py under ncu
+    (two counters, one pass, the same 12 launches over F frames).  Falls back to the committed capture when ncu cannot run."""
+    script = os.path.join(ROOT, "tools", "measure_traffic.py")
+    try:
+        sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+    except OSError:
+        sha = None
+    try:
+        out = subprocess.run([sys.executable, script, "--frames", str(F), "--ncu"], capture_output=True, text=True, timeout=420)
+        for line in out.stdout.splitlines():
+            if line.startswith("{"):
+                j = json.loads(line)
+                if j.get("launches"):
+                    j["source"] = "live: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over tools/measure_traffic.py on this GPU"
+                    j["git_sha"] = sha
+                    return j
+    except (OSError, subprocess.TimeoutExpired, ValueError):
+        pass
+    tp = os.path.join(ROOT, "profiles", "r3_satd_traffic.json")
+    if os.path.exists(tp):
+        j = json.load(open(tp))
+        if j.get("frames_per_launch") == F:
+            j["source"] = "committed capture profiles/r3_satd_traffic.json (ncu could not run here); captured at git %s" % j.get("git_sha")
+            return j
+    return None
+
 
 def run_b200_arm(args):
     import torch
@@ -206,6 +311,7 @@ def run_b200_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    binding = bind_to_gpu(local, world)         # before any pinned allocation
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -217,15 +323,17 @@ def run_b200_arm(args):
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
 
-    # planes of all frames contiguous: offsets of frame f are shifted by f * plane_elems
+    # pinned host planes through the C ABI (x265b200_host_alloc): what PicYuv::create would call
+    hostF, pF = ctx.host_alloc(F * pe * 2)
+    hostR, pR = ctx.host_alloc(F * pe * 2)
+    hF16, hR16 = hostF.view(np.uint16), hostR.view(np.uint16)
+    for f in range(F):
+        hF16[f * pe:(f + 1) * pe] = fenc_np[f]
+        hR16[f * pe:(f + 1) * pe] = ref_np[f]
+    # planes of all frames contiguous on the device: offsets of frame f are shifted by f * plane_elems
     dF = torch.empty(F * pe, dtype=torch.int16, device="cuda")
     dR = torch.empty(F * pe, dtype=torch.int16, device="cuda")
-    hF = torch.empty(F * pe, dtype=torch.int16).pin_memory()
-    hR = torch.empty(F * pe, dtype=torch.int16).pin_memory()
-    for f in range(F):
-        hF[f * pe:(f + 1) * pe] = torch.from_numpy(fenc_np[f].view(np.int16))
-        hR[f * pe:(f + 1) * pe] = torch.from_numpy(ref_np[f].view(np.int16))
-    dF.copy_(hF); dR.copy_(hR)
+    dF.copy_(torch.from_numpy(hF16.view(np.int16))); dR.copy_(torch.from_numpy(hR16.view(np.int16)))
     dev_desc = {}
     for key, (oa, ob) in desc.items():
         A = np.concatenate([oa.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
@@ -235,15 +343,15 @@ def run_b200_arm(args):
     satd_out = {s: torch.empty(dev_desc[s][0].numel(), dtype=torch.int32, device="cuda") for s in SATD_SHAPES}
     resid = torch.empty(samples, dtype=torch.int16, device="cuda")
     coef = torch.empty(samples, dtype=torch.int16, device="cuda")
-    tu_off = {n: (torch.arange(samples // (n * n), dtype=torch.int32, device="cuda") * (n * n)) for n in DCT_SIZES}
     # residual of the 32x32 tiling, block-contiguous; any int16 data is a valid DCT input, so the same
     # buffer is re-read as contiguous N x N blocks for the smaller sizes
     oa, ob, _ = dev_desc[(32, 32)]
     ctx.residual_batch(32, 32, dF, geo.stride, dR, geo.stride, oa, ob, resid, sh)
     torch.cuda.synchronize()
 
-    # optional recon exchange (multi-GPU): every rank contributes one padded reference picture per step
+    # recon exchange (multi-GPU): every rank contributes one padded reference picture per step
     comm_stream = torch.cuda.Stream() if world > 1 else None
+    comm_marks = []
     if world > 1:
         recon_send = dR[:pe]
         recon_all = torch.empty(world * pe, dtype=torch.int16, device="cuda")
@@ -259,7 +367,11 @@ def run_b200_arm(args):
             if world > 1:
                 comm_stream.wait_stream(stream)
                 with torch.cuda.stream(comm_stream):
+                    if marks is not None and not per_launch:
+                        c0 = ev(); c0.record(comm_stream)
                     dist.all_gather_into_tensor(recon_all.view(torch.uint8), recon_send.view(torch.uint8))
+                    if marks is not None and not per_launch:
+                        c1 = ev(); c1.record(comm_stream); comm_marks.append((c0, c1))
             if marks is not None and not per_launch:
                 p0 = ev(); p0.record(stream)
             for s in SATD_SHAPES:
@@ -317,6 +429,22 @@ def run_b200_arm(args):
         tsum[kind] += e0.elapsed_time(e1)
     satd_ms = tsum["satd"] / (args.steps * len(SATD_SHAPES))       # average SATD launch
     dct_ms = tsum["dct"] / (args.steps * len(DCT_SIZES))
+    nccl = None
+    if world > 1:
+        cm = [a.elapsed_time(b) for a, b in comm_marks]
+        # what the exchange carried is what every rank sent: compare rank r's slice of the gathered buffer with a checksum of its plane
+        mine = recon_send.to(torch.int64).sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        got = recon_all.view(world, pe).to(torch.int64).sum(dim=1)
+        nccl = {"allgather_ms_per_step": sum(cm) / max(1, len(cm)), "bytes_per_rank": int(pe * 2), "ranks": world,
+                "what": "one padded 2160p10 luma reference picture per rank all-gathered over NCCL on a side stream, overlapped with the step's kernels "
+                        "(the 1 -> N growth of ms_per_step is this collective sharing SMs and HBM with the SATD stream)",
+                "payload_verified": bool(all(int(sums[r].item()) == int(got[r].item()) for r in range(world)))}
+
+    # ---------------- verification of the headline configuration against the reference's C primitives
+    verified = verify_step(torch, pkg, ctx, geo, fenc_np, ref_np, desc, dev_desc, satd_out, resid, coef, F, sh, samples)
+
     # diagnostic pass (not part of `value`): every launch bracketed by its own event pair
     diag = []
     for _ in range(3):
@@ -331,14 +459,34 @@ def run_b200_arm(args):
     dct_bytes = samples * 4                                        # int16 in + int16 out per coefficient
     dominant = "satd" if tsum["satd"] >= tsum["dct"] else "dct"
     ach = (satd_bytes / (satd_ms * 1e-3) if dominant == "satd" else dct_bytes / (dct_ms * 1e-3)) / 1e9
+
+    # ---------------- e2e through the C ABI's host-buffer layer (frees the device-resident batch first: the job owns its own memory)
+    del dF, dR, resid, coef, satd_out
+    torch.cuda.empty_cache()
+    e2e = run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world, dist, binding)
+    clocks = sampler.stop() if sampler else None
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r2_satd_traffic.json")
-    if dominant == "satd" and os.path.exists(tp):
-        # dram__bytes_read + write per launch of this kernel from the committed ncu --set full capture of this workload
-        tj = json.load(open(tp))
-        traffic = tj["dram_bytes_per_launch_avg"] if tj.get("frames_per_launch") == F else None
+    if rank == 0 and dominant == "satd" and args.traffic != "off":
+        ctx.close()                                                # the ncu child needs the GPU memory
+        ctx = None
+        traffic = measure_traffic(F)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if ORIGINAL_AFFINITY:
+        os.sched_setaffinity(0, ORIGINAL_AFFINITY)                 # the CPU baseline may use every host core
+    cb, _ = time_cpu(3, 1)
+    enc = encoder_fps(args) if world == 1 else None
+    if enc:
+        cb["encoder_fps"] = enc
     roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (10 shapes) + strip8_fast_kernel<SATD> (8x4, 16x8) (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic["dram_bytes_per_launch_avg"] if traffic else None,
+                "traffic_detail": traffic,
                 "algorithmic_bytes_per_launch": satd_bytes if dominant == "satd" else dct_bytes,
                 "peak_source": peak_src,
                 "share_of_step": tsum[dominant] / (ms if world == 1 else sum(tsum.values())),
@@ -347,98 +495,211 @@ def run_b200_arm(args):
                           "per_launch_ms_diagnostic_pass": {"%s_%s" % (k[0], "x".join(map(str, k[1])) if isinstance(k[1], tuple) else k[1]): sum(v) / len(v)
                                                               for k, v in per.items()},
                           "timing": "phase events (SATD x12, DCT x4) inside the timed region; per-launch figures from a separate pass with an event pair per launch"}}
-
-    # ---------------- e2e: same step from pinned host planes, H2D + kernels + D2H inside the timed region
-    e2e = run_e2e(torch, pkg, ctx, geo, hF, hR, desc, F, args, world, dist)
-    clocks = sampler.stop() if sampler else None
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    cb, _ = time_cpu(3, 1)
     line = {"metric": METRIC, "value": value, "unit": "GPixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": workload_config(F, note="per-GPU batch is fixed as N grows (frames shard across GPUs)"
                                                            + ("; one padded recon picture per rank all-gathered over NCCL per step, overlapped" if world > 1 else "")),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cb}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "verified": verified, "roofline": roofline, "cpu_baseline": cb,
+            "host_binding": binding}
+    if nccl:
+        line["nccl"] = nccl
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if verified["mismatches"] or e2e.get("verified", {}).get("mismatches"):
+        sys.exit(3)
 
 
-def run_e2e(torch, pkg, ctx, geo, hF, hR, desc, F, args, world, dist):
-    """host planes -> H2D -> residual + SATD x12 + DCT x4 per frame -> D2H of costs and coefficients,
-    three frames in flight on three streams."""
+def verify_step(torch, pkg, ctx, geo, fenc_np, ref_np, desc, dev_desc, satd_out, resid, coef, F, sh, samples):
+    """every SATD cost (12 shapes) and every DCT coefficient (4 sizes) of frames 0 and F-1 of the timed batch vs the CPU checker"""
+    from cpulibs import OP_SATD, Oracle
+    lib, kind = cpu_libs()
+    if kind == "reference":
+        lib.set_tier(0)                                            # the plain C slots are the parity reference
+    nth = len(os.sched_getaffinity(0))
+    frames = sorted({0, F - 1})
+    mism = blocks = coefs = 0
+    torch.cuda.synchronize()
+    for s in SATD_SHAPES:
+        got = satd_out[s].cpu().numpy()
+        oa, ob = desc[s]
+        n = len(oa)
+        for f in frames:
+            want = lib.pixelcmp_batch(OP_SATD, s[0], s[1], fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob, nth) if kind == "reference" \
+                else lib.pixelcmp_batch(OP_SATD, s[0], s[1], fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob)
+            mism += int((got[f * n:(f + 1) * n] != want).sum())
+            blocks += n
+    per_frame = samples // F
+    oa, ob = desc[(32, 32)]
+    orc = Oracle(DEPTH)
+    res_np = {f: orc.residual_batch(32, 32, fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob) for f in frames}
+    for n in DCT_SIZES:
+        ctx.dct_batch(pkg.TR_DCT, n, resid, n, None, coef, sh, count=samples // (n * n))       # the timed launch again: `coef` holds one size at a time
+        torch.cuda.synchronize()
+        off = (np.arange(per_frame // (n * n)) * n * n).astype(np.int32)
+        for f in frames:
+            got = coef[f * per_frame:(f + 1) * per_frame].cpu().numpy()
+            want = lib.dct_batch(n, res_np[f], n, off, nth) if kind == "reference" else lib.dct_batch(n, res_np[f], n, off)
+            mism += int((got != want).sum())
+            coefs += per_frame
+    return {"satd_blocks": blocks, "dct_coefs": coefs, "mismatches": mism, "frames": frames,
+            "against": "reference C primitives (oracle/_ref)" if kind == "reference" else "oracle port (oracle/x265_oracle.c)"}
+
+
+def run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world, dist, binding):
+    """pinned host planes -> x265b200_plane_upload_padded -> x265b200_frame_job_submit -> x265b200_frame_job_wait -> host results.
+    Everything between the host pointers is the library's: device planes, streams, kernels, copies.  Python only issues the calls."""
+    from cpulibs import OP_SATD
     pe = geo.plane_elems
     cw, ch = geo.coded()
     samples = cw * ch
-    NS = 3
-    streams = [torch.cuda.Stream() for _ in range(NS)]
-    slots = []
-    dd = {k: (torch.from_numpy(v[0]).cuda(), torch.from_numpy(v[1]).cuda()) for k, v in desc.items()}
-    tu_off = {n: (torch.arange(samples // (n * n), dtype=torch.int32, device="cuda") * (n * n)) for n in DCT_SIZES}
-    ncost = sum(len(desc[s][0]) for s in SATD_SHAPES)
-    for _ in range(NS):
-        slots.append({"F": torch.empty(pe, dtype=torch.int16, device="cuda"), "R": torch.empty(pe, dtype=torch.int16, device="cuda"),
-                      "res": torch.empty(samples, dtype=torch.int16, device="cuda"),
-                      "coef": torch.empty(len(DCT_SIZES) * samples, dtype=torch.int16, device="cuda"),
-                      "cost": torch.empty(ncost, dtype=torch.int32, device="cuda"),
-                      "hcoef": torch.empty(len(DCT_SIZES) * samples, dtype=torch.int16).pin_memory(),
-                      "hcost": torch.empty(ncost, dtype=torch.int32).pin_memory()})
-    h2d = 2 * pe * 2
-    d2h = len(DCT_SIZES) * samples * 2 + ncost * 4
+    NS = 4
+    out = {}
+    for mode in ("levels", "dense"):
+        job = pkg.FrameJob(ctx, WIDTH, HEIGHT, 64, slots=NS)
+        for s in SATD_SHAPES:
+            job.add_cmp(pkg.OP_SATD, s[0], s[1], *desc[s])
+        for n in DCT_SIZES:
+            if mode == "levels":
+                qc, qbits, add = quant_params(n, E2E_QP)
+                job.add_transform(pkg.PASS_LEVELS, n, *desc[(n, n)], qc=qc, qbits=qbits, add=add)
+            else:
+                job.add_transform(pkg.PASS_COEF, n, *desc[(n, n)])
+        planes = [(pkg.Plane(ctx, WIDTH, HEIGHT), pkg.Plane(ctx, WIDTH, HEIGHT)) for _ in range(NS)]
+        lib = ctx.lib
+        npass = len(SATD_SHAPES) + len(DCT_SIZES)
+        res = (pkg.PassResult * npass)()
+        slot_of = [None] * NS
+        keep = {}
 
-    def frame(f, k):
-        st, sl = streams[k], slots[k]
-        sh = st.cuda_stream
-        with torch.cuda.stream(st):
-            sl["F"].copy_(hF[f * pe:(f + 1) * pe], non_blocking=True)
-            sl["R"].copy_(hR[f * pe:(f + 1) * pe], non_blocking=True)
-            pos = 0
-            for s in SATD_SHAPES:
-                a, b = dd[s]
-                n = a.numel()
-                ctx.pixelcmp_batch(pkg.OP_SATD, s[0], s[1], sl["F"], geo.stride, sl["R"], geo.stride, a, b, sl["cost"][pos:pos + n], sh)
-                pos += n
-            a, b = dd[(32, 32)]
-            ctx.residual_batch(32, 32, sl["F"], geo.stride, sl["R"], geo.stride, a, b, sl["res"], sh)
-            for i, n in enumerate(DCT_SIZES):
-                ctx.dct_batch(pkg.TR_DCT, n, sl["res"], n, None, sl["coef"][i * samples:(i + 1) * samples], sh, count=samples // (n * n))
-            sl["hcoef"].copy_(sl["coef"], non_blocking=True)
-            sl["hcost"].copy_(sl["cost"], non_blocking=True)
+        def one_step(capture=None):
+            """F frames through the job, NS in flight; capture = {frame index: list to receive copies of its results}"""
+            for f in range(F + NS):
+                k = f % NS
+                if f >= NS:
+                    g = f - NS
+                    if lib.x265b200_frame_job_wait(job.h, slot_of[k], res, npass) != 0:
+                        ctx.check()
+                    if capture is not None and g in capture:
+                        capture[g] = job_results_copy(pkg, job, res, npass)
+                if f < F:
+                    a, b = planes[k]
+                    lib.x265b200_plane_upload_padded(a.h, ctypes.c_void_p(pF + f * pe * 2))
+                    lib.x265b200_plane_upload_padded(b.h, ctypes.c_void_p(pR + f * pe * 2))
+                    slot_of[k] = lib.x265b200_frame_job_submit(job.h, a.h, b.h)
+                    if slot_of[k] < 0:
+                        ctx.check()
 
-    def step():
-        for f in range(F):
-            frame(f, f % NS)
+        for _ in range(2):
+            one_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        steps = max(3, args.steps // 4)
+        h0, d0 = ctx.transfer_stats()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_local = max(e0.elapsed_time(e1), wall)     # host-side enqueue and the final waits count for an end-to-end number
+        h1, d1 = ctx.transfer_stats()
+        ms = ms_local
+        rates = [(h1 - h0) / (ms_local * 1e-3) / 1e9, (d1 - d0) / (ms_local * 1e-3) / 1e9]
+        per_rank = [rates]
+        if world > 1:
+            t = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            gathered = [None] * world
+            dist.all_gather_object(gathered, rates)
+            per_rank = gathered
+        ctx.check()
+        # verification of this path: first and last frame, every cost and every level / coefficient
+        cap = {0: None, F - 1: None}
+        one_step(cap)
+        ver = verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode)
+        per_step_samples = world * F * samples * npass
+        out[mode] = {"value": per_step_samples / (ms / steps * 1e-3) / 1e9, "unit": "GPixels/s",
+                     "h2d_bytes_per_step": int((h1 - h0) // steps), "d2h_bytes_per_step": int((d1 - d0) // steps),
+                     "ms_per_step": ms / steps, "steps": steps,
+                     "per_rank_GBps": [{"h2d": round(r[0], 2), "d2h": round(r[1], 2)} for r in per_rank],
+                     "verified": ver}
+        job.destroy()
+        for a, b in planes:
+            a.destroy(); b.destroy()
+    e = out["levels"]
+    e["entry"] = "x265b200_plane_upload_padded + x265b200_frame_job_submit / x265b200_frame_job_wait (include/x265b200.h, csrc/framejob.cu)"
+    e["what"] = ("pinned host planes (x265b200_host_alloc) -> plane upload -> SATD x12 + (residual + DCT + quant at QP %d) x4 -> host: every cost, numSig per TU, "
+                 "one significance bit per coefficient and the non-zero levels; %d frames in flight; the library owns device memory, streams and copies" % (E2E_QP, NS))
+    e["frames_in_flight"] = NS
+    d = out["dense"]
+    d["what"] = "same call sequence with X265B200_PASS_COEF: every raw DCT coefficient returns to the host (2 bytes per sample, the round-1 contract)"
+    e["dense"] = d
+    e["limit"] = ("levels: the host -> device copy of the two padded planes (37.7 MB per frame pair); dense: the device -> host copy of 70 MB per frame pair; "
+                  "see per_rank_GBps against the PCIe Gen5 x16 ceiling of ~55 GB/s per direction")
+    return e
 
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    steps = max(3, args.steps // 4)
-    t0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    for st in streams:
-        torch.cuda.current_stream().wait_stream(st)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    wall = (time.perf_counter() - t0) * 1e3
-    ms = max(ms, wall)          # host-side enqueue time counts for an end-to-end number
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    per_step_samples = world * F * samples * (len(SATD_SHAPES) + len(DCT_SIZES))
-    ctx.check()
-    return {"value": per_step_samples / (ms / steps * 1e-3) / 1e9, "unit": "GPixels/s", "h2d_bytes_per_step": int(h2d * F),
-            "d2h_bytes_per_step": int(d2h * F), "ms_per_step": ms / steps, "steps": steps,
-            "what": "pinned host planes -> H2D -> residual, SATD x12, DCT x4 -> D2H of every cost and coefficient; 3 frames in flight"}
+
+def job_results_copy(pkg, job, res, npass):
+    out = []
+    for i in range(npass):
+        r = res[i]
+        if r.kind == pkg.PASS_CMP:
+            out.append({"cost": np.ctypeslib.as_array(r.cost, (r.n,)).copy()})
+        elif r.kind == pkg.PASS_COEF:
+            N = job.sizes[i]
+            out.append({"coef": np.ctypeslib.as_array(r.coef, (r.n * N * N,)).copy()})
+        else:
+            N = job.sizes[i]
+            d = {"kind": r.kind, "N": N, "n": r.n, "nlevels": int(r.nlevels),
+                 "numSig": np.ctypeslib.as_array(r.numSig, (r.n,)).copy(),
+                 "sigMap": np.ctypeslib.as_array(r.sigMap, ((r.n * N * N + 31) // 32,)).copy(),
+                 "levels": np.ctypeslib.as_array(r.levels, (max(1, int(r.nlevels)),))[:int(r.nlevels)].copy()}
+            out.append(d)
+    return out
+
+
+def verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode):
+    from cpulibs import OP_SATD, Oracle
+    lib, kind = cpu_libs()
+    if kind == "reference":
+        lib.set_tier(0)
+    nth = len(os.sched_getaffinity(0))
+    orc = Oracle(DEPTH)
+    mism = blocks = coefs = 0
+    for f, res in cap.items():
+        for i, s in enumerate(SATD_SHAPES):
+            oa, ob = desc[s]
+            want = lib.pixelcmp_batch(OP_SATD, s[0], s[1], fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob, nth) if kind == "reference" \
+                else lib.pixelcmp_batch(OP_SATD, s[0], s[1], fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob)
+            mism += int((res[i]["cost"] != want).sum())
+            blocks += len(oa)
+        for i, n in enumerate(DCT_SIZES):
+            oa, ob = desc[(n, n)]
+            r = res[len(SATD_SHAPES) + i]
+            if mode == "dense":
+                if kind == "reference":
+                    want = lib.residual_dct_batch(n, fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob, nth)
+                else:
+                    want = lib.dct_batch(n, orc.residual_batch(n, n, fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob), n, (np.arange(len(oa)) * n * n).astype(np.int32))
+                mism += int((r["coef"] != want).sum())
+            else:
+                qc, qbits, add = quant_params(n, E2E_QP)
+                if kind == "reference":
+                    lv, ns = lib.tu_forward_batch(n, fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob, qc, qbits, add, nth)
+                else:
+                    lv, ns, _, _ = orc.tu_chain_batch(n, fenc_np[f], geo.stride, ref_np[f], geo.stride, oa, ob, qc, qbits, add, 40, 1,
+                                                      np.zeros(geo.plane_elems, np.uint16), geo.stride, oa)
+                mism += int((r["numSig"].astype(np.uint32) != ns).sum())
+                dense = pkg.expand_levels(r) if r["nlevels"] == int((lv != 0).sum()) else None
+                mism += int((dense != lv).sum()) if dense is not None else len(lv)
+            coefs += len(oa) * n * n
+    return {"satd_blocks": blocks, "coefs": coefs, "mismatches": mism, "frames": sorted(cap.keys()),
+            "against": "reference C primitives (oracle/_ref)" if kind == "reference" else "oracle port"}
 
 
 def main():
@@ -448,6 +709,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--traffic", default="auto", choices=["auto", "off"], help="measure the SATD kernels' DRAM traffic with ncu after the run")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the encoder-level CPU baseline (reference CLI)")
+    ap.add_argument("--encoder-frames", type=int, default=6)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -171,8 +171,11 @@ int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const void* A, intp
  * reference encoder/search.cpp:5536-5575 drives through quant.cpp:397-480 and :543-605 (no RDOQ / psy / sign hiding /
  * transform skip, scaling lists off).  quantCoeff: N*N table; qBits/add as quant.cpp:465-466; dqScale/dqShift as
  * quant.cpp:556,567.  Outputs: qCoef[n*N*N], numSig[n], recon blocks at recon + offR[i] (the prediction when
- * numSig == 0), sseZero[n] = sse(fenc, pred) (may be NULL) and sseRecon[n] = sse(fenc, recon).
- * Intermediates live in an L2-sized scratch taken from the stream-ordered allocator. */
+ * numSig == 0), sseZero[n] = sse(fenc, pred) (may be NULL) and sseRecon[n] = sse(fenc, recon).  sseZero is the only
+ * pointer that may be NULL: offF, offP, offR and sseRecon are required (ERR_ARG otherwise).
+ * Default path (x265b200_set_dct_path 0): two fused tensor-core kernels, no scratch memory.  Path 1 (validation twin) runs
+ * the stage kernels of the batched primitives over chunks whose intermediates live in an L2-sized scratch taken from the
+ * stream-ordered allocator. */
 int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
                             const int32_t* offF, const int32_t* offP, int n,
                             const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
@@ -345,6 +348,95 @@ int x265b200_weight_batch(x265b200_ctx* ctx, int sp, const void* src, intptr_t s
  * (intraCost may be NULL: no cap).  fenc and ref share `stride` (a multiple of 4 samples). */
 int x265b200_weight_cost_batch(x265b200_ctx* ctx, const void* fenc, const void* ref, intptr_t stride, int width, int height,
                                const int32_t* intraCost, const int32_t* weights, int K, uint32_t* cost, x265b200_stream stream);
+
+/* Forward half of the chain alone -- Quant::transformNxN for an inter luma TU (reference common/quant.cpp:397-480: sub_ps ->
+ * dct -> quant): qCoef[n*N*N], numSig[n], sseZero[n] = sse(fenc, pred) (may be NULL).  Arguments as x265b200_tu_chain_batch. */
+int x265b200_tu_forward_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
+                              const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int add,
+                              int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, x265b200_stream stream);
+
+/* ------------------------------------------------------------------ host-buffer layer: resident planes and frame jobs
+ *
+ * What a C++ caller in the encoder (ThreadedME, reference encoder/threadedme.cpp:207-261; the lookahead,
+ * encoder/slicetype.cpp:4467) needs between the one-block host slots and the raw device entries: the library owns the
+ * device memory, the pinned staging, the copies in both directions and the streams; the caller hands over HOST pictures and
+ * reads HOST results.  No CUDA type or call appears on the caller's side.
+ */
+
+/* Pinned host memory for pictures the encoder allocates itself (PicYuv::create, reference common/picyuv.cpp:86-118, would call
+ * this instead of X265_MALLOC), or page-locking of a buffer that already exists (PicYuv::m_picBuf), so that plane uploads are
+ * asynchronous DMA.  Uploading from ordinary pageable memory works too, at the speed of a staged copy. */
+void* x265b200_host_alloc(x265b200_ctx* ctx, size_t bytes);
+void x265b200_host_free(x265b200_ctx* ctx, void* p);
+int x265b200_host_register(x265b200_ctx* ctx, void* p, size_t bytes);
+int x265b200_host_unregister(x265b200_ctx* ctx, void* p);
+
+/* A picture plane resident in HBM with the reference's own geometry (PicYuv::create, common/picyuv.cpp:86-118): for a luma plane
+ * (hshift = vshift = 0)  stride = ceil(width / ctu) * ctu + 2 * (ctu + 32),  rows = ceil(height / ctu) * ctu + 2 * (ctu + 16),
+ * sample (0, 0) at element  origin = (ctu + 16) * stride + ctu + 32;  for a chroma plane the CTU-aligned size is shifted by
+ * hshift / vshift, the horizontal margin stays ctu + 32 and the vertical margin is (ctu + 16) >> vshift (picyuv.cpp:106-110).
+ * Block descriptors of the batched entries are element offsets from the plane base, e.g. origin + y * stride + x. */
+typedef struct x265b200_plane x265b200_plane;
+int x265b200_plane_create(x265b200_ctx* ctx, int width, int height, int ctu, int hshift, int vshift, x265b200_plane** plane);
+void x265b200_plane_destroy(x265b200_plane* plane);
+/* any output pointer may be NULL; *device is the device address of the plane base (for mixing with the batched entries) */
+int x265b200_plane_info(const x265b200_plane* plane, intptr_t* stride, int* rows, int32_t* origin, size_t* elems, void** device);
+/* Whole padded plane from a host buffer of the same geometry (PicYuv::m_picBuf).  Asynchronous when the buffer is pinned; the
+ * plane's users (frame jobs) wait for it on the device, and the copy itself waits for jobs still reading the plane. */
+int x265b200_plane_upload_padded(x265b200_plane* plane, const void* hostPlane);
+/* width x height samples at hostPic / hostStride (elements) -> the picture area, then the margins are formed on the device
+ * exactly as extendPicBorder (reference common/pixel.cpp:1044-1061) leaves them: marginX columns left and right of every
+ * picture row, then marginY copies of the first and last padded row.  Cells the reference does not write (rows below
+ * height + marginY when height is not a CTU multiple) keep their previous contents (zero after creation). */
+int x265b200_plane_upload_picture(x265b200_plane* plane, const void* hostPic, intptr_t hostStride);
+/* device -> host of the whole padded plane (for tests and for recon pictures the encoder wants back); synchronous */
+int x265b200_plane_download_padded(x265b200_plane* plane, void* hostPlane);
+/* cumulative bytes copied host -> device / device -> host by planes and frame jobs of this context */
+void x265b200_transfer_stats(const x265b200_ctx* ctx, uint64_t* h2dBytes, uint64_t* d2hBytes);
+
+/* A frame job = the analysis passes run for every frame, registered once with their block descriptors, then executed per
+ * (fenc plane, reference plane) pair.  Several frames are in flight (slots); each slot has its own stream, device outputs and
+ * pinned result buffers, so the upload of frame k+1 overlaps the kernels of frame k and the download of frame k-1.
+ * The call shape follows ThreadedME's per-row task (encoder/threadedme.cpp:207-261: descriptors fixed by the CTU grid, one
+ * result record per PU) with the whole frame as the batch.  One thread drives a job; jobs are independent. */
+typedef struct x265b200_frame_job x265b200_frame_job;
+enum {
+    X265B200_PASS_CMP = 0,              /* op(fenc block, ref block) -> int32 cost per block (SAD / SATD / SA8D) */
+    X265B200_PASS_COEF = 1,             /* residual + forward DCT -> dense int16 coefficients, N*N per TU */
+    X265B200_PASS_LEVELS = 2            /* residual + forward DCT + quant (transformNxN) -> numSig per TU, one significance bit
+                                           per coefficient, and the non-zero levels only (in TU order, raster order inside a TU) */
+};
+typedef struct x265b200_pass_result {
+    int kind;                           /* X265B200_PASS_* */
+    int n;                              /* blocks / TUs of the pass */
+    const int32_t* cost;                /* CMP: n costs */
+    const int16_t* coef;                /* COEF: n * N * N coefficients */
+    const uint16_t* numSig;             /* LEVELS: n counts */
+    const uint32_t* sigMap;             /* LEVELS: bit (i & 31) of word (i >> 5) is set iff coefficient i of the flat n * N * N array is non-zero */
+    const int16_t* levels;              /* LEVELS: the non-zero coefficients in flat order; TU t owns numSig[t] of them */
+    uint32_t nlevels;                   /* LEVELS: sum of numSig */
+} x265b200_pass_result;
+
+/* slots = frames in flight (1..8).  All planes given to x265b200_frame_job_submit must have the geometry
+ * (width, height, ctu, 0, 0) -- luma. */
+int x265b200_frame_job_create(x265b200_ctx* ctx, int width, int height, int ctu, int slots, x265b200_frame_job** job);
+void x265b200_frame_job_destroy(x265b200_frame_job* job);
+/* register a pass; offF / offR are HOST arrays of n element offsets (fenc block, reference block incl. the motion vector),
+ * copied to the device here.  Returns the pass index (>= 0) or an error.  Passes run in registration order. */
+int x265b200_frame_job_add_cmp(x265b200_frame_job* job, int op, int w, int h, const int32_t* offF, const int32_t* offR, int n);
+/* kind = X265B200_PASS_COEF (quantCoeff / qBits / add ignored) or X265B200_PASS_LEVELS (quantCoeff: N*N HOST table,
+ * qBits / add as Quant::transformNxN computes them, reference common/quant.cpp:465-466) */
+int x265b200_frame_job_add_transform(x265b200_frame_job* job, int kind, int N, const int32_t* offF, const int32_t* offR, int n,
+                                     const int32_t* quantCoeff, int qBits, int add);
+/* new descriptors for a registered pass (same n): the motion vectors of the next frame */
+int x265b200_frame_job_set_blocks(x265b200_frame_job* job, int pass, const int32_t* offF, const int32_t* offR);
+/* enqueue every pass for one frame pair; returns the slot (>= 0) whose results x265b200_frame_job_wait delivers, or an
+ * error (X265B200_ERR_ARG when the next slot in the ring has not been waited for yet).  Returns without waiting for the GPU. */
+int x265b200_frame_job_submit(x265b200_frame_job* job, x265b200_plane* fenc, x265b200_plane* ref);
+/* blocks until the slot's results are in host memory; results[p] describes pass p (maxPasses entries are filled at most).
+ * The pointers address pinned memory owned by the job and stay valid until the slot is submitted again. */
+int x265b200_frame_job_wait(x265b200_frame_job* job, int slot, x265b200_pass_result* results, int maxPasses);
+int x265b200_frame_job_pass_count(const x265b200_frame_job* job);
 
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 

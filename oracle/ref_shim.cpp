@@ -21,6 +21,10 @@
 #include "contexts.h"
 #include "temporalfilter.h"
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <cstring>
@@ -45,25 +49,99 @@ extern "C" const uint32_t PFX(entropyStateBits)[128] = { 0 };
 
 using namespace X265_NS;
 
-namespace X265_NS { extern const uint8_t lumaPartitionMapTable[]; }
+namespace X265_NS {
+extern const uint8_t lumaPartitionMapTable[];
+void setupIntrinsicDCT_sse3(EncoderPrimitives&);      /* common/vec/dct-sse3.cpp  : idct 8/16/32 */
+void setupIntrinsicDCT_ssse3(EncoderPrimitives&);     /* common/vec/dct-ssse3.cpp : dct 16/32    */
+void setupIntrinsicDCT_sse41(EncoderPrimitives&);     /* common/vec/dct-sse41.cpp : dequant_scaling */
+}
 
 namespace {
+/* persistent worker pool: bench.py's CPU arm calls a batch entry per primitive pass, and a fresh std::thread set per
+ * pass (round 1) cost more than the small passes themselves.  Work is handed out in chunks from an atomic cursor, so a
+ * slow core does not hold the pass back. */
+class Pool
+{
+public:
+    static Pool& get() { static Pool p; return p; }
+    void run(int n, int nthreads, const std::function<void(int, int)>& f)
+    {
+        if (nthreads <= 1 || n < 2) { f(0, n); return; }
+        std::unique_lock<std::mutex> callers(m_callers);        /* one parallel region at a time */
+        grow(nthreads - 1);
+        int chunk = n / (nthreads * 8);
+        if (chunk < 1) chunk = 1;
+        {
+            std::lock_guard<std::mutex> g(m_mu);
+            m_fn = &f; m_n = n; m_chunk = chunk; m_cursor = 0; m_active = nthreads - 1; m_pending = nthreads - 1; m_gen++;
+        }
+        m_cv.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m_mu);
+        m_done.wait(g, [this] { return m_pending == 0; });
+        m_fn = nullptr;
+    }
+private:
+    Pool() {}
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> g(m_mu); m_quit = true; m_gen++; }
+        m_cv.notify_all();
+        for (auto& t : m_threads) t.join();
+    }
+    void grow(int want)
+    {
+        while ((int)m_threads.size() < want)
+        {
+            int id = (int)m_threads.size();
+            m_threads.emplace_back([this, id] { loop(id); });
+        }
+    }
+    void work()
+    {
+        for (;;)
+        {
+            int lo = m_cursor.fetch_add(m_chunk);
+            if (lo >= m_n) break;
+            int hi = lo + m_chunk < m_n ? lo + m_chunk : m_n;
+            (*m_fn)(lo, hi);
+        }
+    }
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> g(m_mu);
+                m_cv.wait(g, [&] { return m_gen != seen; });
+                seen = m_gen;
+                if (m_quit) return;
+                if (id >= m_active) continue;
+            }
+            work();
+            std::lock_guard<std::mutex> g(m_mu);
+            if (--m_pending == 0) m_done.notify_all();
+        }
+    }
+    std::vector<std::thread> m_threads;
+    std::mutex m_mu, m_callers;
+    std::condition_variable m_cv, m_done;
+    const std::function<void(int, int)>* m_fn = nullptr;
+    std::atomic<int> m_cursor{0};
+    int m_n = 0, m_chunk = 1, m_active = 0, m_pending = 0;
+    uint64_t m_gen = 0;
+    bool m_quit = false;
+};
+
 template<typename F>
 void parfor(int n, int nthreads, F f)
 {
-    if (nthreads <= 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    int chunk = (n + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++)
-    {
-        int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-        if (lo >= hi) break;
-        th.emplace_back([=] { f(lo, hi); });
-    }
-    for (auto& t : th) t.join();
+    Pool::get().run(n, nthreads, std::function<void(int, int)>(f));
 }
 
 EncoderPrimitives g_c;     // plain C table + aliases
+EncoderPrimitives g_simd;  // g_c with the reference's SSE3 / SSSE3 / SSE4.1 intrinsic DCT tier layered on top (vec-primitives.cpp:58-81)
 EncoderPrimitives g_lp;    // copy with enableLowpassDCTPrimitives applied (standard_dct bound)
 bool g_ready = false;
 
@@ -75,6 +153,11 @@ void ensure()
     setupAliasPrimitives(g_c);
     /* HBD alias trampolines dispatch through the global table (primitives.cpp:98-168) */
     memcpy(&primitives, &g_c, sizeof(g_c));
+    /* the best table this image can build: no nasm/yasm, so the .asm tier is out, but the intrinsic tier compiles with g++ */
+    memcpy(&g_simd, &g_c, sizeof(g_c));
+    setupIntrinsicDCT_sse3(g_simd);
+    setupIntrinsicDCT_ssse3(g_simd);
+    setupIntrinsicDCT_sse41(g_simd);
     g_ready = true;
 }
 
@@ -296,18 +379,57 @@ int ref_pixelcmp_batch(int op, int w, int h, const pixel* A, intptr_t sa, const 
     return 0;
 }
 
+/* tier = 0: plain C table; 1: C + the SSE intrinsic DCT tier (what x265_setup_primitives gives a CPU with SSE4.1 when the
+ * .asm tier is not built) */
+static int g_tier = 0;
+void ref_set_tier(int tier) { ensure(); g_tier = tier ? 1 : 0; }
+static const EncoderPrimitives& tab() { return g_tier ? g_simd : g_c; }
+
+/* one transform slot of the chosen tier, for pinning the intrinsic functions against the C ones */
+void ref_tier_dct(int tier, int n, const int16_t* src, int16_t* dst, intptr_t stride)
+{ ensure(); (tier ? g_simd : g_c).cu[trIdx(n)].dct(src, dst, stride); }
+void ref_tier_idct(int tier, int n, const int16_t* src, int16_t* dst, intptr_t stride)
+{ ensure(); (tier ? g_simd : g_c).cu[trIdx(n)].idct(src, dst, stride); }
+
+/* extendPicBorder (common/pixel.cpp:1044-1061) on a padded plane; pic points at sample (0, 0) */
+void ref_extend_pic_border(pixel* pic, intptr_t stride, int width, int height, int marginX, int marginY)
+{ ensure(); extendPicBorder(pic, stride, width, height, marginX, marginY); }
+
+/* Quant::transformNxN's slot sequence for an inter luma TU (common/quant.cpp:397-480 without RDOQ / sign hiding):
+ * sub_ps -> dct -> quant; levels[n*N*N], numSig[n] */
+int ref_tu_forward_batch(int N, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb, const int32_t* offA, const int32_t* offB, int n,
+                         const int32_t* quantCoeff, int qBits, int add, int16_t* levels, uint32_t* numSig, int nthreads)
+{
+    ensure();
+    int cu = trIdx(N);
+    const EncoderPrimitives& t = tab();
+    parfor(n, nthreads, [=, &t](int lo, int hi) {
+        ALIGN_VAR_32(int16_t, resi[32 * 32]);
+        ALIGN_VAR_32(int16_t, coef[32 * 32]);
+        ALIGN_VAR_32(int32_t, deltaU[32 * 32]);
+        for (int i = lo; i < hi; i++)
+        {
+            t.cu[cu].sub_ps(resi, N, A + offA[i], B + offB[i], sa, sb);
+            t.cu[cu].dct(resi, coef, N);
+            numSig[i] = t.quant(coef, quantCoeff, deltaU, levels + (size_t)i * N * N, qBits, add, N * N);
+        }
+    });
+    return 0;
+}
+
 /* residual via the reference's own sub_ps slot (pixel.cpp), then dct slot, per block */
 int ref_residual_dct_batch(int N, const pixel* A, intptr_t sa, const pixel* B, intptr_t sb,
                            const int32_t* offA, const int32_t* offB, int n, int16_t* out, int nthreads)
 {
     ensure();
     int cu = trIdx(N);
-    parfor(n, nthreads, [=](int lo, int hi) {
+    const EncoderPrimitives& t = tab();
+    parfor(n, nthreads, [=, &t](int lo, int hi) {
         ALIGN_VAR_32(int16_t, resi[32 * 32]);
         for (int i = lo; i < hi; i++)
         {
-            g_c.cu[cu].sub_ps(resi, N, A + offA[i], B + offB[i], sa, sb);
-            g_c.cu[cu].dct(resi, out + (size_t)i * N * N, N);
+            t.cu[cu].sub_ps(resi, N, A + offA[i], B + offB[i], sa, sb);
+            t.cu[cu].dct(resi, out + (size_t)i * N * N, N);
         }
     });
     return 0;
@@ -317,9 +439,10 @@ int ref_dct_batch(int N, const int16_t* src, intptr_t srcStride, const int32_t* 
 {
     ensure();
     int cu = trIdx(N);
-    parfor(n, nthreads, [=](int lo, int hi) {
+    const EncoderPrimitives& t = tab();
+    parfor(n, nthreads, [=, &t](int lo, int hi) {
         for (int i = lo; i < hi; i++)
-            g_c.cu[cu].dct(src + off[i], out + (size_t)i * N * N, srcStride);
+            t.cu[cu].dct(src + off[i], out + (size_t)i * N * N, srcStride);
     });
     return 0;
 }

@@ -633,6 +633,30 @@ EXPORT void orc_residual_batch(int w, int h, const pixel* A, intptr_t sa, const 
                 out[(size_t)i * w * h + y * w + x] = (int16_t)((int)A[offA[i] + y * sa + x] - (int)B[offB[i] + y * sb + x]);
 }
 
+/* extendPicBorder (common/pixel.cpp:1044-1061; the row part is extendCURowColBorder, pixel.cpp:1018-1038 without the
+ * word-splat shortcuts): marginX copies of the first / last sample of every picture row to its left / right, then
+ * marginY copies of the first and the last padded row above / below.  pic points at sample (0, 0). */
+EXPORT void orc_extend_pic_border(pixel* pic, intptr_t stride, int width, int height, int marginX, int marginY)
+{
+    for (int y = 0; y < height; y++)
+    {
+        pixel* row = pic + (intptr_t)y * stride;
+        for (int x = 0; x < marginX; x++)
+        {
+            row[-marginX + x] = row[0];
+            row[width + x] = row[width - 1];
+        }
+    }
+    /* the reference copies `stride` samples per row (pixel.cpp:1052, :1057), i.e. the whole buffer row, including the
+     * columns between width + marginX and the row end when the picture is narrower than the CTU-aligned plane */
+    for (int y = 1; y <= marginY; y++)
+        for (int x = -marginX; x < (int)stride - marginX; x++)
+        {
+            pic[x - (intptr_t)y * stride] = pic[x];
+            pic[x + (intptr_t)(height - 1 + y) * stride] = pic[x + (intptr_t)(height - 1) * stride];
+        }
+}
+
 /* Inter luma TU reconstruction chain without RDOQ / psy / sign hiding / transform skip, scaling lists off:
  * encoder/search.cpp:5536-5575 (estimateResidualQT) -> common/quant.cpp:397-480 (transformNxN: dct, quant) and
  * quant.cpp:543-605 (invtransformNxN: dequant_normal, DC-only shortcut :588-598, idct), pixel.cpp sub_ps / add_ps

@@ -273,6 +273,10 @@ class _Base:
         return q, ns.value, z.value, r.value
 
     # ---- tables -----------------------------------------------------------------------
+    def extend_pic_border(self, plane, origin, stride, width, height, marginX, marginY):
+        """in place on `plane` (numpy, pixel dtype); origin = element offset of sample (0, 0)"""
+        self._f("extend_pic_border", None)(_ptr(plane, origin), C.c_ssize_t(stride), width, height, marginX, marginY)
+
     def dct_matrix(self, n):
         out = np.zeros(n * n, np.int16)
         self._f("get_dct_matrix", None)(n, _ptr(out))
@@ -476,6 +480,29 @@ class Reference(_Base):
         self._f("residual_dct_batch")(N, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
                                       _ptr(offA), _ptr(offB), n, _ptr(out), nthreads)
         return out
+
+    def set_tier(self, tier):
+        """0 = plain C table, 1 = C + the reference's SSE intrinsic DCT tier (batch entries only)"""
+        self._f("set_tier", None)(int(tier))
+
+    def tier_dct(self, tier, n, src, osrc, stride):
+        dst = np.zeros(n * n, np.int16)
+        self._f("tier_dct", None)(tier, n, _ptr(src, osrc), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def tier_idct(self, tier, n, src, stride):
+        dst = np.zeros(n * stride, np.int16)
+        self._f("tier_idct", None)(tier, n, _ptr(src), _ptr(dst), C.c_ssize_t(stride))
+        return dst
+
+    def tu_forward_batch(self, N, A, sa, B, sb, offA, offB, qc, qbits, add, nthreads=1):
+        """sub_ps -> dct -> quant per TU through the reference's slots: (levels[n*N*N], numSig[n])"""
+        n = len(offA)
+        lv = np.zeros(n * N * N, np.int16); ns = np.zeros(n, np.uint32)
+        qc = np.ascontiguousarray(qc, np.int32)
+        self._f("tu_forward_batch")(N, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb), _ptr(offA), _ptr(offB), n,
+                                    _ptr(qc), int(qbits), int(add), _ptr(lv), _ptr(ns), nthreads)
+        return lv, ns
 
     def count_nonnull_slots(self):
         return self.lib.ref_count_nonnull_slots()

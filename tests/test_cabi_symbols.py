@@ -18,6 +18,20 @@ def test_library_built_and_exports_all_declared_symbols():
     assert not missing, missing
 
 
+def test_glue_libraries_export_their_header():
+    """the per-depth table fillers export what include/x265b200_glue.h declares (built only where the reference headers exist)"""
+    syms = pkg.declared_symbols(pkg.GLUE_HEADER)
+    assert {"x265b200_setup_primitives", "x265b200_glue_context", "x265b200_glue_depth", "x265b200_glue_status"} <= set(syms)
+    built = [d for d in (8, 10, 12) if os.path.exists(pkg.glue_path(d))]
+    if not built:
+        pytest.skip("glue libraries not built (no reference headers)")
+    pkg.load_library()
+    for d in built:
+        lib = ctypes.CDLL(pkg.glue_path(d))
+        assert not [s for s in syms if not hasattr(lib, s)], d
+        assert lib.x265b200_glue_depth() == d
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

@@ -42,14 +42,14 @@ def test_pixelcmp_frame_all_shapes(depth, torch_mod):
     ctx.check()
 
 
-def test_sad_multi_and_ragged(torch_mod):
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_sad_multi_and_ragged(depth, torch_mod):
     torch = torch_mod
     from gpulib import context
-    depth = 10
     ctx = context(depth); orc = Oracle(depth)
     geo = Geometry(256, 128)
     A = make_plane(geo, depth, 1); B = make_plane(geo, depth, 2)
-    dA, dB = dev(A.view(np.int16)), dev(B.view(np.int16))
+    dA, dB = dev(A.view(np.int16 if depth > 8 else np.uint8)), dev(B.view(np.int16 if depth > 8 else np.uint8))
     for (w, h), K in (((16, 16), 4), ((8, 8), 3), ((64, 32), 9), ((12, 16), 5), ((8, 4), 4), ((16, 8), 3)):   # last two: strip kernel
         offA, offB0 = tile_blocks(geo, w, h, seed=5)
         n = len(offA)

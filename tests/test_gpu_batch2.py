@@ -62,10 +62,10 @@ def test_sse_ss_ssd_s_sa8d_batches(depth):
     ctx.check()
 
 
-def test_ads_batch():
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_ads_batch(depth):
     import torch
     from gpulib import context
-    depth = 10
     ctx = context(depth); orc = Oracle(depth)
     rng = np.random.default_rng(5)
     stride = 4128
@@ -108,15 +108,17 @@ def test_quant_family_batches(depth):
             du = torch.zeros(n * numCoeff, dtype=torch.int32, device="cuda")
             sig = torch.zeros(n, dtype=torch.int32, device="cuda")
             ctx.quant_batch(dev(coef), dev(qc), du, q, qbits, add, numCoeff, n, sig)
-            for i in (0, 1, n // 2, n - 1):
+            hs, hq, hdu = sig.cpu().numpy(), q.cpu().numpy(), du.cpu().numpy()
+            for i in range(n):                                  # every block of the batch
                 r, rq, rdu = orc.quant(coef[i * numCoeff:(i + 1) * numCoeff].copy(), qc, qbits, add, numCoeff)
-                assert int(sig[i]) == r
-                assert np.array_equal(q[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rq)
-                assert np.array_equal(du[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rdu)
+                assert int(hs[i]) == r, (numCoeff, i)
+                assert np.array_equal(hq[i * numCoeff:(i + 1) * numCoeff], rq), (numCoeff, i)
+                assert np.array_equal(hdu[i * numCoeff:(i + 1) * numCoeff], rdu), (numCoeff, i)
             ctx.quant_batch(dev(coef), dev(qc), None, q, qbits, 1 << (qbits - 1), numCoeff, n, sig)
-            for i in (0, n - 1):
+            hs, hq = sig.cpu().numpy(), q.cpu().numpy()
+            for i in range(n):
                 r, rq = orc.nquant(coef[i * numCoeff:(i + 1) * numCoeff].copy(), qc, qbits, 1 << (qbits - 1), numCoeff)
-                assert int(sig[i]) == r and np.array_equal(q[i * numCoeff:(i + 1) * numCoeff].cpu().numpy(), rq)
+                assert int(hs[i]) == r and np.array_equal(hq[i * numCoeff:(i + 1) * numCoeff], rq), (numCoeff, i)
         if numCoeff % 8 == 0:
             out = torch.zeros(n * numCoeff, dtype=torch.int16, device="cuda")
             for scale, shift in ((40, 1), (72 << 4, 5), (64 << 8, 10)):

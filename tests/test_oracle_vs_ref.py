@@ -830,3 +830,58 @@ def test_motion_estimate_sea(libs):
         assert a == b, (case, w, h, a, b)
         moved += max(abs(a[0] - int(np.clip(qmvp[0], 4 * minx, 4 * maxx))), abs(a[1] - int(np.clip(qmvp[1], 4 * miny, 4 * maxy)))) >= 8
     assert moved > 25
+
+
+def test_extend_pic_border(libs):
+    """border extension of an uploaded picture (x265b200_plane_upload_picture) follows extendPicBorder, pixel.cpp:1044-1061"""
+    o, r = libs
+    rng = np.random.default_rng(77)
+    for (w, h, mx, my) in ((96, 40, 24, 9), (352, 288, 96, 80), (33, 17, 5, 3)):
+        stride, rows = w + 2 * mx + 8, h + 2 * my + 4
+        base = rng.integers(0, o.pmax + 1, stride * rows).astype(o.pix)
+        origin = my * stride + mx
+        a, b = base.copy(), base.copy()
+        o.extend_pic_border(a, origin, stride, w, h, mx, my)
+        r.extend_pic_border(b, origin, stride, w, h, mx, my)
+        assert np.array_equal(a, b), (w, h)
+        assert not np.array_equal(a, base)
+
+
+def test_intrinsic_dct_tier_equals_c(libs):
+    """the SSE intrinsic transforms the CPU baseline may use (common/vec/dct-ssse3.cpp, dct-sse3.cpp) equal the C slots"""
+    o, r = libs
+    rng = np.random.default_rng(5)
+    lim = 1 << (o.depth)
+    for n in (8, 16, 32):
+        for trial in range(4):
+            src = rng.integers(-lim + 1, lim, n * n).astype(np.int16)
+            assert np.array_equal(r.tier_dct(1, n, src, 0, n), r.tier_dct(0, n, src, 0, n)), n
+            assert np.array_equal(r.tier_dct(1, n, src, 0, n), o.dct(n, src, 0, n)), n
+            coef = o.dct(n, src, 0, n)
+            assert np.array_equal(r.tier_idct(1, n, coef, n), r.tier_idct(0, n, coef, n)), n
+
+
+def test_tu_forward_batch(libs):
+    """sub_ps -> dct -> quant through the reference's slots (both tiers) vs the oracle's chain"""
+    from frames import Geometry, make_plane, tile_blocks
+    o, r = libs
+    geo = Geometry(352, 288)
+    F = make_plane(geo, o.depth, 11, "natural"); P = make_plane(geo, o.depth, 12, "natural")
+    flat = [26214, 23302, 20560, 18396, 16384, 14564]
+    for N, qp in ((32, 30), (16, 36), (8, 24), (4, 41)):
+        offF, offP = tile_blocks(geo, N, N, seed=3, merange=9)
+        per, rem = qp // 6, qp % 6
+        tshift = 15 - o.depth - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+        qbits = 14 + per + tshift
+        add = 171 << (qbits - 9)
+        qc = np.full(N * N, flat[rem], np.int32)
+        recon = np.zeros(geo.plane_elems, o.pix)
+        rq, rns, _, _ = o.tu_chain_batch(N, F, geo.stride, P, geo.stride, offF, offP, qc, qbits, add, 40 << per, 20 - 14 - tshift if 20 - 14 - tshift > 0 else 1,
+                                         recon, geo.stride, offF)
+        for tier in (0, 1):
+            r.set_tier(tier)
+            lv, ns = r.tu_forward_batch(N, F, geo.stride, P, geo.stride, offF, offP, qc, qbits, add, nthreads=3)
+            assert np.array_equal(lv, rq), (N, tier)
+            assert np.array_equal(ns, rns), (N, tier)
+        r.set_tier(0)
+        assert (rns > 0).any()

@@ -21,14 +21,21 @@ _lib = None
 
 def build_library(glue=True):
     """compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)"""
-    subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "lib"], check=True)
-    if glue and os.path.isdir("/root/reference/source") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "cfg", "x265_config.h")):
+    subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "all"], check=True)
+    if glue and os.path.isdir("/root/reference/source"):
         subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "glue"], check=True)
 
 
-def declared_symbols():
-    """every function name include/x265b200.h declares"""
-    text = open(HEADER).read()
+GLUE_HEADER = os.path.join(ROOT, "include", "x265b200_glue.h")
+
+
+def glue_path(depth):
+    return os.path.join(PKG_DIR, "lib", "libx265b200_glue_%d.so" % depth)
+
+
+def declared_symbols(header=HEADER):
+    """every function name the header (include/x265b200.h by default) declares"""
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(x265b200_[A-Za-z0-9_]+)\s*\(", text)))
 
@@ -45,6 +52,11 @@ def load_library():
             getattr(_lib, name).restype = C.c_uint64
         for name in ("x265b200_quant", "x265b200_nquant", "x265b200_copy_cnt"):
             getattr(_lib, name).restype = C.c_uint32
+        _lib.x265b200_host_alloc.restype = C.c_void_p
+        _lib.x265b200_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.x265b200_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("x265b200_host_free", "x265b200_plane_destroy", "x265b200_frame_job_destroy", "x265b200_transfer_stats"):
+            getattr(_lib, name).restype = None
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
                      "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
                      "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy", "x265b200_denoise_dct"):
@@ -101,6 +113,25 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.x265b200_launch_count(self.h))
+
+    def transfer_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.x265b200_transfer_stats(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def host_alloc(self, nbytes):
+        """pinned host memory as a numpy uint8 array (freed with host_free)"""
+        p = self.lib.x265b200_host_alloc(self.h, nbytes)
+        if not p:
+            raise RuntimeError("x265b200_host_alloc failed")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (nbytes,)), p
+
+    def host_free(self, p):
+        self.lib.x265b200_host_free(self.h, p)
+
+    def tu_forward_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, qCoef, numSig, sseZero=None, stream=0):
+        self._call("x265b200_tu_forward_batch", N, _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
+                   _dp(qc), qbits, add, _dp(qCoef), _dp(numSig), _dp(sseZero), C.c_void_p(stream))
 
     def sm_count(self):
         return int(self.lib.x265b200_sm_count(self.h))
@@ -240,6 +271,123 @@ class Context:
     def residual_batch(self, w, h, A, sa, B, sb, offA, offB, dst, stream=0):
         self._call("x265b200_residual_batch", w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
                    int(offA.numel()), _dp(dst), C.c_void_p(stream))
+
+
+PASS_CMP, PASS_COEF, PASS_LEVELS = 0, 1, 2
+
+
+class PassResult(C.Structure):
+    """x265b200_pass_result (include/x265b200.h)"""
+    _fields_ = [("kind", C.c_int), ("n", C.c_int), ("cost", C.POINTER(C.c_int32)), ("coef", C.POINTER(C.c_int16)),
+                ("numSig", C.POINTER(C.c_uint16)), ("sigMap", C.POINTER(C.c_uint32)), ("levels", C.POINTER(C.c_int16)),
+                ("nlevels", C.c_uint32)]
+
+
+class Plane:
+    """x265b200_plane: a picture plane resident in HBM with PicYuv's geometry; uploads take host (numpy / pinned) buffers"""
+
+    def __init__(self, ctx, width, height, ctu=64, hshift=0, vshift=0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._call("x265b200_plane_create", int(width), int(height), int(ctu), int(hshift), int(vshift), C.byref(h))
+        self.h = h
+        stride, rows, origin, elems, dev = C.c_ssize_t(), C.c_int(), C.c_int32(), C.c_size_t(), C.c_void_p()
+        ctx.lib.x265b200_plane_info(self.h, C.byref(stride), C.byref(rows), C.byref(origin), C.byref(elems), C.byref(dev))
+        self.stride, self.rows, self.origin, self.elems, self.device_ptr = stride.value, rows.value, origin.value, elems.value, dev.value
+
+    def _r(self, name, *args):
+        r = getattr(self.ctx.lib, name)(self.h, *args)
+        if r != 0:
+            raise RuntimeError("%s failed (%d): %s" % (name, r, self.ctx.lib.x265b200_last_error(self.ctx.h).decode()))
+
+    def upload_padded(self, host, addr=None):
+        """host: numpy array of `elems` pixels, or a raw address (pinned memory)"""
+        self._r("x265b200_plane_upload_padded", C.c_void_p(addr if addr is not None else host.ctypes.data))
+
+    def upload_picture(self, host, host_stride, addr=None):
+        self._r("x265b200_plane_upload_picture", C.c_void_p(addr if addr is not None else host.ctypes.data), _ss(host_stride))
+
+    def download_padded(self):
+        out = np.empty(self.elems, self.ctx.pix)
+        self._r("x265b200_plane_download_padded", _p(out))
+        return out
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.x265b200_plane_destroy(self.h)
+            self.h = None
+
+
+class FrameJob:
+    """x265b200_frame_job: analysis passes registered once, run per (fenc plane, reference plane) pair, several frames in flight"""
+
+    def __init__(self, ctx, width, height, ctu=64, slots=3):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._call("x265b200_frame_job_create", int(width), int(height), int(ctu), int(slots), C.byref(h))
+        self.h = h
+        self.sizes = []         # N (transform) or None per pass
+
+    def _r(self, name, *args):
+        r = getattr(self.ctx.lib, name)(self.h, *args)
+        if r < 0:
+            raise RuntimeError("%s failed (%d): %s" % (name, r, self.ctx.lib.x265b200_last_error(self.ctx.h).decode()))
+        return r
+
+    def add_cmp(self, op, w, h, offF, offR):
+        offF = np.ascontiguousarray(offF, np.int32); offR = np.ascontiguousarray(offR, np.int32)
+        self.sizes.append(None)
+        return self._r("x265b200_frame_job_add_cmp", int(op), w, h, _p(offF), _p(offR), len(offF))
+
+    def add_transform(self, kind, N, offF, offR, qc=None, qbits=0, add=0):
+        offF = np.ascontiguousarray(offF, np.int32); offR = np.ascontiguousarray(offR, np.int32)
+        qp = _p(np.ascontiguousarray(qc, np.int32)) if qc is not None else C.c_void_p(0)
+        self.sizes.append(N)
+        return self._r("x265b200_frame_job_add_transform", int(kind), N, _p(offF), _p(offR), len(offF), qp, int(qbits), int(add))
+
+    def set_blocks(self, p, offF, offR):
+        offF = np.ascontiguousarray(offF, np.int32); offR = np.ascontiguousarray(offR, np.int32)
+        self._r("x265b200_frame_job_set_blocks", int(p), _p(offF), _p(offR))
+
+    def submit(self, fenc, ref):
+        return self._r("x265b200_frame_job_submit", fenc.h, ref.h)
+
+    def wait(self, slot, copy=True):
+        """list of dicts, one per pass, numpy views (copies when copy=True) of the job's pinned result memory"""
+        npass = self.ctx.lib.x265b200_frame_job_pass_count(self.h)
+        arr = (PassResult * npass)()
+        self._r("x265b200_frame_job_wait", int(slot), arr, npass)
+        out = []
+        for i in range(npass):
+            r = arr[i]
+            fin = (lambda a: a.copy()) if copy else (lambda a: a)
+            if r.kind == PASS_CMP:
+                out.append({"kind": r.kind, "cost": fin(np.ctypeslib.as_array(r.cost, (r.n,)))})
+            elif r.kind == PASS_COEF:
+                N = self.sizes[i]
+                out.append({"kind": r.kind, "coef": fin(np.ctypeslib.as_array(r.coef, (r.n * N * N,)))})
+            else:
+                N = self.sizes[i]
+                words = (r.n * N * N + 31) // 32
+                out.append({"kind": r.kind, "N": N, "n": r.n, "nlevels": int(r.nlevels),
+                            "numSig": fin(np.ctypeslib.as_array(r.numSig, (r.n,))),
+                            "sigMap": fin(np.ctypeslib.as_array(r.sigMap, (words,))),
+                            "levels": fin(np.ctypeslib.as_array(r.levels, (max(int(r.nlevels), 1),))[:int(r.nlevels)])})
+        return out
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.x265b200_frame_job_destroy(self.h)
+            self.h = None
+
+
+def expand_levels(res):
+    """dense int16 levels of a LEVELS pass result (what the entropy coder's significance walk reconstructs)"""
+    total = res["n"] * res["N"] * res["N"]
+    bits = np.unpackbits(res["sigMap"].view(np.uint8), bitorder="little")[:total].astype(bool)
+    dense = np.zeros(total, np.int16)
+    dense[bits] = res["levels"]
+    return dense
 
 
 class HostAPI:

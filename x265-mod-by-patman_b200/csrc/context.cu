@@ -21,11 +21,11 @@ int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e)
 {
     if (!ctx) return code;
     std::lock_guard<std::mutex> g(ctx->mu);
-    int expected = 0;
-    if (ctx->status.compare_exchange_strong(expected, code))
+    if (ctx->status.load() == 0)
     {
-        ctx->err = what;
-        if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
+        if (e != cudaSuccess) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(ctx->err, sizeof(ctx->err), "%s", what);
+        ctx->status.store(code);        // published after the text: a reader that sees the status sees the whole message
     }
     return code;
 }
@@ -35,11 +35,11 @@ static Lane* lane_acquire(x265b200_ctx* ctx)
     if (cudaSetDevice(ctx->device) != cudaSuccess) { fail(ctx, X265B200_ERR_CUDA, "cudaSetDevice"); return nullptr; }
     {
         std::lock_guard<std::mutex> g(ctx->mu);
-        if (!ctx->free_lanes.empty())
+        while (!ctx->free_lanes.empty())
         {
             Lane* l = ctx->free_lanes.back();
             ctx->free_lanes.pop_back();
-            return l;
+            if (l) return l;                    // the pool never hands out a null lane
         }
     }
     Lane* l = new Lane();
@@ -54,6 +54,7 @@ static Lane* lane_acquire(x265b200_ctx* ctx)
         delete l;
         return nullptr;
     }
+    l->cap = LANE_BYTES;
     std::lock_guard<std::mutex> g(ctx->mu);
     ctx->all_lanes.push_back(l);
     return l;
@@ -61,8 +62,32 @@ static Lane* lane_acquire(x265b200_ctx* ctx)
 
 static void lane_release(x265b200_ctx* ctx, Lane* l)
 {
+    if (!l) return;
     std::lock_guard<std::mutex> g(ctx->mu);
     ctx->free_lanes.push_back(l);
+}
+
+// Whole-plane slots (frameInitLowres, weight_pp on a padded lowres plane: reference common/lowres.cpp:385,
+// encoder/slicetype.cpp:880) stage far more than one block: the lane's two buffers are replaced by larger ones.  Only called
+// before anything of the current call has been written into the lane (every entry allocates first, then packs).
+static bool lane_grow(x265b200_ctx* ctx, Lane* l, size_t need)
+{
+    if (need > LANE_MAX_BYTES) { fail(ctx, X265B200_ERR_ARG, "host call exceeds the maximum staging size (2 GiB)"); return false; }
+    size_t cap = l->cap;
+    while (cap < need) cap <<= 1;
+    uint8_t *h = nullptr, *d = nullptr;
+    cudaError_t e = cudaStreamSynchronize(l->stream);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h, cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d, cap);
+    if (e != cudaSuccess)
+    {
+        if (h) cudaFreeHost(h);
+        fail(ctx, X265B200_ERR_CUDA, "lane growth", e);
+        return false;
+    }
+    cudaFreeHost(l->h); cudaFree(l->d);
+    l->h = h; l->d = d; l->cap = cap;
+    return true;
 }
 
 // One host call: bump-allocates matching host/device staging, then upload -> kernels -> download.
@@ -76,9 +101,10 @@ struct Call
     bool ok() const { return lane != nullptr; }
     size_t alloc(size_t bytes)
     {
+        if (!lane) return 0;                // an earlier alloc of this call already failed
         size_t off = (used + 63) & ~(size_t)63;
         used = off + bytes;
-        if (used > LANE_BYTES) { fail(ctx, X265B200_ERR_ARG, "host call exceeds staging size"); lane_release(ctx, lane); lane = nullptr; return 0; }
+        if (used > lane->cap && !lane_grow(ctx, lane, used)) { lane_release(ctx, lane); lane = nullptr; return 0; }
         return off;
     }
     template<typename T> T* h(size_t off) { return (T*)(lane->h + off); }
@@ -149,7 +175,7 @@ extern "C" int x265b200_open(int device, int bit_depth, x265b200_ctx** out)
     int r = upload_transform_tables(ctx);
     if (r == X265B200_OK) r = upload_filter_tables(ctx);
     if (r == X265B200_OK) r = upload_mma_tables(ctx);
-    if (r != X265B200_OK) { fprintf(stderr, "x265b200: %s\n", ctx->err.c_str()); delete ctx; return r; }
+    if (r != X265B200_OK) { fprintf(stderr, "x265b200: %s\n", ctx->err); delete ctx; return r; }
     *out = ctx;
     return X265B200_OK;
 }
@@ -179,7 +205,7 @@ extern "C" int x265b200_set_dct_path(x265b200_ctx* ctx, int path)
 extern "C" int x265b200_bit_depth(const x265b200_ctx* ctx) { return ctx ? ctx->depth : 0; }
 extern "C" int x265b200_sm_count(const x265b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" int x265b200_status(const x265b200_ctx* ctx) { return ctx ? ctx->status.load() : X265B200_ERR_ARG; }
-extern "C" const char* x265b200_last_error(const x265b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" const char* x265b200_last_error(const x265b200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t x265b200_launch_count(const x265b200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 // ------------------------------------------------------------------ host entries: metrics

@@ -12,7 +12,8 @@
 namespace b200 {
 
 constexpr int FENC_STRIDE = 64;             // common.h:71
-constexpr size_t LANE_BYTES = 1u << 20;     // staging per host-call lane (pinned + device)
+constexpr size_t LANE_BYTES = 1u << 20;     // initial staging per host-call lane (pinned + device); lanes grow on demand
+constexpr size_t LANE_MAX_BYTES = (size_t)2 << 30;   // a single host call may stage at most this much (whole 8K planes fit)
 
 // One host-call lane: a stream plus pinned/device staging.  A thread that enters a host (per-call)
 // entry borrows a lane for the duration of the call, so slots are re-entrant from any number of
@@ -22,6 +23,7 @@ struct Lane
     cudaStream_t stream = nullptr;
     uint8_t* h = nullptr;       // pinned host staging
     uint8_t* d = nullptr;       // device staging
+    size_t cap = 0;             // bytes of each staging buffer
 };
 
 } // namespace b200
@@ -35,8 +37,9 @@ struct x265b200_ctx
     int dct_path = 0;           // 0 = tensor-core IMMA for N >= 16 (default), 1 = CUDA-core butterfly everywhere
     std::atomic<int> status{0};
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // planes + frame jobs (x265b200_transfer_stats)
     std::mutex mu;
-    std::string err;
+    char err[256] = {0};        // first error, written once under `mu` before `status` is published (readers need no lock)
     std::vector<b200::Lane*> free_lanes;
     std::vector<b200::Lane*> all_lanes;
 };

@@ -868,8 +868,11 @@ static int subpel_cmp_launch(x265b200_ctx* ctx, int taps, int accumulate, int op
     int perCta = 128 / G;
     long long cands = (long long)n * K;
     if (cands > 0x7fffffff) return fail(ctx, X265B200_ERR_ARG, "subpel_cmp: too many candidates");
-#define SP(PIX, OP_, TW1_, TH2_, TAPS_) subpel_cmp_kernel<PIX, OP_, TW1_, TH2_, TAPS_><<<ceil_div(cands, perCta), 128, perCta * smem, st>>>(  \
-        (const PIX*)fenc, sf, (const PIX*)ref, sr, offF, offR, frac, K, (int)cands, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost, accumulate)
+    // the 25 PU shapes need at most 47104 bytes (16x16); other multiples of 4 (28x8: 53760) go over the 48 KB default
+#define SP(PIX, OP_, TW1_, TH2_, TAPS_) do { \
+        if (perCta * smem > 48 * 1024) B200_CUDA(ctx, cudaFuncSetAttribute(subpel_cmp_kernel<PIX, OP_, TW1_, TH2_, TAPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(perCta * smem))); \
+        subpel_cmp_kernel<PIX, OP_, TW1_, TH2_, TAPS_><<<ceil_div(cands, perCta), 128, perCta * smem, st>>>(  \
+        (const PIX*)fenc, sf, (const PIX*)ref, sr, offF, offR, frac, K, (int)cands, w, h, G, shift1, offset1, shift2, offset2, maxVal, cost, accumulate); } while (0)
 #define SP_SHAPE(PIX, OP_, TAPS_) do { if (wide && tall) SP(PIX, OP_, 8, 8, TAPS_); else if (wide) SP(PIX, OP_, 8, 4, TAPS_); \
                                        else if (tall) SP(PIX, OP_, 4, 8, TAPS_); else SP(PIX, OP_, 4, 4, TAPS_); } while (0)
     if (taps == 4)

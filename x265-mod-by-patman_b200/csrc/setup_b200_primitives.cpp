@@ -13,6 +13,8 @@
 #include "common.h"
 #include "primitives.h"
 #include "x265b200.h"
+#include "x265b200_glue.h"
+#include <mutex>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -207,13 +209,25 @@ void setupB200Primitives(EncoderPrimitives& p)
 // which must point at an EncoderPrimitives of this build's bit depth.  Returns 0 or an X265B200_ERR_*.
 extern "C" int x265b200_setup_primitives(void* table, int device)
 {
-    if (!X265_NS::g_b200)
+    static std::mutex openLock;         // two encoder instances may initialise at the same time
     {
-        int r = x265b200_open(device, X265_DEPTH, &X265_NS::g_b200);
-        if (r != X265B200_OK) return r;
+        std::lock_guard<std::mutex> g(openLock);
+        if (!X265_NS::g_b200)
+        {
+            int r = x265b200_open(device, X265_DEPTH, &X265_NS::g_b200);
+            if (r != X265B200_OK) return r;
+        }
     }
     X265_NS::setupB200Primitives(*(X265_NS::EncoderPrimitives*)table);
     return X265B200_OK;
+}
+/* A slot cannot report an error (SURVEY.md 8b "Errors"): the encoder polls this at a frame boundary
+ * (INTEGRATION.md shows where) and aborts loudly on a non-zero status; there is no CPU fallback to fall back to. */
+extern "C" int x265b200_glue_status(const char** message)
+{
+    if (!X265_NS::g_b200) { if (message) *message = "x265b200_setup_primitives was not called"; return X265B200_ERR_ARG; }
+    if (message) *message = x265b200_last_error(X265_NS::g_b200);
+    return x265b200_status(X265_NS::g_b200);
 }
 extern "C" x265b200_ctx* x265b200_glue_context(void) { return X265_NS::g_b200; }
 extern "C" int x265b200_glue_depth(void) { return X265_DEPTH; }

@@ -20,6 +20,10 @@ bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, co
                      int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
                      const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);   // tu_fused.cuh (transform_mma.cu)
 
+bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
+                       const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
+                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st);                  // tu_fused.cuh
+
 // recon = clip(pred + resi') with the cbf == 0 and DC-only cases, plus both distortions; 4 samples per thread
 template<typename T>
 __global__ void __launch_bounds__(256)
@@ -102,6 +106,8 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
         return fail(ctx, X265B200_ERR_ARG, "tu_chain: bad size / parameters");
     if ((strideF | strideP) & 3) return fail(ctx, X265B200_ERR_ARG, "tu_chain: plane strides must be multiples of 4 samples");
     if (n == 0) return X265B200_OK;
+    if (!fenc || !pred || !recon || !offF || !offP || !offR || !quantCoeff || !qCoef || !numSig || !sseRecon)
+        return fail(ctx, X265B200_ERR_ARG, "tu_chain: only sseZero may be NULL (offF, offP, offR and sseRecon are required)");
     cudaStream_t st = (cudaStream_t)stream;
     const int NN = N * N;
     // Default: two fused tensor-core kernels over all TUs, no scratch (tu_fused.cuh).
@@ -145,6 +151,42 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
                                                                          (unsigned long long*)(sseZero ? sseZero + c0 : nullptr), (unsigned long long*)sseRecon + c0, ctx->depth);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, X265B200_ERR_CUDA, "recon_kernel launch");
+    }
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// forward half of the chain: what Quant::transformNxN (reference common/quant.cpp:397-480) does for an inter luma TU
+extern "C" int x265b200_tu_forward_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
+                                         const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int add,
+                                         int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if ((N != 4 && N != 8 && N != 16 && N != 32) || n < 0 || qBits < 8)
+        return fail(ctx, X265B200_ERR_ARG, "tu_forward: bad size / parameters");
+    if ((strideF | strideP) & 3) return fail(ctx, X265B200_ERR_ARG, "tu_forward: plane strides must be multiples of 4 samples");
+    if (n == 0) return X265B200_OK;
+    if (!fenc || !pred || !offF || !offP || !quantCoeff || !qCoef || !numSig)
+        return fail(ctx, X265B200_ERR_ARG, "tu_forward: only sseZero may be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->dct_path == 0 && launch_tu_forward(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, qCoef, numSig, sseZero, st))
+        return X265B200_OK;
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_forward fused launch");
+    // validation twin / unaligned operands: the stage kernels over chunks whose scratch stays L2-resident
+    const int NN = N * N;
+    const int chunkTUs = (8 << 20) / NN;
+    int16_t* scratch = nullptr;
+    size_t chunkElems = (size_t)(n < chunkTUs ? n : chunkTUs) * NN;
+    B200_CUDA(ctx, cudaMallocAsync((void**)&scratch, 2 * chunkElems * sizeof(int16_t), st));
+    int rc = X265B200_OK;
+    for (int c0 = 0; c0 < n && rc == X265B200_OK; c0 += chunkTUs)
+    {
+        int m = n - c0 < chunkTUs ? n - c0 : chunkTUs;
+        rc = x265b200_residual_batch(ctx, N, N, fenc, strideF, pred, strideP, offF + c0, offP + c0, m, scratch, stream);
+        if (rc == X265B200_OK) rc = x265b200_dct_batch(ctx, X265B200_TR_DCT, N, scratch, N, nullptr, m, scratch + chunkElems, stream);
+        if (rc == X265B200_OK) rc = launch_quant(ctx, 2, scratch + chunkElems, quantCoeff, nullptr, qCoef + (size_t)c0 * NN, qBits, add, NN, m, numSig + c0, st);
+        if (rc == X265B200_OK && sseZero)
+            rc = x265b200_pixelcmp_batch(ctx, X265B200_SSE_PP, N, N, fenc, strideF, pred, strideP, offF + c0, offP + c0, m, sseZero + c0, stream);
     }
     cudaFreeAsync(scratch, st);
     return rc;

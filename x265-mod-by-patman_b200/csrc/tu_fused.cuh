@@ -825,3 +825,22 @@ bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, co
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess;
 }
+// forward half alone: residual + DCT + quant -> qCoef / numSig (/ sseZero); same preconditions as launch_tu_fused
+bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
+                       const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
+                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st)
+{
+    if (((uintptr_t)qCoef & 7) || ((uintptr_t)quantCoeff & 15) || ((sf | sp) & 3)) return false;
+    int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    int lg = N == 32 ? 5 : N == 16 ? 4 : N == 8 ? 3 : 2;
+    int d8 = ctx->depth - 8;
+    QuantP P; P.qBits = qBits; P.qAdd = qAdd; P.dqScale = 0; P.dqAdd = 0; P.dqShift = 1;
+    if (ctx->pixbytes == 1)
+        launch_tu_fwd<uint8_t>(sms, N, (const uint8_t*)fenc, sf, (const uint8_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
+                               (unsigned long long*)sseZero, st);
+    else
+        launch_tu_fwd<uint16_t>(sms, N, (const uint16_t*)fenc, sf, (const uint16_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
+                                (unsigned long long*)sseZero, st);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess;
+}
