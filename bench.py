@@ -553,7 +553,12 @@ def run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world,
     pe = geo.plane_elems
     cw, ch = geo.coded()
     samples = cw * ch
-    NS = 4
+    NS = args.e2e_slots
+    picture = args.e2e_upload in ("picture", "rows")
+    # "picture" upload: only the width x height picture crosses PCIe (from its place inside the padded host buffer, host stride =
+    # plane stride); the margins are formed on the device as extendPicBorder would (reference common/pixel.cpp:1044-1061).  The
+    # planes the checker sees are then the same pictures with the reference-style margins, not the synthetic margin samples.
+    org_bytes = geo.origin * 2
     out = {}
     for mode in ("levels", "dense"):
         job = pkg.FrameJob(ctx, WIDTH, HEIGHT, 64, slots=NS)
@@ -584,8 +589,15 @@ def run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world,
                         capture[g] = job_results_copy(pkg, job, res, npass)
                 if f < F:
                     a, b = planes[k]
-                    lib.x265b200_plane_upload_padded(a.h, ctypes.c_void_p(pF + f * pe * 2))
-                    lib.x265b200_plane_upload_padded(b.h, ctypes.c_void_p(pR + f * pe * 2))
+                    if args.e2e_upload == "rows":
+                        lib.x265b200_plane_upload_rows(a.h, ctypes.c_void_p(pF + f * pe * 2))
+                        lib.x265b200_plane_upload_rows(b.h, ctypes.c_void_p(pR + f * pe * 2))
+                    elif picture:
+                        lib.x265b200_plane_upload_picture(a.h, ctypes.c_void_p(pF + f * pe * 2 + org_bytes), ctypes.c_ssize_t(geo.stride))
+                        lib.x265b200_plane_upload_picture(b.h, ctypes.c_void_p(pR + f * pe * 2 + org_bytes), ctypes.c_ssize_t(geo.stride))
+                    else:
+                        lib.x265b200_plane_upload_padded(a.h, ctypes.c_void_p(pF + f * pe * 2))
+                        lib.x265b200_plane_upload_padded(b.h, ctypes.c_void_p(pR + f * pe * 2))
                     slot_of[k] = lib.x265b200_frame_job_submit(job.h, a.h, b.h)
                     if slot_of[k] < 0:
                         ctx.check()
@@ -621,7 +633,7 @@ def run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world,
         # verification of this path: first and last frame, every cost and every level / coefficient
         cap = {0: None, F - 1: None}
         one_step(cap)
-        ver = verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode)
+        ver = verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode, picture)
         per_step_samples = world * F * samples * npass
         out[mode] = {"value": per_step_samples / (ms / steps * 1e-3) / 1e9, "unit": "GPixels/s",
                      "h2d_bytes_per_step": int((h1 - h0) // steps), "d2h_bytes_per_step": int((d1 - d0) // steps),
@@ -633,9 +645,12 @@ def run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world,
             a.destroy(); b.destroy()
     e = out["levels"]
     e["entry"] = "x265b200_plane_upload_padded + x265b200_frame_job_submit / x265b200_frame_job_wait (include/x265b200.h, csrc/framejob.cu)"
-    e["what"] = ("pinned host planes (x265b200_host_alloc) -> plane upload -> SATD x12 + (residual + DCT + quant at QP %d) x4 -> host: every cost, numSig per TU, "
+    e["what"] = ("pinned host pictures (x265b200_host_alloc) -> plane upload -> SATD x12 + (residual + DCT + quant at QP %d) x4 -> host: every cost, numSig per TU, "
                  "one significance bit per coefficient and the non-zero levels; %d frames in flight; the library owns device memory, streams and copies" % (E2E_QP, NS))
     e["frames_in_flight"] = NS
+    e["upload"] = {"rows": "x265b200_plane_upload_rows: the 2160 picture rows of the padded host buffer as one linear copy, margins extended on the device (extendPicBorder semantics)",
+                   "picture": "x265b200_plane_upload_picture: the 3840x2160 picture only (strided copy), margins extended on the device (extendPicBorder semantics)",
+                   "padded": "x265b200_plane_upload_padded: the whole padded plane (4032 x 2336)"}[args.e2e_upload]
     d = out["dense"]
     d["what"] = "same call sequence with X265B200_PASS_COEF: every raw DCT coefficient returns to the host (2 bytes per sample, the round-1 contract)"
     e["dense"] = d
@@ -663,7 +678,16 @@ def job_results_copy(pkg, job, res, npass):
     return out
 
 
-def verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode):
+def extended_copy(orc, geo, plane):
+    """the padded plane a picture upload leaves on the device: zeros, the width x height picture, extendPicBorder's margins"""
+    out = np.zeros_like(plane)
+    v, o = plane.reshape(geo.rows, geo.stride), out.reshape(geo.rows, geo.stride)
+    o[geo.margin_y:geo.margin_y + HEIGHT, geo.margin_x:geo.margin_x + WIDTH] = v[geo.margin_y:geo.margin_y + HEIGHT, geo.margin_x:geo.margin_x + WIDTH]
+    orc.extend_pic_border(out, geo.origin, geo.stride, WIDTH, HEIGHT, geo.margin_x, geo.margin_y)
+    return out
+
+
+def verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode, picture):
     from cpulibs import OP_SATD, Oracle
     lib, kind = cpu_libs()
     if kind == "reference":
@@ -671,6 +695,9 @@ def verify_e2e(pkg, geo, fenc_np, ref_np, desc, cap, mode):
     nth = len(os.sched_getaffinity(0))
     orc = Oracle(DEPTH)
     mism = blocks = coefs = 0
+    if picture:
+        fenc_np = {f: extended_copy(orc, geo, fenc_np[f]) for f in cap}
+        ref_np = {f: extended_copy(orc, geo, ref_np[f]) for f in cap}
     for f, res in cap.items():
         for i, s in enumerate(SATD_SHAPES):
             oa, ob = desc[s]
@@ -710,6 +737,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
     ap.add_argument("--traffic", default="auto", choices=["auto", "off"], help="measure the SATD kernels' DRAM traffic with ncu after the run")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="frames in flight of the e2e frame job (1..8)")
+    ap.add_argument("--e2e-upload", default="picture", choices=["picture", "rows", "padded"])
     ap.add_argument("--no-encoder", action="store_true", help="skip the encoder-level CPU baseline (reference CLI)")
     ap.add_argument("--encoder-frames", type=int, default=6)
     args = ap.parse_args()

@@ -389,6 +389,10 @@ int x265b200_plane_upload_padded(x265b200_plane* plane, const void* hostPlane);
  * picture row, then marginY copies of the first and last padded row.  Cells the reference does not write (rows below
  * height + marginY when height is not a CTU multiple) keep their previous contents (zero after creation). */
 int x265b200_plane_upload_picture(x265b200_plane* plane, const void* hostPic, intptr_t hostStride);
+/* Same result as x265b200_plane_upload_picture for a host buffer that already has the plane's geometry (PicYuv::m_picBuf: pass its
+ * base): the picture's rows travel as one linear copy of whole buffer rows (height * stride samples), the margins are formed on the
+ * device.  What the encoder does for a reconstructed picture instead of extendPicBorder + a whole-plane upload. */
+int x265b200_plane_upload_rows(x265b200_plane* plane, const void* hostPlane);
 /* device -> host of the whole padded plane (for tests and for recon pictures the encoder wants back); synchronous */
 int x265b200_plane_download_padded(x265b200_plane* plane, void* hostPlane);
 /* cumulative bytes copied host -> device / device -> host by planes and frame jobs of this context */

@@ -47,7 +47,16 @@ def test_plane_geometry_upload_and_border_extension(depth):
         want.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + h, geo.margin_x:geo.margin_x + w] = pic.reshape(h, hs)[:, :w]
         orc.extend_pic_border(want, geo.origin, geo.stride, w, h, geo.margin_x, geo.margin_y)
         assert np.array_equal(pl2.download_padded(), want), (w, h, ctu)
-        pl.destroy(); pl2.destroy()
+        # the same picture sitting inside a padded host buffer with arbitrary margins: rows upload
+        padded = make_plane(geo, depth, 8)
+        padded.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + h, geo.margin_x:geo.margin_x + w] = pic.reshape(h, hs)[:, :w]
+        pl3 = pkg.Plane(ctx, w, h, ctu)
+        pl3.upload_rows(padded)
+        want3 = np.zeros(geo.plane_elems, orc.pix)
+        want3.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + h] = padded.reshape(geo.rows, geo.stride)[geo.margin_y:geo.margin_y + h]
+        orc.extend_pic_border(want3, geo.origin, geo.stride, w, h, geo.margin_x, geo.margin_y)
+        assert np.array_equal(pl3.download_padded(), want3), (w, h, ctu)
+        pl.destroy(); pl2.destroy(); pl3.destroy()
     # chroma plane of a 4:2:0 picture (picyuv.cpp:106-110)
     pc = pkg.Plane(ctx, 1920, 1080, 64, 1, 1)
     assert pc.stride == 1920 // 2 + 2 * 96 and pc.rows == 1088 // 2 + 2 * 40 and pc.origin == 40 * pc.stride + 96

@@ -103,12 +103,13 @@ int main(void)
             for (int i = 0; i < n[3]; i++)
             {
                 int16_t resi[64], coef[64], q[64];
+                int32_t deltaU[64];
                 uint32_t ns = res[3].numSig[i];
                 if (i % 5 == 0)
                 {
                     x265b200_sub_ps(ctx, 8, 8, resi, 8, hF[g] + offF[3][i], hR[g] + offR[3][i], stride, stride);
                     x265b200_dct(ctx, X265B200_TR_DCT, 8, resi, coef, 8);
-                    uint32_t wantNs = x265b200_nquant(ctx, coef, qc, q, qBits, add, 64);
+                    uint32_t wantNs = x265b200_quant(ctx, coef, qc, deltaU, q, qBits, add, 64);
                     if (wantNs != ns) { fprintf(stderr, "frame %d TU %d: numSig %u != %u\n", g, i, ns, wantNs); return 1; }
                     uint32_t p = pos;
                     for (int c = 0; c < 64; c++)

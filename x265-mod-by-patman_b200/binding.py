@@ -307,6 +307,9 @@ class Plane:
     def upload_picture(self, host, host_stride, addr=None):
         self._r("x265b200_plane_upload_picture", C.c_void_p(addr if addr is not None else host.ctypes.data), _ss(host_stride))
 
+    def upload_rows(self, host, addr=None):
+        self._r("x265b200_plane_upload_rows", C.c_void_p(addr if addr is not None else host.ctypes.data))
+
     def download_padded(self):
         out = np.empty(self.elems, self.ctx.pix)
         self._r("x265b200_plane_download_padded", _p(out))
