@@ -48,7 +48,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-from frames import Geometry, make_plane, tile_blocks  # noqa: E402
+from frames import Geometry, cu_descriptors, make_plane, tile_blocks  # noqa: E402
 
 METRIC = "CTU-batched SATD+DCT GPixels/s @2160p10"
 DEPTH = 10
@@ -56,6 +56,7 @@ WIDTH, HEIGHT = 3840, 2160
 # preset slow: rect on, amp off (reference param.cpp:572-587); min CU 8 -> PUs down to 8x4 / 4x8
 SATD_SHAPES = [(64, 64), (64, 32), (32, 64), (32, 32), (32, 16), (16, 32), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8)]
 DCT_SIZES = [32, 16, 8, 4]
+CU_SIZES = [64, 32, 16, 8]      # fused mode: the three shapes of a CU size (2Nx2N, 2NxN, Nx2N) in one x265b200_cu_satd_batch launch
 E2E_QP = 32             # slice QP of the e2e run's DCT + quant passes (preset slow's default CRF 28 lands around QP 30-34)
 FLAT_QUANT = [26214, 23302, 20560, 18396, 16384, 14564]
 
@@ -263,7 +264,7 @@ def workload_config(nframes, note=""):
 
 # ------------------------------------------------------------------------------------------- B200 arm
 
-def measure_traffic(F):
+def measure_traffic(F, fused):
     """dram__bytes_read + dram__bytes_write per SATD launch, measured now on this GPU by running tools/measure_traffic.py under ncu
     (two counters, one pass, the same 12 launches over F frames).  Falls back to the committed capture when ncu cannot run."""
     script = os.path.join(ROOT, "tools", "measure_traffic.py")
@@ -272,7 +273,7 @@ def measure_traffic(F):
     except OSError:
         sha = None
     try:
-        out = subprocess.run([sys.executable, script, "--frames", str(F), "--ncu"], capture_output=True, text=True, timeout=420)
+        out = subprocess.run([sys.executable, script, "--frames", str(F), "--ncu"] + (["--fused"] if fused else []), capture_output=True, text=True, timeout=420)
         for line in out.stdout.splitlines():
             if line.startswith("{"):
                 j = json.loads(line)
@@ -285,7 +286,7 @@ def measure_traffic(F):
     tp = os.path.join(ROOT, "profiles", "r3_satd_traffic.json")
     if os.path.exists(tp):
         j = json.load(open(tp))
-        if j.get("frames_per_launch") == F:
+        if j.get("frames_per_launch") == F and bool(j.get("fused")) == fused:
             j["source"] = "committed capture profiles/r3_satd_traffic.json (ncu could not run here); captured at git %s" % j.get("git_sha")
             return j
     return None
@@ -340,7 +341,16 @@ def run_b200_arm(args):
         B = np.concatenate([ob.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
         dev_desc[key] = (torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), len(oa))
     samples = F * cw * ch
+    fused = args.satd_mode == "fused"
+    cu_desc, cu_idx = {}, {}
+    for S in CU_SIZES:
+        oF, oR5, idx = cu_descriptors(geo, S, desc[(S, S)], desc[(S, S // 2)], desc[(S // 2, S)])
+        cu_idx[S] = idx
+        A = np.concatenate([oF.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        B = np.concatenate([oR5.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        cu_desc[S] = (torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), len(oF))
     satd_out = {s: torch.empty(dev_desc[s][0].numel(), dtype=torch.int32, device="cuda") for s in SATD_SHAPES}
+    cu_out = {S: torch.empty(5 * cu_desc[S][0].numel(), dtype=torch.int32, device="cuda") for S in CU_SIZES}
     resid = torch.empty(samples, dtype=torch.int16, device="cuda")
     coef = torch.empty(samples, dtype=torch.int16, device="cuda")
     # residual of the 32x32 tiling, block-contiguous; any int16 data is a valid DCT input, so the same
@@ -357,7 +367,8 @@ def run_b200_arm(args):
         recon_all = torch.empty(world * pe, dtype=torch.int16, device="cuda")
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    launches_per_step = len(SATD_SHAPES) + len(DCT_SIZES)
+    launches_per_step = len(SATD_SHAPES) + len(DCT_SIZES)          # shape passes per step (the unit of `value`), fused or not
+    satd_launches = len(CU_SIZES) if fused else len(SATD_SHAPES)
 
     def step(marks=None, per_launch=False):
         """marks: list receiving (kind, key, start event, end event).  In the timed region the events bracket the two PHASES
@@ -374,13 +385,17 @@ def run_b200_arm(args):
                         c1 = ev(); c1.record(comm_stream); comm_marks.append((c0, c1))
             if marks is not None and not per_launch:
                 p0 = ev(); p0.record(stream)
-            for s in SATD_SHAPES:
-                a, b, _ = dev_desc[s]
+            for s in (CU_SIZES if fused else SATD_SHAPES):
                 if per_launch:
                     e0 = ev(); e0.record(stream)
-                ctx.pixelcmp_batch(pkg.OP_SATD, s[0], s[1], dF, geo.stride, dR, geo.stride, a, b, satd_out[s], sh)
+                if fused:
+                    a, b, _ = cu_desc[s]
+                    ctx.cu_satd_batch(s, dF, geo.stride, dR, geo.stride, a, b, cu_out[s], sh)
+                else:
+                    a, b, _ = dev_desc[s]
+                    ctx.pixelcmp_batch(pkg.OP_SATD, s[0], s[1], dF, geo.stride, dR, geo.stride, a, b, satd_out[s], sh)
                 if per_launch:
-                    e1 = ev(); e1.record(stream); marks.append(("satd", s, e0, e1))
+                    e1 = ev(); e1.record(stream); marks.append(("satd", "cu%d" % s if fused else s, e0, e1))
             if marks is not None and not per_launch:
                 p1 = ev(); p1.record(stream); marks.append(("satd", "phase", p0, p1))
             for n in DCT_SIZES:
@@ -427,7 +442,7 @@ def run_b200_arm(args):
     tsum = {"satd": 0.0, "dct": 0.0}
     for kind, key, e0, e1 in marks:
         tsum[kind] += e0.elapsed_time(e1)
-    satd_ms = tsum["satd"] / (args.steps * len(SATD_SHAPES))       # average SATD launch
+    satd_ms = tsum["satd"] / (args.steps * satd_launches)          # average SATD launch
     dct_ms = tsum["dct"] / (args.steps * len(DCT_SIZES))
     nccl = None
     if world > 1:
@@ -443,6 +458,11 @@ def run_b200_arm(args):
                 "payload_verified": bool(all(int(sums[r].item()) == int(got[r].item()) for r in range(world)))}
 
     # ---------------- verification of the headline configuration against the reference's C primitives
+    if fused:       # scatter the per-CU costs back into the per-shape arrays the checker walks
+        for S in CU_SIZES:
+            c5 = cu_out[S].view(F, -1, 5)
+            for k, shape in enumerate([(S, S), (S, S // 2), (S, S // 2), (S // 2, S), (S // 2, S)]):
+                satd_out[shape].view(F, -1)[:, torch.from_numpy(cu_idx[S][k]).cuda()] = c5[:, :, k]
     verified = verify_step(torch, pkg, ctx, geo, fenc_np, ref_np, desc, dev_desc, satd_out, resid, coef, F, sh, samples)
 
     # diagnostic pass (not part of `value`): every launch bracketed by its own event pair
@@ -454,14 +474,20 @@ def run_b200_arm(args):
     for kind, key, e0, e1 in diag:
         per.setdefault((kind, key), []).append(e0.elapsed_time(e1))
     peak, peak_src = peaks()
-    nblocks = sum(dev_desc[s][2] for s in SATD_SHAPES) * F / len(SATD_SHAPES)
-    satd_bytes = samples * 2 * 2 + nblocks * 4                     # 2*b B per sample + 4 B per block
+    if fused:
+        # one fused launch = three shape passes.  Its compulsory DRAM bytes are those of ONE pass: every fenc sample once and every
+        # reference sample of the (overlapping, L2-resident) search windows once, plus five costs per CU
+        nblocks = sum(cu_desc[S][2] for S in CU_SIZES) * F / len(CU_SIZES)
+        satd_bytes = samples * 2 * 2 + nblocks * 5 * 4
+    else:
+        nblocks = sum(dev_desc[s][2] for s in SATD_SHAPES) * F / len(SATD_SHAPES)
+        satd_bytes = samples * 2 * 2 + nblocks * 4                 # 2*b B per sample + 4 B per block
     dct_bytes = samples * 4                                        # int16 in + int16 out per coefficient
     dominant = "satd" if tsum["satd"] >= tsum["dct"] else "dct"
     ach = (satd_bytes / (satd_ms * 1e-3) if dominant == "satd" else dct_bytes / (dct_ms * 1e-3)) / 1e9
 
     # ---------------- e2e through the C ABI's host-buffer layer (frees the device-resident batch first: the job owns its own memory)
-    del dF, dR, resid, coef, satd_out
+    del dF, dR, resid, coef, satd_out, cu_out
     torch.cuda.empty_cache()
     e2e = run_e2e(torch, pkg, ctx, geo, pF, pR, fenc_np, ref_np, desc, F, args, world, dist, binding)
     clocks = sampler.stop() if sampler else None
@@ -469,7 +495,7 @@ def run_b200_arm(args):
     if rank == 0 and dominant == "satd" and args.traffic != "off":
         ctx.close()                                                # the ncu child needs the GPU memory
         ctx = None
-        traffic = measure_traffic(F)
+        traffic = measure_traffic(F, fused)
 
     if world > 1:
         dist.barrier()
@@ -483,15 +509,18 @@ def run_b200_arm(args):
     enc = encoder_fps(args) if world == 1 else None
     if enc:
         cb["encoder_fps"] = enc
-    roofline = {"bound": "hbm", "kernel": "tile4_fast_kernel<uint16,SATD> (10 shapes) + strip8_fast_kernel<SATD> (8x4, 16x8) (csrc/tile_kernels.cuh)" if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
+    satd_kernel = ("cu_satd_kernel<uint16, 64/32/16/8> (csrc/tile_kernels.cuh): 2Nx2N + 2NxN + Nx2N PUs of every CU in one launch, fenc read once" if fused
+                   else "tile4_fast_kernel<uint16,SATD> (10 shapes) + strip8_fast_kernel<SATD> (8x4, 16x8) (csrc/tile_kernels.cuh)")
+    roofline = {"bound": "hbm", "kernel": satd_kernel if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic["dram_bytes_per_launch_avg"] if traffic else None,
                 "traffic_detail": traffic,
                 "algorithmic_bytes_per_launch": satd_bytes if dominant == "satd" else dct_bytes,
                 "peak_source": peak_src,
                 "share_of_step": tsum[dominant] / (ms if world == 1 else sum(tsum.values())),
-                "other": {"satd_GBps": satd_bytes / (satd_ms * 1e-3) / 1e9, "dct_GBps": dct_bytes / (dct_ms * 1e-3) / 1e9,
-                          "satd_gpix_s": samples / (satd_ms * 1e-3) / 1e9, "dct_gcoef_s": samples / (dct_ms * 1e-3) / 1e9,
+                "other": {"satd_mode": args.satd_mode, "satd_launches_per_step": satd_launches, "shape_passes_per_satd_launch": len(SATD_SHAPES) // satd_launches,
+                          "satd_GBps": satd_bytes / (satd_ms * 1e-3) / 1e9, "dct_GBps": dct_bytes / (dct_ms * 1e-3) / 1e9,
+                          "satd_gpix_s": samples * (len(SATD_SHAPES) // satd_launches) / (satd_ms * 1e-3) / 1e9, "dct_gcoef_s": samples / (dct_ms * 1e-3) / 1e9,
                           "per_launch_ms_diagnostic_pass": {"%s_%s" % (k[0], "x".join(map(str, k[1])) if isinstance(k[1], tuple) else k[1]): sum(v) / len(v)
                                                               for k, v in per.items()},
                           "timing": "phase events (SATD x12, DCT x4) inside the timed region; per-launch figures from a separate pass with an event pair per launch"}}
@@ -737,6 +766,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
     ap.add_argument("--traffic", default="auto", choices=["auto", "off"], help="measure the SATD kernels' DRAM traffic with ncu after the run")
+    ap.add_argument("--satd-mode", default="fused", choices=["fused", "shapes"],
+                    help="fused: one x265b200_cu_satd_batch launch per CU size (3 shapes each); shapes: one x265b200_pixelcmp_batch launch per PU shape")
     ap.add_argument("--e2e-slots", type=int, default=4, help="frames in flight of the e2e frame job (1..8)")
     ap.add_argument("--e2e-upload", default="picture", choices=["picture", "rows", "padded"])
     ap.add_argument("--no-encoder", action="store_true", help="skip the encoder-level CPU baseline (reference CLI)")

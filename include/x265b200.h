@@ -111,6 +111,15 @@ int x265b200_sad_multi_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, 
                              const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR,
                              int K, int n, int32_t* out, x265b200_stream stream);
 
+/* SATD of every rectangular partition of n CUs of cuSize x cuSize (8, 16, 32, 64) in one pass, each PU against its own reference
+ * block -- what the inter analysis measures per CU for SIZE_2Nx2N, SIZE_2NxN and SIZE_Nx2N (reference encoder/analysis.cpp
+ * checkInter_rd0_4 -> encoder/search.cpp predInterSearch, one pu[part].satd per PU).  offF[i]: the CU in the fenc plane;
+ * offR[5 * i + k] / cost[5 * i + k]: k = 0 the 2Nx2N PU, 1 / 2 the upper / lower 2NxN PU, 3 / 4 the left / right Nx2N PU, each offset
+ * addressing the top-left sample of that PU's reference block (PU position + its motion vector).  Equal, cost for cost, to five
+ * x265b200_pixelcmp_batch(SATD) results; the fenc CU is read once instead of three times and one launch replaces three. */
+int x265b200_cu_satd_batch(x265b200_ctx* ctx, int cuSize, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                           const int32_t* offF, const int32_t* offR, int n, int32_t* cost, x265b200_stream stream);
+
 /* pixel_sse_ss_t (pixel.cpp:167-186 with int16 inputs) and pixel_ssd_s_t (pixel.cpp:371-383);
  * out is uint64[n] (truncate to 32 bit for an 8-bit build's sse_t). */
 int x265b200_sse_ss_batch(x265b200_ctx* ctx, int w, int h, const int16_t* A, intptr_t strideA,
@@ -207,8 +216,8 @@ int x265b200_me_full_batch(x265b200_ctx* ctx, int w, int h, int merange, const v
                            const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp,
                            const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
-/* search methods, numbered as x265.h:511-519 (X265_DIA_SEARCH .. X265_FULL_SEARCH); UMH and SEA are not built */
-enum { X265B200_ME_DIA = 0, X265B200_ME_HEX = 1, X265B200_ME_STAR = 3, X265B200_ME_FULL = 5 };
+/* search methods, numbered as x265.h:511-519 (X265_DIA_SEARCH .. X265_FULL_SEARCH) */
+enum { X265B200_ME_DIA = 0, X265B200_ME_HEX = 1, X265B200_ME_UMH = 2, X265B200_ME_STAR = 3, X265B200_ME_SEA = 4, X265B200_ME_FULL = 5 };
 
 /* The data-dependent integer searches for n PUs at once, one warp walking each PU: diamond (reference
  * encoder/motion.cpp:1016-1039), hexagon + square refinement (:1041-1138) and star (:386-630, :1327-1435, with its
@@ -221,7 +230,26 @@ int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, int h, int m
                               const void* ref, intptr_t strideR, const int32_t* offF, const int32_t* offR, const int32_t* range,
                               const int32_t* mvp, const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
 
-/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod DIA, HEX, STAR or FULL for n
+/* Uneven multi-hexagon search (reference encoder/motion.cpp:1142-1324, X265_UMH_SEARCH) followed by the hexagon search it falls into,
+ * one warp per PU.  qmvp: the predictor in quarter pels (its clipped full-pel rounding centres the first diamond); mvc: numCand (0..16)
+ * neighbour vectors per PU, quarter pels, whose disagreement scales the search range (motion.cpp:1211-1245).  Other arguments as
+ * x265b200_me_pattern_batch. */
+int x265b200_me_umh_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                          const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                          const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
+
+/* Successive elimination (reference encoder/motion.cpp:1438-1591, X265_SEA): every row of the window bmv +- merange (clipped to range) is
+ * filtered with ads over the integral planes of the reference picture, survivors get a SAD; the reference's cost bookkeeping is kept as
+ * it is (see csrc/mesearch.cu).  sums: the twelve planes x265b200_me_integral_batch wrote for the picture `ref` points into (plane k at
+ * sums + k * planePitch, same stride, addressed with offR like the picture); costTab must cover indices down to -2 * |qmvp| around the
+ * window, as the reference's BitCost tables do.  PU shapes 32x8, 8x32, 8x4, 4x8 are refused: the reference reads stale cache samples
+ * for them. */
+int x265b200_me_sea_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                          const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp, const uint16_t* costTab,
+                          const uint32_t* sums, size_t planePitch, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream);
+
+/* Whole MotionEstimate::motionEstimate (reference encoder/motion.cpp:923-1773) with searchMethod DIA, HEX, UMH, STAR or FULL (SEA: pass the
+ * integral planes through x265b200_motion_estimate_sea_batch) for n
  * PUs of w x h on full-resolution luma planes: SAD at the clipped predictor qmvp / its full-pel rounding / the zero vector
  * and at numCand (0..16, the same count for every PU; pad with 0,0) neighbour vectors mvc[(i * numCand + k) * 2 ..] in
  * quarter pels, the integer search (x265b200_me_pattern_batch or x265b200_me_full_batch), then the half-pel / quarter-pel refinement of
@@ -235,6 +263,15 @@ int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, i
                                    const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                                    int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
                                    int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
+
+/* x265b200_motion_estimate_batch with searchMethod X265_SEA (reference encoder/motion.cpp:1438-1591): sums / planePitch are the twelve
+ * integral planes of the reference picture as x265b200_me_integral_batch writes them (see x265b200_me_sea_batch). */
+int x265b200_motion_estimate_sea_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+                                       const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                       const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                       int numCand, const int32_t* mvc, const uint16_t* costTab,
+                                       const uint32_t* sums, size_t planePitch, int n,
+                                       int32_t* outQMv, int32_t* outCost, x265b200_stream stream);
 
 /* The lookahead's motionEstimate (reference encoder/slicetype.cpp:4484-4566 -> motion.cpp:923-1773 with ref->isLowres): the
  * reference picture is a lowres frame = four half-pel planes (full-pel, half-pel x, half-pel y, half-pel xy, as

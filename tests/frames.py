@@ -74,3 +74,20 @@ def smooth_field(geo, depth, seed, box=9):
     b = (b - b.min()) / (b.max() - b.min())
     dt = np.uint8 if depth == 8 else np.uint16
     return np.rint(b * ((1 << depth) - 1)).astype(dt).ravel()
+
+
+def cu_descriptors(geo, S, d2N, d2NxN, dNx2N):
+    """descriptors of x265b200_cu_satd_batch for every S x S CU of the coded area from the three per-shape descriptor sets
+    (each an (offA, offB) pair of tile_blocks for S x S, S x S/2 and S/2 x S).  Returns (offF[n], offR[5n], idx) where
+    idx[k] maps CU i to the block index of its k-th PU in the per-shape raster order, so that
+    cost5.reshape(n, 5)[:, k] == per-shape cost[idx[k]]."""
+    cw, ch = geo.coded()
+    cx, cy = cw // S, ch // S
+    X, Y = np.meshgrid(np.arange(cx), np.arange(cy))
+    X = X.ravel(); Y = Y.ravel()
+    i0 = Y * cx + X
+    iH = [(2 * Y + k) * cx + X for k in (0, 1)]                 # S x S/2 blocks: cx per row, 2 * cy rows
+    iV = [Y * (2 * cx) + 2 * X + k for k in (0, 1)]             # S/2 x S blocks: 2 * cx per row
+    offF = d2N[0][i0]
+    offR = np.stack([d2N[1][i0], d2NxN[1][iH[0]], d2NxN[1][iH[1]], dNx2N[1][iV[0]], dNx2N[1][iV[1]]], axis=1).astype(np.int32)
+    return offF.astype(np.int32), offR.ravel(), [i0, iH[0], iH[1], iV[0], iV[1]]

@@ -276,3 +276,33 @@ def test_full_size_properties_other_configs(width, height, depth, torch_mod):
         rrec = orc.idct_batch(N, rcoef, np.zeros(len(sel) * N * N, np.int16), N, (np.arange(len(sel)) * N * N).astype(np.int32))
         assert np.array_equal(rec.cpu().numpy().reshape(n, N * N)[sel].ravel(), rrec), N
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_cu_satd_batch_equals_per_shape_costs(depth, torch_mod):
+    """x265b200_cu_satd_batch (2Nx2N + 2NxN + Nx2N PUs of a CU in one pass, five motion vectors per CU) vs the oracle's per-shape SATD"""
+    torch = torch_mod
+    from frames import cu_descriptors
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(640, 384)
+    A = make_plane(geo, depth, 31, "natural"); B = make_plane(geo, depth, 32, "uniform")
+    vt = np.int16 if depth > 8 else np.uint8
+    dA, dB = dev(A.view(vt)), dev(B.view(vt))
+    for S in (8, 16, 32, 64):
+        shapes = [(S, S), (S, S // 2), (S // 2, S)]
+        d = [tile_blocks(geo, w, h, seed=13 + S) for (w, h) in shapes]
+        offF, offR5, idx = cu_descriptors(geo, S, *d)
+        n = len(offF)
+        out = torch.full((5 * n,), -1, dtype=torch.int32, device="cuda")
+        ctx.cu_satd_batch(S, dA, geo.stride, dB, geo.stride, dev(offF), dev(offR5), out)
+        got = out.cpu().numpy().reshape(n, 5)
+        want = [orc.pixelcmp_batch(OP_SATD, w, h, A, geo.stride, B, geo.stride, oa, ob) for (w, h), (oa, ob) in zip(shapes, d)]
+        for k in range(5):
+            assert np.array_equal(got[:, k], want[0 if k == 0 else 1 if k < 3 else 2][idx[k]]), (depth, S, k)
+        # ragged count
+        m = 7
+        out2 = torch.full((5 * m,), -1, dtype=torch.int32, device="cuda")
+        ctx.cu_satd_batch(S, dA, geo.stride, dB, geo.stride, dev(offF[:m].copy()), dev(offR5[:5 * m].copy()), out2)
+        assert np.array_equal(out2.cpu().numpy(), got[:m].ravel())
+    ctx.check()

@@ -519,7 +519,7 @@ def test_me_full_batch(depth):
 
 @pytest.mark.parametrize("depth", DEPTHS)
 def test_motion_estimate_batch(depth):
-    """whole motionEstimate (predictor candidates, full / hexagon / diamond / star search, sub-pel refinement, zero-vector chance) for a batch of
+    """whole motionEstimate (predictor candidates, full / hexagon / diamond / star / uneven multi-hexagon search, sub-pel refinement, zero-vector chance) for a batch of
     PUs vs the oracle's restatement -- itself pinned to the reference's MotionEstimate::motionEstimate by the CPU suite --
     for every SubpelWorkload level, with and without neighbour candidates, including PUs that leave early on zero residual"""
     import torch
@@ -555,7 +555,7 @@ def test_motion_estimate_batch(depth):
         mvc = rng.integers(-4 * m - 6, 4 * m + 7, (n, max(nc, 1), 2)).astype(np.int32)
         mvc[::4, 0] = (12, 8)
         for fen, ref_plane, method in ((F, R, 5), (F, R2, 5), (F, R2, 1), (S, S2, 1), (S, S2, 0), (F, R, 0), (S, S2, 5),
-                                       (S, S2, 3), (S, S3, 3), (F, R, 3), (F, R2, 3)):
+                                       (S, S2, 3), (S, S3, 3), (F, R, 3), (F, R2, 3), (S, S2, 2), (S, S3, 2), (F, R, 2), (F, R2, 2)):
             merange = m if method == 5 else int(rng.integers(1, 40))
             if ref_plane is S3: merange = int(rng.integers(16, 64))
             want_mv = np.zeros((n, 2), np.int32); want_c = np.zeros(n, np.int32)
@@ -572,6 +572,61 @@ def test_motion_estimate_batch(depth):
             if method != 5 and fen is S:
                 walked += int((np.abs(want_mv - np.clip(qmvp, 4 * rngs[:, :2], 4 * rngs[:, 2:])).max(1) >= 16).sum())
     assert walked > 100                                   # pattern searches ended four or more pels from their start
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_sea_batch(depth):
+    """X265_SEA through the whole chain: integral planes from x265b200_me_integral_batch, ads pre-filter and survivor SADs in
+    me_sea_kernel, vs the oracle (pinned to the reference's motionEstimate with its own integral planes by the CPU suite)"""
+    import torch
+    from gpulib import context
+    from frames import Geometry, make_plane, smooth_field
+    from test_oracle_vs_ref import mv_cost_table
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    rng = np.random.default_rng(900 + depth)
+    S = smooth_field(geo, depth, 141, box=9)
+    N = make_plane(geo, depth, 142, "natural")
+    cw, ch = geo.coded()
+    pitch = geo.plane_elems
+    RAD = 4096
+    tab = mv_cost_table(7.1, RAD); dtab = dev(tab.view(np.int16))
+    shapes = [(16, 16), (8, 8), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64), (32, 24), (24, 32),
+              (64, 48), (48, 64), (64, 16), (16, 64), (16, 12), (12, 16), (16, 4), (4, 16), (4, 4)]
+    moved = 0
+    for si, (w, h) in enumerate(shapes):
+        dx, dy = int(rng.integers(-10, 11)), int(rng.integers(-8, 9))
+        if si % 3 == 2:
+            F, R = N, make_plane(geo, depth, 143 + si, "natural")
+        else:
+            F = S
+            R = np.clip(np.roll(S, dy * geo.stride + dx).astype(np.int64) + rng.integers(-3, 4, S.size), 0, orc.pmax).astype(S.dtype)
+        dR = dev(pix_view(R, depth))
+        dsums = torch.zeros(12 * pitch, dtype=torch.int32, device="cuda")
+        ctx.me_integral_batch(dR, geo.stride, geo.rows, 1, dsums, pitch)
+        sums = dsums.cpu().numpy().view(np.uint32)
+        n, nc = 24, (0, 2, 1)[si % 3]
+        subme = si % 4
+        x = rng.integers(0, cw - w + 1, n); y = rng.integers(0, ch - h + 1, n)
+        off = (geo.origin + y * geo.stride + x).astype(np.int32)
+        m = int(rng.integers(4, 24))
+        minx = -np.minimum(m, x + geo.margin_x - 12); maxx = np.minimum(m, cw + geo.margin_x - 12 - w - x)
+        miny = -np.minimum(m, y + geo.margin_y - 12); maxy = np.minimum(m, ch + geo.margin_y - 12 - h - y)
+        rngs = np.stack([minx, miny, maxx, maxy], 1).astype(np.int32).copy()
+        qmvp = rng.integers(-4 * m, 4 * m + 1, (n, 2)).astype(np.int32)
+        qmvp[::5] = 0
+        mvc = rng.integers(-4 * m, 4 * m + 1, (n, max(nc, 1), 2)).astype(np.int32)
+        merange = int(rng.integers(2, 24))
+        want = np.array([orc.motion_estimate_sea(merange, subme, w, h, F, int(off[i]), geo.stride, R, int(off[i]), geo.stride, sums, pitch, rngs[i], qmvp[i],
+                                                 mvc[i, :nc], tab, RAD) for i in range(n)], np.int32)
+        gmv = torch.full((n, 2), -7777, dtype=torch.int32, device="cuda"); gc = torch.full((n,), -7777, dtype=torch.int32, device="cuda")
+        ctx.motion_estimate_sea_batch(w, h, merange, subme, dev(pix_view(F, depth)), geo.stride, dR, geo.stride, dev(off), dev(off), dev(rngs), dev(qmvp),
+                                      nc, dev(np.ascontiguousarray(mvc[:, :nc])) if nc else None, dtab.data_ptr() + 2 * RAD, dsums, pitch, gmv, gc)
+        assert np.array_equal(gc.cpu().numpy(), want[:, 2]), (w, h, subme)
+        assert np.array_equal(gmv.cpu().numpy(), want[:, :2]), (w, h, subme)
+        moved += int((np.abs(want[:, :2] - np.clip(qmvp, 4 * rngs[:, :2], 4 * rngs[:, 2:])).max(1) >= 8).sum())
+    assert moved > 60
     ctx.check()
 
 

@@ -26,10 +26,10 @@ SATD_SHAPES = [(64, 64), (64, 32), (32, 64), (32, 32), (32, 16), (16, 32), (16, 
 METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
 
 
-def workload(F):
+def workload(F, fused=False):
     import numpy as np
     import torch
-    from frames import Geometry, make_plane, tile_blocks
+    from frames import Geometry, cu_descriptors, make_plane, tile_blocks
     pkg = importlib.import_module("x265-mod-by-patman_b200")
     ctx = pkg.Context(10, 0)
     geo = Geometry(3840, 2160)
@@ -38,7 +38,13 @@ def workload(F):
     B = torch.from_numpy(make_plane(geo, 10, 0x9265, "natural").view(np.int16)).cuda()
     dF = A.repeat(F); dR = B.repeat(F)
     outs = []
-    for (w, h) in SATD_SHAPES:
+    cus = []
+    for S in ((64, 32, 16, 8) if fused else ()):
+        oF, oR5, _ = cu_descriptors(geo, S, *[tile_blocks(geo, w, h, seed=1) for (w, h) in ((S, S), (S, S // 2), (S // 2, S))])
+        a = np.concatenate([oF.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        b = np.concatenate([oR5.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
+        cus.append((S, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.empty(5 * len(a), dtype=torch.int32, device="cuda")))
+    for (w, h) in (() if fused else SATD_SHAPES):
         oa, ob = tile_blocks(geo, w, h, seed=1)
         a = np.concatenate([oa.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
         b = np.concatenate([ob.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)
@@ -47,19 +53,26 @@ def workload(F):
     for rep in range(2):                    # first pass warms up (module load); ncu's --launch-skip drops it
         for (w, h, a, b, o) in outs:
             ctx.pixelcmp_batch(pkg.OP_SATD, w, h, dF, geo.stride, dR, geo.stride, a, b, o)
+        for (S, a, b, o) in cus:
+            ctx.cu_satd_batch(S, dF, geo.stride, dR, geo.stride, a, b, o)
     torch.cuda.synchronize()
     ctx.check()
     samples = F * geo.coded()[0] * geo.coded()[1]
-    nblocks = sum(len(o[2]) for o in outs) / len(outs)
-    print(json.dumps({"algorithmic_bytes_per_launch": samples * 4 + nblocks * 4}))
+    if fused:
+        nblocks = sum(len(c[1]) for c in cus) / len(cus)
+        print(json.dumps({"algorithmic_bytes_per_launch": samples * 4 + nblocks * 20}))
+    else:
+        nblocks = sum(len(o[2]) for o in outs) / len(outs)
+        print(json.dumps({"algorithmic_bytes_per_launch": samples * 4 + nblocks * 4}))
 
 
-def under_ncu(F):
+def under_ncu(F, fused=False):
+    nl = 4 if fused else len(SATD_SHAPES)
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["CUDA_VISIBLE_DEVICES"] = env.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
-    cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "--kernel-name", "regex:.*(tile4_fast_kernel|strip8_fast_kernel).*",
-           "--launch-skip", str(len(SATD_SHAPES)), "--launch-count", str(len(SATD_SHAPES)),
-           sys.executable, os.path.abspath(__file__), "--frames", str(F)]
+    cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "--kernel-name", "regex:.*(tile4_fast_kernel|strip8_fast_kernel|cu_satd_kernel).*",
+           "--launch-skip", str(nl), "--launch-count", str(nl),
+           sys.executable, os.path.abspath(__file__), "--frames", str(F)] + (["--fused"] if fused else [])
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=400)
     text = out.stdout
     start = text.find('"ID"')
@@ -87,12 +100,14 @@ def under_ncu(F):
                       "dram_bytes_per_launch": [int(t) for t in tot], "algorithmic_bytes_per_launch": alg,
                       "ratio_to_algorithmic": (sum(tot) / max(1, len(tot)) / alg) if alg else None,
                       "ncu_gpu_time_ms_per_launch": [round(p.get("gpu__time_duration.sum", 0) / 1e6, 4) for p in launches],
-                      "command": " ".join(cmd[:-4] + ["python", "tools/measure_traffic.py", "--frames", str(F)]), "git_sha": sha}))
+                      "fused": fused,
+                      "command": " ".join(cmd[:cmd.index(sys.executable)] + ["python", "tools/measure_traffic.py", "--frames", str(F)] + (["--fused"] if fused else [])), "git_sha": sha}))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--ncu", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="the four x265b200_cu_satd_batch launches instead of the twelve per-shape ones")
     a = ap.parse_args()
-    under_ncu(a.frames) if a.ncu else workload(a.frames)
+    under_ncu(a.frames, a.fused) if a.ncu else workload(a.frames, a.fused)

@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, "include", "x265b200.h")
 
 OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP = 0, 1, 2, 3
 TR_DCT, TR_DST, TR_LOWPASS = 0, 1, 2
-ME_DIA, ME_HEX, ME_STAR, ME_FULL = 0, 1, 3, 5       # search methods, numbered as x265.h:511-519
+ME_DIA, ME_HEX, ME_UMH, ME_STAR, ME_SEA, ME_FULL = 0, 1, 2, 3, 4, 5       # search methods, numbered as x265.h:511-519
 IP_KINDS = {"hpp": 0, "hps": 1, "vpp": 2, "vps": 3, "vsp": 4, "vss": 5, "hvpp": 6, "p2s": 7}
 
 _lib = None
@@ -146,6 +146,10 @@ class Context:
         self._call("x265b200_pixelcmp_batch", op, w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
                    int(offA.numel()), _dp(out), C.c_void_p(stream))
 
+    def cu_satd_batch(self, S, F, sf, R, sr, offF, offR5, out, stream=0):
+        self._call("x265b200_cu_satd_batch", int(S), _dp(F), _ss(sf), _dp(R), _ss(sr), _dp(offF), _dp(offR5), int(offF.numel()), _dp(out),
+                   C.c_void_p(stream))
+
     def sad_multi_batch(self, w, h, F, sf, R, sr, offF, offR, K, out, stream=0):
         self._call("x265b200_sad_multi_batch", w, h, _dp(F), _ss(sf), _dp(R), _ss(sr), _dp(offF), _dp(offR), K,
                    int(offF.numel()), _dp(out), C.c_void_p(stream))
@@ -188,6 +192,12 @@ class Context:
         self._call("x265b200_motion_estimate_batch", int(method), w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR),
                    _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), int(offF.numel()), _dp(out_qmv), _dp(out_cost),
                    C.c_void_p(stream))
+
+    def motion_estimate_sea_batch(self, w, h, merange, subme, fenc, sf, ref, sr, offF, offR, rng, qmvp, num_cand, mvc, cost_tab_centre,
+                                  sums, plane_pitch, out_qmv, out_cost, stream=0):
+        self._call("x265b200_motion_estimate_sea_batch", w, h, int(merange), int(subme), _dp(fenc), _ss(sf), _dp(ref), _ss(sr), _dp(offF), _dp(offR),
+                   _dp(rng), _dp(qmvp), int(num_cand), _dp(mvc), C.c_void_p(int(cost_tab_centre)), _dp(sums), C.c_size_t(int(plane_pitch)),
+                   int(offF.numel()), _dp(out_qmv), _dp(out_cost), C.c_void_p(stream))
 
     def lowres_motion_estimate_batch(self, method, w, h, merange, subme, fenc, sf, planes, sr, plane_pitch, offF, offR, rng, qmvp,
                                      cost_tab_centre, out_qmv, out_cost, stream=0):

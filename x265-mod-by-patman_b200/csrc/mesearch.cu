@@ -233,8 +233,10 @@ struct PatternPU
 
     // SAD + mvcost of up to four full-pel candidates in one pass over the block.  ok[k] says whether the reference
     // measures candidate k at all (it is not read otherwise); q3 marks a candidate charged mvcost(mv << 3), the
-    // reference's raster quirk (motion.cpp:1392), instead of mv << 2.
-    __device__ void eval(int nc, const int (&cand)[4][2], const bool (&ok)[4], int (&cost)[4], int q3 = -1) const
+    // reference's raster quirk (motion.cpp:1392), instead of mv << 2; q3 == -2: plain SADs, no vector cost (SEA's triples).
+    // wrap16 = false: the vector cost is the plain sum of the two table entries (the reference's COST_MV_X4_DIR-free ring of
+    // motion.cpp:1282-1310 adds them as ints), not BitCost::mvcost's uint16_t sum.
+    __device__ void eval(int nc, const int (&cand)[4][2], const bool (&ok)[4], int (&cost)[4], int q3 = -1, bool wrap16 = true) const
     {
         const PIX* rp[4];
         unsigned acc[4];
@@ -261,7 +263,8 @@ struct PatternPU
         {
             const int sh = k == q3 ? 3 : 2;
             const bool use = k < nc && ok[k];
-            cost[k] = (int)__reduce_add_sync(0xffffffffu, acc[k]) + (use ? (int)(uint16_t)(cx[cand[k][0] << sh] + cy[cand[k][1] << sh]) : 0);
+            const int mc = (use && q3 != -2) ? (int)cx[cand[k][0] << sh] + (int)cy[cand[k][1] << sh] : 0;
+            cost[k] = (int)__reduce_add_sync(0xffffffffu, acc[k]) + (wrap16 ? (int)(uint16_t)mc : mc);
         }
     }
 };
@@ -393,12 +396,179 @@ __device__ void star_search(const PatternPU<PIX>& P, int merange, int& x, int& y
     x = b.x; y = b.y; best = b.cost;
 }
 
+// X265_HEX_SEARCH, motion.cpp:1041-1138: the six corners around the start (hex2[1..6] order), the walk, the square refinement
+template<typename PIX>
+__device__ void hex_search(const PatternPU<PIX>& P, int merange, int& x, int& y, int& best)
+{
+    const int minx = P.minx, maxx = P.maxx, miny = P.miny, maxy = P.maxy;
+    int cand[4][2] = { {0, 0}, {0, 0}, {0, 0}, {0, 0} }, cost[4]; bool ok[4] = { false, false, false, false };
+    auto in_range = [&](int cx, int cy) { return cx >= minx && cx <= maxx && cy >= miny && cy <= maxy; };
+        int win = 0;
+        for (int half = 0; half < 2; half++)
+        {
+            for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[half * 3 + k + 1][0]; cand[k][1] = y + c_hex2[half * 3 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
+            P.eval(3, cand, ok, cost);
+            for (int k = 0; k < 3; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 3 + k + 2; }
+        }
+        if (win)
+        {
+            int dir = win - 2;
+            x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
+            for (int i = (merange >> 1) - 1; i > 0 && in_range(x, y); i--)
+            {   // the three corners the previous hexagon did not cover
+                for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[dir + k][0]; cand[k][1] = y + c_hex2[dir + k][1]; ok[k] = P.row_ok(cand[k][1]); }
+                P.eval(3, cand, ok, cost);
+                win = 0;
+                for (int k = 0; k < 3; k++)
+                    if (ok[k] && cost[k] < best) { best = cost[k]; win = k + 1; }
+                if (!win) break;
+                dir = (dir + win - 2 + 6) % 6;                  // mod6m1[dir + 1]
+                x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
+            }
+        }
+        // square refinement around the final centre: the cross, then the corners
+        win = 0;
+        for (int half = 0; half < 2; half++)
+        {
+            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[half * 4 + k + 1][0]; cand[k][1] = y + c_sq1[half * 4 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
+            P.eval(4, cand, ok, cost);
+            for (int k = 0; k < 4; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 4 + k + 1; }
+        }
+        x += c_sq1[win][0]; y += c_sq1[win][1];
+}
+
+// X265_UMH_SEARCH, motion.cpp:1142-1324 (uneven multi-hexagon, from x264): small diamonds around the predictor, the zero vector and
+// the running best; an early-termination ladder on SAD thresholds scaled by the PU height; a cross whose reach adapts to how much
+// the neighbour vectors disagree; the 5x5 corners; rings of the 16-point hexagon at radius 1 .. merange / 4.  Returns true when
+// the search goes on into the hexagon stage with the (possibly widened) merange.  Candidate order, the row-only range check of
+// the x4 groups and the strict-less updates follow the reference; four candidates are measured per pass over the block.
+struct UmhBest { int x, y, cost; };
+template<typename PIX>
+__device__ __forceinline__ void umh_try(const PatternPU<PIX>& P, UmhBest& u, int x, int y)
+{
+    int cand[4][2] = { {x, y}, {x, y}, {x, y}, {x, y} }, cost[4]; bool ok[4] = { true, false, false, false };
+    P.eval(1, cand, ok, cost);
+    if (cost[0] < u.cost) { u.cost = cost[0]; u.x = x; u.y = y; }
+}
+template<typename PIX>
+__device__ __forceinline__ void umh_x4(const PatternPU<PIX>& P, UmhBest& u, int ox, int oy, int d0x, int d0y, int d1x, int d1y, int d2x, int d2y, int d3x, int d3y)
+{
+    int cand[4][2] = { {ox + d0x, oy + d0y}, {ox + d1x, oy + d1y}, {ox + d2x, oy + d2y}, {ox + d3x, oy + d3y} }, cost[4]; bool ok[4];
+    for (int k = 0; k < 4; k++) ok[k] = P.row_ok(cand[k][1]);
+    if (!(ok[0] | ok[1] | ok[2] | ok[3])) return;
+    P.eval(4, cand, ok, cost);
+    for (int k = 0; k < 4; k++)
+        if (ok[k] && cost[k] < u.cost) { u.cost = cost[k]; u.x = cand[k][0]; u.y = cand[k][1]; }
+}
+template<typename PIX>
+__device__ void umh_cross(const PatternPU<PIX>& P, UmhBest& u, int ox, int oy, int start, int x_max, int y_max)
+{   // CROSS, motion.cpp:359-385
+    int i = start;
+    if (x_max <= min(P.maxx - ox, ox - P.minx))
+        for (; i < x_max - 2; i += 4) umh_x4(P, u, ox, oy, i, 0, -i, 0, i + 2, 0, -i - 2, 0);
+    for (; i < x_max; i += 2)
+    {
+        if (ox + i <= P.maxx) umh_try(P, u, ox + i, oy);
+        if (ox - i >= P.minx) umh_try(P, u, ox - i, oy);
+    }
+    i = start;
+    if (y_max <= min(P.maxy - oy, oy - P.miny))
+        for (; i < y_max - 2; i += 4) umh_x4(P, u, ox, oy, 0, i, 0, -i, 0, i + 2, 0, -i - 2);
+    for (; i < y_max; i += 2)
+    {
+        if (oy + i <= P.maxy) umh_try(P, u, ox, oy + i);
+        if (oy - i >= P.miny) umh_try(P, u, ox, oy - i);
+    }
+}
+__constant__ int c_hex4[16][2] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4, -2}, {-4, -1}, {4, -1},
+                                   {-4, 0}, {4, 0}, {-4, 1}, {4, 1}, {-4, 2}, {4, 2}, {-2, 3}, {2, 3} };              // motion.cpp:68-74
+__constant__ unsigned char c_range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };     // motion.cpp:1232
+template<typename PIX>
+__device__ bool umh_search(const PatternPU<PIX>& P, int& merange, int pmvx, int pmvy, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                           int& x, int& y, int& best)
+{
+    UmhBest u = { x, y, best };
+    const int scale = (P.h * P.h) >> 4;                         // sizeScale, motion.cpp:124-152
+#define UMH_THRESH(v) (u.cost < (((v) >> 4) * scale))
+    int cross_start = 1;
+    const int ucost1 = u.cost;
+    umh_x4(P, u, pmvx, pmvy, 0, -1, 0, 1, -1, 0, 1, 0);
+    if (pmvx | pmvy) umh_x4(P, u, 0, 0, 0, -1, 0, 1, -1, 0, 1, 0);
+    const int ucost2 = u.cost;
+    if ((u.x | u.y) && (u.x != pmvx || u.y != pmvy)) umh_x4(P, u, u.x, u.y, 0, -1, 0, 1, -1, 0, 1, 0);
+    if (u.cost == ucost2) cross_start = 3;
+    int ox = u.x, oy = u.y;
+    if (u.cost == ucost2 && UMH_THRESH(2000))
+    {
+        umh_x4(P, u, ox, oy, 0, -2, -1, -1, 1, -1, -2, 0);
+        umh_x4(P, u, ox, oy, 2, 0, -1, 1, 1, 1, 0, 2);
+        if (u.cost == ucost1 && UMH_THRESH(500)) { x = u.x; y = u.y; best = u.cost; return false; }
+        if (u.cost == ucost2)
+        {
+            const int reach = (int)(int16_t)(merange >> 1) | 1;
+            umh_cross(P, u, ox, oy, 3, reach, reach);
+            umh_x4(P, u, ox, oy, -1, -2, 1, -2, -2, -1, 2, -1);
+            umh_x4(P, u, ox, oy, -2, 1, 2, 1, -1, 2, 1, 2);
+            if (u.cost == ucost2) { x = u.x; y = u.y; best = u.cost; return false; }
+            cross_start = reach + 2;
+        }
+    }
+    if (numCand)
+    {   // search range scaled by the disagreement of the predictors and by how good the match already is
+        const bool is64 = P.w == 64 && P.h == 64;
+        int mvd, denom = 1;
+        if (numCand == 1)
+            mvd = is64 ? 25 : abs(qmvp[0] - mvc[0]) + abs(qmvp[1] - mvc[1]);
+        else
+        {
+            denom = numCand - 1;
+            mvd = 0;
+            if (!is64) { mvd = abs(qmvp[0] - mvc[0]) + abs(qmvp[1] - mvc[1]); denom++; }
+            for (int i = 0; i < numCand - 1; i++)
+                mvd += abs(mvc[2 * i] - mvc[2 * i + 2]) + abs(mvc[2 * i + 1] - mvc[2 * i + 3]);
+        }
+        const int sad_ctx = UMH_THRESH(1000) ? 0 : UMH_THRESH(2000) ? 1 : UMH_THRESH(4000) ? 2 : 3;
+        const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+        merange = (merange * c_range_mul[mvd_ctx][sad_ctx]) >> 2;
+    }
+    // the cross and the corners stay centred where the diamonds ended (the reference's FIXME)
+    umh_cross(P, u, ox, oy, cross_start, merange, merange >> 1);
+    umh_x4(P, u, ox, oy, -2, -2, -2, 2, 2, -2, 2, 2);
+    // hexagon grid around the new best
+    ox = u.x; oy = u.y;
+    unsigned short i = 1;
+    do
+    {
+        const int room = min(min(P.maxx - ox, ox - P.minx), min(P.maxy - oy, oy - P.miny));
+        const bool whole = 4 * i <= room;                       // whole ring inside the window: plain int vector costs, no range checks
+        for (int j0 = 0; j0 < 16; j0 += 4)
+        {
+            int cand[4][2], cost[4]; bool ok[4];
+            for (int k = 0; k < 4; k++)
+            {
+                cand[k][0] = ox + c_hex4[j0 + k][0] * i; cand[k][1] = oy + c_hex4[j0 + k][1] * i;
+                ok[k] = whole || P.inside(cand[k][0], cand[k][1]);
+            }
+            if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+            P.eval(4, cand, ok, cost, -1, !whole);
+            for (int k = 0; k < 4; k++)
+                if (ok[k] && cost[k] < u.cost) { u.cost = cost[k]; u.x = cand[k][0]; u.y = cand[k][1]; }
+        }
+    }
+    while (++i <= merange >> 2);
+#undef UMH_THRESH
+    x = u.x; y = u.y; best = u.cost;
+    return P.inside(u.x, u.y);
+}
+
 template<typename PIX>
 __global__ void __launch_bounds__(MP_WARPS * 32)
 me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
                   const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
                   const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int n, int w, int h,
-                  int32_t* __restrict__ bmv, int32_t* __restrict__ bcost)
+                  int32_t* __restrict__ bmv, int32_t* __restrict__ bcost, int numCand, const int32_t* __restrict__ mvc)
 {
     extern __shared__ __align__(16) uint8_t mp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,43 +614,197 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
         while (--i && in_range(x, y));
     }
     else
-    {   // hexagon: the six corners around the start, in hex2[1..6] order
-        int win = 0;
-        for (int half = 0; half < 2; half++)
+    {
+        if (method == X265B200_ME_UMH)
         {
-            for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[half * 3 + k + 1][0]; cand[k][1] = y + c_hex2[half * 3 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
-            P.eval(3, cand, ok, cost);
-            for (int k = 0; k < 3; k++)
-                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 3 + k + 2; }
+            int mr = merange;
+            const int qminx = minx * 4, qmaxx = maxx * 4, qminy = miny * 4, qmaxy = maxy * 4;
+            const int pmvx = min(max(mvp[2 * pu], qminx), qmaxx), pmvy = min(max(mvp[2 * pu + 1], qminy), qmaxy);
+            if (umh_search(P, mr, (pmvx + 2) >> 2, (pmvy + 2) >> 2, mvp + 2 * pu, numCand, mvc ? mvc + 2 * (size_t)numCand * pu : nullptr, x, y, best))
+                hex_search(P, mr, x, y, best);
         }
-        if (win)
-        {
-            int dir = win - 2;
-            x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
-            for (int i = (merange >> 1) - 1; i > 0 && in_range(x, y); i--)
-            {   // the three corners the previous hexagon did not cover
-                for (int k = 0; k < 3; k++) { cand[k][0] = x + c_hex2[dir + k][0]; cand[k][1] = y + c_hex2[dir + k][1]; ok[k] = P.row_ok(cand[k][1]); }
-                P.eval(3, cand, ok, cost);
-                win = 0;
-                for (int k = 0; k < 3; k++)
-                    if (ok[k] && cost[k] < best) { best = cost[k]; win = k + 1; }
-                if (!win) break;
-                dir = (dir + win - 2 + 6) % 6;                  // mod6m1[dir + 1]
-                x += c_hex2[dir + 1][0]; y += c_hex2[dir + 1][1];
-            }
-        }
-        // square refinement around the final centre: the cross, then the corners
-        win = 0;
-        for (int half = 0; half < 2; half++)
-        {
-            for (int k = 0; k < 4; k++) { cand[k][0] = x + c_sq1[half * 4 + k + 1][0]; cand[k][1] = y + c_sq1[half * 4 + k + 1][1]; ok[k] = P.row_ok(cand[k][1]); }
-            P.eval(4, cand, ok, cost);
-            for (int k = 0; k < 4; k++)
-                if (ok[k] && cost[k] < best) { best = cost[k]; win = half * 4 + k + 1; }
-        }
-        x += c_sq1[win][0]; y += c_sq1[win][1];
+        else hex_search(P, merange, x, y, best);
     }
     if (lane == 0) { bmv[2 * pu] = x; bmv[2 * pu + 1] = y; bcost[pu] = best; }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// X265_SEA, motion.cpp:1438-1591 (successive elimination): every row of the window around the running best is pre-filtered
+// with `ads` over the twelve integral planes of the reference picture (csrc/integral.cu) and only the survivors get a SAD.
+// One warp owns a PU and walks its rows in order, because each row's threshold is the best cost so far; inside a row the
+// lanes filter 32 columns at a time (ballot + popc keeps the ascending order the reference's list has), then the survivors
+// are measured four at a time.  The reference's cost bookkeeping is reproduced as it is: the row cost comes from the table
+// shifted by the predictor a second time, indexed by the FULL-pel y and scaled by 4; survivors taken three at a time are
+// charged only the doubly shifted x-cost while the row cost is off the running best; the window width is rounded up to a
+// multiple of 4, so up to three columns right of it are examined too.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ads_terms(int w, int h)
+{   // pixel.cpp:1122-1146: which ads_x{4,2,1} a PU shape is bound to
+    if ((w == 8 && h == 4) || (w == 4 && h == 8) || (w == 16 && h == 8) || (w == 8 && h == 16) || (w == 32 && h == 16) || (w == 16 && h == 32) ||
+        (w == 64 && h == 32) || (w == 32 && h == 64)) return 2;
+    if ((w == 4 && h == 4) || (w == 8 && h == 8) || (w == 16 && h == 12) || (w == 12 && h == 16) || (w == 16 && h == 4) || (w == 4 && h == 16)) return 1;
+    return 4;
+}
+
+constexpr int SEA_MAX_WIDTH = 1024;             // survivors of one row (int16 each) per warp
+
+template<typename PIX>
+__global__ void __launch_bounds__(MP_WARPS * 32)
+me_sea_kernel(int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
+              const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
+              const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, const uint32_t* __restrict__ sums, size_t planePitch,
+              int n, int w, int h, int listCap, int32_t* __restrict__ bmv, int32_t* __restrict__ bcost)
+{
+    extern __shared__ __align__(16) uint8_t mp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pu = blockIdx.x * MP_WARPS + warp;
+    if (pu >= n) return;
+    const int rminx = range[4 * pu], rminy = range[4 * pu + 1], rmaxx = range[4 * pu + 2], rmaxy = range[4 * pu + 3];
+    if (rmaxx < rminx || rmaxy < rminy) return;
+    PIX* fs = (PIX*)mp_smem + (size_t)warp * w * h;
+    int16_t* list = (int16_t*)((PIX*)mp_smem + (size_t)MP_WARPS * w * h) + (size_t)warp * listCap;
+    const PIX* f = fenc + offF[pu];
+    {
+        int px = lane % w, py = lane / w;
+        for (int idx = lane; idx < w * h; idx += 32)
+        {
+            fs[idx] = f[(intptr_t)py * strideF + px];
+            px += 32 % w; py += 32 / w;
+            if (px >= w) { px -= w; py++; }
+        }
+    }
+    __syncwarp();
+    PatternPU<PIX> P;
+    P.fs = fs; P.r0 = ref + offR[pu]; P.strideR = strideR;
+    const int qmx = mvp[2 * pu], qmy = mvp[2 * pu + 1];
+    P.cx = costTab - qmx; P.cy = costTab - qmy;
+    P.w = w; P.h = h; P.lane = lane; P.px0 = lane % w; P.py0 = lane / w; P.dq = 32 / w; P.dr = 32 % w;
+    P.minx = rminx; P.maxx = rmaxx; P.miny = rminy; P.maxy = rmaxy;
+    const uint16_t* pcx = P.cx - qmx;
+    const uint16_t* pcy = P.cy - qmy;
+
+    int x = bmv[2 * pu], y = bmv[2 * pu + 1], best = bcost[pu];
+    const int minX = max(x - merange, rminx), minY = max(y - merange, rminy), maxX = min(x + merange, rmaxx), maxY = min(y + merange, rmaxy);
+    const int width = min((maxX - minX + 3) & ~3, listCap);
+
+    // which sub-block DCs the PU's ads form compares, and on which integral plane (motion.cpp:1445-1548)
+    int deltaX = w <= 8 ? w : w >> 1, deltaY = h <= 8 ? h : h >> 1;
+    const bool vertical = (w == 32 && h == 64) || (w == 16 && h == 32) || (w == 8 && h == 16) || (w == 4 && h == 8);
+    const bool horizontal = (w == 64 && h == 32) || (w == 32 && h == 16) || (w == 16 && h == 8) || (w == 8 && h == 4);
+    const bool smallRect = (w == 4 && h == 4) || (w == 16 && h == 12) || (w == 12 && h == 16) || (w == 16 && h == 4) || (w == 4 && h == 16);
+    const bool asym = (w == 12 && h == 16) || (w == 4 && h == 16) || (w == 24 && h == 32) || (w == 8 && h == 32) || (w == 48 && h == 64) ||
+                      (w == 16 && h == 64) || (w == 16 && h == 12) || (w == 16 && h == 4) || (w == 32 && h == 24) || (w == 32 && h == 8) ||
+                      (w == 64 && h == 48) || (w == 64 && h == 16);
+    int tw, th;
+    if (vertical) { tw = w; th = h >> 1; }
+    else if (horizontal) { tw = w >> 1; th = h; }
+    else if (asym) { tw = smallRect ? w : w >> 1; th = smallRect ? h : h >> 1; }
+    else { tw = w <= 8 ? w : w >> 1; th = w <= 8 ? h : h >> 1; }
+    long long encDC[4];
+    {
+        unsigned s4[4] = { 0, 0, 0, 0 };
+        for (int idx = lane; idx < w * h; idx += 32)
+        {
+            const int yy = idx / w, xx = idx - yy * w;
+            const unsigned v = fs[idx];
+            // sub-block k starts at (k & 1 ? deltaX : 0, k & 2 ? deltaY : 0) and is tw x th; samples outside the PU count as 0
+            if (xx < tw && yy < th) s4[0] += v;
+            if (xx >= deltaX && xx < deltaX + tw && yy < th) s4[1] += v;
+            if (xx < tw && yy >= deltaY && yy < deltaY + th) s4[2] += v;
+            if (xx >= deltaX && xx < deltaX + tw && yy >= deltaY && yy < deltaY + th) s4[3] += v;
+        }
+        for (int k = 0; k < 4; k++) encDC[k] = (long long)__reduce_add_sync(0xffffffffu, s4[k]);
+    }
+    int plane;
+    switch (deltaX)
+    {
+    case 32: plane = deltaY % 24 == 0 ? 1 : deltaY == 8 ? 2 : 0; break;
+    case 24: plane = 3; break;
+    case 16: plane = deltaY % 12 == 0 ? 5 : deltaY == 4 ? 6 : 4; break;
+    case 12: plane = 7; break;
+    case 8: plane = deltaY == 32 ? 8 : 9; break;
+    case 4: plane = deltaY == 16 ? 10 : 11; break;
+    default: plane = 11; break;
+    }
+    const uint32_t* sumsBase = sums + (size_t)plane * planePitch + offR[pu];
+    intptr_t delta = deltaY;
+    if ((w == h && w >= 16) || vertical || (w == 12 && h == 16) || (w == 4 && h == 16) || (w == 24 && h == 32) || (w == 8 && h == 32) ||
+        (w == 48 && h == 64) || (w == 16 && h == 64))
+        delta *= strideR;
+    if (vertical) encDC[1] = encDC[2];
+    if (horizontal) delta = deltaX;
+    const int terms = ads_terms(w, h), half = w >> 1;
+
+    for (int ty = minY; ty <= maxY; ty++)
+    {
+        const int ycost = (int)pcy[ty] << 2;
+        if (best <= ycost) continue;
+        best -= ycost;
+        const uint32_t* srow = sumsBase + minX + (intptr_t)ty * strideR;
+        int xn = 0;
+        for (int base = 0; base < width; base += 32)
+        {
+            const int i = base + lane;
+            bool hit = false;
+            if (i < width)
+            {
+                long long ads;
+                if (terms == 4)
+                    ads = llabs(encDC[0] - (long long)srow[i]) + llabs(encDC[1] - (long long)srow[i + half])
+                        + llabs(encDC[2] - (long long)srow[i + delta]) + llabs(encDC[3] - (long long)srow[i + delta + half]);
+                else if (terms == 2)
+                    ads = llabs(encDC[0] - (long long)srow[i]) + llabs(encDC[1] - (long long)srow[i + delta]);
+                else
+                    ads = llabs(encDC[0] - (long long)srow[i]);
+                hit = (int)(ads + P.cx[(minX + i) * 4]) < best;         // m_fpelMvCosts: the x-cost at full-pel columns
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) list[xn + __popc(m & ((1u << lane) - 1))] = (int16_t)i;
+            xn += __popc(m);
+        }
+        __syncwarp();
+        int i = 0;
+        int cand[4][2], cost[4]; bool ok[4];
+        for (; i < xn - 2; i += 3)
+        {
+            for (int k = 0; k < 4; k++) { cand[k][0] = minX + list[i + (k < 3 ? k : 2)]; cand[k][1] = ty; ok[k] = k < 3; }
+            P.eval(3, cand, ok, cost, -2);
+            for (int k = 0; k < 3; k++)
+            {
+                const int c = cost[k] + (int)pcx[cand[k][0] * 4];
+                if (c < best) { best = c; x = cand[k][0]; y = ty; }
+            }
+        }
+        best += ycost;
+        if (i < xn)
+        {
+            const int rem = xn - i;                                     // 1 or 2
+            for (int k = 0; k < 4; k++) { cand[k][0] = minX + list[i + (k < rem ? k : rem - 1)]; cand[k][1] = ty; ok[k] = k < rem; }
+            P.eval(rem, cand, ok, cost);
+            for (int k = 0; k < rem; k++)
+                if (cost[k] < best) { best = cost[k]; x = cand[k][0]; y = ty; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { bmv[2 * pu] = x; bmv[2 * pu + 1] = y; bcost[pu] = best; }
+}
+
+int launch_me_pattern(x265b200_ctx* ctx, int method, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                      const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* mvp, const uint16_t* costTab, int n,
+                      int32_t* bmv, int32_t* bcost, int numCand, const int32_t* mvc, x265b200_stream stream)
+{
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes;
+    if (ctx->pixbytes == 1)
+        me_pattern_kernel<uint8_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR,
+                                                                                     offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc);
+    else
+        me_pattern_kernel<uint16_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR,
+                                                                                      offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
 }
 
 } // namespace b200
@@ -518,16 +842,42 @@ extern "C" int x265b200_me_pattern_batch(x265b200_ctx* ctx, int method, int w, i
     if (!ctx) return X265B200_ERR_ARG;
     if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0) return fail(ctx, X265B200_ERR_ARG, "me_pattern: bad geometry");
     if (method != X265B200_ME_DIA && method != X265B200_ME_HEX && method != X265B200_ME_STAR)
-        return fail(ctx, X265B200_ERR_ARG, "me_pattern: method must be DIA, HEX or STAR");
+        return fail(ctx, X265B200_ERR_ARG, "me_pattern: method must be DIA, HEX or STAR (UMH: x265b200_me_umh_batch, SEA: x265b200_me_sea_batch)");
+    return b200::launch_me_pattern(ctx, method, w, h, merange, fenc, strideF, ref, strideR, offF, offR, range, mvp, costTab, n, bmv, bcost, 0, nullptr, stream);
+}
+
+extern "C" int x265b200_me_umh_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                     const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp, int numCand, const int32_t* mvc,
+                                     const uint16_t* costTab, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0 || numCand < 0 || numCand > 16 || (numCand && !mvc))
+        return fail(ctx, X265B200_ERR_ARG, "me_umh: bad geometry / candidates");
+    return b200::launch_me_pattern(ctx, X265B200_ME_UMH, w, h, merange, fenc, strideF, ref, strideR, offF, offR, range, qmvp, costTab, n, bmv, bcost, numCand, mvc, stream);
+}
+
+extern "C" int x265b200_me_sea_batch(x265b200_ctx* ctx, int w, int h, int merange, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                     const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp, const uint16_t* costTab,
+                                     const uint32_t* sums, size_t planePitch, int n, int32_t* bmv, int32_t* bcost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3) || n < 0 || merange < 0 || !sums)
+        return fail(ctx, X265B200_ERR_ARG, "me_sea: bad geometry / integral planes");
+    if ((w == 32 && h == 8) || (w == 8 && h == 32) || (w == 8 && h == 4) || (w == 4 && h == 8))
+        return fail(ctx, X265B200_ERR_ARG, "me_sea: the reference reads stale samples of its 64-stride fenc cache for 32x8, 8x32, 8x4 and 4x8 PUs; "
+                                            "these shapes have no defined result");
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes;
+    int listCap = 2 * merange + 8;
+    if (listCap > SEA_MAX_WIDTH) listCap = SEA_MAX_WIDTH;
+    const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes + (size_t)MP_WARPS * listCap * sizeof(int16_t);
+    if (2 * merange + 4 > SEA_MAX_WIDTH) return fail(ctx, X265B200_ERR_ARG, "me_sea: merange too large");
     if (ctx->pixbytes == 1)
-        me_pattern_kernel<uint8_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR,
-                                                                                     offF, offR, range, mvp, costTab, n, w, h, bmv, bcost);
+        me_sea_kernel<uint8_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(merange, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR, offF, offR, range,
+                                                                                 qmvp, costTab, sums, planePitch, n, w, h, listCap, bmv, bcost);
     else
-        me_pattern_kernel<uint16_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR,
-                                                                                      offF, offR, range, mvp, costTab, n, w, h, bmv, bcost);
+        me_sea_kernel<uint16_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(merange, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR, offF, offR, range,
+                                                                                  qmvp, costTab, sums, planePitch, n, w, h, listCap, bmv, bcost);
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }

@@ -274,13 +274,15 @@ static int motion_chain(x265b200_ctx* ctx, int pitch, const MeChroma& chroma, co
                         const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
                         const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
                         int numCand, const int32_t* mvc, const uint16_t* costTab, int n,
-                        int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+                        int32_t* outQMv, int32_t* outCost, x265b200_stream stream, const uint32_t* sums = nullptr, size_t sumsPitch = 0)
 {
     if (!ctx) return X265B200_ERR_ARG;
     if (subpelRefine < 0 || subpelRefine > 7 || numCand < 0 || numCand > ME_MAX_CAND || n < 0 || (numCand && !mvc))
         return fail(ctx, X265B200_ERR_ARG, "motion_estimate: bad arguments");
-    if (searchMethod != X265B200_ME_DIA && searchMethod != X265B200_ME_HEX && searchMethod != X265B200_ME_STAR && searchMethod != X265B200_ME_FULL)
-        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: search method not built (DIA, HEX, STAR, FULL are)");
+    if (searchMethod < X265B200_ME_DIA || searchMethod > X265B200_ME_FULL)
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: unknown search method");
+    if (searchMethod == X265B200_ME_SEA && !sums)
+        return fail(ctx, X265B200_ERR_ARG, "motion_estimate: X265_SEA needs the integral planes (x265b200_motion_estimate_sea_batch)");
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -350,6 +352,10 @@ static int motion_chain(x265b200_ctx* ctx, int pitch, const MeChroma& chroma, co
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     if (searchMethod == X265B200_ME_FULL)
         rc = x265b200_me_full_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream);
+    else if (searchMethod == X265B200_ME_UMH)
+        rc = x265b200_me_umh_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, numCand, mvc, costTab, n, s.bmv, s.bcost, stream);
+    else if (searchMethod == X265B200_ME_SEA)
+        rc = x265b200_me_sea_batch(ctx, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, sums, sumsPitch, n, s.bmv, s.bcost, stream);
     else
         rc = x265b200_me_pattern_batch(ctx, searchMethod, w, h, merange, fenc, strideF, ref, strideR, offF, offR, s.eff, qmvp, costTab, n, s.bmv, s.bcost, stream);
     if (rc) return bail(rc);
@@ -374,6 +380,17 @@ extern "C" int x265b200_motion_estimate_batch(x265b200_ctx* ctx, int searchMetho
 {
     return motion_chain(ctx, 0, MeChroma{ 0, 0, 0, 0, nullptr }, MeChromaArgs{}, searchMethod, w, h, merange, subpelRefine, fenc, strideF, ref, strideR,
                         offF, offR, range, qmvp, numCand, mvc, costTab, n, outQMv, outCost, stream);
+}
+
+extern "C" int x265b200_motion_estimate_sea_batch(x265b200_ctx* ctx, int w, int h, int merange, int subpelRefine,
+                                                  const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                                  const int32_t* offF, const int32_t* offR, const int32_t* range, const int32_t* qmvp,
+                                                  int numCand, const int32_t* mvc, const uint16_t* costTab,
+                                                  const uint32_t* sums, size_t planePitch, int n,
+                                                  int32_t* outQMv, int32_t* outCost, x265b200_stream stream)
+{
+    return motion_chain(ctx, 0, MeChroma{ 0, 0, 0, 0, nullptr }, MeChromaArgs{}, X265B200_ME_SEA, w, h, merange, subpelRefine, fenc, strideF, ref, strideR,
+                        offF, offR, range, qmvp, numCand, mvc, costTab, n, outQMv, outCost, stream, sums, planePitch);
 }
 
 extern "C" int x265b200_lowres_motion_estimate_batch(x265b200_ctx* ctx, int searchMethod, int w, int h, int merange, int subpelRefine,

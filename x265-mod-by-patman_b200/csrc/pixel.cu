@@ -8,6 +8,8 @@
 // transform needs no shuffles; a group of G = min(32, pow2ceil(#tiles)) lanes shares one block and
 // reduces with xor-shuffles.  Adjacent lanes take horizontally adjacent tiles, so a warp-wide
 // load covers whole 128-byte lines of the plane.
+#include <stdio.h>
+#include <stdlib.h>
 #include "internal.h"
 #include "device_util.cuh"
 #include "tile_kernels.cuh"
@@ -555,6 +557,43 @@ extern "C" int x265b200_pixelcmp_batch(x265b200_ctx* ctx, int op, int w, int h, 
     cudaStream_t st = (cudaStream_t)stream;
     return ctx->pixbytes == 1 ? launch_pixelcmp<uint8_t>(ctx, op, w, h, (const uint8_t*)A, sa, (const uint8_t*)B, sb, offA, offB, 1, n, out, st)
                               : launch_pixelcmp<uint16_t>(ctx, op, w, h, (const uint16_t*)A, sa, (const uint16_t*)B, sb, offA, offB, 1, n, out, st);
+}
+
+template<typename T>
+static int launch_cu_satd(x265b200_ctx* ctx, int S, const T* A, intptr_t sa, const T* B, intptr_t sb, const int32_t* offF, const int32_t* offR,
+                          int n, int32_t* out, cudaStream_t st)
+{
+    // lanes per CU: one tile per lane up to 16x16, then 2 / 8 tiles per lane (a warp per CU)
+    int G = S == 8 ? 4 : S == 16 ? 16 : 32;
+    if (const char* e = getenv("X265B200_CU_LANES_LAB"))       // tuning lab only (tools/cu_satd_sweep.py)
+    {
+        int g[4] = { 4, 16, 32, 32 };
+        sscanf(e, "%d,%d,%d,%d", &g[0], &g[1], &g[2], &g[3]);
+        G = g[S == 8 ? 0 : S == 16 ? 1 : S == 32 ? 2 : 3];
+    }
+    const int grid = ceil_div((long long)n * G, 128);
+    switch (S)
+    {
+    case 8:  cu_satd_kernel<T, 8><<<grid, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out); break;
+    case 16: cu_satd_kernel<T, 16><<<grid, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out); break;
+    case 32: cu_satd_kernel<T, 32><<<grid, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out); break;
+    default: cu_satd_kernel<T, 64><<<grid, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out); break;
+    }
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
+
+extern "C" int x265b200_cu_satd_batch(x265b200_ctx* ctx, int cuSize, const void* fenc, intptr_t strideF, const void* ref, intptr_t strideR,
+                                      const int32_t* offF, const int32_t* offR, int n, int32_t* cost, x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if ((cuSize != 8 && cuSize != 16 && cuSize != 32 && cuSize != 64) || n < 0) return fail(ctx, X265B200_ERR_ARG, "cu_satd: CU size must be 8, 16, 32 or 64");
+    if ((strideF | strideR) & 3) return fail(ctx, X265B200_ERR_ARG, "cu_satd: plane strides must be multiples of 4 samples");
+    if (n == 0) return X265B200_OK;
+    if (!fenc || !ref || !offF || !offR || !cost) return fail(ctx, X265B200_ERR_ARG, "cu_satd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    return ctx->pixbytes == 1 ? launch_cu_satd<uint8_t>(ctx, cuSize, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR, offF, offR, n, cost, st)
+                              : launch_cu_satd<uint16_t>(ctx, cuSize, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR, offF, offR, n, cost, st);
 }
 
 extern "C" int x265b200_sad_multi_batch(x265b200_ctx* ctx, int w, int h, const void* fenc, intptr_t sf,

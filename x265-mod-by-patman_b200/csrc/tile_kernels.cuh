@@ -170,4 +170,66 @@ strip8_fast_kernel(const uint16_t* __restrict__ A, intptr_t sa, const uint16_t* 
     if (live && l == 0) out[blk] = (OUT)acc;
 }
 
+// All rectangular partitions of a CU in one pass (SATD): the 2Nx2N PU, the two 2NxN PUs and the two Nx2N PUs of an S x S
+// CU, each against its OWN reference block (five motion vectors per CU), as the inter analysis costs them
+// (reference encoder/search.cpp predInterSearch -> one satd per PU; encoder/analysis.cpp checkInter_rd0_4 for SIZE_2Nx2N /
+// SIZE_2NxN / SIZE_Nx2N).  Every PU's SATD is the sum of its 4x4-tile SATDs (tile4_accumulate), so a lane that owns a fenc
+// tile loads it ONCE and meets it with the matching tile of three reference blocks; the three per-shape launches read the
+// fenc plane three times.  offR[5 * cu + k], out[5 * cu + k]: k = 0 2Nx2N, 1 / 2 upper / lower 2NxN, 3 / 4 left / right Nx2N,
+// each offset addressing the top-left sample of that PU's reference block.  G lanes (power of two) share a CU.
+template<typename T, int S>
+__global__ void __launch_bounds__(128)
+cu_satd_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
+               const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, int n, int G, int32_t* __restrict__ out)
+{
+    constexpr int TW = S >> 2, T4 = TW * TW, HALF = S >> 1;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lg = __ffs(G) - 1;
+    int cu = (int)(gid >> lg);
+    int l = (int)gid & (G - 1);
+    bool live = cu < n;
+    int acc0 = 0, accH0 = 0, accH1 = 0, accV0 = 0, accV1 = 0;
+    if (live)
+    {
+        const T* a = A + offF[cu];
+        const int32_t* r = offR + 5 * (size_t)cu;
+        const T* b0 = B + r[0];
+        const T* bH[2] = { B + r[1], B + r[2] };
+        const T* bV[2] = { B + r[3], B + r[4] };
+        for (int t = l; t < T4; t += G)
+        {
+            const int x = (t % TW) << 2, y = (t / TW) << 2;
+            const int kH = y >= HALF, kV = x >= HALF;
+            uint32_t alo[4], ahi[4], b0lo[4], b0hi[4], b1lo[4], b1hi[4], b2lo[4], b2hi[4];
+            load_tile4x4(a + (intptr_t)y * sa + x, sa, alo, ahi);
+            load_tile4x4(b0 + (intptr_t)y * sb + x, sb, b0lo, b0hi);
+            load_tile4x4((kH ? bH[1] : bH[0]) + (intptr_t)(y - kH * HALF) * sb + x, sb, b1lo, b1hi);
+            load_tile4x4((kV ? bV[1] : bV[0]) + (intptr_t)y * sb + (x - kV * HALF), sb, b2lo, b2hi);
+            int c0 = 0, c1 = 0, c2 = 0;
+            tile4_accumulate<OP_SATD, int>(alo, ahi, b0lo, b0hi, c0);
+            tile4_accumulate<OP_SATD, int>(alo, ahi, b1lo, b1hi, c1);
+            tile4_accumulate<OP_SATD, int>(alo, ahi, b2lo, b2hi, c2);
+            acc0 += c0;
+            accH0 += kH ? 0 : c1; accH1 += kH ? c1 : 0;
+            accV0 += kV ? 0 : c2; accV1 += kV ? c2 : 0;
+        }
+    }
+    acc0 = group_sum(acc0, G);
+    accH0 = group_sum(accH0, G); accH1 = group_sum(accH1, G);
+    accV0 = group_sum(accV0, G); accV1 = group_sum(accV1, G);
+    if (live && l < 5)
+    {
+        int v = l == 0 ? acc0 : l == 1 ? accH0 : l == 2 ? accH1 : l == 3 ? accV0 : accV1;
+        if (G >= 8 || l == 0)
+        {
+            if (G >= 8) out[5 * (size_t)cu + l] = v;
+            else
+            {
+                int32_t* o = out + 5 * (size_t)cu;
+                o[0] = acc0; o[1] = accH0; o[2] = accH1; o[3] = accV0; o[4] = accV1;
+            }
+        }
+    }
+}
+
 } // namespace b200
