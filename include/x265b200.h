@@ -333,6 +333,14 @@ int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t s
  * mode in picture orientation.  Feed dst to x265b200_pixelcmp_batch (sa8d / satd) for the mode costs. */
 int x265b200_intra_pred_batch(x265b200_ctx* ctx, int N, const void* neighbours, int n, void* dst, x265b200_stream stream);
 
+/* The table's three intra slots over n TUs of N x N (4 .. 32), each TU with its own (4N + 1)-sample neighbour array (top-left, 2N above, 2N left;
+ * arrays contiguous): kind 0 = intra_pred[mode] (intra_pred_t, reference common/intrapred.cpp:66-204: planar 0, DC 1, angular 2 .. 34; bFilter
+ * as the slot's argument) -> dst[i * N * N ..]; kind 1 = intra_filter (intrapred.cpp:31-51) -> dst[i * (4N + 1) ..]; kind 2 =
+ * intra_pred_allangs (intrapred.cpp:206-233: modes 2 .. 34, `filt` = the smoothed neighbours, horizontal modes un-flipped, bFilter = bLuma)
+ * -> dst[i * 33 * N * N ..].  filt is only read by kind 2. */
+int x265b200_intra_slot_batch(x265b200_ctx* ctx, int kind, int N, int mode, int bFilter, const void* src, const void* filt, int n, void* dst,
+                              x265b200_stream stream);
+
 /* D block i = op(A block i, B block i) for n blocks of w x h (1..64 each); element types follow the op (see the enum).
  * An offset array may be NULL: blocks are then contiguous (block i at i * w * h, use stride = w). */
 int x265b200_blockop_batch(x265b200_ctx* ctx, int op, int w, int h, const void* A, intptr_t strideA, const int32_t* offA,
@@ -522,6 +530,12 @@ void x265b200_weight_pp(x265b200_ctx*, const void* src, void* dst, intptr_t stri
 void x265b200_weight_sp(x265b200_ctx*, const int16_t* src, void* dst, intptr_t srcStride, intptr_t dstStride, int width, int height, int w0, int round, int shift, int offset);
 void x265b200_integral_inith(x265b200_ctx*, int W, uint32_t* sum, const void* pix, intptr_t stride);
 void x265b200_integral_initv(x265b200_ctx*, int H, uint32_t* sum, intptr_t stride);
+
+/* intra_pred_t / intra_filter_t / intra_allangs_t (primitives.h:143-145) with the TU size (and the mode, which the reference passes
+ * as dirMode and also bakes into the slot index) prepended */
+void x265b200_intra_pred(x265b200_ctx*, int N, int mode, void* dst, intptr_t dstStride, const void* srcPix, int bFilter);
+void x265b200_intra_filter(x265b200_ctx*, int N, const void* samples, void* filtered);
+void x265b200_intra_pred_allangs(x265b200_ctx*, int N, void* dst, const void* refPix, const void* filtPix, int bLuma);
 
 #ifdef __cplusplus
 }

@@ -6,18 +6,19 @@
  * Mirrors reference source/test/testbench.cpp:224-265: C table = setupCPrimitives +
  * setupAliasPrimitives; table under test = zeroed + setupB200Primitives + setupAliasPrimitives,
  * copied into the global `primitives` because HBD aliases dispatch through it; then
- * harness->testCorrectness(cprim, b200prim) for PixelHarness, MBDstHarness, IPFilterHarness.
+ * harness->testCorrectness(cprim, b200prim) for PixelHarness, MBDstHarness, IPFilterHarness, IntraPredHarness.
  * Also checks the coverage contract: every hot-path slot that is non-NULL in the C table is bound to
  * a B200 thunk (not NULL, not the C function).
  *
  * The B200 filler is loaded with dlopen from ../../x265-mod-by-patman_b200/lib so this binary does
- * not link CUDA itself.  usage: testbench_b200_<depth> [seed] [pixel|transforms|interp]
+ * not link CUDA itself.  usage: testbench_b200_<depth> [seed] [pixel|transforms|interp|intrapred]
  */
 #include "common.h"
 #include "primitives.h"
 #include "pixelharness.h"
 #include "mbdstharness.h"
 #include "ipfilterharness.h"
+#include "intrapredharness.h"
 
 #include <dlfcn.h>
 #include <libgen.h>
@@ -43,6 +44,7 @@ const char* const* chromaPartStr[X265_CSP_COUNT] = { lumaPartStr, chroma420Str, 
 static PixelHarness HPixel;
 static MBDstHarness HMBDist;
 static IPFilterHarness HIPFilter;
+static IntraPredHarness HIPred;
 
 static EncoderPrimitives cprim, b200prim;
 
@@ -103,6 +105,11 @@ static int coverage()
         for (int c = 1; c < X265_CSP_COUNT; c++) { SLOT(chroma[c].cu[i].copy_ss); SLOT(chroma[c].cu[i].copy_sp); SLOT(chroma[c].cu[i].copy_ps); SLOT(chroma[c].cu[i].copy_pp); }
         aliasOK = false;
     }
+    for (int i = 0; i < NUM_CU_SIZES; i++)
+    {
+        SLOT(cu[i].intra_filter); SLOT(cu[i].intra_pred_allangs);
+        for (int m = 0; m < NUM_INTRA_MODE; m++) SLOT(cu[i].intra_pred[m]);
+    }
     SLOT(frameInitLowres); SLOT(weight_pp); SLOT(weight_sp); SLOT(denoiseDct);
     for (int i = 0; i < NUM_INTEGRAL_SIZE; i++) { SLOT(integral_inith[i]); SLOT(integral_initv[i]); }
     printf("adjacent: %d slots in the C table, %d bound to B200 entries, %d missing, %d still C, %d extra\n", want, bound, missing, same, extra);
@@ -141,7 +148,7 @@ int main(int argc, char** argv)
 
     if (coverage()) { fprintf(stderr, "coverage contract violated\n"); return 2; }
 
-    TestHarness* harness[] = { &HPixel, &HMBDist, &HIPFilter };
+    TestHarness* harness[] = { &HPixel, &HMBDist, &HIPFilter, &HIPred };
     for (size_t i = 0; i < sizeof(harness) / sizeof(harness[0]); i++)
     {
         if (only && strncmp(only, harness[i]->getName(), strlen(only))) continue;

@@ -860,3 +860,37 @@ def test_intra_pred_batch(depth):
             ref = np.array([orc.sa8d(N, N, fenc, int(a), N, want, int(b), N) for a, b in zip(offA, offB)], np.int32)
             assert np.array_equal(cost.cpu().numpy(), ref), (N, "sa8d")
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_intra_host_slots(depth):
+    """the per-call intra slots (intra_pred[35], intra_filter, intra_pred_allangs) vs the oracle, every size and mode; the reference's own
+    IntraPredHarness runs against the same entries through the table in test_gpu_testbench.py"""
+    import ctypes as C
+    from gpulib import context
+    ctx = context(depth); orc = Oracle(depth)
+    rng = np.random.default_rng(1100 + depth)
+    for N in (4, 8, 16, 32):
+        L = 4 * N + 1
+        for trial in range(3):
+            nb = rng.integers(0, orc.pmax + 1, L).astype(orc.pix) if trial < 2 else ((np.arange(L) % 3 == 0) * orc.pmax).astype(orc.pix)
+            filt = orc.intra_filter(N, nb)
+            got = np.zeros(L, orc.pix)
+            ctx.lib.x265b200_intra_filter(ctx.h, N, C.c_void_p(nb.ctypes.data), C.c_void_p(got.ctypes.data))
+            assert np.array_equal(got, filt), N
+            for mode in range(35):
+                for bFilter in (0, 1):
+                    stride = N + 5
+                    out = np.full(N * stride, 7, orc.pix)
+                    ctx.lib.x265b200_intra_pred(ctx.h, N, mode, C.c_void_p(out.ctypes.data), C.c_ssize_t(stride), C.c_void_p(nb.ctypes.data), bFilter)
+                    want = orc.intra_pred(N, mode, nb, bFilter).reshape(N, N)
+                    assert np.array_equal(out.reshape(N, stride)[:, :N], want), (N, mode, bFilter)
+                    assert (out.reshape(N, stride)[:, N:] == 7).all()
+            from cpulibs import Reference, have_reference
+            if have_reference(depth):
+                for bLuma in (0, 1):
+                    want = Reference(depth).intra_allangs(N, nb.copy(), filt.copy(), bLuma)
+                    got33 = np.zeros(33 * N * N, orc.pix)
+                    ctx.lib.x265b200_intra_pred_allangs(ctx.h, N, C.c_void_p(got33.ctypes.data), C.c_void_p(nb.ctypes.data), C.c_void_p(filt.ctypes.data), bLuma)
+                    assert np.array_equal(got33, want), (N, bLuma)
+    ctx.check()

@@ -1,4 +1,4 @@
-"""The reference's own TestBench harness classes (PixelHarness, MBDstHarness, IPFilterHarness --
+"""The reference's own TestBench harness classes (PixelHarness, MBDstHarness, IPFilterHarness, IntraPredHarness --
 reference source/test/*.cpp, unmodified, prebuilt into oracle/_ref/testbench_b200_<depth> by
 `make -C oracle harness`) run against the B200 table filled by setupB200Primitives.
 This is the reference's own opt-vs-C parity check (testbench.cpp:229-277) with `opt` = CUDA."""

@@ -12,14 +12,14 @@ F = 32
 geo = Geometry(3840, 2160); pe = geo.plane_elems
 A = torch.from_numpy(make_plane(geo, 10, 1, "natural").view(np.int16)).cuda().repeat(F)
 B = torch.from_numpy(make_plane(geo, 10, 2, "natural").view(np.int16)).cuda().repeat(F)
-for S, Gs in ((8, (1, 2, 4)), (16, (2, 4, 8, 16)), (32, (8, 16, 32)), (64, (16, 32))):
+for S, Gs in ((8, (1, 2, 4)), (16, (2, 4, 8, 16)), (32, (4, 8, 16, 32)), (64, (8, 16, 32))):
     oF, oR5, _ = cu_descriptors(geo, S, *[tile_blocks(geo, w, h, seed=1) for (w, h) in ((S, S), (S, S // 2), (S // 2, S))])
     a = torch.from_numpy(np.concatenate([oF.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)).cuda()
     b = torch.from_numpy(np.concatenate([oR5.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)).cuda()
     out = torch.empty(5 * a.numel(), dtype=torch.int32, device="cuda")
     base = None
     for G in Gs:
-        lanes = {8: [G, 16, 32, 32], 16: [4, G, 32, 32], 32: [4, 16, G, 32], 64: [4, 16, 32, G]}[S]
+        lanes = {8: [G, 4, 8, 32], 16: [2, G, 8, 32], 32: [2, 4, G, 32], 64: [2, 4, 8, G]}[S]
         os.environ["X265B200_CU_LANES_LAB"] = ",".join(map(str, lanes))
         for _ in range(3):
             ctx.cu_satd_batch(S, A, geo.stride, B, geo.stride, a, b, out)

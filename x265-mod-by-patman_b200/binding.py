@@ -59,7 +59,8 @@ def load_library():
             getattr(_lib, name).restype = None
         for name in ("x265b200_close", "x265b200_sad_x3", "x265b200_sad_x4", "x265b200_dct", "x265b200_idct",
                      "x265b200_dequant_normal", "x265b200_dequant_scaling", "x265b200_interp", "x265b200_sub_ps", "x265b200_add_ps",
-                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy", "x265b200_denoise_dct"):
+                     "x265b200_pixelavg_pp", "x265b200_addAvg", "x265b200_frame_init_lowres", "x265b200_integral_inith", "x265b200_integral_initv", "x265b200_weight_pp", "x265b200_weight_sp", "x265b200_blockcopy", "x265b200_denoise_dct",
+                     "x265b200_intra_pred", "x265b200_intra_filter", "x265b200_intra_pred_allangs"):
             getattr(_lib, name).restype = None
     return _lib
 

@@ -661,3 +661,30 @@ extern "C" void x265b200_denoise_dct(x265b200_ctx* ctx, int16_t* dctCoef, uint32
     memcpy(dctCoef, c.h<void>(oC), (size_t)numCoeff * 2);
     memcpy(resSum, c.h<void>(oR), (size_t)numCoeff * 4);
 }
+
+// ------------------------------------------------------------------ host entries: intra prediction slots (intra.cu)
+
+static void host_intra(x265b200_ctx* ctx, int kind, int N, int mode, int bFilter, const void* src, const void* filt, void* dst, intptr_t dstStride)
+{
+    Call c(ctx);
+    if (!c.ok()) return;
+    const size_t pb = ctx->pixbytes, L = (size_t)(4 * N + 1) * pb;
+    const size_t outElems = kind == 1 ? (size_t)(4 * N + 1) : kind == 0 ? (size_t)N * N : (size_t)33 * N * N;
+    size_t oS = c.alloc(L), oF = c.alloc(L);
+    size_t inEnd = c.used;
+    size_t oD = c.alloc(outElems * pb);
+    if (!c.ok()) return;
+    memcpy(c.h<void>(oS), src, L);
+    if (filt) memcpy(c.h<void>(oF), filt, L);
+    if (!c.upload(0, inEnd)) return;
+    if (x265b200_intra_slot_batch(ctx, kind, N, mode, bFilter, c.d<void>(oS), filt ? c.d<void>(oF) : nullptr, 1, c.d<void>(oD), c.st()) != X265B200_OK) return;
+    if (!c.download(oD, outElems * pb)) return;
+    if (kind == 0) unpack(dst, c.h<void>(oD), N, N * pb, dstStride * (intptr_t)pb);
+    else memcpy(dst, c.h<void>(oD), outElems * pb);
+}
+extern "C" void x265b200_intra_pred(x265b200_ctx* ctx, int N, int mode, void* dst, intptr_t dstStride, const void* srcPix, int bFilter)
+{ if (ctx) host_intra(ctx, 0, N, mode, bFilter, srcPix, nullptr, dst, dstStride); }
+extern "C" void x265b200_intra_filter(x265b200_ctx* ctx, int N, const void* samples, void* filtered)
+{ if (ctx) host_intra(ctx, 1, N, 0, 0, samples, nullptr, filtered, 0); }
+extern "C" void x265b200_intra_pred_allangs(x265b200_ctx* ctx, int N, void* dst, const void* refPix, const void* filtPix, int bLuma)
+{ if (ctx) host_intra(ctx, 2, N, 0, bLuma, refPix, filtPix, dst, 0); }

@@ -244,9 +244,71 @@ intra_pred_all_kernel(const PIX* __restrict__ neighbours, int N, int lgN, int pm
     }
 }
 
+// The three intra slots of the table as they are called one TU at a time (reference common/intrapred.cpp:31-233), batched over n TUs:
+//   kind 0  intra_pred[mode](dst, dstStride, srcPix, mode, bFilter): one N x N prediction from the (4N + 1) neighbours the caller chose
+//   kind 1  intra_filter(samples, filtered): the 1:2:1 smoothing of the neighbour array
+//   kind 2  intra_pred_allangs(dst, refPix, filtPix, bLuma): modes 2 .. 34, each from the smoothed or the plain neighbours as
+//           g_intraFilterFlags says, horizontal modes left un-flipped (the reference transposes them back, intrapred.cpp:217-231)
+template<typename PIX>
+__global__ void __launch_bounds__(256)
+intra_slot_kernel(int kind, int N, int lgN, int mode, int bFilter, const PIX* __restrict__ src, const PIX* __restrict__ filt, int pmax, PIX* __restrict__ dst)
+{
+    __shared__ uint16_t s[4 * 32 + 1 + 3], f[4 * 32 + 1 + 3];
+    const int tu = blockIdx.x, L = 4 * N + 1, NN = N * N;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) { s[i] = src[(size_t)tu * L + i]; if (filt) f[i] = filt[(size_t)tu * L + i]; }
+    __syncthreads();
+    if (kind == 1)
+    {
+        for (int i = threadIdx.x; i < L; i += blockDim.x)
+        {   // intrapred.cpp:31-51
+            int v;
+            if (i == 0) v = (2 * s[0] + s[1] + s[2 * N + 1] + 2) >> 2;
+            else if (i == 2 * N || i == 4 * N) v = s[i];
+            else if (i == 2 * N + 1) v = (2 * s[i] + s[0] + s[i + 1] + 2) >> 2;
+            else v = (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
+            dst[(size_t)tu * L + i] = (PIX)v;
+        }
+        return;
+    }
+    if (kind == 0)
+    {
+        int dc = N;
+        if (mode == 1)
+        {
+            for (int i = 0; i < N; i++) dc += s[1 + i] + s[2 * N + 1 + i];
+            dc /= 2 * N;
+        }
+        for (int o = threadIdx.x; o < NN; o += blockDim.x)
+            dst[(size_t)tu * NN + o] = (PIX)intra_px_n(s, N, lgN, mode, bFilter, dc, o >> lgN, o & (N - 1), pmax);
+        return;
+    }
+    for (int o = threadIdx.x; o < 33 * NN; o += blockDim.x)
+    {
+        const int m = 2 + (o >> (2 * lgN)), rc = o & (NN - 1), r = rc >> lgN, c = rc & (N - 1);
+        const uint16_t* nb = (c_intraFilterFlags[m] & N) ? f : s;
+        const bool hor = m < 18;
+        dst[(size_t)tu * 33 * NN + o] = (PIX)intra_px_n(nb, N, lgN, m, bFilter, 0, hor ? c : r, hor ? r : c, pmax);
+    }
+}
+
 } // namespace b200
 
 using namespace b200;
+
+extern "C" int x265b200_intra_slot_batch(x265b200_ctx* ctx, int kind, int N, int mode, int bFilter, const void* src, const void* filt, int n, void* dst,
+                                         x265b200_stream stream)
+{
+    if (!ctx) return X265B200_ERR_ARG;
+    if ((N != 4 && N != 8 && N != 16 && N != 32) || n < 0 || kind < 0 || kind > 2 || (kind == 0 && (mode < 0 || mode > 34)) || (kind == 2 && !filt))
+        return fail(ctx, X265B200_ERR_ARG, "intra_slot: bad size / kind / mode");
+    if (n == 0) return X265B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lgN = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5, pmax = (1 << ctx->depth) - 1;
+    if (ctx->pixbytes == 1) intra_slot_kernel<uint8_t><<<n, 256, 0, st>>>(kind, N, lgN, mode, bFilter, (const uint8_t*)src, (const uint8_t*)filt, pmax, (uint8_t*)dst);
+    else intra_slot_kernel<uint16_t><<<n, 256, 0, st>>>(kind, N, lgN, mode, bFilter, (const uint16_t*)src, (const uint16_t*)filt, pmax, (uint16_t*)dst);
+    B200_LAUNCH_CHECK(ctx);
+    return X265B200_OK;
+}
 
 extern "C" int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty,
                                            int32_t* cost, int32_t* mode, x265b200_stream stream)

@@ -563,11 +563,13 @@ template<typename T>
 static int launch_cu_satd(x265b200_ctx* ctx, int S, const T* A, intptr_t sa, const T* B, intptr_t sb, const int32_t* offF, const int32_t* offR,
                           int n, int32_t* out, cudaStream_t st)
 {
-    // lanes per CU: one tile per lane up to 16x16, then 2 / 8 tiles per lane (a warp per CU)
-    int G = S == 8 ? 4 : S == 16 ? 16 : 32;
+    // lanes per CU, from tools/cu_satd_sweep.py on B200 (2160p10 x 32 frames, ms per launch): 8x8: 1 / 2 / 4 lanes 0.90 / 0.62 / 0.76;
+    // 16x16: 2 / 4 / 8 / 16 lanes 0.50 / 0.41 / 0.47 / 0.61; 32x32: 8 / 16 / 32 lanes 0.39 / 0.39 / 0.43; 64x64: 16 / 32 lanes 0.42 / 0.37.
+    // Few lanes with several tiles each win: a lane's three SATDs per tile amortise the five shuffle reductions of the CU.
+    int G = S == 8 ? 2 : S == 16 ? 4 : S == 32 ? 8 : 32;
     if (const char* e = getenv("X265B200_CU_LANES_LAB"))       // tuning lab only (tools/cu_satd_sweep.py)
     {
-        int g[4] = { 4, 16, 32, 32 };
+        int g[4] = { 2, 4, 8, 32 };
         sscanf(e, "%d,%d,%d,%d", &g[0], &g[1], &g[2], &g[3]);
         G = g[S == 8 ? 0 : S == 16 ? 1 : S == 32 ? 2 : 3];
     }

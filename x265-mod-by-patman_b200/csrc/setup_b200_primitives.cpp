@@ -50,6 +50,13 @@ uint32_t t_nquant(const int16_t* c, const int32_t* q, int16_t* qc, int qBits, in
 void t_dequant_normal(const int16_t* q, int16_t* c, int num, int scale, int shift) { x265b200_dequant_normal(g_b200, q, c, num, scale, shift); }
 void t_dequant_scaling(const int16_t* q, const int32_t* dq, int16_t* c, int num, int per, int shift) { x265b200_dequant_scaling(g_b200, q, dq, c, num, per, shift); }
 
+// ---- intra prediction (adjacent slots: the analysis' mode scan and the lookahead's intra estimate call them) ----
+template<int N> void t_intra_pred(pixel* dst, intptr_t dstStride, const pixel* srcPix, int dirMode, int bFilter) { x265b200_intra_pred(g_b200, N, dirMode, dst, dstStride, srcPix, bFilter); }
+template<int N> void t_intra_planar(pixel* dst, intptr_t dstStride, const pixel* srcPix, int, int bFilter) { x265b200_intra_pred(g_b200, N, 0, dst, dstStride, srcPix, bFilter); }
+template<int N> void t_intra_dc(pixel* dst, intptr_t dstStride, const pixel* srcPix, int, int bFilter) { x265b200_intra_pred(g_b200, N, 1, dst, dstStride, srcPix, bFilter); }
+template<int N> void t_intra_filter(const pixel* samples, pixel* filtered) { x265b200_intra_filter(g_b200, N, samples, filtered); }
+template<int N> void t_intra_allangs(pixel* dst, pixel* refPix, pixel* filtPix, int bLuma) { x265b200_intra_pred_allangs(g_b200, N, dst, refPix, filtPix, bLuma); }
+
 // ---- interpolation ----
 template<int T, int W, int H> void t_hpp(const pixel* s, intptr_t ss, pixel* d, intptr_t ds, int idx) { x265b200_interp(g_b200, X265B200_IP_HPP, T, W, H, s, ss, d, ds, idx, 0); }
 template<int T, int W, int H> void t_hps(const pixel* s, intptr_t ss, int16_t* d, intptr_t ds, int idx, int ext) { x265b200_interp(g_b200, X265B200_IP_HPS, T, W, H, s, ss, d, ds, idx, ext); }
@@ -194,6 +201,12 @@ void setupB200Primitives(EncoderPrimitives& p)
     lumaCoef<4>(p.cu[BLOCK_4x4]); lumaCoef<8>(p.cu[BLOCK_8x8]); lumaCoef<16>(p.cu[BLOCK_16x16]); lumaCoef<32>(p.cu[BLOCK_32x32]);
     p.denoiseDct = t_denoise;
     p.frameInitLowres = t_lowres;
+#define B200_INTRA(IDX, N) \
+    p.cu[IDX].intra_filter = t_intra_filter<N>; p.cu[IDX].intra_pred_allangs = t_intra_allangs<N>; \
+    p.cu[IDX].intra_pred[PLANAR_IDX] = t_intra_planar<N>; p.cu[IDX].intra_pred[DC_IDX] = t_intra_dc<N>; \
+    for (int m = 2; m < NUM_INTRA_MODE; m++) p.cu[IDX].intra_pred[m] = t_intra_pred<N>;
+    B200_INTRA(BLOCK_4x4, 4) B200_INTRA(BLOCK_8x8, 8) B200_INTRA(BLOCK_16x16, 16) B200_INTRA(BLOCK_32x32, 32)
+#undef B200_INTRA
     p.weight_pp = t_weight_pp;  p.weight_sp = t_weight_sp;
     p.integral_inith[INTEGRAL_4] = t_integral_h<4>;   p.integral_initv[INTEGRAL_4] = t_integral_v<4>;
     p.integral_inith[INTEGRAL_8] = t_integral_h<8>;   p.integral_initv[INTEGRAL_8] = t_integral_v<8>;
