@@ -233,15 +233,22 @@ def test_tu_chain_batch(depth):
         d_recon = dev(pix_view(np.full(geo.plane_elems, 5, orc.pix), depth))
         q = torch.zeros(n * N * N, dtype=torch.int16, device="cuda"); ns = torch.zeros(n, dtype=torch.int32, device="cuda")
         z = torch.zeros(n, dtype=torch.int64, device="cuda"); r = torch.zeros(n, dtype=torch.int64, device="cuda")
-        ctx.tu_chain_batch(N, dev(pix_view(F, depth)), geo.stride, dev(pix_view(Pcur, depth)), geo.stride, dev(offF), dev(offP), dev(qc),
-                           qbits, add, scale, shift, q, ns, d_recon, geo.stride, dev(offF), z, r)
-        assert np.array_equal(ns.cpu().numpy().astype(np.uint32), rns), (N, qp)
-        assert np.array_equal(q.cpu().numpy(), rq), (N, qp)
-        assert np.array_equal(z.cpu().numpy().astype(np.uint64), rz), (N, qp)
-        assert np.array_equal(r.cpu().numpy().astype(np.uint64), rr), (N, qp)
-        got = d_recon.cpu().numpy()
-        got = got.view(orc.pix) if depth > 8 else got
-        assert np.array_equal(got, recon0), (N, qp)
+        # path 0: tcgen05 single kernel for N = 32 / 16, fused mma.sync pair for 8 / 4; path 2: the mma.sync pair for every size;
+        # path 1: the stage kernels (validation twin)
+        for path in (0, 2, 1):
+            ctx.set_dct_path(path)
+            d_recon = dev(pix_view(np.full(geo.plane_elems, 5, orc.pix), depth))
+            q.zero_(); ns.zero_(); z.zero_(); r.zero_()
+            ctx.tu_chain_batch(N, dev(pix_view(F, depth)), geo.stride, dev(pix_view(Pcur, depth)), geo.stride, dev(offF), dev(offP), dev(qc),
+                               qbits, add, scale, shift, q, ns, d_recon, geo.stride, dev(offF), z, r)
+            assert np.array_equal(ns.cpu().numpy().astype(np.uint32), rns), (N, qp, path)
+            assert np.array_equal(q.cpu().numpy(), rq), (N, qp, path)
+            assert np.array_equal(z.cpu().numpy().astype(np.uint64), rz), (N, qp, path)
+            assert np.array_equal(r.cpu().numpy().astype(np.uint64), rr), (N, qp, path)
+            got = d_recon.cpu().numpy()
+            got = got.view(orc.pix) if depth > 8 else got
+            assert np.array_equal(got, recon0), (N, qp, path)
+        ctx.set_dct_path(0)
         qm = rq.reshape(n, N * N)
         seen |= {"zero"} if (rns == 0).any() else set()
         seen |= {"dc"} if ((rns == 1) & (qm[:, 0] != 0)).any() else set()

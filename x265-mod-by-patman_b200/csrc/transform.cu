@@ -527,7 +527,7 @@ extern "C" int x265b200_dct_batch(x265b200_ctx* ctx, int kind, int N, const int1
     int d8 = ctx->depth - 8;
 #define FWD(NN, MODE, TN) fwd_kernel<NN, MODE><<<ceil_div(n, Tile<NN>::PER_CTA), TR_THREADS, 0, st>>>( \
         src, srcStride, off, n, dst, ilog2(TN) - 1 + d8, ilog2(TN) + 6, ctx->depth)
-    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path == 0 &&
+    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path != 1 &&
         launch_dct_imma(ctx, N, src, srcStride, off, n, dst, ilog2(N) - 1 + d8, ilog2(N) + 6, st, kind == X265B200_TR_DST))
     {
         // tensor-core path (transform_mma.cu)
@@ -565,7 +565,7 @@ extern "C" int x265b200_idct_batch(x265b200_ctx* ctx, int kind, int N, const int
     cudaStream_t st = (cudaStream_t)stream;
     int s2 = 12 - (ctx->depth - 8);
 #define INV(NN, MODE) inv_kernel<NN, MODE><<<ceil_div(n, Tile<NN>::PER_CTA), TR_THREADS, 0, st>>>(src, n, dst, dstStride, off, 7, s2)
-    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path == 0 &&
+    if ((kind == X265B200_TR_DCT || (kind == X265B200_TR_DST && N == 4)) && ctx->dct_path != 1 &&
         launch_idct_imma(ctx, N, src, n, dst, dstStride, off, 7, s2, st, kind == X265B200_TR_DST))
     {
         // tensor-core path (transform_mma.cu)

@@ -14,6 +14,7 @@
 // contraction index j is enumerated in the order the accumulator layout delivers it; that
 // permutation is folded into the constant A operand of stage 2 (table built on the host).
 #include <stdlib.h>
+#include <string.h>
 #include "internal.h"
 #include "device_util.cuh"
 
@@ -36,6 +37,7 @@ __device__ uint32_t c_IA8[2][32];            // block-diagonal: two 8x8 TUs
 __device__ uint32_t c_IB8[32];
 __device__ uint32_t c_IA4[2][2][32];         // [kind: 0 DCT, 1 DST][reg][lane]: eight 4x4 TUs
 __device__ uint32_t c_IB4[2][32];
+__device__ uint8_t c_ummaB[2][2][1024];      // tcgen05 B tiles (tu_umma.cuh)
 
 static const short h_cosmag[32] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
                                     64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4 };
@@ -191,6 +193,22 @@ int upload_mma_tables(x265b200_ctx* ctx)
             }
             ib4[kind][lane] = v;
         }
+    }
+    {   // tcgen05 B tiles (tu_umma.cuh): canonical K-major, no swizzle: byte (n, k) at (n / 8) * 256 + (k / 16) * 128 + (n % 8) * 16 + k % 16
+        static uint8_t ub[2][2][1024];
+        memset(ub, 0, sizeof(ub));
+        for (int s = 0; s < 2; s++)
+        {
+            const int N = s ? 16 : 32;
+            for (int nn = 0; nn < N; nn++)
+                for (int k = 0; k < N; k++)
+                {
+                    const int o = (nn >> 3) * 256 + (k >> 4) * 128 + (nn & 7) * 16 + (k & 15);
+                    ub[s][0][o] = (uint8_t)(int8_t)tcoef(N, nn, k);        // forward: B[n][k] = T[n][k]
+                    ub[s][1][o] = (uint8_t)(int8_t)tcoef(N, k, nn);        // inverse: B[n][k] = T[k][n]
+                }
+        }
+        B200_CUDA(ctx, cudaMemcpyToSymbol(c_ummaB, ub, sizeof(ub)));
     }
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA32, ia32, sizeof(ia32)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB32, ib32, sizeof(ib32)));
@@ -889,5 +907,6 @@ bool launch_dct_imma(x265b200_ctx* ctx, int N, const int16_t* src, intptr_t srcS
 }
 
 #include "tu_fused.cuh"
+#include "tu_umma.cuh"
 
 } // namespace b200

@@ -20,6 +20,10 @@ bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, co
                      int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
                      const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);   // tu_fused.cuh (transform_mma.cu)
 
+bool launch_tu_umma(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
+                    const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
+                    int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
+                    const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);    // tu_umma.cuh (transform_mma.cu)
 bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                        const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
                        int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st);                  // tu_fused.cuh
@@ -110,10 +114,16 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
         return fail(ctx, X265B200_ERR_ARG, "tu_chain: only sseZero may be NULL (offF, offP, offR and sseRecon are required)");
     cudaStream_t st = (cudaStream_t)stream;
     const int NN = N * N;
-    // Default: two fused tensor-core kernels over all TUs, no scratch (tu_fused.cuh).
+    // Default for N = 32 / 16: ONE kernel on the 5th-generation tensor cores, accumulators in tensor memory (tu_umma.cuh).
+    if (ctx->dct_path == 0 && (N == 32 || N == 16) &&
+        launch_tu_umma(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
+                       qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
+        return X265B200_OK;
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_chain tcgen05 launch");
+    // N = 8 / 4 (and path 2): two fused mma.sync kernels over all TUs, no scratch (tu_fused.cuh).
     // dct_path == 1 (validation twin): the six stage kernels of the batched primitives, walked in chunks whose two
     // int16 scratch planes stay L2-resident.
-    if (ctx->dct_path == 0 &&
+    if (ctx->dct_path != 1 &&
         launch_tu_fused(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
                         qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
         return X265B200_OK;
@@ -169,7 +179,7 @@ extern "C" int x265b200_tu_forward_batch(x265b200_ctx* ctx, int N, const void* f
     if (!fenc || !pred || !offF || !offP || !quantCoeff || !qCoef || !numSig)
         return fail(ctx, X265B200_ERR_ARG, "tu_forward: only sseZero may be NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->dct_path == 0 && launch_tu_forward(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, qCoef, numSig, sseZero, st))
+    if (ctx->dct_path != 1 && launch_tu_forward(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, qCoef, numSig, sseZero, st))
         return X265B200_OK;
     if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_forward fused launch");
     // validation twin / unaligned operands: the stage kernels over chunks whose scratch stays L2-resident
