@@ -90,9 +90,11 @@ int x265b200_sm_count(const x265b200_ctx* ctx);
 int x265b200_status(const x265b200_ctx* ctx);
 const char* x265b200_last_error(const x265b200_ctx* ctx);
 /* Implementation switch for the transforms and the TU chain: 0 (default) = tensor cores: warp-level mma.sync for the stand-alone DCT / IDCT
- * (csrc/transform_mma.cu) and the single tcgen05 / tensor-memory kernel for the N = 32 / 16 TU chain (csrc/tu_umma.cuh);
+ * (csrc/transform_mma.cu), the single tcgen05 / tensor-memory kernel for the 32x32 TU chain (csrc/tu_umma.cuh) and the two fused mma.sync
+ * kernels of csrc/tu_fused.cuh for the smaller TUs;
  * 1 = the CUDA-core partial-butterfly and stage kernels (csrc/transform.cu), kept as the validation twin;
- * 2 = mma.sync everywhere (the TU chain as the two fused kernels of csrc/tu_fused.cuh for every size). */
+ * 2 = mma.sync everywhere (the TU chain as the two fused kernels for every size);
+ * 3 = like 0 with the tcgen05 kernel for 16x16 TUs too. */
 int x265b200_set_dct_path(x265b200_ctx* ctx, int path);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t x265b200_launch_count(const x265b200_ctx* ctx);

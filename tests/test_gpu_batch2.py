@@ -233,9 +233,9 @@ def test_tu_chain_batch(depth):
         d_recon = dev(pix_view(np.full(geo.plane_elems, 5, orc.pix), depth))
         q = torch.zeros(n * N * N, dtype=torch.int16, device="cuda"); ns = torch.zeros(n, dtype=torch.int32, device="cuda")
         z = torch.zeros(n, dtype=torch.int64, device="cuda"); r = torch.zeros(n, dtype=torch.int64, device="cuda")
-        # path 0: tcgen05 single kernel for N = 32 / 16, fused mma.sync pair for 8 / 4; path 2: the mma.sync pair for every size;
-        # path 1: the stage kernels (validation twin)
-        for path in (0, 2, 1):
+        # path 0: tcgen05 single kernel for N = 32, fused mma.sync pair below; path 3: tcgen05 for 16 too; path 2: the mma.sync pair for every
+        # size; path 1: the stage kernels (validation twin)
+        for path in (0, 3, 2, 1):
             ctx.set_dct_path(path)
             d_recon = dev(pix_view(np.full(geo.plane_elems, 5, orc.pix), depth))
             q.zero_(); ns.zero_(); z.zero_(); r.zero_()

@@ -107,8 +107,8 @@ class Context:
             raise RuntimeError("x265b200 error %d: %s" % (st, self.lib.x265b200_last_error(self.h).decode()))
 
     def set_dct_path(self, path):
-        """0 = default (tcgen05 TU chain for N = 32 / 16, mma.sync transforms), 1 = CUDA-core butterfly / stage kernels (validation twin),
-        2 = mma.sync kernels everywhere (the TU chain's two-kernel form for every size)"""
+        """0 = default (tcgen05 TU chain for N = 32, mma.sync elsewhere), 1 = CUDA-core butterfly / stage kernels (validation twin),
+        2 = mma.sync kernels everywhere (the TU chain's two-kernel form for every size), 3 = tcgen05 TU chain for N = 16 as well"""
         r = self.lib.x265b200_set_dct_path(self.h, int(path))
         if r != 0:
             raise RuntimeError("x265b200_set_dct_path failed")

@@ -38,6 +38,7 @@ __device__ uint32_t c_IB8[32];
 __device__ uint32_t c_IA4[2][2][32];         // [kind: 0 DCT, 1 DST][reg][lane]: eight 4x4 TUs
 __device__ uint32_t c_IB4[2][32];
 __device__ uint8_t c_ummaB[2][2][1024];      // tcgen05 B tiles (tu_umma.cuh)
+__device__ uint8_t c_ummaAD[2][7168];        // tcgen05: the non-zero block of diag(T, T, ..) between two runs of zero row groups (tu_umma.cuh)
 
 static const short h_cosmag[32] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
                                     64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4 };
@@ -209,6 +210,20 @@ int upload_mma_tables(x265b200_ctx* ctx)
                 }
         }
         B200_CUDA(ctx, cudaMemcpyToSymbol(c_ummaB, ub, sizeof(ub)));
+        // forward stage 2: A = diag(T, T, ..) over the CTA's 128 rows, K = 128 in four steps of 32.  Tile ks (128 x 32, K-major canonical: byte
+        // (m, kk) at (m / 8) * 256 + (kk / 16) * 128 + (m % 8) * 16 + kk % 16) is non-zero only in rows 32 ks .. 32 ks + 31, and that 32 x 32 block
+        // is the same for every ks: [T] for N = 32, [[T16, 0], [0, T16]] for N = 16.  Stored once, 12 zero row groups before and after it.
+        static uint8_t ad[2][7168];
+        memset(ad, 0, sizeof(ad));
+        for (int s = 0; s < 2; s++)
+        {
+            const int N = s ? 16 : 32;
+            for (int m = 0; m < 32; m++)
+                for (int kk = 0; kk < 32; kk++)
+                    if (m / N == kk / N)
+                        ad[s][(12 + (m >> 3)) * 256 + (kk >> 4) * 128 + (m & 7) * 16 + (kk & 15)] = (uint8_t)(int8_t)tcoef(N, m % N, kk % N);
+        }
+        B200_CUDA(ctx, cudaMemcpyToSymbol(c_ummaAD, ad, sizeof(ad)));
     }
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_IA32, ia32, sizeof(ia32)));
     B200_CUDA(ctx, cudaMemcpyToSymbol(c_IB32, ib32, sizeof(ib32)));

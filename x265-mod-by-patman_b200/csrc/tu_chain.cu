@@ -114,13 +114,15 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
         return fail(ctx, X265B200_ERR_ARG, "tu_chain: only sseZero may be NULL (offF, offP, offR and sseRecon are required)");
     cudaStream_t st = (cudaStream_t)stream;
     const int NN = N * N;
-    // Default for N = 32 / 16: ONE kernel on the 5th-generation tensor cores, accumulators in tensor memory (tu_umma.cuh).
-    if (ctx->dct_path == 0 && (N == 32 || N == 16) &&
+    // ONE kernel on the 5th-generation tensor cores, accumulators in tensor memory (tu_umma.cuh): the default for N = 32, where it beats the
+    // two mma.sync kernels (0.50 vs 0.55 ms per 16 frames of 2160p10, and 1.0 x instead of 1.75 x the algorithmic DRAM traffic); at N = 16 it is
+    // 10 % slower than they are and only runs on request (path 3).
+    if (((ctx->dct_path == 0 && N == 32) || (ctx->dct_path == 3 && (N == 32 || N == 16))) &&
         launch_tu_umma(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
                        qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
         return X265B200_OK;
     if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_chain tcgen05 launch");
-    // N = 8 / 4 (and path 2): two fused mma.sync kernels over all TUs, no scratch (tu_fused.cuh).
+    // N = 16 / 8 / 4 (and path 2 for every size): two fused mma.sync kernels over all TUs, no scratch (tu_fused.cuh).
     // dct_path == 1 (validation twin): the six stage kernels of the batched primitives, walked in chunks whose two
     // int16 scratch planes stay L2-resident.
     if (ctx->dct_path != 1 &&
