@@ -474,11 +474,24 @@ def run_b200_arm(args):
     for kind, key, e0, e1 in diag:
         per.setdefault((kind, key), []).append(e0.elapsed_time(e1))
     peak, peak_src = peaks()
+    per_shape = None
     if fused:
-        # one fused launch = three shape passes.  Its compulsory DRAM bytes are those of ONE pass: every fenc sample once and every
-        # reference sample of the (overlapping, L2-resident) search windows once, plus five costs per CU
+        # continuity with the per-shape launches (x265b200_pixelcmp_batch, one PU shape each): three passes, an event pair per launch
+        acc = {s_: [] for s_ in SATD_SHAPES}
+        for _ in range(3):
+            for s_ in SATD_SHAPES:
+                a, b, _n = dev_desc[s_]
+                e0 = ev(); e0.record(stream)
+                ctx.pixelcmp_batch(pkg.OP_SATD, s_[0], s_[1], dF, geo.stride, dR, geo.stride, a, b, satd_out[s_], sh)
+                e1 = ev(); e1.record(stream); acc[s_].append((e0, e1))
+        torch.cuda.synchronize()
+        per_shape = {"%dx%d" % s_: sum(a.elapsed_time(b) for a, b in v) / len(v) for s_, v in acc.items()}
+    if fused:
+        # one fused launch = three shape passes over the same fenc CU: SURVEY 8(d)'s unit (fenc block + reference block, b bytes per sample
+        # each) becomes fenc once + three independently displaced reference blocks = 4 * b bytes per CU sample, plus five costs per CU.
+        # The measured DRAM traffic is lower than that: the three reference reads of a CU overlap and come out of L2.
         nblocks = sum(cu_desc[S][2] for S in CU_SIZES) * F / len(CU_SIZES)
-        satd_bytes = samples * 2 * 2 + nblocks * 5 * 4
+        satd_bytes = samples * 2 * 4 + nblocks * 5 * 4
     else:
         nblocks = sum(dev_desc[s][2] for s in SATD_SHAPES) * F / len(SATD_SHAPES)
         satd_bytes = samples * 2 * 2 + nblocks * 4                 # 2*b B per sample + 4 B per block
@@ -523,7 +536,12 @@ def run_b200_arm(args):
                           "satd_gpix_s": samples * (len(SATD_SHAPES) // satd_launches) / (satd_ms * 1e-3) / 1e9, "dct_gcoef_s": samples / (dct_ms * 1e-3) / 1e9,
                           "per_launch_ms_diagnostic_pass": {"%s_%s" % (k[0], "x".join(map(str, k[1])) if isinstance(k[1], tuple) else k[1]): sum(v) / len(v)
                                                               for k, v in per.items()},
-                          "timing": "phase events (SATD x12, DCT x4) inside the timed region; per-launch figures from a separate pass with an event pair per launch"}}
+                          "per_shape_launch_ms": per_shape,
+                          "per_shape_note": "the twelve single-shape launches (x265b200_pixelcmp_batch) timed after the run for comparison; algorithmic bytes of one such launch = 2 * b per sample" if per_shape else None,
+                          "algorithmic_bytes_note": ("fused launch: fenc once + three independently displaced reference blocks = 4 * b bytes per CU sample + 20 B per CU "
+                                                     "(three shape passes per launch); DRAM traffic is below it because the reference reads of a CU overlap in L2") if fused else
+                                                    "2 * b bytes per sample + 4 B per block (SURVEY 8d)",
+                          "timing": "phase events (SATD launches, DCT x4) inside the timed region; per-launch figures from a separate pass with an event pair per launch"}}
     line = {"metric": METRIC, "value": value, "unit": "GPixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": workload_config(F, note="per-GPU batch is fixed as N grows (frames shard across GPUs)"

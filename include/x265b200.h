@@ -330,6 +330,23 @@ int x265b200_bidir_satd_batch(x265b200_ctx* ctx, int w, int h, const void* fenc,
 int x265b200_lowres_intra_batch(x265b200_ctx* ctx, const void* plane, intptr_t stride, int widthInCU, int heightInCU, int penalty,
                                 int32_t* cost, int32_t* mode, x265b200_stream stream);
 
+/* Predictor selection of the lookahead (reference encoder/slicetype.cpp:4520-4558, inside CostEstimateGroup::estimateCUCost) for n 8x8 CUs: CU i has
+ * numc[i] (0..5) candidate vectors mvc[(5 * i + k) * 2 ..] in quarter pels (its already-searched neighbours' vectors); each is costed by the 8x8 SATD of
+ * the fenc block against ReferencePlanes::lowresMC of the vector (common/lowres.h:74-93: a half-pel plane of the lowres reference, or the rounded average
+ * of the two nearest ones; planes / planePitch as in x265b200_lowres_motion_estimate_batch, offR = the CU's co-located block).  mvp[2i..] = the cheapest
+ * (the first of equal costs), 0 when numc[i] == 0; mvpCost[i] = its cost (1 << 28 = MotionEstimate::COST_MAX when nothing was measured); skipCost[i] =
+ * the reference's skipCost (INT_MAX unless, in a B frame, a candidate was measured while the running predictor was the zero vector). */
+int x265b200_lowres_mvp_batch(x265b200_ctx* ctx, const void* fenc, intptr_t strideF, const int32_t* offF, const void* planes, intptr_t strideR,
+                              size_t planePitch, const int32_t* offR, const int32_t* mvc, const int32_t* numc, int bBidir, int n,
+                              int32_t* mvp, int32_t* mvpCost, int32_t* skipCost, x265b200_stream stream);
+
+/* The bi-directional candidates of a B-frame CU (reference encoder/slicetype.cpp:4577-4596): cost[2i] = 8x8 SATD of fenc against the rounded average of
+ * both lists' motion-compensated blocks (lowresMC at mv0[2i..] in reference 0 and mv1[2i..] in reference 1), cost[2i + 1] = against the average of the two
+ * co-located full-pel blocks.  The caller adds lowresPenalty and takes the minimum with the list costs (COPY2_IF_LT, listused = 3). */
+int x265b200_lowres_bidir_cost_batch(x265b200_ctx* ctx, const void* fenc, intptr_t strideF, const int32_t* offF,
+                                     const void* planes0, intptr_t stride0, size_t planePitch0, const void* planes1, intptr_t stride1, size_t planePitch1,
+                                     const int32_t* offR, const int32_t* mv0, const int32_t* mv1, int n, int32_t* cost, x265b200_stream stream);
+
 /* All 35 luma intra predictions of n TUs of N x N (4, 8, 16, 32) as the analysis forms them before costing the modes
  * (reference encoder/search.cpp:1703-1727 on common/intrapred.cpp): neighbours[i * (4N+1) ..] = top-left, 2N above, 2N left
  * (unfiltered; the 1:2:1 smoothed copy is made on chip), DC with edge smoothing for N <= 16, planar from the smoothed
@@ -490,6 +507,36 @@ int x265b200_frame_job_submit(x265b200_frame_job* job, x265b200_plane* fenc, x26
  * The pointers address pinned memory owned by the job and stay valid until the slot is submitted again. */
 int x265b200_frame_job_wait(x265b200_frame_job* job, int slot, x265b200_pass_result* results, int maxPasses);
 int x265b200_frame_job_pass_count(const x265b200_frame_job* job);
+
+/* The ThreadedME contract as one call (reference encoder/threadedme.h:112-130, threadedme.cpp:207-261 -> Analysis::deriveMVsForCTU ->
+ * Search::puMotionEstimation, encoder/search.cpp:226-404): n searches, each one PU against one reference picture, given as HOST records and returned
+ * as the per-reference part of MEData.  Records may mix all PU shapes, references and candidate counts; the call groups them, runs
+ * x265b200_motion_estimate_batch per group on resident planes and finishes every search with search.cpp:392-394's bookkeeping:
+ *   bits = pu.bits + bitcost(mv), mvCost = mvcost(mv), cost = (satdCost - mvCost) + ((bits * lambda + 128) >> 8).
+ * costTab / bitsTab: HOST pointers to the CENTRE elements of BitCost's tables for the slice QP (s_costs[qp] and s_bitsizes, encoder/bitcost.h), valid for
+ * indices -tabRadius .. tabRadius; lambda = RDCost::m_lambda (encoder/rdcost.h:91).  mvmin / mvmax in full pels as motionEstimate receives them after
+ * setSearchRange.  Choosing the best reference per list, checkBestMVP and the bi-prediction candidate stay with the caller. */
+#define X265B200_TME_MAX_CAND 8
+typedef struct x265b200_tme_pu {
+    int16_t w, h;                       /* PU size (g_puLookup, threadedme.h:67-92, or any multiple of 4 up to 64) */
+    int16_t ref;                        /* index into refPlanes */
+    int16_t numCand;                    /* neighbour vectors in mvc */
+    int32_t offF, offR;                 /* the PU in the fenc plane, its co-located block in the reference plane (element offsets) */
+    int32_t mvmin[2], mvmax[2];         /* search window, full pels */
+    int32_t mvp[2];                     /* predictor, quarter pels */
+    int32_t mvc[X265B200_TME_MAX_CAND][2];
+    uint32_t bits;                      /* list / reference / mvp-index bits charged before the vector's own (search.cpp:269-271) */
+} x265b200_tme_pu;
+typedef struct x265b200_tme_result {
+    int32_t mv[2];                      /* MEData::mv (quarter pels) */
+    uint32_t mvCost;                    /* MEData::mvCost */
+    uint32_t bits;                      /* MEData::bits contribution of this search */
+    uint32_t cost;                      /* MEData::cost candidate */
+    uint32_t satdCost;                  /* what motionEstimate returned */
+} x265b200_tme_result;
+int x265b200_tme_search_batch(x265b200_ctx* ctx, int searchMethod, int merange, int subpelRefine, const x265b200_plane* fencPlane,
+                              const x265b200_plane* const* refPlanes, int numRefs, const uint16_t* costTab, const float* bitsTab,
+                              int tabRadius, uint64_t lambda, const x265b200_tme_pu* pus, int n, x265b200_tme_result* results);
 
 /* ------------------------------------------------------------------ host (per-call, drop-in slots) */
 

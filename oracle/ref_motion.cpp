@@ -182,3 +182,72 @@ void ref_motion_estimate_batch(int method, int subme, int w, int h, pixel* fencP
     }
     for (auto& t : th) t.join();
 }
+
+/* the lookahead's predictor selection and bi-directional candidates (encoder/slicetype.cpp:4520-4558, 4577-4596) driven through the
+ * reference's own ReferencePlanes::lowresMC (common/lowres.h:74-93), MotionEstimate::bufSATD and the pixelavg_pp slot: the loop bodies are
+ * the reference's statements, only the surrounding Lowres / Lookahead objects are replaced by plain pointers */
+static void ref_planes(ReferencePlanes& r, pixel* planes, intptr_t stride, size_t pitch)
+{
+    for (int k = 0; k < 4; k++) r.lowresPlane[k] = planes + k * pitch;
+    r.fpelPlane[0] = r.lowresPlane[0];
+    r.lumaStride = stride;
+    r.isLowres = true;
+}
+extern "C" __attribute__((visibility("default")))
+void ref_lowres_mvp(pixel* fencPlane, intptr_t strideF, intptr_t offF, pixel* planes, intptr_t strideR, size_t pitch, intptr_t offR,
+                    const int32_t* mvcIn, int numc, int bBidir, int32_t* out)
+{
+    ref_ensure();
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setSourcePU(fencPlane, strideF, offF, 8, 8, X265_HEX_SEARCH, 1);
+    ReferencePlanes ref;
+    ref_planes(ref, planes, strideR, pitch);
+    ReferencePlanes* fref = &ref;
+    const intptr_t pelOffset = offR;
+    MV mvc[5], mvp;
+    for (int i = 0; i < numc; i++) mvc[i] = MV(mvcIn[2 * i], mvcIn[2 * i + 1]);
+    int skipCost = INT_MAX, mvpcost = MotionEstimate::COST_MAX;
+    if (!numc)
+        mvp = 0;
+    else
+    {
+        ALIGN_VAR_32(pixel, subpelbuf[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE]);
+        for (int idx = 0; idx < numc; idx++)
+        {
+            intptr_t stride = X265_LOWRES_CU_SIZE;
+            pixel *src = fref->lowresMC(pelOffset, mvc[idx], subpelbuf, stride, 0);
+            int cost = me.bufSATD(src, stride);
+            COPY2_IF_LT(mvpcost, cost, mvp, mvc[idx]);
+            if (!mvp.notZero() && bBidir)
+                skipCost = cost;
+        }
+    }
+    out[0] = mvp.x; out[1] = mvp.y; out[2] = mvpcost; out[3] = skipCost;
+}
+extern "C" __attribute__((visibility("default")))
+void ref_lowres_bidir(pixel* fencPlane, intptr_t strideF, intptr_t offF, pixel* planes0, intptr_t s0, size_t pitch0, pixel* planes1, intptr_t s1,
+                      size_t pitch1, intptr_t offR, const int32_t* mv0, const int32_t* mv1, int32_t* out)
+{
+    ref_ensure();
+    MotionEstimate me;
+    me.init(X265_CSP_I400);
+    me.setSourcePU(fencPlane, strideF, offF, 8, 8, X265_HEX_SEARCH, 1);
+    ReferencePlanes r0, r1;
+    ref_planes(r0, planes0, s0, pitch0);
+    ref_planes(r1, planes1, s1, pitch1);
+    ReferencePlanes *fref0 = &r0, *fref1 = &r1;
+    const intptr_t pelOffset = offR;
+    ALIGN_VAR_32(pixel, subpelbuf0[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE]);
+    ALIGN_VAR_32(pixel, subpelbuf1[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE]);
+    intptr_t stride0 = X265_LOWRES_CU_SIZE, stride1 = X265_LOWRES_CU_SIZE;
+    pixel *src0 = fref0->lowresMC(pelOffset, MV(mv0[0], mv0[1]), subpelbuf0, stride0, 0);
+    pixel *src1 = fref1->lowresMC(pelOffset, MV(mv1[0], mv1[1]), subpelbuf1, stride1, 0);
+    ALIGN_VAR_32(pixel, ref[X265_LOWRES_CU_SIZE * X265_LOWRES_CU_SIZE]);
+    primitives.pu[LUMA_8x8].pixelavg_pp[NONALIGNED](ref, X265_LOWRES_CU_SIZE, src0, stride0, src1, stride1, 32);
+    out[0] = me.bufSATD(ref, X265_LOWRES_CU_SIZE);
+    src0 = fref0->lowresPlane[0] + pelOffset;
+    src1 = fref1->lowresPlane[0] + pelOffset;
+    primitives.pu[LUMA_8x8].pixelavg_pp[NONALIGNED](ref, X265_LOWRES_CU_SIZE, src0, fref0->lumaStride, src1, fref1->lumaStride, 32);
+    out[1] = me.bufSATD(ref, X265_LOWRES_CU_SIZE);
+}

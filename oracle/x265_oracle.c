@@ -1853,3 +1853,56 @@ EXPORT int orc_motion_estimate_sea(int merange, int subme, int w, int h, const p
                  planes, costTab, qmvp };
     return me_estimate(c, 4, merange, subme, range, qmvp, numCand, mvc, costTab, outQMv);
 }
+
+/* ------------------------------------------------------------------ lookahead cost assembly (encoder/slicetype.cpp:4520-4620)
+ * lowresMC (common/lowres.h:74-93): the block a quarter-pel vector addresses in a lowres reference = the half-pel plane itself when the
+ * vector is half / full pel, else the rounded average of the two nearest planes.  planes = the four half-pel planes, `pitch` apart, each
+ * addressed at the CU's co-located block. */
+static void orc_lowres_mc(const pixel* planes, intptr_t stride, size_t pitch, int qx, int qy, pixel* out /* 8 x 8, stride 8 */)
+{
+    const pixel* a = planes + (size_t)((qy & 2) | ((qx & 2) >> 1)) * pitch + (qx >> 2) + (intptr_t)(qy >> 2) * stride;
+    if ((qx | qy) & 1)
+    {
+        const int bx = qx + (qx & 1), by = qy + (qy & 1);
+        const pixel* b = planes + (size_t)((by & 2) | ((bx & 2) >> 1)) * pitch + (bx >> 2) + (intptr_t)(by >> 2) * stride;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) out[y * 8 + x] = (pixel)((a[y * stride + x] + b[y * stride + x] + 1) >> 1);
+    }
+    else
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) out[y * 8 + x] = a[y * stride + x];
+}
+
+/* predictor selection (slicetype.cpp:4520-4558): every neighbour vector is costed by the 8x8 SATD of its motion-compensated block; the
+ * cheapest (first on ties, COPY2_IF_LT) becomes the predictor; while the running predictor is the zero vector and the frame is a B frame,
+ * skipCost follows the cost of the candidate just measured (the reference's own rule, kept as it is).  numc == 0: mvp = 0, nothing measured.
+ * out: mvp[2], mvpCost (COST_MAX = 1 << 28 when numc == 0), skipCost (INT_MAX when never set). */
+EXPORT void orc_lowres_mvp(const pixel* fenc, intptr_t sf, const pixel* planes, intptr_t sr, size_t pitch, const int32_t* mvc, int numc, int bBidir,
+                           int32_t* out /* mvpx, mvpy, mvpCost, skipCost */)
+{
+    int mvpx = 0, mvpy = 0, mvpcost = 1 << 28, skip = 0x7fffffff;
+    for (int i = 0; i < numc; i++)
+    {
+        pixel buf[64];
+        orc_lowres_mc(planes, sr, pitch, mvc[2 * i], mvc[2 * i + 1], buf);
+        int cost = orc_satd(8, 8, fenc, sf, buf, 8);
+        if (cost < mvpcost) { mvpcost = cost; mvpx = mvc[2 * i]; mvpy = mvc[2 * i + 1]; }
+        if (!(mvpx | mvpy) && bBidir) skip = cost;
+    }
+    out[0] = mvpx; out[1] = mvpy; out[2] = mvpcost; out[3] = skip;
+}
+
+/* bi-directional candidates of a B-frame CU (slicetype.cpp:4577-4596): SATD against the average of both lists' motion-compensated blocks,
+ * and against the average of the two co-located full-pel blocks.  out: bidir cost, co-located cost. */
+EXPORT void orc_lowres_bidir(const pixel* fenc, intptr_t sf, const pixel* planes0, intptr_t s0, size_t pitch0, const pixel* planes1, intptr_t s1,
+                             size_t pitch1, const int32_t* mv0, const int32_t* mv1, int32_t* out)
+{
+    pixel a[64], b[64], r[64];
+    orc_lowres_mc(planes0, s0, pitch0, mv0[0], mv0[1], a);
+    orc_lowres_mc(planes1, s1, pitch1, mv1[0], mv1[1], b);
+    for (int i = 0; i < 64; i++) r[i] = (pixel)((a[i] + b[i] + 1) >> 1);
+    out[0] = orc_satd(8, 8, fenc, sf, r, 8);
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) r[y * 8 + x] = (pixel)((planes0[y * s0 + x] + planes1[y * s1 + x] + 1) >> 1);
+    out[1] = orc_satd(8, 8, fenc, sf, r, 8);
+}

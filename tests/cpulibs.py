@@ -273,6 +273,20 @@ class _Base:
         return q, ns.value, z.value, r.value
 
     # ---- tables -----------------------------------------------------------------------
+    def lowres_mvp(self, fenc, of, sf, planes, orf, sr, pitch, mvc, bidir):
+        """oracle: predictor selection of the lookahead for one 8x8 CU -> (mvpx, mvpy, mvpCost, skipCost)"""
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        out = np.zeros(4, np.int32)
+        self._f("lowres_mvp", None)(_ptr(fenc, of), C.c_ssize_t(sf), _ptr(planes, orf), C.c_ssize_t(sr), C.c_size_t(pitch), _ptr(mvc), len(mvc) // 2, int(bidir), _ptr(out))
+        return out
+
+    def lowres_bidir(self, fenc, of, sf, planes0, o0, s0, pitch0, planes1, o1, s1, pitch1, mv0, mv1):
+        out = np.zeros(2, np.int32)
+        mv0 = np.ascontiguousarray(mv0, np.int32); mv1 = np.ascontiguousarray(mv1, np.int32)
+        self._f("lowres_bidir", None)(_ptr(fenc, of), C.c_ssize_t(sf), _ptr(planes0, o0), C.c_ssize_t(s0), C.c_size_t(pitch0), _ptr(planes1, o1), C.c_ssize_t(s1),
+                                     C.c_size_t(pitch1), _ptr(mv0), _ptr(mv1), _ptr(out))
+        return out
+
     def extend_pic_border(self, plane, origin, stride, width, height, marginX, marginY):
         """in place on `plane` (numpy, pixel dtype); origin = element offset of sample (0, 0)"""
         self._f("extend_pic_border", None)(_ptr(plane, origin), C.c_ssize_t(stride), width, height, marginX, marginY)
@@ -479,6 +493,20 @@ class Reference(_Base):
         out = np.zeros(n * N * N, np.int16)
         self._f("residual_dct_batch")(N, _ptr(A), C.c_ssize_t(sa), _ptr(B), C.c_ssize_t(sb),
                                       _ptr(offA), _ptr(offB), n, _ptr(out), nthreads)
+        return out
+
+    def lowres_mvp_ref(self, fenc, of, sf, planes, orf, sr, pitch, mvc, bidir):
+        mvc = np.ascontiguousarray(mvc, np.int32).reshape(-1)
+        out = np.zeros(4, np.int32)
+        self.lib.ref_lowres_mvp(_ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(planes), C.c_ssize_t(sr), C.c_size_t(pitch), C.c_ssize_t(orf),
+                                _ptr(mvc), len(mvc) // 2, int(bidir), _ptr(out))
+        return out
+
+    def lowres_bidir_ref(self, fenc, of, sf, planes0, s0, pitch0, planes1, s1, pitch1, orf, mv0, mv1):
+        out = np.zeros(2, np.int32)
+        mv0 = np.ascontiguousarray(mv0, np.int32); mv1 = np.ascontiguousarray(mv1, np.int32)
+        self.lib.ref_lowres_bidir(_ptr(fenc), C.c_ssize_t(sf), C.c_ssize_t(of), _ptr(planes0), C.c_ssize_t(s0), C.c_size_t(pitch0), _ptr(planes1), C.c_ssize_t(s1),
+                                  C.c_size_t(pitch1), C.c_ssize_t(orf), _ptr(mv0), _ptr(mv1), _ptr(out))
         return out
 
     def set_tier(self, tier):

@@ -901,3 +901,40 @@ def test_intra_host_slots(depth):
                     ctx.lib.x265b200_intra_pred_allangs(ctx.h, N, C.c_void_p(got33.ctypes.data), C.c_void_p(nb.ctypes.data), C.c_void_p(filt.ctypes.data), bLuma)
                     assert np.array_equal(got33, want), (N, bLuma)
     ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_lookahead_mvp_and_bidir_batches(depth):
+    """predictor selection and bi-directional candidates of the lookahead for every 8x8 CU of a lowres frame vs the oracle (pinned to the
+    reference's lowresMC / bufSATD / pixelavg_pp by the CPU suite)"""
+    import torch
+    from gpulib import context
+    from frames import Geometry
+    from test_oracle_vs_ref import lowres_planes
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    rng = np.random.default_rng(1300 + depth)
+    P0 = lowres_planes(geo, depth, 95); P1 = lowres_planes(geo, depth, 96)
+    pitch = geo.plane_elems
+    cw, ch = geo.coded()
+    xs, ys = np.meshgrid(np.arange(0, cw, 8), np.arange(0, ch, 8))
+    off = (geo.origin + ys.ravel() * geo.stride + xs.ravel()).astype(np.int32)
+    n = len(off)
+    F = P1[:pitch].copy()
+    numc = rng.integers(0, 6, n).astype(np.int32)
+    mvc = rng.integers(-40, 41, (n, 5, 2)).astype(np.int32)
+    mvc[::3, 0] = 0; mvc[1::5, 2] = 0
+    for bid in (0, 1):
+        mvp = torch.full((n, 2), -99, dtype=torch.int32, device="cuda"); mc = torch.zeros(n, dtype=torch.int32, device="cuda"); sk = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.lowres_mvp_batch(dev(pix_view(F, depth)), geo.stride, dev(off), dev(pix_view(P0, depth)), geo.stride, pitch, dev(off), dev(mvc.ravel()), dev(numc), bid, mvp, mc, sk)
+        want = np.array([orc.lowres_mvp(F, int(off[i]), geo.stride, P0, int(off[i]), geo.stride, pitch, mvc[i, :numc[i]], bid) for i in range(n)], np.int32)
+        assert np.array_equal(mvp.cpu().numpy(), want[:, :2]), bid
+        assert np.array_equal(mc.cpu().numpy(), want[:, 2]) and np.array_equal(sk.cpu().numpy(), want[:, 3]), bid
+    mv0 = rng.integers(-40, 41, (n, 2)).astype(np.int32); mv1 = rng.integers(-40, 41, (n, 2)).astype(np.int32)
+    mv0[::4] = 0; mv1[::6] &= ~1
+    cost = torch.zeros(2 * n, dtype=torch.int32, device="cuda")
+    ctx.lowres_bidir_cost_batch(dev(pix_view(F, depth)), geo.stride, dev(off), dev(pix_view(P0, depth)), geo.stride, pitch, dev(pix_view(P1, depth)), geo.stride, pitch,
+                                dev(off), dev(mv0.ravel()), dev(mv1.ravel()), cost)
+    want = np.array([orc.lowres_bidir(F, int(off[i]), geo.stride, P0, int(off[i]), geo.stride, pitch, P1, int(off[i]), geo.stride, pitch, mv0[i], mv1[i]) for i in range(n)], np.int32)
+    assert np.array_equal(cost.cpu().numpy().reshape(n, 2), want)
+    ctx.check()

@@ -174,3 +174,68 @@ def test_frame_job_c_example():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "frame job example ok" in out.stdout
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_tme_search_batch(depth):
+    """the ThreadedME-shaped entry: host PU records of mixed shapes, references and candidate counts in, MEData-style results out; every search
+    vs the oracle's motionEstimate and the bit / cost bookkeeping of search.cpp:392-394 redone in numpy"""
+    from gpulib import context, pkg
+    from frames import smooth_field
+    from test_oracle_vs_ref import mv_cost_table
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(416, 240)
+    rng = np.random.default_rng(1500 + depth)
+    S = smooth_field(geo, depth, 7)
+    F = S
+    refs_np = [np.clip(np.roll(S, dy * geo.stride + dx).astype(np.int64) + rng.integers(-2, 3, S.size), 0, orc.pmax).astype(S.dtype)
+               for (dx, dy) in ((3, -2), (-7, 5), (0, 0))]
+    pF = pkg.Plane(ctx, 416, 240); pF.upload_padded(F)
+    pR = []
+    for r in refs_np:
+        p = pkg.Plane(ctx, 416, 240); p.upload_padded(r); pR.append(p)
+    RAD = 2048
+    lam_tab = 11.3137
+    tab = mv_cost_table(lam_tab, RAD)
+    i = np.arange(RAD + 1, dtype=np.float32)
+    bits_half = np.log(i + np.float32(1)).astype(np.float32) * np.float32(2.0 / np.log(np.float32(2.0))) + np.float32(1.718)
+    bits_half[0] = np.float32(0.718)
+    bits_tab = np.concatenate([bits_half[:0:-1], bits_half]).astype(np.float32)
+    lam = int(np.floor(256.0 * lam_tab))
+    shapes = [(8, 4), (4, 8), (8, 8), (16, 4), (16, 12), (4, 16), (12, 16), (16, 8), (8, 16), (16, 16), (32, 8), (32, 24), (8, 32), (24, 32), (32, 16),
+              (16, 32), (32, 32), (64, 16), (64, 48), (16, 64), (48, 64), (64, 32), (32, 64), (64, 64)]          # g_puLookup, threadedme.h:67-92
+    cw, ch = geo.coded()
+    n = 160
+    for method, subme, merange in ((1, 2, 16), (2, 3, 24), (3, 1, 16), (0, 5, 12)):
+        pus = (pkg.TmePU * n)()
+        want = []
+        for k in range(n):
+            w, h = shapes[int(rng.integers(0, len(shapes)))]
+            x = int(rng.integers(0, cw - w + 1)); y = int(rng.integers(0, ch - h + 1))
+            off = geo.origin + y * geo.stride + x
+            m = int(rng.integers(4, 20))
+            rr = [-min(m, x + geo.margin_x - 8), -min(m, y + geo.margin_y - 8), min(m, cw + geo.margin_x - 8 - w - x), min(m, ch + geo.margin_y - 8 - h - y)]
+            nc = int(rng.integers(0, 4))
+            ref = int(rng.integers(0, 3))
+            mvp = rng.integers(-4 * m, 4 * m + 1, 2).astype(np.int32)
+            mvc = rng.integers(-4 * m, 4 * m + 1, (nc, 2)).astype(np.int32)
+            bits0 = int(rng.integers(1, 12))
+            p = pus[k]
+            p.w, p.h, p.ref, p.numCand, p.offF, p.offR, p.bits = w, h, ref, nc, off, off, bits0
+            p.mvmin[0], p.mvmin[1], p.mvmax[0], p.mvmax[1] = rr[0], rr[1], rr[2], rr[3]
+            p.mvp[0], p.mvp[1] = int(mvp[0]), int(mvp[1])
+            for c in range(nc):
+                p.mvc[c][0], p.mvc[c][1] = int(mvc[c][0]), int(mvc[c][1])
+            mx, my, satd = orc.motion_estimate_full(subme, w, h, F, off, geo.stride, refs_np[ref], off, geo.stride, np.array(rr, np.int32), mvp, mvc, tab, RAD, method, merange)
+            dx, dy = mx - int(mvp[0]), my - int(mvp[1])
+            mvcost = (int(tab[RAD + dx]) + int(tab[RAD + dy])) & 0xffff
+            bits = bits0 + int(np.float32(bits_tab[RAD + dx] + bits_tab[RAD + dy]) + np.float32(0.5))
+            cost = ((satd - mvcost) + ((bits * lam + 128) >> 8)) & 0xffffffff
+            want.append((mx, my, mvcost, bits, cost, satd))
+        res = ctx.tme_search_batch(method, merange, subme, pF, pR, tab, bits_tab, RAD, lam, pus)
+        got = [(r.mv[0], r.mv[1], r.mvCost, r.bits, r.cost, r.satdCost) for r in res]
+        assert got == want, (method, [i for i in range(n) if got[i] != want[i]][:5])
+    ctx.check()
+    pF.destroy()
+    for p in pR:
+        p.destroy()

@@ -885,3 +885,34 @@ def test_tu_forward_batch(libs):
             assert np.array_equal(ns, rns), (N, tier)
         r.set_tier(0)
         assert (rns > 0).any()
+
+
+def test_lookahead_mvp_and_bidir_costs(libs):
+    """predictor selection (slicetype.cpp:4520-4558) and the bi-directional candidates (:4577-4596) of the lookahead: the oracle vs the
+    reference's own lowresMC / bufSATD / pixelavg_pp driven with the reference's loop bodies"""
+    o, r = libs
+    from frames import Geometry
+    geo = Geometry(192, 128)
+    rng = np.random.default_rng(311)
+    P0 = lowres_planes(geo, o.depth, 95); P1 = lowres_planes(geo, o.depth, 96)
+    pitch = geo.plane_elems
+    cw, ch = geo.coded()
+    zero_pred = skip_set = 0
+    for case in range(300):
+        x = int(rng.integers(0, cw // 8)) * 8; y = int(rng.integers(0, ch // 8)) * 8
+        of = geo.origin + y * geo.stride + x
+        F = P0[(case % 4) * pitch:(case % 4 + 1) * pitch] if case % 3 == 0 else P1[:pitch]
+        numc = int(rng.integers(0, 6))
+        mvc = rng.integers(-40, 41, (numc, 2)).astype(np.int32)
+        if numc and case % 4 == 0: mvc[int(rng.integers(0, numc))] = 0
+        if numc and case % 7 == 0: mvc[0] = 0
+        bid = case & 1
+        a = o.lowres_mvp(F, of, geo.stride, P0, of, geo.stride, pitch, mvc, bid)
+        b = r.lowres_mvp_ref(F, of, geo.stride, P0, of, geo.stride, pitch, mvc, bid)
+        assert np.array_equal(a, b), (case, a, b)
+        zero_pred += int(numc > 0 and a[0] == 0 and a[1] == 0); skip_set += int(a[3] != 0x7fffffff)
+        mv0 = rng.integers(-40, 41, 2).astype(np.int32); mv1 = rng.integers(-40, 41, 2).astype(np.int32)
+        a = o.lowres_bidir(F, of, geo.stride, P0, of, geo.stride, pitch, P1, of, geo.stride, pitch, mv0, mv1)
+        b = r.lowres_bidir_ref(F, of, geo.stride, P0, geo.stride, pitch, P1, geo.stride, pitch, of, mv0, mv1)
+        assert np.array_equal(a, b), (case, a, b)
+    assert zero_pred > 5 and skip_set > 5

@@ -60,7 +60,7 @@ def workload(F, fused=False):
     samples = F * geo.coded()[0] * geo.coded()[1]
     if fused:
         nblocks = sum(len(c[1]) for c in cus) / len(cus)
-        print(json.dumps({"algorithmic_bytes_per_launch": samples * 4 + nblocks * 20}))
+        print(json.dumps({"algorithmic_bytes_per_launch": samples * 8 + nblocks * 20}))
     else:
         nblocks = sum(len(o[2]) for o in outs) / len(outs)
         print(json.dumps({"algorithmic_bytes_per_launch": samples * 4 + nblocks * 4}))

@@ -131,6 +131,15 @@ class Context:
     def host_free(self, p):
         self.lib.x265b200_host_free(self.h, p)
 
+    def tme_search_batch(self, method, merange, subme, fenc_plane, ref_planes, cost_tab, bits_tab, radius, lam, pus):
+        """pus: ctypes array of TmePU; cost_tab (uint16) / bits_tab (float32): numpy arrays of 2 * radius + 1 entries; returns a TmeResult array"""
+        n = len(pus)
+        res = (TmeResult * n)()
+        refs = (C.c_void_p * len(ref_planes))(*[p.h for p in ref_planes])
+        self._call("x265b200_tme_search_batch", int(method), int(merange), int(subme), fenc_plane.h, refs, len(ref_planes),
+                   C.c_void_p(cost_tab.ctypes.data + 2 * radius), C.c_void_p(bits_tab.ctypes.data + 4 * radius), int(radius), C.c_uint64(int(lam)), pus, n, res)
+        return res
+
     def tu_forward_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, qCoef, numSig, sseZero=None, stream=0):
         self._call("x265b200_tu_forward_batch", N, _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
                    _dp(qc), qbits, add, _dp(qCoef), _dp(numSig), _dp(sseZero), C.c_void_p(stream))
@@ -235,6 +244,14 @@ class Context:
     def weight_cost_batch(self, fenc, ref, stride, width, height, intra, weights, K, cost, stream=0):
         self._call("x265b200_weight_cost_batch", _dp(fenc), _dp(ref), _ss(stride), width, height, _dp(intra), _dp(weights), int(K), _dp(cost), C.c_void_p(stream))
 
+    def lowres_mvp_batch(self, fenc, sf, offF, planes, sr, pitch, offR, mvc, numc, bidir, mvp, mvp_cost, skip_cost, stream=0):
+        self._call("x265b200_lowres_mvp_batch", _dp(fenc), _ss(sf), _dp(offF), _dp(planes), _ss(sr), C.c_size_t(int(pitch)), _dp(offR), _dp(mvc), _dp(numc),
+                   int(bidir), int(offF.numel()), _dp(mvp), _dp(mvp_cost), _dp(skip_cost), C.c_void_p(stream))
+
+    def lowres_bidir_cost_batch(self, fenc, sf, offF, planes0, s0, pitch0, planes1, s1, pitch1, offR, mv0, mv1, cost, stream=0):
+        self._call("x265b200_lowres_bidir_cost_batch", _dp(fenc), _ss(sf), _dp(offF), _dp(planes0), _ss(s0), C.c_size_t(int(pitch0)), _dp(planes1), _ss(s1),
+                   C.c_size_t(int(pitch1)), _dp(offR), _dp(mv0), _dp(mv1), int(offF.numel()), _dp(cost), C.c_void_p(stream))
+
     def me_integral_batch(self, pix, stride, rows, nframes, sums, plane_pitch, stream=0):
         self._call("x265b200_me_integral_batch", _dp(pix), _ss(stride), int(rows), int(nframes), _dp(sums), C.c_size_t(int(plane_pitch)), C.c_void_p(stream))
 
@@ -293,6 +310,20 @@ class PassResult(C.Structure):
     _fields_ = [("kind", C.c_int), ("n", C.c_int), ("cost", C.POINTER(C.c_int32)), ("coef", C.POINTER(C.c_int16)),
                 ("numSig", C.POINTER(C.c_uint16)), ("sigMap", C.POINTER(C.c_uint32)), ("levels", C.POINTER(C.c_int16)),
                 ("nlevels", C.c_uint32)]
+
+
+TME_MAX_CAND = 8
+
+
+class TmePU(C.Structure):
+    """x265b200_tme_pu"""
+    _fields_ = [("w", C.c_int16), ("h", C.c_int16), ("ref", C.c_int16), ("numCand", C.c_int16), ("offF", C.c_int32), ("offR", C.c_int32),
+                ("mvmin", C.c_int32 * 2), ("mvmax", C.c_int32 * 2), ("mvp", C.c_int32 * 2), ("mvc", (C.c_int32 * 2) * TME_MAX_CAND), ("bits", C.c_uint32)]
+
+
+class TmeResult(C.Structure):
+    """x265b200_tme_result"""
+    _fields_ = [("mv", C.c_int32 * 2), ("mvCost", C.c_uint32), ("bits", C.c_uint32), ("cost", C.c_uint32), ("satdCost", C.c_uint32)]
 
 
 class Plane:
