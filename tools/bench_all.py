@@ -127,9 +127,37 @@ def main():
         qbits = 14 + 4 + tshift                                  # qp 28
         qo = torch.empty(S, dtype=torch.int16, device="cuda"); ns = torch.empty(n, dtype=torch.int32, device="cuda")
         z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
-        ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
-                                               qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
-        add("tu_chain %dx%d (two fused tensor-core kernels)" % (N, N), ms, S * (3 * b + 2) + n * 20, S)
+        for path, label in ((0, "default: tcgen05 single kernel" if N == 32 else "default: two fused mma.sync kernels"), (2, "two fused mma.sync kernels"),
+                            (3, "tcgen05 single kernel")):
+            if (path == 2 and N != 32) or (path == 3 and N != 16):
+                continue
+            ctx.set_dct_path(path)
+            ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,
+                                                   qo, ns, recon, geo.stride, oa, z, r), reps=5, warm=2)
+            add("tu_chain %dx%d (%s)" % (N, N, label), ms, S * (3 * b + 2) + n * 20, S)
+        ctx.set_dct_path(0)
+    # ---- all rectangular PUs of a CU in one pass (fenc once + three independently displaced reference blocks = 4b bytes per CU sample)
+    from frames import cu_descriptors
+    for Scu in (64, 32, 16, 8):
+        oF, oR5, _ = cu_descriptors(geo, Scu, *[tile_blocks(geo, w, h, seed=1) for (w, h) in ((Scu, Scu), (Scu, Scu // 2), (Scu // 2, Scu))])
+        a_ = torch.from_numpy(np.concatenate([oF.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)).cuda()
+        b_ = torch.from_numpy(np.concatenate([oR5.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)).cuda()
+        o_ = torch.empty(5 * a_.numel(), dtype=torch.int32, device="cuda")
+        ms = timeit(lambda: ctx.cu_satd_batch(Scu, A, geo.stride, B, geo.stride, a_, b_, o_))
+        add("cu_satd %dx%d CU (2Nx2N + 2NxN + Nx2N PUs, five vectors; per shape-pass sample)" % (Scu, Scu), ms, S * 4 * b + a_.numel() * 20, 3 * S)
+    # ---- intra: all 35 predictions of N x N TUs from their neighbour arrays (output-bound: 35 b bytes per sample), and the lookahead's intra estimate
+    for N in (32, 8):
+        nt = min(S // (N * N), 40000)
+        nb_ = torch.randint(0, 1 << D, (nt * (4 * N + 1),), dtype=torch.int32, device="cuda").to(A.dtype)
+        dstI = torch.empty(nt * 35 * N * N, dtype=A.dtype, device="cuda")
+        ms = timeit(lambda: ctx.intra_pred_batch(N, nb_, nt, dstI))
+        add("intra_pred_all %dx%d (35 modes per TU; 35 b bytes written per sample)" % (N, N), ms, nt * N * N * 35 * b, nt * N * N * 35)
+        del dstI
+    lw_, lh_ = cw // 2, ch // 2                    # a lowres frame lives in the corner of a full-size plane here: only the geometry matters
+    ci = torch.empty((lw_ // 8) * (lh_ // 8), dtype=torch.int32, device="cuda"); mi = torch.empty_like(ci)
+    base = geo.origin
+    ms = timeit(lambda: ctx.lowres_intra_batch(A, base, geo.stride, lw_ // 8, lh_ // 8, 12, ci, mi))
+    add("lowres_intra (35 modes x 8x8 SATD per CU, one 1080p-lowres frame; per CU sample)", ms, lw_ * lh_ * b, lw_ * lh_)
     # ---- sub-pel candidate cost (interpolation fused with SATD): K = 4 quarter-pel candidates per block
     for (w, h) in ((64, 64), (16, 16), (8, 8)):
         oa, ob = desc(w, h)
@@ -193,7 +221,7 @@ def main():
             ms = timeit(lambda: ctx.interp_batch("hvpp", 8, w, h, A, geo.stride, oa, dstP, geo.stride, oa, idxhv))
             add("hvpp %s" % tag, ms, S * 2 * b, S)
     ctx.check()
-    print("| primitive (2160p%d x %d frames per launch) | ms | GB/s (algorithmic) | of measured HBM %.0f GB/s | G samples/s |" % (D, F, peak))
+    print("| primitive (2160p%d x %d frames per launch) | ms | GB/s (algorithmic) | of %s HBM %.0f GB/s | G samples/s |" % (D, F, "measured (MEASURED_PEAKS.json)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "FALLBACK (B200_PROFILING.md)", peak))
     print("|---|---|---|---|---|")
     for r in rows:
         print("| %s | %.4f | %.0f | %.2f | %.0f |" % (r["primitive"], r["ms"], r["GBps"], r["frac_of_measured_hbm"], r["Gunits_per_s"]))
