@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -63,5 +64,18 @@ int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSucc
     } while (0)
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// tuning lab only: X265B200_LAB="k0,k1,..." selects kernel variants under test (tools/bench_all.py sweeps); unset = library defaults
+inline int lab_knob(int i, int dflt)
+{
+    static int vals[16];
+    static int count = [] {
+        int c = 0;
+        if (const char* e = getenv("X265B200_LAB"))
+            while (*e && c < 16) { vals[c++] = atoi(e); while (*e && *e != ',') e++; if (*e == ',') e++; }
+        return c;
+    }();
+    return i < count ? vals[i] : dflt;
+}
 
 } // namespace b200

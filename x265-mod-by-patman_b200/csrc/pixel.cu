@@ -216,8 +216,8 @@ sa8d_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intpt
 // (|value| <= 8 * 4095 < 2^15).  PKH (depth <= 10): the two horizontal stages that pair different words (distance 4
 // and 2) stay packed as well (8 * 1023 * 4 < 2^15), and the last stage, which pairs the two lanes of a word, is folded
 // into the sum of magnitudes: |a + b| + |a - b| = 2 max(|a|, |b|).  Otherwise the horizontal pass runs in int32.
-template<typename T, bool PKH>
-__global__ void __launch_bounds__(128)
+template<typename T, bool PKH, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB)
 sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
                  int n, int w, int h, int G, int mode16, int32_t* __restrict__ out)
@@ -471,7 +471,17 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
         long long threads = (long long)n * G;
         if (!((sa | sb) & 3))
         {
-            if (ctx->depth <= 10)
+            if (int tpl = lab_knob(2, 0))                 // lab: 8x8 tiles per lane
+            {
+                int tiles = (w >> 3) * (h >> 3);
+                G = 1;
+                while (G * 2 * tpl <= tiles && G < 32) G <<= 1;
+                if (mode16 && G < 4) G = tiles < 4 ? tiles : 4;
+                threads = (long long)n * G;
+            }
+            if (ctx->depth <= 10 && lab_knob(1, 0) == 1)
+                sa8d_fast_kernel<T, true, 8><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
+            else if (ctx->depth <= 10)
                 sa8d_fast_kernel<T, true><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
             else
                 sa8d_fast_kernel<T, false><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
