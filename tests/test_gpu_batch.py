@@ -305,4 +305,20 @@ def test_cu_satd_batch_equals_per_shape_costs(depth, torch_mod):
         out2 = torch.full((5 * m,), -1, dtype=torch.int32, device="cuda")
         ctx.cu_satd_batch(S, dA, geo.stride, dB, geo.stride, dev(offF[:m].copy()), dev(offR5[:5 * m].copy()), out2)
         assert np.array_equal(out2.cpu().numpy(), got[:m].ravel())
+    # extreme pictures (TestBench cases 1 and 2: all-max against all-min, and the reverse) and a checkerboard of the two: the largest
+    # differences and transform sums a legal picture can produce (the 32 / 64 wide CUs run the f16 tensor-core Hadamard at depth <= 10)
+    hi = np.full(geo.plane_elems, orc.pmax, orc.pix); lo = np.zeros(geo.plane_elems, orc.pix)
+    chk = np.where((np.arange(geo.plane_elems) % geo.stride + np.arange(geo.plane_elems) // geo.stride) & 1, orc.pmax, 0).astype(orc.pix)
+    for P, Q in ((hi, lo), (lo, hi), (chk, lo), (hi, chk), (chk, B)):
+        dP, dQ = dev(P.view(vt)), dev(Q.view(vt))
+        for S in (16, 32, 64):
+            shapes = [(S, S), (S, S // 2), (S // 2, S)]
+            d = [tile_blocks(geo, w, h, seed=40 + S) for (w, h) in shapes]
+            offF, offR5, idx = cu_descriptors(geo, S, *d)
+            out = torch.full((5 * len(offF),), -1, dtype=torch.int32, device="cuda")
+            ctx.cu_satd_batch(S, dP, geo.stride, dQ, geo.stride, dev(offF), dev(offR5), out)
+            got = out.cpu().numpy().reshape(-1, 5)
+            want = [orc.pixelcmp_batch(OP_SATD, w, h, P, geo.stride, Q, geo.stride, oa, ob) for (w, h), (oa, ob) in zip(shapes, d)]
+            for k in range(5):
+                assert np.array_equal(got[:, k], want[0 if k == 0 else 1 if k < 3 else 2][idx[k]]), (depth, S, k, "extreme")
     ctx.check()

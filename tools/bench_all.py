@@ -139,8 +139,8 @@ def main():
             qo = torch.empty(S, dtype=torch.int16, device="cuda"); ns = torch.empty(n, dtype=torch.int32, device="cuda")
             z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
             for path, label in ((0, "default: tcgen05 single kernel" if N == 32 else "default: two fused mma.sync kernels"), (2, "two fused mma.sync kernels"),
-                                (3, "tcgen05 single kernel"), (4, "tcgen05 single kernel, two threads per row")):
-                if (path in (2, 4) and N != 32) or (path == 3 and N != 16):
+                                (3, "tcgen05 single kernel")):
+                if (path == 2 and N != 32) or (path == 3 and N != 16):
                     continue
                 ctx.set_dct_path(path)
                 ms = timeit(lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, oa, ob, qcN, qbits, 85 << (qbits - 9), 64 << 4, 6 - tshift,

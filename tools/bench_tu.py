@@ -29,8 +29,8 @@ for N in (32, 16, 8, 4):
     qc = torch.full((N * N,), 26214, dtype=torch.int32, device="cuda")
     q = torch.empty(S, dtype=torch.int16, device="cuda"); ns = torch.empty(n, dtype=torch.int32, device="cuda")
     z = torch.empty(n, dtype=torch.int64, device="cuda"); r = torch.empty(n, dtype=torch.int64, device="cuda")
-    for path in (3, 4, 2):
-        if (path == 3 and N < 16) or (path == 4 and N != 32):
+    for path in (3, 2):
+        if path == 3 and N < 16:
             continue
         ctx.set_dct_path(path)
         run = lambda: ctx.tu_chain_batch(N, A, geo.stride, B, geo.stride, a, bb, qc, qbits, 171 << (qbits - 9), 40 << 5, max(1, 6 - tshift), q, ns, recon, geo.stride, a, z, r)
@@ -44,7 +44,7 @@ for N in (32, 16, 8, 4):
         ms = e0.elapsed_time(e1) / 5
         gbs = S * (3 * b + 2) / (ms * 1e-3) / 1e9
         rows.append((N, path, ms, gbs, gbs / peak, int(ns.sum())))
-        print("tu_chain %2dx%-2d %-28s %.4f ms  %.0f GB/s  %.2f of HBM (%.0f GB/s)  numSig total %d" % (N, N, "tcgen05 single kernel" if path == 3 else "tcgen05, two threads per row" if path == 4 else "mma.sync two kernels",
+        print("tu_chain %2dx%-2d %-28s %.4f ms  %.0f GB/s  %.2f of HBM (%.0f GB/s)  numSig total %d" % (N, N, "tcgen05 single kernel" if path == 3 else "mma.sync two kernels",
               ms, gbs, gbs / peak, peak, int(ns.sum())))
 ctx.set_dct_path(0)
 ctx.check()

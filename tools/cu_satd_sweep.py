@@ -30,5 +30,5 @@ for S, Gs in ((8, (1, 2, 4)), (16, (2, 4, 8, 16)), (32, (4, 8, 16, 32)), (64, (8
         e1.record(); torch.cuda.synchronize()
         chk = int(out.to(torch.int64).sum())
         base = chk if base is None else base
-        print("S=%d G=%d  %.4f ms  %s" % (S, G, e0.elapsed_time(e1) / 6, "ok" if chk == base else "MISMATCH"))
+        print("S=%d G=%d  %.4f ms  %s  sum %d" % (S, G, e0.elapsed_time(e1) / 6, "ok" if chk == base else "MISMATCH", chk))
 ctx.check()

@@ -197,7 +197,7 @@ extern "C" void x265b200_close(x265b200_ctx* ctx)
 
 extern "C" int x265b200_set_dct_path(x265b200_ctx* ctx, int path)
 {
-    if (!ctx || path < 0 || path > 4) return X265B200_ERR_ARG;
+    if (!ctx || path < 0 || path > 3) return X265B200_ERR_ARG;
     ctx->dct_path = path;
     return X265B200_OK;
 }

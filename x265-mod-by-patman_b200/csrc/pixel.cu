@@ -471,15 +471,16 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
         long long threads = (long long)n * G;
         if (!((sa | sb) & 3))
         {
-            if (int tpl = lab_knob(2, 0))                 // lab: 8x8 tiles per lane
-            {
-                int tiles = (w >> 3) * (h >> 3);
-                G = 1;
-                while (G * 2 * tpl <= tiles && G < 32) G <<= 1;
-                if (mode16 && G < 4) G = tiles < 4 ? tiles : 4;
-                threads = (long long)n * G;
-            }
-            if (ctx->depth <= 10 && lab_knob(1, 0) == 1)
+            // lanes per block and register cap, swept on B200 (profiles/r3_all_primitives_10bit.md): four 8x8 tiles per lane for 64x64 (0.2016 ->
+            // 0.1910 ms per 32 frames of 2160p10), two for 32x32 with the kernel capped at 64 registers = 8 CTAs per SM (0.2463 -> 0.2111 ms);
+            // the smaller CUs keep one tile per lane and gain from the cap alone (16x16 0.2657 -> 0.2439, 8x8 0.2934 -> 0.2702 ms)
+            const int tiles = (w >> 3) * (h >> 3);
+            const int tpl = tiles >= 64 ? 4 : tiles >= 16 ? 2 : 1;
+            G = 1;
+            while (G * 2 * tpl <= tiles && G < 32) G <<= 1;
+            if (mode16 && G < 4) G = 4;
+            threads = (long long)n * G;
+            if (ctx->depth <= 10 && tiles < 64)
                 sa8d_fast_kernel<T, true, 8><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
             else if (ctx->depth <= 10)
                 sa8d_fast_kernel<T, true><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
@@ -582,6 +583,18 @@ static int launch_cu_satd(x265b200_ctx* ctx, int S, const T* A, intptr_t sa, con
         int g[4] = { 2, 4, 8, 32 };
         sscanf(e, "%d,%d,%d,%d", &g[0], &g[1], &g[2], &g[3]);
         G = g[S == 8 ? 0 : S == 16 ? 1 : S == 32 ? 2 : 3];
+    }
+    // 32 and 64 wide CUs of 16-bit pictures up to 10 bits: the horizontal Hadamard as f16 tensor-core MMAs (tile_kernels.cuh cu_satd_mma_kernel),
+    // bit-identical: 0.3715 -> 0.3446 ms (64 wide, 16 lanes per CU) and 0.3869 -> 0.3753 ms (32 wide) per 32 frames of 2160p10; at 16 and 8 wide the
+    // L1 data pipe (89 / 91 % busy), not the ALU, is the limit and the packed-integer kernel stays ahead.  X265B200_LAB="0,0,0,0,1" turns it off.
+    if (sizeof(T) == 2 && ctx->depth <= 10 && S >= 32 && G >= 4 && !lab_knob(4, 0))
+    {
+        if (!getenv("X265B200_CU_LANES_LAB")) G = S == 32 ? 8 : 16;
+        const int gridM = ceil_div((long long)n * G, 128);
+        if (S == 32) cu_satd_mma_kernel<32><<<gridM, 128, 0, st>>>((const uint16_t*)A, sa, (const uint16_t*)B, sb, offF, offR, n, G, out);
+        else cu_satd_mma_kernel<64><<<gridM, 128, 0, st>>>((const uint16_t*)A, sa, (const uint16_t*)B, sb, offF, offR, n, G, out);
+        B200_LAUNCH_CHECK(ctx);
+        return X265B200_OK;
     }
     const int grid = ceil_div((long long)n * G, 128);
     switch (S)

@@ -601,16 +601,7 @@ int launch_quant(x265b200_ctx* ctx, int mode, const int16_t* coef, const int32_t
         constexpr int NB = 4;
         long long threads = (long long)ceil_div(n, NB) * per;
         int grid = ceil_div(threads, 256);
-        const int nqv = mode == 1 ? lab_knob(0, 0) : 0;
-        if (nqv == 1)
-            quant_multi_kernel<true, false, 8><<<ceil_div((long long)ceil_div(n, 8) * per, 256), 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
-        else if (nqv == 2)
-            quant_multi_kernel<true, false, 8><<<ceil_div((long long)ceil_div(n, 8) * per, 128), 128, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
-        else if (nqv == 3)
-            quant_multi_kernel<true, false, 4><<<ceil_div(threads, 128), 128, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
-        else if (nqv == 4)
-            quant_multi_kernel<true, false, 2><<<ceil_div((long long)ceil_div(n, 2) * per, 256), 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);
-        else if (mode == 0)
+        if (mode == 0)
             quant_multi_kernel<false, true, NB><<<grid, 256, 0, st>>>(coef, quantCoeff, deltaU, qCoef, qBits, add, numCoeff, n, numSig);
         else if (mode == 1)
             quant_multi_kernel<true, false, NB><<<grid, 256, 0, st>>>(coef, quantCoeff, nullptr, qCoef, qBits, add, numCoeff, n, numSig);

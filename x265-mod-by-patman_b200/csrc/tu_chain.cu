@@ -117,7 +117,7 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
     // ONE kernel on the 5th-generation tensor cores, accumulators in tensor memory (tu_umma.cuh): the default for N = 32, where it beats the
     // two mma.sync kernels (0.50 vs 0.55 ms per 16 frames of 2160p10, and 1.0 x instead of 1.75 x the algorithmic DRAM traffic); at N = 16 it is
     // 10 % slower than they are and only runs on request (path 3).
-    if (((ctx->dct_path == 0 && N == 32) || (ctx->dct_path == 3 && (N == 32 || N == 16)) || (ctx->dct_path == 4 && N == 32)) &&
+    if (((ctx->dct_path == 0 && N == 32) || (ctx->dct_path == 3 && (N == 32 || N == 16))) &&
         launch_tu_umma(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
                        qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
         return X265B200_OK;

@@ -495,376 +495,6 @@ tu_umma_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(COLS));
 }
 
-// ---- N = 32 with TWO threads per row (256 threads per CTA) ------------------------------------------------------------------------
-// The row-per-thread kernel above holds a whole 32-coefficient row of the accumulator in registers (115-128 registers, 4 CTAs = 16 warps
-// per SM; ncu: issue slots 41 % busy, long-scoreboard the top stall, the warps of a CTA idle together while its MMAs run).  Here warp
-// w and warp w + 4 share the 32 rows of one TU: thread (row, hf) owns columns 16 hf .. 16 hf + 15 of the row through every stage -- the
-// same shared-memory operand layouts (a thread writes ONE 16-element chunk of each byte plane instead of two), the same MMAs, tcgen05.ld
-// of its 16 columns.  Per-thread state halves (<= 64 registers), so 4 CTAs are 32 warps per SM, and a stage's epilogue is spread over twice
-// the warps.  The per-TU scalars (numSig, the DC level, both SSE sums) meet through shared memory: the stage barriers order the mid-chain
-// ones, a 64-thread named barrier per TU the final sums.
-namespace umma {
-__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-}
-} // namespace umma
-
-// one stage of the split kernel: like umma_stage<32, LO>, every thread receiving columns col0 .. col0 + 15 of its row
-template<int LO>
-__device__ __forceinline__ void umma_stage_half(int mode, uint32_t dHi, uint32_t dLo, uint32_t cAddr, uint32_t tmem, uint32_t bar, uint32_t& phase,
-                                                int col0, int (&v)[16])
-{
-    constexpr int N = 32;
-    __syncwarp();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x < 32)
-    {
-        if (threadIdx.x == 0)
-        {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (mode != 2)
-            {
-                const uint32_t lbo = mode ? 1024 : 128, sbo = mode ? 128 : 256;
-                const uint64_t db = mode ? umma::make_desc(cAddr, 256, 128) : umma::make_desc(cAddr, 128, 256);
-                umma::mma_i8(tmem, umma::make_desc(dHi, lbo, sbo), db, umma::make_idesc(N, 1, 1, mode, mode), 0);
-                umma::mma_i8(tmem + LO, umma::make_desc(dLo, lbo, sbo), db, umma::make_idesc(N, 0, 1, mode, mode), 0);
-            }
-            else
-            {
-                constexpr uint32_t lbo = (N / 16) * 128;
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++)
-                {
-                    const uint64_t da = umma::make_desc(cAddr + (12 - 4 * ks) * 256, 128, 256);
-                    umma::mma_i8(tmem, da, umma::make_desc(dHi + ks * 4 * lbo, lbo, 128), umma::make_idesc(N, 1, 1, 0, 1), ks);
-                    umma::mma_i8(tmem + LO, da, umma::make_desc(dLo + ks * 4 * lbo, lbo, 128), umma::make_idesc(N, 1, 0, 0, 1), ks);
-                }
-            }
-            umma::commit(bar);
-        }
-        __syncwarp();
-    }
-    umma::wait_bar(bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t lane0 = tmem + ((uint32_t)(threadIdx.x & 96) << 16) + (uint32_t)col0;      // warps w and w + 4 read TMEM lanes 32 (w % 4) ..
-#pragma unroll
-    for (int c = 0; c < 16; c += 8)
-    {
-        uint32_t h[8], l[8];
-        umma::ld8(lane0 + c, h);
-        umma::ld8(lane0 + LO + c, l);
-        umma::ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[c + i] = ((int)h[i] << 8) + (int)l[i];
-    }
-}
-
-// the thread's 16-element chunk of both byte planes (8 packed words) at byte offset `base` of the plane
-__device__ __forceinline__ void umma_write_chunk(uint8_t* hi, uint8_t* lo, int base, const uint32_t (&w)[8])
-{
-    uint32_t l[4], h[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) split4(make_uint2(w[2 * q], w[2 * q + 1]), l[q], h[q]);
-    *(uint4*)(lo + base) = make_uint4(l[0], l[1], l[2], l[3]);
-    *(uint4*)(hi + base) = make_uint4(h[0], h[1], h[2], h[3]);
-}
-
-// lab: X265B200_TU_TIMELINE=1 prints the %globaltimer stamps of one group of CTA 0 (warp 0 and warp 4) after the launch
-#define TU_STAMP(i) do { if (timeline && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && g == blockIdx.x + 8 * gridDim.x) { unsigned long long t__; \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); timeline[(warp >> 2) * 16 + (i)] = t__; } } while (0)
-template<typename T, int MINB, int COLS>
-__global__ void __launch_bounds__(256, MINB)
-tu_umma32_split_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred, intptr_t sp, const int32_t* __restrict__ offF,
-                       const int32_t* __restrict__ offP, int n, const int32_t* __restrict__ quantCoeff, QuantP P, int fshift1, int fshift2, int ishift2,
-                       int depth, int16_t* __restrict__ qCoef, uint32_t* __restrict__ numSig, T* __restrict__ recon, intptr_t sr,
-                       const int32_t* __restrict__ offR, unsigned long long* __restrict__ sseZero, unsigned long long* __restrict__ sseRecon,
-                       unsigned long long* __restrict__ timeline, int prefetch)
-{
-    constexpr int N = 32, NT = 4, NN = N * N;
-    typedef WarpTile<16> WT;                                                    // a thread's half row: 16 samples = two 16-byte pieces
-    extern __shared__ __align__(1024) uint8_t umma_smem[];
-    uint8_t (*sAk)[4096] = (uint8_t (*)[4096])umma_smem;                        // same carve-up as tu_umma_kernel
-    uint8_t (*sAm)[4096] = (uint8_t (*)[4096])(umma_smem + 8192);
-    uint8_t* sB = umma_smem + 16384;
-    uint8_t* sTd = umma_smem + 17408;
-    int32_t* sQ = (int32_t*)(umma_smem + 24576);
-    uint8_t (*sTile)[2][1024] = (uint8_t (*)[2][1024])(umma_smem + 28672);      // [8 warps][fenc, prediction] 32 half rows of 32 bytes
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmemBase;
-    __shared__ int sSig[NT][2], sDC[NT][2];
-    __shared__ unsigned long long sZ[NT], sD[NT];
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < 2 * 4096 / 16; i += 256) { ((uint4*)sAk)[i] = make_uint4(0, 0, 0, 0); ((uint4*)sAm)[i] = make_uint4(0, 0, 0, 0); }
-    for (int i = tid; i < 1024 / 16; i += 256) ((uint4*)sB)[i] = ((const uint4*)c_ummaB[0][0])[i];
-    for (int i = tid; i < 7168 / 16; i += 256) ((uint4*)sTd)[i] = ((const uint4*)c_ummaAD[0])[i];
-    for (int i = tid; i < N * N / 4; i += 256)
-    {
-        const int r = i / (N / 4), c = i % (N / 4);
-        ((int4*)sQ)[r * (N / 4) + (c ^ (r & (N / 4 - 1)))] = __ldg((const int4*)quantCoeff + i);
-    }
-    if (tid == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(umma::smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < 32)
-    {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(umma::smem_u32(&tmemBase)), "n"(COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmemBase, barA = umma::smem_u32(&bar);
-    const uint32_t aK[2] = { umma::smem_u32(sAk[0]), umma::smem_u32(sAk[1]) }, aM[2] = { umma::smem_u32(sAm[0]), umma::smem_u32(sAm[1]) };
-    const uint32_t bF = umma::smem_u32(sB), aD = umma::smem_u32(sTd);
-    uint32_t phase = 0;
-
-    const int lane = tid & 31, warp = tid >> 5, wq = warp & 3, hf = warp >> 2;
-    const int rid = tid & 127, row = lane;                   // the CTA row (TMEM lane) and the line inside the TU: one TU per warp pair
-    const int col0 = hf * 16;
-    const int kBase = (rid >> 3) * 256 + (rid & 7) * 16 + hf * 128;                     // forward 1 (K-major row rid) and forward 2 (B data, K = rid): chunk hf
-    const int mBase = (row >> 3) * 1024 + (row & 7) * 16 + (wq * 2 + hf) * 128;          // inverse 1 / 2: K index row, MN chunk of this half row
-    const uint32_t mx = ((uint32_t)((1 << depth) - 1)) * 0x10001u, negmx = (0u - (uint32_t)((1 << depth) - 1)) & 0xffffu;
-    const uint32_t negmx2 = negmx | (negmx << 16);
-    const int ngroups = (n + NT - 1) / NT;
-    uint8_t* tF = sTile[warp][0];
-    uint8_t* tP = sTile[warp][1];
-    uint8_t* tQ = sAk[0] + warp * 1024;                      // level rows on their way out (the forward-1 planes are idle by then)
-
-    // Descriptors run two groups ahead and the rows of the next group are pulled into L2 while this one computes: a group's first phase
-    // was two dependent DRAM round trips (descriptor, then rows; 3 - 3.5 us of its 7.4 us by the %globaltimer stamps below).
-    auto desc_of = [&](int g_, int& oF, int& oP, int& oR) {
-        const int t_ = g_ * NT + wq;
-        const bool l_ = g_ < ngroups && t_ < n;
-        oF = l_ ? __ldg(offF + t_) : -1; oP = l_ ? __ldg(offP + t_) : 0; oR = l_ ? __ldg(offR + t_) : 0;
-    };
-    int curF, curP, curR, nxtF, nxtP, nxtR;
-    desc_of(blockIdx.x, curF, curP, curR);
-    desc_of(blockIdx.x + gridDim.x, nxtF, nxtP, nxtR);
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x)
-    {
-        const int tu = g * NT + wq;
-        const bool live = tu < n;
-        TU_STAMP(0);
-        const int myOffF = live ? curF : 0, myOffP = live ? curP : 0, myOffR = live ? curR : 0;
-        if (prefetch && nxtF >= 0)
-        {   // lane = row of the next TU: this thread's half row of fenc (one 32-byte sector) and of the prediction (any alignment: both ends)
-            const T* pf = fenc + nxtF + (intptr_t)lane * sf + col0;
-            const T* pp = pred + nxtP + (intptr_t)lane * sp + col0;
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(pp + 15));
-        }
-        curF = nxtF; curP = nxtP; curR = nxtR;
-        desc_of(g + 2 * gridDim.x, nxtF, nxtP, nxtR);
-        uint32_t f[8], p[8], w[8];
-        if constexpr (sizeof(T) == 2)
-        {
-            __syncwarp();                                   // the previous group's readers of these tiles are done
-#pragma unroll
-            for (int it = 0; it < WT::NI; it++)
-            {
-                const int R = it * WT::RPI + lane / WT::PPR, c = lane % WT::PPR;
-                uint4 vf = make_uint4(0, 0, 0, 0);
-                uint32_t vp[4] = { 0, 0, 0, 0 };
-                if (live)
-                {
-                    vf = __ldg((const uint4*)(fenc + myOffF + (intptr_t)R * sf + col0 + 8 * c));
-                    load_row_quads<2>(pred + myOffP + (intptr_t)R * sp + col0 + 8 * c, vp);
-                }
-                *WT::piece(tF, R, c) = vf;
-                *WT::piece(tP, R, c) = make_uint4(vp[0], vp[1], vp[2], vp[3]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < WT::PPR; c++)
-            {
-                const uint4 a = *WT::piece(tF, lane, c), b = *WT::piece(tP, lane, c);
-                f[4 * c] = a.x; f[4 * c + 1] = a.y; f[4 * c + 2] = a.z; f[4 * c + 3] = a.w;
-                p[4 * c] = b.x; p[4 * c + 1] = b.y; p[4 * c + 2] = b.z; p[4 * c + 3] = b.w;
-            }
-        }
-        else
-        {
-            if (live)
-            {
-                load_row_quads<4>(fenc + myOffF + (intptr_t)row * sf + col0, f);
-                load_row_quads<4>(pred + myOffP + (intptr_t)row * sp + col0, p);
-            }
-            else
-            {
-#pragma unroll
-                for (int i = 0; i < 8; i++) { f[i] = 0; p[i] = 0; }
-            }
-        }
-        uint32_t z32 = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i += 2)
-        {
-            w[i] = psub16(f[i], p[i]); w[i + 1] = psub16(f[i + 1], p[i + 1]);
-            z32 += sumsq4(make_uint2(w[i], w[i + 1]));
-        }
-        int v[16];
-        TU_STAMP(1);
-        // ---- forward stage 1
-        umma_write_chunk(sAk[0], sAk[1], kBase, w);
-        umma_stage_half<COLS / 2>(0, aK[0], aK[1], bF, tmem, barA, phase, col0, v);
-        TU_STAMP(2);
-        {
-            const int add = 1 << (fshift1 - 1);
-#pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = __byte_perm((v[2 * i] + add) >> fshift1, (v[2 * i + 1] + add) >> fshift1, 0x5410);
-        }
-        // ---- forward stage 2
-        umma_write_chunk(sAm[0], sAm[1], kBase, w);
-        TU_STAMP(3);
-        umma_stage_half<COLS / 2>(2, aM[0], aM[1], aD, tmem, barA, phase, col0, v);
-        TU_STAMP(4);
-        // ---- quant and dequant along the half row
-        int sig = 0, lvDC = 0;
-        {
-            const int add = 1 << (fshift2 - 1);
-            const int4* qRow = (const int4*)sQ + row * (N / 4);
-            const int qs = row & (N / 4 - 1);
-#pragma unroll
-            for (int c = 0; c < 2; c++)
-            {
-                const int cc = 2 * hf + c;                  // the 8-coefficient chunk of the row
-                const int4 qa = qRow[(2 * cc) ^ qs], qb = qRow[(2 * cc + 1) ^ qs];
-                const int qq[8] = { qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w };
-                uint32_t lvp[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                {
-                    int lv0, lv1;
-                    const int c0 = (int)(int16_t)((v[8 * c + 2 * e] + add) >> fshift2), c1 = (int)(int16_t)((v[8 * c + 2 * e + 1] + add) >> fshift2);
-                    sig += quant_one(c0, qq[2 * e], P, lv0) + quant_one(c1, qq[2 * e + 1], P, lv1);
-                    if (c == 0 && e == 0) lvDC = lv0;        // meaningful in the thread (row 0, hf 0) only
-                    lvp[e] = pack_sat_s16(lv0, lv1);
-                    w[4 * c + e] = dequant_pair(lvp[e], P);
-                }
-                if constexpr (sizeof(T) == 2) *WT::piece(tQ, lane, c) = make_uint4(lvp[0], lvp[1], lvp[2], lvp[3]);
-                else if (live) *(uint4*)(qCoef + (size_t)tu * NN + row * N + col0 + 8 * c) = make_uint4(lvp[0], lvp[1], lvp[2], lvp[3]);
-            }
-            if constexpr (sizeof(T) == 2)
-            {
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < WT::NI; it++)
-                {
-                    const int R = it * WT::RPI + lane / WT::PPR, c = lane % WT::PPR;
-                    if (live) *(uint4*)(qCoef + (size_t)tu * NN + R * N + col0 + 8 * c) = *WT::piece(tQ, R, c);
-                }
-            }
-        }
-        {
-            const int wsig = __reduce_add_sync(0xffffffffu, sig);
-            if (lane == 0)
-            {
-                sSig[wq][hf] = wsig;
-                if (hf == 0) { sDC[wq][0] = (int)(int16_t)(w[0] & 0xffff); sDC[wq][1] = lvDC; }      // coefficient (0, 0): dequantised value and level
-            }
-        }
-        // ---- inverse stage 1
-        TU_STAMP(5);
-        umma_write_chunk(sAm[0], sAm[1], mBase, w);
-        umma_stage_half<COLS / 2>(1, aM[0], aM[1], bF, tmem, barA, phase, col0, v);         // (its barrier publishes sSig / sDC)
-        TU_STAMP(6);
-#pragma unroll
-        for (int i = 0; i < 8; i++) w[i] = pack_sat_s16((v[2 * i] + 64) >> 7, (v[2 * i + 1] + 64) >> 7);
-        // ---- inverse stage 2
-        umma_write_chunk(sAm[0], sAm[1], mBase, w);
-        TU_STAMP(7);
-        umma_stage_half<COLS / 2>(1, aM[0], aM[1], bF, tmem, barA, phase, col0, v);
-        TU_STAMP(8);
-        const int ns = sSig[wq][0] + sSig[wq][1];
-        const bool dcOnly = ns == 1 && sDC[wq][1] != 0;
-        const int dq0 = sDC[wq][0];
-        // ---- reconstruction
-        uint32_t d32 = 0;
-        if constexpr (sizeof(T) == 2)
-        {
-#pragma unroll
-            for (int c = 0; c < WT::PPR; c++)
-            {
-                const uint4 a = *WT::piece(tF, lane, c), b = *WT::piece(tP, lane, c);
-                f[4 * c] = a.x; f[4 * c + 1] = a.y; f[4 * c + 2] = a.z; f[4 * c + 3] = a.w;
-                p[4 * c] = b.x; p[4 * c + 1] = b.y; p[4 * c + 2] = b.z; p[4 * c + 3] = b.w;
-            }
-        }
-        {
-            const int add = 1 << (ishift2 - 1);
-            const int dcv = dc_fill_value(dq0, depth);
-            T* out = recon + myOffR + (intptr_t)row * sr + col0;
-#pragma unroll
-            for (int i = 0; i < 8; i += 2)
-            {
-                uint32_t r0, r1;
-                if (dcOnly) { r0 = r1 = __byte_perm(dcv, dcv, 0x5410); }
-                else
-                {
-                    r0 = pack_sat_s16((v[2 * i] + add) >> ishift2, (v[2 * i + 1] + add) >> ishift2);
-                    r1 = pack_sat_s16((v[2 * i + 2] + add) >> ishift2, (v[2 * i + 3] + add) >> ishift2);
-                }
-                uint32_t o0 = p[i], o1 = p[i + 1];
-                if (ns)
-                {
-                    o0 = __viaddmin_s16x2_relu(p[i], __vmins2(__vmaxs2(r0, negmx2), mx), mx);
-                    o1 = __viaddmin_s16x2_relu(p[i + 1], __vmins2(__vmaxs2(r1, negmx2), mx), mx);
-                }
-                if constexpr (sizeof(T) == 2) { p[i] = o0; p[i + 1] = o1; }
-                else if (live) store_pix4(out + 2 * i, o0, o1);
-                d32 += sumsq4(make_uint2(psub16(f[i], o0), psub16(f[i + 1], o1)));
-            }
-            if constexpr (sizeof(T) == 2)
-            {
-                const bool al = !(((uintptr_t)out | (uintptr_t)(sr * 2)) & 15);
-                if (__all_sync(0xffffffffu, al || !live))
-                {
-#pragma unroll
-                    for (int c = 0; c < WT::PPR; c++) *WT::piece(tP, lane, c) = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
-                    __syncwarp();
-#pragma unroll
-                    for (int it = 0; it < WT::NI; it++)
-                    {
-                        const int R = it * WT::RPI + lane / WT::PPR, c = lane % WT::PPR;
-                        if (live) *(uint4*)(recon + myOffR + (intptr_t)R * sr + col0 + 8 * c) = *WT::piece(tP, R, c);
-                    }
-                }
-                else if (live)
-                {
-#pragma unroll
-                    for (int i = 0; i < 8; i += 2) store_pix4(out + 2 * i, p[i], p[i + 1]);
-                }
-            }
-        }
-        __syncwarp();
-        TU_STAMP(9);
-        const unsigned long long zs = tu_sum64<32>(z32), ds = tu_sum64<32>(d32);
-        if (hf == 1 && lane == 0) { sZ[wq] = zs; sD[wq] = ds; }
-        asm volatile("bar.sync %0, 64;" :: "r"(1 + wq) : "memory");                      // the two warps of this TU
-        if (hf == 0 && lane == 0 && live)
-        {
-            numSig[tu] = (uint32_t)ns;
-            if (sseZero) sseZero[tu] = zs + sZ[wq];
-            sseRecon[tu] = ds + sD[wq];
-        }
-        TU_STAMP(10);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(COLS));
-}
-#undef TU_STAMP
-
 // the whole chain over n TUs of size N (32 or 16) in one launch.  Returns false when nothing was launched (alignment / size not covered).
 bool launch_tu_umma(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                     const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
@@ -886,32 +516,6 @@ bool launch_tu_umma(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, con
     if (const char* e = getenv("X265B200_UMMA_TRACE")) { int* tp = (int*)strtoull(e, nullptr, 0); cudaMemcpyToSymbol(g_ummaTrace, &tp, sizeof(tp)); }
 #endif
     if (grid > ngroups) grid = ngroups;
-    if (N == 32 && ctx->dct_path == 4)
-    {   // two threads per row (tu_umma32_split_kernel): 256 threads, <= 64 registers, 4 CTAs = 32 warps per SM
-        constexpr int SM_BYTES = 28672 + 8 * 2 * 1024;
-#define UMS(T) cudaFuncSetAttribute(tu_umma32_split_kernel<T, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES); \
-               tu_umma32_split_kernel<T, 4, 64><<<grid, 256, SM_BYTES, st>>>((const T*)fenc, sf, (const T*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, 12 - d8, \
-                   ctx->depth, qCoef, numSig, (T*)recon, sr, offR, (unsigned long long*)sseZero, (unsigned long long*)sseRecon, tline, lab_knob(3, 1))
-        unsigned long long* tline = nullptr;
-        if (getenv("X265B200_TU_TIMELINE")) { cudaMalloc(&tline, 32 * 8); cudaMemset(tline, 0, 32 * 8); }
-        if (ctx->pixbytes == 1) { UMS(uint8_t); } else { UMS(uint16_t); }
-#undef UMS
-        if (tline)
-        {
-            unsigned long long h[32];
-            cudaStreamSynchronize(st);
-            cudaMemcpy(h, tline, sizeof(h), cudaMemcpyDeviceToHost);
-            cudaFree(tline);
-            for (int wv = 0; wv < 2; wv++)
-            {
-                fprintf(stderr, "tu timeline warp %d (ns since group start):", wv * 4);
-                for (int i = 0; i <= 10; i++) fprintf(stderr, " %lld", (long long)(h[wv * 16 + i] - h[wv * 16]));
-                fprintf(stderr, "\n");
-            }
-        }
-        ctx->launches.fetch_add(1, std::memory_order_relaxed);
-        return cudaGetLastError() == cudaSuccess;
-    }
 #define UM(T, N_) cudaFuncSetAttribute(tu_umma_kernel<T, N_, N_ == 32 ? RES32 : RES16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 28672 + 4 * 2 * 64 * N_ + pad); \
                   tu_umma_kernel<T, N_, N_ == 32 ? RES32 : RES16, 64><<<grid, 128, 28672 + 4 * 2 * 64 * N_ + pad, st>>>((const T*)fenc, sf, (const T*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, 12 - d8, \
                       ctx->depth, qCoef, numSig, (T*)recon, sr, offR, (unsigned long long*)sseZero, (unsigned long long*)sseRecon, lab)
