@@ -177,8 +177,8 @@ strip8_fast_kernel(const uint16_t* __restrict__ A, intptr_t sa, const uint16_t* 
 // tile loads it ONCE and meets it with the matching tile of three reference blocks; the three per-shape launches read the
 // fenc plane three times.  offR[5 * cu + k], out[5 * cu + k]: k = 0 2Nx2N, 1 / 2 upper / lower 2NxN, 3 / 4 left / right Nx2N,
 // each offset addressing the top-left sample of that PU's reference block.  G lanes (power of two) share a CU.
-template<typename T, int S>
-__global__ void __launch_bounds__(128)
+template<typename T, int S, int MINB = 0>
+__global__ void __launch_bounds__(128, MINB)
 cu_satd_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
                const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, int n, int G, int32_t* __restrict__ out)
 {
