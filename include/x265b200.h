@@ -186,14 +186,30 @@ int x265b200_residual_batch(x265b200_ctx* ctx, int w, int h, const void* A, intp
  * quant.cpp:556,567.  Outputs: qCoef[n*N*N], numSig[n], recon blocks at recon + offR[i] (the prediction when
  * numSig == 0), sseZero[n] = sse(fenc, pred) (may be NULL) and sseRecon[n] = sse(fenc, recon).  sseZero is the only
  * pointer that may be NULL: offF, offP, offR and sseRecon are required (ERR_ARG otherwise).
- * Default path (x265b200_set_dct_path 0): two fused tensor-core kernels, no scratch memory.  Path 1 (validation twin) runs
- * the stage kernels of the batched primitives over chunks whose intermediates live in an L2-sized scratch taken from the
- * stream-ordered allocator. */
+ * Default path (x265b200_set_dct_path 0): one tcgen05 / tensor-memory kernel for N = 32, two fused mma.sync kernels for N = 16 / 8 / 4, no
+ * scratch memory.  Path 1 (validation twin) runs the stage kernels of the batched primitives over chunks whose intermediates live in an
+ * L2-sized scratch taken from the stream-ordered allocator; path 2 = the mma.sync pair for every size; path 3 = tcgen05 for N = 16 too. */
 int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
                             const int32_t* offF, const int32_t* offP, int n,
                             const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
                             int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
                             uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream);
+
+/* The same chain for the other TU classes of the residual quadtree (the planes, strides and N are the caller's):
+ *   X265B200_TU_INTER       inter luma -- and every chroma TU: the chroma loop of Search::estimateResidualQT (reference
+ *                           encoder/search.cpp:5638-5700) issues the identical slot sequence on the Cb / Cr planes with log2TrSizeC
+ *                           (4:2:2: the two vertically stacked sub-TUs are two TUs of the batch), chroma QP in quantCoeff / qBits / dqScale;
+ *   X265B200_TU_INTRA_LUMA  intra luma (Search::codeIntraLumaQT, search.cpp:327-390 residual path): a 4x4 TU takes the DST-VII pair
+ *                           dst4x4 / idst4x4 instead of the DCT (reference common/quant.cpp:430-441) and never the DC-only shortcut
+ *                           (quant.cpp:585-588 `useDST`); 8x8 ... 32x32 are identical to X265B200_TU_INTER.  `add` is the caller's
+ *                           rounding offset (171 << (qBits - 9) for intra slices, quant.cpp:466).
+ * x265b200_tu_chain_batch(..) == x265b200_tu_chain_tt_batch(.., X265B200_TU_INTER, ..). */
+enum { X265B200_TU_INTER = 0, X265B200_TU_INTRA_LUMA = 1 };
+int x265b200_tu_chain_tt_batch(x265b200_ctx* ctx, int N, int ttype, const void* fenc, intptr_t strideF, const void* pred, intptr_t strideP,
+                               const int32_t* offF, const int32_t* offP, int n,
+                               const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                               int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
+                               uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream);
 
 /* Sub-pel candidate cost, interpolation fused with the metric (reference encoder/motion.cpp:1780-1821,
  * MotionEstimate::subpelCompare, luma part): for candidate i of block i / K (n blocks, K candidates each),

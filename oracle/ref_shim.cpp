@@ -308,11 +308,14 @@ int ref_p2s(int w, int h, const pixel* s, intptr_t ss, int16_t* d, intptr_t ds)
 }
 
 /* ---- inter luma TU chain composed from the reference's own slots, in the order search.cpp:5536-5575 / quant.cpp:397-605 call them ---- */
-void ref_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* quantCoeff,
-                  int qBits, int add, int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr,
-                  uint64_t* sseZero, uint64_t* sseRecon)
+/* ttype 1 = intra luma: the 4x4 TU goes through the dst4x4 / idst4x4 slots and skips the DC-only shortcut, as Quant::transformNxN /
+ * invtransformNxN do (quant.cpp:430-441, :585-603) */
+void ref_tu_chain_tt(int N, int ttype, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* quantCoeff,
+                     int qBits, int add, int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr,
+                     uint64_t* sseZero, uint64_t* sseRecon)
 {
     ensure();
+    const bool useDST = ttype == 1 && N == 4;
     int cu = trIdx(N);
     ALIGN_VAR_32(int16_t, resi[32 * 32]);
     ALIGN_VAR_32(int16_t, coef[32 * 32]);
@@ -321,7 +324,8 @@ void ref_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intp
     ALIGN_VAR_32(int32_t, deltaU[32 * 32]);
     ALIGN_VAR_32(int16_t, q[32 * 32]);
     g_c.cu[cu].sub_ps(resi, N, fenc, pred, sf, sp);
-    g_c.cu[cu].dct(resi, coef, N);
+    if (useDST) g_c.dst4x4(resi, coef, N);
+    else g_c.cu[cu].dct(resi, coef, N);
     uint32_t ns = g_c.quant(coef, quantCoeff, deltaU, q, qBits, add, N * N);
     memcpy(qCoef, q, sizeof(int16_t) * N * N);
     *numSig = ns;
@@ -333,17 +337,25 @@ void ref_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intp
         return;
     }
     g_c.dequant_normal(q, dq, N * N, dqScale, dqShift);
-    if (ns == 1 && q[0] != 0)
+    if (ns == 1 && q[0] != 0 && !useDST)
     {
         const int shift_1st = 7 - 6, add_1st = 1 << (shift_1st - 1);
         const int shift_2nd = 12 - (X265_DEPTH - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
         int dc_val = (((dq[0] * (64 >> 6) + add_1st) >> shift_1st) * (64 >> 3) + add_2nd) >> shift_2nd;
         g_c.cu[cu].blockfill_s[NONALIGNED](rec, N, (int16_t)dc_val);
     }
+    else if (useDST)
+        g_c.idst4x4(dq, rec, N);
     else
         g_c.cu[cu].idct(dq, rec, N);
     g_c.cu[cu].add_ps[NONALIGNED](recon, sr, pred, rec, sp, N);
     *sseRecon = g_c.cu[cu].sse_pp(fenc, sf, recon, sr);
+}
+void ref_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* quantCoeff,
+                  int qBits, int add, int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr,
+                  uint64_t* sseZero, uint64_t* sseRecon)
+{
+    ref_tu_chain_tt(N, 0, fenc, sf, pred, sp, quantCoeff, qBits, add, dqScale, dqShift, qCoef, numSig, recon, sr, sseZero, sseRecon);
 }
 
 /* ---- slot census for the coverage contract (SURVEY.md section 8a checklist) ---- */

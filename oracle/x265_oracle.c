@@ -662,17 +662,22 @@ EXPORT void orc_extend_pic_border(pixel* pic, intptr_t stride, int width, int he
  * quant.cpp:543-605 (invtransformNxN: dequant_normal, DC-only shortcut :588-598, idct), pixel.cpp sub_ps / add_ps
  * (:821-831) and sse_pp.  numSig == 0 leaves the prediction as reconstruction (cbf = 0).
  * Outputs per TU: qCoef[N*N], numSig, recon block, sse(fenc, pred), sse(fenc, recon). */
-EXPORT void orc_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp,
-                         const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
-                         int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr, uint64_t* sseZero, uint64_t* sseRecon)
+/* ttype 0: inter luma, and every chroma TU (the chroma loop of estimateResidualQT, search.cpp:5638-5700, runs the same calls on the chroma
+ * planes with log2TrSizeC).  ttype 1: intra luma -- for N == 4 Quant::transformNxN / invtransformNxN take the DST-VII pair instead
+ * (quant.cpp:430-441 "useDST", :585 `useDST = !sizeIdx && ttype == TEXT_LUMA && bIntra`, :600-603) and the DC-only shortcut is off (:588). */
+EXPORT void orc_tu_chain_tt(int N, int ttype, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp,
+                            const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                            int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr, uint64_t* sseZero, uint64_t* sseRecon)
 {
+    const int useDST = ttype == 1 && N == 4;
     int16_t resi[32 * 32], coef[32 * 32], dq[32 * 32], rec[32 * 32];
     int32_t deltaU[32 * 32];
     int nn = N * N;
     for (int y = 0; y < N; y++)
         for (int x = 0; x < N; x++)
             resi[y * N + x] = (int16_t)((int)fenc[y * sf + x] - (int)pred[y * sp + x]);
-    orc_dct(N, resi, coef, N);
+    if (useDST) orc_dst4(resi, coef, N);
+    else orc_dct(N, resi, coef, N);
     uint32_t ns = orc_quant(coef, quantCoeff, deltaU, qCoef, qBits, add, nn);
     *numSig = ns;
     *sseZero = (uint64_t)orc_sse_pp(N, N, fenc, sf, pred, sp);
@@ -684,7 +689,7 @@ EXPORT void orc_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pre
         return;
     }
     orc_dequant_normal(qCoef, dq, nn, dqScale, dqShift);
-    if (ns == 1 && qCoef[0] != 0)
+    if (ns == 1 && qCoef[0] != 0 && !useDST)
     {
         /* quant.cpp:588-598 */
         const int shift_1st = 7 - 6, add_1st = 1 << (shift_1st - 1);
@@ -692,12 +697,20 @@ EXPORT void orc_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pre
         int dc_val = (((dq[0] * (64 >> 6) + add_1st) >> shift_1st) * (64 >> 3) + add_2nd) >> shift_2nd;
         for (int i = 0; i < nn; i++) rec[i] = (int16_t)dc_val;
     }
+    else if (useDST)
+        orc_idst4(dq, rec, N);
     else
         orc_idct(N, dq, rec, N);
     for (int y = 0; y < N; y++)
         for (int x = 0; x < N; x++)
             recon[y * sr + x] = (pixel)clip3(0, PIXEL_MAX, (int)pred[y * sp + x] + rec[y * N + x]);   /* add_ps, pixel.cpp:821-831 */
     *sseRecon = (uint64_t)orc_sse_pp(N, N, fenc, sf, recon, sr);
+}
+EXPORT void orc_tu_chain(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp,
+                         const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                         int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr, uint64_t* sseZero, uint64_t* sseRecon)
+{
+    orc_tu_chain_tt(N, 0, fenc, sf, pred, sp, quantCoeff, qBits, add, dqScale, dqShift, qCoef, numSig, recon, sr, sseZero, sseRecon);
 }
 
 EXPORT void orc_tu_chain_batch(int N, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* offF,
@@ -708,6 +721,15 @@ EXPORT void orc_tu_chain_batch(int N, const pixel* fenc, intptr_t sf, const pixe
     for (int i = 0; i < n; i++)
         orc_tu_chain(N, fenc + offF[i], sf, pred + offP[i], sp, quantCoeff, qBits, add, dqScale, dqShift,
                      qCoef + (size_t)i * N * N, numSig + i, recon + offR[i], sr, sseZero + i, sseRecon + i);
+}
+EXPORT void orc_tu_chain_tt_batch(int N, int ttype, const pixel* fenc, intptr_t sf, const pixel* pred, intptr_t sp, const int32_t* offF,
+                                  const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                                  int16_t* qCoef, uint32_t* numSig, pixel* recon, intptr_t sr, const int32_t* offR,
+                                  uint64_t* sseZero, uint64_t* sseRecon)
+{
+    for (int i = 0; i < n; i++)
+        orc_tu_chain_tt(N, ttype, fenc + offF[i], sf, pred + offP[i], sp, quantCoeff, qBits, add, dqScale, dqShift,
+                        qCoef + (size_t)i * N * N, numSig + i, recon + offR[i], sr, sseZero + i, sseRecon + i);
 }
 
 /* dct over n strided blocks of one int16 plane; output contiguous n x (N*N) */

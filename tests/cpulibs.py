@@ -265,11 +265,12 @@ class _Base:
         self._f("lowres", None)(_ptr(src, os_), C.c_ssize_t(ss), _ptr(d0), _ptr(dh), _ptr(dv), _ptr(dc), C.c_ssize_t(ds), width, height)
 
     # ---- inter luma TU chain (sub_ps, dct, quant, dequant, DC shortcut / idct, add_ps, sse) ---------------
-    def tu_chain(self, N, fenc, of, sf, pred, op_, sp, qc, qbits, add, dqscale, dqshift, recon, orr, sr):
+    def tu_chain(self, N, fenc, of, sf, pred, op_, sp, qc, qbits, add, dqscale, dqshift, recon, orr, sr, ttype=0):
+        """ttype 0 = inter luma / any chroma TU, 1 = intra luma (DST-VII and no DC-only shortcut at N = 4)"""
         q = np.zeros(N * N, np.int16)
         ns = C.c_uint32(0); z = C.c_uint64(0); r = C.c_uint64(0)
-        self._f("tu_chain", None)(N, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(pred, op_), C.c_ssize_t(sp), _ptr(qc), qbits, add,
-                                  dqscale, dqshift, _ptr(q), C.byref(ns), _ptr(recon, orr), C.c_ssize_t(sr), C.byref(z), C.byref(r))
+        self._f("tu_chain_tt", None)(N, ttype, _ptr(fenc, of), C.c_ssize_t(sf), _ptr(pred, op_), C.c_ssize_t(sp), _ptr(qc), qbits, add,
+                                     dqscale, dqshift, _ptr(q), C.byref(ns), _ptr(recon, orr), C.c_ssize_t(sr), C.byref(z), C.byref(r))
         return q, ns.value, z.value, r.value
 
     # ---- tables -----------------------------------------------------------------------
@@ -354,12 +355,12 @@ class Oracle(_Base):
         self._f("dct_batch", None)(N, dst4, _ptr(src), C.c_ssize_t(stride), _ptr(off), n, _ptr(out))
         return out
 
-    def tu_chain_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, dqscale, dqshift, recon, sr, offR):
+    def tu_chain_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, dqscale, dqshift, recon, sr, offR, ttype=0):
         n = len(offF)
         q = np.zeros(n * N * N, np.int16); ns = np.zeros(n, np.uint32); z = np.zeros(n, np.uint64); r = np.zeros(n, np.uint64)
-        self._f("tu_chain_batch", None)(N, _ptr(fenc), C.c_ssize_t(sf), _ptr(pred), C.c_ssize_t(sp), _ptr(offF), _ptr(offP), n,
-                                        _ptr(qc), qbits, add, dqscale, dqshift, _ptr(q), _ptr(ns), _ptr(recon), C.c_ssize_t(sr),
-                                        _ptr(offR), _ptr(z), _ptr(r))
+        self._f("tu_chain_tt_batch", None)(N, ttype, _ptr(fenc), C.c_ssize_t(sf), _ptr(pred), C.c_ssize_t(sp), _ptr(offF), _ptr(offP), n,
+                                           _ptr(qc), qbits, add, dqscale, dqshift, _ptr(q), _ptr(ns), _ptr(recon), C.c_ssize_t(sr),
+                                           _ptr(offR), _ptr(z), _ptr(r))
         return q, ns, z, r
 
     def blockcopy_batch(self, kind, w, h, S, ss, offS, D, sd, offD, param=0):

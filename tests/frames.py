@@ -28,6 +28,24 @@ class Geometry:
         return self.cu_w * self.ctu, self.cu_h * self.ctu
 
 
+class ChromaGeometry:
+    """one chroma plane of the same picture (picyuv.cpp:108-118): the horizontal margin stays the luma one ("keep 16-byte alignment for
+    chroma CTUs"), the vertical one and the coded size follow the chroma shifts (4:2:0: 1, 1; 4:2:2: 1, 0; 4:4:4: 0, 0)"""
+
+    def __init__(self, luma, hshift, vshift):
+        self.width, self.height, self.ctu = luma.width >> hshift, luma.height >> vshift, luma.ctu
+        self.cw, self.ch = (luma.cu_w * luma.ctu) >> hshift, (luma.cu_h * luma.ctu) >> vshift
+        self.margin_x = luma.margin_x
+        self.margin_y = luma.margin_y >> vshift
+        self.stride = self.cw + 2 * self.margin_x
+        self.rows = self.ch + 2 * self.margin_y
+        self.origin = self.margin_y * self.stride + self.margin_x
+        self.plane_elems = self.stride * self.rows
+
+    def coded(self):
+        return self.cw, self.ch
+
+
 def make_plane(geo, depth, seed, kind="uniform"):
     dt = np.uint8 if depth == 8 else np.uint16
     pmax = (1 << depth) - 1

@@ -258,6 +258,70 @@ def test_tu_chain_batch(depth):
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
+def test_tu_chain_intra_luma_and_chroma(depth):
+    """x265b200_tu_chain_tt_batch: intra luma (DST-VII and no DC-only shortcut at 4x4; 8x8 identical to inter) on every path, and the chain on
+    4:2:0 / 4:2:2 chroma planes (their own stride and margins, TU sizes 4 ... 32, the stacked 4:2:2 sub-TUs as separate TUs)"""
+    import torch
+    from gpulib import context, pkg
+    from frames import ChromaGeometry, Geometry, make_plane, tile_blocks
+    ctx = context(depth); orc = Oracle(depth)
+    geo = Geometry(832, 480)
+    flat = [26214, 23302, 20560, 18396, 16384, 14564]; inv = [40, 45, 51, 57, 64, 72]
+    rng = np.random.default_rng(100 + depth)
+
+    def run(g, F, P, N, qp, ttype, paths, intra_add):
+        offF, _ = tile_blocks(g, N, N, seed=6)
+        n = len(offF)
+        per, rem = qp // 6, qp % 6
+        tshift = 15 - depth - {4: 2, 8: 3, 16: 4, 32: 5}[N]
+        qbits = 14 + per + tshift
+        add = (171 if intra_add else 85) << (qbits - 9)
+        qc = (flat[rem] + rng.integers(-2000, 2001, N * N)).astype(np.int32)
+        scale, shift = inv[rem] << per, 20 - 14 - tshift
+        recon0 = np.full(g.plane_elems, 3, orc.pix)
+        rq, rns, rz, rr = orc.tu_chain_batch(N, F, g.stride, P, g.stride, offF, offF, qc, qbits, add, scale, shift, recon0, g.stride, offF, ttype=ttype)
+        q = torch.zeros(n * N * N, dtype=torch.int16, device="cuda"); ns = torch.zeros(n, dtype=torch.int32, device="cuda")
+        z = torch.zeros(n, dtype=torch.int64, device="cuda"); r = torch.zeros(n, dtype=torch.int64, device="cuda")
+        for path in paths:
+            ctx.set_dct_path(path)
+            d_recon = dev(pix_view(np.full(g.plane_elems, 3, orc.pix), depth))
+            q.zero_(); ns.zero_(); z.zero_(); r.zero_()
+            ctx.tu_chain_batch(N, dev(pix_view(F, depth)), g.stride, dev(pix_view(P, depth)), g.stride, dev(offF), dev(offF), dev(qc),
+                               qbits, add, scale, shift, q, ns, d_recon, g.stride, dev(offF), z, r, ttype=ttype)
+            assert np.array_equal(ns.cpu().numpy().astype(np.uint32), rns), (N, qp, ttype, path)
+            assert np.array_equal(q.cpu().numpy(), rq), (N, qp, ttype, path)
+            assert np.array_equal(z.cpu().numpy().astype(np.uint64), rz), (N, qp, ttype, path)
+            assert np.array_equal(r.cpu().numpy().astype(np.uint64), rr), (N, qp, ttype, path)
+            got = d_recon.cpu().numpy()
+            assert np.array_equal(got.view(orc.pix) if depth > 8 else got, recon0), (N, qp, ttype, path)
+        ctx.set_dct_path(0)
+        return rq.reshape(n, N * N), rns
+
+    F = make_plane(geo, depth, 51, "natural")
+    P = np.clip(F.astype(np.int64) + rng.integers(-6, 7, geo.plane_elems) * (1 << (depth - 8)), 0, orc.pmax).astype(orc.pix)
+    Pflat = np.clip(F.astype(np.int64) - (11 << (depth - 8)), 0, orc.pmax).astype(orc.pix)
+    Pflat3 = np.clip(F.astype(np.int64) - (3 << (depth - 8)), 0, orc.pmax).astype(orc.pix)
+    dc_seen = False
+    for qp, Pc in ((22, P), (30, P), (38, Pflat), (44, Pflat), (12, P), (38, Pflat3), (44, Pflat3)):
+        qm, rns = run(geo, F, Pc, 4, qp, pkg.TU_INTRA_LUMA, (0, 1), True)
+        dc_seen |= bool(((rns == 1) & (qm[:, 0] != 0)).any())      # the case where the DST path must NOT take the DC-only shortcut
+    assert dc_seen
+    # the DST differs from the DCT (a wrong dispatch cannot pass both), and 8x8 intra luma is the inter chain
+    a, _ = run(geo, F, P, 4, 22, pkg.TU_INTRA_LUMA, (0,), True)
+    b, _ = run(geo, F, P, 4, 22, pkg.TU_INTER, (0,), True)
+    assert not np.array_equal(a, b)
+    run(geo, F, P, 8, 27, pkg.TU_INTRA_LUMA, (0, 1), True)
+    # chroma planes: 4:2:0 and 4:2:2
+    for hs, vs in ((1, 1), (1, 0)):
+        cg = ChromaGeometry(geo, hs, vs)
+        Fc = make_plane(cg, depth, 61 + vs, "natural")
+        Pc = np.clip(Fc.astype(np.int64) + rng.integers(-5, 6, cg.plane_elems) * (1 << (depth - 8)), 0, orc.pmax).astype(orc.pix)
+        for N, qp in ((4, 24), (8, 31), (16, 35), (32, 29)):
+            run(cg, Fc, Pc, N, qp, pkg.TU_INTER, (0, 1) if N != 32 else (0, 2), False)
+    ctx.check()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
 def test_blockop_and_lowres_batches(depth):
     """adjacent slots: sub_ps / add_ps / pixelavg_pp / addAvg over descriptor batches (luma and odd chroma
     shapes, misaligned offsets, odd strides) and the whole-plane lowres downscale, element-wise vs the oracle"""

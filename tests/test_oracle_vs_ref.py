@@ -298,6 +298,14 @@ def test_tu_chain(libs):
         b = r.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r1, 7, stride)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (N, qp, trial)
         assert np.array_equal(r0, r1), (N, qp, trial)
+        # intra luma: DST-VII at 4x4 and no DC-only shortcut (quant.cpp:430-441, :585-603); the other sizes unchanged
+        r2 = np.full(stride * 40, 3, o.pix); r3 = r2.copy()
+        c = o.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r2, 7, stride, ttype=1)
+        d = r.tu_chain(N, fenc, 5, stride, pred, 5, stride, qc, qbits, add, inv[rem] << per, 20 - 14 - tshift, r3, 7, stride, ttype=1)
+        assert np.array_equal(c[0], d[0]) and c[1:] == d[1:], (N, qp, trial, "intra")
+        assert np.array_equal(r2, r3), (N, qp, trial, "intra")
+        if N != 4:
+            assert np.array_equal(c[0], a[0]) and np.array_equal(r2, r0)
 
 
 def test_adjacent_slots(libs):

@@ -10,4 +10,4 @@ opening a context without a usable sm_100 device raises.
 """
 from .binding import (Context, HostAPI, LIB_PATH, OP_SAD, OP_SATD, OP_SA8D, OP_SSE_PP, TR_DCT, TR_DST,  # noqa: F401
                       TR_LOWPASS, ME_DIA, ME_HEX, ME_UMH, ME_STAR, ME_SEA, ME_FULL, IP_KINDS, load_library, declared_symbols, build_library, GLUE_HEADER, glue_path,
-                      Plane, FrameJob, PassResult, TmePU, TmeResult, TME_MAX_CAND, expand_levels, PASS_CMP, PASS_COEF, PASS_LEVELS)
+                      Plane, FrameJob, PassResult, TmePU, TmeResult, TME_MAX_CAND, expand_levels, PASS_CMP, PASS_COEF, PASS_LEVELS, TU_INTER, TU_INTRA_LUMA)

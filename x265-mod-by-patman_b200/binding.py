@@ -292,10 +292,16 @@ class Context:
                    _dp(offDst), _dp(coeffIdx), int(offSrc.numel()), C.c_void_p(stream))
 
     def tu_chain_batch(self, N, fenc, sf, pred, sp, offF, offP, qc, qbits, add, dqscale, dqshift, qCoef, numSig, recon, sr, offR,
-                       sseZero, sseRecon, stream=0):
-        self._call("x265b200_tu_chain_batch", N, _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
-                   _dp(qc), qbits, add, dqscale, dqshift, _dp(qCoef), _dp(numSig), _dp(recon), _ss(sr), _dp(offR),
-                   _dp(sseZero), _dp(sseRecon), C.c_void_p(stream))
+                       sseZero, sseRecon, stream=0, ttype=None):
+        """ttype None: x265b200_tu_chain_batch (inter luma / chroma); TU_INTER / TU_INTRA_LUMA: x265b200_tu_chain_tt_batch"""
+        if ttype is None:
+            self._call("x265b200_tu_chain_batch", N, _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
+                       _dp(qc), qbits, add, dqscale, dqshift, _dp(qCoef), _dp(numSig), _dp(recon), _ss(sr), _dp(offR),
+                       _dp(sseZero), _dp(sseRecon), C.c_void_p(stream))
+        else:
+            self._call("x265b200_tu_chain_tt_batch", N, int(ttype), _dp(fenc), _ss(sf), _dp(pred), _ss(sp), _dp(offF), _dp(offP), int(offF.numel()),
+                       _dp(qc), qbits, add, dqscale, dqshift, _dp(qCoef), _dp(numSig), _dp(recon), _ss(sr), _dp(offR),
+                       _dp(sseZero), _dp(sseRecon), C.c_void_p(stream))
 
     def residual_batch(self, w, h, A, sa, B, sb, offA, offB, dst, stream=0):
         self._call("x265b200_residual_batch", w, h, _dp(A), _ss(sa), _dp(B), _ss(sb), _dp(offA), _dp(offB),
@@ -303,6 +309,7 @@ class Context:
 
 
 PASS_CMP, PASS_COEF, PASS_LEVELS = 0, 1, 2
+TU_INTER, TU_INTRA_LUMA = 0, 1
 
 
 class PassResult(C.Structure):

@@ -147,7 +147,7 @@ levels_pack_kernel(const int16_t* __restrict__ q, long long total, const uint32_
 
 bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                        const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
-                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st);                  // tu_fused.cuh
+                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st, int dst4);        // tu_fused.cuh
 
 struct Pass
 {

@@ -18,7 +18,7 @@ int launch_quant(x265b200_ctx* ctx, int mode, const int16_t* coef, const int32_t
 bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                      const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
                      int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
-                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);   // tu_fused.cuh (transform_mma.cu)
+                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st, int dst4);   // tu_fused.cuh (transform_mma.cu)
 
 bool launch_tu_umma(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                     const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
@@ -26,7 +26,7 @@ bool launch_tu_umma(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, con
                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st);    // tu_umma.cuh (transform_mma.cu)
 bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                        const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
-                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st);                  // tu_fused.cuh
+                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st, int dst4);        // tu_fused.cuh
 
 // recon = clip(pred + resi') with the cbf == 0 and DC-only cases, plus both distortions; 4 samples per thread
 template<typename T>
@@ -35,7 +35,7 @@ recon_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred
              const int32_t* __restrict__ offF, const int32_t* __restrict__ offP, int n, int N,
              const int16_t* __restrict__ resi, const int16_t* __restrict__ dq, const int16_t* __restrict__ qCoef,
              const uint32_t* __restrict__ numSig, T* __restrict__ recon, intptr_t sr, const int32_t* __restrict__ offR,
-             unsigned long long* __restrict__ sseZero, unsigned long long* __restrict__ sseRecon, int depth)
+             unsigned long long* __restrict__ sseZero, unsigned long long* __restrict__ sseRecon, int depth, int dcShortcut)
 {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int qw = N >> 2;
@@ -56,7 +56,7 @@ recon_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred
         uint32_t ns = numSig[tu];
         size_t base = (size_t)tu * N * N;
         int rr[4] = { 0, 0, 0, 0 };
-        if (ns == 1 && qCoef[base] != 0)
+        if (ns == 1 && qCoef[base] != 0 && dcShortcut)
         {
             // DC only, quant.cpp:588-598
             const int shift_2nd = 12 - (depth - 8) - 3, add_2nd = 1 << (shift_2nd - 1);
@@ -99,17 +99,21 @@ recon_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred
 
 using namespace b200;
 
-extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred,
-                                       intptr_t strideP, const int32_t* offF, const int32_t* offP, int n,
-                                       const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
-                                       int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
-                                       uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream)
+// ttype: X265B200_TU_INTER (inter luma and every chroma TU: the chroma loop of estimateResidualQT, search.cpp:5638-5700, is this chain on the
+// chroma planes with log2TrSizeC) or X265B200_TU_INTRA_LUMA (a 4x4 TU takes DST-VII and no DC-only shortcut, quant.cpp:430-441, :585-603)
+extern "C" int x265b200_tu_chain_tt_batch(x265b200_ctx* ctx, int N, int ttype, const void* fenc, intptr_t strideF, const void* pred,
+                                          intptr_t strideP, const int32_t* offF, const int32_t* offP, int n,
+                                          const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                                          int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
+                                          uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream)
 {
     if (!ctx) return X265B200_ERR_ARG;
     if ((N != 4 && N != 8 && N != 16 && N != 32) || n < 0 || qBits < 8 || dqShift < 1)
         return fail(ctx, X265B200_ERR_ARG, "tu_chain: bad size / parameters");
+    if (ttype != X265B200_TU_INTER && ttype != X265B200_TU_INTRA_LUMA) return fail(ctx, X265B200_ERR_ARG, "tu_chain: unknown TU type");
     if ((strideF | strideP) & 3) return fail(ctx, X265B200_ERR_ARG, "tu_chain: plane strides must be multiples of 4 samples");
     if (n == 0) return X265B200_OK;
+    const int dst4 = ttype == X265B200_TU_INTRA_LUMA && N == 4;
     if (!fenc || !pred || !recon || !offF || !offP || !offR || !quantCoeff || !qCoef || !numSig || !sseRecon)
         return fail(ctx, X265B200_ERR_ARG, "tu_chain: only sseZero may be NULL (offF, offP, offR and sseRecon are required)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -127,7 +131,7 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
     // int16 scratch planes stay L2-resident.
     if (ctx->dct_path != 1 &&
         launch_tu_fused(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
-                        qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st))
+                        qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, st, dst4))
         return X265B200_OK;
     if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_chain fused launch");
     const int chunkTUs = (8 << 20) / NN;
@@ -147,25 +151,35 @@ extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fen
         int m = n - c0 < chunkTUs ? n - c0 : chunkTUs;
         int16_t* q = qCoef + (size_t)c0 * NN;
         rc = x265b200_residual_batch(ctx, N, N, fenc, strideF, pred, strideP, offF + c0, offP + c0, m, s0, stream);
-        if (rc == X265B200_OK) rc = x265b200_dct_batch(ctx, X265B200_TR_DCT, N, s0, N, nullptr, m, s1, stream);
+        if (rc == X265B200_OK) rc = x265b200_dct_batch(ctx, dst4 ? X265B200_TR_DST : X265B200_TR_DCT, N, s0, N, nullptr, m, s1, stream);
         if (rc == X265B200_OK) rc = launch_quant(ctx, 2, s1, quantCoeff, nullptr, q, qBits, add, NN, m, numSig + c0, st);
         if (rc == X265B200_OK) rc = x265b200_dequant_normal_batch(ctx, q, s0, m * NN, dqScale, dqShift, stream);
-        if (rc == X265B200_OK) rc = x265b200_idct_batch(ctx, X265B200_TR_DCT, N, s0, m, s1, N, nullptr, stream);
+        if (rc == X265B200_OK) rc = x265b200_idct_batch(ctx, dst4 ? X265B200_TR_DST : X265B200_TR_DCT, N, s0, m, s1, N, nullptr, stream);
         if (rc != X265B200_OK) break;
         long long threads = (long long)m * (NN >> 2);
         if (ctx->pixbytes == 1)
             recon_kernel<uint8_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint8_t*)fenc, strideF, (const uint8_t*)pred, strideP, offF + c0, offP + c0, m, N,
                                                                         s1, s0, q, numSig + c0, (uint8_t*)recon, strideR, offR + c0,
-                                                                        (unsigned long long*)(sseZero ? sseZero + c0 : nullptr), (unsigned long long*)sseRecon + c0, ctx->depth);
+                                                                        (unsigned long long*)(sseZero ? sseZero + c0 : nullptr), (unsigned long long*)sseRecon + c0, ctx->depth, !dst4);
         else
             recon_kernel<uint16_t><<<ceil_div(threads, 256), 256, 0, st>>>((const uint16_t*)fenc, strideF, (const uint16_t*)pred, strideP, offF + c0, offP + c0, m, N,
                                                                          s1, s0, q, numSig + c0, (uint16_t*)recon, strideR, offR + c0,
-                                                                         (unsigned long long*)(sseZero ? sseZero + c0 : nullptr), (unsigned long long*)sseRecon + c0, ctx->depth);
+                                                                         (unsigned long long*)(sseZero ? sseZero + c0 : nullptr), (unsigned long long*)sseRecon + c0, ctx->depth, !dst4);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, X265B200_ERR_CUDA, "recon_kernel launch");
     }
     cudaFreeAsync(scratch, st);
     return rc;
+}
+
+extern "C" int x265b200_tu_chain_batch(x265b200_ctx* ctx, int N, const void* fenc, intptr_t strideF, const void* pred,
+                                       intptr_t strideP, const int32_t* offF, const int32_t* offP, int n,
+                                       const int32_t* quantCoeff, int qBits, int add, int dqScale, int dqShift,
+                                       int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t strideR, const int32_t* offR,
+                                       uint64_t* sseZero, uint64_t* sseRecon, x265b200_stream stream)
+{
+    return x265b200_tu_chain_tt_batch(ctx, N, X265B200_TU_INTER, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, dqScale, dqShift,
+                                      qCoef, numSig, recon, strideR, offR, sseZero, sseRecon, stream);
 }
 
 // forward half of the chain: what Quant::transformNxN (reference common/quant.cpp:397-480) does for an inter luma TU
@@ -181,7 +195,7 @@ extern "C" int x265b200_tu_forward_batch(x265b200_ctx* ctx, int N, const void* f
     if (!fenc || !pred || !offF || !offP || !quantCoeff || !qCoef || !numSig)
         return fail(ctx, X265B200_ERR_ARG, "tu_forward: only sseZero may be NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->dct_path != 1 && launch_tu_forward(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, qCoef, numSig, sseZero, st))
+    if (ctx->dct_path != 1 && launch_tu_forward(ctx, N, fenc, strideF, pred, strideP, offF, offP, n, quantCoeff, qBits, add, qCoef, numSig, sseZero, st, 0))
         return X265B200_OK;
     if (cudaGetLastError() != cudaSuccess) return fail(ctx, X265B200_ERR_CUDA, "tu_forward fused launch");
     // validation twin / unaligned operands: the stage kernels over chunks whose scratch stays L2-resident

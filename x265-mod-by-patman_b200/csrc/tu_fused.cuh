@@ -565,11 +565,11 @@ __global__ void __launch_bounds__(128)
 tu_fwd_small_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred, intptr_t sp,
                     const int32_t* __restrict__ offF, const int32_t* __restrict__ offP, int n,
                     const int32_t* __restrict__ quantCoeff, QuantP P, int shift1, int shift2,
-                    int16_t* __restrict__ qCoef, uint32_t* __restrict__ numSig, unsigned long long* __restrict__ sseZero)
+                    int16_t* __restrict__ qCoef, uint32_t* __restrict__ numSig, unsigned long long* __restrict__ sseZero, int kind)
 {
     constexpr int TPG = SMALL == 8 ? 2 : 8;
     constexpr int NN = SMALL * SMALL;
-    // lane = 4g + t.  loads: N = 8 TU t>>1 (lane bits 0,2,3,4 vary inside the TU), N = 4 TU (g>>2)*4 + t (bits 2,3 vary).
+    // kind 1 (SMALL == 4 only): DST-VII instead of the DCT (intra luma 4x4 TUs).  lane = 4g + t.  loads: N = 8 TU t>>1 (lane bits 0,2,3,4 vary inside the TU), N = 4 TU (g>>2)*4 + t (bits 2,3 vary).
     // stores after pair_to_quad: N = 8 TU t&1 (bits 1,2,3,4 vary), N = 4 TU 4(t&1) + (t>>1) + 2(g>>2) (bits 2,3 vary).
     constexpr int LD_MASK = SMALL == 8 ? 0x1d : 0x0c;
     constexpr int ST_MASK = SMALL == 8 ? 0x1e : 0x0c;
@@ -579,7 +579,7 @@ tu_fwd_small_kernel(const T* __restrict__ fenc, intptr_t sf, const T* __restrict
     int ngroups = (n + TPG * UN - 1) / (TPG * UN);
     if (warp >= ngroups) return;
     int g = lane >> 2, t = lane & 3;
-    const uint32_t (*A)[2][32] = SMALL == 8 ? c_A8 : c_A4[0];
+    const uint32_t (*A)[2][32] = SMALL == 8 ? c_A8 : c_A4[kind];
     uint32_t a1[2] = { A[0][0][lane], A[0][1][lane] };
     uint32_t a2[2] = { A[1][0][lane], A[1][1][lane] };
     const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
@@ -644,11 +644,11 @@ tu_inv_small_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restric
                     const T* __restrict__ fenc, intptr_t sf, const T* __restrict__ pred, intptr_t sp,
                     const int32_t* __restrict__ offF, const int32_t* __restrict__ offP,
                     T* __restrict__ recon, intptr_t sr, const int32_t* __restrict__ offR,
-                    unsigned long long* __restrict__ sseRecon, int shift1, int shift2, int depth)
+                    unsigned long long* __restrict__ sseRecon, int shift1, int shift2, int depth, int kind)
 {
     constexpr int TPG = SMALL == 8 ? 2 : 8;
     constexpr int NN = SMALL * SMALL;
-    // outputs after pair_to_quad: N = 8 TU t&1, row g, columns 4(t>>1)..+3 (lane bits 1,2,3,4 vary inside the TU);
+    // kind 1 (SMALL == 4 only): inverse DST-VII, and no DC-only shortcut (quant.cpp:585-588).  outputs after pair_to_quad: N = 8 TU t&1, row g, columns 4(t>>1)..+3 (lane bits 1,2,3,4 vary inside the TU);
     // N = 4 TU (t>>1)*4 + (g>>2) + 2(t&1), row g&3 (bits 2,3 vary)
     constexpr int ST_MASK = SMALL == 8 ? 0x1e : 0x0c;
     int lane = threadIdx.x & 31;
@@ -659,7 +659,7 @@ tu_inv_small_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restric
     int g = lane >> 2, t = lane & 3;
     uint32_t a1[2], b2;
     if (SMALL == 8) { a1[0] = c_IA8[0][lane]; a1[1] = c_IA8[1][lane]; b2 = c_IB8[lane]; }
-    else { a1[0] = c_IA4[0][0][lane]; a1[1] = c_IA4[0][1][lane]; b2 = c_IB4[0][lane]; }
+    else { a1[0] = c_IA4[kind][0][lane]; a1[1] = c_IA4[kind][1][lane]; b2 = c_IB4[kind][lane]; }
     const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
     const uint32_t mx = (uint32_t)((1 << depth) - 1) * 0x10001u, negmx = (uint32_t)(-((1 << depth) - 1) & 0xffff) * 0x10001u;
     const int ld_tu = SMALL == 8 ? (t >> 1) : ((g >> 2) * 4 + t);
@@ -710,7 +710,7 @@ tu_inv_small_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restric
             {
                 uint32_t ns = numSig[tu];
                 int q0 = qCoef[(size_t)tu * NN];
-                if (ns == 1 && q0 != 0)
+                if (ns == 1 && q0 != 0 && !kind)
                 {
                     int dcv = dc_fill_value(dequant_one(q0, P), depth);
                     quad = make_uint2(pack2(dcv, dcv), pack2(dcv, dcv));
@@ -728,7 +728,7 @@ tu_inv_small_kernel(const int16_t* __restrict__ qCoef, const uint32_t* __restric
 template<typename T>
 static void launch_tu_fwd(int sms, int N, const T* fenc, intptr_t sf, const T* pred, intptr_t sp, const int32_t* offF, const int32_t* offP, int n,
                           const int32_t* quantCoeff, QuantP P, int shift1, int shift2, int16_t* qCoef, uint32_t* numSig,
-                          unsigned long long* sseZero, cudaStream_t st)
+                          unsigned long long* sseZero, cudaStream_t st, int dst4)
 {
     int grid;
     if (N == 32)
@@ -750,21 +750,21 @@ static void launch_tu_fwd(int sms, int N, const T* fenc, intptr_t sf, const T* p
         int need = ceil_div(ceil_div(n, 2 * 4), 4);
         grid = PGRID((tu_fwd_small_kernel<T, 8, 4>));
         if (grid > need) grid = need;
-        tu_fwd_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
+        tu_fwd_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero, 0);
     }
     else
     {
         int need = ceil_div(ceil_div(n, 8 * 4), 4);
         grid = PGRID((tu_fwd_small_kernel<T, 4, 4>));
         if (grid > need) grid = need;
-        tu_fwd_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero);
+        tu_fwd_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(fenc, sf, pred, sp, offF, offP, n, quantCoeff, P, shift1, shift2, qCoef, numSig, sseZero, dst4 ? 1 : 0);
     }
 }
 
 template<typename T>
 static void launch_tu_inv(int sms, int N, const int16_t* qCoef, const uint32_t* numSig, int n, QuantP P, const T* fenc, intptr_t sf,
                           const T* pred, intptr_t sp, const int32_t* offF, const int32_t* offP, T* recon, intptr_t sr, const int32_t* offR,
-                          unsigned long long* sseRecon, int shift1, int shift2, int depth, cudaStream_t st)
+                          unsigned long long* sseRecon, int shift1, int shift2, int depth, cudaStream_t st, int dst4)
 {
     int grid;
     if (N == 32)
@@ -785,14 +785,14 @@ static void launch_tu_inv(int sms, int N, const int16_t* qCoef, const uint32_t* 
         int need = ceil_div(ceil_div(n, 2 * 4), 4);
         grid = PGRID((tu_inv_small_kernel<T, 8, 4>));
         if (grid > need) grid = need;
-        tu_inv_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
+        tu_inv_small_kernel<T, 8, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth, 0);
     }
     else
     {
         int need = ceil_div(ceil_div(n, 8 * 4), 4);
         grid = PGRID((tu_inv_small_kernel<T, 4, 4>));
         if (grid > need) grid = need;
-        tu_inv_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth);
+        tu_inv_small_kernel<T, 4, 4><<<grid, 128, 0, st>>>(qCoef, numSig, n, P, fenc, sf, pred, sp, offF, offP, recon, sr, offR, sseRecon, shift1, shift2, depth, dst4 ? 1 : 0);
     }
 }
 
@@ -801,7 +801,7 @@ static void launch_tu_inv(int sms, int N, const int16_t* qCoef, const uint32_t* 
 bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                      const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
                      int dqScale, int dqShift, int16_t* qCoef, uint32_t* numSig, void* recon, intptr_t sr,
-                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st)
+                     const int32_t* offR, uint64_t* sseZero, uint64_t* sseRecon, cudaStream_t st, int dst4)
 {
     if (((uintptr_t)qCoef & 7) || ((uintptr_t)quantCoeff & 15) || ((sf | sp) & 3)) return false;
     int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
@@ -811,16 +811,16 @@ bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, co
     if (ctx->pixbytes == 1)
     {
         launch_tu_fwd<uint8_t>(sms, N, (const uint8_t*)fenc, sf, (const uint8_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
-                               (unsigned long long*)sseZero, st);
+                               (unsigned long long*)sseZero, st, dst4);
         launch_tu_inv<uint8_t>(sms, N, qCoef, numSig, n, P, (const uint8_t*)fenc, sf, (const uint8_t*)pred, sp, offF, offP, (uint8_t*)recon, sr, offR,
-                               (unsigned long long*)sseRecon, 7, 12 - d8, ctx->depth, st);
+                               (unsigned long long*)sseRecon, 7, 12 - d8, ctx->depth, st, dst4);
     }
     else
     {
         launch_tu_fwd<uint16_t>(sms, N, (const uint16_t*)fenc, sf, (const uint16_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
-                                (unsigned long long*)sseZero, st);
+                                (unsigned long long*)sseZero, st, dst4);
         launch_tu_inv<uint16_t>(sms, N, qCoef, numSig, n, P, (const uint16_t*)fenc, sf, (const uint16_t*)pred, sp, offF, offP, (uint16_t*)recon, sr, offR,
-                                (unsigned long long*)sseRecon, 7, 12 - d8, ctx->depth, st);
+                                (unsigned long long*)sseRecon, 7, 12 - d8, ctx->depth, st, dst4);
     }
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess;
@@ -828,7 +828,7 @@ bool launch_tu_fused(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, co
 // forward half alone: residual + DCT + quant -> qCoef / numSig (/ sseZero); same preconditions as launch_tu_fused
 bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, const void* pred, intptr_t sp,
                        const int32_t* offF, const int32_t* offP, int n, const int32_t* quantCoeff, int qBits, int qAdd,
-                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st)
+                       int16_t* qCoef, uint32_t* numSig, uint64_t* sseZero, cudaStream_t st, int dst4)
 {
     if (((uintptr_t)qCoef & 7) || ((uintptr_t)quantCoeff & 15) || ((sf | sp) & 3)) return false;
     int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
@@ -837,10 +837,10 @@ bool launch_tu_forward(x265b200_ctx* ctx, int N, const void* fenc, intptr_t sf, 
     QuantP P; P.qBits = qBits; P.qAdd = qAdd; P.dqScale = 0; P.dqAdd = 0; P.dqShift = 1;
     if (ctx->pixbytes == 1)
         launch_tu_fwd<uint8_t>(sms, N, (const uint8_t*)fenc, sf, (const uint8_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
-                               (unsigned long long*)sseZero, st);
+                               (unsigned long long*)sseZero, st, dst4);
     else
         launch_tu_fwd<uint16_t>(sms, N, (const uint16_t*)fenc, sf, (const uint16_t*)pred, sp, offF, offP, n, quantCoeff, P, lg - 1 + d8, lg + 6, qCoef, numSig,
-                                (unsigned long long*)sseZero, st);
+                                (unsigned long long*)sseZero, st, dst4);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess;
 }
