@@ -522,7 +522,7 @@ def run_b200_arm(args):
     enc = encoder_fps(args) if world == 1 else None
     if enc:
         cb["encoder_fps"] = enc
-    satd_kernel = ("cu_satd_kernel<uint16, 64/32/16/8> (csrc/tile_kernels.cuh): 2Nx2N + 2NxN + Nx2N PUs of every CU in one launch, fenc read once" if fused
+    satd_kernel = ("cu_satd_mma_kernel<64/32> (f16 tensor-core Hadamard) + cu_satd_kernel<uint16, 16/8> (csrc/tile_kernels.cuh): 2Nx2N + 2NxN + Nx2N PUs of every CU in one launch, fenc read once" if fused
                    else "tile4_fast_kernel<uint16,SATD> (10 shapes) + strip8_fast_kernel<SATD> (8x4, 16x8) (csrc/tile_kernels.cuh)")
     roofline = {"bound": "hbm", "kernel": satd_kernel if dominant == "satd" else "dct*_imma_kernel (csrc/transform_mma.cu)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -533,6 +533,11 @@ def run_b200_arm(args):
                 "share_of_step": tsum[dominant] / (ms if world == 1 else sum(tsum.values())),
                 "other": {"satd_mode": args.satd_mode, "satd_launches_per_step": satd_launches, "shape_passes_per_satd_launch": len(SATD_SHAPES) // satd_launches,
                           "satd_GBps": satd_bytes / (satd_ms * 1e-3) / 1e9, "dct_GBps": dct_bytes / (dct_ms * 1e-3) / 1e9,
+                          "satd_frac_of_dram_floor": (samples * 2 * 2 / (satd_ms * 1e-3) / 1e9 / peak) if fused else None,
+                          "dram_floor_note": ("the least DRAM traffic a fused launch can have is both planes once (2 * b bytes per CU sample): the three reference "
+                                              "reads of a CU overlap in L2, so `traffic` is near that floor and below the algorithmic bytes") if fused else None,
+                          "limiter": ("ncu (profiles/r3_cu_satd_ncu_summary.txt): 64 / 32 wide: latency at 16 warps per SM, ALU pipe 51 %, L1 data pipe 70 %; "
+                                      "16 / 8 wide: L1 data pipe 89 / 91 % (one wavefront per 8-byte row of a displaced block), L2 sectors 3x the algorithmic bytes at 8 wide") if fused else None,
                           "satd_gpix_s": samples * (len(SATD_SHAPES) // satd_launches) / (satd_ms * 1e-3) / 1e9, "dct_gcoef_s": samples / (dct_ms * 1e-3) / 1e9,
                           "per_launch_ms_diagnostic_pass": {"%s_%s" % (k[0], "x".join(map(str, k[1])) if isinstance(k[1], tuple) else k[1]): sum(v) / len(v)
                                                               for k, v in per.items()},

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--depth", type=int, default=10)
     ap.add_argument("--merange", type=int, default=57)
     ap.add_argument("--subme", type=int, default=2)
-    ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 3 STAR, 5 FULL")
+    ap.add_argument("--methods", default="5,1", help="search methods for the whole-chain timing: 0 DIA, 1 HEX, 2 UMH, 3 STAR, 4 SEA, 5 FULL")
     ap.add_argument("--shapes", default="64,32,16,8", help="square PU sizes to run")
     ap.add_argument("--bidir", action="store_true", help="also time the bi-prediction cost entry")
     ap.add_argument("--lowres", action="store_true", help="also time the lookahead's lowres search")
@@ -48,6 +48,7 @@ def main():
     dtab = torch.from_numpy(tab.view(np.int16)).cuda()
     sm_clock = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 0
     rows = []
+    sums, integral_ms = None, None
     for (w, h) in [(int(v), int(v)) for v in args.shapes.split(",")]:
         oa, _ = tile_blocks(geo, w, h, seed=1)
         n = oa.size
@@ -78,21 +79,40 @@ def main():
         oq = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); oc = torch.zeros((n,), dtype=torch.int32, device="cuda")
 
         for method in [int(v) for v in args.methods.split(",")]:
+            if method == 4 and (w, h) in ((32, 8), (8, 32), (8, 4), (4, 8)):
+                continue
+            if method == 4 and sums is None:
+                # successive elimination reads the twelve integral planes of the reference picture (framefilter.cpp:737-833); built once, timed
+                pitch = geo.plane_elems
+                sums = torch.empty(12 * pitch, dtype=torch.int32, device="cuda")
+                ctx.me_integral_batch(B, geo.stride, geo.rows, 1, sums, pitch); torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); ctx.me_integral_batch(B, geo.stride, geo.rows, 1, sums, pitch); e1.record(); e1.synchronize()
+                integral_ms = e0.elapsed_time(e1)
+
             def run_me():
-                ctx.motion_estimate_batch(method, w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc,
-                                          dtab.data_ptr() + 2 * RAD, oq, oc)
+                if method == 4:
+                    ctx.motion_estimate_sea_batch(w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc,
+                                                  dtab.data_ptr() + 2 * RAD, sums, geo.plane_elems, oq, oc)
+                else:
+                    ctx.motion_estimate_batch(method, w, h, M, args.subme, A, geo.stride, B, geo.stride, d[0], d[0], d[1], qmvp, 2, mvc,
+                                              dtab.data_ptr() + 2 * RAD, oq, oc)
             run_me(); torch.cuda.synchronize()
             ts = []
             for _ in range(3):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(); run_me(); e1.record(); e1.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            name = {0: "dia", 1: "hex", 3: "star", 5: "full"}[method]
+            name = {0: "dia", 1: "hex", 2: "umh", 3: "star", 4: "sea", 5: "full"}[method]
             row["motion_estimate_%s_ms_per_frame" % name] = sorted(ts)[1]
+            if method == 4:
+                row["sea_integral_planes_ms_per_reference_picture"] = integral_ms
             if refl:
                 # the reference's own MotionEstimate::motionEstimate on every host core, on a sample of the same PUs
-                k = min(n, 400 if method == 5 else 40000)
+                k = min(n, 400 if method == 5 else 4000 if method == 4 else 40000)
                 if method == 5: k = max(8, min(k, int(4e9 / (cands / n * w * h))))
+                if method == 4:
+                    continue                                 # the reference's SEA needs its own integral planes: pinned in the CPU suite, not timed here
                 sel = np.linspace(0, n - 1, k).astype(np.int64)
                 hq = qmvp.cpu().numpy()[sel].copy(); hm = mvc.cpu().numpy()[sel].copy()
                 so = oa[sel].astype(np.int32)

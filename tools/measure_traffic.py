@@ -70,7 +70,7 @@ def under_ncu(F, fused=False):
     nl = 4 if fused else len(SATD_SHAPES)
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["CUDA_VISIBLE_DEVICES"] = env.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
-    cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "--kernel-name", "regex:.*(tile4_fast_kernel|strip8_fast_kernel|cu_satd_kernel).*",
+    cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "--kernel-name", "regex:.*(tile4_fast_kernel|strip8_fast_kernel|cu_satd_kernel|cu_satd_mma_kernel).*",
            "--launch-skip", str(nl), "--launch-count", str(nl),
            sys.executable, os.path.abspath(__file__), "--frames", str(F)] + (["--fused"] if fused else [])
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=400)

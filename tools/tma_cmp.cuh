@@ -1,5 +1,5 @@
-// tma_cmp.cuh -- SAD / SATD / SSE over pixel planes with the blocks staged in shared memory by TMA
-// (cp.async.bulk.tensor.2d -> SASS UTMALDG), shared by pixel.cu and the tuning lab tools/satd_lab.cu.
+// tma_cmp.cuh (lab tool, not part of the library) -- SAD / SATD / SSE over pixel planes with the blocks staged in shared memory by TMA
+// (cp.async.bulk.tensor.2d -> SASS UTMALDG), used by the tuning lab tools/satd_lab.cu and tools/tma_probe.cu only (TMA box origins must be 16-byte aligned, reference blocks are not).
 //
 // Why: a reference block sits at an arbitrary motion-vector offset, so a register-path kernel has to
 // fetch the aligned superset of every row and realign it with funnel shifts, and the bytes it keeps in

@@ -1,4 +1,4 @@
-// tma_probe.cu -- isolates the TMA box-load mechanics used by csrc/tma_cmp.cuh (one experiment per process).
+// tma_probe.cu -- isolates the TMA box-load mechanics used by tools/tma_cmp.cuh (one experiment per process).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I x265-mod-by-patman_b200/csrc tools/tma_probe.cu -o tools/tma_probe
 // mode bits: 1 mbarrier_init fence, 2 proxy fence, 4 exact row count in the map, 8 descriptor in global memory,
 //            16 aligned coordinates (64, 32), 32 int32 elements, 64 libcu++ barrier + cp_async_bulk_tensor wrappers, 128 static smem

@@ -184,7 +184,7 @@ __device__ __forceinline__ int intra_ref_n(const uint16_t* s, int N, int hor, in
     const int k = -2 - i;
     return intra_nb_n(s, N, hor, 2 * N + ((128 + (k + 1) * c_intraInvAngle[-angleOffset - 1]) >> 8));
 }
-__device__ int intra_px_n(const uint16_t* s, int N, int lgN, int mode, int bFilter, int dc, int r, int c, int pmax)
+__device__ __forceinline__ int intra_px_n(const uint16_t* s, int N, int lgN, int mode, int bFilter, int dc, int r, int c, int pmax)
 {
     if (mode == 0)
         return ((N - 1 - c) * s[2 * N + 1 + r] + (N - 1 - r) * s[1 + c] + (c + 1) * s[1 + N] + (r + 1) * s[3 * N + 1] + N) >> (lgN + 1);
@@ -236,11 +236,17 @@ intra_pred_all_kernel(const PIX* __restrict__ neighbours, int N, int lgN, int pm
     __syncthreads();
     const int bFilter = N <= 16, NN = N * N;
     PIX* out = dst + (size_t)tu * 35 * NN;
-    for (int o = threadIdx.x; o < 35 * NN; o += blockDim.x)
+    // a thread forms four horizontally adjacent samples of one (mode, row) and stores them as one word pair: the mode's set-up (filter flag,
+    // angle, neighbour array) is shared by the four, and a warp writes 256 (128) contiguous bytes instead of 64 (32)
+    for (int o4 = threadIdx.x; o4 < 35 * NN / 4; o4 += blockDim.x)
     {
-        const int mode = o >> (2 * lgN), rc = o & (NN - 1), r = rc >> lgN, c = rc & (N - 1);
+        const int o = o4 << 2, mode = o >> (2 * lgN), rc = o & (NN - 1), r = rc >> lgN, c = rc & (N - 1);
         const uint16_t* src = mode == 1 ? s : mode == 0 ? (N >= 8 ? f : s) : ((c_intraFilterFlags[mode] & N) ? f : s);
-        out[o] = (PIX)intra_px_n(src, N, lgN, mode, bFilter, dc, r, c, pmax);
+        int v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = intra_px_n(src, N, lgN, mode, bFilter, dc, r, c + i, pmax);
+        if (sizeof(PIX) == 2) *(uint2*)(out + o) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+        else *(uint32_t*)(out + o) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
     }
 }
 
@@ -334,8 +340,10 @@ extern "C" int x265b200_intra_pred_batch(x265b200_ctx* ctx, int N, const void* n
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int lgN = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5, pmax = (1 << ctx->depth) - 1;
-    if (ctx->pixbytes == 1) intra_pred_all_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t*)neighbours, N, lgN, pmax, (uint8_t*)dst);
-    else intra_pred_all_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t*)neighbours, N, lgN, pmax, (uint16_t*)dst);
+    if (((uintptr_t)dst & 7)) return fail(ctx, X265B200_ERR_ARG, "intra_pred: dst must be 8-byte aligned");
+    const int threads = N == 4 ? 160 : 256;                 // 35 * N * N / 4 four-sample groups per TU: 140 at N = 4
+    if (ctx->pixbytes == 1) intra_pred_all_kernel<uint8_t><<<n, threads, 0, st>>>((const uint8_t*)neighbours, N, lgN, pmax, (uint8_t*)dst);
+    else intra_pred_all_kernel<uint16_t><<<n, threads, 0, st>>>((const uint16_t*)neighbours, N, lgN, pmax, (uint16_t*)dst);
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }
