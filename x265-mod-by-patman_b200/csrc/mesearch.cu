@@ -563,8 +563,11 @@ __device__ bool umh_search(const PatternPU<PIX>& P, int& merange, int pmvx, int 
     return P.inside(u.x, u.y);
 }
 
-template<typename PIX>
-__global__ void __launch_bounds__(MP_WARPS * 32)
+// WPC warps (= PUs) per CTA.  A CTA lives as long as its longest walk: one warp per CTA lets every finished walk give its slot back at once,
+// which is what the uneven multi-hexagon search on small PUs needs (8x8: 5.1 -> 1.25 ms per 2160p frame); the other methods are a few
+// per cent faster with four (profiles/r3_motion_search_10bit.json).
+template<typename PIX, int WPC>
+__global__ void __launch_bounds__(WPC * 32)
 me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
                   const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
                   const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int n, int w, int h,
@@ -572,7 +575,7 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
 {
     extern __shared__ __align__(16) uint8_t mp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pu = blockIdx.x * MP_WARPS + warp;
+    const int pu = blockIdx.x * WPC + warp;
     if (pu >= n) return;                                        // whole warps leave; only __syncwarp below
     const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
     if (maxx < minx || maxy < miny) return;
@@ -796,13 +799,13 @@ int launch_me_pattern(x265b200_ctx* ctx, int method, int w, int h, int merange, 
 {
     if (n == 0) return X265B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)MP_WARPS * w * h * ctx->pixbytes;
-    if (ctx->pixbytes == 1)
-        me_pattern_kernel<uint8_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR,
-                                                                                     offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc);
-    else
-        me_pattern_kernel<uint16_t><<<ceil_div(n, MP_WARPS), MP_WARPS * 32, smem, st>>>(method, merange, (const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR,
-                                                                                      offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc);
+    const int wpc = (method == X265B200_ME_UMH && w * h < 256) ? 1 : MP_WARPS;
+    const size_t smem = (size_t)wpc * w * h * ctx->pixbytes;
+#define MPK(PIX, WPC) me_pattern_kernel<PIX, WPC><<<ceil_div(n, WPC), WPC * 32, smem, st>>>(method, merange, (const PIX*)fenc, strideF, (const PIX*)ref, strideR, \
+                                                                                 offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc)
+    if (ctx->pixbytes == 1) { if (wpc == 1) MPK(uint8_t, 1); else MPK(uint8_t, MP_WARPS); }
+    else { if (wpc == 1) MPK(uint16_t, 1); else MPK(uint16_t, MP_WARPS); }
+#undef MPK
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
 }
