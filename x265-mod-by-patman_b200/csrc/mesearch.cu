@@ -349,27 +349,36 @@ __device__ void star_two_point(const PatternPU<PIX>& P, StarBest& b)
         if (ok[k] && cost[k] < b.cost) { b.cost = cost[k]; b.x = cand[k][0]; b.y = cand[k][1]; }
 }
 
-// X265_STAR_SEARCH, motion.cpp:1327-1435
+// X265_STAR_SEARCH, motion.cpp:1327-1435.  phase 0: the whole search in this warp.  The stride-5 raster pass some PUs take (first pattern
+// ended more than 5 away) is ~530 candidates: in one warp it lasts longer than every other walk of the launch together, so the library
+// splits the search around it -- phase 1 stops at the raster decision (returns true, x / y / best = the state before it), the raster runs
+// as its own CTA-per-PU kernel (me_star_raster_kernel), phase 2 resumes with the re-centred passes.
 template<typename PIX>
-__device__ void star_search(const PatternPU<PIX>& P, int merange, int& x, int& y, int& best)
+__device__ bool star_search(const PatternPU<PIX>& P, int merange, int& x, int& y, int& best, int phase)
 {
     StarBest b = { x, y, best, 0, 0 };
-    star_pattern(P, b, 3, merange);
     bool done = false;
-    if (b.dist == 1)
+    if (phase != 2)
     {
-        if (!b.point) done = true;
-        else
+        star_pattern(P, b, 3, merange);
+        if (b.dist == 1)
         {
-            const int saved = b.cost;
-            star_two_point(P, b);
-            done = b.cost == saved;
+            if (!b.point) done = true;
+            else
+            {
+                const int saved = b.cost;
+                star_two_point(P, b);
+                done = b.cost == saved;
+            }
         }
     }
+    else b.dist = 6;                                        // only PUs that were due for the raster come back; the loop below resets it
     if (!done)
     {
-        if (b.dist > 5)
-        {   // raster over the window in steps of 5, four columns per pass where the reference uses sad_x4
+        if (phase != 2 && b.dist > 5)
+        {
+            if (phase == 1) { x = b.x; y = b.y; best = b.cost; return true; }
+            // raster over the window in steps of 5, four columns per pass where the reference uses sad_x4
             int cand[4][2], cost[4]; bool ok[4];
             for (int ty = P.miny; ty <= P.maxy; ty += 5)
                 for (int tx = P.minx; tx <= P.maxx; tx += 5)
@@ -394,6 +403,84 @@ __device__ void star_search(const PatternPU<PIX>& P, int merange, int& x, int& y
         }
     }
     x = b.x; y = b.y; best = b.cost;
+    return false;
+}
+
+// The raster pass of the star search (motion.cpp:1365-1399) for the PUs phase 1 flagged: one CTA per PU, a lane owns one candidate of the
+// stride-5 grid and walks the whole block (fenc from shared memory, the lanes of a warp read reference samples 10 bytes apart: a few cache
+// lines per request).  The reference measures the grid four columns at a time with sad_x4 and charges the fourth candidate of each group
+// mvcost(mv << 3) (:1392); groups run while tx + 15 <= maxx, the rest of a row is single candidates.  Visiting order = raster order of the
+// grid with strict-less updates: carried by the key (cost << 32 | grid index + 1), index 0 being the state before the pass.
+constexpr int RS_WARPS = 8;
+template<typename PIX>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+me_star_raster_kernel(const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
+                      const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
+                      const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int w, int h,
+                      const int32_t* __restrict__ flags, int32_t* __restrict__ bmv, int32_t* __restrict__ bcost)
+{
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    __shared__ unsigned long long red[RS_WARPS];
+    const int pu = blockIdx.x;
+    if (!flags[pu]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
+    PIX* fs = (PIX*)rs_smem;
+    {
+        const PIX* f = fenc + offF[pu];
+        for (int idx = threadIdx.x; idx < w * h; idx += RS_WARPS * 32) fs[idx] = f[(intptr_t)(idx / w) * strideF + idx % w];
+    }
+    __syncthreads();
+    const int ncx = (maxx - minx) / 5 + 1, ncy = (maxy - miny) / 5 + 1;
+    const int grouped = maxx - minx >= 15 ? 4 * ((maxx - minx - 15) / 20 + 1) : 0;      // columns measured as groups of four
+    const uint16_t* cx = costTab - mvp[2 * pu];
+    const uint16_t* cy = costTab - mvp[2 * pu + 1];
+    const PIX* r0 = ref + offR[pu];
+    const int chunks = (ncx + 31) >> 5;
+    unsigned long long best = ~0ull;
+    for (int item = warp; item < ncy * chunks; item += RS_WARPS)
+    {
+        const int j = item / chunks, i = (item - j * chunks) * 32 + lane;
+        const bool live = i < ncx;
+        const int tx = minx + 5 * (live ? i : ncx - 1), ty = miny + 5 * j;
+        const PIX* rp = r0 + (intptr_t)ty * strideR + tx;
+        unsigned acc = 0;
+        for (int yy = 0; yy < h; yy++)
+        {
+            const PIX* rr = rp + (intptr_t)yy * strideR;
+            const PIX* ff = fs + yy * w;
+#pragma unroll 4
+            for (int xx = 0; xx < w; xx++) acc = __usad((unsigned)ff[xx], (unsigned)rr[xx], acc);
+        }
+        if (live)
+        {
+            const int sh = (i < grouped && (i & 3) == 3) ? 3 : 2;
+            const unsigned cost = acc + (unsigned)(uint16_t)((int)cx[tx << sh] + (int)cy[ty << sh]);
+            const unsigned long long key = ((unsigned long long)cost << 32) | (unsigned)(j * ncx + i + 1);
+            best = key < best ? key : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) red[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 1; k < RS_WARPS; k++) best = red[k] < best ? red[k] : best;
+        const long long cost = (long long)(best >> 32);
+        if (best != ~0ull && cost < (long long)bcost[pu])
+        {
+            const int idx = (int)((unsigned)best - 1u);
+            bcost[pu] = (int32_t)cost;
+            bmv[2 * pu] = minx + 5 * (idx % ncx);
+            bmv[2 * pu + 1] = miny + 5 * (idx / ncx);
+        }
+    }
 }
 
 // X265_HEX_SEARCH, motion.cpp:1041-1138: the six corners around the start (hex2[1..6] order), the walk, the square refinement
@@ -571,12 +658,14 @@ __global__ void __launch_bounds__(WPC * 32)
 me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
                   const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, const int32_t* __restrict__ range,
                   const int32_t* __restrict__ mvp, const uint16_t* __restrict__ costTab, int n, int w, int h,
-                  int32_t* __restrict__ bmv, int32_t* __restrict__ bcost, int numCand, const int32_t* __restrict__ mvc)
+                  int32_t* __restrict__ bmv, int32_t* __restrict__ bcost, int numCand, const int32_t* __restrict__ mvc,
+                  int phase, int32_t* __restrict__ flags)
 {
     extern __shared__ __align__(16) uint8_t mp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pu = blockIdx.x * WPC + warp;
     if (pu >= n) return;                                        // whole warps leave; only __syncwarp below
+    if (phase == 2 && !flags[pu]) return;                       // star search, second half: only the PUs that took the raster pass
     const int minx = range[4 * pu], miny = range[4 * pu + 1], maxx = range[4 * pu + 2], maxy = range[4 * pu + 3];
     if (maxx < minx || maxy < miny) return;
     PIX* fs = (PIX*)mp_smem + (size_t)warp * w * h;
@@ -600,7 +689,11 @@ me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_
     int cand[4][2] = { {0, 0}, {0, 0}, {0, 0}, {0, 0} }, cost[4]; bool ok[4] = { false, false, false, false };
     auto in_range = [&](int cx, int cy) { return cx >= minx && cx <= maxx && cy >= miny && cy <= maxy; };
 
-    if (method == X265B200_ME_STAR) star_search(P, merange, x, y, best);
+    if (method == X265B200_ME_STAR)
+    {
+        const bool raster = star_search(P, merange, x, y, best, phase);
+        if (phase == 1 && lane == 0) flags[pu] = raster;
+    }
     else if (method == 0)
     {   // diamond, radius 1: up, down, left, right
         int i = merange;
@@ -801,10 +894,32 @@ int launch_me_pattern(x265b200_ctx* ctx, int method, int w, int h, int merange, 
     cudaStream_t st = (cudaStream_t)stream;
     const int wpc = (method == X265B200_ME_UMH && w * h < 256) ? 1 : MP_WARPS;
     const size_t smem = (size_t)wpc * w * h * ctx->pixbytes;
+    int phase = 0;
+    int32_t* flags = nullptr;
 #define MPK(PIX, WPC) me_pattern_kernel<PIX, WPC><<<ceil_div(n, WPC), WPC * 32, smem, st>>>(method, merange, (const PIX*)fenc, strideF, (const PIX*)ref, strideR, \
-                                                                                 offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc)
-    if (ctx->pixbytes == 1) { if (wpc == 1) MPK(uint8_t, 1); else MPK(uint8_t, MP_WARPS); }
-    else { if (wpc == 1) MPK(uint16_t, 1); else MPK(uint16_t, MP_WARPS); }
+                                                                                 offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc, phase, flags)
+#define MPL() do { if (ctx->pixbytes == 1) { if (wpc == 1) MPK(uint8_t, 1); else MPK(uint8_t, MP_WARPS); } \
+                   else { if (wpc == 1) MPK(uint16_t, 1); else MPK(uint16_t, MP_WARPS); } } while (0)
+    if (method == X265B200_ME_STAR && !lab_knob(6, 0))
+    {   // star search split around its raster pass: pattern kernel up to the decision, CTA-per-PU raster for the PUs that take it, pattern kernel again
+        B200_CUDA(ctx, cudaMallocAsync((void**)&flags, (size_t)n * sizeof(int32_t), st));
+        B200_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)n * sizeof(int32_t), st));
+        phase = 1;
+        MPL();
+        if (ctx->pixbytes == 1)
+            me_star_raster_kernel<uint8_t><<<n, RS_WARPS * 32, (size_t)w * h, st>>>((const uint8_t*)fenc, strideF, (const uint8_t*)ref, strideR, offF, offR, range, mvp, costTab,
+                                                                                 w, h, flags, bmv, bcost);
+        else
+            me_star_raster_kernel<uint16_t><<<n, RS_WARPS * 32, (size_t)w * h * 2, st>>>((const uint16_t*)fenc, strideF, (const uint16_t*)ref, strideR, offF, offR, range, mvp, costTab,
+                                                                                      w, h, flags, bmv, bcost);
+        phase = 2;
+        MPL();
+        ctx->launches.fetch_add(2, std::memory_order_relaxed);
+        cudaFreeAsync(flags, st);
+    }
+    else
+        MPL();
+#undef MPL
 #undef MPK
     B200_LAUNCH_CHECK(ctx);
     return X265B200_OK;
