@@ -339,6 +339,32 @@ quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__
             if (blk0 + j >= n) break;
             int c[8] = { (int16_t)(cv[j].x & 0xffff), cv[j].x >> 16, (int16_t)(cv[j].y & 0xffff), cv[j].y >> 16,
                          (int16_t)(cv[j].z & 0xffff), cv[j].z >> 16, (int16_t)(cv[j].w & 0xffff), cv[j].w >> 16 };
+            if (NQUANT)
+            {   // nquant is ALU-pipe bound (about 11 ALU operations per coefficient at 4 bytes per coefficient): the tail runs on packed pairs --
+                // clip3(-32768, 32767, .) of two levels is one cvt.pack.sat, (int16)abs(.) is max(w, -w) per 16-bit lane (-32768 stays 0x8000 as
+                // the cast leaves it), and the non-zero count is taken from the packed result (a level is zero exactly when its output is)
+                uint32_t o[4], nz = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i += 2)
+                {
+                    int x[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                    {
+                        const int m = c[i + e] >> 31;
+                        const int l = (int)((unsigned)abs(c[i + e]) * (unsigned)q[i + e] + (unsigned)add) >> qBits;   // int32 wrap, dct.cpp:702-703
+                        x[e] = (l ^ m) - m;                                                                        // level * sign
+                    }
+                    uint32_t w;
+                    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(w) : "r"(x[1]), "r"(x[0]));
+                    w = __viaddmax_s16x2(~w, 0x00010001u, w);
+                    o[i >> 1] = w;
+                    nz += __vminu2(w, 0x00010001u);
+                }
+                sig[j] += (int)((nz & 0xffffu) + (nz >> 16));
+                *(int4*)(qCoef + (size_t)(blk0 + j) * numCoeff + pos) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                continue;
+            }
             int lv[8], du[8];
 #pragma unroll
             for (int i = 0; i < 8; i++)
