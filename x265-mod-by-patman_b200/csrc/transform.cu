@@ -339,7 +339,7 @@ quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__
             if (blk0 + j >= n) break;
             int c[8] = { (int16_t)(cv[j].x & 0xffff), cv[j].x >> 16, (int16_t)(cv[j].y & 0xffff), cv[j].y >> 16,
                          (int16_t)(cv[j].z & 0xffff), cv[j].z >> 16, (int16_t)(cv[j].w & 0xffff), cv[j].w >> 16 };
-            if (NQUANT)
+            if constexpr (NQUANT)
             {   // nquant is ALU-pipe bound (about 11 ALU operations per coefficient at 4 bytes per coefficient): the tail runs on packed pairs --
                 // clip3(-32768, 32767, .) of two levels is one cvt.pack.sat, (int16)abs(.) is max(w, -w) per 16-bit lane (-32768 stays 0x8000 as
                 // the cast leaves it), and the non-zero count is taken from the packed result (a level is zero exactly when its output is)
@@ -363,8 +363,9 @@ quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__
                 }
                 sig[j] += (int)((nz & 0xffffu) + (nz >> 16));
                 *(int4*)(qCoef + (size_t)(blk0 + j) * numCoeff + pos) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
-                continue;
             }
+            else
+            {
             int lv[8], du[8];
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -377,7 +378,7 @@ quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__
                 sig[j] += level != 0;
                 level = (int)((unsigned)level * (unsigned)sign);
                 level = clip16(level);
-                lv[i] = NQUANT ? abs(level) : level;                                  // nquant: (int16)abs(clip), dct.cpp:711
+                lv[i] = level;
             }
             size_t base = (size_t)(blk0 + j) * numCoeff + pos;
             int4 o;
@@ -388,6 +389,7 @@ quant_multi_kernel(const int16_t* __restrict__ coef, const int32_t* __restrict__
             {
                 *(int4*)(deltaU + base) = make_int4(du[0], du[1], du[2], du[3]);
                 *(int4*)(deltaU + base + 4) = make_int4(du[4], du[5], du[6], du[7]);
+            }
             }
         }
     }
