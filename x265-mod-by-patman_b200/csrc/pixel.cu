@@ -216,7 +216,7 @@ sa8d_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intpt
 // (|value| <= 8 * 4095 < 2^15).  PKH (depth <= 10): the two horizontal stages that pair different words (distance 4
 // and 2) stay packed as well (8 * 1023 * 4 < 2^15), and the last stage, which pairs the two lanes of a word, is folded
 // into the sum of magnitudes: |a + b| + |a - b| = 2 max(|a|, |b|).  Otherwise the horizontal pass runs in int32.
-template<typename T, bool PKH, int MINB = 1>
+template<typename T, bool PKH, int MINB = 1, bool V16 = false>
 __global__ void __launch_bounds__(128, MINB)
 sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
                  const int32_t* __restrict__ offA, const int32_t* __restrict__ offB,
@@ -259,8 +259,16 @@ sa8d_fast_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, 
             for (int half = 0; half < 2; half++)
             {
                 uint32_t wa[4][4], wb[4][4];
-                load_rows8<4>(pa + (intptr_t)(half * 4) * sa, sa, wa);
-                load_rows8<4>(pb + (intptr_t)(half * 4) * sb, sb, wb);
+                if (V16 && sizeof(T) == 2)
+                {   // 16-byte chunk loads (strides % 8 == 0): a row of the tile is one or two requests instead of two or three
+                    load_rows8_v16((const uint16_t*)pa + (intptr_t)(half * 4) * sa, sa, wa);
+                    load_rows8_v16((const uint16_t*)pb + (intptr_t)(half * 4) * sb, sb, wb);
+                }
+                else
+                {
+                    load_rows8<4>(pa + (intptr_t)(half * 4) * sa, sa, wa);
+                    load_rows8<4>(pb + (intptr_t)(half * 4) * sb, sb, wb);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -480,7 +488,9 @@ static int launch_pixelcmp(x265b200_ctx* ctx, int op, int w, int h, const T* A, 
             while (G * 2 * tpl <= tiles && G < 32) G <<= 1;
             if (mode16 && G < 4) G = 4;
             threads = (long long)n * G;
-            if (ctx->depth <= 10 && tiles < 64)
+            if (ctx->depth <= 10 && tiles < 64 && !((sa | sb) & 7) && lab_knob(0, 0))
+                sa8d_fast_kernel<T, true, 8, true><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
+            else if (ctx->depth <= 10 && tiles < 64)
                 sa8d_fast_kernel<T, true, 8><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
             else if (ctx->depth <= 10)
                 sa8d_fast_kernel<T, true><<<ceil_div(threads, 128), 128, 0, st>>>(A, sa, B, sb, offA, offB, n, w, h, G, mode16, (int32_t*)out);
