@@ -44,7 +44,7 @@ def main():
         qmvp = torch.from_numpy(rng.integers(-60, 61, (n, 2)).astype(np.int32)).cuda()
         mvc = torch.from_numpy(rng.integers(-200, 201, (n, 3, 2)).astype(np.int32)).cuda()
         oq = torch.zeros((n, 2), dtype=torch.int32, device="cuda"); oc = torch.zeros(n, dtype=torch.int32, device="cuda")
-        for method in (pkg.ME_FULL, pkg.ME_HEX, pkg.ME_DIA, pkg.ME_STAR):
+        for method in (pkg.ME_FULL, pkg.ME_HEX, pkg.ME_DIA, pkg.ME_STAR, pkg.ME_UMH):
             for subme in (0, 2, 7):
                 ctx.motion_estimate_batch(method, w, h, m if method != pkg.ME_STAR else 64, subme, F, geo.stride, R, geo.stride, off, off, dwin, qmvp,
                                           3, mvc, dtab.data_ptr() + 2 * RAD, oq, oc)
