@@ -58,6 +58,7 @@ int main(int argc, char** argv)
                     uint64_t r = splitmix(oa.size() * 31 + w * 7 + h);
                     int mvx = (int)(r % 115) - 57, mvy = (int)((r >> 20) % 115) - 57;
                     int rx = x + mvx, ry = y + mvy;
+                    if (argc > 3) rx &= ~7;                      // lab: 16-byte aligned reference blocks, the only ones a TMA box can start at
                     if (rx < -mx + 8) rx = -mx + 8; if (rx > W + mx - w - 8) rx = W + mx - w - 8;
                     if (ry < -my + 8) ry = -my + 8; if (ry > H + my - h - 8) ry = H + my - h - 8;
                     oa.push_back((int32_t)(f * pe + (size_t)(my + y) * stride + mx + x));
