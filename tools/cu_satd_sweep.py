@@ -7,11 +7,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from frames import Geometry, cu_descriptors, make_plane, tile_blocks
 pkg = importlib.import_module("x265-mod-by-patman_b200")
-ctx = pkg.Context(10, 0)
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+ctx = pkg.Context(D, 0)
 F = 32
 geo = Geometry(3840, 2160); pe = geo.plane_elems
-A = torch.from_numpy(make_plane(geo, 10, 1, "natural").view(np.int16)).cuda().repeat(F)
-B = torch.from_numpy(make_plane(geo, 10, 2, "natural").view(np.int16)).cuda().repeat(F)
+vt = np.uint8 if D == 8 else np.int16
+A = torch.from_numpy(make_plane(geo, D, 1, "natural").view(vt)).cuda().repeat(F)
+B = torch.from_numpy(make_plane(geo, D, 2, "natural").view(vt)).cuda().repeat(F)
 for S, Gs in ((8, (1, 2, 4)), (16, (2, 4, 8, 16)), (32, (4, 8, 16, 32)), (64, (8, 16, 32))):
     oF, oR5, _ = cu_descriptors(geo, S, *[tile_blocks(geo, w, h, seed=1) for (w, h) in ((S, S), (S, S // 2), (S // 2, S))])
     a = torch.from_numpy(np.concatenate([oF.astype(np.int64) + f * pe for f in range(F)]).astype(np.int32)).cuda()

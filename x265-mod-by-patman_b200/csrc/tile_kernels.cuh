@@ -268,9 +268,9 @@ __device__ __forceinline__ float hadamard_cols_fold(const float (&r01)[4], const
     return sum;
 }
 
-template<int S>
+template<typename T, int S>
 __global__ void __launch_bounds__(128, 1)                   // (128, 1): 118 registers and all tile loads hoisted; without the 1 ptxas picks 110 and the kernel is 20 % slower
-cu_satd_mma_kernel(const uint16_t* __restrict__ A, intptr_t sa, const uint16_t* __restrict__ B, intptr_t sb,
+cu_satd_mma_kernel(const T* __restrict__ A, intptr_t sa, const T* __restrict__ B, intptr_t sb,
                    const int32_t* __restrict__ offF, const int32_t* __restrict__ offR, int n, int G, int32_t* __restrict__ out)
 {
     constexpr int TW = S >> 2, T4 = TW * TW, HALF = S >> 1;
@@ -296,10 +296,10 @@ cu_satd_mma_kernel(const uint16_t* __restrict__ A, intptr_t sa, const uint16_t* 
         bn[h][0] = bp[h][0] ^ 0x80008000u;
         bn[h][1] = bp[h][1] ^ 0x80008000u;
     }
-    const uint16_t* a = A;
-    const uint16_t* b0 = B;
-    const uint16_t* bH[2] = { B, B };
-    const uint16_t* bV[2] = { B, B };
+    const T* a = A;                                         // 8-bit pictures: load_tile4x4 widens the bytes to the same packed 16-bit pairs
+    const T* b0 = B;
+    const T* bH[2] = { B, B };
+    const T* bV[2] = { B, B };
     if (live)
     {
         const int32_t* r = offR + 5 * (size_t)cu;
