@@ -900,7 +900,7 @@ int launch_me_pattern(x265b200_ctx* ctx, int method, int w, int h, int merange, 
                                                                                  offF, offR, range, mvp, costTab, n, w, h, bmv, bcost, numCand, mvc, phase, flags)
 #define MPL() do { if (ctx->pixbytes == 1) { if (wpc == 1) MPK(uint8_t, 1); else MPK(uint8_t, MP_WARPS); } \
                    else { if (wpc == 1) MPK(uint16_t, 1); else MPK(uint16_t, MP_WARPS); } } while (0)
-    if (method == X265B200_ME_STAR && !lab_knob(6, 0))
+    if (method == X265B200_ME_STAR && !lab_knob(1, 0))
     {   // star search split around its raster pass: pattern kernel up to the decision, CTA-per-PU raster for the PUs that take it, pattern kernel again
         B200_CUDA(ctx, cudaMallocAsync((void**)&flags, (size_t)n * sizeof(int32_t), st));
         B200_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)n * sizeof(int32_t), st));
