@@ -651,8 +651,8 @@ __device__ bool umh_search(const PatternPU<PIX>& P, int& merange, int pmvx, int 
 }
 
 // WPC warps (= PUs) per CTA.  A CTA lives as long as its longest walk: one warp per CTA lets every finished walk give its slot back at once,
-// which is what the uneven multi-hexagon search on small PUs needs (8x8: 5.1 -> 1.25 ms per 2160p frame); the other methods are a few
-// per cent faster with four (profiles/r3_motion_search_10bit.json).
+// a few per cent for the uneven multi-hexagon search on small PUs (8x8: 5.1 -> 4.9 ms per 2160p frame with the reference's cost table); the
+// other methods are a few per cent faster with four (profiles/r3_motion_search_10bit.json).
 template<typename PIX, int WPC>
 __global__ void __launch_bounds__(WPC * 32)
 me_pattern_kernel(int method, int merange, const PIX* __restrict__ fenc, intptr_t strideF, const PIX* __restrict__ ref, intptr_t strideR,
