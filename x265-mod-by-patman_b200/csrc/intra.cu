@@ -123,27 +123,32 @@ lowres_intra_kernel(const PIX* __restrict__ plane, intptr_t stride, int widthInC
     dc /= 2 * IN_N;
     __syncwarp();
 
-    for (int mode = lane; mode < 35; mode += 32)
+    // work item = (mode, 4x4 tile): 140 items over 32 lanes (five passes, the last 12 lanes wide) instead of 35 modes over 32 lanes (two passes
+    // of four tiles each, the second 3 lanes wide); the four tiles of a mode sit in adjacent lanes and meet by two xor shuffles
+    for (int i0 = 0; i0 < 140; i0 += 32)
     {
-        IntraMode m;
-        m.mode = mode; m.dc = dc;
-        m.hor = mode >= 2 && mode < 18;
-        m.angleOffset = mode < 2 ? 0 : (m.hor ? 10 - mode : mode - 26);
-        m.angle = c_intraAngle[8 + m.angleOffset];
-        // DC reads the unfiltered samples, planar the smoothed ones (cuSize >= 8), angular modes follow the flag table
-        m.s = mode == 1 ? s : mode == 0 ? f : ((c_intraFilterFlags[mode] & IN_N) ? f : s);
+        const int item = i0 + lane;
         int sum = 0;
-#pragma unroll 1
-        for (int t = 0; t < 4; t++)
+        if (item < 140)
         {
+            const int mode = item >> 2, t = item & 3;
+            IntraMode m;
+            m.mode = mode; m.dc = dc;
+            m.hor = mode >= 2 && mode < 18;
+            m.angleOffset = mode < 2 ? 0 : (m.hor ? 10 - mode : mode - 26);
+            m.angle = c_intraAngle[8 + m.angleOffset];
+            // DC reads the unfiltered samples, planar the smoothed ones (cuSize >= 8), angular modes follow the flag table
+            m.s = mode == 1 ? s : mode == 0 ? f : ((c_intraFilterFlags[mode] & IN_N) ? f : s);
             const int r0 = (t >> 1) * 4, c0 = (t & 1) * 4;
             int d[16];
 #pragma unroll
             for (int i = 0; i < 16; i++)
                 d[i] = (int)fencS[warp][(r0 + (i >> 2)) * IN_N + c0 + (i & 3)] - m.px(r0 + (i >> 2), c0 + (i & 3), pmax);
-            sum += hadamard4x4_abs(d);
+            sum = hadamard4x4_abs(d);
         }
-        costs[warp][mode] = sum >> 1;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (item < 140 && (lane & 3) == 0) costs[warp][item >> 2] = sum >> 1;
     }
     __syncwarp();
     if (lane == 0)
