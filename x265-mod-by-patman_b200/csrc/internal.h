@@ -66,7 +66,7 @@ int fail(x265b200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSucc
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // tuning lab only: X265B200_LAB="k0,k1,..." selects kernel variants under test; unset = library defaults.
-//   k0: smallest CU width whose per-CU SATD takes the f16 tensor-core kernel (default 32; 0 = never)        csrc/pixel.cu launch_cu_satd
+//   k0: 0 = per-CU SATD of 32 / 64 wide CUs on the packed-integer kernel instead of the f16 tensor-core one      csrc/pixel.cu launch_cu_satd
 //   k1: 1 = star search as ONE pattern kernel (raster pass inside the warp) instead of the three-launch split   csrc/mesearch.cu launch_me_pattern
 inline int lab_knob(int i, int dflt)
 {

@@ -597,17 +597,17 @@ static int launch_cu_satd(x265b200_ctx* ctx, int S, const T* A, intptr_t sa, con
     // 32 and 64 wide CUs of 16-bit pictures up to 10 bits: the horizontal Hadamard as f16 tensor-core MMAs (tile_kernels.cuh cu_satd_mma_kernel),
     // bit-identical: 0.3715 -> 0.3446 ms (64 wide, 16 lanes per CU) and 0.3869 -> 0.3753 ms (32 wide) per 32 frames of 2160p10; at 16 and 8 wide the
     // L1 data pipe (89 / 91 % busy), not the ALU, is the limit and the packed-integer kernel stays ahead.  X265B200_LAB="0" turns it off (lab).
-    const int mmaMin = lab_knob(0, 32);                       // smallest CU width that takes the tensor-core kernel (lab: 0 = off)
-    if (sizeof(T) == 2 && ctx->depth <= 10 && mmaMin && S >= mmaMin && G >= 4)      // 8-bit pictures: measured slower (0.294 vs 0.285 ms at 64 wide)
+    if constexpr (sizeof(T) == 2)                               // 8-bit pictures: measured slower (0.294 vs 0.285 ms at 64 wide), they keep the integer kernel
     {
-        if (!getenv("X265B200_CU_LANES_LAB")) G = S == 64 ? 16 : S == 32 ? 8 : 4;
-        const int gridM = ceil_div((long long)n * G, 128);
-        if (S == 64) cu_satd_mma_kernel<T, 64><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
-        else if (S == 32) cu_satd_mma_kernel<T, 32><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
-        else if (S == 16) cu_satd_mma_kernel<T, 16><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
-        else cu_satd_mma_kernel<T, 8><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
-        B200_LAUNCH_CHECK(ctx);
-        return X265B200_OK;
+        if (ctx->depth <= 10 && S >= 32 && G >= 4 && lab_knob(0, 1))
+        {
+            if (!getenv("X265B200_CU_LANES_LAB")) G = S == 64 ? 16 : 8;
+            const int gridM = ceil_div((long long)n * G, 128);
+            if (S == 64) cu_satd_mma_kernel<T, 64><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
+            else cu_satd_mma_kernel<T, 32><<<gridM, 128, 0, st>>>(A, sa, B, sb, offF, offR, n, G, out);
+            B200_LAUNCH_CHECK(ctx);
+            return X265B200_OK;
+        }
     }
     const int grid = ceil_div((long long)n * G, 128);
     switch (S)
