@@ -241,15 +241,57 @@ intra_pred_all_kernel(const PIX* __restrict__ neighbours, int N, int lgN, int pm
     __syncthreads();
     const int bFilter = N <= 16, NN = N * N;
     PIX* out = dst + (size_t)tu * 35 * NN;
-    // a thread forms four horizontally adjacent samples of one (mode, row) and stores them as one word pair: the mode's set-up (filter flag,
-    // angle, neighbour array) is shared by the four, and a warp writes 256 (128) contiguous bytes instead of 64 (32)
+    // Main reference array of every angular mode with a non-zero angle, rm[mode - 2][i + N] = ref(i) for i = -N .. 2N: the left / top swap of the
+    // horizontal modes, the smoothed-or-plain choice of the filter flag table and the projection of the side array for negative angles
+    // (intrapred.cpp:150-180) are resolved ONCE per TU and mode here instead of once per predicted sample.
+    __shared__ uint16_t rm[33][3 * 32 + 2];
+    const int RL = 3 * N + 2;
+    for (int e = threadIdx.x; e < 33 * RL; e += blockDim.x)
+    {
+        const int mode = 2 + e / RL, i = e % RL - N;
+        const int hor = mode < 18, angleOffset = hor ? 10 - mode : mode - 26;
+        const uint16_t* src = (c_intraFilterFlags[mode] & N) ? f : s;
+        int v = 0;
+        bool need = c_intraAngle[8 + angleOffset] != 0 && i < 2 * N && (i >= -1 || angleOffset < 0);
+        if (need && i < -1) need = ((128 + (-1 - i) * c_intraInvAngle[-angleOffset - 1]) >> 8) <= 2 * N;     // projections past the side array are never read
+        if (need) v = intra_ref_n(src, N, hor, angleOffset, i);
+        rm[mode - 2][e % RL] = (uint16_t)v;
+    }
+    __syncthreads();
+    // a thread forms four horizontally adjacent samples of one (mode, row) and stores them as one word pair: a warp writes 256 (128) contiguous
+    // bytes instead of 64 (32)
     for (int o4 = threadIdx.x; o4 < 35 * NN / 4; o4 += blockDim.x)
     {
         const int o = o4 << 2, mode = o >> (2 * lgN), rc = o & (NN - 1), r = rc >> lgN, c = rc & (N - 1);
-        const uint16_t* src = mode == 1 ? s : mode == 0 ? (N >= 8 ? f : s) : ((c_intraFilterFlags[mode] & N) ? f : s);
         int v[4];
+        const int hor = mode >= 2 && mode < 18;
+        const int angle = mode < 2 ? 0 : c_intraAngle[8 + (hor ? 10 - mode : mode - 26)];
+        if (angle == 0)
+        {   // planar, DC, pure horizontal / vertical (with their edge filters): the per-sample rule
+            const uint16_t* src = mode == 1 ? s : mode == 0 ? (N >= 8 ? f : s) : ((c_intraFilterFlags[mode] & N) ? f : s);
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = intra_px_n(src, N, lgN, mode, bFilter, dc, r, c + i, pmax);
+            for (int i = 0; i < 4; i++) v[i] = intra_px_n(src, N, lgN, mode, bFilter, dc, r, c + i, pmax);
+        }
+        else
+        {
+            const uint16_t* ref = rm[mode - 2] + N;
+            if (!hor)
+            {   // the row shares offset and fraction: five neighbouring reference samples, four interpolations
+                const int sum = (r + 1) * angle, off = sum >> 5, frac = sum & 31;
+                int a = ref[off + c];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const int b = ref[off + c + i + 1]; v[i] = ((32 - frac) * a + frac * b + 16) >> 5; a = b; }
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    const int sum = (c + i + 1) * angle, off = sum >> 5, frac = sum & 31;
+                    v[i] = ((32 - frac) * ref[off + r] + frac * ref[off + r + 1] + 16) >> 5;
+                }
+            }
+        }
         if (sizeof(PIX) == 2) *(uint2*)(out + o) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
         else *(uint32_t*)(out + o) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
     }
